@@ -1,0 +1,77 @@
+"""ctypes binding of libfmi_b200.so — the C ABI declared in include/fmi_b200.h.
+
+There is no CPU fallback: if the shared library is missing it is built with nvcc, and if that is
+impossible or a kernel fails, the caller gets a RuntimeError carrying fmi_last_error().
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libfmi_b200.so"
+
+F32, BF16, F16 = 0, 1, 2
+MMA_TF32, MMA_BF16 = 0, 1
+
+_vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
+
+# name -> (restype, argtypes); must list every symbol of include/fmi_b200.h
+PROTOTYPES = {
+    "fmi_version": (_i, []),
+    "fmi_last_error": (C.c_char_p, []),
+    "fmi_device_check": (_i, []),
+    "fmi_fused_bias_act": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _f, _i64, _i64, _i64, _i, _i, _vp]),
+    "fmi_bias_act_bwd": (_i, [_vp, _vp, _vp, _vp, _f, _f, _i64, _i64, _i64, _i, _vp]),
+    "fmi_upfirdn2d": (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "fmi_upfirdn2d_out_size": (_i, [_i, _i, _i, _i, _i, _i]),
+    "fmi_scale_mask": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "fmi_composite": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "fmi_composite_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "fmi_attn_workspace_bytes": (_i64, [_i, _i, _i, _i, _i, _i, _i]),
+    "fmi_attn_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _vp, _f, _i, _vp, _i64, _vp, _i64, _vp,
+                          _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i64, _vp]),
+    "fmi_attn_materialize": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "fmi_conv1x1": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "fmi_modconv_workspace_bytes": (_i64, [_i, _i, _i, _i, _i, _i, _i]),
+    "fmi_modconv_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i,
+                             _i, _vp, _i64, _vp]),
+}
+
+_lib = None
+
+
+def header_symbols() -> list[str]:
+    """Function names declared in include/fmi_b200.h (parsed, so tests can diff against PROTOTYPES)."""
+    import re
+    text = (_PKG.parent / "include" / "fmi_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(fmi_[a-z0-9_]+)\s*\(", text)))
+
+
+def load(build_if_missing: bool = True) -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        if not build_if_missing:
+            raise RuntimeError(f"{LIB_PATH} is missing; run `python -m face_mask_inpaint_b200.build`")
+        from . import build as _build
+        _build.build(verbose=bool(os.environ.get("FMI_VERBOSE")))
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError here == header/library mismatch: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().fmi_last_error().decode(errors="replace")
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise RuntimeError(f"{what} failed (code {rc}): {last_error()}")

@@ -1,0 +1,271 @@
+"""Autograd wrappers over the C ABI (include/fmi_b200.h) that mirror the reference's op-level API:
+
+  fused_leaky_relu / FusedLeakyReLU      modules/psp/stylegan2/op/fused_act.py:72-85
+  upfirdn2d                              modules/psp/stylegan2/op/upfirdn2d.py:142-147
+  scale_img / composite                  modules/model.py:10-12, :99 ; psp_encoders.py:135-138
+
+Same names, argument meaning and error behaviour (RuntimeError for non-CUDA tensors, as the reference's
+CHECK_CUDA, fused_bias_act.cpp:7-16). PyTorch is used for device memory and streams only; all arithmetic
+happens in libfmi_b200.so. There is no CPU path.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+from torch.autograd import Function
+
+from . import _lib
+
+_DT = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16, torch.float16: _lib.F16}
+
+
+def _dt(t: torch.Tensor) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise RuntimeError(f"fmi_b200: unsupported dtype {t.dtype} (fp32 / bf16 / fp16 only)") from None
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("fmi_b200: tensor must be a CUDA tensor (there is no CPU fallback)")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+# ------------------------------------------------------------------------------------------------
+# fused bias + activation
+# ------------------------------------------------------------------------------------------------
+def fused_bias_act(input, bias, refer, act, grad, alpha, scale):
+    """Drop-in for the pybind op `fused.fused_bias_act` (op/fused_bias_act.cpp:11-21): empty tensors mean
+    'absent', a fresh output tensor is returned, nothing is mutated."""
+    _need_cuda(input, bias, refer)
+    x = input.contiguous()
+    b = bias.contiguous() if bias is not None and bias.numel() else None
+    r = refer.contiguous() if refer is not None and refer.numel() else None
+    if r is not None and r.dtype != x.dtype:
+        r = r.to(x.dtype)
+    if b is not None and b.dtype != x.dtype and b.dtype != torch.float32:
+        b = b.float()
+    y = torch.empty_like(x)
+    step_b = 1
+    for i in range(2, x.dim()):
+        step_b *= x.size(i)
+    size_b = b.numel() if b is not None else 1
+    lib = _lib.load()
+    _lib.check(lib.fmi_fused_bias_act(_ptr(x), _ptr(b), _ptr(r), _ptr(y), int(act), int(grad), float(alpha),
+                                      float(scale), x.numel(), step_b, size_b, _dt(x),
+                                      _dt(b) if b is not None else _dt(x), _stream()), "fmi_fused_bias_act")
+    return y
+
+
+class FusedLeakyReLUFunctionBackward(Function):
+    """op/fused_act.py:18-47 with the bias-gradient reduction fused into the kernel."""
+
+    @staticmethod
+    def forward(ctx, grad_output, out, negative_slope, scale, bias_numel):
+        ctx.save_for_backward(out)
+        ctx.negative_slope = negative_slope
+        ctx.scale = scale
+        g = grad_output.contiguous()
+        if g.dtype != out.dtype:
+            g = g.to(out.dtype)
+        grad_input = torch.empty_like(g)
+        grad_bias = torch.zeros(bias_numel, dtype=torch.float32, device=g.device)
+        step_b = 1
+        for i in range(2, g.dim()):
+            step_b *= g.size(i)
+        lib = _lib.load()
+        _lib.check(lib.fmi_bias_act_bwd(_ptr(g), _ptr(out), _ptr(grad_input), _ptr(grad_bias), float(negative_slope),
+                                        float(scale), g.numel(), step_b, bias_numel, _dt(g), _stream()),
+                   "fmi_bias_act_bwd")
+        return grad_input, grad_bias
+
+    @staticmethod
+    def backward(ctx, gradgrad_input, gradgrad_bias):
+        out, = ctx.saved_tensors
+        gradgrad_out = fused_bias_act(gradgrad_input, gradgrad_bias.to(gradgrad_input.dtype), out, 3, 1,
+                                      ctx.negative_slope, ctx.scale)
+        return gradgrad_out, None, None, None, None
+
+
+class FusedLeakyReLUFunction(Function):
+    """op/fused_act.py:50-69."""
+
+    @staticmethod
+    def forward(ctx, input, bias, negative_slope, scale):
+        out = fused_bias_act(input, bias, None, 3, 0, negative_slope, scale)
+        ctx.save_for_backward(out)
+        ctx.negative_slope = negative_slope
+        ctx.scale = scale
+        ctx.bias_numel = bias.numel()
+        ctx.bias_dtype = bias.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        out, = ctx.saved_tensors
+        grad_input, grad_bias = FusedLeakyReLUFunctionBackward.apply(grad_output, out, ctx.negative_slope, ctx.scale,
+                                                                     ctx.bias_numel)
+        return grad_input, grad_bias.to(ctx.bias_dtype), None, None
+
+
+def fused_leaky_relu(input, bias, negative_slope=0.2, scale=2 ** 0.5):
+    """op/fused_act.py:84-85."""
+    return FusedLeakyReLUFunction.apply(input, bias, negative_slope, scale)
+
+
+class FusedLeakyReLU(nn.Module):
+    """op/fused_act.py:72-81 — same parameter name (`bias`) and shape."""
+
+    def __init__(self, channel, negative_slope=0.2, scale=2 ** 0.5):
+        super().__init__()
+        self.bias = nn.Parameter(torch.zeros(channel))
+        self.negative_slope = negative_slope
+        self.scale = scale
+
+    def forward(self, input):
+        return fused_leaky_relu(input, self.bias, self.negative_slope, self.scale)
+
+
+# ------------------------------------------------------------------------------------------------
+# upfirdn2d
+# ------------------------------------------------------------------------------------------------
+def upfirdn2d_op(input, kernel, up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1):
+    """Drop-in for the pybind op `upfirdn2d_op.upfirdn2d` (op/upfirdn2d.cpp:12-23): input is
+    [major, in_h, in_w, minor]; returns [major, out_h, out_w, minor]."""
+    _need_cuda(input, kernel)
+    x = input.contiguous()
+    k = kernel.contiguous().float()
+    major, in_h, in_w, minor = x.shape
+    kh, kw = k.shape
+    lib = _lib.load()
+    out_h = lib.fmi_upfirdn2d_out_size(in_h, up_y, down_y, pad_y0, pad_y1, kh)
+    out_w = lib.fmi_upfirdn2d_out_size(in_w, up_x, down_x, pad_x0, pad_x1, kw)
+    if out_h < 1 or out_w < 1:
+        raise RuntimeError(f"upfirdn2d: empty output extent ({out_h} x {out_w})")
+    y = torch.empty((major, out_h, out_w, minor), dtype=x.dtype, device=x.device)
+    _lib.check(lib.fmi_upfirdn2d(_ptr(x), _ptr(k), _ptr(y), major, in_h, in_w, minor, kh, kw, up_x, up_y, down_x,
+                                 down_y, pad_x0, pad_x1, pad_y0, pad_y1, _dt(x), _stream()), "fmi_upfirdn2d")
+    return y
+
+
+class UpFirDn2dBackward(Function):
+    """op/upfirdn2d.py:17-82."""
+
+    @staticmethod
+    def forward(ctx, grad_output, kernel, grad_kernel, up, down, pad, g_pad, in_size, out_size):
+        up_x, up_y = up
+        down_x, down_y = down
+        g_pad_x0, g_pad_x1, g_pad_y0, g_pad_y1 = g_pad
+        grad_output = grad_output.reshape(-1, out_size[0], out_size[1], 1)
+        grad_input = upfirdn2d_op(grad_output, grad_kernel, down_x, down_y, up_x, up_y, g_pad_x0, g_pad_x1, g_pad_y0,
+                                  g_pad_y1)
+        grad_input = grad_input.view(in_size[0], in_size[1], in_size[2], in_size[3])
+        ctx.save_for_backward(kernel)
+        ctx.up, ctx.down, ctx.pad = up, down, pad
+        ctx.in_size, ctx.out_size = in_size, out_size
+        return grad_input
+
+    @staticmethod
+    def backward(ctx, gradgrad_input):
+        kernel, = ctx.saved_tensors
+        gradgrad_input = gradgrad_input.reshape(-1, ctx.in_size[2], ctx.in_size[3], 1)
+        gradgrad_out = upfirdn2d_op(gradgrad_input, kernel, ctx.up[0], ctx.up[1], ctx.down[0], ctx.down[1], *ctx.pad)
+        gradgrad_out = gradgrad_out.view(ctx.in_size[0], ctx.in_size[1], ctx.out_size[0], ctx.out_size[1])
+        return gradgrad_out, None, None, None, None, None, None, None, None
+
+
+class UpFirDn2d(Function):
+    """op/upfirdn2d.py:85-139."""
+
+    @staticmethod
+    def forward(ctx, input, kernel, up, down, pad):
+        up_x, up_y = up
+        down_x, down_y = down
+        pad_x0, pad_x1, pad_y0, pad_y1 = pad
+        kernel_h, kernel_w = kernel.shape
+        batch, channel, in_h, in_w = input.shape
+        ctx.in_size = input.shape
+        input = input.reshape(-1, in_h, in_w, 1)
+        ctx.save_for_backward(kernel, torch.flip(kernel, [0, 1]))
+        out_h = (in_h * up_y + pad_y0 + pad_y1 - kernel_h) // down_y + 1
+        out_w = (in_w * up_x + pad_x0 + pad_x1 - kernel_w) // down_x + 1
+        ctx.out_size = (out_h, out_w)
+        ctx.up, ctx.down, ctx.pad = (up_x, up_y), (down_x, down_y), (pad_x0, pad_x1, pad_y0, pad_y1)
+        g_pad_x0 = kernel_w - pad_x0 - 1
+        g_pad_y0 = kernel_h - pad_y0 - 1
+        g_pad_x1 = in_w * up_x - out_w * down_x + pad_x0 - up_x + 1
+        g_pad_y1 = in_h * up_y - out_h * down_y + pad_y0 - up_y + 1
+        ctx.g_pad = (g_pad_x0, g_pad_x1, g_pad_y0, g_pad_y1)
+        out = upfirdn2d_op(input, kernel, up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1)
+        return out.view(-1, channel, out_h, out_w)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        kernel, grad_kernel = ctx.saved_tensors
+        grad_input = UpFirDn2dBackward.apply(grad_output, kernel, grad_kernel, ctx.up, ctx.down, ctx.pad, ctx.g_pad,
+                                             ctx.in_size, ctx.out_size)
+        return grad_input, None, None, None, None
+
+
+def upfirdn2d(input, kernel, up=1, down=1, pad=(0, 0)):
+    """op/upfirdn2d.py:142-147."""
+    return UpFirDn2d.apply(input, kernel, (up, up), (down, down), (pad[0], pad[1], pad[0], pad[1]))
+
+
+# ------------------------------------------------------------------------------------------------
+# compositing
+# ------------------------------------------------------------------------------------------------
+def scale_img(img, size):
+    """modules/model.py:10-12 for a single-channel mask [N,1,Hm,Wm] (bilinear, align_corners=True)."""
+    _need_cuda(img)
+    if img.dim() != 4 or img.size(1) != 1:
+        raise RuntimeError("fmi_b200.scale_img: expects a [N,1,H,W] mask")
+    m = img.contiguous().float()
+    n, _, hm, wm = m.shape
+    h, w = int(size[0]), int(size[1])
+    out = torch.empty((n, 1, h, w), dtype=torch.float32, device=m.device)
+    _lib.check(_lib.load().fmi_scale_mask(_ptr(m), _ptr(out), n, hm, wm, h, w, _stream()), "fmi_scale_mask")
+    return out.to(img.dtype)
+
+
+class _Composite(Function):
+    @staticmethod
+    def forward(ctx, src, ref, mask_full):
+        _need_cuda(src, ref, mask_full)
+        s = src.contiguous()
+        r = ref.contiguous().to(s.dtype)
+        m = mask_full.contiguous().float()
+        if m.dim() == 3:
+            m = m.unsqueeze(1)
+        n, c, h, w = s.shape
+        out = torch.empty_like(s)
+        _lib.check(_lib.load().fmi_composite(_ptr(s), _ptr(r), _ptr(m), _ptr(out), n, c, h, w, m.size(-2), m.size(-1),
+                                             _dt(s), _stream()), "fmi_composite")
+        ctx.save_for_backward(m)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        m, = ctx.saved_tensors
+        g = grad_out.contiguous()
+        n, c, h, w = g.shape
+        gs = torch.empty_like(g) if ctx.needs_input_grad[0] else None
+        gr = torch.empty_like(g) if ctx.needs_input_grad[1] else None
+        _lib.check(_lib.load().fmi_composite_bwd(_ptr(g), _ptr(m), _ptr(gs), _ptr(gr), n, c, h, w, m.size(-2),
+                                                 m.size(-1), _dt(g), _stream()), "fmi_composite_bwd")
+        return gs, gr, None
+
+
+def composite(src, ref, mask_full):
+    """(1 - m) * src + m * ref with m = scale_img(mask_full, src.shape[-2:]) fused in one pass
+    (modules/model.py:98-99; psp_encoders.py:127-138). mask_full is the [N,1,Hm,Wm] (or [N,Hm,Wm]) mask."""
+    return _Composite.apply(src, ref, mask_full)

@@ -1,0 +1,163 @@
+/*
+ * fmi_b200.h — C ABI of the B200-native (sm_100a) generator hot path of
+ * syncdoth/face_mask_inpaint.
+ *
+ * Every entry point takes raw DEVICE pointers, plain sizes and a CUDA stream
+ * (cudaStream_t passed as void*), launches asynchronously on that stream, never
+ * synchronises the host, never allocates unless stated, and returns 0 on success
+ * or a negative FMI_E* code (message via fmi_last_error(), thread-local).
+ * No torch types cross this boundary.
+ *
+ * The reference interfaces each entry point replaces are cited as
+ * file:line relative to the reference repository root.
+ */
+#ifndef FMI_B200_H_
+#define FMI_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* element types of activation buffers */
+#define FMI_F32 0
+#define FMI_BF16 1
+#define FMI_F16 2
+
+/* tensor-core operand precision of the contraction kernels */
+#define FMI_MMA_TF32 0 /* fp32 I/O contract: max rel err <= 1e-3 */
+#define FMI_MMA_BF16 1 /* bf16 contract:     max rel err <= 2e-2 */
+
+/* error codes */
+#define FMI_OK 0
+#define FMI_EINVAL (-1)   /* bad argument / unsupported configuration (never silent garbage) */
+#define FMI_ECUDA (-2)    /* CUDA runtime / driver error                                  */
+#define FMI_EARCH (-3)    /* device is not sm_100                                          */
+#define FMI_ENOMEM (-4)   /* caller-provided workspace too small                           */
+
+int fmi_version(void);
+const char* fmi_last_error(void);
+/* 0 when the current CUDA device can run these kernels (compute capability 10.x). */
+int fmi_device_check(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * a5  fused bias + activation.
+ * Replaces pybind `fused.fused_bias_act(input, bias, refer, act, grad, alpha, scale)`
+ *   (modules/psp/stylegan2/op/fused_bias_act.cpp:11-21, kernel fused_bias_act_kernel.cu:18-49).
+ *   y[i] = act'(x[i] + b[(i / step_b) % size_b]) * scale,  act*10+grad in {10,11,12,30,31,32};
+ *   b == NULL / ref == NULL mean "absent" (the reference's numel()==0 convention, :62-63).
+ * x, ref, y have element type `dtype`; b has element type `bias_dtype` (fp32 parameters with
+ * bf16 activations are allowed — new capability, the reference requires equal types).
+ * ------------------------------------------------------------------------------------------- */
+int fmi_fused_bias_act(const void* x, const void* b, const void* ref, void* y, int act, int grad,
+                       float alpha, float scale, int64_t size_x, int64_t step_b, int64_t size_b,
+                       int dtype, int bias_dtype, void* stream);
+
+/* Fused backward of fused_leaky_relu: FusedLeakyReLUFunctionBackward.forward
+ *   (modules/psp/stylegan2/op/fused_act.py:18-38):
+ *   grad_in = grad_out * (out > 0 ? 1 : alpha) * scale ; grad_bias[c] = sum_{n,inner} grad_in.
+ * grad_bias is fp32 [size_b] and is ACCUMULATED into (caller zeroes it); may be NULL.
+ * Layout [outer, size_b, step_b] contiguous. */
+int fmi_bias_act_bwd(const void* grad_out, const void* out, void* grad_in, float* grad_bias,
+                     float alpha, float scale, int64_t size_x, int64_t step_b, int64_t size_b,
+                     int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a4  upfirdn2d.
+ * Replaces pybind `upfirdn2d.upfirdn2d(input[major,in_h,in_w,minor], kernel[kh,kw], up_x, up_y,
+ *   down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1)` (modules/psp/stylegan2/op/upfirdn2d.cpp:12-23,
+ *   upfirdn2d_kernel.cu:140-272). Output [major,out_h,out_w,minor] with
+ *   out = (in*up + pad0 + pad1 - k + down) / down  (upfirdn2d_kernel.cu:167-168).
+ * Taps are applied flipped (true convolution, upfirdn2d_kernel.cu:77). kernel is fp32 on device.
+ * EVERY (up, down, pad, kernel<=32x32) configuration is computed (the reference silently
+ * returns uninitialised memory outside its six template modes).
+ * ------------------------------------------------------------------------------------------- */
+int fmi_upfirdn2d(const void* x, const float* kernel, void* y, int64_t major, int in_h, int in_w,
+                  int minor, int kh, int kw, int up_x, int up_y, int down_x, int down_y,
+                  int pad_x0, int pad_x1, int pad_y0, int pad_y1, int dtype, void* stream);
+/* output extent helper (same formula), returns <0 when the extent would be empty */
+int fmi_upfirdn2d_out_size(int in, int up, int down, int pad0, int pad1, int k);
+
+/* ---------------------------------------------------------------------------------------------
+ * a7  masked source/reference compositing.
+ * scale_img: F.interpolate(mask, size, mode='bilinear', align_corners=True) (modules/model.py:10-12)
+ * blend:     out = (1-m)*src + m*ref  (modules/model.py:99; psp_encoders.py:135-138)
+ * mask is fp32 [N,1,Hm,Wm] at FULL resolution; it is sampled in-register at (H,W).
+ * src/ref/out are [N,C,H,W] of `dtype`. Products are rounded separately (no FMA contraction) so
+ * the fp32 result is bit-identical to the reference's separate mul/add kernels given equal m.
+ * ------------------------------------------------------------------------------------------- */
+int fmi_scale_mask(const float* mask, float* out, int N, int Hm, int Wm, int H, int W, void* stream);
+int fmi_composite(const void* src, const void* ref, const float* mask, void* out, int N, int C,
+                  int H, int W, int Hm, int Wm, int dtype, void* stream);
+/* backward: g_src = (1-m)*g, g_ref = m*g (either may be NULL) */
+int fmi_composite_bwd(const void* grad_out, const float* mask, void* grad_src, void* grad_ref, int N,
+                      int C, int H, int W, int Hm, int Wm, int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a1/a2  reference-guided attention (ExampleGuidedAttention.forward,
+ *   modules/example_guided_att.py:21-41) and PICNet Auto_Attn.forward
+ *   (modules/pluralistic_model/base_function.py:420-448), as ONE flash-style kernel family:
+ *     q  = Wq x (+ bq)                      1x1 conv C -> d      (example_guided_att.py:27, base_function.py:429)
+ *     P  = softmax_j(q_i . q_j)             no 1/sqrt(d) scale   (example_guided_att.py:30, base_function.py:432-433)
+ *     O_g = v_g P^T   for value groups g    (example_guided_att.py:18, base_function.py:436,443)
+ *     out_g[c,i] = a_g*w_i*O_g[c,i] + r_i*v_g[c,i]
+ *        plain  group: w_i = 1,      r_i = b_g           (Auto_Attn: a=gamma, b=1; EGA src: a=1, b=0)
+ *        masked group: w_i = 1-m_i,  r_i = m_i           (EGA ref: a=1; Auto_Attn pre: a=alpha)
+ *   The S x S map never leaves the SM (TMEM/registers).
+ *
+ * fmi_attn_workspace_bytes: bytes of scratch the caller must provide (operand staging in the
+ *   tensor-core layout: q^T [N,S,dpad] and the concatenated values [N,Cv,S] in bf16 / tf32).
+ * fmi_attn_fwd arguments:
+ *   x       [N,C,S]  query source features (fp32 or bf16 = dtype)
+ *   wq      [d,C] fp32, bq [d] fp32 or NULL
+ *   v0,v1   value groups [N,C0,S], [N,C1,S] (v1 may be NULL, C1 = 0); v0 may alias x
+ *   mask    [N,S] fp32 (already at feature resolution) or NULL when no group is masked
+ *   a0,a1   device pointers to fp32 scalars (NULL = 1.0); b0,b1 host floats
+ *   masked0/masked1  0/1
+ *   out0,out1  [N,C0,S], [N,C1,S] with batch strides out0_bs/out1_bs ELEMENTS (so both can live in
+ *              one [N,C0+C1,S] concatenated tensor); element type = dtype
+ *   lse     [N,S] fp32 row log-sum-exp (natural log) or NULL — saved for backward
+ *   mma     FMI_MMA_TF32 | FMI_MMA_BF16
+ * ------------------------------------------------------------------------------------------- */
+int64_t fmi_attn_workspace_bytes(int N, int C, int d, int C0, int C1, int S, int mma);
+int fmi_attn_fwd(const void* x, const float* wq, const float* bq, const void* v0, const void* v1,
+                 const float* mask, const float* a0, float b0, int masked0, const float* a1, float b1,
+                 int masked1, void* out0, int64_t out0_bs, void* out1, int64_t out1_bs, float* lse,
+                 int N, int C, int d, int C0, int C1, int S, int dtype, int mma, void* workspace,
+                 int64_t workspace_bytes, void* stream);
+
+/* Opt-in materialisation of the S x S map that Auto_Attn returns (base_function.py:448):
+ *   attn[n,i,j] = exp(q_i.q_j - lse_i). q^T is taken from the workspace of the matching
+ *   fmi_attn_fwd call. attn is fp32 [N,S,S]. */
+int fmi_attn_materialize(const void* workspace, const float* lse, float* attn, int N, int d, int S,
+                         int mma, void* stream);
+
+/* 1x1 convolution  y[n,o,s] = sum_c W[o,c] x[n,c,s] + b[o]  in fp32 SIMT (query conv,
+ *   example_guided_att.py:9,27; out_conv, example_guided_att.py:13,38-39). */
+int fmi_conv1x1(const void* x, const float* w, const float* b, void* y, int N, int Cin, int Cout,
+                int S, int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a3/a6  modulated convolution as a shared-weight implicit GEMM
+ *   (ModulatedConv2d.forward, modules/psp/stylegan2/model.py:241-279; StyledConv.forward :340-346;
+ *    ToRGB.forward :360-369; NoiseInjection :289-294).
+ *   y[b,o,p] = epi( demod[b,o] * sum_{i,t} (scale*W[o,i,t]) * (s[b,i] * x[b,i,p+t]) )
+ *   demod[b,o] = rsqrt( sum_i s[b,i]^2 * sum_t (scale*W[o,i,t])^2 + 1e-8 )        (:247-249)
+ *   epi (StyledConv) = sqrt2 * lrelu_0.2( . + noise_w*noise[b|1,p] + act_bias[o] ) (:341-344)
+ *   epi (ToRGB)      = . + bias[o] + skip[b,o,p]                                  (:361-367)
+ *   upsample=1: conv_transpose2d(stride 2) -> (2H+1)^2 then the 4x4 blur pad(1,1) -> (2H)^2
+ *     (:255-263), computed as a second streaming pass fused with the epilogue.
+ * See DESIGN.md for the staged layouts. Declared here; documented fully with the kernel.
+ * ------------------------------------------------------------------------------------------- */
+int64_t fmi_modconv_workspace_bytes(int B, int I, int O, int H, int W, int ksize, int upsample);
+int fmi_modconv_fwd(const void* x, const float* weight, const float* style_s, const float* noise,
+                    int noise_batched, const float* noise_w, const float* bias, const void* skip,
+                    const float* blur_k, void* y, int B, int I, int O, int H, int W, int ksize,
+                    int upsample, int demodulate, int act, int dtype, void* workspace,
+                    int64_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FMI_B200_H_ */
