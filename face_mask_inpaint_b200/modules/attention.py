@@ -1,0 +1,122 @@
+"""Drop-in ExampleGuidedAttention (modules/example_guided_att.py:5-41) and Auto_Attn
+(modules/pluralistic_model/base_function.py:401-448) on the fused sm_100a attention kernel.
+
+Parameter names/shapes are the reference's: `conv.weight [C/4,C,1,1]`, `out_conv.{weight,bias}`;
+`query_conv.{weight,bias}`, `gamma`, `alpha`, `model.*`.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+from torch import nn
+
+from .. import ops
+
+
+class ExampleGuidedAttention(nn.Module):
+    """modules/example_guided_att.py:5-41."""
+
+    def __init__(self, in_channels, out_channels=None):
+        super().__init__()
+        self.conv = nn.Conv2d(in_channels, in_channels // 4, 1, bias=False)  # parameter holder (:9)
+        self.out_channels = out_channels
+        if out_channels is not None:
+            self.out_conv = nn.Conv2d(in_channels * 2, out_channels, 1)      # parameter holder (:13)
+
+    def forward(self, src_mask, src_feature, ref_feature):
+        """src_mask [N,1,H,W] (already at feature resolution), src/ref features [N,C,H,W] ->
+        [N, 2C or out_channels, H, W]: cat[(1-m)*ref_att + m*ref, src_att] (:34-36) (+ out_conv :38-39)."""
+        out = _EGAFunction.apply(src_mask, src_feature, ref_feature, self.conv.weight)
+        if self.out_channels is not None:
+            out = _Conv1x1Function.apply(out, self.out_conv.weight, self.out_conv.bias)
+        return out
+
+
+class _EGAFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, src_mask, src_feature, ref_feature, wq):
+        out, lse, _ = ops.attention_forward(src_feature, wq, None, src_feature, ref_feature, mask=src_mask,
+                                            b0=0.0, masked0=False, masked1=True, order=(1, 0),
+                                            need_lse=ctx.needs_input_grad[1] or ctx.needs_input_grad[2] or
+                                            ctx.needs_input_grad[3])
+        ctx.save_for_backward(src_mask, src_feature, ref_feature, wq, out, lse)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        raise NotImplementedError("fmi_b200: ExampleGuidedAttention backward kernel is not implemented yet "
+                                  "(no PyTorch/CPU fallback by design)")
+
+
+class _Conv1x1Function(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        return ops.conv1x1(x, weight, bias)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        raise NotImplementedError("fmi_b200: conv1x1 backward kernel is not implemented yet")
+
+
+class _AutoAttnFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, wq, bq, gamma, pre, mask, alpha):
+        need_lse = any(ctx.needs_input_grad) or _materialize()
+        if pre is None:
+            out, lse, ws = ops.attention_forward(x, wq, bq, x, None, a0=gamma, b0=1.0, need_lse=need_lse)
+        else:
+            out, lse, ws = ops.attention_forward(x, wq, bq, x, pre, mask=mask, a0=gamma, b0=1.0, a1=alpha,
+                                                 masked1=True, order=(0, 1), need_lse=need_lse)
+        attn = None
+        if _materialize():
+            n, s = x.shape[0], x[0, 0].numel()
+            attn = ops.attention_map(ws, lse, n, wq.shape[0], s, ops.mma_mode(x.dtype))
+            ctx.mark_non_differentiable(attn)
+        ctx.save_for_backward(x, wq, bq, gamma, pre, mask, alpha, out, lse)
+        return out, attn
+
+    @staticmethod
+    def backward(ctx, grad_out, grad_attn):
+        raise NotImplementedError("fmi_b200: Auto_Attn backward kernel is not implemented yet "
+                                  "(no PyTorch/CPU fallback by design)")
+
+
+def _materialize() -> bool:
+    return os.environ.get("FMI_MATERIALIZE_ATTN", "0") == "1"
+
+
+class Auto_Attn(nn.Module):
+    """modules/pluralistic_model/base_function.py:401-448 (Short+Long attention layer).
+
+    `forward` returns `(out, attention)` like the reference; the S x S `attention` map (1 GiB fp32 per image at
+    128^2, discarded by both callers: network.py:268,365) is `None` unless FMI_MATERIALIZE_ATTN=1.
+    `resblock` builds the `model` sub-block used by the `pre` branch (:413-418, :446); when the package is
+    installed over the reference (patch.py) it is the reference's own ResBlock (out-of-scope conv block)."""
+
+    resblock_factory = None  # set by patch.install(); signature (in_nc, out_nc, hidden_nc, norm_layer) -> nn.Module
+
+    def __init__(self, input_nc, norm_layer=nn.BatchNorm2d):
+        super().__init__()
+        self.input_nc = input_nc
+        self.query_conv = nn.Conv2d(input_nc, input_nc // 4, kernel_size=1)  # parameter holder (:408)
+        self.gamma = nn.Parameter(torch.zeros(1))
+        self.alpha = nn.Parameter(torch.zeros(1))
+        self.softmax = nn.Softmax(dim=-1)  # kept for attribute parity; unused
+        factory = type(self).resblock_factory
+        if factory is None:
+            from .picnet_blocks import ResBlock
+            factory = lambda i, o, h, nl: ResBlock(i, o, h, norm_layer=nl, use_spect=True)  # noqa: E731
+        self.model = factory(int(input_nc * 2), input_nc, input_nc, norm_layer)
+
+    def forward(self, x, pre=None, mask=None):
+        if pre is None:
+            out, attention = _AutoAttnFunction.apply(x, self.query_conv.weight, self.query_conv.bias, self.gamma,
+                                                     None, None, None)
+            return out, attention
+        m = mask.expand(x.shape[0], 1, *x.shape[2:]) if mask.dim() == 4 else mask
+        cat, attention = _AutoAttnFunction.apply(x, self.query_conv.weight, self.query_conv.bias, self.gamma, pre, m,
+                                                 self.alpha)
+        out = self.model(cat)  # ResBlock(cat[out, context_flow]) (:446)
+        return out, attention

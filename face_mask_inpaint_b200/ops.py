@@ -269,3 +269,96 @@ def composite(src, ref, mask_full):
     """(1 - m) * src + m * ref with m = scale_img(mask_full, src.shape[-2:]) fused in one pass
     (modules/model.py:98-99; psp_encoders.py:127-138). mask_full is the [N,1,Hm,Wm] (or [N,Hm,Wm]) mask."""
     return _Composite.apply(src, ref, mask_full)
+
+
+# ------------------------------------------------------------------------------------------------
+# attention (a1 ExampleGuidedAttention, a2 Auto_Attn) and the 1x1 convolutions around it
+# ------------------------------------------------------------------------------------------------
+import os
+
+_WS = {}
+
+
+def _workspace(device, nbytes: int) -> torch.Tensor:
+    """Grow-only per-device scratch (operand staging for the tensor-core kernels); stream-ordered reuse."""
+    key = (device.type, device.index, torch.cuda.current_stream().cuda_stream)
+    buf = _WS.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _WS[key] = buf
+    return buf
+
+
+def mma_mode(dtype: torch.dtype) -> int:
+    """Tensor-core operand precision: TF32 for the fp32 contract (<=1e-3), bf16 for the bf16 contract (<=2e-2).
+    FMI_PRECISION=bf16 forces bf16 operands for fp32 I/O (SURVEY.md §5 'Config / flags')."""
+    env = os.environ.get("FMI_PRECISION", "").lower()
+    if env == "bf16":
+        return _lib.MMA_BF16
+    if env in ("fp32", "tf32"):
+        return _lib.MMA_TF32
+    return _lib.MMA_TF32 if dtype == torch.float32 else _lib.MMA_BF16
+
+
+def conv1x1(x, weight, bias=None):
+    """1x1 nn.Conv2d forward (example_guided_att.py:9,13) on [N,C,H,W] through fmi_conv1x1."""
+    _need_cuda(x, weight, bias)
+    xc = x.contiguous()
+    n, cin = xc.shape[0], xc.shape[1]
+    cout = weight.shape[0]
+    s = xc[0, 0].numel()
+    w = weight.reshape(cout, cin).contiguous().float()
+    b = bias.contiguous().float() if bias is not None else None
+    y = torch.empty((n, cout) + tuple(xc.shape[2:]), dtype=xc.dtype, device=xc.device)
+    _lib.check(_lib.load().fmi_conv1x1(_ptr(xc), _ptr(w), _ptr(b), _ptr(y), n, cin, cout, s, _dt(xc), _stream()),
+               "fmi_conv1x1")
+    return y
+
+
+def attention_forward(x, wq, bq, v0, v1=None, mask=None, a0=None, b0=0.0, masked0=False, a1=None, b1=0.0,
+                      masked1=False, order=(0, 1), need_lse=False, mma=None):
+    """One fused pass of fmi_attn_fwd. x [N,C,H,W]; v0/v1 value groups [N,C0|C1,H,W]; mask [N,1,H,W] or None.
+    Returns (out [N, C0+C1, H, W] with the groups concatenated in `order`, lse [N,S] or None, workspace)."""
+    _need_cuda(x, wq, bq, v0, v1, mask, a0, a1)
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        raise RuntimeError("fmi_b200 attention: fp32 or bf16 activations only")
+    xc = x.contiguous()
+    v0c = xc if v0 is x else v0.contiguous().to(xc.dtype)
+    v1c = v1.contiguous().to(xc.dtype) if v1 is not None else None
+    n, c = xc.shape[0], xc.shape[1]
+    spatial = tuple(xc.shape[2:])
+    s = xc[0, 0].numel()
+    d = wq.shape[0]
+    c0 = v0c.shape[1]
+    c1 = v1c.shape[1] if v1c is not None else 0
+    w = wq.reshape(d, c).contiguous().float()
+    b = bq.contiguous().float() if bq is not None else None
+    m = mask.reshape(n, s).contiguous().float() if mask is not None else None
+    if mma is None:
+        mma = mma_mode(xc.dtype)
+    lib = _lib.load()
+    ws_bytes = lib.fmi_attn_workspace_bytes(n, c, d, c0, c1, s, mma)
+    if ws_bytes < 0:
+        raise RuntimeError(f"fmi_attn_workspace_bytes: {_lib.last_error()}")
+    ws = _workspace(xc.device, ws_bytes)
+    out = torch.empty((n, c0 + c1) + spatial, dtype=xc.dtype, device=xc.device)
+    esz = out.element_size()
+    bs = (c0 + c1) * s
+    off0 = 0 if order[0] == 0 else c1 * s
+    off1 = c0 * s if order[0] == 0 else 0
+    lse = torch.empty((n, s), dtype=torch.float32, device=xc.device) if need_lse else None
+    a0c = a0.reshape(1).float().contiguous() if a0 is not None else None
+    a1c = a1.reshape(1).float().contiguous() if a1 is not None else None
+    _lib.check(lib.fmi_attn_fwd(_ptr(xc), _ptr(w), _ptr(b), _ptr(v0c), _ptr(v1c), _ptr(m), _ptr(a0c), float(b0),
+                                int(masked0), _ptr(a1c), float(b1), int(masked1), out.data_ptr() + off0 * esz, bs,
+                                (out.data_ptr() + off1 * esz) if c1 else None, bs, _ptr(lse), n, c, d, c0, c1, s,
+                                _dt(xc), mma, ws.data_ptr(), ws.numel(), _stream()), "fmi_attn_fwd")
+    return out, lse, ws
+
+
+def attention_map(ws, lse, n, d, s, mma):
+    """Opt-in S x S map (what Auto_Attn returns, base_function.py:448) from the staged q and the row lse."""
+    attn = torch.empty((n, s, s), dtype=torch.float32, device=lse.device)
+    _lib.check(_lib.load().fmi_attn_materialize(ws.data_ptr(), _ptr(lse), _ptr(attn), n, d, s, mma, _stream()),
+               "fmi_attn_materialize")
+    return attn
