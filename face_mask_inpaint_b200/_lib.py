@@ -34,9 +34,15 @@ PROTOTYPES = {
                           _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i64, _vp]),
     "fmi_attn_materialize": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "fmi_conv1x1": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
-    "fmi_modconv_workspace_bytes": (_i64, [_i, _i, _i, _i, _i, _i, _i]),
-    "fmi_modconv_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i,
-                             _i, _vp, _i64, _vp]),
+    "fmi_nchw_to_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "fmi_nhwc_to_nchw": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "fmi_style_modulation": (_i, [_vp, _i64, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "fmi_modconv_weight_bytes": (_i64, [_i, _i, _i, _i, _i]),
+    "fmi_modconv_weight_prep": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "fmi_styled_conv_workspace_bytes": (_i64, [_i, _i, _i, _i, _i, _i]),
+    "fmi_styled_conv_nhwc": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i64,
+                                  _vp]),
+    "fmi_torgb_nhwc": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
 }
 
 _lib = None

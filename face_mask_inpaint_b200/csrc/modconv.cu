@@ -1,0 +1,622 @@
+// a3/a6: StyleGAN2 modulated convolution (ModulatedConv2d.forward, modules/psp/stylegan2/model.py:241-279) with the
+// StyledConv / NoiseInjection / FusedLeakyReLU / ToRGB glue (:289-294, :340-346, :360-369) fused around it.
+//
+// Reformulation. The reference builds per-sample weights w[b] = scale*W*s[b] (*demod[b]) and runs a grouped conv
+// (groups = batch) through cuDNN. Here the same per-sample weights are staged once per layer in the tensor-core
+// operand type, tap-major and K-major ([b][tap][o][i], i contiguous), and the convolution is an implicit GEMM on
+// tcgen05:  D[pixel, o] = sum_{tap, i} X[b, pixel + tap, i] * Wp[b][tap][o][i]
+//   A operand: activations kept in NHWC between layers (channels contiguous = K-major); the im2col gather is a 4-D TMA
+//              box {64 ch, TW, TH, 1} at the tap-shifted coordinate — out-of-bounds rows are zero-filled by TMA, which
+//              is exactly the conv zero padding. One box = 128 rows x 128 bytes, SWIZZLE_128B.
+//   B operand: Wp tile {64 ch, N_tile} by 2-D TMA.   Accumulator: 128 x N_tile fp32 in TMEM.
+//   Epilogue (StyledConv): sqrt2 * lrelu_0.2(acc + noise_w * noise[b|0, p] + act_bias[o])  -> NHWC store.
+// upsample=True (:255-263): conv_transpose2d(stride 2) is split into its 4 output-parity classes (1, 2, 2 and 4 taps:
+//   9/4 taps per output pixel, the same FLOPs as the reference), each an implicit GEMM writing the (2H+1)^2 NHWC
+//   intermediate; a second streaming kernel applies the 4x4 blur (pad 1,1) fused with noise + bias + leaky-ReLU.
+// ToRGB (:360-369): 1x1 modulated conv to 3 channels without demodulation — HBM-bound, so a warp-shuffle SIMT kernel
+//   that also fuses `+ bias` and `+ upfirdn2d(skip, up=2)` (Upsample, :30-49).
+#include "common.cuh"
+#include "sm100.cuh"
+
+using namespace sm100;
+
+namespace {
+
+constexpr int kGemmThreads = 192;
+constexpr int kMaxTaps = 9;
+constexpr int A_STAGE_BYTES = 128 * 128;
+
+struct ConvGemmParams {
+  int B, I, O, H, W;   // input NHWC
+  int OH, OW;          // output NHWC extents
+  int Mh, Mw;          // iteration domain of this launch (per image)
+  int TH, TW, tiles_w; // pixel tile (TH*TW <= 128)
+  int ntaps, tap_dy[kMaxTaps], tap_dx[kMaxTaps], tap_slab[kMaxTaps];
+  int T;               // weight slabs per sample
+  int sy, sx, py, px;  // output pixel = (m*sy + py, n*sx + px)
+  int n_tile, k_chunks, stages;
+  int act;             // 0: raw accumulator, 1: noise + bias + leaky relu
+  const float* noise;
+  int noise_batched;
+  const float* noise_w;
+  const float* bias;
+  float slope, gain;
+  void* out;
+};
+
+template <bool TF32>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+    modconv_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                        const ConvGemmParams p) {
+  constexpr int EPA = TF32 ? 32 : 64;
+  using OT = typename std::conditional<TF32, float, __nv_bfloat16>::type;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int b_stage_bytes = p.n_tile * 128;
+  const int stage_bytes = A_STAGE_BYTES + b_stage_bytes;
+  __shared__ uint64_t full[8], empty[8], acc_full;
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tile = blockIdx.x, o0 = blockIdx.y * p.n_tile, b = blockIdx.z;
+  const int m0 = (tile / p.tiles_w) * p.TH, n0 = (tile % p.tiles_w) * p.TW;
+  const int iters = p.ntaps * p.k_chunks;
+
+  if (tid == 0) {
+    for (int i = 0; i < 8; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(&acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_base_s, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      tma_prefetch_desc(&map_x);
+      tma_prefetch_desc(&map_w);
+      const uint32_t bytes = (uint32_t)(p.TH * p.TW * 128 + b_stage_bytes);
+      for (int it = 0; it < iters; ++it) {
+        const int st = it % p.stages;
+        const int tap = it / p.k_chunks, kc = it % p.k_chunks;
+        mbar_wait(&empty[st], ((it / p.stages) & 1) ^ 1);
+        mbar_arrive_expect_tx(&full[st], bytes);
+        uint8_t* sA = smem + st * stage_bytes;
+        tma_load_4d(sA, &map_x, &full[st], kc * EPA, n0 + p.tap_dx[tap], m0 + p.tap_dy[tap], b);
+        tma_load_2d(sA + A_STAGE_BYTES, &map_w, &full[st], kc * EPA, (b * p.T + p.tap_slab[tap]) * p.O + o0);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc(TF32 ? KIND_TF32 : KIND_BF16, 128, p.n_tile);
+      for (int it = 0; it < iters; ++it) {
+        const int st = it % p.stages;
+        mbar_wait(&full[st], (it / p.stages) & 1);
+        tc_fence_after();
+        uint8_t* sA = smem + st * stage_bytes;
+        const uint64_t adesc = make_sdesc_k_sw128(smem_u32(sA));
+        const uint64_t bdesc = make_sdesc_k_sw128(smem_u32(sA + A_STAGE_BYTES));
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+          const uint32_t acc = (it > 0 || s > 0) ? 1u : 0u;
+          if (TF32) mma_ss_tf32(tmem, adesc + 2 * s, bdesc + 2 * s, idesc, acc);
+          else mma_ss_f16(tmem, adesc + 2 * s, bdesc + 2 * s, idesc, acc);
+        }
+        tc_commit(&empty[st]);
+      }
+      tc_commit(&acc_full);
+    }
+    __syncwarp();
+  } else {
+    const int lane_base = (warp & 3) * 32;
+    const int r = lane_base + (tid & 31);  // tile row == TMEM lane
+    const uint32_t lane_addr = (uint32_t)lane_base << 16;
+    const int m = m0 + r / p.TW, n = n0 + r % p.TW;
+    const bool valid = r < p.TH * p.TW && m < p.Mh && n < p.Mw;
+    const int oy = m * p.sy + p.py, ox = n * p.sx + p.px;
+    float nz = 0.f;
+    if (p.act && valid && p.noise) {
+      const float nw = p.noise_w ? *p.noise_w : 1.f;
+      nz = nw * p.noise[(int64_t)(p.noise_batched ? b : 0) * p.OH * p.OW + (int64_t)oy * p.OW + ox];
+    }
+    OT* out = (OT*)p.out + (((int64_t)b * p.OH + oy) * p.OW + ox) * p.O + o0;
+    mbar_wait(&acc_full, 0);
+    tc_fence_after();
+    for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem + lane_addr + c0, v);
+      tc_wait_ld();
+      if (!valid) continue;
+      float f[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) f[k] = __uint_as_float(v[k]);
+      if (p.act) {
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          float t = f[k] + nz + (p.bias ? __ldg(p.bias + o0 + c0 + k) : 0.f);
+          f[k] = (t > 0.f ? t : t * p.slope) * p.gain;
+        }
+      }
+      const int ncols = min(32, p.n_tile - c0);
+      if constexpr (TF32) {
+#pragma unroll
+        for (int k = 0; k < 32; k += 4)
+          if (k < ncols)
+            *reinterpret_cast<float4*>(out + c0 + k) =
+                make_float4(__uint_as_float(f32_to_tf32_rna(f[k])), __uint_as_float(f32_to_tf32_rna(f[k + 1])),
+                            __uint_as_float(f32_to_tf32_rna(f[k + 2])), __uint_as_float(f32_to_tf32_rna(f[k + 3])));
+      } else {
+#pragma unroll
+        for (int k = 0; k < 32; k += 8)
+          if (k < ncols) {
+            uint4 u;
+            u.x = pack_bf16x2(f[k], f[k + 1]);
+            u.y = pack_bf16x2(f[k + 2], f[k + 3]);
+            u.z = pack_bf16x2(f[k + 4], f[k + 5]);
+            u.w = pack_bf16x2(f[k + 6], f[k + 7]);
+            *reinterpret_cast<uint4*>(out + c0 + k) = u;
+          }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 256);
+}
+
+// ---- s[b, i] = latent[b, :] . Wm[i, :] / sqrt(K) + bm[i]   (EqualLinear, model.py:159-167, lr_mul = 1) -----------
+__global__ void __launch_bounds__(256) style_mod_kernel(const float* __restrict__ latent, int64_t ld,
+                                                        const float* __restrict__ mw, const float* __restrict__ mb,
+                                                        float* __restrict__ s, int B, int K, int I, float scale) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  for (int idx = blockIdx.x * warps_per_block + (threadIdx.x >> 5); idx < B * I; idx += gridDim.x * warps_per_block) {
+    const int b = idx / I, i = idx % I;
+    float acc = 0.f;
+    // the reference multiplies the weight by `scale` first (F.linear(input, weight * scale)): same rounding here
+    for (int k = lane; k < K; k += 32) acc = fmaf(latent[(int64_t)b * ld + k], mw[(int64_t)i * K + k] * scale, acc);
+    acc = warp_sum(acc);
+    if (lane == 0) s[idx] = acc + (mb ? mb[i] : 0.f);
+  }
+}
+
+// ---- per-sample modulated (and demodulated) weights in operand layout -------------------------------------------
+// Wp[b][t][o][i] = OT( scale * W[o, i, t] * s[b, i] * demod[b, o] ),
+// demod[b, o] = rsqrt( sum_{i,t} (scale * W[o,i,t] * s[b,i])^2 + 1e-8 )   (model.py:245-249). One block per (o, b).
+template <typename OT, bool ROUND_TF32>
+__global__ void __launch_bounds__(256) weight_prep_kernel(const float* __restrict__ w, const float* __restrict__ s,
+                                                          OT* __restrict__ wp, int I, int O, int T, float scale,
+                                                          int demodulate) {
+  const int o = blockIdx.x, b = blockIdx.y;
+  const float* wo = w + (int64_t)o * I * T;
+  const float* sb = s + (int64_t)b * I;
+  __shared__ float red[8];
+  __shared__ float demod_s;
+  float d = 1.f;
+  if (demodulate) {
+    float acc = 0.f;
+    for (int e = threadIdx.x; e < I * T; e += 256) {
+      const float v = scale * wo[e] * sb[e / T];
+      acc = fmaf(v, v, acc);
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      float t = threadIdx.x < 8 ? red[threadIdx.x] : 0.f;
+      t = warp_sum(t);
+      if (threadIdx.x == 0) demod_s = rsqrtf(t + 1e-8f);
+    }
+    __syncthreads();
+    d = demod_s;
+  }
+  for (int e = threadIdx.x; e < I * T; e += 256) {
+    const int t = e / I, i = e % I;  // write order: i fastest (coalesced); read w[o][i][t] strided (L1/L2 resident)
+    float v = scale * wo[i * T + t] * sb[i] * d;
+    if (ROUND_TF32) v = __uint_as_float(f32_to_tf32_rna(v));
+    wp[(((int64_t)b * T + t) * O + o) * I + i] = from_f32<OT>(v);
+  }
+}
+
+// ---- layout changes at the module boundary -------------------------------------------------------------------------
+template <typename TI, typename OT, bool ROUND_TF32>
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const TI* __restrict__ x, OT* __restrict__ y, int C, int HW,
+                                                           int64_t x_bstride) {
+  __shared__ float t[32][33];
+  const int b = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j, pp = p0 + tx;
+    t[j][tx] = (c < C && pp < HW) ? to_f32<TI>(x[(int64_t)b * x_bstride + (int64_t)c * HW + pp]) : 0.f;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int pp = p0 + j, c = c0 + tx;
+    if (pp < HW && c < C) {
+      float v = t[tx][j];
+      if (ROUND_TF32) v = __uint_as_float(f32_to_tf32_rna(v));
+      y[((int64_t)b * HW + pp) * C + c] = from_f32<OT>(v);
+    }
+  }
+}
+
+template <typename OT, typename TO>
+__global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const OT* __restrict__ x, TO* __restrict__ y, int C, int HW) {
+  __shared__ float t[32][33];
+  const int b = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int j = ty; j < 32; j += 8) {
+    const int pp = p0 + j, c = c0 + tx;
+    t[j][tx] = (c < C && pp < HW) ? to_f32<OT>(x[((int64_t)b * HW + pp) * C + c]) : 0.f;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j, pp = p0 + tx;
+    if (c < C && pp < HW) y[((int64_t)b * C + c) * HW + pp] = from_f32<TO>(t[tx][j]);
+  }
+}
+
+// ---- 4x4 blur (pad 1,1) of the (2H+1)^2 NHWC intermediate fused with noise + bias + leaky relu --------------------
+// out[b,y,x,c] = gain * lrelu( sum_{a,e} kf[a][e] * mid[b, y+a-1, x+e-1, c] + nw*noise[b|0,y,x] + bias[c] )
+template <typename OT, int VEC>
+__global__ void __launch_bounds__(256) blur_act_nhwc_kernel(const OT* __restrict__ mid, OT* __restrict__ out,
+                                                            const float* __restrict__ kf /*4x4 blur.kernel*/,
+                                                            const float* __restrict__ noise, int noise_batched,
+                                                            const float* __restrict__ noise_w,
+                                                            const float* __restrict__ bias, int B, int C, int OH, int OW,
+                                                            int act, float slope, float gain) {
+  const int MH = OH + 1, MW = OW + 1;
+  const int cv = C / VEC;
+  __shared__ float sk[16];
+  if (threadIdx.x < 16) sk[threadIdx.x] = kf[15 - threadIdx.x];  // flipped taps (upfirdn2d_kernel.cu:77)
+  __syncthreads();
+  const float nw = noise_w ? *noise_w : 1.f;
+  const int64_t total = (int64_t)B * OH * OW * cv;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % cv) * VEC;
+    int64_t t = idx / cv;
+    const int x = (int)(t % OW);
+    t /= OW;
+    const int y = (int)(t % OH);
+    const int b = (int)(t / OH);
+    float acc[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int yy = y + a - 1;
+      if (yy < 0 || yy >= MH) continue;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int xx = x + e - 1;
+        if (xx < 0 || xx >= MW) continue;
+        const OT* src = mid + (((int64_t)b * MH + yy) * MW + xx) * C + c;
+        const float kv = sk[a * 4 + e];
+        Vec16<OT> v = ld_vec16(src);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) acc[k] = fmaf(to_f32<OT>(v.e[k]), kv, acc[k]);
+      }
+    }
+    Vec16<OT> o;
+    if (act) {
+      const float nz = noise ? nw * noise[(int64_t)(noise_batched ? b : 0) * OH * OW + (int64_t)y * OW + x] : 0.f;
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        float u = acc[k] + nz + (bias ? __ldg(bias + c + k) : 0.f);
+        o.e[k] = from_f32<OT>((u > 0.f ? u : u * slope) * gain);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) o.e[k] = from_f32<OT>(acc[k]);
+    }
+    st_vec16(out + (((int64_t)b * OH + y) * OW + x) * C + c, o);
+  }
+}
+
+// ---- ToRGB: 1x1 modulated conv to 3 channels (no demod) + bias + upsampled skip -------------------------------------
+// rgb[b,o,y,x] = sum_i (scale*W[o,i]*s[b,i]) * act[b,y,x,i] + bias[o] + upfirdn2d(skip, k, up=2, pad=(2,1))[b,o,y,x]
+// LANES lanes cooperate on one pixel (16-byte channel vectors), reduced with warp shuffles.
+template <typename OT, int VEC>
+__global__ void __launch_bounds__(256) torgb_nhwc_kernel(const OT* __restrict__ x, const float* __restrict__ w,
+                                                         const float* __restrict__ s, const float* __restrict__ bias,
+                                                         const float* __restrict__ skip, const float* __restrict__ kf,
+                                                         float* __restrict__ rgb, int B, int I, int H, int W, float scale,
+                                                         int lanes) {
+  extern __shared__ float sw[];  // [3][I] modulated weights of this image, then 16 taps
+  const int b = blockIdx.y;
+  float* sk = sw + 3 * I;
+  for (int e = threadIdx.x; e < 3 * I; e += blockDim.x) sw[e] = scale * w[e] * s[(int64_t)b * I + (e % I)];
+  if (threadIdx.x < 16) sk[threadIdx.x] = kf ? kf[15 - threadIdx.x] : 0.f;  // flipped taps
+  __syncthreads();
+  const int sub = threadIdx.x % lanes;                 // lane within the pixel group
+  const int groups_per_block = blockDim.x / lanes;
+  const int HW = H * W;
+  const int h2 = H / 2, w2 = W / 2;
+  for (int pix = blockIdx.x * groups_per_block + threadIdx.x / lanes; pix < HW; pix += gridDim.x * groups_per_block) {
+    const OT* xp = x + ((int64_t)b * HW + pix) * I;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int c = sub * VEC; c < I; c += lanes * VEC) {
+      Vec16<OT> v = ld_vec16_stream(xp + c);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        const float f = to_f32<OT>(v.e[k]);
+        a0 = fmaf(f, sw[c + k], a0);
+        a1 = fmaf(f, sw[I + c + k], a1);
+        a2 = fmaf(f, sw[2 * I + c + k], a2);
+      }
+    }
+    for (int off = lanes >> 1; off > 0; off >>= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, off);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, off);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, off);
+    }
+    if (sub == 0) {
+      const int y = pix / W, xx = pix % W;
+      float r[3] = {a0 + bias[0], a1 + bias[1], a2 + bias[2]};
+      if (skip) {
+        // Upsample: zero-insert x2, pad (2,1), flipped 4x4 taps (model.py:30-49, upfirdn2d_kernel.cu:77)
+#pragma unroll
+        for (int ky = 0; ky < 4; ++ky) {
+          const int uy = y + ky - 2;
+          if (uy < 0 || (uy & 1) || (uy >> 1) >= h2) continue;
+#pragma unroll
+          for (int kx = 0; kx < 4; ++kx) {
+            const int ux = xx + kx - 2;
+            if (ux < 0 || (ux & 1) || (ux >> 1) >= w2) continue;
+            const float kv = sk[ky * 4 + kx];
+            const int64_t si = ((int64_t)b * 3 * h2 + (uy >> 1)) * w2 + (ux >> 1);
+#pragma unroll
+            for (int o = 0; o < 3; ++o) r[o] = fmaf(kv, skip[si + (int64_t)o * h2 * w2], r[o]);
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 0; o < 3; ++o) rgb[((int64_t)b * 3 + o) * HW + pix] = r[o];
+    }
+  }
+}
+
+inline int esz_of(int mma) { return mma == FMI_MMA_TF32 ? 4 : 2; }
+
+struct TilePlan { int TH, TW, tiles_h, tiles_w; };
+TilePlan pick_tile(int Mh, int Mw) {
+  TilePlan best{};
+  int64_t best_area = -1;
+  const int cands[5][2] = {{4, 32}, {8, 16}, {16, 8}, {32, 4}, {2, 64}};
+  for (auto& c : cands) {
+    int th = c[0], tw = c[1];
+    if (tw > 256 || th > 256) continue;
+    int tiles_h = (Mh + th - 1) / th, tiles_w = (Mw + tw - 1) / tw;
+    int64_t area = (int64_t)tiles_h * tiles_w;
+    if (best_area < 0 || area < best_area) {
+      best_area = area;
+      best = {th, tw, tiles_h, tiles_w};
+    }
+  }
+  // small images: one tile covering the whole plane when it fits
+  if ((int64_t)Mh * Mw <= 128 && Mw <= 128) best = {Mh, Mw, 1, 1};
+  return best;
+}
+
+template <bool TF32>
+int launch_gemm_class(const CUtensorMap& mx, const CUtensorMap& mw, ConvGemmParams p, cudaStream_t st) {
+  auto kern = modconv_gemm_kernel<TF32>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    FMI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
+    attr_set = true;
+  }
+  const int stage_bytes = A_STAGE_BYTES + p.n_tile * 128;
+  int stages = (232448 - 4096) / stage_bytes;
+  if (stages > 8) stages = 8;
+  p.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + 1024;
+  TilePlan tp = pick_tile(p.Mh, p.Mw);
+  p.TH = tp.TH; p.TW = tp.TW; p.tiles_w = tp.tiles_w;
+  dim3 grid(tp.tiles_h * tp.tiles_w, p.O / p.n_tile, p.B);
+  kern<<<grid, kGemmThreads, smem, st>>>(mx, mw, p);
+  return fmi_check_cuda(cudaGetLastError(), "modconv_gemm launch");
+}
+
+}  // namespace
+
+// =====================================================================================================================
+// C ABI
+// =====================================================================================================================
+extern "C" int fmi_nchw_to_nhwc(const void* x, void* y, int B, int C, int H, int W, int dtype, int mma, void* stream) {
+  FMI_REQUIRE(fmi_dtype_ok(dtype) && (mma == FMI_MMA_TF32 || mma == FMI_MMA_BF16), "nchw_to_nhwc: bad dtype/mma");
+  if (B == 0) return FMI_OK;
+  FMI_REQUIRE(x && y && C >= 1 && H >= 1 && W >= 1, "nchw_to_nhwc: bad arguments");
+  const int HW = H * W;
+  dim3 grid((HW + 31) / 32, (C + 31) / 32, B);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t bs = (int64_t)C * HW;
+  FMI_DISPATCH_DTYPE(dtype, T, {
+    if (mma == FMI_MMA_TF32) nchw_to_nhwc_kernel<T, float, true><<<grid, 256, 0, st>>>((const T*)x, (float*)y, C, HW, bs);
+    else nchw_to_nhwc_kernel<T, __nv_bfloat16, false><<<grid, 256, 0, st>>>((const T*)x, (__nv_bfloat16*)y, C, HW, bs);
+  });
+  return fmi_check_cuda(cudaGetLastError(), "nchw_to_nhwc launch");
+}
+
+extern "C" int fmi_nhwc_to_nchw(const void* x, void* y, int B, int C, int H, int W, int mma, int dtype, void* stream) {
+  FMI_REQUIRE(fmi_dtype_ok(dtype) && (mma == FMI_MMA_TF32 || mma == FMI_MMA_BF16), "nhwc_to_nchw: bad dtype/mma");
+  if (B == 0) return FMI_OK;
+  FMI_REQUIRE(x && y && C >= 1 && H >= 1 && W >= 1, "nhwc_to_nchw: bad arguments");
+  const int HW = H * W;
+  dim3 grid((HW + 31) / 32, (C + 31) / 32, B);
+  cudaStream_t st = (cudaStream_t)stream;
+  FMI_DISPATCH_DTYPE(dtype, T, {
+    if (mma == FMI_MMA_TF32) nhwc_to_nchw_kernel<float, T><<<grid, 256, 0, st>>>((const float*)x, (T*)y, C, HW);
+    else nhwc_to_nchw_kernel<__nv_bfloat16, T><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (T*)y, C, HW);
+  });
+  return fmi_check_cuda(cudaGetLastError(), "nhwc_to_nchw launch");
+}
+
+extern "C" int fmi_style_modulation(const float* latent, int64_t latent_row_stride, const float* mod_weight,
+                                    const float* mod_bias, float* s, int B, int K, int I, void* stream) {
+  if (B == 0) return FMI_OK;
+  FMI_REQUIRE(latent && mod_weight && s && K >= 1 && I >= 1, "style_modulation: bad arguments");
+  int grid = (B * I + 7) / 8;
+  if (grid > FMI_NUM_SMS * 8) grid = FMI_NUM_SMS * 8;
+  style_mod_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(latent, latent_row_stride, mod_weight, mod_bias, s, B, K, I,
+                                                            1.0f / sqrtf((float)K));
+  return fmi_check_cuda(cudaGetLastError(), "style_modulation launch");
+}
+
+extern "C" int64_t fmi_modconv_weight_bytes(int B, int I, int O, int ksize, int mma) {
+  return (int64_t)B * ksize * ksize * O * I * esz_of(mma);
+}
+
+extern "C" int fmi_modconv_weight_prep(const float* weight, const float* s, void* wp, int B, int I, int O, int ksize,
+                                       int demodulate, int mma, void* stream) {
+  FMI_REQUIRE(mma == FMI_MMA_TF32 || mma == FMI_MMA_BF16, "modconv_weight_prep: bad mma");
+  if (B == 0) return FMI_OK;
+  FMI_REQUIRE(weight && s && wp && I >= 1 && O >= 1 && (ksize == 1 || ksize == 3), "modconv_weight_prep: bad arguments");
+  const int T = ksize * ksize;
+  const float scale = 1.0f / sqrtf((float)(I * T));  // model.py:225-226
+  dim3 grid(O, B);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mma == FMI_MMA_TF32) weight_prep_kernel<float, true><<<grid, 256, 0, st>>>(weight, s, (float*)wp, I, O, T, scale, demodulate);
+  else weight_prep_kernel<__nv_bfloat16, false><<<grid, 256, 0, st>>>(weight, s, (__nv_bfloat16*)wp, I, O, T, scale, demodulate);
+  return fmi_check_cuda(cudaGetLastError(), "modconv_weight_prep launch");
+}
+
+extern "C" int64_t fmi_styled_conv_workspace_bytes(int B, int O, int H, int W, int upsample, int mma) {
+  if (!upsample) return 0;
+  return (int64_t)B * (2 * H + 1) * (2 * W + 1) * O * esz_of(mma);
+}
+
+extern "C" int fmi_styled_conv_nhwc(const void* x, const void* wp, void* y, const float* noise, int noise_batched,
+                                    const float* noise_w, const float* act_bias, const float* blur_k, int B, int I, int O,
+                                    int H, int W, int upsample, int act, int mma, void* workspace, int64_t workspace_bytes,
+                                    void* stream) {
+  FMI_REQUIRE(mma == FMI_MMA_TF32 || mma == FMI_MMA_BF16, "styled_conv: bad mma");
+  if (B == 0) return FMI_OK;
+  FMI_REQUIRE(x && wp && y, "styled_conv: null pointer");
+  FMI_REQUIRE(I >= 16 && O >= 32 && O % 32 == 0 && H >= 1 && W >= 1,
+              "styled_conv: unsupported shape I=%d O=%d H=%d W=%d (O must be a multiple of 32)", I, O, H, W);
+  const int esz = esz_of(mma);
+  FMI_REQUIRE((I * esz) % 16 == 0 && (O * esz) % 16 == 0, "styled_conv: channel counts must give 16-byte rows");
+  FMI_REQUIRE(O <= 256 || O % 256 == 0, "styled_conv: O=%d must be <= 256 or a multiple of 256", O);
+  FMI_REQUIRE(fmi_aligned(x, 16) && fmi_aligned(wp, 16) && fmi_aligned(y, 16), "styled_conv: buffers must be 16-byte aligned");
+  int rc = fmi_device_check();
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool tf32 = mma == FMI_MMA_TF32;
+  const uint32_t epa = 128 / esz;
+  const CUtensorMapDataType dt = tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const int T = 9;
+
+  ConvGemmParams p{};
+  p.B = B; p.I = I; p.O = O; p.H = H; p.W = W; p.T = T;
+  p.n_tile = O <= 256 ? O : 256;
+  p.k_chunks = (I + epa - 1) / epa;
+  p.noise = noise; p.noise_batched = noise_batched; p.noise_w = noise_w; p.bias = act_bias;
+  p.slope = 0.2f; p.gain = 1.4142135623730951f;
+
+  CUtensorMap mw;
+  {
+    uint64_t dims[2] = {(uint64_t)I, (uint64_t)B * T * O};
+    uint64_t str[1] = {(uint64_t)I * esz};
+    uint32_t box[2] = {epa, (uint32_t)p.n_tile};
+    int e = make_tensor_map(&mw, dt, 2, wp, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    FMI_REQUIRE(e == 0, "styled_conv: cuTensorMapEncodeTiled(weights) failed (%d)", e);
+  }
+  auto make_x_map = [&](CUtensorMap* m, int th, int tw) -> int {
+    uint64_t dims[4] = {(uint64_t)I, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)I * esz, (uint64_t)W * I * esz, (uint64_t)H * W * I * esz};
+    uint32_t box[4] = {epa, (uint32_t)tw, (uint32_t)th, 1};
+    return make_tensor_map(m, dt, 4, x, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+  };
+
+  if (!upsample) {
+    p.OH = H; p.OW = W; p.Mh = H; p.Mw = W; p.sy = p.sx = 1; p.py = p.px = 0;
+    p.ntaps = 9;
+    for (int t = 0; t < 9; ++t) { p.tap_dy[t] = t / 3 - 1; p.tap_dx[t] = t % 3 - 1; p.tap_slab[t] = t; }
+    p.act = act; p.out = y;
+    TilePlan tp = pick_tile(p.Mh, p.Mw);
+    CUtensorMap mx;
+    int e = make_x_map(&mx, tp.TH, tp.TW);
+    FMI_REQUIRE(e == 0, "styled_conv: cuTensorMapEncodeTiled(x) failed (%d)", e);
+    return tf32 ? launch_gemm_class<true>(mx, mw, p, st) : launch_gemm_class<false>(mx, mw, p, st);
+  }
+
+  // ---- upsample: conv_transpose2d(stride 2) by output parity class, then blur + epilogue
+  const int MH = 2 * H + 1, MW = 2 * W + 1;
+  const int64_t need = (int64_t)B * MH * MW * O * esz;
+  FMI_REQUIRE(workspace && workspace_bytes >= need, "styled_conv: workspace too small (%lld < %lld)",
+              (long long)workspace_bytes, (long long)need);
+  FMI_REQUIRE(blur_k, "styled_conv: upsample needs the 4x4 blur kernel");
+  p.OH = MH; p.OW = MW; p.sy = p.sx = 2; p.act = 0; p.out = workspace;
+  for (int py = 0; py < 2; ++py)
+    for (int px = 0; px < 2; ++px) {
+      // out[2m+py, 2n+px]: ky in {0,2} (py==0) or {1}; input row m - ky/2
+      p.py = py; p.px = px;
+      p.Mh = py == 0 ? H + 1 : H;
+      p.Mw = px == 0 ? W + 1 : W;
+      int nt = 0;
+      for (int ky = py; ky < 3; ky += 2)
+        for (int kx = px; kx < 3; kx += 2) {
+          p.tap_dy[nt] = -(ky / 2);
+          p.tap_dx[nt] = -(kx / 2);
+          p.tap_slab[nt] = ky * 3 + kx;
+          ++nt;
+        }
+      p.ntaps = nt;
+      TilePlan tp = pick_tile(p.Mh, p.Mw);
+      CUtensorMap mx;
+      int e = make_x_map(&mx, tp.TH, tp.TW);
+      FMI_REQUIRE(e == 0, "styled_conv: cuTensorMapEncodeTiled(x) failed (%d)", e);
+      rc = tf32 ? launch_gemm_class<true>(mx, mw, p, st) : launch_gemm_class<false>(mx, mw, p, st);
+      if (rc) return rc;
+    }
+  // blur: flipped taps (upfirdn2d_kernel.cu:77)
+  const int OH = 2 * H, OW = 2 * W;
+  const int64_t total_vec = (int64_t)B * OH * OW * (O * esz / 16);
+  int grid = (int)imin64((total_vec + 255) / 256, (int64_t)FMI_NUM_SMS * 32);
+  if (tf32)
+    blur_act_nhwc_kernel<float, 4><<<grid, 256, 0, st>>>((const float*)workspace, (float*)y, blur_k, noise, noise_batched,
+                                                         noise_w, act_bias, B, O, OH, OW, act, p.slope, p.gain);
+  else
+    blur_act_nhwc_kernel<__nv_bfloat16, 8><<<grid, 256, 0, st>>>((const __nv_bfloat16*)workspace, (__nv_bfloat16*)y, blur_k,
+                                                                 noise, noise_batched, noise_w, act_bias, B, O, OH, OW,
+                                                                 act, p.slope, p.gain);
+  return fmi_check_cuda(cudaGetLastError(), "blur_act launch");
+}
+
+extern "C" int fmi_torgb_nhwc(const void* x, const float* weight, const float* s, const float* bias, const float* skip,
+                              const float* blur_k, float* rgb, int B, int I, int H, int W, int mma, void* stream) {
+  FMI_REQUIRE(mma == FMI_MMA_TF32 || mma == FMI_MMA_BF16, "torgb: bad mma");
+  if (B == 0) return FMI_OK;
+  FMI_REQUIRE(x && weight && s && bias && rgb, "torgb: null pointer");
+  FMI_REQUIRE(!skip || (blur_k && H % 2 == 0 && W % 2 == 0), "torgb: skip needs the blur kernel and even H, W");
+  const int esz = esz_of(mma);
+  const int vec = 16 / esz;
+  FMI_REQUIRE(I % vec == 0, "torgb: I=%d must be a multiple of %d", I, vec);
+  int lanes = I / vec;  // lanes per pixel, power of two <= 32
+  if (lanes > 32) lanes = 32;
+  int l2 = 1;
+  while (l2 * 2 <= lanes) l2 *= 2;
+  lanes = l2;
+  const int groups = 256 / lanes;
+  int gx = (H * W + groups - 1) / groups;
+  if (gx > FMI_NUM_SMS * 8) gx = FMI_NUM_SMS * 8;
+  dim3 grid(gx, B);
+  const size_t smem = (size_t)(3 * I + 16) * sizeof(float);
+  const float scale = 1.0f / sqrtf((float)I);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mma == FMI_MMA_TF32)
+    torgb_nhwc_kernel<float, 4><<<grid, 256, smem, st>>>((const float*)x, weight, s, bias, skip, blur_k, rgb, B, I, H, W, scale, lanes);
+  else
+    torgb_nhwc_kernel<__nv_bfloat16, 8><<<grid, 256, smem, st>>>((const __nv_bfloat16*)x, weight, s, bias, skip, blur_k, rgb, B, I, H, W, scale, lanes);
+  return fmi_check_cuda(cudaGetLastError(), "torgb launch");
+}

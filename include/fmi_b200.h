@@ -139,23 +139,47 @@ int fmi_conv1x1(const void* x, const float* w, const float* b, void* y, int N, i
                 int S, int dtype, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
- * a3/a6  modulated convolution as a shared-weight implicit GEMM
- *   (ModulatedConv2d.forward, modules/psp/stylegan2/model.py:241-279; StyledConv.forward :340-346;
- *    ToRGB.forward :360-369; NoiseInjection :289-294).
- *   y[b,o,p] = epi( demod[b,o] * sum_{i,t} (scale*W[o,i,t]) * (s[b,i] * x[b,i,p+t]) )
- *   demod[b,o] = rsqrt( sum_i s[b,i]^2 * sum_t (scale*W[o,i,t])^2 + 1e-8 )        (:247-249)
- *   epi (StyledConv) = sqrt2 * lrelu_0.2( . + noise_w*noise[b|1,p] + act_bias[o] ) (:341-344)
- *   epi (ToRGB)      = . + bias[o] + skip[b,o,p]                                  (:361-367)
- *   upsample=1: conv_transpose2d(stride 2) -> (2H+1)^2 then the 4x4 blur pad(1,1) -> (2H)^2
- *     (:255-263), computed as a second streaming pass fused with the epilogue.
- * See DESIGN.md for the staged layouts. Declared here; documented fully with the kernel.
+ * a3/a6  modulated convolution (ModulatedConv2d.forward, modules/psp/stylegan2/model.py:241-279) with
+ *   the StyledConv / NoiseInjection / FusedLeakyReLU / ToRGB glue (:289-294, :340-346, :360-369).
+ *   Activations are kept in NHWC in the tensor-core operand type between layers (bf16 for
+ *   FMI_MMA_BF16, tf32-rounded fp32 for FMI_MMA_TF32); per-sample modulated+demodulated weights are
+ *   staged tap-major/K-major once per layer; the convolution is an implicit GEMM on tcgen05 with the
+ *   im2col gather done by 4-D TMA boxes. See DESIGN.md.
  * ------------------------------------------------------------------------------------------- */
-int64_t fmi_modconv_workspace_bytes(int B, int I, int O, int H, int W, int ksize, int upsample);
-int fmi_modconv_fwd(const void* x, const float* weight, const float* style_s, const float* noise,
-                    int noise_batched, const float* noise_w, const float* bias, const void* skip,
-                    const float* blur_k, void* y, int B, int I, int O, int H, int W, int ksize,
-                    int upsample, int demodulate, int act, int dtype, void* workspace,
-                    int64_t workspace_bytes, void* stream);
+/* NCHW (dtype) -> NHWC (operand type of `mma`) and back: the module boundary. */
+int fmi_nchw_to_nhwc(const void* x, void* y, int B, int C, int H, int W, int dtype, int mma, void* stream);
+int fmi_nhwc_to_nchw(const void* x, void* y, int B, int C, int H, int W, int mma, int dtype, void* stream);
+
+/* s[b,i] = latent[b,:] . mod_weight[i,:] / sqrt(K) + mod_bias[i]
+ *   (EqualLinear `modulation`, model.py:159-167 with lr_mul = 1; called at :244). latent rows are
+ *   latent_row_stride floats apart (so latent[:, layer] of a [B, n_latent, K] tensor needs no copy). */
+int fmi_style_modulation(const float* latent, int64_t latent_row_stride, const float* mod_weight,
+                         const float* mod_bias, float* s, int B, int K, int I, void* stream);
+
+/* wp[b][tap][o][i] = scale*W[o,i,tap]*s[b,i]*demod[b,o],  demod = rsqrt(sum (scale*W*s)^2 + 1e-8)
+ *   (model.py:245-249); weight is the parameter [O,I,k,k] fp32, k in {1,3}. */
+int64_t fmi_modconv_weight_bytes(int B, int I, int O, int ksize, int mma);
+int fmi_modconv_weight_prep(const float* weight, const float* s, void* wp, int B, int I, int O, int ksize,
+                            int demodulate, int mma, void* stream);
+
+/* One StyledConv (3x3) on NHWC operands: y = epi(modconv(x)). x [B,H,W,I], wp from
+ *   fmi_modconv_weight_prep, y [B,OH,OW,O] with OH = H (plain) or 2H (upsample: conv_transpose2d
+ *   stride 2 -> (2H+1)^2 intermediate in `workspace` -> 4x4 blur pad (1,1), model.py:255-263).
+ *   act = 1: y = sqrt2*lrelu_0.2(conv + noise_w*noise[b|0,p] + act_bias[o])  (model.py:341-344, :294);
+ *   act = 0: y = conv (ModulatedConv2d alone). noise is fp32 [B or 1, OH*OW] or NULL; noise_w a device
+ *   scalar; blur_k the module's 4x4 `blur.kernel` buffer (already x4), required when upsample. */
+int64_t fmi_styled_conv_workspace_bytes(int B, int O, int H, int W, int upsample, int mma);
+int fmi_styled_conv_nhwc(const void* x, const void* wp, void* y, const float* noise, int noise_batched,
+                         const float* noise_w, const float* act_bias, const float* blur_k, int B, int I,
+                         int O, int H, int W, int upsample, int act, int mma, void* workspace,
+                         int64_t workspace_bytes, void* stream);
+
+/* ToRGB (model.py:360-369): rgb[b,o,p] = sum_i (W[o,i]*s[b,i]/sqrt(I)) * x[b,p,i] + bias[o]
+ *   + upfirdn2d(skip, blur_k, up=2, pad=(2,1)) (Upsample, model.py:30-49) when skip != NULL.
+ *   x NHWC operand type; weight [3,I], s [B,I], bias [3], skip [B,3,H/2,W/2], rgb [B,3,H,W] fp32. */
+int fmi_torgb_nhwc(const void* x, const float* weight, const float* s, const float* bias,
+                   const float* skip, const float* blur_k, float* rgb, int B, int I, int H, int W, int mma,
+                   void* stream);
 
 #ifdef __cplusplus
 }
