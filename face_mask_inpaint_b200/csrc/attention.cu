@@ -10,7 +10,8 @@
 // Data layout in HBM
 //   inputs/outputs stay in the reference's NCHW ([N, C, S], S contiguous).
 //   workspace (tensor-core operand staging, written by two tiny prologue kernels):
-//     Qt   [N, S, dpad]   q transposed, d padded to a whole 128-byte row, bf16 or tf32-rounded fp32
+//     Qt   [N, S, qrow]   q transposed, bf16, d padded to a whole 128-byte row (dpad); with the fp32 contract the row
+//                         is [hi | lo]: q = hi + lo to 16 mantissa bits, and E = hi.hi + hi.lo + lo.hi (3 bf16 MMAs)
 //     Vcat [N, Cv, S]     value groups concatenated, bf16 or tf32-rounded fp32 (S contiguous = K-major B operand)
 //
 // Main kernel: one CTA per (128 query rows, image, 256-channel slice of V). 6 warps:
@@ -35,13 +36,16 @@ constexpr int BM = 128;          // query rows per CTA
 constexpr int BN = 128;          // keys per tile
 constexpr int CV_MAX = 256;      // value channels per CTA (TMEM columns of O)
 constexpr int ATOM_BYTES = 128;  // swizzle atom row
-constexpr int kAttnThreads = 192;
-constexpr int kSmemBudget = 232448 - 2048;  // 227 KB opt-in minus alignment slack and static barriers
+constexpr int kAttnThreads = 320;  // TMA warp + MMA warp + two softmax warpgroups
+constexpr int kStaticSmem = 3072;               // barriers + exchange buffer, padded to the 1024-byte alignment
+constexpr int kSmemBudget = 232448 - kStaticSmem;  // 227 KB opt-in minus the static part (dynamic base is 1024-aligned)
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
 
 struct AttnParams {
-  int N, S, C0, C1, cv_tile, d_atoms;  // d_atoms = 128-byte atoms per Qt row
+  int N, S, C0, C1, cv_tile;
+  int d_atoms;  // 128-byte (64 x bf16) atoms per Qt component
+  int split;    // 1: Qt rows hold [hi | lo] bf16 components (fp32 contract), 0: hi only
   int k_stages, v_stages;
   const void* v0;
   const void* v1;
@@ -70,9 +74,11 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
   constexpr int V_CHUNKS = BN / EPA;         // K-chunks of the PV product per key tile
   constexpr int P_COLS_PER_CHUNK = 32;       // TMEM columns of P per chunk (32 tf32 or 64 packed bf16)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw;  // 1024-byte aligned by construction (checked below): SWIZZLE_128B needs it
+  if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
 
-  const int q_tile_bytes = p.d_atoms * BM * ATOM_BYTES;
+  const int q_atoms = p.d_atoms * (1 + p.split);  // atoms per Qt row
+  const int q_tile_bytes = q_atoms * BM * ATOM_BYTES;
   const int v_chunk_bytes = p.cv_tile * ATOM_BYTES;
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + q_tile_bytes;                   // k_stages tiles
@@ -80,6 +86,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
 
   __shared__ uint64_t q_full, k_full[2], k_empty[2], v_full[8], v_empty[8], s_full[2], p_full[2], pv_done[2];
   __shared__ uint32_t tmem_base_s;
+  __shared__ float xch[2][2][BM];  // row max / row sum exchange between the two softmax warpgroups (double buffered)
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int i_tile = blockIdx.x, n = blockIdx.y, cv0 = blockIdx.z * p.cv_tile;
@@ -91,7 +98,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
       mbar_init(&k_full[i], 1);
       mbar_init(&k_empty[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 128);
+      mbar_init(&p_full[i], 256);
       mbar_init(&pv_done[i], 1);
     }
     for (int i = 0; i < 8; ++i) {
@@ -117,15 +124,15 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
       tma_prefetch_desc(&map_q);
       tma_prefetch_desc(&map_v);
       mbar_arrive_expect_tx(&q_full, q_tile_bytes);
-      for (int a = 0; a < p.d_atoms; ++a)
-        tma_load_2d(sQ + a * BM * ATOM_BYTES, &map_q, &q_full, a * EPA, n * p.S + i_tile * BM);
+      for (int a = 0; a < q_atoms; ++a)
+        tma_load_2d(sQ + a * BM * ATOM_BYTES, &map_q, &q_full, a * 64, n * p.S + i_tile * BM);
       auto load_k = [&](int jj) {
         const int j = (i_tile + jj) % NT;
         const int slot = jj % p.k_stages;
         mbar_wait(&k_empty[slot], ((jj / p.k_stages) & 1) ^ 1);
         mbar_arrive_expect_tx(&k_full[slot], q_tile_bytes);
-        for (int a = 0; a < p.d_atoms; ++a)
-          tma_load_2d(sK + slot * q_tile_bytes + a * BN * ATOM_BYTES, &map_q, &k_full[slot], a * EPA, n * p.S + j * BN);
+        for (int a = 0; a < q_atoms; ++a)
+          tma_load_2d(sK + slot * q_tile_bytes + a * BN * ATOM_BYTES, &map_q, &k_full[slot], a * 64, n * p.S + j * BN);
       };
       auto load_v = [&](int jj) {
         const int j = (i_tile + jj) % NT;
@@ -148,21 +155,26 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (elect_one()) {
-      const uint32_t idesc_qk = make_idesc(TF32 ? KIND_TF32 : KIND_BF16, BM, BN);
+      const uint32_t idesc_qk = make_idesc(KIND_BF16, BM, BN);  // logits always from bf16 (hi/lo split) operands
       const uint32_t idesc_pv = make_idesc(TF32 ? KIND_TF32 : KIND_BF16, BM, p.cv_tile);
       auto issue_qk = [&](int jj) {
         const int slot = jj % p.k_stages, b = jj & 1;
         mbar_wait(&k_full[slot], (jj / p.k_stages) & 1);
         tc_fence_after();
         uint32_t acc = 0;
-        for (int a = 0; a < p.d_atoms; ++a) {
-          const uint64_t adesc = make_sdesc_k_sw128(smem_u32(sQ + a * BM * ATOM_BYTES));
-          const uint64_t bdesc = make_sdesc_k_sw128(smem_u32(sK + slot * q_tile_bytes + a * BN * ATOM_BYTES));
+        // fp32 contract: q = hi + lo (two bf16 terms, 16 mantissa bits); E = hi.hi + hi.lo + lo.hi (error ~2^-16)
+        const int npairs = p.split ? 3 : 1;
+        for (int pr = 0; pr < npairs; ++pr) {
+          const int ca = pr == 2 ? 1 : 0, cb = pr == 1 ? 1 : 0;  // component (0 = hi, 1 = lo) of A and B
+          for (int a = 0; a < p.d_atoms; ++a) {
+            const uint64_t adesc = make_sdesc_k_sw128(smem_u32(sQ + (ca * p.d_atoms + a) * BM * ATOM_BYTES));
+            const uint64_t bdesc =
+                make_sdesc_k_sw128(smem_u32(sK + slot * q_tile_bytes + (cb * p.d_atoms + a) * BN * ATOM_BYTES));
 #pragma unroll
-          for (int s = 0; s < 4; ++s) {
-            if (TF32) mma_ss_tf32(tmem_S(b), adesc + 2 * s, bdesc + 2 * s, idesc_qk, acc);
-            else mma_ss_f16(tmem_S(b), adesc + 2 * s, bdesc + 2 * s, idesc_qk, acc);
-            acc = 1;
+            for (int s = 0; s < 4; ++s) {
+              mma_ss_f16(tmem_S(b), adesc + 2 * s, bdesc + 2 * s, idesc_qk, acc);
+              acc = 1;
+            }
           }
         }
         tc_commit(&k_empty[slot]);
@@ -200,79 +212,91 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
     __syncwarp();
   } else {
     // ------------------------------------------------------------------ softmax + epilogue (one thread per row)
+    // Two softmax warpgroups split every S tile by columns: thread (wg, row) owns 64 of the 128 logits of its row.
+    const int wg = (warp - 2) >> 2;         // 0: key columns [0,64), 1: [64,128)
     const int lane_base = (warp & 3) * 32;  // TMEM lanes this warp may touch
     const int row = lane_base + (tid & 31);
     const uint32_t lane_addr = (uint32_t)lane_base << 16;
+    const int n_chunks = p.cv_tile / 32;    // 32-column chunks of O: chunk k belongs to warpgroup k & 1
     float m_used = 0.f, l = 0.f;
     for (int jj = 0; jj < NT; ++jj) {
       const int b = jj & 1;
       mbar_wait(&s_full[b], (jj >> 1) & 1);
       tc_fence_after();
-      uint32_t s[128];
-#pragma unroll
-      for (int q4 = 0; q4 < 4; ++q4)
-        tmem_ld32(tmem_S(b) + lane_addr + q4 * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[q4 * 32]));
+      uint32_t s[64];
+      tmem_ld32(tmem_S(b) + lane_addr + wg * 64, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+      tmem_ld32(tmem_S(b) + lane_addr + wg * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
       tc_wait_ld();
-      float mx = __uint_as_float(s[0]);
+      float mx4[4];
 #pragma unroll
-      for (int k = 1; k < 128; ++k) mx = fmaxf(mx, __uint_as_float(s[k]));
-      mx *= kLog2e;
+      for (int q = 0; q < 4; ++q) mx4[q] = __uint_as_float(s[q]);
+#pragma unroll
+      for (int k = 4; k < 64; ++k) mx4[k & 3] = fmaxf(mx4[k & 3], __uint_as_float(s[k]));
+      float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * kLog2e;
+      // row maximum over both halves: exchange through shared memory (double buffered by tile parity)
+      xch[b][wg][row] = mx;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      mx = fmaxf(mx, xch[b][wg ^ 1][row]);
       if (jj == 0) {
         m_used = mx;
       } else {
         const bool need = mx > m_used + kRescaleThreshold;
         if (__any_sync(0xffffffffu, need)) {
-          // O may only be touched once PV(jj-1) has landed
+          // O may only be touched once PV(jj-1) has landed; each warpgroup rescales its own column chunks
           mbar_wait(&pv_done[(jj - 1) & 1], ((jj - 1) >> 1) & 1);
           tc_fence_after();
           const float f = need ? ex2(m_used - mx) : 1.f;
-          for (int c0 = 0; c0 < p.cv_tile; c0 += 32) {
+          for (int ck = wg; ck < n_chunks; ck += 2) {
             uint32_t o[32];
-            tmem_ld32(tmem_O + lane_addr + c0, o);
+            tmem_ld32(tmem_O + lane_addr + ck * 32, o);
             tc_wait_ld();
 #pragma unroll
             for (int k = 0; k < 32; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * f);
-            tmem_st32(tmem_O + lane_addr + c0, o);
+            tmem_st32(tmem_O + lane_addr + ck * 32, o);
           }
           l *= f;
           if (need) m_used = mx;
         }
       }
-      float sum = 0.f;
+      float sum4[4] = {0.f, 0.f, 0.f, 0.f};
       const float neg_m = -m_used;
 #pragma unroll
-      for (int k = 0; k < 128; ++k) {
+      for (int k = 0; k < 64; ++k) {
         const float pk = ex2(fmaf(__uint_as_float(s[k]), kLog2e, neg_m));
-        sum += pk;
+        sum4[k & 3] += pk;
         s[k] = __float_as_uint(pk);
       }
-      l += sum;
+      l += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
       if (TF32) {
+        // the tensor core drops the 13 low mantissa bits of a tf32 operand: +0x1000 first = round to nearest
 #pragma unroll
-        for (int k = 0; k < 128; ++k) s[k] = f32_to_tf32_rna(__uint_as_float(s[k]));
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4)
-          tmem_st32(tmem_S(b) + lane_addr + q4 * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[q4 * 32]));
+        for (int k = 0; k < 64; ++k) s[k] += 0x1000u;
+        tmem_st32(tmem_S(b) + lane_addr + wg * 64, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+        tmem_st32(tmem_S(b) + lane_addr + wg * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
       } else {
 #pragma unroll
-        for (int k = 0; k < 64; ++k) s[k] = pack_bf16x2(__uint_as_float(s[2 * k]), __uint_as_float(s[2 * k + 1]));
-#pragma unroll
-        for (int q4 = 0; q4 < 2; ++q4)
-          tmem_st32(tmem_S(b) + lane_addr + q4 * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[q4 * 32]));
+        for (int k = 0; k < 32; ++k) s[k] = pack_bf16x2(__uint_as_float(s[2 * k]), __uint_as_float(s[2 * k + 1]));
+        tmem_st32(tmem_S(b) + lane_addr + wg * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
       }
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(&p_full[b]);
     }
-    // ---- epilogue
+    // ---- epilogue: total row sum = both halves
+    // (the exchange buffer of the other parity was last read two tiles ago: free)
+    const int xb = (NT & 1);
+    xch[xb][wg][row] = l;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    l += xch[xb][wg ^ 1][row];
     mbar_wait(&pv_done[(NT - 1) & 1], ((NT - 1) >> 1) & 1);
     tc_fence_after();
     const float inv_l = 1.f / l;
     const int i = i_tile * BM + row;
     const float m_i = p.mask ? p.mask[(int64_t)n * p.S + i] : 0.f;
     const float alpha0 = p.a0 ? *p.a0 : 1.f, alpha1 = p.a1 ? *p.a1 : 1.f;
-    if (p.lse && blockIdx.z == 0) p.lse[(int64_t)n * p.S + i] = (m_used + log2f(l)) * 0.6931471805599453f;
-    for (int c0 = 0; c0 < p.cv_tile; c0 += 32) {
+    if (p.lse && blockIdx.z == 0 && wg == 0) p.lse[(int64_t)n * p.S + i] = (m_used + log2f(l)) * 0.6931471805599453f;
+    for (int ck = wg; ck < n_chunks; ck += 2) {
+      const int c0 = ck * 32;
       uint32_t o[32];
       tmem_ld32(tmem_O + lane_addr + c0, o);
       tc_wait_ld();
@@ -352,10 +376,13 @@ __global__ void __launch_bounds__(256) conv1x1_kernel(const TI* __restrict__ x, 
       if (s >= S) continue;
       float v = acc[a][b] + bo;
       if (OUT_QT) {
+        // Qt row = [hi(dpad)] or, with SPLIT (= ROUND_TF32 slot of the template), [hi(dpad) | lo(dpad)]
         if (o < dpad) {
           if (o >= Cout) v = 0.f;
-          if (ROUND_TF32) v = __uint_as_float(f32_to_tf32_rna(v));
-          y[((int64_t)n * S + s) * dpad + o] = from_f32<TO>(v);
+          const int64_t rowlen = ROUND_TF32 ? 2 * dpad : dpad;
+          const TO hi = from_f32<TO>(v);
+          y[((int64_t)n * S + s) * rowlen + o] = hi;
+          if (ROUND_TF32) y[((int64_t)n * S + s) * rowlen + dpad + o] = from_f32<TO>(v - to_f32<TO>(hi));
         }
       } else if (o < Cout) {
         y[((int64_t)n * Cout + o) * S + s] = from_f32<TO>(v);
@@ -405,18 +432,24 @@ __global__ void __launch_bounds__(256) pack_values_kernel(const TI* __restrict__
 }
 
 // attn[n, i, j] = exp(q_i . q_j - lse_i) from the staged Qt (opt-in materialisation, base_function.py:448)
-template <typename TQ>
-__global__ void __launch_bounds__(256) attn_materialize_kernel(const TQ* __restrict__ qt, const float* __restrict__ lse,
-                                                               float* __restrict__ attn, int S, int dpad) {
+__global__ void __launch_bounds__(256) attn_materialize_kernel(const __nv_bfloat16* __restrict__ qt,
+                                                               const float* __restrict__ lse, float* __restrict__ attn,
+                                                               int S, int dpad, int split) {
   extern __shared__ float sq[];  // 16 query rows x dpad
   const int n = blockIdx.y, i0 = blockIdx.x * 16;
-  const TQ* qn = qt + (int64_t)n * S * dpad;
-  for (int t = threadIdx.x; t < 16 * dpad; t += 256) sq[t] = to_f32<TQ>(qn[(int64_t)i0 * dpad + t]);
+  const int rowlen = dpad * (1 + split);
+  const __nv_bfloat16* qn = qt + (int64_t)n * S * rowlen;
+  auto qval = [&](int64_t row, int k) {
+    float v = __bfloat162float(qn[row * rowlen + k]);
+    if (split) v += __bfloat162float(qn[row * rowlen + dpad + k]);
+    return v;
+  };
+  for (int t = threadIdx.x; t < 16 * dpad; t += 256) sq[t] = qval(i0 + t / dpad, t % dpad);
   __syncthreads();
   for (int j = threadIdx.x; j < S; j += 256) {
     float acc[16] = {};
     for (int k = 0; k < dpad; ++k) {
-      const float kv = to_f32<TQ>(qn[(int64_t)j * dpad + k]);
+      const float kv = qval(j, k);
 #pragma unroll
       for (int r = 0; r < 16; ++r) acc[r] = fmaf(sq[r * dpad + k], kv, acc[r]);
     }
@@ -427,7 +460,7 @@ __global__ void __launch_bounds__(256) attn_materialize_kernel(const TQ* __restr
 }
 
 struct AttnPlan {
-  int dpad, d_atoms, cv_tile, k_stages, v_stages, esz;
+  int dpad, d_atoms, split, cv_tile, k_stages, v_stages, esz;  // esz: element size of the V / P operands
   int64_t qt_bytes, vcat_bytes;
   size_t smem;
 };
@@ -438,29 +471,29 @@ int make_plan(int N, int d, int C0, int C1, int S, int mma, AttnPlan* pl) {
   FMI_REQUIRE(S >= BN && S % BN == 0, "attn: S=%d must be a positive multiple of %d", S, BN);
   FMI_REQUIRE(C0 % 32 == 0 && C1 % 32 == 0, "attn: value channel counts (%d, %d) must be multiples of 32", C0, C1);
   const int esz = mma == FMI_MMA_TF32 ? 4 : 2;
-  const int epa = ATOM_BYTES / esz;
   pl->esz = esz;
-  pl->dpad = (d + epa - 1) / epa * epa;
-  pl->d_atoms = pl->dpad / epa;
+  pl->split = mma == FMI_MMA_TF32 ? 1 : 0;  // fp32 contract: logits from [hi | lo] bf16 pairs
+  pl->dpad = (d + 63) / 64 * 64;
+  pl->d_atoms = pl->dpad / 64;
   const int Cv = C0 + C1;
   pl->cv_tile = Cv <= CV_MAX ? Cv : CV_MAX;
   FMI_REQUIRE(Cv % pl->cv_tile == 0 && pl->cv_tile % 16 == 0, "attn: C0+C1=%d must be <= 256 or a multiple of 256", Cv);
-  const int q_tile = pl->d_atoms * BM * ATOM_BYTES;
+  const int q_tile = pl->d_atoms * (1 + pl->split) * BM * ATOM_BYTES;
   const int v_chunk = pl->cv_tile * ATOM_BYTES;
   pl->k_stages = (3 * q_tile + 4 * v_chunk <= kSmemBudget) ? 2 : 1;
   int vs = (kSmemBudget - (1 + pl->k_stages) * q_tile) / v_chunk;
   if (vs > 8) vs = 8;
   FMI_REQUIRE(vs >= 2, "attn: d=%d too large for shared memory", d);
   pl->v_stages = vs;
-  pl->smem = (size_t)(1 + pl->k_stages) * q_tile + (size_t)vs * v_chunk + 1024;
-  pl->qt_bytes = ((int64_t)N * S * pl->dpad * esz + 1023) / 1024 * 1024;
+  pl->smem = (size_t)(1 + pl->k_stages) * q_tile + (size_t)vs * v_chunk;
+  pl->qt_bytes = ((int64_t)N * S * pl->dpad * (1 + pl->split) * 2 + 1023) / 1024 * 1024;
   pl->vcat_bytes = ((int64_t)N * Cv * S * esz + 1023) / 1024 * 1024;
   return FMI_OK;
 }
 
 template <typename TI>
 int launch_conv1x1_any(const void* x, const float* w, const float* b, void* y, int N, int Cin, int Cout, int S, int dpad,
-                       int out_mode /*0 NCHW same type, 1 Qt bf16, 2 Qt tf32*/, cudaStream_t st) {
+                       int out_mode /*0 NCHW same type, 1 Qt bf16 [hi], 2 Qt bf16 [hi | lo]*/, cudaStream_t st) {
   const int o_extent = out_mode == 0 ? Cout : dpad;
   dim3 grid((S + CT_S - 1) / CT_S, (o_extent + CT_O - 1) / CT_O, N);
   if (out_mode == 0)
@@ -468,8 +501,8 @@ int launch_conv1x1_any(const void* x, const float* w, const float* b, void* y, i
   else if (out_mode == 1)
     conv1x1_kernel<TI, __nv_bfloat16, true, false><<<grid, 256, 0, st>>>((const TI*)x, w, b, (__nv_bfloat16*)y, Cin, Cout, S, dpad);
   else
-    conv1x1_kernel<TI, float, true, true><<<grid, 256, 0, st>>>((const TI*)x, w, b, (float*)y, Cin, Cout, S, dpad);
-  return fmi_check_cuda(cudaGetLastError(), "conv1x1 launch");
+    conv1x1_kernel<TI, __nv_bfloat16, true, true><<<grid, 256, 0, st>>>((const TI*)x, w, b, (__nv_bfloat16*)y, Cin, Cout, S, dpad);
+  return fmi_launched("conv1x1");
 }
 
 template <typename TI>
@@ -480,7 +513,7 @@ int launch_pack_values(const void* v0, const void* v1, void* vcat, int N, int C0
     pack_values_kernel<TI, float, true><<<grid, 256, 0, st>>>((const TI*)v0, (const TI*)v1, (float*)vcat, C0, C1, S, total4);
   else
     pack_values_kernel<TI, __nv_bfloat16, false><<<grid, 256, 0, st>>>((const TI*)v0, (const TI*)v1, (__nv_bfloat16*)vcat, C0, C1, S, total4);
-  return fmi_check_cuda(cudaGetLastError(), "pack_values launch");
+  return fmi_launched("pack_values");
 }
 
 template <bool TF32, typename T>
@@ -488,12 +521,16 @@ int launch_attn(const CUtensorMap& mq, const CUtensorMap& mv, const AttnParams& 
   auto kern = attn_fwd_kernel<TF32, T>;
   static bool attr_set = false;  // per template instantiation
   if (!attr_set) {
-    FMI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
+    cudaFuncAttributes fa;
+    FMI_CUDA(cudaFuncGetAttributes(&fa, kern));
+    FMI_REQUIRE((int)fa.sharedSizeBytes <= kStaticSmem, "attn_fwd: static shared memory grew to %d bytes", (int)fa.sharedSizeBytes);
+    FMI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     attr_set = true;
   }
   dim3 grid(prm.S / BM, prm.N, (prm.C0 + prm.C1) / prm.cv_tile);
+  FmiProfScope prof(0, st);
   kern<<<grid, kAttnThreads, pl.smem, st>>>(mq, mv, prm);
-  return fmi_check_cuda(cudaGetLastError(), "attn_fwd launch");
+  return fmi_launched("attn_fwd");
 }
 
 }  // namespace
@@ -553,10 +590,11 @@ extern "C" int fmi_attn_fwd(const void* x, const float* wq, const float* bq, con
   const CUtensorMapDataType dt = tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   const uint32_t epa = ATOM_BYTES / pl.esz;
   {
-    uint64_t dims[2] = {(uint64_t)pl.dpad, (uint64_t)N * S};
-    uint64_t str[1] = {(uint64_t)pl.dpad * pl.esz};
-    uint32_t box[2] = {epa, (uint32_t)BM};
-    int e = make_tensor_map(&mq, dt, 2, qt, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    const uint64_t qrow = (uint64_t)pl.dpad * (1 + pl.split);  // bf16 elements per Qt row
+    uint64_t dims[2] = {qrow, (uint64_t)N * S};
+    uint64_t str[1] = {qrow * 2};
+    uint32_t box[2] = {64, (uint32_t)BM};
+    int e = make_tensor_map(&mq, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, qt, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
     FMI_REQUIRE(e == 0, "attn_fwd: cuTensorMapEncodeTiled(Qt) failed (%d)", e);
   }
   {
@@ -567,7 +605,7 @@ extern "C" int fmi_attn_fwd(const void* x, const float* wq, const float* bq, con
     FMI_REQUIRE(e == 0, "attn_fwd: cuTensorMapEncodeTiled(Vcat) failed (%d)", e);
   }
   AttnParams prm;
-  prm.N = N; prm.S = S; prm.C0 = C0; prm.C1 = C1; prm.cv_tile = pl.cv_tile; prm.d_atoms = pl.d_atoms;
+  prm.N = N; prm.S = S; prm.C0 = C0; prm.C1 = C1; prm.cv_tile = pl.cv_tile; prm.d_atoms = pl.d_atoms; prm.split = pl.split;
   prm.k_stages = pl.k_stages; prm.v_stages = pl.v_stages;
   prm.v0 = v0; prm.v1 = v1; prm.mask = mask; prm.a0 = a0; prm.a1 = a1; prm.b0 = b0; prm.b1 = b1;
   prm.masked0 = masked0; prm.masked1 = masked1;
@@ -588,9 +626,7 @@ extern "C" int fmi_attn_materialize(const void* workspace, const float* lse, flo
   FMI_REQUIRE(workspace && lse && attn, "attn_materialize: null pointer");
   dim3 grid(S / 16, N);
   size_t smem = (size_t)16 * pl.dpad * sizeof(float);
-  if (mma == FMI_MMA_TF32)
-    attn_materialize_kernel<float><<<grid, 256, smem, (cudaStream_t)stream>>>((const float*)workspace, lse, attn, S, pl.dpad);
-  else
-    attn_materialize_kernel<__nv_bfloat16><<<grid, 256, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)workspace, lse, attn, S, pl.dpad);
-  return fmi_check_cuda(cudaGetLastError(), "attn_materialize launch");
+  attn_materialize_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)workspace, lse, attn, S, pl.dpad,
+                                                                      pl.split);
+  return fmi_launched("attn_materialize");
 }

@@ -184,7 +184,7 @@ int launch_fwd(const void* x, const void* b, const void* ref, void* y, int code,
     int grid = (int)imin64((n_tail + 255) / 256, (int64_t)FMI_NUM_SMS * 16);
     bias_act_scalar_kernel<T, BT><<<grid, 256, 0, st>>>(xp, bp, rp, yp, code, alpha, scale, tail_begin, size_x, step_b, size_b);
   }
-  return fmi_check_cuda(cudaGetLastError(), "fused_bias_act launch");
+  return fmi_launched("fused_bias_act");
 }
 
 template <typename T>
@@ -205,7 +205,7 @@ int launch_bwd(const void* grad_out, const void* out, void* grad_in, float* grad
     bias_act_bwd_warp_kernel<T><<<grid, 256, 0, st>>>((const T*)grad_out, (const T*)out, (T*)grad_in, grad_bias, alpha,
                                                         scale, rows, inner, size_b);
   }
-  return fmi_check_cuda(cudaGetLastError(), "bias_act_bwd launch");
+  return fmi_launched("bias_act_bwd");
 }
 
 }  // namespace

@@ -15,6 +15,20 @@
 void fmi_set_error(const char* fmt, ...);
 int fmi_check_cuda(cudaError_t e, const char* what);
 
+// Called right after every kernel launch: counts it (fmi_kernel_launch_count) and surfaces launch errors.
+int fmi_launched(const char* kernel_name);
+
+// Optional CUDA-event timing of the dominant kernels on their launch stream (fmi_profile_enable / _collect):
+// kind 0 = attention main kernel, kind 1 = modulated-conv implicit GEMM.
+struct FmiProfScope {
+  FmiProfScope(int kind, cudaStream_t st);
+  ~FmiProfScope();
+  int kind_;
+  cudaStream_t st_;
+  cudaEvent_t e0_, e1_;
+  bool on_;
+};
+
 #define FMI_REQUIRE(cond, ...)      \
   do {                              \
     if (!(cond)) {                  \

@@ -148,7 +148,7 @@ int launch_composite(const void* a, const void* b, const float* mask, void* o0, 
     composite_kernel<T, 1, MODE><<<grid, 256, 0, st>>>((const T*)a, (const T*)b, mask, (T*)o0, (T*)o1, N, C, H, W, Hm,
                                                         Wm, sh, sw);
   }
-  return fmi_check_cuda(cudaGetLastError(), "composite launch");
+  return fmi_launched("composite");
 }
 
 }  // namespace
@@ -160,7 +160,7 @@ extern "C" int fmi_scale_mask(const float* mask, float* out, int N, int Hm, int 
   int64_t total = (int64_t)N * H * W;
   int grid = (int)imin64((total + 255) / 256, (int64_t)FMI_NUM_SMS * 16);
   scale_mask_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(mask, out, N, Hm, Wm, H, W, ac_scale(Hm, H), ac_scale(Wm, W));
-  return fmi_check_cuda(cudaGetLastError(), "scale_mask launch");
+  return fmi_launched("scale_mask");
 }
 
 extern "C" int fmi_composite(const void* src, const void* ref, const float* mask, void* out, int N, int C, int H,

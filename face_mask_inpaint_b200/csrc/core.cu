@@ -19,6 +19,67 @@ int fmi_check_cuda(cudaError_t e, const char* what) {
   return FMI_ECUDA;
 }
 
+// ---- launch accounting and optional CUDA-event profiling of the dominant kernels ------------------------------
+#include <atomic>
+#include <mutex>
+#include <utility>
+#include <vector>
+
+static std::atomic<long long> g_launches{0};
+static std::atomic<int> g_prof_on{0};
+static std::mutex g_prof_mu;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events[2];
+
+int fmi_launched(const char* kernel_name) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) return FMI_OK;
+  fmi_set_error("launch of %s failed: CUDA error %d (%s)", kernel_name, (int)e, cudaGetErrorString(e));
+  return FMI_ECUDA;
+}
+
+FmiProfScope::FmiProfScope(int kind, cudaStream_t st) : kind_(kind), st_(st), e0_(nullptr), e1_(nullptr), on_(false) {
+  if (!g_prof_on.load(std::memory_order_relaxed) || kind < 0 || kind > 1) return;
+  if (cudaEventCreate(&e0_) != cudaSuccess || cudaEventCreate(&e1_) != cudaSuccess) return;
+  on_ = true;
+  cudaEventRecord(e0_, st_);
+}
+FmiProfScope::~FmiProfScope() {
+  if (!on_) return;
+  cudaEventRecord(e1_, st_);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_events[kind_].emplace_back(e0_, e1_);
+}
+
+extern "C" long long fmi_kernel_launch_count(void) { return g_launches.load(); }
+
+extern "C" int fmi_profile_enable(int on) {
+  g_prof_on.store(on ? 1 : 0);
+  return FMI_OK;
+}
+
+// Synchronises on the recorded events; returns the summed duration (ms) and number of launches of `kind`.
+extern "C" int fmi_profile_collect(int kind, double* total_ms, int* launches) {
+  FMI_REQUIRE(kind >= 0 && kind <= 1 && total_ms && launches, "profile_collect: bad arguments");
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  double sum = 0;
+  int n = 0;
+  for (auto& pr : g_prof_events[kind]) {
+    float ms = 0.f;
+    cudaEventSynchronize(pr.second);
+    if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) {
+      sum += ms;
+      ++n;
+    }
+    cudaEventDestroy(pr.first);
+    cudaEventDestroy(pr.second);
+  }
+  g_prof_events[kind].clear();
+  *total_ms = sum;
+  *launches = n;
+  return FMI_OK;
+}
+
 extern "C" int fmi_version(void) { return 100; }
 
 extern "C" const char* fmi_last_error(void) { return g_err; }

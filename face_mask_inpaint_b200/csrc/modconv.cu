@@ -423,8 +423,9 @@ int launch_gemm_class(const CUtensorMap& mx, const CUtensorMap& mw, ConvGemmPara
   TilePlan tp = pick_tile(p.Mh, p.Mw);
   p.TH = tp.TH; p.TW = tp.TW; p.tiles_w = tp.tiles_w;
   dim3 grid(tp.tiles_h * tp.tiles_w, p.O / p.n_tile, p.B);
+  FmiProfScope prof(1, st);
   kern<<<grid, kGemmThreads, smem, st>>>(mx, mw, p);
-  return fmi_check_cuda(cudaGetLastError(), "modconv_gemm launch");
+  return fmi_launched("modconv_gemm");
 }
 
 }  // namespace
@@ -444,7 +445,7 @@ extern "C" int fmi_nchw_to_nhwc(const void* x, void* y, int B, int C, int H, int
     if (mma == FMI_MMA_TF32) nchw_to_nhwc_kernel<T, float, true><<<grid, 256, 0, st>>>((const T*)x, (float*)y, C, HW, bs);
     else nchw_to_nhwc_kernel<T, __nv_bfloat16, false><<<grid, 256, 0, st>>>((const T*)x, (__nv_bfloat16*)y, C, HW, bs);
   });
-  return fmi_check_cuda(cudaGetLastError(), "nchw_to_nhwc launch");
+  return fmi_launched("nchw_to_nhwc");
 }
 
 extern "C" int fmi_nhwc_to_nchw(const void* x, void* y, int B, int C, int H, int W, int mma, int dtype, void* stream) {
@@ -458,7 +459,7 @@ extern "C" int fmi_nhwc_to_nchw(const void* x, void* y, int B, int C, int H, int
     if (mma == FMI_MMA_TF32) nhwc_to_nchw_kernel<float, T><<<grid, 256, 0, st>>>((const float*)x, (T*)y, C, HW);
     else nhwc_to_nchw_kernel<__nv_bfloat16, T><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (T*)y, C, HW);
   });
-  return fmi_check_cuda(cudaGetLastError(), "nhwc_to_nchw launch");
+  return fmi_launched("nhwc_to_nchw");
 }
 
 extern "C" int fmi_style_modulation(const float* latent, int64_t latent_row_stride, const float* mod_weight,
@@ -469,7 +470,7 @@ extern "C" int fmi_style_modulation(const float* latent, int64_t latent_row_stri
   if (grid > FMI_NUM_SMS * 8) grid = FMI_NUM_SMS * 8;
   style_mod_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(latent, latent_row_stride, mod_weight, mod_bias, s, B, K, I,
                                                             1.0f / sqrtf((float)K));
-  return fmi_check_cuda(cudaGetLastError(), "style_modulation launch");
+  return fmi_launched("style_modulation");
 }
 
 extern "C" int64_t fmi_modconv_weight_bytes(int B, int I, int O, int ksize, int mma) {
@@ -487,7 +488,7 @@ extern "C" int fmi_modconv_weight_prep(const float* weight, const float* s, void
   cudaStream_t st = (cudaStream_t)stream;
   if (mma == FMI_MMA_TF32) weight_prep_kernel<float, true><<<grid, 256, 0, st>>>(weight, s, (float*)wp, I, O, T, scale, demodulate);
   else weight_prep_kernel<__nv_bfloat16, false><<<grid, 256, 0, st>>>(weight, s, (__nv_bfloat16*)wp, I, O, T, scale, demodulate);
-  return fmi_check_cuda(cudaGetLastError(), "modconv_weight_prep launch");
+  return fmi_launched("modconv_weight_prep");
 }
 
 extern "C" int64_t fmi_styled_conv_workspace_bytes(int B, int O, int H, int W, int upsample, int mma) {
@@ -590,7 +591,7 @@ extern "C" int fmi_styled_conv_nhwc(const void* x, const void* wp, void* y, cons
     blur_act_nhwc_kernel<__nv_bfloat16, 8><<<grid, 256, 0, st>>>((const __nv_bfloat16*)workspace, (__nv_bfloat16*)y, blur_k,
                                                                  noise, noise_batched, noise_w, act_bias, B, O, OH, OW,
                                                                  act, p.slope, p.gain);
-  return fmi_check_cuda(cudaGetLastError(), "blur_act launch");
+  return fmi_launched("blur_act");
 }
 
 extern "C" int fmi_torgb_nhwc(const void* x, const float* weight, const float* s, const float* bias, const float* skip,
@@ -618,5 +619,5 @@ extern "C" int fmi_torgb_nhwc(const void* x, const float* weight, const float* s
     torgb_nhwc_kernel<float, 4><<<grid, 256, smem, st>>>((const float*)x, weight, s, bias, skip, blur_k, rgb, B, I, H, W, scale, lanes);
   else
     torgb_nhwc_kernel<__nv_bfloat16, 8><<<grid, 256, smem, st>>>((const __nv_bfloat16*)x, weight, s, bias, skip, blur_k, rgb, B, I, H, W, scale, lanes);
-  return fmi_check_cuda(cudaGetLastError(), "torgb launch");
+  return fmi_launched("torgb");
 }

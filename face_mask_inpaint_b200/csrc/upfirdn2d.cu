@@ -191,5 +191,5 @@ extern "C" int fmi_upfirdn2d(const void* x, const float* kernel, void* y, int64_
       upfirdn2d_generic_kernel<T><<<grid, 256, 0, st>>>((const T*)x, kernel, (T*)y, p);
     }
   });
-  return fmi_check_cuda(cudaGetLastError(), "upfirdn2d launch");
+  return fmi_launched("upfirdn2d");
 }

@@ -40,6 +40,14 @@ int fmi_version(void);
 const char* fmi_last_error(void);
 /* 0 when the current CUDA device can run these kernels (compute capability 10.x). */
 int fmi_device_check(void);
+/* Number of kernels this library has launched since it was loaded (all entry points). */
+long long fmi_kernel_launch_count(void);
+/* Optional CUDA-event timing of the dominant kernels on their own launch stream:
+ *   kind 0 = attention main kernel, kind 1 = modulated-conv implicit GEMM.
+ * fmi_profile_collect synchronises on the recorded events, returns their summed duration (ms) and
+ * count, and clears the record. Off by default (no events are created). */
+int fmi_profile_enable(int on);
+int fmi_profile_collect(int kind, double* total_ms, int* launches);
 
 /* ---------------------------------------------------------------------------------------------
  * a5  fused bias + activation.

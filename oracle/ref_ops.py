@@ -270,3 +270,20 @@ def generator_synthesis(sd: dict, latent: torch.Tensor, noises: Optional[Sequenc
         skip = to_rgb(out, latent[:, i + 2], *_rgb_args(sd, f'to_rgbs.{blk}'), skip=skip)
         i += 2
     return skip
+
+
+# --------------------------------------------------------------------------------------------
+# bounded samples of the attention workload for the CPU baseline legs of bench.py
+# --------------------------------------------------------------------------------------------
+def example_guided_attention_rows(src_mask, src_feature, ref_feature, conv_weight, rows: torch.Tensor):
+    """modules/example_guided_att.py:21-36 restricted to the query pixels `rows` (a 1-D index tensor): the same
+    arithmetic per output pixel (q-conv for all pixels, softmax over all S keys, both value products, the masked
+    blend), only fewer rows of the S x S map. Returns [N, 2C, len(rows)]."""
+    n, c, h, w = src_feature.shape
+    query = F.conv2d(src_feature, conv_weight).reshape(n, -1, h * w)                 # :27-28
+    att = torch.softmax(query[:, :, rows].permute(0, 2, 1) @ query, dim=-1)           # :30   [N, R, S]
+    src_att = src_feature.reshape(n, c, -1) @ att.permute(0, 2, 1)                    # :18,:31
+    ref_att = ref_feature.reshape(n, c, -1) @ att.permute(0, 2, 1)                    # :18,:32
+    m = src_mask.reshape(n, 1, -1)[:, :, rows]
+    flow = (1 - m) * ref_att + m * ref_feature.reshape(n, c, -1)[:, :, rows]          # :34
+    return torch.cat([flow, src_att], dim=1)                                          # :36

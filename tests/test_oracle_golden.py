@@ -1,0 +1,117 @@
+"""Pins the CPU oracle (oracle/ref_ops.py) against outputs of the reference's OWN modules, recorded by
+tests/golden/make_golden.py from /root/reference (the reference ships no tests or golden vectors of its own).
+CPU only; fp32 vs fp32 with the same ATen kernels underneath, so agreement is to rounding (1e-6)."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import ref_ops as O
+
+GOLD = Path(__file__).resolve().parent / "golden"
+
+
+def load(name):
+    return {k: torch.from_numpy(v) for k, v in np.load(GOLD / name).items()}
+
+
+def test_example_guided_attention_matches_reference():
+    g = load("attention.npz")
+    for tag, has_oc in [("ega_plain", False), ("ega_outconv", True)]:
+        got = O.example_guided_attention(g[f"{tag}.mask"], g[f"{tag}.src"], g[f"{tag}.ref"], g[f"{tag}.conv_w"],
+                                         g.get(f"{tag}.oc_w") if has_oc else None,
+                                         g.get(f"{tag}.oc_b") if has_oc else None)
+        assert rel_err(got, g[f"{tag}.out"]) <= 1e-6
+
+
+def test_auto_attn_matches_reference():
+    g = load("attention.npz")
+    out, _, attn = O.auto_attn(g["auto.x"], g["auto.q_w"], g["auto.q_b"], g["auto.gamma"], return_attention=True)
+    assert rel_err(out, g["auto.out"]) <= 1e-6
+    assert rel_err(attn, g["auto.attn"]) <= 1e-6
+    out, ctx, _ = O.auto_attn(g["auto.x"], g["auto.q_w"], g["auto.q_b"], g["auto.gamma"], g["auto.pre"], g["auto.mask"],
+                              g["auto.alpha"])
+    assert rel_err(torch.cat([out, ctx], 1), g["auto.cat"]) <= 1e-6
+
+
+@pytest.mark.parametrize("tag", ["blur", "blur_bwd", "up", "down", "k3", "odd", "crop"])
+def test_upfirdn2d_matches_reference_native(tag):
+    g = load("upfirdn2d_composite.npz")
+    up, down, p0, p1 = [int(v) for v in g[f"ufd.{tag}.cfg"]]
+    got = O.upfirdn2d(g[f"ufd.{tag}.x"], g[f"ufd.{tag}.k"], up=up, down=down, pad=(p0, p1))
+    assert got.shape == g[f"ufd.{tag}.y"].shape
+    assert rel_err(got, g[f"ufd.{tag}.y"]) <= 1e-6
+
+
+def test_upfirdn2d_minor_dim_matches_reference_native():
+    g = load("upfirdn2d_composite.npz")
+    got = O.upfirdn2d_native(g["ufd.minor.x"], g["ufd.minor.k"], 2, 1, 1, 2, 1, 2, 0, 1)
+    assert rel_err(got, g["ufd.minor.y"]) <= 1e-6
+
+
+def test_upfirdn2d_backward_restatement_is_the_adjoint():
+    """op/upfirdn2d.py:17-57: the gradient op equals autograd through the forward restatement."""
+    g = torch.Generator().manual_seed(0)
+    for up, down, pad, taps in [(1, 1, (1, 1), [1, 3, 3, 1]), (2, 1, (2, 1), [1, 3, 3, 1]), (1, 2, (1, 1), [1, 3, 3, 1])]:
+        x = torch.randn(2, 3, 8, 8, generator=g, dtype=torch.float64, requires_grad=True)
+        k = (O.make_kernel(taps) * up ** 2).double()
+        y = O.upfirdn2d(x, k, up=up, down=down, pad=pad)
+        go = torch.randn(y.shape, generator=g, dtype=torch.float64)
+        y.backward(go)
+        assert rel_err(O.upfirdn2d_backward(go, k, up, down, pad, x.shape), x.grad) <= 1e-12
+
+
+@pytest.mark.parametrize("tag", ["c32", "c16", "c7x9"])
+def test_composite_matches_reference(tag):
+    g = load("upfirdn2d_composite.npz")
+    h, w = g[f"comp.{tag}.src"].shape[-2:]
+    assert rel_err(O.scale_img(g["comp.mask"], (h, w)), g[f"comp.{tag}.m"]) <= 1e-6
+    assert rel_err(O.composite(g[f"comp.{tag}.src"], g[f"comp.{tag}.ref"], g["comp.mask"]), g[f"comp.{tag}.out"]) <= 1e-6
+
+
+@pytest.mark.parametrize("tag,up", [("plain", False), ("up", True)])
+def test_styled_conv_matches_reference(tag, up):
+    g = load("stylegan2_layers.npz")
+    sd = {k[len(f"sc.{tag}.sd."):]: v for k, v in g.items() if k.startswith(f"sc.{tag}.sd.")}
+    conv = O.modulated_conv2d(g[f"sc.{tag}.x"], g[f"sc.{tag}.style"], sd["conv.weight"], sd["conv.modulation.weight"],
+                              sd["conv.modulation.bias"], True, up)
+    assert rel_err(conv, g[f"sc.{tag}.conv"]) <= 1e-5
+    out = O.styled_conv(g[f"sc.{tag}.x"], g[f"sc.{tag}.style"], sd["conv.weight"], sd["conv.modulation.weight"],
+                        sd["conv.modulation.bias"], sd["noise.weight"], sd["activate.bias"], g[f"sc.{tag}.noise"],
+                        upsample=up)
+    assert rel_err(out, g[f"sc.{tag}.out"]) <= 1e-5
+
+
+def test_to_rgb_matches_reference():
+    g = load("stylegan2_layers.npz")
+    sd = {k[len("rgb.sd."):]: v for k, v in g.items() if k.startswith("rgb.sd.")}
+    args = (sd["conv.weight"], sd["conv.modulation.weight"], sd["conv.modulation.bias"], sd["bias"])
+    assert rel_err(O.to_rgb(g["rgb.x"], g["rgb.style"], *args, skip=g["rgb.skip"]), g["rgb.out"]) <= 1e-5
+    assert rel_err(O.to_rgb(g["rgb.x"], g["rgb.style"], *args), g["rgb.out_noskip"]) <= 1e-5
+
+
+def test_generator_synthesis_matches_reference():
+    """Whole StyleGAN2 synthesis at 32x32; parameters are rebuilt from the seed (tests/golden_util.py) — the
+    reference loaded the same state_dict with strict=True when the golden was made."""
+    from golden_util import build_generator32
+    g = load("generator32.npz")
+    torch.set_num_threads(max(torch.get_num_threads(), 4))
+    gen = build_generator32()
+    sd = {k: v.detach() for k, v in gen.state_dict().items()}
+    got = O.generator_synthesis(sd, g["latent"])
+    assert rel_err(got, g["image"]) <= 1e-5
+
+
+def test_fused_bias_act_semantics():
+    """op/fused_bias_act_kernel.cu:18-49 has no CPU-runnable reference: check the restatement's switch table."""
+    x = torch.tensor([[-2.0, 3.0], [0.5, -0.25]])
+    b = torch.tensor([1.0, -1.0])
+    r = torch.tensor([[1.0, -1.0], [-1.0, 1.0]])
+    assert torch.allclose(O.fused_bias_act(x, b, None, 3, 0, 0.2, 2.0), torch.tensor([[-0.4, 4.0], [3.0, -0.5]]))
+    assert torch.allclose(O.fused_bias_act(x, None, r, 3, 1, 0.2, 2.0), torch.tensor([[-4.0, 1.2], [0.2, -0.5]]))
+    assert torch.allclose(O.fused_bias_act(x, b, r, 3, 2, 0.2, 2.0), torch.zeros(2, 2))
+    assert torch.allclose(O.fused_bias_act(x, b, None, 1, 0, 0.2, 2.0), (x + b) * 2)
+    gi, gb = O.fused_leaky_relu_backward(torch.ones(2, 2, 1, 1), torch.tensor([[[[1.0]], [[-1.0]]], [[[-1.0]], [[1.0]]]]))
+    assert torch.allclose(gb, torch.tensor([1.2 * 2 ** 0.5, 1.2 * 2 ** 0.5]))

@@ -1,0 +1,13 @@
+#!/bin/bash
+# tests + ncu launch list + one full capture of the attention kernel (same command run plain first, per the recipe)
+mkdir -p gpurun_out
+python __graft_entry__.py smoke 2>&1 | tail -3 | tee gpurun_out/smoke.log
+timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
+tail -6 gpurun_out/pytest_gpu.log
+CMD="python bench.py --steps 3 --warmup 3"
+$CMD > gpurun_out/plain.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_attn.csv $CMD > gpurun_out/ncu1.log 2>&1
+$CMD > gpurun_out/plain2.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:attn_fwd -s 3 -c 2 -f -o gpurun_out/prof_attn $CMD > gpurun_out/ncu2.log 2>&1
+tail -3 gpurun_out/ncu2.log
+ls -la gpurun_out/
