@@ -1,0 +1,218 @@
+"""Install the sm_100a hot path over an importable copy of the reference repository, so its scripts
+(PICNet_inference.py, psp_inference.py, train_reference_fill.py, train_psp.py) run unchanged.
+
+    import face_mask_inpaint_b200.patch as patch
+    patch.install("/path/to/face_mask_inpaint")      # before the reference's `modules.*` are imported (or after)
+
+What is replaced:
+  * package `modules.psp.stylegan2.op` (+ `.fused_act`, `.upfirdn2d`): pre-seeded in sys.modules, so the reference's
+    import-time JIT `load()` of its two CUDA extensions (op/fused_act.py:9-15, op/upfirdn2d.py:8-14) never runs;
+  * classes `ExampleGuidedAttention` (modules/example_guided_att.py), `Auto_Attn`
+    (modules/pluralistic_model/base_function.py) and `ModulatedConv2d`, `StyledConv`, `ToRGB`, `Blur`, `Upsample`,
+    `Downsample`, `EqualLinear`, `Generator` (modules/psp/stylegan2/model.py) — rebound in their defining modules and in
+    every already-imported module that did `from ... import <name>`;
+  * `scale_img` and the masked source/reference blends (modules/model.py:95-99, psp_encoders.py:127-138): the two calling
+    forwards (`ReferenceFill.forward`, `GradualStyleEncoder.forward`) are replaced by equivalents that call the fused
+    compositing kernels.
+Everything else (encoders, decoder conv blocks, losses, data loading, CLI) is the reference's own code.
+"""
+from __future__ import annotations
+
+import importlib
+import sys
+import types
+
+_INSTALLED = False
+
+
+def _op_package():
+    from . import ops
+    pkg = types.ModuleType("modules.psp.stylegan2.op")
+    pkg.__path__ = []  # a package, so `from .op import x` and `import modules.psp.stylegan2.op.fused_act` resolve
+    pkg.FusedLeakyReLU = ops.FusedLeakyReLU
+    pkg.fused_leaky_relu = ops.fused_leaky_relu
+    pkg.upfirdn2d = ops.upfirdn2d
+    fa = types.ModuleType("modules.psp.stylegan2.op.fused_act")
+    fa.FusedLeakyReLU, fa.fused_leaky_relu = ops.FusedLeakyReLU, ops.fused_leaky_relu
+    fa.FusedLeakyReLUFunction = ops.FusedLeakyReLUFunction
+    fa.FusedLeakyReLUFunctionBackward = ops.FusedLeakyReLUFunctionBackward
+    uf = types.ModuleType("modules.psp.stylegan2.op.upfirdn2d")
+    uf.upfirdn2d, uf.UpFirDn2d, uf.UpFirDn2dBackward = ops.upfirdn2d, ops.UpFirDn2d, ops.UpFirDn2dBackward
+    pkg.fused_act, pkg.upfirdn2d_module = fa, uf
+    return pkg, fa, uf
+
+
+def _rebind_everywhere(name: str, old, new):
+    """Rebind `name` in every imported module whose attribute is the old object (covers `from x import name`)."""
+    for mod in list(sys.modules.values()):
+        if mod is None or not hasattr(mod, "__dict__"):
+            continue
+        if mod.__dict__.get(name) is old:
+            setattr(mod, name, new)
+
+
+def _ensure_msssim_shim():
+    try:
+        import pytorch_msssim  # noqa: F401
+        return
+    except Exception:
+        pass
+    import torch
+    import torch.nn.functional as F
+
+    def _gauss(size=11, sigma=1.5):
+        c = torch.arange(size, dtype=torch.float32) - size // 2
+        g = torch.exp(-(c ** 2) / (2 * sigma ** 2))
+        return g / g.sum()
+
+    def ssim(X, Y, data_range=255, size_average=True, **_):
+        ch = X.shape[1]
+        g = _gauss().to(X.device, X.dtype)
+        w = (g[:, None] * g[None, :]).expand(ch, 1, 11, 11).contiguous()
+        c1, c2 = (0.01 * data_range) ** 2, (0.03 * data_range) ** 2
+        mu_x, mu_y = F.conv2d(X, w, groups=ch), F.conv2d(Y, w, groups=ch)
+        sxx = F.conv2d(X * X, w, groups=ch) - mu_x ** 2
+        syy = F.conv2d(Y * Y, w, groups=ch) - mu_y ** 2
+        sxy = F.conv2d(X * Y, w, groups=ch) - mu_x * mu_y
+        m = ((2 * mu_x * mu_y + c1) * (2 * sxy + c2)) / ((mu_x ** 2 + mu_y ** 2 + c1) * (sxx + syy + c2))
+        v = m.flatten(1).mean(1)
+        return v.mean() if size_average else v
+
+    def ms_ssim(X, Y, data_range=255, size_average=True, **kw):
+        # single-scale stand-in when the image is too small for 5 scales; metric only, not on the hot path
+        return ssim(X, Y, data_range=data_range, size_average=size_average)
+
+    shim = types.ModuleType("pytorch_msssim")
+    shim.ssim, shim.ms_ssim = ssim, ms_ssim
+    sys.modules["pytorch_msssim"] = shim
+
+
+def install(reference_root: str | None = None, msssim_shim: bool = True) -> None:
+    """Idempotent. `reference_root` is prepended to sys.path when given."""
+    global _INSTALLED
+    if reference_root and reference_root not in sys.path:
+        sys.path.insert(0, reference_root)
+    if _INSTALLED:
+        return
+    from .modules import attention as my_att
+    from .modules import stylegan2 as my_sg
+
+    pkg, fa, uf = _op_package()
+    sys.modules["modules.psp.stylegan2.op"] = pkg
+    sys.modules["modules.psp.stylegan2.op.fused_act"] = fa
+    sys.modules["modules.psp.stylegan2.op.upfirdn2d"] = uf
+    if msssim_shim:
+        _ensure_msssim_shim()
+
+    ega_mod = importlib.import_module("modules.example_guided_att")
+    _rebind_everywhere("ExampleGuidedAttention", ega_mod.ExampleGuidedAttention, my_att.ExampleGuidedAttention)
+
+    bf = importlib.import_module("modules.pluralistic_model.base_function")
+    ref_resblock = bf.ResBlock
+    my_att.Auto_Attn.resblock_factory = staticmethod(
+        lambda i, o, h, nl: ref_resblock(i, o, h, norm_layer=nl, use_spect=True))
+    _rebind_everywhere("Auto_Attn", bf.Auto_Attn, my_att.Auto_Attn)
+
+    sg = importlib.import_module("modules.psp.stylegan2.model")
+    for name in ("ModulatedConv2d", "StyledConv", "ToRGB", "Blur", "Upsample", "Downsample", "EqualLinear",
+                 "NoiseInjection", "Generator"):
+        _rebind_everywhere(name, getattr(sg, name), getattr(my_sg, name))
+    _install_compositing_callers()
+    _INSTALLED = True
+
+
+def _install_compositing_callers():
+    """a7: the two callers that blend source/reference features with the resized mask get forwards that use the
+    fused kernels (ops.scale_img / ops.composite) — same signature, same results:
+      ReferenceFill.forward            modules/model.py:81-112
+      GradualStyleEncoder.forward      modules/psp/encoders/psp_encoders.py:100-152
+    Everything they call besides the blend (encoders, decoder, style blocks, FPN adds) is the reference's own code."""
+    from . import ops
+
+    model = importlib.import_module("modules.model")
+    _rebind_everywhere("scale_img", model.scale_img, _scale_img_any)
+
+    def reference_fill_forward(self, src_image, ref_image, src_mask=None, resize=True, no_prior=False):
+        if src_mask is None:
+            src_mask = self.mask_detector(src_image, mode='eval')
+        if self.encoder_type == 'drn':
+            src_dist = ref_dist = None
+            src_features, ref_features = self.src_encoder(src_image), self.ref_encoder(ref_image)
+        else:
+            src_dist, src_features = self.src_encoder(src_image)
+            ref_dist, ref_features = self.ref_encoder(ref_image)
+        full_mask = src_mask.unsqueeze(1)
+        if self.use_att:
+            enc = self.attention(_scale_img_any(full_mask, src_features.shape[-2:]), src_features, ref_features)
+        else:
+            enc = ops.composite(src_features, ref_features, full_mask)      # (1-m)*src + m*ref, m resized in-kernel
+        if self.encoder_type == 'drn' or no_prior:
+            out = self.decoder(enc)
+        else:
+            out = self.decoder(enc, z=self.decoder.get_z(src_dist, ref_dist, return_zq=not self.use_att))
+        if resize:
+            out = _scale_img_any(out, (218, 178)) if no_prior else self.pool(out)
+        return out
+
+    model.ReferenceFill.forward = reference_fill_forward
+
+    try:
+        enc_mod = importlib.import_module("modules.psp.encoders.psp_encoders")
+    except Exception:  # the pSp side needs packages the PICNet side does not; leave it alone if it cannot import
+        return
+
+    def gradual_style_encoder_forward(self, x, ref=None, mask=None):
+        taps = {6: None, 20: None, 23: None}
+
+        def trunk(t):
+            t = self.input_layer(t)
+            feats = dict(taps)
+            for idx, layer in enumerate(self.body._modules.values()):
+                t = layer(t)
+                if idx in feats:
+                    feats[idx] = t
+            return feats[6], feats[20], feats[23]
+
+        c1, c2, c3 = trunk(x)
+        if ref is not None:
+            assert mask is not None, "ref and mask should both be provided"
+            full_mask = mask.unsqueeze(1)
+            r1, r2, r3 = trunk(ref)
+            if self.use_attention:
+                c3 = self.attention1(_scale_img_any(full_mask, r3.shape[-2:]), c3, r3)
+                c2 = self.attention2(_scale_img_any(full_mask, r2.shape[-2:]), c2, r2)
+            else:
+                c3 = _blend(c3, r3, full_mask)
+                c2 = _blend(c2, r2, full_mask)
+            c1 = _blend(c1, r1, full_mask)
+        latents = [self.styles[j](c3) for j in range(self.coarse_ind)]
+        p2 = self._upsample_add(c3, self.latlayer1(c2))
+        latents += [self.styles[j](p2) for j in range(self.coarse_ind, self.middle_ind)]
+        p1 = self._upsample_add(p2, self.latlayer2(c1))
+        latents += [self.styles[j](p1) for j in range(self.middle_ind, self.style_count)]
+        import torch
+        return torch.stack(latents, dim=1)
+
+    enc_mod.GradualStyleEncoder.forward = gradual_style_encoder_forward
+
+
+def _blend(src, ref, full_mask):
+    """mask * ref + (1 - mask) * src with the mask resized to the feature resolution (psp_encoders.py:135-138)."""
+    from . import ops
+    return ops.composite(src, ref, full_mask)  # CUDA only: raises for CPU tensors (no fallback)
+
+
+def _scale_img_any(img, size):
+    """modules/model.py:10-12. Masks ([N,1,H,W], the hot-path use) go through fmi_scale_mask and must be CUDA tensors
+    (no CPU fallback). The one other use — resizing the decoded RGB image in the `no_prior` branch (model.py:108-109) —
+    is not on the hot path and keeps the reference's own F.interpolate."""
+    from . import ops
+    if img.dim() == 4 and img.size(1) == 1:
+        return ops.scale_img(img, size)
+    import torch.nn.functional as F
+    return F.interpolate(img, size=size, mode='bilinear', align_corners=True)
+
+
+def uninstall_flag_for_tests():
+    global _INSTALLED
+    _INSTALLED = False
