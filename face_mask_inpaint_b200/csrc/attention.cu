@@ -25,6 +25,8 @@
 //   TMEM: O 256 columns + 2 x 128 columns of S/P = 512 columns (whole SM).
 //   The S x S map never leaves the SM. Key tiles are visited diagonal-first (tile j = i first): with keys == queries the
 //   row maximum is almost always on the diagonal block, so the lazy rescale practically never fires.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "sm100.cuh"
 
@@ -58,7 +60,10 @@ struct AttnParams {
   void* out1;
   int64_t out0_bs, out1_bs;
   float* lse;
+  long long* trace;  // debug: per-tile clock64 stamps of CTA (0,0,0) (fmi_debug_set_attn_trace), else NULL
 };
+
+static long long* g_attn_trace = nullptr;
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -66,10 +71,13 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-template <bool TF32, typename T>
+// CLUSTER: two CTAs (adjacent query tiles of one image) form a cluster and share every K and V tile: each CTA loads half
+// of the tile and TMA-multicasts it into both shared memories, halving the L2 -> SMEM fill traffic that bounds the
+// non-cluster kernel (profiles/README.md). Ring slots are released by both consumers (multicast tcgen05.commit).
+template <bool TF32, typename T, bool CLUSTER>
 __global__ void __launch_bounds__(kAttnThreads, 1)
-    attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_v,
-                    const AttnParams p) {
+    attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                    const __grid_constant__ CUtensorMap map_v, const AttnParams p) {
   constexpr int EPA = TF32 ? 32 : 64;        // operand elements per 128-byte atom row
   constexpr int V_CHUNKS = BN / EPA;         // K-chunks of the PV product per key tile
   constexpr int P_COLS_PER_CHUNK = 32;       // TMEM columns of P per chunk (32 tf32 or 64 packed bf16)
@@ -91,19 +99,23 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
   const int tid = threadIdx.x, warp = tid >> 5;
   const int i_tile = blockIdx.x, n = blockIdx.y, cv0 = blockIdx.z * p.cv_tile;
   const int NT = p.S / BN;  // key tiles
+  const uint32_t cta_rank = CLUSTER ? cluster_ctarank() : 0;
+  const int tile0 = CLUSTER ? (i_tile & ~1) : i_tile;  // first key tile (diagonal first; shared by the CTA pair)
+  constexpr uint32_t kConsumers = CLUSTER ? 2 : 1;     // CTAs that must release a K/V ring slot
+  constexpr uint16_t kMask = 0x3;
 
   if (tid == 0) {
     mbar_init(&q_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], 1);
+      mbar_init(&k_empty[i], kConsumers);
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 256);
       mbar_init(&pv_done[i], 1);
     }
     for (int i = 0; i < 8; ++i) {
       mbar_init(&v_full[i], 1);
-      mbar_init(&v_empty[i], 1);
+      mbar_init(&v_empty[i], kConsumers);
     }
     fence_barrier_init();
   }
@@ -112,7 +124,8 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
     tmem_relinquish();
   }
   tc_fence_before();
-  __syncthreads();
+  if (CLUSTER) cluster_sync_all();  // the peer's barriers must be initialised before any multicast reaches them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
   const uint32_t tmem_O = tmem;  // [0, 256)
@@ -122,26 +135,39 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
       tma_prefetch_desc(&map_q);
+      tma_prefetch_desc(&map_k);
       tma_prefetch_desc(&map_v);
       mbar_arrive_expect_tx(&q_full, q_tile_bytes);
       for (int a = 0; a < q_atoms; ++a)
         tma_load_2d(sQ + a * BM * ATOM_BYTES, &map_q, &q_full, a * 64, n * p.S + i_tile * BM);
       auto load_k = [&](int jj) {
-        const int j = (i_tile + jj) % NT;
+        const int j = (tile0 + jj) % NT;
         const int slot = jj % p.k_stages;
         mbar_wait(&k_empty[slot], ((jj / p.k_stages) & 1) ^ 1);
-        mbar_arrive_expect_tx(&k_full[slot], q_tile_bytes);
-        for (int a = 0; a < q_atoms; ++a)
-          tma_load_2d(sK + slot * q_tile_bytes + a * BN * ATOM_BYTES, &map_q, &k_full[slot], a * 64, n * p.S + j * BN);
+        mbar_arrive_expect_tx(&k_full[slot], q_tile_bytes);  // both halves land here
+        for (int a = 0; a < q_atoms; ++a) {
+          uint8_t* dst = sK + slot * q_tile_bytes + a * BN * ATOM_BYTES;
+          if (CLUSTER)  // this CTA fetches key rows [64r, 64r+64) of the tile and multicasts them to both CTAs
+            tma_load_2d_mc(dst + cta_rank * (BN / 2) * ATOM_BYTES, &map_k, &k_full[slot], a * 64,
+                           n * p.S + j * BN + cta_rank * (BN / 2), kMask);
+          else
+            tma_load_2d(dst, &map_k, &k_full[slot], a * 64, n * p.S + j * BN);
+        }
       };
       auto load_v = [&](int jj) {
-        const int j = (i_tile + jj) % NT;
+        const int j = (tile0 + jj) % NT;
         for (int c = 0; c < V_CHUNKS; ++c) {
           const int use = jj * V_CHUNKS + c;
           const int slot = use % p.v_stages;
           mbar_wait(&v_empty[slot], ((use / p.v_stages) & 1) ^ 1);
           mbar_arrive_expect_tx(&v_full[slot], v_chunk_bytes);
-          tma_load_2d(sV + slot * v_chunk_bytes, &map_v, &v_full[slot], j * BN + c * EPA, n * (p.C0 + p.C1) + cv0);
+          if (CLUSTER) {  // this CTA fetches channels [r*cv/2, (r+1)*cv/2) of the chunk for both CTAs
+            const int half = p.cv_tile / 2;
+            tma_load_2d_mc(sV + slot * v_chunk_bytes + cta_rank * half * ATOM_BYTES, &map_v, &v_full[slot],
+                           j * BN + c * EPA, n * (p.C0 + p.C1) + cv0 + cta_rank * half, kMask);
+          } else {
+            tma_load_2d(sV + slot * v_chunk_bytes, &map_v, &v_full[slot], j * BN + c * EPA, n * (p.C0 + p.C1) + cv0);
+          }
         }
       };
       // same order as the MMA warp consumes: K(0), K(1), V(0), K(2), V(1), ...
@@ -177,7 +203,8 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
             }
           }
         }
-        tc_commit(&k_empty[slot]);
+        if (CLUSTER) tc_commit_mc(&k_empty[slot], kMask);
+        else tc_commit(&k_empty[slot]);
         tc_commit(&s_full[b]);
       };
       mbar_wait(&q_full, 0);
@@ -187,9 +214,13 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
         if (jj + 1 < NT) {
           // S[(jj+1)&1] still holds P(jj-1) until PV(jj-1) has completed
           if (jj >= 1) mbar_wait(&pv_done[(jj + 1) & 1], ((jj - 1) >> 1) & 1);
+          if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && jj < 256) p.trace[jj * 16 + 7] = clock64();  // PV(jj-1) complete
           issue_qk(jj + 1);
         }
+        const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && jj < 256;
+        if (tr) p.trace[jj * 16 + 8] = clock64();   // QK(jj+1) issued, about to wait for P(jj)
         mbar_wait(&p_full[b], (jj >> 1) & 1);
+        if (tr) p.trace[jj * 16 + 9] = clock64();   // P(jj) available
         tc_fence_after();
         for (int c = 0; c < V_CHUNKS; ++c) {
           const int use = jj * V_CHUNKS + c;
@@ -204,9 +235,11 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
             if (TF32) mma_ts_tf32(tmem_O, a_t, bdesc + 2 * s, idesc_pv, acc);
             else mma_ts_f16(tmem_O, a_t, bdesc + 2 * s, idesc_pv, acc);
           }
-          tc_commit(&v_empty[slot]);
+          if (CLUSTER) tc_commit_mc(&v_empty[slot], kMask);
+          else tc_commit(&v_empty[slot]);
         }
         tc_commit(&pv_done[b]);
+        if (tr) p.trace[jj * 16 + 10] = clock64();  // PV(jj) issued (V chunks were available)
       }
     }
     __syncwarp();
@@ -221,12 +254,16 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
     float m_used = 0.f, l = 0.f;
     for (int jj = 0; jj < NT; ++jj) {
       const int b = jj & 1;
+      const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 64 && jj < 256;
+      if (tr) p.trace[jj * 16 + 0] = clock64();  // softmax warps ready for tile jj
       mbar_wait(&s_full[b], (jj >> 1) & 1);
+      if (tr) p.trace[jj * 16 + 1] = clock64();  // S(jj) available
       tc_fence_after();
       uint32_t s[64];
       tmem_ld32(tmem_S(b) + lane_addr + wg * 64, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
       tmem_ld32(tmem_S(b) + lane_addr + wg * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
       tc_wait_ld();
+      if (tr) p.trace[jj * 16 + 2] = clock64();  // S in registers
       float mx4[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) mx4[q] = __uint_as_float(s[q]);
@@ -237,6 +274,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
       xch[b][wg][row] = mx;
       asm volatile("bar.sync 1, 256;" ::: "memory");
       mx = fmaxf(mx, xch[b][wg ^ 1][row]);
+      if (tr) p.trace[jj * 16 + 3] = clock64();  // row max exchanged
       if (jj == 0) {
         m_used = mx;
       } else {
@@ -267,6 +305,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
         s[k] = __float_as_uint(pk);
       }
       l += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
+      if (tr) p.trace[jj * 16 + 4] = clock64();  // exponentials done
       if (TF32) {
         // the tensor core drops the 13 low mantissa bits of a tf32 operand: +0x1000 first = round to nearest
 #pragma unroll
@@ -281,6 +320,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(&p_full[b]);
+      if (tr) p.trace[jj * 16 + 5] = clock64();  // P(jj) published
     }
     // ---- epilogue: total row sum = both halves
     // (the exchange buffer of the other parity was last read two tiles ago: free)
@@ -322,7 +362,8 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CLUSTER) cluster_sync_all();  // no CTA may exit while its peer can still multicast into it / arrive on its barriers
+  else __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
@@ -516,9 +557,10 @@ int launch_pack_values(const void* v0, const void* v1, void* vcat, int N, int C0
   return fmi_launched("pack_values");
 }
 
-template <bool TF32, typename T>
-int launch_attn(const CUtensorMap& mq, const CUtensorMap& mv, const AttnParams& prm, const AttnPlan& pl, cudaStream_t st) {
-  auto kern = attn_fwd_kernel<TF32, T>;
+template <bool TF32, typename T, bool CLUSTER>
+int launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnParams& prm,
+                const AttnPlan& pl, cudaStream_t st) {
+  auto kern = attn_fwd_kernel<TF32, T, CLUSTER>;
   static bool attr_set = false;  // per template instantiation
   if (!attr_set) {
     cudaFuncAttributes fa;
@@ -529,8 +571,30 @@ int launch_attn(const CUtensorMap& mq, const CUtensorMap& mv, const AttnParams& 
   }
   dim3 grid(prm.S / BM, prm.N, (prm.C0 + prm.C1) / prm.cv_tile);
   FmiProfScope prof(0, st);
-  kern<<<grid, kAttnThreads, pl.smem, st>>>(mq, mv, prm);
+  if (CLUSTER) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kAttnThreads);
+    cfg.dynamicSmemBytes = pl.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    FMI_CUDA(cudaLaunchKernelEx(&cfg, kern, mq, mk, mv, prm));
+  } else {
+    kern<<<grid, kAttnThreads, pl.smem, st>>>(mq, mk, mv, prm);
+  }
   return fmi_launched("attn_fwd");
+}
+
+template <bool TF32, typename T>
+int launch_attn_any(bool cluster, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
+                    const AttnParams& prm, const AttnPlan& pl, cudaStream_t st) {
+  return cluster ? launch_attn<TF32, T, true>(mq, mk, mv, prm, pl, st) : launch_attn<TF32, T, false>(mq, mk, mv, prm, pl, st);
 }
 
 }  // namespace
@@ -586,7 +650,10 @@ extern "C" int fmi_attn_fwd(const void* x, const float* wq, const float* bq, con
   }
   if (rc) return rc;
 
-  CUtensorMap mq, mv;
+  // 2-CTA clusters (K/V multicast) need an even number of query tiles; FMI_ATTN_CLUSTER=0 disables them
+  static const bool cluster_env = [] { const char* e = getenv("FMI_ATTN_CLUSTER"); return !(e && e[0] == '0'); }();
+  const bool cluster = cluster_env && ((S / BM) % 2 == 0) && (pl.cv_tile % 16 == 0);
+  CUtensorMap mq, mk, mv;
   const CUtensorMapDataType dt = tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   const uint32_t epa = ATOM_BYTES / pl.esz;
   {
@@ -596,11 +663,14 @@ extern "C" int fmi_attn_fwd(const void* x, const float* wq, const float* bq, con
     uint32_t box[2] = {64, (uint32_t)BM};
     int e = make_tensor_map(&mq, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, qt, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
     FMI_REQUIRE(e == 0, "attn_fwd: cuTensorMapEncodeTiled(Qt) failed (%d)", e);
+    uint32_t kbox[2] = {64, (uint32_t)(cluster ? BN / 2 : BN)};  // each CTA of a pair fetches half of the key rows
+    e = make_tensor_map(&mk, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, qt, dims, str, kbox, CU_TENSOR_MAP_SWIZZLE_128B);
+    FMI_REQUIRE(e == 0, "attn_fwd: cuTensorMapEncodeTiled(K) failed (%d)", e);
   }
   {
     uint64_t dims[2] = {(uint64_t)S, (uint64_t)N * (C0 + C1)};
     uint64_t str[1] = {(uint64_t)S * pl.esz};
-    uint32_t box[2] = {epa, (uint32_t)pl.cv_tile};
+    uint32_t box[2] = {epa, (uint32_t)(cluster ? pl.cv_tile / 2 : pl.cv_tile)};
     int e = make_tensor_map(&mv, dt, 2, vcat, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
     FMI_REQUIRE(e == 0, "attn_fwd: cuTensorMapEncodeTiled(Vcat) failed (%d)", e);
   }
@@ -610,12 +680,20 @@ extern "C" int fmi_attn_fwd(const void* x, const float* wq, const float* bq, con
   prm.v0 = v0; prm.v1 = v1; prm.mask = mask; prm.a0 = a0; prm.a1 = a1; prm.b0 = b0; prm.b1 = b1;
   prm.masked0 = masked0; prm.masked1 = masked1;
   prm.out0 = out0; prm.out1 = out1; prm.out0_bs = out0_bs; prm.out1_bs = out1_bs; prm.lse = lse;
+  prm.trace = g_attn_trace;
   if (tf32) {
-    if (dtype == FMI_F32) return launch_attn<true, float>(mq, mv, prm, pl, st);
-    return launch_attn<true, __nv_bfloat16>(mq, mv, prm, pl, st);
+    if (dtype == FMI_F32) return launch_attn_any<true, float>(cluster, mq, mk, mv, prm, pl, st);
+    return launch_attn_any<true, __nv_bfloat16>(cluster, mq, mk, mv, prm, pl, st);
   }
-  if (dtype == FMI_F32) return launch_attn<false, float>(mq, mv, prm, pl, st);
-  return launch_attn<false, __nv_bfloat16>(mq, mv, prm, pl, st);
+  if (dtype == FMI_F32) return launch_attn_any<false, float>(cluster, mq, mk, mv, prm, pl, st);
+  return launch_attn_any<false, __nv_bfloat16>(cluster, mq, mk, mv, prm, pl, st);
+}
+
+// Debug aid: clock64 stamps of CTA (0,0,0) of subsequent fmi_attn_fwd calls are written to dev_buffer
+// (>= 256*16 long long); NULL switches tracing off. Not part of the product interface.
+extern "C" int fmi_debug_set_attn_trace(void* dev_buffer) {
+  g_attn_trace = (long long*)dev_buffer;
+  return FMI_OK;
 }
 
 extern "C" int fmi_attn_materialize(const void* workspace, const float* lse, float* attn, int N, int d, int S, int mma,

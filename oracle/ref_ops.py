@@ -77,7 +77,7 @@ def upfirdn2d_native(inp: torch.Tensor, kernel: torch.Tensor, up_x: int, up_y: i
     out = out[:, max(-pad_y0, 0):out.shape[1] - max(-pad_y1, 0), max(-pad_x0, 0):out.shape[2] - max(-pad_x1, 0), :]
     out = out.permute(0, 3, 1, 2)
     out = out.reshape([-1, 1, in_h * up_y + pad_y0 + pad_y1, in_w * up_x + pad_x0 + pad_x1])
-    w = torch.flip(kernel, [0, 1]).view(1, 1, kernel_h, kernel_w).to(out.dtype)
+    w = torch.flip(kernel, [0, 1]).view(1, 1, kernel_h, kernel_w).to(out)
     out = F.conv2d(out, w)
     out = out.reshape(-1, minor, in_h * up_y + pad_y0 + pad_y1 - kernel_h + 1,
                       in_w * up_x + pad_x0 + pad_x1 - kernel_w + 1)
@@ -211,7 +211,7 @@ def modulated_conv2d(x: torch.Tensor, style: torch.Tensor, weight: torch.Tensor,
         p = (len(blur_kernel) - factor) - (ksize - 1)                                   # :207-209
         pad0, pad1 = (p + 1) // 2 + factor - 1, p // 2 + 1
         k = make_kernel(list(blur_kernel)) * (factor ** 2)                              # :78-82
-        out = upfirdn2d(out, k.to(out.dtype), pad=(pad0, pad1))                         # :263
+        out = upfirdn2d(out, k.to(out), pad=(pad0, pad1))                         # :263
     else:
         xin = x.reshape(1, batch * in_channel, height, width)                           # :274
         out = F.conv2d(xin, w, padding=ksize // 2, groups=batch)                        # :275
@@ -234,7 +234,7 @@ def to_rgb(x, style, weight, mod_weight, mod_bias, bias, skip=None, blur_kernel=
     out = out + bias
     if skip is not None:
         k = make_kernel(list(blur_kernel)) * 4
-        skip = upfirdn2d(skip, k.to(skip.dtype), up=2, down=1, pad=(2, 1))
+        skip = upfirdn2d(skip, k.to(skip), up=2, down=1, pad=(2, 1))
         out = out + skip
     return out
 

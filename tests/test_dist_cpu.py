@@ -1,0 +1,99 @@
+"""N > 1 host logic on CPU with the gloo backend, world_size 2: batch sharding, gradient all-reduce through the
+post-accumulate-grad / optimizer-pre-step hooks (incl. a parameter that never gets a gradient and an optimizer step
+hidden inside a callee, as in modules/loss.py:126-132), state broadcast, and the agreed non-finite decision."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+class Net(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.a = torch.nn.Linear(6, 8)
+        self.b = torch.nn.Linear(8, 3)
+        self.unused = torch.nn.Parameter(torch.ones(4))  # like Auto_Attn.alpha / model.* (never receives a gradient)
+        self.register_buffer("u", torch.randn(5))
+
+    def forward(self, x):
+        return self.b(torch.tanh(self.a(x)))
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from face_mask_inpaint_b200 import dist as fd
+    r, lr, w = fd.init_from_env("gloo")
+    assert (r, w) == (rank, world)
+    torch.manual_seed(100 + rank)          # different init per rank ...
+    net = Net()
+    fd.broadcast_module_state(net)          # ... made identical, buffers included
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(8, 6, generator=g)
+    y = torch.randn(8, 3, generator=g)
+    idx = list(fd.shard_batch(8, rank, world))
+    opt = torch.optim.SGD(net.parameters(), lr=0.1)
+    red = fd.GradientAllReducer(net.parameters(), bucket_bytes=256).attach(opt)   # tiny buckets: several of them
+
+    def hidden_step():                      # backward + step inside a callee, like GANOptimizer.__call__
+        opt.zero_grad()
+        loss = torch.nn.functional.mse_loss(net(x[idx]), y[idx])
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(2):
+        loss = hidden_step()
+    finite = fd.all_ranks_finite(loss if rank == 0 else torch.tensor(float("nan")))
+    red.remove()
+    q.put((rank, {k: v.detach().numpy().copy() for k, v in net.state_dict().items()}, len(red.buckets), finite, idx))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_matches_single_process_step():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # single-process reference on the concatenated batch, starting from rank 0's initial state
+    torch.manual_seed(100)
+    net = Net()
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(8, 6, generator=g)
+    y = torch.randn(8, 3, generator=g)
+    opt = torch.optim.SGD(net.parameters(), lr=0.1)
+    for _ in range(2):
+        opt.zero_grad()
+        torch.nn.functional.mse_loss(net(x), y).backward()
+        opt.step()
+    want = net.state_dict()
+    assert res[0][4] == [0, 1, 2, 3] and res[1][4] == [4, 5, 6, 7]
+    assert res[0][2] >= 2                      # more than one bucket was exercised
+    for rank, sd, _, finite, _ in res:
+        assert finite is False                 # one rank saw a NaN -> every rank agrees to skip
+        for k in want:
+            assert torch.allclose(torch.from_numpy(sd[k]), want[k], atol=1e-6), (rank, k)
+
+
+def test_shard_batch_covers_everything():
+    from face_mask_inpaint_b200.dist import shard_batch
+    for n in (0, 1, 7, 8, 13):
+        for w in (1, 2, 4, 8):
+            got = [i for r in range(w) for i in shard_batch(n, r, w)]
+            assert got == list(range(n))
