@@ -61,6 +61,8 @@ struct AttnParams {
   int64_t out0_bs, out1_bs;
   float* lse;
   long long* trace;  // debug: per-tile clock64 stamps of CTA (0,0,0) (fmi_debug_set_attn_trace), else NULL
+  int dbg;             // debug knobs (FMI_ATTN_DBG): skip parts of the fast kernel to attribute time; 0 in production
+  const float* qmax2;  // [N] max_j |q_j|^2 per image (selects fixed-bound fast path vs this robust kernel), or NULL
 };
 
 static long long* g_attn_trace = nullptr;
@@ -70,6 +72,8 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+
+constexpr float kSafeQ2 = 256.f;  // attn_fwd2_kernel's fixed-bound softmax is used when max_j |q_j|^2 <= this
 
 // CLUSTER: two CTAs (adjacent query tiles of one image) form a cluster and share every K and V tile: each CTA loads half
 // of the tile and TMA-multicasts it into both shared memories, halving the L2 -> SMEM fill traffic that bounds the
@@ -98,6 +102,8 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int i_tile = blockIdx.x, n = blockIdx.y, cv0 = blockIdx.z * p.cv_tile;
+  // as the fallback of attn_fwd2_kernel this kernel only takes the images whose logits are too large for the fixed bound
+  if (p.qmax2 && p.qmax2[n] <= kSafeQ2) return;
   const int NT = p.S / BN;  // key tiles
   const uint32_t cta_rank = CLUSTER ? cluster_ctarank() : 0;
   const int tile0 = CLUSTER ? (i_tile & ~1) : i_tile;  // first key tile (diagonal first; shared by the CTA pair)
@@ -367,6 +373,8 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
   if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
+#include "attention_v2.cuh"
+
 // ---- prologue kernels ---------------------------------------------------------------------------
 // 1x1 convolution as a small SIMT fp32 GEMM: y[n,o,s] = sum_c W[o,c] x[n,c,s] + b[o].
 //   OUT_QT = false: y is NCHW of type TO.
@@ -502,8 +510,9 @@ __global__ void __launch_bounds__(256) attn_materialize_kernel(const __nv_bfloat
 
 struct AttnPlan {
   int dpad, d_atoms, split, cv_tile, k_stages, v_stages, esz;  // esz: element size of the V / P operands
-  int64_t qt_bytes, vcat_bytes;
-  size_t smem;
+  int k_stages2, v_stages2;                                    // ring depths of attn_fwd2_kernel
+  int64_t qt_bytes, vcat_bytes, qmax_bytes;
+  size_t smem, smem2;
 };
 
 int make_plan(int N, int d, int C0, int C1, int S, int mma, AttnPlan* pl) {
@@ -529,6 +538,13 @@ int make_plan(int N, int d, int C0, int C1, int S, int mma, AttnPlan* pl) {
   pl->smem = (size_t)(1 + pl->k_stages) * q_tile + (size_t)vs * v_chunk;
   pl->qt_bytes = ((int64_t)N * S * pl->dpad * (1 + pl->split) * 2 + 1023) / 1024 * 1024;
   pl->vcat_bytes = ((int64_t)N * Cv * S * esz + 1023) / 1024 * 1024;
+  pl->qmax_bytes = ((int64_t)N * 4 + 1023) / 1024 * 1024;
+  // fast kernel: same tiles, its own (smaller) static footprint
+  pl->k_stages2 = (3 * q_tile + 4 * v_chunk <= kAttn2SmemBudget) ? 2 : 1;
+  int vs2 = (kAttn2SmemBudget - (1 + pl->k_stages2) * q_tile) / v_chunk;
+  if (vs2 > 8) vs2 = 8;
+  pl->v_stages2 = vs2;
+  pl->smem2 = (size_t)(1 + pl->k_stages2) * q_tile + (size_t)vs2 * v_chunk;
   return FMI_OK;
 }
 
@@ -591,6 +607,45 @@ int launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap&
   return fmi_launched("attn_fwd");
 }
 
+template <bool TF32, typename T, bool CLUSTER>
+int launch_attn2(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, AttnParams prm, const AttnPlan& pl,
+                 cudaStream_t st) {
+  auto kern = attn_fwd2_kernel<TF32, T, CLUSTER>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncAttributes fa;
+    FMI_CUDA(cudaFuncGetAttributes(&fa, kern));
+    FMI_REQUIRE((int)fa.sharedSizeBytes <= kAttn2StaticSmem, "attn_fwd2: static shared memory grew to %d bytes",
+                (int)fa.sharedSizeBytes);
+    FMI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn2SmemBudget));
+    attr_set = true;
+  }
+  prm.k_stages = pl.k_stages2;
+  prm.v_stages = pl.v_stages2;
+  dim3 grid(prm.S / BM, prm.N, (prm.C0 + prm.C1) / prm.cv_tile);
+  FmiProfScope prof(0, st);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kAttn2Threads);
+  cfg.dynamicSmemBytes = pl.smem2;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CLUSTER ? 2 : 1;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  FMI_CUDA(cudaLaunchKernelEx(&cfg, kern, mq, mk, mv, prm));
+  return fmi_launched("attn_fwd2");
+}
+
+template <bool TF32, typename T>
+int launch_attn2_any(bool cluster, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
+                     const AttnParams& prm, const AttnPlan& pl, cudaStream_t st) {
+  return cluster ? launch_attn2<TF32, T, true>(mq, mk, mv, prm, pl, st) : launch_attn2<TF32, T, false>(mq, mk, mv, prm, pl, st);
+}
+
 template <bool TF32, typename T>
 int launch_attn_any(bool cluster, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
                     const AttnParams& prm, const AttnPlan& pl, cudaStream_t st) {
@@ -603,7 +658,7 @@ extern "C" int64_t fmi_attn_workspace_bytes(int N, int C, int d, int C0, int C1,
   (void)C;
   AttnPlan pl;
   if (make_plan(N, d, C0, C1, S, mma, &pl)) return -1;
-  return pl.qt_bytes + pl.vcat_bytes;
+  return pl.qt_bytes + pl.vcat_bytes + pl.qmax_bytes;
 }
 
 extern "C" int fmi_conv1x1(const void* x, const float* w, const float* b, void* y, int N, int Cin, int Cout, int S,
@@ -630,8 +685,8 @@ extern "C" int fmi_attn_fwd(const void* x, const float* wq, const float* bq, con
   FMI_REQUIRE(C >= 1, "attn_fwd: bad C");
   FMI_REQUIRE((C1 == 0) == (v1 == nullptr) && (C1 == 0 || out1), "attn_fwd: v1/out1 must be given exactly when C1 > 0");
   FMI_REQUIRE(!(masked0 || masked1) || mask, "attn_fwd: masked group without a mask");
-  FMI_REQUIRE(workspace_bytes >= pl.qt_bytes + pl.vcat_bytes, "attn_fwd: workspace too small (%lld < %lld)",
-              (long long)workspace_bytes, (long long)(pl.qt_bytes + pl.vcat_bytes));
+  FMI_REQUIRE(workspace_bytes >= pl.qt_bytes + pl.vcat_bytes + pl.qmax_bytes, "attn_fwd: workspace too small (%lld < %lld)",
+              (long long)workspace_bytes, (long long)(pl.qt_bytes + pl.vcat_bytes + pl.qmax_bytes));
   FMI_REQUIRE(fmi_aligned(workspace, 1024), "attn_fwd: workspace must be 1024-byte aligned");
   FMI_REQUIRE(fmi_aligned(v0, 16) && (!v1 || fmi_aligned(v1, 16)), "attn_fwd: value tensors must be 16-byte aligned");
   rc = fmi_device_check();
@@ -639,7 +694,10 @@ extern "C" int fmi_attn_fwd(const void* x, const float* wq, const float* bq, con
   cudaStream_t st = (cudaStream_t)stream;
   uint8_t* qt = (uint8_t*)workspace;
   uint8_t* vcat = qt + pl.qt_bytes;
+  float* qmax2 = (float*)(vcat + pl.vcat_bytes);
   const bool tf32 = mma == FMI_MMA_TF32;
+  // FMI_ATTN_KERNEL=robust: only the online-max kernel; default: fixed-bound fast kernel + robust fallback per image
+  static const bool fast_env = [] { const char* e = getenv("FMI_ATTN_KERNEL"); return !(e && e[0] == 'r'); }();
 
   if (dtype == FMI_F32) {
     rc = launch_conv1x1_any<float>(x, wq, bq, qt, N, C, d, S, pl.dpad, tf32 ? 2 : 1, st);
@@ -649,6 +707,13 @@ extern "C" int fmi_attn_fwd(const void* x, const float* wq, const float* bq, con
     if (!rc) rc = launch_pack_values<__nv_bfloat16>(v0, v1, vcat, N, C0, C1, S, mma, st);
   }
   if (rc) return rc;
+  if (fast_env) {
+    FMI_CUDA(cudaMemsetAsync(qmax2, 0, (size_t)N * sizeof(float), st));
+    dim3 g((S + 63) / 64 < 592 ? (S + 63) / 64 : 592, N);
+    qnorm_max_kernel<<<g, 256, 0, st>>>((const __nv_bfloat16*)qt, qmax2, S, pl.dpad, pl.split);
+    rc = fmi_launched("qnorm_max");
+    if (rc) return rc;
+  }
 
   // 2-CTA clusters (K/V multicast) need an even number of query tiles; FMI_ATTN_CLUSTER=0 disables them
   static const bool cluster_env = [] { const char* e = getenv("FMI_ATTN_CLUSTER"); return !(e && e[0] == '0'); }();
@@ -681,6 +746,15 @@ extern "C" int fmi_attn_fwd(const void* x, const float* wq, const float* bq, con
   prm.masked0 = masked0; prm.masked1 = masked1;
   prm.out0 = out0; prm.out1 = out1; prm.out0_bs = out0_bs; prm.out1_bs = out1_bs; prm.lse = lse;
   prm.trace = g_attn_trace;
+  prm.qmax2 = fast_env ? qmax2 : nullptr;
+  { const char* e = getenv("FMI_ATTN_DBG"); prm.dbg = e ? atoi(e) : 0; }
+  if (fast_env) {  // fast kernel first; images with max|q|^2 > kSafeQ2 fall through to the robust kernel below
+    if (tf32) rc = dtype == FMI_F32 ? launch_attn2_any<true, float>(cluster, mq, mk, mv, prm, pl, st)
+                                    : launch_attn2_any<true, __nv_bfloat16>(cluster, mq, mk, mv, prm, pl, st);
+    else rc = dtype == FMI_F32 ? launch_attn2_any<false, float>(cluster, mq, mk, mv, prm, pl, st)
+                               : launch_attn2_any<false, __nv_bfloat16>(cluster, mq, mk, mv, prm, pl, st);
+    if (rc) return rc;
+  }
   if (tf32) {
     if (dtype == FMI_F32) return launch_attn_any<true, float>(cluster, mq, mk, mv, prm, pl, st);
     return launch_attn_any<true, __nv_bfloat16>(cluster, mq, mk, mv, prm, pl, st);

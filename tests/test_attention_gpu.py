@@ -155,3 +155,28 @@ def test_attention_rejects_unsupported_shapes():
     x = torch.randn(1, 64, 10, 10, device=DEV)  # S = 100 is not a multiple of 128
     with pytest.raises(RuntimeError, match="multiple of 128"):
         ops.attention_forward(x, torch.randn(16, 64, device=DEV), None, x, None)
+
+
+@pytest.mark.parametrize("logit_std", [64.0, 256.0])
+def test_attention_large_logits_take_the_robust_kernel(logit_std):
+    """max|q|^2 beyond the fixed-bound range: the fast kernel steps aside per image and the online-max kernel runs.
+    Error grows with |logit| * 2^-16, so the bound here is 1e-2, not the 1e-3 contract."""
+    from face_mask_inpaint_b200.modules import Auto_Attn
+    n, c, h, w = 2, 128, 32, 32
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(n, c, h, w, generator=g)
+    x[1] *= 0.05  # second image stays in the fast kernel's range: both kernels produce parts of one batch
+    wq = _scaled_query_weight(c, c // 4, x, logit_std, g)
+    mod = Auto_Attn(c, None)
+    with torch.no_grad():
+        mod.query_conv.weight.copy_(wq)
+        mod.query_conv.bias.zero_()
+        mod.gamma.fill_(1.0)
+    want, _, _ = O.auto_attn(x, mod.query_conv.weight.detach(), mod.query_conv.bias.detach(), mod.gamma.detach())
+    q2 = torch.nn.functional.conv2d(x, wq).pow(2).sum(1).flatten(1).max(1).values
+    assert q2[0] > 256 and q2[1] < 256, q2  # image 0 -> robust kernel, image 1 -> fast kernel
+    mod = mod.to(DEV)
+    with torch.no_grad():
+        got, _ = mod(x.to(DEV))
+    assert torch.isfinite(got).all()
+    assert rel_err(got - x.to(DEV), want - x) <= 1e-2
