@@ -33,9 +33,12 @@ PROTOTYPES = {
     "fmi_composite": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "fmi_composite_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "fmi_attn_workspace_bytes": (_i64, [_i, _i, _i, _i, _i, _i, _i]),
-    "fmi_attn_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _vp, _f, _i, _vp, _i64, _vp, _i64, _vp,
+    "fmi_attn_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _vp, _f, _i, _vp, _i64, _vp, _i64, _vp, _vp,
                           _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i64, _vp]),
     "fmi_attn_materialize": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "fmi_attn_bwd_workspace_bytes": (_i64, [_i, _i, _i, _i, _i, _i, _i]),
+    "fmi_attn_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _vp, _f, _i, _vp, _vp, _vp, _i64, _vp, _i64,
+                          _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i64, _vp]),
     "fmi_conv1x1": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "fmi_nchw_to_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "fmi_nhwc_to_nchw": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),

@@ -60,6 +60,7 @@ struct AttnParams {
   void* out1;
   int64_t out0_bs, out1_bs;
   float* lse;
+  void* o_save;        // [N, C0+C1, S] (type T) normalised attention output before the blend, for backward; or NULL
   long long* trace;  // debug: per-tile clock64 stamps of CTA (0,0,0) (fmi_debug_set_attn_trace), else NULL
   int dbg;             // debug knobs (FMI_ATTN_DBG): skip parts of the fast kernel to attribute time; 0 in production
   const float* qmax2;  // [N] max_j |q_j|^2 per image (selects fixed-bound fast path vs this robust kernel), or NULL
@@ -355,6 +356,11 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
       const bool masked = g1 ? p.masked1 : p.masked0;
       const float a = (g1 ? alpha1 : alpha0) * (masked ? (1.f - m_i) : 1.f);
       const float r = masked ? m_i : (g1 ? p.b1 : p.b0);
+      if (p.o_save) {
+        T* os = (T*)p.o_save + ((int64_t)n * (p.C0 + p.C1) + cg) * p.S + i;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) os[(int64_t)k * p.S] = from_f32<T>(__uint_as_float(o[k]) * inv_l);
+      }
       if (r != 0.f || masked) {
 #pragma unroll
         for (int k = 0; k < 32; ++k) {
@@ -654,6 +660,23 @@ int launch_attn_any(bool cluster, const CUtensorMap& mq, const CUtensorMap& mk, 
 
 }  // namespace
 
+// Operand staging shared with the backward pass (attn_bwd.cu): Qt (bf16 [hi | lo] rows) and Vcat.
+int fmi_attn_stage_operands(const void* x, const float* wq, const float* bq, const void* v0, const void* v1, void* qt,
+                            void* vcat, int N, int C, int d, int C0, int C1, int S, int dtype, int mma, cudaStream_t st) {
+  AttnPlan pl;
+  int rc = make_plan(N, d, C0, C1, S, mma, &pl);
+  if (rc) return rc;
+  const bool tf32 = mma == FMI_MMA_TF32;
+  if (dtype == FMI_F32) {
+    rc = launch_conv1x1_any<float>(x, wq, bq, qt, N, C, d, S, pl.dpad, tf32 ? 2 : 1, st);
+    if (!rc) rc = launch_pack_values<float>(v0, v1, vcat, N, C0, C1, S, mma, st);
+  } else {
+    rc = launch_conv1x1_any<__nv_bfloat16>(x, wq, bq, qt, N, C, d, S, pl.dpad, tf32 ? 2 : 1, st);
+    if (!rc) rc = launch_pack_values<__nv_bfloat16>(v0, v1, vcat, N, C0, C1, S, mma, st);
+  }
+  return rc;
+}
+
 extern "C" int64_t fmi_attn_workspace_bytes(int N, int C, int d, int C0, int C1, int S, int mma) {
   (void)C;
   AttnPlan pl;
@@ -673,7 +696,7 @@ extern "C" int fmi_conv1x1(const void* x, const float* w, const float* b, void* 
 
 extern "C" int fmi_attn_fwd(const void* x, const float* wq, const float* bq, const void* v0, const void* v1,
                             const float* mask, const float* a0, float b0, int masked0, const float* a1, float b1,
-                            int masked1, void* out0, int64_t out0_bs, void* out1, int64_t out1_bs, float* lse, int N, int C,
+                            int masked1, void* out0, int64_t out0_bs, void* out1, int64_t out1_bs, float* lse, void* o_save, int N, int C,
                             int d, int C0, int C1, int S, int dtype, int mma, void* workspace, int64_t workspace_bytes,
                             void* stream) {
   FMI_REQUIRE(dtype == FMI_F32 || dtype == FMI_BF16, "attn_fwd: dtype must be fp32 or bf16");
@@ -744,7 +767,7 @@ extern "C" int fmi_attn_fwd(const void* x, const float* wq, const float* bq, con
   prm.k_stages = pl.k_stages; prm.v_stages = pl.v_stages;
   prm.v0 = v0; prm.v1 = v1; prm.mask = mask; prm.a0 = a0; prm.a1 = a1; prm.b0 = b0; prm.b1 = b1;
   prm.masked0 = masked0; prm.masked1 = masked1;
-  prm.out0 = out0; prm.out1 = out1; prm.out0_bs = out0_bs; prm.out1_bs = out1_bs; prm.lse = lse;
+  prm.out0 = out0; prm.out1 = out1; prm.out0_bs = out0_bs; prm.out1_bs = out1_bs; prm.lse = lse; prm.o_save = o_save;
   prm.trace = g_attn_trace;
   prm.qmax2 = fast_env ? qmax2 : nullptr;
   { const char* e = getenv("FMI_ATTN_DBG"); prm.dbg = e ? atoi(e) : 0; }

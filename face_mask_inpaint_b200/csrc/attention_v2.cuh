@@ -288,6 +288,11 @@ __global__ void __launch_bounds__(kAttn2Threads, 1)
       const bool masked = g1 ? p.masked1 : p.masked0;
       const float a = (g1 ? alpha1 : alpha0) * (masked ? (1.f - mk) : 1.f);
       const float r = masked ? mk : (g1 ? p.b1 : p.b0);
+      if (p.o_save) {
+        T* os = (T*)p.o_save + ((int64_t)n * (p.C0 + p.C1) + cg) * p.S + i;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) os[(int64_t)k * p.S] = from_f32<T>(__uint_as_float(o[k]) * inv_l);
+      }
       if (r != 0.f || masked) {
 #pragma unroll
         for (int k = 0; k < 32; ++k) {

@@ -1,5 +1,6 @@
 """Drop-in ExampleGuidedAttention (modules/example_guided_att.py:5-41) and Auto_Attn
-(modules/pluralistic_model/base_function.py:401-448) on the fused sm_100a attention kernel.
+(modules/pluralistic_model/base_function.py:401-448) on the fused sm_100a attention kernels (forward: fmi_attn_fwd,
+backward: fmi_attn_bwd).
 
 Parameter names/shapes are the reference's: `conv.weight [C/4,C,1,1]`, `out_conv.{weight,bias}`;
 `query_conv.{weight,bias}`, `gamma`, `alpha`, `model.*`.
@@ -34,53 +35,94 @@ class ExampleGuidedAttention(nn.Module):
 
 
 class _EGAFunction(torch.autograd.Function):
+    """value group 0 = src (out = O_src -> channels [C,2C)), group 1 = ref (masked blend -> channels [0,C))."""
+
     @staticmethod
     def forward(ctx, src_mask, src_feature, ref_feature, wq):
-        out, lse, _ = ops.attention_forward(src_feature, wq, None, src_feature, ref_feature, mask=src_mask,
-                                            b0=0.0, masked0=False, masked1=True, order=(1, 0),
-                                            need_lse=ctx.needs_input_grad[1] or ctx.needs_input_grad[2] or
-                                            ctx.needs_input_grad[3])
-        ctx.save_for_backward(src_mask, src_feature, ref_feature, wq, out, lse)
+        need = any(ctx.needs_input_grad[1:])
+        if need:
+            out, lse, _, o_saved = ops.attention_forward(src_feature, wq, None, src_feature, ref_feature, mask=src_mask,
+                                                         b0=0.0, masked0=False, masked1=True, order=(1, 0),
+                                                         need_lse=True, save_o=True)
+            ctx.save_for_backward(src_mask, src_feature, ref_feature, wq, o_saved, lse)
+        else:
+            out, _, _ = ops.attention_forward(src_feature, wq, None, src_feature, ref_feature, mask=src_mask, b0=0.0,
+                                              masked0=False, masked1=True, order=(1, 0))
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
-        raise NotImplementedError("fmi_b200: ExampleGuidedAttention backward kernel is not implemented yet "
-                                  "(no PyTorch/CPU fallback by design)")
+        src_mask, src, ref, wq, o_saved, lse = ctx.saved_tensors
+        dq, dv0, dv1, _, _ = ops.attention_backward(src, wq, None, src, ref, src_mask, None, 0.0, False, None, 0.0, True,
+                                                    o_saved, lse, grad_out, order=(1, 0),
+                                                    need_dv0=ctx.needs_input_grad[1], need_dv1=ctx.needs_input_grad[2])
+        dw, dx, _ = ops.qconv_backward(dq, src, wq, False)
+        g_src = None
+        if ctx.needs_input_grad[1]:
+            g_src = (dv0 + dx).to(src.dtype)
+        g_ref = dv1.to(ref.dtype) if ctx.needs_input_grad[2] else None
+        return None, g_src, g_ref, (dw.to(wq.dtype) if ctx.needs_input_grad[3] else None)
 
 
 class _Conv1x1Function(torch.autograd.Function):
+    """out_conv (example_guided_att.py:38-39): forward on fmi_conv1x1; its gradients are plain dense products."""
+
     @staticmethod
     def forward(ctx, x, weight, bias):
         ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
         return ops.conv1x1(x, weight, bias)
 
     @staticmethod
     def backward(ctx, grad_out):
-        raise NotImplementedError("fmi_b200: conv1x1 backward kernel is not implemented yet")
+        x, weight = ctx.saved_tensors
+        n, co = grad_out.shape[0], grad_out.shape[1]
+        ci = x.shape[1]
+        g = grad_out.reshape(n, co, -1).float()
+        xf = x.reshape(n, ci, -1).float()
+        dw = torch.einsum('nos,ncs->oc', g, xf).reshape(weight.shape).to(weight.dtype)
+        dx = torch.einsum('oc,nos->ncs', weight.reshape(co, ci).float(), g).reshape(x.shape).to(x.dtype)
+        db = g.sum((0, 2)).to(weight.dtype) if ctx.has_bias else None
+        return dx, dw, db
 
 
 class _AutoAttnFunction(torch.autograd.Function):
+    """group 0 = x (out = gamma*O + x); optional group 1 = pre (alpha*(1-m)*O_pre + m*pre)."""
+
     @staticmethod
     def forward(ctx, x, wq, bq, gamma, pre, mask, alpha):
-        need_lse = any(ctx.needs_input_grad) or _materialize()
-        if pre is None:
-            out, lse, ws = ops.attention_forward(x, wq, bq, x, None, a0=gamma, b0=1.0, need_lse=need_lse)
-        else:
-            out, lse, ws = ops.attention_forward(x, wq, bq, x, pre, mask=mask, a0=gamma, b0=1.0, a1=alpha,
-                                                 masked1=True, order=(0, 1), need_lse=need_lse)
+        need = any(ctx.needs_input_grad)
+        kw = dict(a0=gamma, b0=1.0)
+        if pre is not None:
+            kw.update(mask=mask, a1=alpha, masked1=True, order=(0, 1))
+        res = ops.attention_forward(x, wq, bq, x, pre, need_lse=need or _materialize(), save_o=need, **kw)
+        out, lse, ws = res[0], res[1], res[2]
         attn = None
         if _materialize():
             n, s = x.shape[0], x[0, 0].numel()
             attn = ops.attention_map(ws, lse, n, wq.shape[0], s, ops.mma_mode(x.dtype))
             ctx.mark_non_differentiable(attn)
-        ctx.save_for_backward(x, wq, bq, gamma, pre, mask, alpha, out, lse)
+        if need:
+            ctx.has_pre = pre is not None
+            saved = [x, wq, bq, gamma, res[3], lse]
+            if pre is not None:
+                saved += [pre, mask, alpha]
+            ctx.save_for_backward(*saved)
         return out, attn
 
     @staticmethod
     def backward(ctx, grad_out, grad_attn):
-        raise NotImplementedError("fmi_b200: Auto_Attn backward kernel is not implemented yet "
-                                  "(no PyTorch/CPU fallback by design)")
+        x, wq, bq, gamma, o_saved, lse = ctx.saved_tensors[:6]
+        pre = mask = alpha = None
+        if ctx.has_pre:
+            pre, mask, alpha = ctx.saved_tensors[6:]
+        dq, dv0, dv1, da0, da1 = ops.attention_backward(x, wq, bq, x, pre, mask, gamma, 1.0, False, alpha, 0.0,
+                                                        ctx.has_pre, o_saved, lse, grad_out, order=(0, 1))
+        dw, dx, db = ops.qconv_backward(dq, x, wq, True)
+        g_x = (dv0 + dx).to(x.dtype)
+        return (g_x, dw.to(wq.dtype), db.to(bq.dtype), da0.reshape(1).to(gamma.dtype),
+                dv1.to(pre.dtype) if ctx.has_pre else None, None,
+                da1.reshape(1).to(alpha.dtype) if ctx.has_pre else None)
 
 
 def _materialize() -> bool:

@@ -316,7 +316,7 @@ def conv1x1(x, weight, bias=None):
 
 
 def attention_forward(x, wq, bq, v0, v1=None, mask=None, a0=None, b0=0.0, masked0=False, a1=None, b1=0.0,
-                      masked1=False, order=(0, 1), need_lse=False, mma=None):
+                      masked1=False, order=(0, 1), need_lse=False, mma=None, save_o=False):
     """One fused pass of fmi_attn_fwd. x [N,C,H,W]; v0/v1 value groups [N,C0|C1,H,W]; mask [N,1,H,W] or None.
     Returns (out [N, C0+C1, H, W] with the groups concatenated in `order`, lse [N,S] or None, workspace)."""
     _need_cuda(x, wq, bq, v0, v1, mask, a0, a1)
@@ -347,12 +347,16 @@ def attention_forward(x, wq, bq, v0, v1=None, mask=None, a0=None, b0=0.0, masked
     off0 = 0 if order[0] == 0 else c1 * s
     off1 = c0 * s if order[0] == 0 else 0
     lse = torch.empty((n, s), dtype=torch.float32, device=xc.device) if need_lse else None
+    o_saved = torch.empty((n, c0 + c1, s), dtype=xc.dtype, device=xc.device) if save_o else None
     a0c = a0.reshape(1).float().contiguous() if a0 is not None else None
     a1c = a1.reshape(1).float().contiguous() if a1 is not None else None
     _lib.check(lib.fmi_attn_fwd(_ptr(xc), _ptr(w), _ptr(b), _ptr(v0c), _ptr(v1c), _ptr(m), _ptr(a0c), float(b0),
                                 int(masked0), _ptr(a1c), float(b1), int(masked1), out.data_ptr() + off0 * esz, bs,
-                                (out.data_ptr() + off1 * esz) if c1 else None, bs, _ptr(lse), n, c, d, c0, c1, s,
+                                (out.data_ptr() + off1 * esz) if c1 else None, bs, _ptr(lse), _ptr(o_saved), n, c, d, c0,
+                                c1, s,
                                 _dt(xc), mma, ws.data_ptr(), ws.numel(), _stream()), "fmi_attn_fwd")
+    if save_o:
+        return out, lse, ws, o_saved
     return out, lse, ws
 
 
@@ -362,3 +366,61 @@ def attention_map(ws, lse, n, d, s, mma):
     _lib.check(_lib.load().fmi_attn_materialize(ws.data_ptr(), _ptr(lse), _ptr(attn), n, d, s, mma, _stream()),
                "fmi_attn_materialize")
     return attn
+
+
+def attention_backward(x, wq, bq, v0, v1, mask, a0, b0, masked0, a1, b1, masked1, o_saved, lse, grad_out, order=(0, 1),
+                       need_dv0=True, need_dv1=True, mma=None):
+    """fmi_attn_bwd for the forward call with the same arguments; grad_out is [N, C0+C1, H, W] (groups concatenated in
+    `order`). Returns (dq [N,d,H,W] fp32, dv0, dv1 (fp32 or None), da0, da1 (fp32 scalars))."""
+    _need_cuda(x, wq, v0, grad_out)
+    xc = x.contiguous()
+    v0c = xc if v0 is x else v0.contiguous().to(xc.dtype)
+    v1c = v1.contiguous().to(xc.dtype) if v1 is not None else None
+    n, c = xc.shape[0], xc.shape[1]
+    spatial = tuple(xc.shape[2:])
+    s = xc[0, 0].numel()
+    d = wq.shape[0]
+    c0 = v0c.shape[1]
+    c1 = v1c.shape[1] if v1c is not None else 0
+    w = wq.reshape(d, c).contiguous().float()
+    b = bq.contiguous().float() if bq is not None else None
+    m = mask.reshape(n, s).contiguous().float() if mask is not None else None
+    if mma is None:
+        mma = mma_mode(xc.dtype)
+    g = grad_out.contiguous().to(xc.dtype)
+    esz = g.element_size()
+    bs = (c0 + c1) * s
+    off0 = 0 if order[0] == 0 else c1 * s
+    off1 = c0 * s if order[0] == 0 else 0
+    lib = _lib.load()
+    ws_bytes = lib.fmi_attn_bwd_workspace_bytes(n, c, d, c0, c1, s, mma)
+    if ws_bytes < 0:
+        raise RuntimeError(f"fmi_attn_bwd_workspace_bytes: {_lib.last_error()}")
+    ws = _workspace(xc.device, ws_bytes)
+    dpad = (d + 63) // 64 * 64
+    dq = torch.empty((n, s, dpad), dtype=torch.float32, device=xc.device)
+    dv0 = torch.empty((n, c0) + spatial, dtype=torch.float32, device=xc.device) if need_dv0 else None
+    dv1 = torch.empty((n, c1) + spatial, dtype=torch.float32, device=xc.device) if (need_dv1 and c1) else None
+    da = torch.zeros(2, dtype=torch.float32, device=xc.device)
+    a0c = a0.reshape(1).float().contiguous() if a0 is not None else None
+    a1c = a1.reshape(1).float().contiguous() if a1 is not None else None
+    _lib.check(lib.fmi_attn_bwd(_ptr(xc), _ptr(w), _ptr(b), _ptr(v0c), _ptr(v1c), _ptr(m), _ptr(a0c), float(b0),
+                                int(masked0), _ptr(a1c), float(b1), int(masked1), _ptr(o_saved), _ptr(lse),
+                                g.data_ptr() + off0 * esz, bs, (g.data_ptr() + off1 * esz) if c1 else None, bs,
+                                _ptr(dq), _ptr(dv0), _ptr(dv1), da.data_ptr(), da.data_ptr() + 4, n, c, d, c0, c1, s,
+                                _dt(xc), mma, ws.data_ptr(), ws.numel(), _stream()), "fmi_attn_bwd")
+    dq = dq[:, :, :d].permute(0, 2, 1).reshape((n, d) + spatial)
+    return dq, dv0, dv1, da[0], da[1]
+
+
+def qconv_backward(dq, x, weight, need_bias):
+    """Gradients of the 1x1 query conv from dq [N,d,H,W]: plain dense products (library GEMMs, not hot-path kernels):
+    dW[d,C] = sum_n dq_n x_n^T, dx = W^T dq, db = sum dq."""
+    n, d = dq.shape[0], dq.shape[1]
+    c = x.shape[1]
+    dqf = dq.reshape(n, d, -1)
+    xf = x.reshape(n, c, -1).float()
+    dw = torch.einsum('nds,ncs->dc', dqf, xf).reshape(weight.shape)
+    dx = torch.einsum('dc,nds->ncs', weight.reshape(d, c).float(), dqf).reshape(x.shape)
+    db = dqf.sum((0, 2)) if need_bias else None
+    return dw, dx, db

@@ -126,13 +126,31 @@ int fmi_composite_bwd(const void* grad_out, const float* mask, void* grad_src, v
  *   out0,out1  [N,C0,S], [N,C1,S] with batch strides out0_bs/out1_bs ELEMENTS (so both can live in
  *              one [N,C0+C1,S] concatenated tensor); element type = dtype
  *   lse     [N,S] fp32 row log-sum-exp (natural log) or NULL — saved for backward
+ *   o_save  [N,C0+C1,S] (dtype) normalised attention output O before the blend, or NULL — saved for backward
  *   mma     FMI_MMA_TF32 | FMI_MMA_BF16
  * ------------------------------------------------------------------------------------------- */
 int64_t fmi_attn_workspace_bytes(int N, int C, int d, int C0, int C1, int S, int mma);
 int fmi_attn_fwd(const void* x, const float* wq, const float* bq, const void* v0, const void* v1,
                  const float* mask, const float* a0, float b0, int masked0, const float* a1, float b1,
                  int masked1, void* out0, int64_t out0_bs, void* out1, int64_t out1_bs, float* lse,
-                 int N, int C, int d, int C0, int C1, int S, int dtype, int mma, void* workspace,
+                 void* o_save, int N, int C, int d, int C0, int C1, int S, int dtype, int mma, void* workspace,
+                 int64_t workspace_bytes, void* stream);
+
+/* Backward of fmi_attn_fwd (training: train_reference_fill.py / train_psp.py go through it by autograd).
+ *   Inputs as in fmi_attn_fwd plus: o_saved and lse from the forward, dout0/dout1 = gradients of the two
+ *   output groups (dtype, batch strides in elements). Outputs (fp32, caller-allocated):
+ *     dq  [N,S,dpad]  gradient of the projected query q^T (dpad = d rounded up to 64; columns >= d are zero)
+ *     dv0 [N,C0,S], dv1 [N,C1,S]  gradients of the value groups incl. the blend's direct path (NULL = skip)
+ *     da0, da1  device scalars, ACCUMULATED (gradients of gamma / alpha); NULL = skip
+ *   The 1x1-conv gradients that follow from dq (dWq = dq x^T, dx += Wq^T dq, dbq = sum dq) are plain GEMMs
+ *   left to the caller. Round-1 implementation: per image the S x S maps are materialised in the operand
+ *   type inside `workspace` (3 S^2 elements) and every contraction is a tcgen05 GEMM. */
+int64_t fmi_attn_bwd_workspace_bytes(int N, int C, int d, int C0, int C1, int S, int mma);
+int fmi_attn_bwd(const void* x, const float* wq, const float* bq, const void* v0, const void* v1,
+                 const float* mask, const float* a0, float b0, int masked0, const float* a1, float b1,
+                 int masked1, const void* o_saved, const float* lse, const void* dout0, int64_t dout0_bs,
+                 const void* dout1, int64_t dout1_bs, float* dq, float* dv0, float* dv1, float* da0,
+                 float* da1, int N, int C, int d, int C0, int C1, int S, int dtype, int mma, void* workspace,
                  int64_t workspace_bytes, void* stream);
 
 /* Opt-in materialisation of the S x S map that Auto_Attn returns (base_function.py:448):
