@@ -95,10 +95,13 @@ __global__ void __launch_bounds__(256) transpose_kernel(const OT* __restrict__ i
   }
 }
 
-// G = X + X^T for a square operand-type matrix (out-of-place)
+// G = X + X^T for square operand-type matrices (out-of-place, blockIdx.z = image; strides in elements)
 template <typename OT, bool TF32>
-__global__ void __launch_bounds__(256) sym_add_kernel(const OT* __restrict__ x, OT* __restrict__ g, int S) {
+__global__ void __launch_bounds__(256) sym_add_kernel(const OT* __restrict__ x, OT* __restrict__ g, int S, int64_t x_bs,
+                                                      int64_t g_bs) {
   __shared__ float t[32][33];
+  x += (int64_t)blockIdx.z * x_bs;
+  g += (int64_t)blockIdx.z * g_bs;
   const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   for (int j = ty; j < 32; j += 8) t[j][tx] = to_f32<OT>(x[(int64_t)(c0 + j) * S + r0 + tx]);  // block (c0, r0) of X
@@ -109,7 +112,10 @@ __global__ void __launch_bounds__(256) sym_add_kernel(const OT* __restrict__ x, 
   }
 }
 
-// From the staged Qt [S, qrow] bf16 ([hi | lo]):
+// G is written into the (fp32-sized) P buffer: per-image stride of that buffer in OT elements
+template <typename OT> inline int64_t P_stride_elems(int64_t SS) { return SS * 4 / (int64_t)sizeof(OT); }
+
+// From the staged Qt [nb, S, qrow] bf16 ([hi | lo]) (blockIdx.y = image of the group):
 //   TF32: QA = [hi | hi | lo], QB = [hi | lo | hi]  (fp32, K = 3 dpad) so that QA.QB^T = hi.hi + hi.lo + lo.hi;
 //         Qn [dpad, S] = tf32(hi + lo) transposed
 //   BF16: QA = QB = hi (K = dpad), Qn [dpad, S] = hi transposed
@@ -120,6 +126,11 @@ __global__ void __launch_bounds__(256) q_operands_kernel(const __nv_bfloat16* __
   const int rowlen = dpad * (1 + split);
   const int kq = TF32 ? 3 * dpad : dpad;
   const int64_t total = (int64_t)S * dpad;
+  const int b = blockIdx.y;
+  qt += (int64_t)b * S * rowlen;
+  qa += (int64_t)b * S * kq;
+  if (TF32) qb += (int64_t)b * S * kq;
+  qn += (int64_t)b * dpad * S;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int64_t s = e / dpad;
     const int k = (int)(e % dpad);
@@ -147,7 +158,7 @@ __global__ void fill_kernel(float* p, float v, int64_t n) {
 inline int64_t al(int64_t b) { return (b + 1023) / 1024 * 1024; }
 
 struct BwdPlan {
-  int dpad, split, esz, kq;
+  int dpad, split, esz, kq, nb;  // nb = images processed per group of batched launches
   int64_t qt, vcat, qa, qb, qn, dop, dot, vt, delta, rvec, p, pt, ds, total;
 };
 
@@ -161,6 +172,12 @@ int make_bwd_plan(int N, int d, int C0, int C1, int S, int mma, BwdPlan* pl) {
   pl->split = mma == FMI_MMA_TF32 ? 1 : 0;
   pl->dpad = (d + 63) / 64 * 64;
   pl->kq = pl->split ? 3 * pl->dpad : pl->dpad;
+  // the S x S maps dominate the scratch: as many images per group as fit in ~8 GiB (at least one)
+  const int64_t per_image = (int64_t)S * S * (4 + 2 * esz);
+  int64_t nb = (8ll << 30) / per_image;
+  if (nb < 1) nb = 1;
+  if (nb > N) nb = N;
+  pl->nb = (int)nb;
   int64_t off = 0;
   auto take = [&](int64_t bytes) { int64_t o = off; off += al(bytes); return o; };
   pl->qt = take((int64_t)N * S * pl->dpad * (1 + pl->split) * 2);
@@ -168,15 +185,15 @@ int make_bwd_plan(int N, int d, int C0, int C1, int S, int mma, BwdPlan* pl) {
   pl->dop = take((int64_t)N * Cv * S * esz);
   pl->delta = take((int64_t)N * S * 4);
   pl->rvec = take((int64_t)S * 4);
-  // per-image buffers (reused for every image)
-  pl->qa = take((int64_t)S * pl->kq * esz);
-  pl->qb = take((int64_t)S * pl->kq * esz);
-  pl->qn = take((int64_t)pl->dpad * S * esz);
-  pl->dot = take((int64_t)S * Cv * esz);
-  pl->vt = take((int64_t)S * Cv * esz);
-  pl->p = take((int64_t)S * S * 4);  // P stays fp32 (unrounded); later reused for G
-  pl->pt = take((int64_t)S * S * esz);
-  pl->ds = take((int64_t)S * S * esz);
+  // per-group buffers (reused for every group of nb images)
+  pl->qa = take(nb * S * pl->kq * esz);
+  pl->qb = take(nb * S * pl->kq * esz);
+  pl->qn = take(nb * pl->dpad * S * esz);
+  pl->dot = take(nb * S * Cv * esz);
+  pl->vt = take(nb * S * Cv * esz);
+  pl->p = take(nb * S * S * 4);  // P stays fp32 (unrounded); later reused for G
+  pl->pt = take(nb * S * S * esz);
+  pl->ds = take(nb * S * S * esz);
   pl->total = off;
   return FMI_OK;
 }
@@ -205,46 +222,48 @@ int run_bwd(const BwdPlan& pl, uint8_t* ws, const float* mask, const float* a0, 
   float* P = (float*)(ws + pl.p);   // fp32 P; the buffer is reused for G (operand type) once dE exists
   OT* G = (OT*)(ws + pl.p);
   const __nv_bfloat16* qt = (const __nv_bfloat16*)(ws + pl.qt);
+  const int64_t SS = (int64_t)S * S;
+  int rc;
 
   {
     dim3 grid((S + 255) / 256, N);
     attn_bwd_prep_kernel<T, OT, TF32><<<grid, 256, 0, st>>>((const T*)dout0, dout0_bs, (const T*)dout1, dout1_bs,
                                                              (const T*)o_saved, mask, a0, a1, masked0, masked1, dop, delta,
                                                              da0, da1, C0, C1, S);
-    int rc = fmi_launched("attn_bwd_prep");
-    if (rc) return rc;
+    if ((rc = fmi_launched("attn_bwd_prep"))) return rc;
   }
   const int rowlen = pl.dpad * (1 + pl.split);
-  for (int n = 0; n < N; ++n) {
-    int rc;
+  for (int n0 = 0; n0 < N; n0 += pl.nb) {
+    const int nb = N - n0 < pl.nb ? N - n0 : pl.nb;
     {
-      int grid = (int)imin64(((int64_t)S * pl.dpad + 255) / 256, (int64_t)FMI_NUM_SMS * 8);
-      q_operands_kernel<OT, TF32><<<grid, 256, 0, st>>>(qt + (int64_t)n * S * rowlen, qa, qb, qn, S, pl.dpad, pl.split);
+      dim3 qg((unsigned)imin64(((int64_t)S * pl.dpad + 255) / 256, (int64_t)FMI_NUM_SMS * 8), nb);
+      q_operands_kernel<OT, TF32><<<qg, 256, 0, st>>>(qt + (int64_t)n0 * S * rowlen, qa, qb, qn, S, pl.dpad, pl.split);
       if ((rc = fmi_launched("q_operands"))) return rc;
-      dim3 tg((S + 31) / 32, (Cv + 31) / 32, 1);
-      transpose_kernel<OT><<<tg, 256, 0, st>>>(dop + (int64_t)n * Cv * S, S, 0, dot, Cv, 0, Cv, S);
+      dim3 tg((S + 31) / 32, (Cv + 31) / 32, nb);
+      transpose_kernel<OT><<<tg, 256, 0, st>>>(dop + (int64_t)n0 * Cv * S, S, (int64_t)Cv * S, dot, Cv, (int64_t)S * Cv, Cv, S);
       if ((rc = fmi_launched("transpose"))) return rc;
-      transpose_kernel<OT><<<tg, 256, 0, st>>>(vcat + (int64_t)n * Cv * S, S, 0, vt, Cv, 0, Cv, S);
+      transpose_kernel<OT><<<tg, 256, 0, st>>>(vcat + (int64_t)n0 * Cv * S, S, (int64_t)Cv * S, vt, Cv, (int64_t)S * Cv, Cv, S);
       if ((rc = fmi_launched("transpose"))) return rc;
     }
     GemmParams g{};
-    // 1: P, PT
-    g.M = S; g.N = S; g.K = pl.kq; g.epi = EPI_EXP_SYM; g.out0 = P; g.out1 = PT; g.ldo = S;
-    g.rowvec = lse + (int64_t)n * S;
-    if ((rc = launch_gemm_nt<TF32>(qa, pl.kq, 0, qb, pl.kq, 0, 1, g, st))) return rc;
+    // 1: P (fp32), PT (operand type)
+    g.M = S; g.N = S; g.K = pl.kq; g.epi = EPI_EXP_SYM; g.out0 = P; g.out1 = PT; g.ldo = S; g.out_bs = SS;
+    g.rowvec = lse + (int64_t)n0 * S; g.vec_bs = S;
+    if ((rc = launch_gemm_nt<TF32>(qa, pl.kq, (int64_t)S * pl.kq, qb, pl.kq, (int64_t)S * pl.kq, nb, g, st))) return rc;
     // 2a: delta_i = sum_j P[i,j] dP[i,j] from exactly the P and dP that 2b uses (the algebraically equal
     //     sum_c dO'[c,i] O[c,i] from the forward differs by the forward's roundings, and for peaked attention
     //     dP - delta cancels to that difference — measured 3x gradient error)
-    float* delta_n = delta + (int64_t)n * S;
-    FMI_CUDA(cudaMemsetAsync(delta_n, 0, (size_t)S * sizeof(float), st));
+    float* delta_g = delta + (int64_t)n0 * S;
+    FMI_CUDA(cudaMemsetAsync(delta_g, 0, (size_t)nb * S * sizeof(float), st));
     g = GemmParams{};
-    g.M = S; g.N = S; g.K = Cv; g.epi = EPI_ROWDOT; g.out0 = delta_n; g.ldo = S; g.aux = P; g.ld_aux = S;
-    if ((rc = launch_gemm_nt<TF32>(dot, Cv, 0, vt, Cv, 0, 1, g, st))) return rc;
+    g.M = S; g.N = S; g.K = Cv; g.epi = EPI_ROWDOT; g.out0 = delta_g; g.ldo = S; g.out_bs = S; g.aux = P; g.ld_aux = S;
+    g.aux_bs = SS;
+    if ((rc = launch_gemm_nt<TF32>(dot, Cv, (int64_t)S * Cv, vt, Cv, (int64_t)S * Cv, nb, g, st))) return rc;
     // 2b: dE = P o (dP - delta)
     g = GemmParams{};
-    g.M = S; g.N = S; g.K = Cv; g.epi = EPI_DS; g.out0 = dS; g.ldo = S; g.rowvec = delta_n;
-    g.aux = P; g.ld_aux = S;
-    if ((rc = launch_gemm_nt<TF32>(dot, Cv, 0, vt, Cv, 0, 1, g, st))) return rc;
+    g.M = S; g.N = S; g.K = Cv; g.epi = EPI_DS; g.out0 = dS; g.ldo = S; g.out_bs = SS; g.rowvec = delta_g; g.vec_bs = S;
+    g.aux = P; g.ld_aux = S; g.aux_bs = SS;
+    if ((rc = launch_gemm_nt<TF32>(dot, Cv, (int64_t)S * Cv, vt, Cv, (int64_t)S * Cv, nb, g, st))) return rc;
     // 3: dV per value group (+ r_j * dOut_g[c, j])
     for (int grp = 0; grp < (C1 ? 2 : 1); ++grp) {
       const int Cg = grp ? C1 : C0, cofs = grp ? C0 : 0;
@@ -253,32 +272,37 @@ int run_bwd(const BwdPlan& pl, uint8_t* ws, const float* mask, const float* a0, 
       float* dv = grp ? dv1 : dv0;
       if (!dv) continue;
       g = GemmParams{};
-      g.M = Cg; g.N = S; g.K = S; g.out0 = dv + (int64_t)n * Cg * S; g.ldo = S;
+      g.M = Cg; g.N = S; g.K = S; g.out0 = dv + (int64_t)n0 * Cg * S; g.ldo = S; g.out_bs = (int64_t)Cg * S;
       if (masked || bconst != 0.f) {
         g.epi = EPI_ADD_COLSCALE;
         if (masked) {
-          g.colvec = mask + (int64_t)n * S;
+          g.colvec = mask + (int64_t)n0 * S;
+          g.vec_bs = S;
         } else {
           fill_kernel<<<(S + 255) / 256, 256, 0, st>>>(rvec, bconst, S);
           if ((rc = fmi_launched("fill"))) return rc;
           g.colvec = rvec;
+          g.vec_bs = 0;
         }
-        g.aux = (const uint8_t*)(grp ? dout1 : dout0) + (int64_t)n * (grp ? dout1_bs : dout0_bs) * sizeof(T);
+        const int64_t dbs = grp ? dout1_bs : dout0_bs;
+        g.aux = (const uint8_t*)(grp ? dout1 : dout0) + (int64_t)n0 * dbs * sizeof(T);
         g.ld_aux = S;
+        g.aux_bs = dbs;
         g.aux_dtype = dtype;
       } else {
         g.epi = EPI_STORE_F32;
       }
-      if ((rc = launch_gemm_nt<TF32>(dop + ((int64_t)n * Cv + cofs) * S, S, 0, PT, S, 0, 1, g, st))) return rc;
+      if ((rc = launch_gemm_nt<TF32>(dop + ((int64_t)n0 * Cv + cofs) * S, S, (int64_t)Cv * S, PT, S, SS, nb, g, st))) return rc;
     }
     // 4: G = dE + dE^T (into the P buffer), dq = G . q
     if (dq) {
-      dim3 sg(S / 32, S / 32);
-      sym_add_kernel<OT, TF32><<<sg, 256, 0, st>>>(dS, G, S);
+      dim3 sg(S / 32, S / 32, nb);
+      sym_add_kernel<OT, TF32><<<sg, 256, 0, st>>>(dS, G, S, SS, P_stride_elems<OT>(SS));
       if ((rc = fmi_launched("sym_add"))) return rc;
       g = GemmParams{};
-      g.M = S; g.N = pl.dpad; g.K = S; g.epi = EPI_STORE_F32; g.out0 = dq + (int64_t)n * S * pl.dpad; g.ldo = pl.dpad;
-      if ((rc = launch_gemm_nt<TF32>(G, S, 0, qn, S, 0, 1, g, st))) return rc;
+      g.M = S; g.N = pl.dpad; g.K = S; g.epi = EPI_STORE_F32; g.out0 = dq + (int64_t)n0 * S * pl.dpad; g.ldo = pl.dpad;
+      g.out_bs = (int64_t)S * pl.dpad;
+      if ((rc = launch_gemm_nt<TF32>(G, S, P_stride_elems<OT>(SS), qn, S, (int64_t)pl.dpad * S, nb, g, st))) return rc;
     }
   }
   return FMI_OK;

@@ -36,7 +36,7 @@ constexpr int kGemmThreads = 192;
 constexpr int A_TILE_BYTES = 128 * 128;
 
 template <bool TF32>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kGemmThreads, 2)
     gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                    const GemmParams p) {
   constexpr int EPA = TF32 ? 32 : 64;
@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(&tmem_base_s, 256);
+    tmem_alloc(&tmem_base_s, 128);  // n_tile <= 128 accumulator columns; leaves room for 4 CTAs per SM
     tmem_relinquish();
   }
   tc_fence_before();
@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, 256);
+  if (warp == 1) tmem_dealloc(tmem, 128);
 }
 
 // Host launcher. A: [batch, M, K] with row pitch lda, B: [batch, N, K] with row pitch ldb (elements of the operand type).
@@ -223,6 +223,11 @@ int launch_gemm_nt(const void* A, int64_t lda, int64_t a_bs, const void* B, int6
   const int stage_bytes = A_TILE_BYTES + n_tile * 128;
   int stages = (232448 - 2048) / stage_bytes;
   if (stages > 8) stages = 8;
+  // Short-K products (the S x S maps of the attention backward, K = 64..512) are latency-bound per CTA (ncu: tensor pipe
+  // 5 %, one CTA per SM): a 3-deep ring keeps the footprint under 100 KB so two CTAs share an SM and one's epilogue
+  // overlaps the other's loads.
+  const int iters = (p.K + (int)epa - 1) / (int)epa;
+  if (iters <= 16 && stages > 3) stages = 3;
   p.stages = stages;
   const CUtensorMapDataType dt = TF32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   CUtensorMap ma, mb;
