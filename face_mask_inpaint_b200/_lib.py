@@ -49,6 +49,9 @@ PROTOTYPES = {
     "fmi_styled_conv_nhwc": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i64,
                                   _vp]),
     "fmi_torgb_nhwc": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "fmi_torgb_weights": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "fmi_styled_conv_torgb_nhwc": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i,
+                                        _vp]),
 }
 
 _lib = None

@@ -34,7 +34,7 @@ struct ConvGemmParams {
   int ntaps, tap_dy[kMaxTaps], tap_dx[kMaxTaps], tap_slab[kMaxTaps];
   int T;               // weight slabs per sample
   int sy, sx, py, px;  // output pixel = (m*sy + py, n*sx + px)
-  int n_tile, k_chunks, stages;
+  int n_tile, k_chunks, stages, tmem_cols;
   int act;             // 0: raw accumulator, 1: noise + bias + leaky relu
   const float* noise;
   int noise_batched;
@@ -42,10 +42,16 @@ struct ConvGemmParams {
   const float* bias;
   float slope, gain;
   void* out;
+  // fused ToRGB (plain layers with a single N tile): rgb_w [B,3,O] modulated weights, rgb_out [B,3,OH,OW] fp32
+  const float* rgb_w;
+  const float* rgb_bias;
+  const float* rgb_skip;
+  const float* rgb_kf;
+  float* rgb_out;
 };
 
 template <bool TF32>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kGemmThreads, 3)
     modconv_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                         const ConvGemmParams p) {
   constexpr int EPA = TF32 ? 32 : 64;
@@ -56,6 +62,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   const int stage_bytes = A_STAGE_BYTES + b_stage_bytes;
   __shared__ uint64_t full[8], empty[8], acc_full;
   __shared__ uint32_t tmem_base_s;
+  __shared__ float4 s_rgbw[256];  // fused ToRGB weights of this image: (w_r, w_g, w_b, -) per output channel
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int tile = blockIdx.x, o0 = blockIdx.y * p.n_tile, b = blockIdx.z;
@@ -71,7 +78,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(&tmem_base_s, 256);
+    tmem_alloc(&tmem_base_s, p.tmem_cols);  // power of two >= n_tile: narrow layers leave TMEM for co-resident CTAs
     tmem_relinquish();
   }
   tc_fence_before();
@@ -129,6 +136,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       nz = nw * p.noise[(int64_t)(p.noise_batched ? b : 0) * p.OH * p.OW + (int64_t)oy * p.OW + ox];
     }
     OT* out = (OT*)p.out + (((int64_t)b * p.OH + oy) * p.OW + ox) * p.O + o0;
+    // fused ToRGB (model.py:360-369): the 1x1 modulated conv to 3 channels reads exactly the activations this thread
+    // holds, so it is 3 dot products in the epilogue instead of a kernel that re-reads the whole layer output from HBM
+    if (p.rgb_out) {
+      for (int e = tid - 64; e < p.n_tile; e += 128) {
+        const float* w = p.rgb_w + ((int64_t)b * 3) * p.O + o0 + e;
+        s_rgbw[e] = make_float4(w[0], w[p.O], w[2 * p.O], 0.f);
+      }
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+    }
+    float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
     mbar_wait(&acc_full, 0);
     tc_fence_after();
     for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
@@ -144,6 +161,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         for (int k = 0; k < 32; ++k) {
           float t = f[k] + nz + (p.bias ? __ldg(p.bias + o0 + c0 + k) : 0.f);
           f[k] = (t > 0.f ? t : t * p.slope) * p.gain;
+        }
+      }
+      if (p.rgb_out) {
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          const float4 w = s_rgbw[c0 + k];
+          const float a = TF32 ? __uint_as_float(f32_to_tf32_rna(f[k])) : __bfloat162float(__float2bfloat16_rn(f[k]));
+          rgb0 = fmaf(a, w.x, rgb0);
+          rgb1 = fmaf(a, w.y, rgb1);
+          rgb2 = fmaf(a, w.z, rgb2);
         }
       }
       const int ncols = min(32, p.n_tile - c0);
@@ -167,10 +194,34 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
           }
       }
     }
+    if (p.rgb_out && valid) {
+      float r3[3] = {rgb0 + p.rgb_bias[0], rgb1 + p.rgb_bias[1], rgb2 + p.rgb_bias[2]};
+      const int HW = p.OH * p.OW;
+      if (p.rgb_skip) {
+        // Upsample of the previous RGB: zero-insert x2, pad (2,1), flipped 4x4 taps (model.py:30-49)
+        const int h2 = p.OH / 2, w2 = p.OW / 2;
+#pragma unroll
+        for (int ky = 0; ky < 4; ++ky) {
+          const int uy = oy + ky - 2;
+          if (uy < 0 || (uy & 1) || (uy >> 1) >= h2) continue;
+#pragma unroll
+          for (int kx = 0; kx < 4; ++kx) {
+            const int ux = ox + kx - 2;
+            if (ux < 0 || (ux & 1) || (ux >> 1) >= w2) continue;
+            const float kv = __ldg(p.rgb_kf + 15 - (ky * 4 + kx));
+            const int64_t si = ((int64_t)b * 3 * h2 + (uy >> 1)) * w2 + (ux >> 1);
+#pragma unroll
+            for (int o = 0; o < 3; ++o) r3[o] = fmaf(kv, p.rgb_skip[si + (int64_t)o * h2 * w2], r3[o]);
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 0; o < 3; ++o) p.rgb_out[((int64_t)b * 3 + o) * HW + (int64_t)oy * p.OW + ox] = r3[o];
+    }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, 256);
+  if (warp == 1) tmem_dealloc(tmem, p.tmem_cols);
 }
 
 // ---- s[b, i] = latent[b, :] . Wm[i, :] / sqrt(K) + bm[i]   (EqualLinear, model.py:159-167, lr_mul = 1) -----------
@@ -268,57 +319,79 @@ __global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const OT* __restrict_
 // ---- 4x4 blur (pad 1,1) of the (2H+1)^2 NHWC intermediate fused with noise + bias + leaky relu --------------------
 // out[b,y,x,c] = gain * lrelu( sum_{a,e} kf[a][e] * mid[b, y+a-1, x+e-1, c] + nw*noise[b|0,y,x] + bias[c] )
 template <typename OT, int VEC>
-__global__ void __launch_bounds__(256) blur_act_nhwc_kernel(const OT* __restrict__ mid, OT* __restrict__ out,
+__global__ void __launch_bounds__(256, 4) blur_act_nhwc_kernel(const OT* __restrict__ mid, OT* __restrict__ out,
                                                             const float* __restrict__ kf /*4x4 blur.kernel*/,
                                                             const float* __restrict__ noise, int noise_batched,
                                                             const float* __restrict__ noise_w,
                                                             const float* __restrict__ bias, int B, int C, int OH, int OW,
                                                             int act, float slope, float gain) {
+  // Each thread owns a vertical strip of RY outputs of one (x, channel-vector) column and walks the RY+3 input rows once:
+  // every loaded vector feeds up to 4 output rows from registers (5.5 loads per output instead of 16). Consecutive
+  // threads take consecutive channel vectors, then consecutive x: every warp-level load is one contiguous 512-byte run.
+  constexpr int RY = 4;
   const int MH = OH + 1, MW = OW + 1;
   const int cv = C / VEC;
   __shared__ float sk[16];
   if (threadIdx.x < 16) sk[threadIdx.x] = kf[15 - threadIdx.x];  // flipped taps (upfirdn2d_kernel.cu:77)
   __syncthreads();
   const float nw = noise_w ? *noise_w : 1.f;
-  const int64_t total = (int64_t)B * OH * OW * cv;
+  const int strips = (OH + RY - 1) / RY;
+  const int64_t total = (int64_t)B * strips * OW * cv;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(idx % cv) * VEC;
     int64_t t = idx / cv;
     const int x = (int)(t % OW);
     t /= OW;
-    const int y = (int)(t % OH);
-    const int b = (int)(t / OH);
-    float acc[VEC];
+    const int y0 = (int)(t % strips) * RY;
+    const int b = (int)(t / strips);
+    float acc[RY][VEC];
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+    for (int r = 0; r < RY; ++r)
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      const int yy = y + a - 1;
+      for (int k = 0; k < VEC; ++k) acc[r][k] = 0.f;
+#pragma unroll
+    for (int rr = 0; rr < RY + 3; ++rr) {
+      const int yy = y0 + rr - 1;
       if (yy < 0 || yy >= MH) continue;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int xx = x + e - 1;
         if (xx < 0 || xx >= MW) continue;
-        const OT* src = mid + (((int64_t)b * MH + yy) * MW + xx) * C + c;
-        const float kv = sk[a * 4 + e];
-        Vec16<OT> v = ld_vec16(src);
+        const Vec16<OT> v = ld_vec16(mid + (((int64_t)b * MH + yy) * MW + xx) * C + c);
+        float f[VEC];
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) acc[k] = fmaf(to_f32<OT>(v.e[k]), kv, acc[k]);
+        for (int k = 0; k < VEC; ++k) f[k] = to_f32<OT>(v.e[k]);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          const int r = rr - a;  // output row y0 + r reads input row (y0 + r) + a - 1
+          if (r < 0 || r >= RY) continue;
+          const float kv = sk[a * 4 + e];
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) acc[r][k] = fmaf(f[k], kv, acc[r][k]);
+        }
       }
     }
-    Vec16<OT> o;
-    if (act) {
-      const float nz = noise ? nw * noise[(int64_t)(noise_batched ? b : 0) * OH * OW + (int64_t)y * OW + x] : 0.f;
+    float bv[VEC];
 #pragma unroll
-      for (int k = 0; k < VEC; ++k) {
-        float u = acc[k] + nz + (bias ? __ldg(bias + c + k) : 0.f);
-        o.e[k] = from_f32<OT>((u > 0.f ? u : u * slope) * gain);
+    for (int k = 0; k < VEC; ++k) bv[k] = (act && bias) ? __ldg(bias + c + k) : 0.f;
+#pragma unroll
+    for (int r = 0; r < RY; ++r) {
+      const int y = y0 + r;
+      if (y >= OH) break;
+      Vec16<OT> o;
+      if (act) {
+        const float nz = noise ? nw * noise[(int64_t)(noise_batched ? b : 0) * OH * OW + (int64_t)y * OW + x] : 0.f;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+          const float u = acc[r][k] + nz + bv[k];
+          o.e[k] = from_f32<OT>((u > 0.f ? u : u * slope) * gain);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) o.e[k] = from_f32<OT>(acc[r][k]);
       }
-    } else {
-#pragma unroll
-      for (int k = 0; k < VEC; ++k) o.e[k] = from_f32<OT>(acc[k]);
+      st_vec16(out + (((int64_t)b * OH + y) * OW + x) * C + c, o);
     }
-    st_vec16(out + (((int64_t)b * OH + y) * OW + x) * C + c, o);
   }
 }
 
@@ -412,12 +485,18 @@ int launch_gemm_class(const CUtensorMap& mx, const CUtensorMap& mw, ConvGemmPara
   auto kern = modconv_gemm_kernel<TF32>;
   static bool attr_set = false;
   if (!attr_set) {
-    FMI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
+    FMI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 6144));  // static: 5 KB
     attr_set = true;
   }
   const int stage_bytes = A_STAGE_BYTES + p.n_tile * 128;
-  int stages = (232448 - 4096) / stage_bytes;
+  int stages = (232448 - 8192) / stage_bytes;
   if (stages > 8) stages = 8;
+  // A tile of a narrow high-resolution layer is only ntaps * k_chunks = 9..18 pipeline steps: the per-CTA fixed cost
+  // (TMEM alloc, barrier init, first TMA) dominates when one CTA owns the SM (ncu: 32->32 @1024^2 ran at 1/15 of its HBM
+  // roofline). Keep the ring at 3 stages there so 2-3 CTAs are co-resident and overlap each other's prologue/epilogue.
+  const int total_iters = p.ntaps * p.k_chunks;
+  if (total_iters <= 36 && stages > 3) stages = 3;
+  p.tmem_cols = p.n_tile <= 32 ? 32 : p.n_tile <= 64 ? 64 : p.n_tile <= 128 ? 128 : 256;
   p.stages = stages;
   const size_t smem = (size_t)stages * stage_bytes + 1024;
   TilePlan tp = pick_tile(p.Mh, p.Mw);
@@ -496,10 +575,63 @@ extern "C" int64_t fmi_styled_conv_workspace_bytes(int B, int O, int H, int W, i
   return (int64_t)B * (2 * H + 1) * (2 * W + 1) * O * esz_of(mma);
 }
 
+namespace {
+struct RgbFuse {  // fused ToRGB of a plain StyledConv (fmi_styled_conv_torgb_nhwc)
+  const float* w;     // [B,3,O] modulated weights (fmi_torgb_weights)
+  const float* bias;  // [3]
+  const float* skip;  // [B,3,H/2,W/2] or NULL
+  const float* kf;    // 4x4 upsample kernel (needed with skip)
+  float* out;         // [B,3,H,W]
+};
+int styled_conv_impl(const void* x, const void* wp, void* y, const float* noise, int noise_batched, const float* noise_w,
+                     const float* act_bias, const float* blur_k, int B, int I, int O, int H, int W, int upsample, int act,
+                     int mma, void* workspace, int64_t workspace_bytes, void* stream, const RgbFuse* rgb);
+}  // namespace
+
 extern "C" int fmi_styled_conv_nhwc(const void* x, const void* wp, void* y, const float* noise, int noise_batched,
                                     const float* noise_w, const float* act_bias, const float* blur_k, int B, int I, int O,
                                     int H, int W, int upsample, int act, int mma, void* workspace, int64_t workspace_bytes,
                                     void* stream) {
+  return styled_conv_impl(x, wp, y, noise, noise_batched, noise_w, act_bias, blur_k, B, I, O, H, W, upsample, act, mma,
+                          workspace, workspace_bytes, stream, nullptr);
+}
+
+// rgb_w[b][o][c] = W[o,c] * s[b,c] / sqrt(C)   (ToRGB's modulated, not demodulated, 1x1 weights; model.py:357,245)
+__global__ void __launch_bounds__(256) torgb_weights_kernel(const float* __restrict__ w, const float* __restrict__ s,
+                                                            float* __restrict__ out, int B, int C, float scale) {
+  const int total = B * 3 * C;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int c = e % C, o = (e / C) % 3, b = e / (3 * C);
+    out[e] = scale * w[o * C + c] * s[b * C + c];
+  }
+}
+
+extern "C" int fmi_torgb_weights(const float* weight, const float* s, float* rgb_w, int B, int C, void* stream) {
+  if (B == 0) return FMI_OK;
+  FMI_REQUIRE(weight && s && rgb_w && C >= 1, "torgb_weights: bad arguments");
+  torgb_weights_kernel<<<(B * 3 * C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(weight, s, rgb_w, B, C,
+                                                                                   1.0f / sqrtf((float)C));
+  return fmi_launched("torgb_weights");
+}
+
+// A plain (non-upsampling) StyledConv with the following ToRGB fused into its epilogue (O <= 256):
+//   y as fmi_styled_conv_nhwc(act = 1); rgb[b,o,p] = sum_c rgb_w[b,o,c] * y[b,p,c] + rgb_bias[o] + upsample(skip)[b,o,p].
+extern "C" int fmi_styled_conv_torgb_nhwc(const void* x, const void* wp, void* y, const float* noise, int noise_batched,
+                                          const float* noise_w, const float* act_bias, const float* rgb_w,
+                                          const float* rgb_bias, const float* rgb_skip, const float* rgb_kernel, float* rgb,
+                                          int B, int I, int O, int H, int W, int mma, void* stream) {
+  FMI_REQUIRE(rgb_w && rgb_bias && rgb, "styled_conv_torgb: null pointer");
+  FMI_REQUIRE(O <= 256, "styled_conv_torgb: fused ToRGB needs O <= 256 (got %d); use fmi_torgb_nhwc", O);
+  FMI_REQUIRE(!rgb_skip || (rgb_kernel && H % 2 == 0 && W % 2 == 0), "styled_conv_torgb: skip needs the kernel and even H, W");
+  RgbFuse f{rgb_w, rgb_bias, rgb_skip, rgb_kernel, rgb};
+  return styled_conv_impl(x, wp, y, noise, noise_batched, noise_w, act_bias, nullptr, B, I, O, H, W, 0, 1, mma, nullptr, 0,
+                          stream, &f);
+}
+
+namespace {
+int styled_conv_impl(const void* x, const void* wp, void* y, const float* noise, int noise_batched, const float* noise_w,
+                     const float* act_bias, const float* blur_k, int B, int I, int O, int H, int W, int upsample, int act,
+                     int mma, void* workspace, int64_t workspace_bytes, void* stream, const RgbFuse* rgb) {
   FMI_REQUIRE(mma == FMI_MMA_TF32 || mma == FMI_MMA_BF16, "styled_conv: bad mma");
   if (B == 0) return FMI_OK;
   FMI_REQUIRE(x && wp && y, "styled_conv: null pointer");
@@ -544,12 +676,16 @@ extern "C" int fmi_styled_conv_nhwc(const void* x, const void* wp, void* y, cons
     p.ntaps = 9;
     for (int t = 0; t < 9; ++t) { p.tap_dy[t] = t / 3 - 1; p.tap_dx[t] = t % 3 - 1; p.tap_slab[t] = t; }
     p.act = act; p.out = y;
+    if (rgb) {
+      p.rgb_w = rgb->w; p.rgb_bias = rgb->bias; p.rgb_skip = rgb->skip; p.rgb_kf = rgb->kf; p.rgb_out = rgb->out;
+    }
     TilePlan tp = pick_tile(p.Mh, p.Mw);
     CUtensorMap mx;
     int e = make_x_map(&mx, tp.TH, tp.TW);
     FMI_REQUIRE(e == 0, "styled_conv: cuTensorMapEncodeTiled(x) failed (%d)", e);
     return tf32 ? launch_gemm_class<true>(mx, mw, p, st) : launch_gemm_class<false>(mx, mw, p, st);
   }
+  FMI_REQUIRE(!rgb, "styled_conv: ToRGB fusion is for plain (non-upsampling) layers");
 
   // ---- upsample: conv_transpose2d(stride 2) by output parity class, then blur + epilogue
   const int MH = 2 * H + 1, MW = 2 * W + 1;
@@ -582,7 +718,7 @@ extern "C" int fmi_styled_conv_nhwc(const void* x, const void* wp, void* y, cons
     }
   // blur: flipped taps (upfirdn2d_kernel.cu:77)
   const int OH = 2 * H, OW = 2 * W;
-  const int64_t total_vec = (int64_t)B * OH * OW * (O * esz / 16);
+  const int64_t total_vec = (int64_t)B * ((OH + 3) / 4) * OW * (O * esz / 16);  // one thread per 4-row strip
   int grid = (int)imin64((total_vec + 255) / 256, (int64_t)FMI_NUM_SMS * 32);
   if (tf32)
     blur_act_nhwc_kernel<float, 4><<<grid, 256, 0, st>>>((const float*)workspace, (float*)y, blur_k, noise, noise_batched,
@@ -593,6 +729,7 @@ extern "C" int fmi_styled_conv_nhwc(const void* x, const void* wp, void* y, cons
                                                                  act, p.slope, p.gain);
   return fmi_launched("blur_act");
 }
+}  // namespace
 
 extern "C" int fmi_torgb_nhwc(const void* x, const float* weight, const float* s, const float* bias, const float* skip,
                               const float* blur_k, float* rgb, int B, int I, int H, int W, int mma, void* stream) {

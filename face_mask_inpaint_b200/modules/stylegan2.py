@@ -191,6 +191,25 @@ def styled_conv_nhwc(x, wp, o, upsample, act, mma, noise=None, noise_w=None, act
     return y
 
 
+def styled_conv_torgb_nhwc(x, wp, o, mma, noise, noise_w, act_bias, rgb_weight, rgb_s, rgb_bias, skip, up_kernel):
+    """Plain StyledConv + the ToRGB that follows it, one kernel (fmi_styled_conv_torgb_nhwc; O <= 256).
+    Returns (activations NHWC, rgb [B,3,H,W] fp32)."""
+    b, h, w, i = x.shape
+    lib = _lib.load()
+    y = torch.empty((b, h, w, o), dtype=x.dtype, device=x.device)
+    rgb = torch.empty((b, 3, h, w), dtype=torch.float32, device=x.device)
+    rgb_w = torch.empty((b, 3, o), dtype=torch.float32, device=x.device)
+    _lib.check(lib.fmi_torgb_weights(_p(rgb_weight), _p(rgb_s), _p(rgb_w), b, o, ops._stream()), "fmi_torgb_weights")
+    noise = noise.float().contiguous()
+    nb = 1 if (noise.shape[0] == b and b > 1) else 0
+    if skip is not None:
+        skip = skip.float().contiguous()
+    _lib.check(lib.fmi_styled_conv_torgb_nhwc(_p(x), _p(wp), _p(y), _p(noise), nb, _p(noise_w), _p(act_bias), _p(rgb_w),
+                                              _p(rgb_bias), _p(skip), _p(up_kernel), _p(rgb), b, i, o, h, w, mma,
+                                              ops._stream()), "fmi_styled_conv_torgb_nhwc")
+    return y, rgb
+
+
 def torgb_nhwc(x, weight, s, bias, skip, blur_k, mma):
     b, h, w, i = x.shape
     rgb = torch.empty((b, 3, h, w), dtype=torch.float32, device=x.device)
@@ -435,8 +454,18 @@ class Generator(nn.Module):
         for conv1, conv2, noise1, noise2, to_rgb in zip(self.convs[::2], self.convs[1::2], noise[1::2], noise[2::2],
                                                         self.to_rgbs):
             out = conv1.forward_nhwc(out, lat[:, i], mma, noise=noise1)
-            out = conv2.forward_nhwc(out, lat[:, i + 1], mma, noise=noise2)
-            skip = to_rgb.forward_nhwc(out, lat[:, i + 2], mma, skip)
+            if conv2.conv.out_channel <= 256 and not conv2.conv.upsample:
+                # conv2 + ToRGB in one kernel (the RGB projection rides in conv2's epilogue)
+                b, h, w, _ = out.shape
+                conv2.conv._check()
+                wp = prep_weights(conv2.conv.weight, conv2.conv.styles(lat[:, i + 1]), conv2.conv.demodulate, mma)
+                out, skip = styled_conv_torgb_nhwc(
+                    out, wp, conv2.conv.out_channel, mma, conv2._noise(noise2, b, h, w, out.device), conv2.noise.weight,
+                    conv2.activate.bias, to_rgb.conv.weight, to_rgb.conv.styles(lat[:, i + 2]), to_rgb.bias, skip,
+                    to_rgb.upsample.kernel)
+            else:
+                out = conv2.forward_nhwc(out, lat[:, i + 1], mma, noise=noise2)
+                skip = to_rgb.forward_nhwc(out, lat[:, i + 2], mma, skip)
             i += 2
         image = skip.to(in_dtype) if in_dtype != torch.float32 else skip
         if return_latents:

@@ -200,6 +200,16 @@ int fmi_styled_conv_nhwc(const void* x, const void* wp, void* y, const float* no
                          int O, int H, int W, int upsample, int act, int mma, void* workspace,
                          int64_t workspace_bytes, void* stream);
 
+/* A plain StyledConv with the following ToRGB fused into its epilogue (StyledConv.forward :340-346 followed by
+ *   ToRGB.forward :360-369 on its output, Generator.forward :537-539) for O <= 256: the 1x1 modulated conv to 3
+ *   channels is accumulated from the activations the epilogue already holds, so the layer output is not re-read.
+ *   rgb_w [B,3,O] = W[o,c]*s[b,c]/sqrt(O) from fmi_torgb_weights; rgb_skip [B,3,H/2,W/2] or NULL; rgb [B,3,H,W] fp32. */
+int fmi_torgb_weights(const float* weight, const float* s, float* rgb_w, int B, int C, void* stream);
+int fmi_styled_conv_torgb_nhwc(const void* x, const void* wp, void* y, const float* noise, int noise_batched,
+                               const float* noise_w, const float* act_bias, const float* rgb_w,
+                               const float* rgb_bias, const float* rgb_skip, const float* rgb_kernel, float* rgb,
+                               int B, int I, int O, int H, int W, int mma, void* stream);
+
 /* ToRGB (model.py:360-369): rgb[b,o,p] = sum_i (W[o,i]*s[b,i]/sqrt(I)) * x[b,p,i] + bias[o]
  *   + upfirdn2d(skip, blur_k, up=2, pad=(2,1)) (Upsample, model.py:30-49) when skip != NULL.
  *   x NHWC operand type; weight [3,I], s [B,I], bias [3], skip [B,3,H/2,W/2], rgb [B,3,H,W] fp32. */
