@@ -263,8 +263,12 @@ def run_ours(args, rank, local_rank, world):
         "e2e": {"value": world * BATCH / (ms_e2e * 1e-3), "unit": "img/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": ms_e2e},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "kernel": "attn_fwd_kernel<TF32>", "achieved": achieved, "peak": peak_tf,
-                     "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
+        "roofline": {"bound": "tensor", "kernel": "attn_fwd2_kernel<TF32,float,cluster2>", "achieved": achieved,
+                     "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the round-1 `ncu --set full` capture of
+                     # this command (profiles/r01_ncu_attn_fwd2_tf32_summary.csv): 595 MB + 502 MB
+                     "traffic": 1.097e9, "traffic_unit": "bytes/launch (ncu)",
+                     "algorithmic_bytes_per_launch": 6.86e8,
                      "kernel_ms": kern_ms, "launches_timed": n.value, "algorithmic_flops_per_launch": flops_launch,
                      "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_kind}); the kernel runs "
                                     "kind::tf32 MMAs whose nominal rate is half the bf16 rate"},

@@ -8,6 +8,6 @@ CMD="python bench.py --steps 3 --warmup 3"
 $CMD > gpurun_out/plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_attn.csv $CMD > gpurun_out/ncu1.log 2>&1
 $CMD > gpurun_out/plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:attn_fwd -s 3 -c 2 -f -o gpurun_out/prof_attn $CMD > gpurun_out/ncu2.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:attn_fwd2 -s 3 -c 2 -f -o gpurun_out/prof_attn $CMD > gpurun_out/ncu2.log 2>&1
 tail -3 gpurun_out/ncu2.log
 ls -la gpurun_out/
