@@ -50,6 +50,10 @@ PROTOTYPES = {
                                   _vp]),
     "fmi_torgb_nhwc": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "fmi_torgb_weights": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "fmi_styled_conv_bwd_workspace_bytes": (_i64, [_i, _i, _i, _i, _i, _i, _i, _i]),
+    "fmi_styled_conv_bwd_nhwc": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i,
+                                      _i, _i, _i, _i, _vp, _i64, _vp]),
+    "fmi_torgb_bwd_nhwc": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "fmi_styled_conv_torgb_nhwc": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i,
                                         _vp]),
 }

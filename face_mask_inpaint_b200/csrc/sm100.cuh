@@ -169,6 +169,28 @@ __device__ __forceinline__ uint64_t make_sdesc_k_sw128(uint32_t smem_addr) {
   return d;
 }
 
+// Shared-memory matrix descriptor for an MN-major operand: rows of the tile are K indices (128-byte rows = one atom of
+// 64 bf16 / 32 tf32 MN elements, SWIZZLE_128B — what TMA writes for an NHWC box {64 ch, pixels} when the pixels are the
+// contraction index). Canonical layout ((T,8,m),(8,k)):((1,T,LBO),(8T,SBO)): 8 K rows are 128 B apart, the next 8-row
+// group is SBO = 1024 B further, the next MN atom (next 128 bytes of channels) starts LBO bytes further.
+// 32-bit operands (tf32) only exist MN-major in the SWIZZLE_128B_BASE32B flavour (layout type 1; TMA writes it with
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): 32-byte chunks permuted by (row mod 4), so the K atom is 4 rows and SBO = 512 B.
+// Plain SWIZZLE_128B with kind::tf32 MN-major silently accumulates nothing (measured).
+__device__ __forceinline__ uint64_t make_sdesc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes, bool base32b = false) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((base32b ? 512 : 1024) >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(base32b ? 1 : 2) << 61;
+  return d;
+}
+
+// fp32 reduction into global memory, 16 bytes at a time
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 // ---- tcgen05: MMA -----------------------------------------------------------------------------
 // D[tmem] (+)= A[smem] * B[smem]^T ; kind::f16 covers fp16/bf16, kind::tf32 covers tf32
 __device__ __forceinline__ void mma_ss_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,

@@ -26,11 +26,8 @@ def _p(t):
     return None if t is None else t.data_ptr()
 
 
-def _no_grad_only(*tensors):
-    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
-        raise NotImplementedError(
-            "fmi_b200: the modulated-conv backward kernels (dgrad/wgrad) are not implemented yet; run the StyleGAN2 "
-            "decoder under torch.no_grad() (there is no PyTorch fallback by design)")
+def _wants_grad(*tensors):
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
 
 
 class PixelNorm(nn.Module):
@@ -129,7 +126,7 @@ def _op_dtype(mma):
     return torch.float32 if mma == _lib.MMA_TF32 else torch.bfloat16
 
 
-def to_nhwc(x, mma):
+def _to_nhwc_raw(x, mma):
     b, c, h, w = x.shape
     xc = x.contiguous()
     y = torch.empty((b, h, w, c), dtype=_op_dtype(mma), device=x.device)
@@ -138,25 +135,77 @@ def to_nhwc(x, mma):
     return y
 
 
-def to_nchw(y, mma, dtype):
+def _to_nchw_raw(y, mma, dtype):
     b, h, w, c = y.shape
+    yc = y.contiguous()
     x = torch.empty((b, c, h, w), dtype=dtype, device=y.device)
-    _lib.check(_lib.load().fmi_nhwc_to_nchw(_p(y), _p(x), b, c, h, w, mma, ops._DT[dtype], ops._stream()),
+    _lib.check(_lib.load().fmi_nhwc_to_nchw(_p(yc), _p(x), b, c, h, w, mma, ops._DT[dtype], ops._stream()),
                "fmi_nhwc_to_nchw")
     return x
 
 
+class _ToNHWC(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, mma):
+        ctx.mma, ctx.dtype = mma, x.dtype
+        return _to_nhwc_raw(x, mma)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _to_nchw_raw(g, ctx.mma, ctx.dtype), None
+
+
+class _ToNCHW(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y, mma, dtype):
+        ctx.mma = mma
+        return _to_nchw_raw(y, mma, dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _to_nhwc_raw(g, ctx.mma), None, None
+
+
+def to_nhwc(x, mma):
+    """NCHW (any supported dtype) -> NHWC in the tensor-core operand type; differentiable."""
+    return _ToNHWC.apply(x, mma)
+
+
+def to_nchw(y, mma, dtype):
+    return _ToNCHW.apply(y, mma, dtype)
+
+
+class _StyleModFn(torch.autograd.Function):
+    """s = EqualLinear(style) (model.py:244, :159-167 with lr_mul = 1). The backward is three tiny dense products
+    ([B,I] x [I,K]) done as library GEMMs, like EqualLinear's own F.linear."""
+
+    @staticmethod
+    def forward(ctx, style, mod_weight, mod_bias):
+        st = style.float()
+        if st.stride(-1) != 1:
+            st = st.contiguous()
+        b, k = st.shape
+        i = mod_weight.shape[0]
+        s = torch.empty((b, i), dtype=torch.float32, device=st.device)
+        _lib.check(_lib.load().fmi_style_modulation(_p(st), st.stride(0), _p(mod_weight), _p(mod_bias), _p(s), b, k, i,
+                                                    ops._stream()), "fmi_style_modulation")
+        ctx.save_for_backward(st, mod_weight)
+        ctx.style_dtype = style.dtype
+        return s
+
+    @staticmethod
+    def backward(ctx, ds):
+        st, mw = ctx.saved_tensors
+        scale = 1.0 / math.sqrt(st.shape[1])
+        dstyle = (ds @ mw) * scale if ctx.needs_input_grad[0] else None
+        dmw = (ds.t() @ st) * scale if ctx.needs_input_grad[1] else None
+        dmb = ds.sum(0) if ctx.needs_input_grad[2] else None
+        return (dstyle.to(ctx.style_dtype) if dstyle is not None else None), dmw, dmb
+
+
 def style_modulation(style, mod_weight, mod_bias):
     """s = EqualLinear(style) (model.py:244); style may be a strided row view latent[:, i]."""
-    st = style.float()
-    if st.stride(-1) != 1:
-        st = st.contiguous()
-    b, k = st.shape
-    i = mod_weight.shape[0]
-    s = torch.empty((b, i), dtype=torch.float32, device=st.device)
-    _lib.check(_lib.load().fmi_style_modulation(_p(st), st.stride(0), _p(mod_weight), _p(mod_bias), _p(s), b, k, i,
-                                                ops._stream()), "fmi_style_modulation")
-    return s
+    return _StyleModFn.apply(style, mod_weight, mod_bias)
 
 
 def prep_weights(weight, s, demodulate, mma):
@@ -220,6 +269,81 @@ def torgb_nhwc(x, weight, s, bias, skip, blur_k, mma):
     return rgb
 
 
+class _StyledConvFn(torch.autograd.Function):
+    """fmi_styled_conv_nhwc / fmi_styled_conv_bwd_nhwc: the whole StyledConv (model.py:340-346) or, with act=False,
+    ModulatedConv2d alone (:241-279) on NHWC operands, differentiable w.r.t. x, weight, s, noise_w and act_bias."""
+
+    @staticmethod
+    def forward(ctx, x, weight, s, noise, noise_w, act_bias, blur_k, demodulate, upsample, act, mma):
+        o = weight.shape[1]
+        x = x.contiguous()
+        wp = prep_weights(weight, s, demodulate, mma)
+        y = styled_conv_nhwc(x, wp, o, upsample, act, mma, noise, noise_w, act_bias, blur_k)
+        if noise is not None:
+            noise = noise.float().contiguous()
+        ctx.save_for_backward(x, weight, s, noise, blur_k, y if act else None)
+        ctx.cfg = (bool(demodulate), bool(upsample), bool(act), mma)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, s, noise, blur_k, y = ctx.saved_tensors
+        demodulate, upsample, act, mma = ctx.cfg
+        b, h, w, i = x.shape
+        o = weight.shape[1]
+        dy = dy.contiguous()
+        if dy.dtype != x.dtype:
+            dy = dy.to(x.dtype)
+        dev = x.device
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dw = torch.empty(weight.shape, dtype=torch.float32, device=dev)
+        ds = torch.empty((b, i), dtype=torch.float32, device=dev)
+        dnw = torch.empty(1, dtype=torch.float32, device=dev) if act else None
+        dbias = torch.empty(o, dtype=torch.float32, device=dev) if act else None
+        lib = _lib.load()
+        nbytes = lib.fmi_styled_conv_bwd_workspace_bytes(b, i, o, h, w, int(upsample), int(act), mma)
+        ws = ops._workspace(dev, nbytes)
+        nb = int(noise is not None and noise.shape[0] == b and b > 1)
+        _lib.check(lib.fmi_styled_conv_bwd_nhwc(_p(x), _p(y), _p(dy), _p(weight), _p(s), _p(noise), nb, _p(blur_k), _p(dx),
+                                                _p(dw), _p(ds), _p(dnw), _p(dbias), b, i, o, h, w, int(upsample), int(act),
+                                                int(demodulate), mma, ws.data_ptr(), ws.numel(), ops._stream()),
+                   "fmi_styled_conv_bwd_nhwc")
+        return dx, dw, ds, None, dnw, dbias, None, None, None, None, None
+
+
+class _ToRGBFn(torch.autograd.Function):
+    """fmi_torgb_nhwc without the skip branch / fmi_torgb_bwd_nhwc (model.py:360-364)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, s, bias, mma):
+        x = x.contiguous()
+        ctx.save_for_backward(x, weight, s)
+        ctx.mma = mma
+        return torgb_nhwc(x, weight, s, bias, None, None, mma)
+
+    @staticmethod
+    def backward(ctx, drgb):
+        x, weight, s = ctx.saved_tensors
+        mma = ctx.mma
+        b, h, w, c = x.shape
+        dev = x.device
+        lib = _lib.load()
+        drgb = drgb.float().contiguous()
+        rgb_w = torch.empty((b, 3, c), dtype=torch.float32, device=dev)
+        _lib.check(lib.fmi_torgb_weights(_p(weight), _p(s), _p(rgb_w), b, c, ops._stream()), "fmi_torgb_weights")
+        dx = torch.empty_like(x)
+        d_rgbw = torch.empty((b, 3, c), dtype=torch.float32, device=dev)
+        dbias = torch.empty(3, dtype=torch.float32, device=dev)
+        _lib.check(lib.fmi_torgb_bwd_nhwc(_p(x), _p(drgb), _p(rgb_w), _p(dx), _p(d_rgbw), _p(dbias), b, c, h, w, mma,
+                                          ops._stream()), "fmi_torgb_bwd_nhwc")
+        # rgb_w[b,o,c] = W[o,c] s[b,c] / sqrt(C): [B,3,C]-sized products, host-side plumbing
+        scale = 1.0 / math.sqrt(c)
+        w2 = weight.reshape(3, c)
+        dw = (torch.einsum('boc,bc->oc', d_rgbw, s) * scale).reshape(weight.shape)
+        ds = torch.einsum('boc,oc->bc', d_rgbw, w2) * scale
+        return dx, dw, ds, dbias.reshape(1, 3, 1, 1), None
+
+
 # ----------------------------------------------------------------------------------------------------
 # modules
 # ----------------------------------------------------------------------------------------------------
@@ -267,12 +391,10 @@ class ModulatedConv2d(nn.Module):
     def forward_nhwc(self, x, s, mma, act=False, noise=None, noise_w=None, act_bias=None):
         """x NHWC operand type; s the modulation [B,I] (from `styles`)."""
         self._check()
-        wp = prep_weights(self.weight, s, self.demodulate, mma)
-        return styled_conv_nhwc(x, wp, self.out_channel, self.upsample, act, mma, noise, noise_w, act_bias,
-                                self.blur.kernel if self.upsample else None)
+        return _StyledConvFn.apply(x, self.weight, s, noise, noise_w, act_bias, self.blur.kernel if self.upsample else None,
+                                   self.demodulate, self.upsample, act, mma)
 
     def forward(self, input, style):
-        _no_grad_only(input, style, self.weight)
         ops._need_cuda(input, style)
         mma = ops.mma_mode(input.dtype)
         s = self.styles(style)
@@ -280,7 +402,7 @@ class ModulatedConv2d(nn.Module):
             if self.out_channel != 3 or self.demodulate:
                 raise NotImplementedError("fmi_b200: 1x1 modulated conv is implemented for ToRGB (3 channels, no demod)")
             zero = torch.zeros(3, device=input.device)
-            return torgb_nhwc(to_nhwc(input, mma), self.weight, s, zero, None, None, mma).to(input.dtype)
+            return _ToRGBFn.apply(to_nhwc(input, mma), self.weight, s, zero, mma).to(input.dtype)
         y = self.forward_nhwc(to_nhwc(input, mma), s, mma)
         return to_nchw(y, mma, input.dtype)
 
@@ -332,7 +454,6 @@ class StyledConv(nn.Module):
                                       act_bias=self.activate.bias)
 
     def forward(self, input, style, noise=None):
-        _no_grad_only(input, style, self.conv.weight)
         ops._need_cuda(input, style)
         mma = ops.mma_mode(input.dtype)
         y = self.forward_nhwc(to_nhwc(input, mma), style, mma, noise)
@@ -351,6 +472,12 @@ class ToRGB(nn.Module):
 
     def forward_nhwc(self, x, style, mma, skip=None):
         s = self.conv.styles(style)
+        if _wants_grad(x, s, skip, self.conv.weight, self.bias):
+            # training: the 1x1 modulated conv through its own backward kernel, the skip through upfirdn2d's
+            rgb = _ToRGBFn.apply(x, self.conv.weight, s, self.bias, mma)
+            if skip is not None:
+                rgb = rgb + self.upsample(skip.float())
+            return rgb
         blur_k = None
         if skip is not None:
             if self.upsample.kernel.shape != (4, 4) or self.upsample.pad != (2, 1):
@@ -359,7 +486,6 @@ class ToRGB(nn.Module):
         return torgb_nhwc(x, self.conv.weight, s, self.bias, skip, blur_k, mma)
 
     def forward(self, input, style, skip=None):
-        _no_grad_only(input, style, skip, self.conv.weight)
         ops._need_cuda(input, style)
         mma = ops.mma_mode(input.dtype)
         return self.forward_nhwc(to_nhwc(input, mma), style, mma, skip).to(input.dtype)
@@ -441,10 +567,10 @@ class Generator(nn.Module):
             latent2 = styles[1].unsqueeze(1).repeat(1, self.n_latent - inject_index, 1)
             latent = torch.cat([latent, latent2], 1)
 
-        _no_grad_only(latent, self.conv1.conv.weight)
         ops._need_cuda(latent)
         in_dtype = latent.dtype
         mma = ops.mma_mode(in_dtype)
+        train = _wants_grad(latent, *self.parameters())
         lat = latent.float()
         # synthesis (model.py:528-541) in NHWC operand layout
         out = to_nhwc(self.input(lat), mma)
@@ -454,7 +580,7 @@ class Generator(nn.Module):
         for conv1, conv2, noise1, noise2, to_rgb in zip(self.convs[::2], self.convs[1::2], noise[1::2], noise[2::2],
                                                         self.to_rgbs):
             out = conv1.forward_nhwc(out, lat[:, i], mma, noise=noise1)
-            if conv2.conv.out_channel <= 256 and not conv2.conv.upsample:
+            if conv2.conv.out_channel <= 256 and not conv2.conv.upsample and not train:
                 # conv2 + ToRGB in one kernel (the RGB projection rides in conv2's epilogue)
                 b, h, w, _ = out.shape
                 conv2.conv._check()

@@ -217,6 +217,25 @@ int fmi_torgb_nhwc(const void* x, const float* weight, const float* s, const flo
                    const float* skip, const float* blur_k, float* rgb, int B, int I, int H, int W, int mma,
                    void* stream);
 
+/* Backward of fmi_styled_conv_nhwc (training: train_psp.py with train_decoder goes through it by autograd; the
+ *   reference differentiates model.py:241-279 + :289-294 + fused_act.py:18-47 with ATen).
+ *   Inputs: x, y (the forward output, needed when act = 1), dy [B,OH,OW,O] in the operand type, the fp32 parameter
+ *   `weight` [O,I,3,3], the modulation s [B,I], noise as in the forward.
+ *   Outputs: dx [B,H,W,I] operand type (NULL to skip), dweight [O,I,3,3] fp32 (through modulation AND demodulation),
+ *   ds [B,I] fp32, and with act = 1: dnoise_w (1 float) and dbias [O] fp32. Outputs are overwritten, not accumulated.
+ *   H and W must be powers of two >= 4; I, O multiples of 32, I <= 512. */
+int64_t fmi_styled_conv_bwd_workspace_bytes(int B, int I, int O, int H, int W, int upsample, int act, int mma);
+int fmi_styled_conv_bwd_nhwc(const void* x, const void* y, const void* dy, const float* weight, const float* s,
+                             const float* noise, int noise_batched, const float* blur_k, void* dx, float* dweight,
+                             float* ds, float* dnoise_w, float* dbias, int B, int I, int O, int H, int W, int upsample,
+                             int act, int demodulate, int mma, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Backward of the 1x1 modulated conv of ToRGB (model.py:360-369): dx[b,p,c] = sum_o rgb_w[b,o,c] * drgb[b,o,p]
+ *   (operand type, NHWC), d_rgbw[b,o,c] = sum_p drgb[b,o,p] * x[b,p,c] (fp32, gradient w.r.t. the modulated weights
+ *   rgb_w = fmi_torgb_weights), dbias[o] = sum drgb. The skip branch is differentiated by fmi_upfirdn2d. */
+int fmi_torgb_bwd_nhwc(const void* x, const float* drgb, const float* rgb_w, void* dx, float* d_rgbw, float* dbias,
+                       int B, int I, int H, int W, int mma, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,236 @@
+"""GPU gradient parity of the StyleGAN2 decoder path (a3 ModulatedConv2d, a6 StyledConv / ToRGB / Generator) against
+autograd through the CPU oracle (the reference's own formulation, modules/psp/stylegan2/model.py:241-279, :340-369).
+Needed by train_psp.py (train_decoder): fmi_styled_conv_bwd_nhwc / fmi_torgb_bwd_nhwc.
+Tolerance per gradient tensor: north_star's max|a-b|/max|b| <= 1e-3 for fp32 I/O (TF32 operands), <= 2e-2 for bf16.
+
+The leaky-ReLU derivative is discontinuous at 0: an element whose pre-activation lies within the FORWARD tolerance of zero
+takes the other slope (a 5x change of that element's gradient), which says nothing about the backward kernels. The oracle
+gradient is therefore evaluated at the activation pattern of the forward under test (mask = y > 0 taken from our output);
+everything else — convolution, blur, modulation, demodulation, noise, bias — is the reference formulation under autograd.
+`noise.weight` is a scalar sum of ~1e4..1e6 signed terms, so it is compared against the size of that sum's terms."""
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import ref_ops as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+MODES = [("fp32", torch.float32, 1e-3), ("bf16", torch.bfloat16, 2e-2)]
+
+
+def _mods():
+    from face_mask_inpaint_b200.modules import stylegan2 as SG
+    return SG
+
+
+def _randomize(mod, g):
+    with torch.no_grad():
+        for name, p in mod.named_parameters():
+            if name.endswith("noise.weight"):
+                p.fill_(0.3)
+            elif name.endswith("activate.bias") or name.endswith(".bias") and p.dim() == 4:
+                p.copy_(0.1 * torch.randn(p.shape, generator=g))
+            elif name.endswith("modulation.bias"):
+                p.copy_(1 + 0.2 * torch.randn(p.shape, generator=g))
+
+
+SQRT2 = 2 ** 0.5
+
+
+def _styled_conv_masked(x, style, weight, mod_weight, mod_bias, noise_weight, act_bias, noise, mask, upsample):
+    """O.styled_conv (model.py:340-346) with the leaky-ReLU branch chosen by `mask` instead of the sign of its input."""
+    out = O.modulated_conv2d(x, style, weight, mod_weight, mod_bias, True, upsample)
+    out = out + noise_weight * noise + act_bias.view(1, -1, 1, 1)
+    return SQRT2 * torch.where(mask, out, 0.2 * out)
+
+
+def _check(named_got, named_want, tol, scales=None):
+    bad = []
+    for name, want in named_want.items():
+        got = named_got[name]
+        assert got is not None, f"no gradient for {name}"
+        assert tuple(got.shape) == tuple(want.shape), f"{name}: shape {tuple(got.shape)} vs {tuple(want.shape)}"
+        if scales and name in scales:
+            err = (got.detach().double().cpu() - want.double()).abs().max().item() / scales[name]
+        else:
+            err = rel_err(got, want)
+        if not err <= tol:
+            bad.append(f"{name}: {err:.3e}")
+    assert not bad, "gradient rel err above tolerance: " + ", ".join(bad)
+
+
+@pytest.mark.parametrize("cfg", [
+    # (B, I, O, H, W, upsample)
+    (2, 64, 64, 16, 16, False),
+    (2, 64, 32, 16, 16, True),
+    (3, 512, 512, 4, 4, False),     # conv1 of the generator: 16 pixels per image = one 16-pixel K tile; two N tiles
+    (2, 512, 512, 4, 4, True),      # first up layer: 5x5 parity planes
+    (2, 256, 128, 32, 32, True),    # three taps per CTA on 128-wide N, M = 128
+    (1, 128, 256, 32, 32, False),   # two M tiles
+    (1, 32, 32, 128, 128, True),    # 32 channels = half a swizzle atom on both operands, split-K over 256 K tiles
+    (1, 64, 32, 64, 128, False),    # non-square
+])
+@pytest.mark.parametrize("mode", MODES, ids=[m[0] for m in MODES])
+def test_styled_conv_backward(cfg, mode):
+    SG = _mods()
+    b, i, o, h, w, up = cfg
+    _, dtype, tol = mode
+    g = torch.Generator().manual_seed(10)
+    mod = SG.StyledConv(i, o, 3, 512, upsample=up)
+    _randomize(mod, g)
+    x = torch.randn(b, i, h, w, generator=g).to(dtype).float()
+    style = torch.randn(b, 512, generator=g)
+    oh, ow = (2 * h, 2 * w) if up else (h, w)
+    noise = torch.randn(b, 1, oh, ow, generator=g)
+    gout = torch.randn(b, o, oh, ow, generator=g).to(dtype).float()
+
+    names = ['conv.weight', 'conv.modulation.weight', 'conv.modulation.bias', 'noise.weight', 'activate.bias']
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in mod.state_dict().items() if k in names}
+    mod = mod.to(DEV)
+    xg = x.to(dtype).to(DEV).requires_grad_(True)
+    sg = style.to(DEV).requires_grad_(True)
+    y = mod(xg, sg, noise=noise.to(DEV))
+    y.backward(gout.to(dtype).to(DEV))
+    got = {k: p.grad for k, p in mod.named_parameters() if k in names}
+    got['x'] = xg.grad
+    got['style'] = sg.grad
+
+    # oracle gradients: CPU fp32 autograd through the reference formulation at our activation pattern
+    mask = (y.detach().float() > 0).cpu()
+    xr = x.clone().requires_grad_(True)
+    sr = style.clone().requires_grad_(True)
+    want_y = _styled_conv_masked(xr, sr, sd['conv.weight'], sd['conv.modulation.weight'], sd['conv.modulation.bias'],
+                                 sd['noise.weight'], sd['activate.bias'], noise, mask, up)
+    assert rel_err(y, want_y) <= tol
+    want_y.backward(gout)
+    want = {k: v.grad for k, v in sd.items()}
+    want['x'] = xr.grad
+    want['style'] = sr.grad
+    # noise.weight: |error| against the root-sum-square of the terms it adds up (x 30: ~the largest partial sums)
+    nscale = 30 * ((gout * noise) ** 2).sum().sqrt().item() * SQRT2
+    _check(got, want, tol, scales={'noise.weight': max(nscale, abs(want['noise.weight'].item()))})
+
+
+@pytest.mark.parametrize("up", [False, True])
+def test_modulated_conv2d_backward_no_act(up):
+    """ModulatedConv2d alone (act = 0): the gradient enters the GEMMs without the activation pass."""
+    SG = _mods()
+    b, i, o, h, w = 2, 64, 64, 16, 16
+    g = torch.Generator().manual_seed(11)
+    mod = SG.ModulatedConv2d(i, o, 3, 512, upsample=up)
+    _randomize(mod, g)
+    x = torch.randn(b, i, h, w, generator=g)
+    style = torch.randn(b, 512, generator=g)
+    oh = 2 * h if up else h
+    gout = torch.randn(b, o, oh, oh, generator=g)
+    wr = mod.weight.detach().clone().requires_grad_(True)
+    xr = x.clone().requires_grad_(True)
+    O.modulated_conv2d(xr, style, wr, mod.modulation.weight.detach(), mod.modulation.bias.detach(), True, up).backward(gout)
+    mod = mod.to(DEV)
+    xg = x.to(DEV).requires_grad_(True)
+    mod(xg, style.to(DEV)).backward(gout.to(DEV))
+    _check({'x': xg.grad, 'weight': mod.weight.grad}, {'x': xr.grad, 'weight': wr.grad}, 1e-3)
+
+
+@pytest.mark.parametrize("with_skip", [False, True])
+@pytest.mark.parametrize("mode", MODES, ids=[m[0] for m in MODES])
+def test_to_rgb_backward(with_skip, mode):
+    SG = _mods()
+    _, dtype, tol = mode
+    b, i, h, w = 2, 64, 32, 32
+    g = torch.Generator().manual_seed(12)
+    mod = SG.ToRGB(i, 512)
+    _randomize(mod, g)
+    x = torch.randn(b, i, h, w, generator=g).to(dtype).float()
+    style = torch.randn(b, 512, generator=g)
+    skip = torch.randn(b, 3, h // 2, w // 2, generator=g) if with_skip else None
+    gout = torch.randn(b, 3, h, w, generator=g)
+    names = ['conv.weight', 'conv.modulation.weight', 'conv.modulation.bias', 'bias']
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in mod.state_dict().items() if k in names}
+    xr = x.clone().requires_grad_(True)
+    kr = skip.clone().requires_grad_(True) if with_skip else None
+    O.to_rgb(xr, style, sd['conv.weight'], sd['conv.modulation.weight'], sd['conv.modulation.bias'], sd['bias'],
+             kr).backward(gout)
+    want = {k: v.grad for k, v in sd.items()}
+    want['x'] = xr.grad
+    if with_skip:
+        want['skip'] = kr.grad
+    mod = mod.to(DEV)
+    xg = x.to(dtype).to(DEV).requires_grad_(True)
+    kg = skip.to(DEV).requires_grad_(True) if with_skip else None
+    mod(xg, style.to(DEV), kg).float().backward(gout.to(DEV))
+    got = {k: p.grad for k, p in mod.named_parameters() if k in names}
+    got['x'] = xg.grad
+    if with_skip:
+        got['skip'] = kg.grad
+    _check(got, want, tol)
+
+
+@pytest.mark.parametrize("mode", MODES, ids=[m[0] for m in MODES])
+def test_generator_backward(mode, monkeypatch):
+    """Whole synthesis network at 32x32 (7 StyledConv + 4 ToRGB): gradients of every parameter the image depends on
+    and of the latent, against autograd through the oracle's Generator.forward restatement."""
+    SG = _mods()
+    name, dtype, tol = mode
+    # operand rounding compounds over 11 chained layers in both directions (each layer alone meets the north_star
+    # tolerance in test_styled_conv_backward); measured 1.0e-3..1.9e-3 (tf32) per parameter tensor
+    tol = 3e-3
+    if name == "bf16":
+        monkeypatch.setenv("FMI_PRECISION", "bf16")
+        tol = 4e-2
+    g = torch.Generator().manual_seed(13)
+    torch.manual_seed(13)
+    gen = SG.Generator(32, 512, 2)
+    _randomize(gen, g)
+    latent = torch.randn(2, gen.n_latent, 512, generator=g)
+    gout = torch.randn(2, 3, 32, 32, generator=g)
+    sd = {k: v.detach().clone() for k, v in gen.state_dict().items()}
+    for k, v in sd.items():
+        if v.is_floating_point() and not k.startswith('noises.') and not k.endswith('.kernel'):
+            v.requires_grad_(True)
+    # our forward/backward first, recording every StyledConv output (NHWC) for the activation pattern
+    recorded = []
+    orig = SG.styled_conv_nhwc
+
+    def rec(*a, **k):
+        y = orig(*a, **k)
+        recorded.append(y)
+        return y
+
+    monkeypatch.setattr(SG, 'styled_conv_nhwc', rec)
+    gen_d = SG.Generator(32, 512, 2)
+    gen_d.load_state_dict({k: v.detach() for k, v in sd.items()})
+    gen_d = gen_d.to(DEV)
+    lg = latent.to(DEV).requires_grad_(True)
+    img, _ = gen_d([lg], input_is_latent=True, randomize_noise=False)
+    img.backward(gout.to(DEV))
+    got = {k: p.grad for k, p in gen_d.named_parameters()}
+    got['latent'] = lg.grad
+    masks = [(y.detach().float().permute(0, 3, 1, 2) > 0).cpu() for y in recorded]
+    assert len(masks) == gen.num_layers
+
+    # oracle: Generator.forward restatement (ref_ops.generator_synthesis) at that activation pattern
+    lr = latent.clone().requires_grad_(True)
+    batch = latent.shape[0]
+    noises = [sd[f'noises.noise_{i}'] for i in range(gen.num_layers)]
+    out = sd['input.input'].repeat(batch, 1, 1, 1)
+    out = _styled_conv_masked(out, lr[:, 0], *O._sc_args(sd, 'conv1'), noises[0], masks[0], False)
+    skip = O.to_rgb(out, lr[:, 1], *O._rgb_args(sd, 'to_rgb1'))
+    i = 1
+    for blk in range((gen.num_layers - 1) // 2):
+        out = _styled_conv_masked(out, lr[:, i], *O._sc_args(sd, f'convs.{2 * blk}'), noises[1 + 2 * blk],
+                                  masks[1 + 2 * blk], True)
+        out = _styled_conv_masked(out, lr[:, i + 1], *O._sc_args(sd, f'convs.{2 * blk + 1}'), noises[2 + 2 * blk],
+                                  masks[2 + 2 * blk], False)
+        skip = O.to_rgb(out, lr[:, i + 2], *O._rgb_args(sd, f'to_rgbs.{blk}'), skip=skip)
+        i += 2
+    assert rel_err(img, skip) <= tol
+    skip.backward(gout)
+    want = {k: v.grad for k, v in sd.items() if v.requires_grad and v.grad is not None}
+    want['latent'] = lr.grad
+    assert set(want) - set(k for k, v in got.items() if v is not None) == set()
+    scales = {k: max(30 * float(gout.abs().max()) * float(masks[0].numel()) ** 0.5, float(v.abs()))
+              for k, v in want.items() if k.endswith('noise.weight')}
+    _check(got, want, tol, scales=scales)
