@@ -7,6 +7,7 @@ element read once, every output element written once) / CUDA-event time; `frac` 
 Working sets are >= 256 MB (larger than the 126 MB L2) so no flush is needed between iterations.
 """
 import json
+import os
 import sys
 from pathlib import Path
 
@@ -46,8 +47,12 @@ def main():
     torch.manual_seed(0)
     k4 = SG.make_kernel([1, 3, 3, 1]).to(dev)
 
+    only = os.environ.get("PERF_ONLY")  # substring filter (ncu captures)
+
     def report(name, nbytes, fn):
-        t = time_cuda(fn)
+        if only and only not in name:
+            return
+        t = time_cuda(fn, *((1, 1) if os.environ.get("PERF_QUICK") else ()))
         gbs = nbytes / t * 1e-6
         print(f"{name:62s} {t:8.3f} {gbs:8.1f} {gbs / peak:6.2f}", flush=True)
 

@@ -69,6 +69,13 @@ UFD_CASES = [
     (2, 10, 10, [1, 3, 3, 1], 1, 1, (-1, -2)),   # negative pad = crop
     (5, 65, 131, [1, 3, 3, 1], 1, 1, (1, 1)),    # ragged tile edges
     (2, 300, 300, [1, 3, 3, 1], 1, 1, (2, 2)),   # several tiles
+    (3, 150, 70, [1, 3, 3, 1], 2, 1, (2, 1)),    # polyphase up=2: several tiles, ragged edges
+    (2, 33, 65, [1, 3, 3, 1], 2, 1, (1, 2)),     # up=2 with odd leading pad (the other tap phase)
+    (2, 20, 20, [1, 3, 3, 1], 2, 1, (3, 0)),
+    (2, 40, 40, [1, 3, 3, 1], 2, 1, (-1, 1)),    # up=2 with a crop
+    (3, 300, 140, [1, 3, 3, 1], 1, 2, (1, 1)),   # down=2: several tiles
+    (2, 67, 131, [1, 3, 3, 1], 1, 2, (2, 1)),    # down=2, odd extents
+    (2, 64, 64, [1, 2, 1], 1, 2, (0, 1)),        # down=2 with 3 taps
 ]
 
 
