@@ -380,6 +380,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1)
 }
 
 #include "attention_v2.cuh"
+#include "attention_v3.cuh"
 
 // ---- prologue kernels ---------------------------------------------------------------------------
 // 1x1 convolution as a small SIMT fp32 GEMM: y[n,o,s] = sum_c W[o,c] x[n,c,s] + b[o].
@@ -517,8 +518,9 @@ __global__ void __launch_bounds__(256) attn_materialize_kernel(const __nv_bfloat
 struct AttnPlan {
   int dpad, d_atoms, split, cv_tile, k_stages, v_stages, esz;  // esz: element size of the V / P operands
   int k_stages2, v_stages2;                                    // ring depths of attn_fwd2_kernel
+  int v_stages3;                                               // V ring depth of attn_fwd3_kernel (CTA pairs)
   int64_t qt_bytes, vcat_bytes, qmax_bytes;
-  size_t smem, smem2;
+  size_t smem, smem2, smem3;
 };
 
 int make_plan(int N, int d, int C0, int C1, int S, int mma, AttnPlan* pl) {
@@ -551,6 +553,11 @@ int make_plan(int N, int d, int C0, int C1, int S, int mma, AttnPlan* pl) {
   if (vs2 > 8) vs2 = 8;
   pl->v_stages2 = vs2;
   pl->smem2 = (size_t)(1 + pl->k_stages2) * q_tile + (size_t)vs2 * v_chunk;
+  // pair kernel: each CTA holds half of every K tile (2 stages) and half of every V chunk
+  int vs3 = (kAttn3SmemBudget - 2 * q_tile) / (v_chunk / 2);
+  if (vs3 > 8) vs3 = 8;
+  pl->v_stages3 = vs3;
+  pl->smem3 = (size_t)2 * q_tile + (size_t)(vs3 > 0 ? vs3 : 0) * (v_chunk / 2);
   return FMI_OK;
 }
 
@@ -644,6 +651,39 @@ int launch_attn2(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap
   cfg.numAttrs = 1;
   FMI_CUDA(cudaLaunchKernelEx(&cfg, kern, mq, mk, mv, prm));
   return fmi_launched("attn_fwd2");
+}
+
+template <bool TF32, typename T>
+int launch_attn3(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, AttnParams prm, const AttnPlan& pl,
+                 cudaStream_t st) {
+  auto kern = attn_fwd3_kernel<TF32, T>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncAttributes fa;
+    FMI_CUDA(cudaFuncGetAttributes(&fa, kern));
+    FMI_REQUIRE((int)fa.sharedSizeBytes <= kAttn3StaticSmem, "attn_fwd3: static shared memory grew to %d bytes",
+                (int)fa.sharedSizeBytes);
+    FMI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn3SmemBudget));
+    attr_set = true;
+  }
+  prm.k_stages = 2;
+  prm.v_stages = pl.v_stages3;
+  dim3 grid(prm.S / BM, prm.N, (prm.C0 + prm.C1) / prm.cv_tile);
+  FmiProfScope prof(0, st);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kAttn3Threads);
+  cfg.dynamicSmemBytes = pl.smem3;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  FMI_CUDA(cudaLaunchKernelEx(&cfg, kern, mq, mk, mv, prm));
+  return fmi_launched("attn_fwd3");
 }
 
 template <bool TF32, typename T>
@@ -771,7 +811,27 @@ extern "C" int fmi_attn_fwd(const void* x, const float* wq, const float* bq, con
   prm.trace = g_attn_trace;
   prm.qmax2 = fast_env ? qmax2 : nullptr;
   { const char* e = getenv("FMI_ATTN_DBG"); prm.dbg = e ? atoi(e) : 0; }
-  if (fast_env) {  // fast kernel first; images with max|q|^2 > kSafeQ2 fall through to the robust kernel below
+  // CTA-pair kernel (cta_group::2, Q in tensor memory): opt-in with FMI_ATTN_PAIR=1. It is parity-green but measured
+  // 5-15 % SLOWER than attn_fwd2_kernel (profiles/README.md), so it is kept as the vehicle for the round-2 work on the
+  // pair path, not as the default. Needs an even number of query tiles and a V tile that splits into two MMA-N halves.
+  static const bool pair_env = [] { const char* e = getenv("FMI_ATTN_PAIR"); return e && e[0] == '1'; }();
+  const bool pair = fast_env && pair_env && cluster && pl.cv_tile % 32 == 0 && pl.v_stages3 >= 2 &&
+                    256 - pl.d_atoms * (1 + pl.split) * 32 >= 2 * BS;  // Q in TMEM must leave two S/P buffers
+  if (pair) {
+    CUtensorMap mk3;
+    const uint64_t qrow = (uint64_t)pl.dpad * (1 + pl.split);
+    uint64_t dims[2] = {qrow, (uint64_t)N * S};
+    uint64_t str[1] = {qrow * 2};
+    uint32_t kbox[2] = {64, (uint32_t)(BS / 2)};  // 32 key rows: this CTA's half of one 64-key step
+    int e = make_tensor_map(&mk3, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, qt, dims, str, kbox, CU_TENSOR_MAP_SWIZZLE_128B);
+    FMI_REQUIRE(e == 0, "attn_fwd: cuTensorMapEncodeTiled(K, pair) failed (%d)", e);
+    // mv already has the half-height box {epa, cv_tile / 2} of the cluster variants
+    if (tf32) rc = dtype == FMI_F32 ? launch_attn3<true, float>(mq, mk3, mv, prm, pl, st)
+                                    : launch_attn3<true, __nv_bfloat16>(mq, mk3, mv, prm, pl, st);
+    else rc = dtype == FMI_F32 ? launch_attn3<false, float>(mq, mk3, mv, prm, pl, st)
+                               : launch_attn3<false, __nv_bfloat16>(mq, mk3, mv, prm, pl, st);
+    if (rc) return rc;
+  } else if (fast_env) {  // fast kernel first; images with max|q|^2 > kSafeQ2 fall through to the robust kernel below
     if (tf32) rc = dtype == FMI_F32 ? launch_attn2_any<true, float>(cluster, mq, mk, mv, prm, pl, st)
                                     : launch_attn2_any<true, __nv_bfloat16>(cluster, mq, mk, mv, prm, pl, st);
     else rc = dtype == FMI_F32 ? launch_attn2_any<false, float>(cluster, mq, mk, mv, prm, pl, st)

@@ -125,11 +125,45 @@ __global__ void __launch_bounds__(kAttn2Threads, 1)
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ---------------------------------------------------------------- QK issuer: S[h & 3] = Q K_h^T  (128 x 64)
+    // ---------------------------------------------------------------- QK issuer
+    // Default: one N = 64 MMA group per 64-key step. Experiment (FMI_ATTN_DBG=32): one N = 128 group per 128-key tile
+    // writing TWO adjacent S buffers — tools/umma_rate.cu measured ~86 clk per isolated MMA at N = 64 against 107 clk at
+    // N = 128, so the hi/lo-split logits should cost 1284 instead of 2064 clk per tile; in the kernel it changed nothing
+    // (profiles/README.md, "what does not bound the attention kernel"), so the QK issue rate is not the limiter.
     if (lane0) {
-      const uint32_t idesc_qk = make_idesc(KIND_BF16, BM, BS);
       const int npairs = p.split ? 3 : 1;
       mbar_wait(&q_full, 0);
+      if (p.dbg & 32) {
+        const uint32_t idesc_qk = make_idesc(KIND_BF16, BM, BN);
+        for (int t = 0; t < NT; ++t) {
+          const int slot = t % p.k_stages, b0 = (2 * t) & 3;
+          if (t >= 2) {  // P(2t-4), P(2t-3) lived in these buffers
+            mbar_wait(&pv_done[b0], ((t >> 1) - 1) & 1);
+            mbar_wait(&pv_done[b0 + 1], ((t >> 1) - 1) & 1);
+          }
+          mbar_wait(&k_full[slot], (t / p.k_stages) & 1);
+          tc_fence_after();
+          uint32_t acc = 0;
+          for (int pr = 0; pr < npairs; ++pr) {
+            const int ca = pr == 2 ? 1 : 0, cb = pr == 1 ? 1 : 0;
+            for (int a = 0; a < p.d_atoms; ++a) {
+              const uint64_t adesc = make_sdesc_k_sw128(smem_u32(sQ + (ca * p.d_atoms + a) * BM * ATOM_BYTES));
+              const uint64_t bdesc =
+                  make_sdesc_k_sw128(smem_u32(sK + slot * q_tile_bytes + (cb * p.d_atoms + a) * BN * ATOM_BYTES));
+#pragma unroll
+              for (int s = 0; s < 4; ++s) {
+                if (!(p.dbg & 16)) mma_ss_f16(tmem_S(b0), adesc + 2 * s, bdesc + 2 * s, idesc_qk, acc);
+                acc = 1;
+              }
+            }
+          }
+          tc_commit(&s_full[b0]);
+          tc_commit(&s_full[b0 + 1]);
+          if (CLUSTER) tc_commit_mc(&k_empty[slot], kMask);
+          else tc_commit(&k_empty[slot]);
+        }
+      } else {
+      const uint32_t idesc_qk = make_idesc(KIND_BF16, BM, BS);
       for (int h = 0; h < NS; ++h) {
         const int t = h >> 1, slot = t % p.k_stages, b = h & 3;
         if (h >= 4) mbar_wait(&pv_done[b], ((h >> 2) - 1) & 1);  // P(h-4) lived in this buffer
@@ -154,6 +188,7 @@ __global__ void __launch_bounds__(kAttn2Threads, 1)
           if (CLUSTER) tc_commit_mc(&k_empty[slot], kMask);
           else tc_commit(&k_empty[slot]);
         }
+      }
       }
     }
     __syncwarp();
