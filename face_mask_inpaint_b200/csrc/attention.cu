@@ -814,7 +814,7 @@ extern "C" int fmi_attn_fwd(const void* x, const float* wq, const float* bq, con
   // CTA-pair kernel (cta_group::2, Q in tensor memory): opt-in with FMI_ATTN_PAIR=1. It is parity-green but measured
   // 5-15 % SLOWER than attn_fwd2_kernel (profiles/README.md), so it is kept as the vehicle for the round-2 work on the
   // pair path, not as the default. Needs an even number of query tiles and a V tile that splits into two MMA-N halves.
-  static const bool pair_env = [] { const char* e = getenv("FMI_ATTN_PAIR"); return e && e[0] == '1'; }();
+  const bool pair_env = [] { const char* e = getenv("FMI_ATTN_PAIR"); return e && e[0] == '1'; }();  // read per call
   const bool pair = fast_env && pair_env && cluster && pl.cv_tile % 32 == 0 && pl.v_stages3 >= 2 &&
                     256 - pl.d_atoms * (1 + pl.split) * 32 >= 2 * BS;  // Q in TMEM must leave two S/P buffers
   if (pair) {

@@ -92,6 +92,8 @@ __global__ void __launch_bounds__(kGemmThreads, 3)
   } else if (warp == 1) {
     if (elect_one()) {
       const uint32_t idesc = make_idesc(TF32 ? KIND_TF32 : KIND_BF16, 128, p.n_tile);
+      const int last_valid = p.I - (p.k_chunks - 1) * EPA;               // channels in the last chunk
+      const int last_ksteps = (last_valid + EPA / 4 - 1) / (EPA / 4);     // MMA K = EPA / 4 elements
       for (int it = 0; it < iters; ++it) {
         const int st = it % p.stages;
         mbar_wait(&full[st], (it / p.stages) & 1);
@@ -99,8 +101,12 @@ __global__ void __launch_bounds__(kGemmThreads, 3)
         uint8_t* sA = smem + st * stage_bytes;
         const uint64_t adesc = make_sdesc_k_sw128(smem_u32(sA));
         const uint64_t bdesc = make_sdesc_k_sw128(smem_u32(sA + A_STAGE_BYTES));
+        // the last channel chunk of a narrow layer is partly TMA zero fill (I = 32 bf16 fills half a 128-byte row):
+        // skip the K steps that would only multiply zeros (each N <= 64 MMA costs ~85 clk whatever it multiplies)
+        const int ksteps = (it % p.k_chunks == p.k_chunks - 1) ? last_ksteps : 4;
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
+          if (s >= ksteps) break;
           const uint32_t acc = (it > 0 || s > 0) ? 1u : 0u;
           if (TF32) mma_ss_tf32(tmem, adesc + 2 * s, bdesc + 2 * s, idesc, acc);
           else mma_ss_f16(tmem, adesc + 2 * s, bdesc + 2 * s, idesc, acc);

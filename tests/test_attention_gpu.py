@@ -180,3 +180,35 @@ def test_attention_large_logits_take_the_robust_kernel(logit_std):
         got, _ = mod(x.to(DEV))
     assert torch.isfinite(got).all()
     assert rel_err(got - x.to(DEV), want - x) <= 1e-2
+
+
+@pytest.mark.parametrize("case", [(2, 128, 32, 32, None), (2, 256, 32, 32, 256), (2, 512, 16, 16, 512), (1, 256, 64, 64, None)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_example_guided_attention_pair_kernel(case, dtype, monkeypatch):
+    """attn_fwd3_kernel (CTA pairs, tcgen05 cta_group::2, Q staged in tensor memory) is opt-in (FMI_ATTN_PAIR=1) and must
+    stay parity-green: same cases and tolerances as the default kernel, plus bitwise-close agreement with it."""
+    from face_mask_inpaint_b200.modules import ExampleGuidedAttention
+    n, c, h, w, oc = case
+    g = torch.Generator().manual_seed(5)
+    src = torch.randn(n, c, h, w, generator=g).to(dtype).float()
+    ref = torch.randn(n, c, h, w, generator=g).to(dtype).float()
+    mask = _mask(n, h, w, g)
+    wq = _scaled_query_weight(c, c // 4, src, 1.0, g)
+    mod = ExampleGuidedAttention(c, oc)
+    with torch.no_grad():
+        mod.conv.weight.copy_(wq)
+        if oc is not None:
+            mod.out_conv.weight.copy_(torch.randn(mod.out_conv.weight.shape, generator=g) / (2 * c) ** 0.5)
+            mod.out_conv.bias.copy_(torch.randn(oc, generator=g))
+    want = O.example_guided_attention(mask, src, ref, mod.conv.weight.detach(),
+                                      mod.out_conv.weight.detach() if oc else None,
+                                      mod.out_conv.bias.detach() if oc else None)
+    mod = mod.to(DEV)
+    args = (mask.to(DEV), src.to(dtype).to(DEV), ref.to(dtype).to(DEV))
+    with torch.no_grad():
+        base = mod(*args)
+        monkeypatch.setenv("FMI_ATTN_PAIR", "1")
+        got = mod(*args)
+    tol = 1e-3 if dtype == torch.float32 else 2e-2
+    assert rel_err(got, want) <= tol
+    assert rel_err(got, base) <= tol / 4
