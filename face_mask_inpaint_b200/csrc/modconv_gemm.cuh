@@ -1,6 +1,8 @@
 // Implicit-GEMM convolution on tcgen05 shared by the modulated-conv forward (modconv.cu) and its data gradient
 // (modconv_bwd.cu): kernel, tile planner and launcher. See modconv.cu for the formulation.
 #pragma once
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "sm100.cuh"
 
@@ -17,6 +19,7 @@ struct ConvGemmParams {
   int OH, OW;          // output NHWC extents
   int Mh, Mw;          // iteration domain of this launch (per image)
   int TH, TW, tiles_w; // pixel tile (TH*TW <= 128)
+  int tiles_per_img, n_otiles, total_tiles;  // persistent tile loop: t -> (sample, output-channel tile, pixel tile)
   int ntaps, tap_dy[kMaxTaps], tap_dx[kMaxTaps], tap_slab[kMaxTaps];
   int tap_boff[kMaxTaps];  // added to the batch coordinate of the A box (parity planes of the up-conv data gradient)
   int T;               // weight slabs per sample
@@ -37,6 +40,10 @@ struct ConvGemmParams {
   float* rgb_out;
 };
 
+// Persistent: each CTA walks output tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... (pixel tile fastest, then output-
+// channel tile, then sample). The TMA ring runs ahead across tile boundaries and the accumulator is double buffered in
+// TMEM, so the epilogue of tile i overlaps the MMAs of tile i+1. (One tile per CTA left the tensor pipe 5 % active on the
+// 32 -> 32 @1024^2 layer — ncu: 27 % warps active, the CTA lifetime was prologue + TMA latency + epilogue.)
 template <bool TF32>
 __global__ void __launch_bounds__(kGemmThreads, 3)
     modconv_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
@@ -47,25 +54,37 @@ __global__ void __launch_bounds__(kGemmThreads, 3)
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int b_stage_bytes = p.n_tile * 128;
   const int stage_bytes = A_STAGE_BYTES + b_stage_bytes;
-  __shared__ uint64_t full[8], empty[8], acc_full;
+  __shared__ uint64_t full[8], empty[8], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
-  __shared__ float4 s_rgbw[256];  // fused ToRGB weights of this image: (w_r, w_g, w_b, -) per output channel
+  __shared__ float4 s_rgbw[256];  // fused ToRGB weights of the current image: (w_r, w_g, w_b, -) per output channel
 
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int tile = blockIdx.x, o0 = blockIdx.y * p.n_tile, b = blockIdx.z;
-  const int m0 = (tile / p.tiles_w) * p.TH, n0 = (tile % p.tiles_w) * p.TW;
   const int iters = p.ntaps * p.k_chunks;
+  const int per_img = p.tiles_per_img * p.n_otiles;
+  auto decode = [&](int t, int& b, int& o0, int& m0, int& n0) {
+    b = t / per_img;
+    const int rem = t - b * per_img;
+    const int oi = rem / p.tiles_per_img;
+    const int tile = rem - oi * p.tiles_per_img;
+    o0 = oi * p.n_tile;
+    const int ty = tile / p.tiles_w;
+    m0 = ty * p.TH;
+    n0 = (tile - ty * p.tiles_w) * p.TW;
+  };
 
   if (tid == 0) {
     for (int i = 0; i < 8; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
     }
-    mbar_init(&acc_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 128);
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(&tmem_base_s, p.tmem_cols);  // power of two >= n_tile: narrow layers leave TMEM for co-resident CTAs
+    tmem_alloc(&tmem_base_s, p.tmem_cols);  // two accumulators; narrow layers leave TMEM for co-resident CTAs
     tmem_relinquish();
   }
   tc_fence_before();
@@ -78,14 +97,19 @@ __global__ void __launch_bounds__(kGemmThreads, 3)
       tma_prefetch_desc(&map_x);
       tma_prefetch_desc(&map_w);
       const uint32_t bytes = (uint32_t)(p.TH * p.TW * 128 + b_stage_bytes);
-      for (int it = 0; it < iters; ++it) {
-        const int st = it % p.stages;
-        const int tap = it / p.k_chunks, kc = it % p.k_chunks;
-        mbar_wait(&empty[st], ((it / p.stages) & 1) ^ 1);
-        mbar_arrive_expect_tx(&full[st], bytes);
-        uint8_t* sA = smem + st * stage_bytes;
-        tma_load_4d(sA, &map_x, &full[st], kc * EPA, n0 + p.tap_dx[tap], m0 + p.tap_dy[tap], b + p.tap_boff[tap]);
-        tma_load_2d(sA + A_STAGE_BYTES, &map_w, &full[st], kc * EPA, (b * p.T + p.tap_slab[tap]) * p.O + o0);
+      int g = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        int b, o0, m0, n0;
+        decode(t, b, o0, m0, n0);
+        for (int it = 0; it < iters; ++it, ++g) {
+          const int st = g % p.stages;
+          const int tap = it / p.k_chunks, kc = it % p.k_chunks;
+          mbar_wait(&empty[st], ((g / p.stages) & 1) ^ 1);
+          mbar_arrive_expect_tx(&full[st], bytes);
+          uint8_t* sA = smem + st * stage_bytes;
+          tma_load_4d(sA, &map_x, &full[st], kc * EPA, n0 + p.tap_dx[tap], m0 + p.tap_dy[tap], b + p.tap_boff[tap]);
+          tma_load_2d(sA + A_STAGE_BYTES, &map_w, &full[st], kc * EPA, (b * p.T + p.tap_slab[tap]) * p.O + o0);
+        }
       }
     }
     __syncwarp();
@@ -94,122 +118,142 @@ __global__ void __launch_bounds__(kGemmThreads, 3)
       const uint32_t idesc = make_idesc(TF32 ? KIND_TF32 : KIND_BF16, 128, p.n_tile);
       const int last_valid = p.I - (p.k_chunks - 1) * EPA;               // channels in the last chunk
       const int last_ksteps = (last_valid + EPA / 4 - 1) / (EPA / 4);     // MMA K = EPA / 4 elements
-      for (int it = 0; it < iters; ++it) {
-        const int st = it % p.stages;
-        mbar_wait(&full[st], (it / p.stages) & 1);
+      int g = 0, i = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++i) {
+        const int as = i & 1;
+        mbar_wait(&acc_empty[as], ((i >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator
         tc_fence_after();
-        uint8_t* sA = smem + st * stage_bytes;
-        const uint64_t adesc = make_sdesc_k_sw128(smem_u32(sA));
-        const uint64_t bdesc = make_sdesc_k_sw128(smem_u32(sA + A_STAGE_BYTES));
-        // the last channel chunk of a narrow layer is partly TMA zero fill (I = 32 bf16 fills half a 128-byte row):
-        // skip the K steps that would only multiply zeros (each N <= 64 MMA costs ~85 clk whatever it multiplies)
-        const int ksteps = (it % p.k_chunks == p.k_chunks - 1) ? last_ksteps : 4;
+        const uint32_t d_tmem = tmem + as * p.n_tile;
+        for (int it = 0; it < iters; ++it, ++g) {
+          const int st = g % p.stages;
+          mbar_wait(&full[st], (g / p.stages) & 1);
+          tc_fence_after();
+          uint8_t* sA = smem + st * stage_bytes;
+          const uint64_t adesc = make_sdesc_k_sw128(smem_u32(sA));
+          const uint64_t bdesc = make_sdesc_k_sw128(smem_u32(sA + A_STAGE_BYTES));
+          // the last channel chunk of a narrow layer is partly TMA zero fill (I = 32 bf16 fills half a 128-byte row):
+          // skip the K steps that would only multiply zeros (each N <= 64 MMA costs ~85 clk whatever it multiplies)
+          const int ksteps = (it % p.k_chunks == p.k_chunks - 1) ? last_ksteps : 4;
 #pragma unroll
-        for (int s = 0; s < 4; ++s) {
-          if (s >= ksteps) break;
-          const uint32_t acc = (it > 0 || s > 0) ? 1u : 0u;
-          if (TF32) mma_ss_tf32(tmem, adesc + 2 * s, bdesc + 2 * s, idesc, acc);
-          else mma_ss_f16(tmem, adesc + 2 * s, bdesc + 2 * s, idesc, acc);
+          for (int s = 0; s < 4; ++s) {
+            if (s >= ksteps) break;
+            const uint32_t acc = (it > 0 || s > 0) ? 1u : 0u;
+            if (TF32) mma_ss_tf32(d_tmem, adesc + 2 * s, bdesc + 2 * s, idesc, acc);
+            else mma_ss_f16(d_tmem, adesc + 2 * s, bdesc + 2 * s, idesc, acc);
+          }
+          tc_commit(&empty[st]);
         }
-        tc_commit(&empty[st]);
+        tc_commit(&acc_full[as]);
       }
-      tc_commit(&acc_full);
     }
     __syncwarp();
   } else {
     const int lane_base = (warp & 3) * 32;
     const int r = lane_base + (tid & 31);  // tile row == TMEM lane
     const uint32_t lane_addr = (uint32_t)lane_base << 16;
-    const int m = m0 + r / p.TW, n = n0 + r % p.TW;
-    const bool valid = r < p.TH * p.TW && m < p.Mh && n < p.Mw;
-    const int oy = m * p.sy + p.py, ox = n * p.sx + p.px;
-    float nz = 0.f;
-    if (p.act && valid && p.noise) {
-      const float nw = p.noise_w ? *p.noise_w : 1.f;
-      nz = nw * p.noise[(int64_t)(p.noise_batched ? b : 0) * p.OH * p.OW + (int64_t)oy * p.OW + ox];
-    }
-    OT* out = (OT*)p.out + (((int64_t)b * p.OH + oy) * p.OW + ox) * p.O + o0;
-    // fused ToRGB (model.py:360-369): the 1x1 modulated conv to 3 channels reads exactly the activations this thread
-    // holds, so it is 3 dot products in the epilogue instead of a kernel that re-reads the whole layer output from HBM
-    if (p.rgb_out) {
-      for (int e = tid - 64; e < p.n_tile; e += 128) {
-        const float* w = p.rgb_w + ((int64_t)b * 3) * p.O + o0 + e;
-        s_rgbw[e] = make_float4(w[0], w[p.O], w[2 * p.O], 0.f);
+    int cur_b = -1, cur_o0 = -1, i = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++i) {
+      const int as = i & 1;
+      int b, o0, m0, n0;
+      decode(t, b, o0, m0, n0);
+      const int m = m0 + r / p.TW, n = n0 + r % p.TW;
+      const bool valid = r < p.TH * p.TW && m < p.Mh && n < p.Mw;
+      const int oy = m * p.sy + p.py, ox = n * p.sx + p.px;
+      float nz = 0.f;
+      if (p.act && valid && p.noise) {
+        const float nw = p.noise_w ? *p.noise_w : 1.f;
+        nz = nw * p.noise[(int64_t)(p.noise_batched ? b : 0) * p.OH * p.OW + (int64_t)oy * p.OW + ox];
       }
-      asm volatile("bar.sync 2, 128;" ::: "memory");
-    }
-    float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
-    mbar_wait(&acc_full, 0);
-    tc_fence_after();
-    for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld32(tmem + lane_addr + c0, v);
-      tc_wait_ld();
-      if (!valid) continue;
-      float f[32];
-#pragma unroll
-      for (int k = 0; k < 32; ++k) f[k] = __uint_as_float(v[k]);
-      if (p.act) {
-#pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          float t = f[k] + nz + (p.bias ? __ldg(p.bias + o0 + c0 + k) : 0.f);
-          f[k] = (t > 0.f ? t : t * p.slope) * p.gain;
+      OT* out = (OT*)p.out + (((int64_t)b * p.OH + oy) * p.OW + ox) * p.O + o0;
+      // fused ToRGB (model.py:360-369): the 1x1 modulated conv to 3 channels reads exactly the activations this thread
+      // holds, so it is 3 dot products in the epilogue instead of a kernel that re-reads the whole layer output from HBM
+      if (p.rgb_out && (b != cur_b || o0 != cur_o0)) {
+        asm volatile("bar.sync 2, 128;" ::: "memory");  // readers of the previous image's weights are done
+        for (int e = tid - 64; e < p.n_tile; e += 128) {
+          const float* w = p.rgb_w + ((int64_t)b * 3) * p.O + o0 + e;
+          s_rgbw[e] = make_float4(w[0], w[p.O], w[2 * p.O], 0.f);
         }
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        cur_b = b;
+        cur_o0 = o0;
       }
-      if (p.rgb_out) {
-#pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          const float4 w = s_rgbw[c0 + k];
-          const float a = TF32 ? __uint_as_float(f32_to_tf32_rna(f[k])) : __bfloat162float(__float2bfloat16_rn(f[k]));
-          rgb0 = fmaf(a, w.x, rgb0);
-          rgb1 = fmaf(a, w.y, rgb1);
-          rgb2 = fmaf(a, w.z, rgb2);
+      float rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
+      mbar_wait(&acc_full[as], (i >> 1) & 1);
+      tc_fence_after();
+      for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem + lane_addr + as * p.n_tile + c0, v);
+        tc_wait_ld();
+        if (c0 + 32 >= p.n_tile) {  // last read of this accumulator: hand it back to the MMA warp before the stores
+          tc_fence_before();
+          mbar_arrive(&acc_empty[as]);
         }
-      }
-      const int ncols = min(32, p.n_tile - c0);
-      if constexpr (TF32) {
+        if (!valid) continue;
+        float f[32];
 #pragma unroll
-        for (int k = 0; k < 32; k += 4)
-          if (k < ncols)
-            *reinterpret_cast<float4*>(out + c0 + k) =
-                make_float4(__uint_as_float(f32_to_tf32_rna(f[k])), __uint_as_float(f32_to_tf32_rna(f[k + 1])),
-                            __uint_as_float(f32_to_tf32_rna(f[k + 2])), __uint_as_float(f32_to_tf32_rna(f[k + 3])));
-      } else {
+        for (int k = 0; k < 32; ++k) f[k] = __uint_as_float(v[k]);
+        if (p.act) {
 #pragma unroll
-        for (int k = 0; k < 32; k += 8)
-          if (k < ncols) {
-            uint4 u;
-            u.x = pack_bf16x2(f[k], f[k + 1]);
-            u.y = pack_bf16x2(f[k + 2], f[k + 3]);
-            u.z = pack_bf16x2(f[k + 4], f[k + 5]);
-            u.w = pack_bf16x2(f[k + 6], f[k + 7]);
-            *reinterpret_cast<uint4*>(out + c0 + k) = u;
-          }
-      }
-    }
-    if (p.rgb_out && valid) {
-      float r3[3] = {rgb0 + p.rgb_bias[0], rgb1 + p.rgb_bias[1], rgb2 + p.rgb_bias[2]};
-      const int HW = p.OH * p.OW;
-      if (p.rgb_skip) {
-        // Upsample of the previous RGB: zero-insert x2, pad (2,1), flipped 4x4 taps (model.py:30-49)
-        const int h2 = p.OH / 2, w2 = p.OW / 2;
-#pragma unroll
-        for (int ky = 0; ky < 4; ++ky) {
-          const int uy = oy + ky - 2;
-          if (uy < 0 || (uy & 1) || (uy >> 1) >= h2) continue;
-#pragma unroll
-          for (int kx = 0; kx < 4; ++kx) {
-            const int ux = ox + kx - 2;
-            if (ux < 0 || (ux & 1) || (ux >> 1) >= w2) continue;
-            const float kv = __ldg(p.rgb_kf + 15 - (ky * 4 + kx));
-            const int64_t si = ((int64_t)b * 3 * h2 + (uy >> 1)) * w2 + (ux >> 1);
-#pragma unroll
-            for (int o = 0; o < 3; ++o) r3[o] = fmaf(kv, p.rgb_skip[si + (int64_t)o * h2 * w2], r3[o]);
+          for (int k = 0; k < 32; ++k) {
+            float tt = f[k] + nz + (p.bias ? __ldg(p.bias + o0 + c0 + k) : 0.f);
+            f[k] = (tt > 0.f ? tt : tt * p.slope) * p.gain;
           }
         }
-      }
+        if (p.rgb_out) {
 #pragma unroll
-      for (int o = 0; o < 3; ++o) p.rgb_out[((int64_t)b * 3 + o) * HW + (int64_t)oy * p.OW + ox] = r3[o];
+          for (int k = 0; k < 32; ++k) {
+            const float4 w = s_rgbw[c0 + k];
+            const float a = TF32 ? __uint_as_float(f32_to_tf32_rna(f[k])) : __bfloat162float(__float2bfloat16_rn(f[k]));
+            rgb0 = fmaf(a, w.x, rgb0);
+            rgb1 = fmaf(a, w.y, rgb1);
+            rgb2 = fmaf(a, w.z, rgb2);
+          }
+        }
+        const int ncols = min(32, p.n_tile - c0);
+        if constexpr (TF32) {
+#pragma unroll
+          for (int k = 0; k < 32; k += 4)
+            if (k < ncols)
+              *reinterpret_cast<float4*>(out + c0 + k) =
+                  make_float4(__uint_as_float(f32_to_tf32_rna(f[k])), __uint_as_float(f32_to_tf32_rna(f[k + 1])),
+                              __uint_as_float(f32_to_tf32_rna(f[k + 2])), __uint_as_float(f32_to_tf32_rna(f[k + 3])));
+        } else {
+#pragma unroll
+          for (int k = 0; k < 32; k += 8)
+            if (k < ncols) {
+              uint4 u;
+              u.x = pack_bf16x2(f[k], f[k + 1]);
+              u.y = pack_bf16x2(f[k + 2], f[k + 3]);
+              u.z = pack_bf16x2(f[k + 4], f[k + 5]);
+              u.w = pack_bf16x2(f[k + 6], f[k + 7]);
+              *reinterpret_cast<uint4*>(out + c0 + k) = u;
+            }
+        }
+      }
+      if (p.rgb_out && valid) {
+        float r3[3] = {rgb0 + p.rgb_bias[0], rgb1 + p.rgb_bias[1], rgb2 + p.rgb_bias[2]};
+        const int HW = p.OH * p.OW;
+        if (p.rgb_skip) {
+          // Upsample of the previous RGB: zero-insert x2, pad (2,1), flipped 4x4 taps (model.py:30-49)
+          const int h2 = p.OH / 2, w2 = p.OW / 2;
+#pragma unroll
+          for (int ky = 0; ky < 4; ++ky) {
+            const int uy = oy + ky - 2;
+            if (uy < 0 || (uy & 1) || (uy >> 1) >= h2) continue;
+#pragma unroll
+            for (int kx = 0; kx < 4; ++kx) {
+              const int ux = ox + kx - 2;
+              if (ux < 0 || (ux & 1) || (ux >> 1) >= w2) continue;
+              const float kv = __ldg(p.rgb_kf + 15 - (ky * 4 + kx));
+              const int64_t si = ((int64_t)b * 3 * h2 + (uy >> 1)) * w2 + (ux >> 1);
+#pragma unroll
+              for (int o = 0; o < 3; ++o) r3[o] = fmaf(kv, p.rgb_skip[si + (int64_t)o * h2 * w2], r3[o]);
+            }
+          }
+        }
+#pragma unroll
+        for (int o = 0; o < 3; ++o) p.rgb_out[((int64_t)b * 3 + o) * HW + (int64_t)oy * p.OW + ox] = r3[o];
+      }
     }
   }
   tc_fence_before();
@@ -248,19 +292,27 @@ int launch_gemm_class(const CUtensorMap& mx, const CUtensorMap& mw, ConvGemmPara
     attr_set = true;
   }
   const int stage_bytes = A_STAGE_BYTES + p.n_tile * 128;
-  int stages = (232448 - 8192) / stage_bytes;
+  // Two accumulators per CTA in TMEM. Narrow tiles (N <= 64: 128 columns) leave room for 3 co-resident CTAs, N <= 128 for
+  // 2; the TMA ring is sized to the CTA's share of shared memory.
+  p.tmem_cols = p.n_tile <= 16 ? 32 : p.n_tile <= 32 ? 64 : p.n_tile <= 64 ? 128 : p.n_tile <= 128 ? 256 : 512;
+  const int ctas_per_sm = p.n_tile <= 64 ? 3 : p.n_tile <= 128 ? 2 : 1;
+  int stages = ((232448 - 6144) / ctas_per_sm - 2048) / stage_bytes;
   if (stages > 8) stages = 8;
-  // A tile of a narrow high-resolution layer is only ntaps * k_chunks = 9..18 pipeline steps: the per-CTA fixed cost
-  // (TMEM alloc, barrier init, first TMA) dominates when one CTA owns the SM (ncu: 32->32 @1024^2 ran at 1/15 of its HBM
-  // roofline). Keep the ring at 3 stages there so 2-3 CTAs are co-resident and overlap each other's prologue/epilogue.
-  const int total_iters = p.ntaps * p.k_chunks;
-  if (total_iters <= 36 && stages > 3) stages = 3;
-  p.tmem_cols = p.n_tile <= 32 ? 32 : p.n_tile <= 64 ? 64 : p.n_tile <= 128 ? 128 : 256;
+  FMI_REQUIRE(stages >= 2, "modconv_gemm: stage of %d bytes does not fit twice", stage_bytes);
   p.stages = stages;
   const size_t smem = (size_t)stages * stage_bytes + 1024;
   TilePlan tp = pick_tile(p.Mh, p.Mw);
   p.TH = tp.TH; p.TW = tp.TW; p.tiles_w = tp.tiles_w;
-  dim3 grid(tp.tiles_h * tp.tiles_w, p.O / p.n_tile, p.B);
+  p.tiles_per_img = tp.tiles_h * tp.tiles_w;
+  p.n_otiles = p.O / p.n_tile;
+  const int64_t total = (int64_t)p.tiles_per_img * p.n_otiles * p.B;
+  FMI_REQUIRE(total < (1ll << 31), "modconv_gemm: too many tiles");
+  p.total_tiles = (int)total;
+  int grid = (int)imin64(total, (int64_t)FMI_NUM_SMS * ctas_per_sm);
+  {  // debug: FMI_MODCONV_ONE_TILE=1 launches one CTA per tile (no tile loop) — must be bit-identical to the persistent run
+    static const bool one_tile = [] { const char* e = getenv("FMI_MODCONV_ONE_TILE"); return e && e[0] == '1'; }();
+    if (one_tile) grid = (int)total;
+  }
   FmiProfScope prof(1, st);
   kern<<<grid, kGemmThreads, smem, st>>>(mx, mw, p);
   return fmi_launched("modconv_gemm");

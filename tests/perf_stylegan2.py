@@ -42,7 +42,8 @@ def main():
     lib = _lib.load()
     gflop_img = 148.5 if size == 1024 else float("nan")
     with torch.no_grad():
-        for mode in ("fp32", "bf16"):
+        modes = ("fp32", "bf16") if not os.environ.get("SG_ONLY") else (os.environ["SG_ONLY"],)
+        for mode in modes:
             os.environ["FMI_PRECISION"] = mode
             fn = lambda: gen([latent], input_is_latent=True, randomize_noise=False)[0]
             img = fn()
@@ -61,6 +62,8 @@ def main():
             if mode == "fp32":
                 img32 = img
         os.environ.pop("FMI_PRECISION")
+        if os.environ.get("SG_ONLY"):
+            return
         print(f"bf16 vs fp32-contract image: rel diff {((img.float() - img32).abs().max() / img32.abs().max()).item():.3e}")
         # reference formulation on the same GPU (smaller batch: per-sample weights + grouped conv are memory hungry)
         rb = 2
