@@ -95,12 +95,17 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(Shape sh, int iters, long 
     uint32_t v[32];
     const uint32_t base = tmem + ((uint32_t)(warp * 32) << 16) + 256;
     for (int k = 0; k < 32; ++k) v[k] = k;
+    long long n_ops = 0;
+    const long long c_start = clock64();
     while (!*(volatile int*)&stop_flag) {
       for (int c = 0; c < 128; c += 32) {
         if (sh.traffic != 3) { tmem_ld32(base + c, v); tc_wait_ld(); }
         if (sh.traffic != 2) { tmem_st32(base + c, v); tc_wait_st(); }
+        ++n_ops;
       }
     }
+    // average latency of one 32-column tcgen05.ld and/or .st (+ wait) of this warp while the MMAs were running
+    if (warp == 1 && (tid & 31) == 0) cycles[gridDim.x + blockIdx.x] = (clock64() - c_start) / (n_ops > 0 ? n_ops : 1);
   }
   __syncthreads();
   tc_fence_before();
@@ -192,7 +197,7 @@ int main() {
   CK(cudaDeviceGetAttribute(&clk_khz, cudaDevAttrClockRate, dev));
   CK(cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   long long* d_cycles;
-  CK(cudaMalloc(&d_cycles, sms * sizeof(long long)));
+  CK(cudaMalloc(&d_cycles, 2 * sms * sizeof(long long)));
   const int iters = 20000;
   printf("%d SMs, %d MHz nominal; %d iterations x 4 MMAs (K = 4 x %s) per SM\n", sms, clk_khz / 1000, iters, "16 bf16 | 8 tf32");
   printf("%-44s %12s %12s %10s\n", "shape (M=128)", "clk/MMA", "MAC/clk/SM", "of nominal");
@@ -210,7 +215,15 @@ int main() {
     const double per_mma = avg / (iters * 4.0);
     const double k = sh.tf32 ? 8 : 16;
     const double mac = 128.0 * sh.N * k / per_mma;
-    printf("%-44s %12.1f %12.1f %10.2f\n", sh.name, per_mma, mac, mac / (sh.tf32 ? 2048.0 : 4096.0));
+    printf("%-44s %12.1f %12.1f %10.2f", sh.name, per_mma, mac, mac / (sh.tf32 ? 2048.0 : 4096.0));
+    if (sh.traffic) {
+      std::vector<long long> l(sms);
+      CK(cudaMemcpy(l.data(), d_cycles + sms, sms * sizeof(long long), cudaMemcpyDeviceToHost));
+      double a = 0;
+      for (long long c : l) a += (double)c;
+      printf("   | x32 %s round trip: %.0f clk", sh.traffic == 1 ? "ld+st" : sh.traffic == 2 ? "ld" : "st", a / sms);
+    }
+    printf("\n");
   }
   const Shape pair_shapes[] = {
       {"pair bf16 SS N=64 (QK, Q in smem), 3 acc", 0, 0, 64, 3, 2, 0},
