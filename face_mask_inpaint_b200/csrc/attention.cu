@@ -599,7 +599,9 @@ int launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap&
     attr_set = true;
   }
   dim3 grid(prm.S / BM, prm.N, (prm.C0 + prm.C1) / prm.cv_tile);
-  FmiProfScope prof(0, st);
+  // kind 0 = the kernel that does the work; as the fallback behind the fast kernel (qmax2 given: it exits at once for
+  // every image the fast kernel took) it is timed separately so it cannot dilute the roofline average
+  FmiProfScope prof(prm.qmax2 ? 2 : 0, st);
   if (CLUSTER) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;

@@ -19,7 +19,7 @@ int fmi_check_cuda(cudaError_t e, const char* what);
 int fmi_launched(const char* kernel_name);
 
 // Optional CUDA-event timing of the dominant kernels on their launch stream (fmi_profile_enable / _collect):
-// kind 0 = attention main kernel, kind 1 = modulated-conv implicit GEMM.
+// kind 0 = attention main kernel, kind 1 = modulated-conv implicit GEMM, kind 2 = attention robust kernel run as fallback.
 struct FmiProfScope {
   FmiProfScope(int kind, cudaStream_t st);
   ~FmiProfScope();

@@ -28,7 +28,7 @@ int fmi_check_cuda(cudaError_t e, const char* what) {
 static std::atomic<long long> g_launches{0};
 static std::atomic<int> g_prof_on{0};
 static std::mutex g_prof_mu;
-static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events[2];
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events[3];
 
 int fmi_launched(const char* kernel_name) {
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -39,7 +39,7 @@ int fmi_launched(const char* kernel_name) {
 }
 
 FmiProfScope::FmiProfScope(int kind, cudaStream_t st) : kind_(kind), st_(st), e0_(nullptr), e1_(nullptr), on_(false) {
-  if (!g_prof_on.load(std::memory_order_relaxed) || kind < 0 || kind > 1) return;
+  if (!g_prof_on.load(std::memory_order_relaxed) || kind < 0 || kind > 2) return;
   if (cudaEventCreate(&e0_) != cudaSuccess || cudaEventCreate(&e1_) != cudaSuccess) return;
   on_ = true;
   cudaEventRecord(e0_, st_);
@@ -60,7 +60,7 @@ extern "C" int fmi_profile_enable(int on) {
 
 // Synchronises on the recorded events; returns the summed duration (ms) and number of launches of `kind`.
 extern "C" int fmi_profile_collect(int kind, double* total_ms, int* launches) {
-  FMI_REQUIRE(kind >= 0 && kind <= 1 && total_ms && launches, "profile_collect: bad arguments");
+  FMI_REQUIRE(kind >= 0 && kind <= 2 && total_ms && launches, "profile_collect: bad arguments");
   std::lock_guard<std::mutex> lk(g_prof_mu);
   double sum = 0;
   int n = 0;

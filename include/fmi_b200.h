@@ -43,7 +43,8 @@ int fmi_device_check(void);
 /* Number of kernels this library has launched since it was loaded (all entry points). */
 long long fmi_kernel_launch_count(void);
 /* Optional CUDA-event timing of the dominant kernels on their own launch stream:
- *   kind 0 = attention main kernel, kind 1 = modulated-conv implicit GEMM.
+ *   kind 0 = attention main kernel, kind 1 = modulated-conv implicit GEMM, kind 2 = the robust attention kernel when
+ *   it runs as the per-image fallback behind the fast one (normally an immediate exit).
  * fmi_profile_collect synchronises on the recorded events, returns their summed duration (ms) and
  * count, and clears the record. Off by default (no events are created). */
 int fmi_profile_enable(int on);
