@@ -199,10 +199,44 @@ def gen_stylegan2():
     np.savez_compressed(OUT / "generator32.npz", latent=np_(latent), image=np_(img))
 
 
+def gen_picnet():
+    """BASELINE config 1: the reference's ReferenceFill (modules/model.py) with the README configuration, every parameter
+    filled by name (golden_util.fill_by_name), get_z replaced by the distribution means, one forward at 256x256, batch 1.
+    Stored: the 256x256 output, the 1024x1024 decoder output subsampled 8x, the attention input features' statistics
+    and the reference's state_dict keys (the drop-in contract of modules/picnet.py)."""
+    import types as _types
+    from golden_util import fill_by_name, picnet_inputs, mean_z
+    from modules.model import ReferenceFill
+    enc = dict(type='pluralistic', ngf=32, z_nc=128, img_f=128, layers=5, norm='none', activation='LeakyReLU',
+               init_type='orthogonal')
+    dec = dict(ngf=32, z_nc=256, img_f=256, L=0, layers=5, norm='instance', activation='LeakyReLU', init_type='orthogonal')
+    torch.manual_seed(0)
+    model = ReferenceFill(None, dict(enc), dict(dec), use_att=True).eval()
+    fill_by_name(model)
+    model.decoder.get_z = _types.MethodType(mean_z, model.decoder)
+    keys = sorted(model.state_dict().keys())
+    src, ref, mask = picnet_inputs(1)
+    with torch.no_grad():
+        full = model(src, ref, mask, resize=False)
+    # a second model instance: SpectralNorm's u/v advanced once per forward, so every forward starts from fresh state
+    model2 = ReferenceFill(None, dict(enc), dict(dec), use_att=True).eval()
+    fill_by_name(model2)
+    model2.decoder.get_z = _types.MethodType(mean_z, model2.decoder)
+    with torch.no_grad():
+        out = model2(src, ref, mask)
+    np.savez_compressed(OUT / "picnet_ref.npz", image=np_(out), full_sub8=np_(full[:, :, ::8, ::8]),
+                        keys=np.array(keys), n_params=np.array(sum(p.numel() for p in model.parameters())))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    if len(sys.argv) > 1 and sys.argv[1] == "picnet":
+        gen_picnet()
+        print("picnet_ref.npz", (OUT / "picnet_ref.npz").stat().st_size)
+        sys.exit(0)
     gen_attention()
     gen_upfirdn2d_and_composite()
     gen_stylegan2()
+    gen_picnet()
     for f in sorted(OUT.glob("*.npz")):
         print(f.name, f.stat().st_size)

@@ -21,3 +21,46 @@ def build_generator32():
     gen = mine.Generator(32, 512, 2)
     randomize(gen, torch.Generator().manual_seed(6))
     return gen
+
+
+def fill_by_name(module, seed=0):
+    """Deterministic, name-keyed values for EVERY parameter (PICNet golden: the reference model and this package's mirror
+    get identical weights without shipping a checkpoint). SpectralNorm u/v are unit vectors, weights ~ N(0, 1/fan_in),
+    norm scales ~ 1, biases small, the zero-initialised attention gains (gamma, alpha) non-zero."""
+    import zlib
+    with torch.no_grad():
+        for name, p in module.named_parameters():
+            g = torch.Generator().manual_seed((zlib.crc32(name.encode()) + seed) & 0x7FFFFFFF)
+            leaf = name.rsplit('.', 1)[-1]
+            if leaf.endswith('_u') or leaf.endswith('_v'):
+                v = torch.randn(p.shape, generator=g)
+                p.copy_(v / (v.norm() + 1e-12))
+            elif leaf == 'gamma':
+                p.fill_(1.0)
+            elif leaf == 'alpha':
+                p.fill_(0.5)
+            elif p.dim() >= 2:
+                p.copy_(torch.randn(p.shape, generator=g) / p[0].numel() ** 0.5)
+            elif leaf == 'bias':
+                p.copy_(0.05 * torch.randn(p.shape, generator=g))
+            else:  # norm scales
+                p.copy_(1 + 0.1 * torch.randn(p.shape, generator=g))
+    return module
+
+
+def picnet_inputs(n=1, seed=7):
+    """Synthetic masked-face / reference / binary-mask inputs of BASELINE config 1: U[0,1) images, lower-face
+    rectangle mask."""
+    g = torch.Generator().manual_seed(seed)
+    src = torch.rand(n, 3, 256, 256, generator=g)
+    ref = torch.rand(n, 3, 256, 256, generator=g)
+    mask = torch.zeros(n, 256, 256)
+    mask[:, 128:230, 50:206] = 1.0
+    return src, ref, mask
+
+
+def mean_z(self, src_distribution, ref_distribution, return_zq=False, mask=None):
+    """Replacement for ResGenerator.get_z in the PICNet golden: the distribution means instead of rsample(), so the CPU
+    reference and the GPU mirror do not depend on their (different) random generators."""
+    q_mu, p_mu = src_distribution[0], ref_distribution[0]
+    return q_mu if return_zq else torch.cat([q_mu, p_mu], dim=1)
