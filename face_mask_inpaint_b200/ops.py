@@ -280,13 +280,15 @@ _WS = {}
 
 
 def _workspace(device, nbytes: int) -> torch.Tensor:
-    """Grow-only per-device scratch (operand staging for the tensor-core kernels); stream-ordered reuse."""
+    """Grow-only per-device scratch (operand staging for the tensor-core kernels); stream-ordered reuse. The returned view
+    starts on a 1024-byte boundary (TMA / SWIZZLE_128B staging; the caching allocator only guarantees 512)."""
     key = (device.type, device.index, torch.cuda.current_stream().cuda_stream)
     buf = _WS.get(key)
-    if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+    if buf is None or buf.numel() < nbytes + 1024:
+        buf = torch.empty(max(nbytes, 1 << 20) + 1024, dtype=torch.uint8, device=device)
         _WS[key] = buf
-    return buf
+    off = (-buf.data_ptr()) % 1024
+    return buf[off:off + max(nbytes, buf.numel() - 1024)]
 
 
 def mma_mode(dtype: torch.dtype) -> int:

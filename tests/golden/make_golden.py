@@ -228,15 +228,44 @@ def gen_picnet():
                         keys=np.array(keys), n_params=np.array(sum(p.numel() for p in model.parameters())))
 
 
+def gen_refpsp(size=256):
+    """BASELINE config 3 (reduced output size for the fixture): the reference's pSp (modules/psp/psp.py) with
+    GradualStyleEncoder(50, 'ir_se') + attention and its StyleGAN2 decoder, `load_weights` bypassed (no pretrained files
+    offline), latent_avg = 0, every parameter filled by name, eval mode, randomize_noise=False, batch 1.
+    Stored: codes [1, n_styles, 512], the face-pooled 256x256 image and the reference's state_dict keys."""
+    from argparse import Namespace
+    from golden_util import fill_by_name, refpsp_inputs
+    _install_op_stub()
+    import modules.psp.psp as ref_psp
+    ref_psp.pSp.load_weights = lambda self: None
+    opts = Namespace(output_size=size, encoder_type='GradualStyleEncoder', use_attention=1, train_decoder=0,
+                     start_from_latent_avg=1, learn_in_w=0, pt_ckpt_path=None, stylegan_weights=None)
+    torch.manual_seed(0)
+    net = ref_psp.pSp(opts).eval()
+    net.latent_avg = torch.zeros(opts.n_styles, 512)
+    fill_by_name(net)
+    keys = sorted(net.state_dict().keys())
+    x, ref, mask = refpsp_inputs(1)
+    with torch.no_grad():
+        img, codes = net(x, ref=ref, src_mask=mask, resize=True, randomize_noise=False, return_latents=True)
+    np.savez_compressed(OUT / f"refpsp{size}.npz", image=np_(img), codes=np_(codes), keys=np.array(keys),
+                        n_params=np.array(sum(p.numel() for p in net.parameters())))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    if len(sys.argv) > 1 and sys.argv[1] == "picnet":
-        gen_picnet()
-        print("picnet_ref.npz", (OUT / "picnet_ref.npz").stat().st_size)
+    if len(sys.argv) > 1 and sys.argv[1] in ("picnet", "refpsp"):
+        if sys.argv[1] == "picnet":
+            gen_picnet()
+        else:
+            gen_refpsp()
+        for f in sorted(OUT.glob("*.npz")):
+            print(f.name, f.stat().st_size)
         sys.exit(0)
     gen_attention()
     gen_upfirdn2d_and_composite()
     gen_stylegan2()
     gen_picnet()
+    gen_refpsp()
     for f in sorted(OUT.glob("*.npz")):
         print(f.name, f.stat().st_size)

@@ -24,27 +24,46 @@ def build_generator32():
 
 
 def fill_by_name(module, seed=0):
-    """Deterministic, name-keyed values for EVERY parameter (PICNet golden: the reference model and this package's mirror
-    get identical weights without shipping a checkpoint). SpectralNorm u/v are unit vectors, weights ~ N(0, 1/fan_in),
-    norm scales ~ 1, biases small, the zero-initialised attention gains (gamma, alpha) non-zero."""
+    """Deterministic, name-keyed values for EVERY parameter (whole-model goldens: the reference model and this package's
+    mirror get identical weights without shipping a checkpoint). SpectralNorm u/v are unit vectors, conv / linear weights
+    ~ N(0, 1/fan_in), StyleGAN2 modulated-conv weights and the constant input ~ N(0, 1) (they are demodulated / scaled by
+    the layer), norm scales ~ 1, PReLU slopes ~ 0.25, biases small, noise strengths 0.1, the zero-initialised attention
+    gains (gamma, alpha) non-zero."""
     import zlib
+    seen = set()
     with torch.no_grad():
-        for name, p in module.named_parameters():
-            g = torch.Generator().manual_seed((zlib.crc32(name.encode()) + seed) & 0x7FFFFFFF)
-            leaf = name.rsplit('.', 1)[-1]
-            if leaf.endswith('_u') or leaf.endswith('_v'):
-                v = torch.randn(p.shape, generator=g)
-                p.copy_(v / (v.norm() + 1e-12))
-            elif leaf == 'gamma':
-                p.fill_(1.0)
-            elif leaf == 'alpha':
-                p.fill_(0.5)
-            elif p.dim() >= 2:
-                p.copy_(torch.randn(p.shape, generator=g) / p[0].numel() ** 0.5)
-            elif leaf == 'bias':
-                p.copy_(0.05 * torch.randn(p.shape, generator=g))
-            else:  # norm scales
-                p.copy_(1 + 0.1 * torch.randn(p.shape, generator=g))
+        for mname, mod in module.named_modules():
+            kind = type(mod).__name__
+            for leaf, p in mod.named_parameters(recurse=False):
+                if id(p) in seen:
+                    continue
+                seen.add(id(p))
+                name = f"{mname}.{leaf}" if mname else leaf
+                g = torch.Generator().manual_seed((zlib.crc32(name.encode()) + seed) & 0x7FFFFFFF)
+                r = torch.randn(p.shape, generator=g)
+                if leaf.endswith('_u') or leaf.endswith('_v'):
+                    p.copy_(r / (r.norm() + 1e-12))
+                elif leaf == 'gamma':
+                    p.fill_(1.0)
+                elif leaf == 'alpha':
+                    p.fill_(0.5)
+                elif kind == 'PReLU':
+                    p.copy_(0.25 + 0.05 * r)
+                elif kind == 'NoiseInjection':
+                    p.fill_(0.1)
+                elif kind in ('ModulatedConv2d', 'ConstantInput'):
+                    p.copy_(r)
+                elif p.dim() >= 2:
+                    p.copy_(r / p[0].numel() ** 0.5)
+                elif leaf == 'bias':
+                    p.copy_((1.0 if mname.endswith('modulation') else 0.0) + 0.05 * r)
+                else:  # norm scales
+                    p.copy_(1 + 0.1 * r)
+        # the StyleGAN2 noise maps are BUFFERS drawn at construction (model.py:441-443): name-keyed too
+        for name, b in module.named_buffers():
+            if '.noises.noise_' in f'.{name}':
+                g = torch.Generator().manual_seed((zlib.crc32(name.encode()) + seed) & 0x7FFFFFFF)
+                b.copy_(torch.randn(b.shape, generator=g))
     return module
 
 
@@ -64,3 +83,13 @@ def mean_z(self, src_distribution, ref_distribution, return_zq=False, mask=None)
     reference and the GPU mirror do not depend on their (different) random generators."""
     q_mu, p_mu = src_distribution[0], ref_distribution[0]
     return q_mu if return_zq else torch.cat([q_mu, p_mu], dim=1)
+
+
+def refpsp_inputs(n=1, seed=11):
+    """Synthetic inputs of BASELINE config 3: U[-1,1) source / reference, binary lower-face mask."""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(n, 3, 256, 256, generator=g) * 2 - 1
+    ref = torch.rand(n, 3, 256, 256, generator=g) * 2 - 1
+    mask = torch.zeros(n, 256, 256)
+    mask[:, 128:230, 50:206] = 1.0
+    return x, ref, mask

@@ -100,6 +100,25 @@ def main():
                     print(f"{name + f' B={batch} cudnn_tf32={int(tf32)}':58s} {t:10.2f} {batch / t * 1e3:9.1f} "
                           f"{gflop_img * batch / t:8.1f}{extra}", flush=True)
                 os.environ.pop("FMI_PRECISION", None)
+        # bf16 autocast + channels_last for the cuDNN conv blocks (library tuning of the out-of-scope part), bf16 attention
+        torch.backends.cudnn.allow_tf32 = True
+        ours_cl = copy.deepcopy(ours)   # (SpectralNorm views its 4-D weight as a matrix: the parameters stay NCHW)
+        ours_cl.decoder.get_z = types.MethodType(mean_z, ours_cl.decoder)
+        ref_cl = copy.deepcopy(refm)
+        ref_cl.decoder.get_z = types.MethodType(mean_z, ref_cl.decoder)
+        for batch in (4, 8):
+            src, ref, mask = (t.cuda() for t in picnet_inputs(batch))
+            for name, model in (("ours, bf16 autocast, channels_last activations", ours_cl),
+                                ("ref-GPU, bf16 autocast, channels_last activations", ref_cl)):
+                def fn():
+                    with torch.autocast("cuda", dtype=torch.bfloat16):
+                        return model(src.contiguous(memory_format=torch.channels_last),
+                                     ref.contiguous(memory_format=torch.channels_last), mask)
+                try:
+                    t = time_cuda(fn)
+                    print(f"{name + f' B={batch}':58s} {t:10.2f} {batch / t * 1e3:9.1f} {gflop_img * batch / t:8.1f}", flush=True)
+                except Exception as ex:  # noqa: BLE001
+                    print(f"{name} B={batch}: failed: {type(ex).__name__}: {str(ex)[:200]}")
         # parity of the two GPU paths on the same weights and the same (fresh) SpectralNorm state (B=1)
         torch.backends.cudnn.allow_tf32 = False
 
