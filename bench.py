@@ -164,6 +164,72 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def whole_model_throughput(dev, world, barrier, max_over_ranks):
+    """images/sec of the two generators BASELINE.json's metric names, forward only, synthetic inputs resident on the
+    device, per-GPU batch fixed (weak scaling), max over ranks: PICNet-ref 256^2 (modules/picnet.py, per-GPU batch 4, fp32
+    contract) and RefpSp 1024^2 (modules/psp.py, per-GPU batch 8, bf16 operands). The conv trunks of both are cuDNN (out of
+    the kernel scope); attention, compositing and the whole StyleGAN2 decoder are this package's kernels.
+    Failures are reported, not raised: the bench line above does not depend on this block."""
+    out = {}
+    iters = 5
+
+    def timed(fn):
+        for _ in range(2):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1) / iters)
+
+    prev = os.environ.get("FMI_PRECISION")
+    try:
+        with torch.no_grad():
+            from face_mask_inpaint_b200.modules.picnet import build_picnet_ref
+            torch.manual_seed(7)
+            net = build_picnet_ref().eval().to(dev)
+            with torch.no_grad():
+                net.decoder.attn1.gamma.fill_(1.0)
+            b = 4
+            src, ref = torch.rand(b, 3, 256, 256, device=dev), torch.rand(b, 3, 256, 256, device=dev)
+            mask = torch.zeros(b, 256, 256, device=dev)
+            mask[:, 128:230, 50:206] = 1.0
+            ms = timed(lambda: net(src, ref, mask))
+            out["picnet_ref_256"] = {"value": world * b / (ms * 1e-3), "unit": "img/s", "per_gpu_batch": b, "ms_per_step": ms,
+                                     "precision": "fp32 I/O, TF32 attention operands, cuDNN convs (TF32 allowed)",
+                                     "what": "ReferenceFill forward: 2 encoders, ExampleGuidedAttention@32^2, decoder with "
+                                             "Auto_Attn@128^2 up to 1024^2, pooled to 256^2"}
+            del net
+            from face_mask_inpaint_b200.modules.psp import pSp, refpsp_opts
+            os.environ["FMI_PRECISION"] = "bf16"
+            net = pSp(refpsp_opts(output_size=1024)).eval().to(dev)
+            b = 8
+            x, ref = torch.rand(b, 3, 256, 256, device=dev) * 2 - 1, torch.rand(b, 3, 256, 256, device=dev) * 2 - 1
+            mask = torch.zeros(b, 256, 256, device=dev)
+            mask[:, 128:230, 50:206] = 1.0
+            ms = timed(lambda: net(x, ref=ref, src_mask=mask, resize=True, randomize_noise=False))
+            codes = net.encoder(x, ref=ref, mask=mask)
+            ms_dec = timed(lambda: net.decoder([codes], input_is_latent=True, randomize_noise=False))
+            out["refpsp_1024"] = {"value": world * b / (ms * 1e-3), "unit": "img/s", "per_gpu_batch": b, "ms_per_step": ms,
+                                  "decoder_only_ms": ms_dec, "decoder_only_img_s": world * b / (ms_dec * 1e-3),
+                                  "precision": "bf16 tensor-core operands in the decoder and attention, cuDNN trunk fp32/TF32",
+                                  "what": "pSp forward: IR-SE50 GradualStyleEncoder on source+reference, attention1/2, masked "
+                                          "blend, StyleGAN2-1024 decoder, face_pool to 256^2"}
+            del net
+    except Exception as ex:  # noqa: BLE001
+        out["error"] = f"{type(ex).__name__}: {str(ex)[:300]}"
+    finally:
+        if prev is None:
+            os.environ.pop("FMI_PRECISION", None)
+        else:
+            os.environ["FMI_PRECISION"] = prev
+        torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args, rank, local_rank, world):
     import torch.distributed as dist
     from face_mask_inpaint_b200 import _lib
@@ -246,6 +312,9 @@ def run_ours(args, rank, local_rank, world):
         ms_e2e = max_over_ranks(e0.elapsed_time(e1) / e2e_steps)
         clocks = sampler.stop() if sampler else None
 
+    # ---------------- whole-model numbers of BASELINE.json's metric (not the bench line; reported beside it)
+    models = None if args.no_models else whole_model_throughput(dev, world, barrier, max_over_ranks)
+
     if world > 1:
         dist.destroy_process_group()
     if rank != 0:
@@ -279,6 +348,8 @@ def run_ours(args, rank, local_rank, world):
                      "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_kind}); the kernel runs "
                                     "kind::tf32 MMAs whose nominal rate is half the bf16 rate"},
     }
+    if models is not None:
+        line["whole_models"] = models
     if world == 1:
         v, sample, cores, _ = cpu_reference_images_per_sec(12.0, 1024, None, 1)
         line["cpu_baseline"] = {"value": v, "unit": "img/s", "cores": cores, "kind": "port", "sample": sample}
@@ -291,6 +362,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-models", action="store_true", help="skip the whole-model (PICNet-ref / RefpSp) throughput block")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
