@@ -9,9 +9,11 @@ Workload (BASELINE.json configs[1], the reference-attention microbench at its la
   value       device-resident inputs, CUDA-event timed, max over ranks
   e2e         the same step through the public module API from pinned HOST buffers (H2D of src/ref/mask and D2H of the
               output inside the timed region)
-  roofline    the dominant kernel (attn_fwd_kernel) timed live with CUDA events on its own launch stream
+  roofline    the dominant kernel (attn_fwd2_kernel) timed live with CUDA events on its own launch stream
   cpu_baseline / --impl reference : the reference's algorithm (oracle/ref_ops.py, PyTorch CPU, all host threads) on a
               bounded sample of the same workload
+  whole_models  (extra key, not the bench line) forward img/s of the two generators BASELINE.json's metric names:
+              PICNet-ref 256^2 (per-GPU batch 4) and RefpSp 1024^2 (per-GPU batch 8, bf16 operands); --no-models skips it
 
   python bench.py --gpus N --steps K --warmup W [--impl reference]
 """
