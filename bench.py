@@ -292,26 +292,73 @@ def run_ours(args, rank, local_rank, world):
         fallback_ms = tot_fb.value / max(1, n_fb.value)
 
         # ---------------- end to end from pinned host memory through the public module API
+        # Every step moves its own inputs host -> device (pinned, 269 MB) and its own result device -> host (268 MB) inside the
+        # timed region. The three phases run on three streams with two buffer sets, so the H2D of step i+1 and the D2H of
+        # step i-1 overlap the kernels of step i (PCIe is full duplex): the step time tends to max(H2D, compute, D2H)
+        # instead of their sum. The module call itself is the public API, unchanged.
         src_p, ref_p, mask_p = src_h.pin_memory(), ref_h.pin_memory(), mask_h.pin_memory()
-        out_p = torch.empty(out.shape, dtype=out.dtype).pin_memory()
+        out_p = [torch.empty(out.shape, dtype=out.dtype).pin_memory() for _ in range(2)]
         e2e_steps = max(1, min(args.steps, 50))
+        s_in, s_cmp, s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
+        d_in = [tuple(torch.empty_like(t, device=dev) for t in (src_h, ref_h, mask_h)) for _ in range(2)]
+        ev_in = [torch.cuda.Event() for _ in range(2)]       # inputs of the set have landed
+        ev_used = [torch.cuda.Event() for _ in range(2)]     # the kernels have consumed the set
+        ev_out = [torch.cuda.Event() for _ in range(2)]      # the result of the set has reached the host
+        for e in ev_used + ev_out:
+            e.record()
 
-        def e2e_step():
-            s_d = src_p.to(dev, non_blocking=True)
-            r_d = ref_p.to(dev, non_blocking=True)
-            m_d = mask_p.to(dev, non_blocking=True)
-            o = mod(m_d, s_d, r_d)
-            out_p.copy_(o, non_blocking=True)
+        def e2e_step(i):
+            k = i & 1
+            with torch.cuda.stream(s_in):
+                s_in.wait_event(ev_used[k])
+                for dst, srcp in zip(d_in[k], (src_p, ref_p, mask_p)):
+                    dst.copy_(srcp, non_blocking=True)
+                ev_in[k].record(s_in)
+            with torch.cuda.stream(s_cmp):
+                s_cmp.wait_event(ev_in[k])
+                o = mod(d_in[k][2], d_in[k][0], d_in[k][1])
+                ev_used[k].record(s_cmp)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_used[k])
+                s_out.wait_event(ev_out[k])   # (same stream: ordering only) the host buffer of this set is free again
+                out_p[k].copy_(o, non_blocking=True)
+                o.record_stream(s_out)
+                ev_out[k].record(s_out)
 
-        for _ in range(2):
-            e2e_step()
+        for i in range(4):
+            e2e_step(i)
         barrier()
         e0.record()
-        for _ in range(e2e_steps):
-            e2e_step()
+        for st in (s_in, s_cmp, s_out):
+            st.wait_event(e0)
+        for i in range(e2e_steps):
+            e2e_step(i)
+        for st in (s_in, s_cmp, s_out):
+            torch.cuda.current_stream().wait_stream(st)
         e1.record()
         barrier()
         ms_e2e = max_over_ranks(e0.elapsed_time(e1) / e2e_steps)
+        # the pipelined steps must have produced the same result as the device-resident run (same inputs every step)
+        ref_out = out.float().cpu()
+        for k in range(2):
+            diff = (out_p[k].float() - ref_out).abs().max().item()
+            if not diff <= 1e-5 * ref_out.abs().max().item():
+                raise RuntimeError(f"bench: pipelined e2e output of buffer set {k} differs from the resident run by {diff}")
+        # serial variant (copy in, run, copy out, one stream) for the record
+        def e2e_serial():
+            s_d = src_p.to(dev, non_blocking=True)
+            r_d = ref_p.to(dev, non_blocking=True)
+            m_d = mask_p.to(dev, non_blocking=True)
+            out_p[0].copy_(mod(m_d, s_d, r_d), non_blocking=True)
+
+        e2e_serial()
+        barrier()
+        e0.record()
+        for _ in range(min(e2e_steps, 10)):
+            e2e_serial()
+        e1.record()
+        barrier()
+        ms_e2e_serial = max_over_ranks(e0.elapsed_time(e1) / min(e2e_steps, 10))
         clocks = sampler.stop() if sampler else None
 
     # ---------------- whole-model numbers of BASELINE.json's metric (not the bench line; reported beside it)
@@ -337,7 +384,10 @@ def run_ours(args, rank, local_rank, world):
                    "parallelism": f"batch-sharded x{world}, no collective"},
         "clocks": clocks,
         "e2e": {"value": world * BATCH / (ms_e2e * 1e-3), "unit": "img/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": ms_e2e},
+                "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": ms_e2e,
+                "pipelining": "3 streams, 2 buffer sets: H2D(i+1) and D2H(i-1) overlap the kernels of step i; every step "
+                              "moves all of its own bytes",
+                "serial_ms_per_step": ms_e2e_serial, "serial_value": world * BATCH / (ms_e2e_serial * 1e-3)},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": "attn_fwd2_kernel<TF32,float,cluster2>", "achieved": achieved,
                      "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
