@@ -762,7 +762,8 @@ extern "C" int fmi_attn_fwd(const void* x, const float* wq, const float* bq, con
   float* qmax2 = (float*)(vcat + pl.vcat_bytes);
   const bool tf32 = mma == FMI_MMA_TF32;
   // FMI_ATTN_KERNEL=robust: only the online-max kernel; default: fixed-bound fast kernel + robust fallback per image
-  static const bool fast_env = [] { const char* e = getenv("FMI_ATTN_KERNEL"); return !(e && e[0] == 'r'); }();
+  static const bool fast_env0 = [] { const char* e = getenv("FMI_ATTN_KERNEL"); return !(e && e[0] == 'r'); }();
+  const bool fast_env = fast_env0 && pl.d_atoms <= 2;  // the fast kernels keep the Q/K descriptors of <= 4 atoms in registers
 
   if (dtype == FMI_F32) {
     rc = launch_conv1x1_any<float>(x, wq, bq, qt, N, C, d, S, pl.dpad, tf32 ? 2 : 1, st);

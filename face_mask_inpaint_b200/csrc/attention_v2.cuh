@@ -19,6 +19,27 @@ constexpr int kAttn2SmemBudget = 232448 - kAttn2StaticSmem;
 constexpr int BS = 64;                  // keys per step
 
 
+// S[buffer] = Q K_h^T for one 64-key step with every descriptor precomputed by the caller: the loop body is nothing but the
+// MMAs. tools/umma_rate.cu: with a lean issue loop a 128x64x16 MMA takes 48 clk (shared-memory operand bound), with address
+// arithmetic, predicate tests and descriptor construction between the MMAs the same instruction took 87 clk — for these small
+// MMAs the issuing thread's own instruction stream is the limiter, and the hi/lo-split logits need 12 of them per step.
+template <int D_ATOMS, int NPAIRS>
+__device__ __forceinline__ void qk_step_mmas(uint32_t d_tmem, const uint64_t (&qa)[4], const uint64_t (&kb)[4], uint64_t hoff,
+                                             uint32_t idesc) {
+#pragma unroll
+  for (int pr = 0; pr < NPAIRS; ++pr) {
+    const int ca = pr == 2 ? 1 : 0, cb = pr == 1 ? 1 : 0;  // hi.hi, hi.lo, lo.hi
+#pragma unroll
+    for (int a = 0; a < D_ATOMS; ++a) {
+      const uint64_t ad = qa[ca * D_ATOMS + a], bd = kb[cb * D_ATOMS + a] + hoff;
+      mma_ss_f16(d_tmem, ad, bd, idesc, (pr | a) ? 1u : 0u);
+      mma_ss_f16(d_tmem, ad + 2, bd + 2, idesc, 1u);
+      mma_ss_f16(d_tmem, ad + 4, bd + 4, idesc, 1u);
+      mma_ss_f16(d_tmem, ad + 6, bd + 6, idesc, 1u);
+    }
+  }
+}
+
 template <bool TF32, typename T, bool CLUSTER>
 __global__ void __launch_bounds__(kAttn2Threads, 1)
     attn_fwd2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
@@ -164,24 +185,29 @@ __global__ void __launch_bounds__(kAttn2Threads, 1)
         }
       } else {
       const uint32_t idesc_qk = make_idesc(KIND_BF16, BM, BS);
+      // descriptors of the (fixed) Q atoms and of the K atoms of both ring slots; a step only adds the half-tile offset
+      uint64_t qa[4], kb[2][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int ii = i < q_atoms ? i : 0;
+        qa[i] = make_sdesc_k_sw128(smem_u32(sQ + ii * BM * ATOM_BYTES));
+        kb[0][i] = make_sdesc_k_sw128(smem_u32(sK + ii * BN * ATOM_BYTES));
+        kb[1][i] = make_sdesc_k_sw128(smem_u32(sK + (p.k_stages > 1 ? q_tile_bytes : 0) + ii * BN * ATOM_BYTES));
+      }
+      const uint64_t half_tile = (uint64_t)((BS * ATOM_BYTES) >> 4);  // start-address field is in 16-byte units
       for (int h = 0; h < NS; ++h) {
         const int t = h >> 1, slot = t % p.k_stages, b = h & 3;
         if (h >= 4) mbar_wait(&pv_done[b], ((h >> 2) - 1) & 1);  // P(h-4) lived in this buffer
         mbar_wait(&k_full[slot], (t / p.k_stages) & 1);
         tc_fence_after();
-        uint32_t acc = 0;
-        for (int pr = 0; pr < npairs; ++pr) {
-          const int ca = pr == 2 ? 1 : 0, cb = pr == 1 ? 1 : 0;
-          for (int a = 0; a < p.d_atoms; ++a) {
-            const uint64_t adesc = make_sdesc_k_sw128(smem_u32(sQ + (ca * p.d_atoms + a) * BM * ATOM_BYTES));
-            const uint64_t bdesc = make_sdesc_k_sw128(
-                smem_u32(sK + slot * q_tile_bytes + (cb * p.d_atoms + a) * BN * ATOM_BYTES + (h & 1) * BS * ATOM_BYTES));
-#pragma unroll
-            for (int s = 0; s < 4; ++s) {
-              if (!(p.dbg & 16)) mma_ss_f16(tmem_S(b), adesc + 2 * s, bdesc + 2 * s, idesc_qk, acc);
-              acc = 1;
-            }
-          }
+        const uint64_t hoff = (h & 1) ? half_tile : 0;
+        const uint32_t d_s = tmem_S(b);
+        if (slot == 0) {
+          if (p.split) { if (p.d_atoms == 1) qk_step_mmas<1, 3>(d_s, qa, kb[0], hoff, idesc_qk); else qk_step_mmas<2, 3>(d_s, qa, kb[0], hoff, idesc_qk); }
+          else { if (p.d_atoms == 1) qk_step_mmas<1, 1>(d_s, qa, kb[0], hoff, idesc_qk); else qk_step_mmas<2, 1>(d_s, qa, kb[0], hoff, idesc_qk); }
+        } else {
+          if (p.split) { if (p.d_atoms == 1) qk_step_mmas<1, 3>(d_s, qa, kb[1], hoff, idesc_qk); else qk_step_mmas<2, 3>(d_s, qa, kb[1], hoff, idesc_qk); }
+          else { if (p.d_atoms == 1) qk_step_mmas<1, 1>(d_s, qa, kb[1], hoff, idesc_qk); else qk_step_mmas<2, 1>(d_s, qa, kb[1], hoff, idesc_qk); }
         }
         tc_commit(&s_full[b]);
         if (h & 1) {  // both halves of the K tile consumed

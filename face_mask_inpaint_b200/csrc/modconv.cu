@@ -15,6 +15,8 @@
 //   intermediate; a second streaming kernel applies the 4x4 blur (pad 1,1) fused with noise + bias + leaky-ReLU.
 // ToRGB (:360-369): 1x1 modulated conv to 3 channels without demodulation — HBM-bound, so a warp-shuffle SIMT kernel
 //   that also fuses `+ bias` and `+ upfirdn2d(skip, up=2)` (Upsample, :30-49).
+#include <stdlib.h>
+
 #include "modconv_gemm.cuh"
 
 using namespace sm100;
@@ -44,36 +46,51 @@ __global__ void __launch_bounds__(256) style_mod_kernel(const float* __restrict_
 // demod[b, o] = rsqrt( sum_{i,t} (scale * W[o,i,t] * s[b,i])^2 + 1e-8 )   (model.py:245-249). One block per (o, b).
 template <typename OT, bool ROUND_TF32>
 __global__ void __launch_bounds__(256) weight_prep_kernel(const float* __restrict__ w, const float* __restrict__ s,
-                                                          OT* __restrict__ wp, int I, int O, int T, float scale,
-                                                          int demodulate) {
-  const int o = blockIdx.x, b = blockIdx.y;
-  const float* wo = w + (int64_t)o * I * T;
-  const float* sb = s + (int64_t)b * I;
+                                                          OT* __restrict__ wp, int B, int I, int O, int T,
+                                                          float scale, int demodulate) {
+  // One block per output channel o; W[o] (I*T floats, <= 18 KB) is staged ONCE in shared memory with coalesced loads and
+  // pre-multiplied by `scale`, then every sample of the batch is produced from it (the first version re-read W[o] from
+  // global memory with a stride-T gather once per sample: 59 us per 512x512 layer, 10 % of the decoder forward).
+  extern __shared__ float sw[];  // [I*T] scale * W[o], original (i, t) order
   __shared__ float red[8];
   __shared__ float demod_s;
-  float d = 1.f;
-  if (demodulate) {
-    float acc = 0.f;
-    for (int e = threadIdx.x; e < I * T; e += 256) {
-      const float v = scale * wo[e] * sb[e / T];
-      acc = fmaf(v, v, acc);
+  const int o = blockIdx.x;
+  const int n = I * T;
+  const float* wo = w + (int64_t)o * n;
+  for (int e = threadIdx.x; e < n; e += 256) sw[e] = scale * wo[e];
+  __syncthreads();
+  for (int b = blockIdx.y; b < B; b += gridDim.y) {
+    const float* sb = s + (int64_t)b * I;
+    float d = 1.f;
+    if (demodulate) {
+      float acc = 0.f;
+      for (int i = threadIdx.x; i < I; i += 256) {
+        const float si = sb[i];
+        float q = 0.f;
+        for (int t = 0; t < T; ++t) {
+          const float v = sw[i * T + t];
+          q = fmaf(v, v, q);
+        }
+        acc = fmaf(q, si * si, acc);
+      }
+      acc = warp_sum(acc);
+      __syncthreads();  // red / demod_s of the previous sample have been read
+      if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+      __syncthreads();
+      if (threadIdx.x < 32) {
+        float tt = threadIdx.x < 8 ? red[threadIdx.x] : 0.f;
+        tt = warp_sum(tt);
+        if (threadIdx.x == 0) demod_s = rsqrtf(tt + 1e-8f);
+      }
+      __syncthreads();
+      d = demod_s;
     }
-    acc = warp_sum(acc);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      float t = threadIdx.x < 8 ? red[threadIdx.x] : 0.f;
-      t = warp_sum(t);
-      if (threadIdx.x == 0) demod_s = rsqrtf(t + 1e-8f);
+    for (int e = threadIdx.x; e < n; e += 256) {
+      const int t = e / I, i = e - t * I;  // write order: i fastest (coalesced); smem read is a stride-T gather (T = 9: no conflicts)
+      float v = sw[i * T + t] * sb[i] * d;
+      if (ROUND_TF32) v = __uint_as_float(f32_to_tf32_rna(v));
+      wp[(((int64_t)b * T + t) * O + o) * I + i] = from_f32<OT>(v);
     }
-    __syncthreads();
-    d = demod_s;
-  }
-  for (int e = threadIdx.x; e < I * T; e += 256) {
-    const int t = e / I, i = e % I;  // write order: i fastest (coalesced); read w[o][i][t] strided (L1/L2 resident)
-    float v = scale * wo[i * T + t] * sb[i] * d;
-    if (ROUND_TF32) v = __uint_as_float(f32_to_tf32_rna(v));
-    wp[(((int64_t)b * T + t) * O + o) * I + i] = from_f32<OT>(v);
   }
 }
 
@@ -314,10 +331,16 @@ extern "C" int fmi_modconv_weight_prep(const float* weight, const float* s, void
   FMI_REQUIRE(weight && s && wp && I >= 1 && O >= 1 && (ksize == 1 || ksize == 3), "modconv_weight_prep: bad arguments");
   const int T = ksize * ksize;
   const float scale = 1.0f / sqrtf((float)(I * T));  // model.py:225-226
-  dim3 grid(O, B);
+  // blocks: O x (batch slices); each block stages W[o] once and loops over its samples
+  int by = B;
+  while (by > 1 && (int64_t)O * by > (int64_t)FMI_NUM_SMS * 8) by = (by + 1) / 2;
   cudaStream_t st = (cudaStream_t)stream;
-  if (mma == FMI_MMA_TF32) weight_prep_kernel<float, true><<<grid, 256, 0, st>>>(weight, s, (float*)wp, I, O, T, scale, demodulate);
-  else weight_prep_kernel<__nv_bfloat16, false><<<grid, 256, 0, st>>>(weight, s, (__nv_bfloat16*)wp, I, O, T, scale, demodulate);
+  const size_t smem = (size_t)I * T * sizeof(float);
+  FMI_REQUIRE(smem <= 48 * 1024, "modconv_weight_prep: I*k*k = %d floats exceed the staging buffer", I * T);
+  if (mma == FMI_MMA_TF32)
+    weight_prep_kernel<float, true><<<dim3(O, by, 1), 256, smem, st>>>(weight, s, (float*)wp, B, I, O, T, scale, demodulate);
+  else
+    weight_prep_kernel<__nv_bfloat16, false><<<dim3(O, by, 1), 256, smem, st>>>(weight, s, (__nv_bfloat16*)wp, B, I, O, T, scale, demodulate);
   return fmi_launched("modconv_weight_prep");
 }
 
@@ -431,6 +454,16 @@ int styled_conv_impl(const void* x, const void* wp, void* y, const float* noise,
       p.rgb_w = rgb->w; p.rgb_bias = rgb->bias; p.rgb_skip = rgb->skip; p.rgb_kf = rgb->kf; p.rgb_out = rgb->out;
     }
     TilePlan tp = pick_tile(p.Mh, p.Mw);
+    // halo mode (FMI_MODCONV_HALO=1): wide, narrow-channel layers re-read every activation once per tap from L2 (ncu: 10 GB
+    // of L2 reads for 0.6 GB of DRAM reads on 32 -> 32 @1024^2); loading each kernel row once cuts that 3x, is parity-green,
+    // but measured SLOWER (5.59 vs 5.37 ms per forward): L2 re-reads are not what bounds these layers
+    const bool halo_env = [] { const char* e = getenv("FMI_MODCONV_HALO"); return e && e[0] == '1'; }();  // opt-in (read per call): measured 4-7 % slower
+    p.halo = halo_env && W >= 128 && p.n_tile <= 128;
+    if (p.halo) {
+      for (int a = 0; a < 3; ++a)
+        for (int c = 0; c < 3; ++c) p.halo_slab[a][c] = a * 3 + c;
+      tp = TilePlan{1, 130, 0, 0};  // box: 130 pixels of one row
+    }
     CUtensorMap mx;
     int e = make_x_map(&mx, tp.TH, tp.TW);
     FMI_REQUIRE(e == 0, "styled_conv: cuTensorMapEncodeTiled(x) failed (%d)", e);

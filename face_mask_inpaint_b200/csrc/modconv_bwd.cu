@@ -18,6 +18,8 @@
 //   5. weight_bwd_kernel         through the modulation/demodulation:  du = d (G - Wp c), c[b,o] = sum_{i,t} G Wp;
 //                                dW[o,i,t] = scale sum_b s[b,i] du ;  ds[b,i] = scale sum_{o,t} W[o,i,t] du
 //   ToRGB: torgb_bwd_nhwc_kernel  dx[p,c] = sum_o rgb_w[b,o,c] drgb[b,o,p];  d rgb_w[b,o,c] = sum_p drgb[b,o,p] x[p,c]
+#include <stdlib.h>
+
 #include "modconv_gemm.cuh"
 
 using namespace sm100;
@@ -589,6 +591,14 @@ extern "C" int fmi_styled_conv_bwd_nhwc(const void* x, const void* y, const void
     }
     {
       TilePlan tp = pick_tile(p.Mh, p.Mw);
+      const bool halo_env = [] { const char* e = getenv("FMI_MODCONV_HALO"); return e && e[0] == '1'; }();  // opt-in (read per call): measured 4-7 % slower
+      p.halo = halo_env && !upsample && W >= 128 && p.n_tile <= 128;
+      if (p.halo) {
+        // dx[p] += g[p + (oy, ox)] WpT[t] with (oy, ox) = -(tap offset of t): kernel row dyi reads offset dyi - 1
+        for (int a = 0; a < 3; ++a)
+          for (int c = 0; c < 3; ++c) p.halo_slab[a][c] = (2 - a) * 3 + (2 - c);
+        tp = TilePlan{1, 130, 0, 0};
+      }
       uint64_t dims[4] = {(uint64_t)O, (uint64_t)GW, (uint64_t)GH, (uint64_t)GB};
       uint64_t str[3] = {(uint64_t)O * esz, (uint64_t)GW * O * esz, (uint64_t)GH * GW * O * esz};
       uint32_t box[4] = {epa, (uint32_t)tp.TW, (uint32_t)tp.TH, 1};

@@ -13,6 +13,7 @@ using namespace sm100;
 constexpr int kGemmThreads = 192;
 constexpr int kMaxTaps = 9;
 constexpr int A_STAGE_BYTES = 128 * 128;
+constexpr int A_HALO_BYTES = 17 * 1024;   // 130 pixel rows of 128 bytes, padded to the 1024-byte swizzle period
 
 struct ConvGemmParams {
   int B, I, O, H, W;   // input NHWC
@@ -20,6 +21,12 @@ struct ConvGemmParams {
   int Mh, Mw;          // iteration domain of this launch (per image)
   int TH, TW, tiles_w; // pixel tile (TH*TW <= 128)
   int tiles_per_img, n_otiles, total_tiles;  // persistent tile loop: t -> (sample, output-channel tile, pixel tile)
+  // halo mode (plain 3x3 convs on wide images): the pixel tile is 128 consecutive pixels of ONE image row; per kernel row
+  // dy a single TMA box of 130 pixels (x0-1 .. x0+128, zero filled outside) serves the three horizontal taps — the A
+  // descriptor of tap dx starts (dx+1) * 128 bytes into the SWIZZLE_128B tile (tools/umma_probe.cu tests 9-12: the MMA unit
+  // swizzles on address bits, so a row-shifted start address reads the right rows). 3 instead of 9 activation loads.
+  int halo;
+  int halo_slab[3][3];  // weight slab of tap (dy-1, dx-1)
   int ntaps, tap_dy[kMaxTaps], tap_dx[kMaxTaps], tap_slab[kMaxTaps];
   int tap_boff[kMaxTaps];  // added to the batch coordinate of the A box (parity planes of the up-conv data gradient)
   int T;               // weight slabs per sample
@@ -53,13 +60,14 @@ __global__ void __launch_bounds__(kGemmThreads, 3)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int b_stage_bytes = p.n_tile * 128;
-  const int stage_bytes = A_STAGE_BYTES + b_stage_bytes;
+  const int a_bytes = p.halo ? A_HALO_BYTES : A_STAGE_BYTES;
+  const int stage_bytes = a_bytes + (p.halo ? 3 : 1) * b_stage_bytes;
   __shared__ uint64_t full[8], empty[8], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ float4 s_rgbw[256];  // fused ToRGB weights of the current image: (w_r, w_g, w_b, -) per output channel
 
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int iters = p.ntaps * p.k_chunks;
+  const int iters = (p.halo ? 3 : p.ntaps) * p.k_chunks;
   const int per_img = p.tiles_per_img * p.n_otiles;
   auto decode = [&](int t, int& b, int& o0, int& m0, int& n0) {
     b = t / per_img;
@@ -105,8 +113,16 @@ __global__ void __launch_bounds__(kGemmThreads, 3)
           const int st = g % p.stages;
           const int tap = it / p.k_chunks, kc = it % p.k_chunks;
           mbar_wait(&empty[st], ((g / p.stages) & 1) ^ 1);
-          mbar_arrive_expect_tx(&full[st], bytes);
           uint8_t* sA = smem + st * stage_bytes;
+          if (p.halo) {  // `tap` is the kernel row here
+            mbar_arrive_expect_tx(&full[st], (uint32_t)(130 * 128 + 3 * b_stage_bytes));
+            tma_load_4d(sA, &map_x, &full[st], kc * EPA, n0 - 1, m0 + tap - 1, b);
+            for (int dxi = 0; dxi < 3; ++dxi)
+              tma_load_2d(sA + A_HALO_BYTES + dxi * b_stage_bytes, &map_w, &full[st], kc * EPA,
+                          (b * p.T + p.halo_slab[tap][dxi]) * p.O + o0);
+            continue;
+          }
+          mbar_arrive_expect_tx(&full[st], bytes);
           tma_load_4d(sA, &map_x, &full[st], kc * EPA, n0 + p.tap_dx[tap], m0 + p.tap_dy[tap], b + p.tap_boff[tap]);
           tma_load_2d(sA + A_STAGE_BYTES, &map_w, &full[st], kc * EPA, (b * p.T + p.tap_slab[tap]) * p.O + o0);
         }
@@ -129,6 +145,22 @@ __global__ void __launch_bounds__(kGemmThreads, 3)
           mbar_wait(&full[st], (g / p.stages) & 1);
           tc_fence_after();
           uint8_t* sA = smem + st * stage_bytes;
+          if (p.halo) {
+            const int ksteps_h = (it % p.k_chunks == p.k_chunks - 1) ? last_ksteps : 4;
+            for (int dxi = 0; dxi < 3; ++dxi) {
+              const uint64_t ad = make_sdesc_k_sw128(smem_u32(sA) + dxi * 128);  // window shifted by dxi pixel rows
+              const uint64_t bd = make_sdesc_k_sw128(smem_u32(sA + A_HALO_BYTES + dxi * b_stage_bytes));
+#pragma unroll
+              for (int s = 0; s < 4; ++s) {
+                if (s >= ksteps_h) break;
+                const uint32_t acc = (it > 0 || dxi > 0 || s > 0) ? 1u : 0u;
+                if (TF32) mma_ss_tf32(d_tmem, ad + 2 * s, bd + 2 * s, idesc, acc);
+                else mma_ss_f16(d_tmem, ad + 2 * s, bd + 2 * s, idesc, acc);
+              }
+            }
+            tc_commit(&empty[st]);
+            continue;
+          }
           const uint64_t adesc = make_sdesc_k_sw128(smem_u32(sA));
           const uint64_t bdesc = make_sdesc_k_sw128(smem_u32(sA + A_STAGE_BYTES));
           // the last channel chunk of a narrow layer is partly TMA zero fill (I = 32 bf16 fills half a 128-byte row):
@@ -291,17 +323,19 @@ int launch_gemm_class(const CUtensorMap& mx, const CUtensorMap& mw, ConvGemmPara
     FMI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 6144));  // static: 5 KB
     attr_set = true;
   }
-  const int stage_bytes = A_STAGE_BYTES + p.n_tile * 128;
+  const int stage_bytes = p.halo ? A_HALO_BYTES + 3 * p.n_tile * 128 : A_STAGE_BYTES + p.n_tile * 128;
   // Two accumulators per CTA in TMEM. Narrow tiles (N <= 64: 128 columns) leave room for 3 co-resident CTAs, N <= 128 for
   // 2; the TMA ring is sized to the CTA's share of shared memory.
   p.tmem_cols = p.n_tile <= 16 ? 32 : p.n_tile <= 32 ? 64 : p.n_tile <= 64 ? 128 : p.n_tile <= 128 ? 256 : 512;
-  const int ctas_per_sm = p.n_tile <= 64 ? 3 : p.n_tile <= 128 ? 2 : 1;
+  // (a halo stage is 17 KB + three weight tiles and carries three taps: fewer, fatter CTAs)
+  const int ctas_per_sm = p.halo ? (p.n_tile <= 32 ? 2 : 1) : (p.n_tile <= 64 ? 3 : p.n_tile <= 128 ? 2 : 1);
   int stages = ((232448 - 6144) / ctas_per_sm - 2048) / stage_bytes;
   if (stages > 8) stages = 8;
   FMI_REQUIRE(stages >= 2, "modconv_gemm: stage of %d bytes does not fit twice", stage_bytes);
   p.stages = stages;
   const size_t smem = (size_t)stages * stage_bytes + 1024;
   TilePlan tp = pick_tile(p.Mh, p.Mw);
+  if (p.halo) tp = TilePlan{1, 128, p.Mh, (p.Mw + 127) / 128};
   p.TH = tp.TH; p.TW = tp.TW; p.tiles_w = tp.tiles_w;
   p.tiles_per_img = tp.tiles_h * tp.tiles_w;
   p.n_otiles = p.O / p.n_tile;

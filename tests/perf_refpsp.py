@@ -72,6 +72,27 @@ def main():
                 print(f"{f'ours {prec} operands B={batch}':64s} {t:10.2f} {batch / t * 1e3:9.1f}  | encoder (cuDNN trunk + our "
                       f"attention/blends) {enc:6.2f} ms, decoder {t - enc:6.2f} ms (implicit GEMMs {tot.value:5.2f} ms)", flush=True)
             os.environ.pop("FMI_PRECISION")
+        # library tuning of the out-of-scope trunk: bf16 autocast (+ channels_last inputs) around the IR-SE50 encoder only
+        os.environ["FMI_PRECISION"] = "bf16"
+        for batch in (2, 8):
+            x, ref, mask = (t.cuda() for t in refpsp_inputs(batch))
+            for cl in (False, True):
+                xx = x.contiguous(memory_format=torch.channels_last) if cl else x
+                rr = ref.contiguous(memory_format=torch.channels_last) if cl else ref
+
+                def fn():
+                    with torch.autocast("cuda", dtype=torch.bfloat16):
+                        codes = net.encoder(xx, ref=rr, mask=mask)
+                    codes = codes.float() + net.latent_avg.cuda()
+                    return net.face_pool(net.decoder([codes], input_is_latent=True, randomize_noise=False)[0])
+
+                try:
+                    t = time_cuda(fn)
+                    print(f"{f'ours bf16 operands + bf16-autocast trunk (channels_last={int(cl)}) B={batch}':64s} {t:10.2f} "
+                          f"{batch / t * 1e3:9.1f}", flush=True)
+                except Exception as ex:  # noqa: BLE001
+                    print(f"autocast trunk cl={cl} B={batch} failed: {type(ex).__name__}: {str(ex)[:200]}")
+        os.environ.pop("FMI_PRECISION")
         # the reference formulation on this GPU, batch 2
         x, ref, mask = (t.cuda() for t in refpsp_inputs(2))
         refnet = copy.deepcopy(net)

@@ -70,7 +70,8 @@ def _check(named_got, named_want, tol, scales=None):
     (2, 256, 128, 32, 32, True),    # three taps per CTA on 128-wide N, M = 128
     (1, 128, 256, 32, 32, False),   # two M tiles
     (1, 32, 32, 128, 128, True),    # 32 channels = half a swizzle atom on both operands, split-K over 256 K tiles
-    (1, 64, 32, 64, 128, False),    # non-square
+    (1, 64, 32, 64, 128, False),    # non-square; W = 128: forward and data gradient run in halo mode
+    (1, 64, 64, 8, 256, False),     # halo mode, two tiles per row
 ])
 @pytest.mark.parametrize("mode", MODES, ids=[m[0] for m in MODES])
 def test_styled_conv_backward(cfg, mode):

@@ -36,6 +36,9 @@ def _randomize(mod, g):
     (2, 512, 512, 4, 4, True),      # first up layer: parity classes of 5x5 / 4x5 / 5x4 / 4x4
     (1, 128, 64, 40, 24, False),    # ragged tiles
     (1, 32, 32, 64, 64, True),      # 32 input channels = half a swizzle row (TMA zero fill along K)
+    (1, 32, 32, 8, 256, False),     # halo mode (W >= 128): one 130-pixel box per kernel row, two tiles per row
+    (2, 64, 64, 5, 130, False),     # halo mode, ragged second tile (2 valid pixels), top/bottom padding rows
+    (1, 128, 128, 4, 128, False),   # halo mode, N tile 128, two K chunks
 ])
 @pytest.mark.parametrize("mode", MODES, ids=[m[0] for m in MODES])
 def test_modulated_conv2d(cfg, mode):
@@ -124,3 +127,26 @@ def test_generator_synthesis(mode, monkeypatch):
     assert got.shape == (2, 3, 64, 64)
     err = rel_err(got, want)
     assert err <= tol, f"rel err {err:.3e}"
+
+
+@pytest.mark.parametrize("cfg", [(1, 32, 32, 8, 256), (2, 64, 64, 5, 130), (1, 128, 128, 4, 128)])
+@pytest.mark.parametrize("mode", MODES, ids=[m[0] for m in MODES])
+def test_modulated_conv2d_halo_mode(cfg, mode, monkeypatch):
+    """Opt-in halo mode of the implicit GEMM (FMI_MODCONV_HALO=1): one 130-pixel TMA box per kernel row, the three
+    horizontal taps read row-shifted windows of it (tools/umma_probe.cu tests 9-12 establish that the MMA unit swizzles on
+    address bits, so a descriptor may start at any 128-byte row of a SWIZZLE_128B tile)."""
+    monkeypatch.setenv("FMI_MODCONV_HALO", "1")
+    SG = _mods()
+    b, i, o, h, w = cfg
+    _, dtype, tol = mode
+    g = torch.Generator().manual_seed(21)
+    mod = SG.ModulatedConv2d(i, o, 3, 512)
+    _randomize(mod, g)
+    x = torch.randn(b, i, h, w, generator=g).to(dtype).float()
+    style = torch.randn(b, 512, generator=g)
+    want = O.modulated_conv2d(x, style, mod.weight.detach(), mod.modulation.weight.detach(),
+                              mod.modulation.bias.detach(), True, False)
+    mod = mod.to(DEV)
+    with torch.no_grad():
+        got = mod(x.to(dtype).to(DEV), style.to(DEV))
+    assert rel_err(got, want) <= tol

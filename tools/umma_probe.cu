@@ -254,6 +254,145 @@ int run(const char* name, int N, int katoms) {
   return pass ? 0 : 1;
 }
 
+// ---- halo test: ONE TMA box of 130 consecutive pixels (NHWC row segment starting at x = -1, zero filled) serves the three
+// horizontal taps of a 3x3 convolution: the A descriptor of tap dx simply starts (dx + 1) pixel rows = (dx + 1) * 128 bytes
+// further into the SWIZZLE_128B tile. Valid iff the MMA unit applies the 128-byte swizzle to ADDRESS bits (as TMA does
+// when it writes), not to row indices relative to the descriptor start.
+template <bool TF32>
+__global__ void __launch_bounds__(128) halo_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                   const __grid_constant__ CUtensorMap mapB, float* __restrict__ D, int N,
+                                                   int base_off_mode) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  constexpr int EPA = TF32 ? 32 : 64;
+  uint8_t* sA = smem;                 // 130 rows x 128 B (padded to 17 KB)
+  uint8_t* sB = smem + 17 * 1024;     // N rows x 128 B
+  __shared__ uint64_t bar_load, bar_mma;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) {
+    mbar_init(&bar_load, 1);
+    mbar_init(&bar_mma, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(&tmem_base_s, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  if (tid == 0) {
+    mbar_arrive_expect_tx(&bar_load, 130 * 128 + N * 128);
+    tma_load_4d(sA, &mapA, &bar_load, 0, -1, 1, 0);   // pixels x = -1 .. 128 of image row 1
+    tma_load_2d(sB, &mapB, &bar_load, 0, 0);
+    mbar_wait(&bar_load, 0);
+    tc_fence_after();
+    const uint32_t idesc = make_idesc(TF32 ? KIND_TF32 : KIND_BF16, 128, N);
+    for (int j = 0; j < 3; ++j) {
+      const uint32_t a_addr = smem_u32(sA) + j * 128;
+      uint64_t adesc = make_sdesc_k_sw128(a_addr);
+      if (base_off_mode) adesc |= (uint64_t)((a_addr >> 7) & 7) << 49;  // PTX "matrix base offset" field
+      const uint64_t bdesc = make_sdesc_k_sw128(smem_u32(sB));
+      for (int s = 0; s < 4; ++s) {
+        if (TF32) mma_ss_tf32(tmem + j * N, adesc + 2 * s, bdesc + 2 * s, idesc, s > 0);
+        else mma_ss_f16(tmem + j * N, adesc + 2 * s, bdesc + 2 * s, idesc, s > 0);
+      }
+    }
+    tc_commit(&bar_mma);
+  }
+  __syncwarp();
+  mbar_wait(&bar_mma, 0);
+  tc_fence_after();
+  for (int c0 = 0; c0 < 3 * N; c0 += 32) {
+    uint32_t v[32];
+    tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+    tc_wait_ld();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) D[(size_t)tid * 3 * N + c0 + j] = __uint_as_float(v[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+template <bool TF32>
+int run_halo(const char* name, int base_off_mode) {
+  const int EPA = TF32 ? 32 : 64, K = EPA, N = 64, esz = TF32 ? 4 : 2;
+  const int IH = 3, IW = 160;
+  std::vector<float> X((size_t)IH * IW * K), B((size_t)N * K);
+  srand(4321);
+  auto rnd = [] { return (float)(rand() % 2001 - 1000) / 1000.f; };
+  for (auto& v : X) v = TF32 ? tf32_round(rnd()) : bf16_round(rnd());
+  for (auto& v : B) v = TF32 ? tf32_round(rnd()) : bf16_round(rnd());
+  std::vector<float> ref((size_t)128 * 3 * N);
+  for (int j = 0; j < 3; ++j)
+    for (int m = 0; m < 128; ++m)
+      for (int n = 0; n < N; ++n) {
+        const int x = m + j - 1;
+        double s = 0;
+        if (x >= 0 && x < IW)
+          for (int k = 0; k < K; ++k) s += (double)X[((size_t)1 * IW + x) * K + k] * B[(size_t)n * K + k];
+        ref[(size_t)m * 3 * N + j * N + n] = (float)s;
+      }
+  auto upload = [&](const std::vector<float>& src) -> void* {
+    void* d;
+    if (TF32) {
+      CK(cudaMalloc(&d, src.size() * 4));
+      CK(cudaMemcpy(d, src.data(), src.size() * 4, cudaMemcpyHostToDevice));
+    } else {
+      std::vector<__nv_bfloat16> h(src.size());
+      for (size_t i = 0; i < src.size(); ++i) h[i] = __float2bfloat16_rn(src[i]);
+      CK(cudaMalloc(&d, src.size() * 2));
+      CK(cudaMemcpy(d, h.data(), src.size() * 2, cudaMemcpyHostToDevice));
+    }
+    return d;
+  };
+  void* dX = upload(X);
+  void* dB = upload(B);
+  float* dD;
+  CK(cudaMalloc(&dD, ref.size() * 4));
+  CK(cudaMemset(dD, 0xFF, ref.size() * 4));
+  CUtensorMapDataType dt = TF32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUtensorMap mA, mB;
+  {
+    uint64_t dims[4] = {(uint64_t)K, (uint64_t)IW, (uint64_t)IH, 1};
+    uint64_t str[3] = {(uint64_t)K * esz, (uint64_t)IW * K * esz, (uint64_t)IH * IW * K * esz};
+    uint32_t box[4] = {(uint32_t)EPA, 130, 1, 1};
+    if (make_tensor_map(&mA, dt, 4, dX, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) { printf("%s: map A failed\n", name); return 1; }
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
+    uint64_t str[1] = {(uint64_t)K * esz};
+    uint32_t box[2] = {(uint32_t)EPA, (uint32_t)N};
+    if (make_tensor_map(&mB, dt, 2, dB, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) { printf("%s: map B failed\n", name); return 1; }
+  }
+  const size_t smem = 17 * 1024 + N * 128 + 1024;
+  auto kern = halo_kernel<TF32>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<1, 128, smem>>>(mA, mB, dD, N, base_off_mode);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("%s: KERNEL FAILED: %s\n", name, cudaGetErrorString(e)); return 1; }
+  std::vector<float> out(ref.size());
+  CK(cudaMemcpy(out.data(), dD, out.size() * 4, cudaMemcpyDeviceToHost));
+  int rc = 0;
+  for (int j = 0; j < 3; ++j) {
+    double maxerr = 0, maxref = 0;
+    for (int m = 0; m < 128; ++m)
+      for (int n = 0; n < N; ++n) {
+        const size_t i = (size_t)m * 3 * N + j * N + n;
+        maxerr = fmax(maxerr, fabs((double)out[i] - ref[i]));
+        maxref = fmax(maxref, fabs((double)ref[i]));
+      }
+    const bool pass = maxerr <= 1e-3 * maxref;
+    printf("%s (base_offset field %s): tap shift %d rows: max_abs_err=%.3e max_ref=%.3e -> %s\n", name,
+           base_off_mode ? "set" : "0", j, maxerr, maxref, pass ? "PASS" : "FAIL");
+    rc |= !pass;
+  }
+  return rc;
+}
+
 int main(int argc, char** argv) {
   int t = argc > 1 ? atoi(argv[1]) : 0;
   switch (t) {
@@ -266,6 +405,10 @@ int main(int argc, char** argv) {
     case 6: return run<false, A_IM2COL>("im2col_bf16_k128_n64", 64, 2);
     case 7: return run<false, A_TMA2D>("ss_bf16_k64_n16", 16, 1);
     case 8: return run<true, A_IM2COL>("im2col_tf32_k64_n64", 64, 2);
+    case 9: return run_halo<false>("halo_bf16", 0);
+    case 10: return run_halo<false>("halo_bf16", 1);
+    case 11: return run_halo<true>("halo_tf32", 0);
+    case 12: return run_halo<true>("halo_tf32", 1);
     default: printf("unknown test %d\n", t); return 3;
   }
 }
