@@ -24,6 +24,26 @@
 #pragma once
 
 constexpr int kAttn3Threads = 384;
+
+// One 64-key step of S = Q K^T on a CTA pair with Q in tensor memory: descriptors / TMEM addresses come precomputed, the
+// body is only MMAs (see qk_step_mmas in attention_v2.cuh for why that matters).
+template <int D_ATOMS, int NPAIRS>
+__device__ __forceinline__ void qk_step_mmas_ts2(uint32_t d_tmem, uint32_t tmem_q, const uint64_t (&kb)[4], uint64_t hoff,
+                                                 uint32_t idesc) {
+#pragma unroll
+  for (int pr = 0; pr < NPAIRS; ++pr) {
+    const int ca = pr == 2 ? 1 : 0, cb = pr == 1 ? 1 : 0;  // hi.hi, hi.lo, lo.hi
+#pragma unroll
+    for (int a = 0; a < D_ATOMS; ++a) {
+      const uint32_t at = tmem_q + (ca * D_ATOMS + a) * 32;
+      const uint64_t bd = kb[cb * D_ATOMS + a] + hoff;
+      mma2_ts_f16(d_tmem, at, bd, idesc, (pr | a) ? 1u : 0u);
+      mma2_ts_f16(d_tmem, at + 8, bd + 2, idesc, 1u);
+      mma2_ts_f16(d_tmem, at + 16, bd + 4, idesc, 1u);
+      mma2_ts_f16(d_tmem, at + 24, bd + 6, idesc, 1u);
+    }
+  }
+}
 constexpr int kAttn3StaticSmem = 2048;
 constexpr int kAttn3SmemBudget = 232448 - kAttn3StaticSmem;
 
@@ -136,36 +156,41 @@ __global__ void __launch_bounds__(kAttn3Threads, 1)
     // ---------------------------------------------------------------- QK issuer (leader): S[h % NB] = Q K_h^T  (256 x 64)
     if (lane0 && leader) {
       const uint32_t idesc_qk = make_idesc(KIND_BF16, 2 * BM, BS);
-      const int npairs = p.split ? 3 : 1;
       const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
       long long w_q = 0, w_pv = 0, w_k = 0, c0 = clock64(), c1;
       mbar_wait_cluster(&q_pair, 0);  // both Q tiles are in tensor memory
       tc_fence_after();
       c1 = clock64(); w_q = c1 - c0;
+      // K atoms of both ring slots: [atom][step][32 rows]; a step adds the 32-row offset
+      uint64_t kb[2][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int ii = i < q_atoms ? i : 0;
+        kb[0][i] = make_sdesc_k_sw128(smem_u32(sK + ii * 2 * KH * ATOM_BYTES));
+        kb[1][i] = make_sdesc_k_sw128(smem_u32(sK + k_half_bytes + ii * 2 * KH * ATOM_BYTES));
+      }
+      const uint64_t step_off = (uint64_t)((KH * ATOM_BYTES) >> 4);
+      int b = 0, use = 0;
       for (int h = 0; h < NS; ++h) {
-        const int t = h >> 1, slot = t % p.k_stages, b = h % NB, use = h / NB;
+        const int t = h >> 1, slot = t & 1;
         c0 = clock64();
         if (use > 0) mbar_wait(&pv_done[b], (use - 1) & 1);  // P(h - NB) lived in this buffer
         c1 = clock64(); w_pv += c1 - c0;
-        mbar_wait(&k_full[slot], (t / p.k_stages) & 1);
+        mbar_wait(&k_full[slot], (t >> 1) & 1);
         tc_fence_after();
         c0 = clock64(); w_k += c0 - c1;
-        uint32_t acc = 0;
-        for (int pr = 0; pr < npairs; ++pr) {
-          const int ca = pr == 2 ? 1 : 0, cb = pr == 1 ? 1 : 0;  // hi.hi, hi.lo, lo.hi
-          for (int a = 0; a < p.d_atoms; ++a) {
-            const uint32_t a_t = tmem_Q + (ca * p.d_atoms + a) * 32;
-            const uint64_t bdesc = make_sdesc_k_sw128(
-                smem_u32(sK + slot * k_half_bytes + ((cb * p.d_atoms + a) * 2 + (h & 1)) * KH * ATOM_BYTES));
-#pragma unroll
-            for (int s = 0; s < 4; ++s) {
-              mma2_ts_f16(tmem_S(b), a_t + s * 8, bdesc + 2 * s, idesc_qk, acc);
-              acc = 1;
-            }
-          }
+        const uint64_t hoff = (h & 1) ? step_off : 0;
+        const uint32_t d_s = tmem_S(b);
+        if (slot == 0) {
+          if (p.split) { if (p.d_atoms == 1) qk_step_mmas_ts2<1, 3>(d_s, tmem_Q, kb[0], hoff, idesc_qk); else qk_step_mmas_ts2<2, 3>(d_s, tmem_Q, kb[0], hoff, idesc_qk); }
+          else { if (p.d_atoms == 1) qk_step_mmas_ts2<1, 1>(d_s, tmem_Q, kb[0], hoff, idesc_qk); else qk_step_mmas_ts2<2, 1>(d_s, tmem_Q, kb[0], hoff, idesc_qk); }
+        } else {
+          if (p.split) { if (p.d_atoms == 1) qk_step_mmas_ts2<1, 3>(d_s, tmem_Q, kb[1], hoff, idesc_qk); else qk_step_mmas_ts2<2, 3>(d_s, tmem_Q, kb[1], hoff, idesc_qk); }
+          else { if (p.d_atoms == 1) qk_step_mmas_ts2<1, 1>(d_s, tmem_Q, kb[1], hoff, idesc_qk); else qk_step_mmas_ts2<2, 1>(d_s, tmem_Q, kb[1], hoff, idesc_qk); }
         }
         tc_commit2_mc(&s_full[b], kBoth);
         if (h & 1) tc_commit2_mc(&k_empty[slot], kBoth);  // both steps of the K tile consumed
+        if (++b == NB) { b = 0; ++use; }
       }
       if (tr) { p.trace[0] = w_q; p.trace[1] = w_pv; p.trace[2] = w_k; p.trace[3] = clock64(); }
     }
