@@ -190,6 +190,7 @@ def whole_model_throughput(dev, world, barrier, max_over_ranks):
     prev = os.environ.get("FMI_PRECISION")
     try:
         with torch.no_grad():
+            from face_mask_inpaint_b200.graphs import CapturedForward
             from face_mask_inpaint_b200.modules.picnet import build_picnet_ref
             torch.manual_seed(7)
             net = build_picnet_ref().eval().to(dev)
@@ -199,12 +200,16 @@ def whole_model_throughput(dev, world, barrier, max_over_ranks):
             src, ref = torch.rand(b, 3, 256, 256, device=dev), torch.rand(b, 3, 256, 256, device=dev)
             mask = torch.zeros(b, 256, 256, device=dev)
             mask[:, 128:230, 50:206] = 1.0
-            ms = timed(lambda: net(src, ref, mask))
+            ms_eager = timed(lambda: net(src, ref, mask))
+            fwd = CapturedForward(net, src, ref, mask)
+            ms = timed(lambda: fwd(src, ref, mask))
             out["picnet_ref_256"] = {"value": world * b / (ms * 1e-3), "unit": "img/s", "per_gpu_batch": b, "ms_per_step": ms,
+                                     "launch": "one CUDA-graph replay per forward (graphs.CapturedForward)",
+                                     "eager_ms_per_step": ms_eager, "eager_value": world * b / (ms_eager * 1e-3),
                                      "precision": "fp32 I/O, TF32 attention operands, cuDNN convs (TF32 allowed)",
                                      "what": "ReferenceFill forward: 2 encoders, ExampleGuidedAttention@32^2, decoder with "
                                              "Auto_Attn@128^2 up to 1024^2, pooled to 256^2"}
-            del net
+            del net, fwd
             from face_mask_inpaint_b200.modules.psp import pSp, refpsp_opts
             os.environ["FMI_PRECISION"] = "bf16"
             net = pSp(refpsp_opts(output_size=1024)).eval().to(dev)
@@ -212,10 +217,15 @@ def whole_model_throughput(dev, world, barrier, max_over_ranks):
             x, ref = torch.rand(b, 3, 256, 256, device=dev) * 2 - 1, torch.rand(b, 3, 256, 256, device=dev) * 2 - 1
             mask = torch.zeros(b, 256, 256, device=dev)
             mask[:, 128:230, 50:206] = 1.0
-            ms = timed(lambda: net(x, ref=ref, src_mask=mask, resize=True, randomize_noise=False))
+            ms_eager = timed(lambda: net(x, ref=ref, src_mask=mask, resize=True, randomize_noise=False))
+            fwd = CapturedForward(net, x, ref=ref, src_mask=mask, resize=True, randomize_noise=False)
+            ms = timed(lambda: fwd(x, ref=ref, src_mask=mask))
+            del fwd
             codes = net.encoder(x, ref=ref, mask=mask)
             ms_dec = timed(lambda: net.decoder([codes], input_is_latent=True, randomize_noise=False))
             out["refpsp_1024"] = {"value": world * b / (ms * 1e-3), "unit": "img/s", "per_gpu_batch": b, "ms_per_step": ms,
+                                  "launch": "one CUDA-graph replay per forward (graphs.CapturedForward)",
+                                  "eager_ms_per_step": ms_eager, "eager_value": world * b / (ms_eager * 1e-3),
                                   "decoder_only_ms": ms_dec, "decoder_only_img_s": world * b / (ms_dec * 1e-3),
                                   "precision": "bf16 tensor-core operands in the decoder and attention, cuDNN trunk fp32/TF32",
                                   "what": "pSp forward: IR-SE50 GradualStyleEncoder on source+reference, attention1/2, masked "

@@ -1,0 +1,386 @@
+// f1: the PICNet decoder conv blocks — ResBlockDecoder / Output of
+// modules/pluralistic_model/base_function.py:308-398 as built by ResGenerator (network.py:175-268) — on the tcgen05
+// implicit-GEMM kernel of modconv_gemm.cuh (weights shared by the batch instead of per-sample) plus three streaming kernels.
+//
+// One ResBlockDecoder, input x [B,H,W,Cin] -> output [B,2H,2W,Co], NHWC in the tensor-core operand type:
+//   a1 = lrelu(IN(x))                    instnorm_stats + instnorm_finalize + norm_act      (base_function.py:343-345)
+//   h  = conv3x3(a1) + b1                implicit GEMM, 9 taps, TMA zero fill = padding 1    (:336,345)
+//   a2 = lrelu(IN(h))                    written into channels [0,Ch) of the buffer that holds x in channels [Ch,Ch+Cin)
+//   y  = convT(a2) + b2 + convT_s(x) + bs ONE implicit GEMM over the concatenated channels [a2 | x] with the concatenated
+//                                        weights [W2 | Ws]: both are ConvTranspose2d(3, stride 2, padding 1, output_padding 1)
+//                                        (:337-338,350), so main path and shortcut share taps and the sum is the accumulator.
+//                                        Stride 2 is run as its 4 output-parity classes: out[2m+py, 2n+px] reads
+//                                        ky = 1 (py = 0) or ky in {0 (row m+1), 2 (row m)} (py = 1) — 1/2/2/4 taps, 9/4 taps
+//                                        per output pixel, the FLOPs of the reference; rows m+1 = H are TMA zero fill.
+//   The epilogue writes y straight into the channel slice of the NEXT block's [a2 | x] buffer, or — last block — applies the
+//   Output block's leaky-ReLU (:389-392) and writes the interior of a reflection-padded buffer; `reflect_border` completes
+//   ReflectionPad2d(1) and the Output conv is a 9-tap valid conv with tanh, storing the fp32 NCHW image.
+// InstanceNorm2d(affine=True, eps=1e-5; base_function.py:46): biased variance over H*W per (sample, channel).
+#include "modconv_gemm.cuh"
+
+using namespace sm100;
+using namespace fmi_conv;
+
+namespace {
+
+// ---- Wp[t][o][i_off + i] = OT(w[o,i,t])  (Conv2d weight [O,I,3,3])  or  OT(w[i,o,t])  (ConvTranspose2d weight [I,O,3,3]) ----
+template <typename OT, bool ROUND_TF32>
+__global__ void __launch_bounds__(256) conv_weight_prep_kernel(const float* __restrict__ w, OT* __restrict__ wp, int O, int I,
+                                                               int transposed, int O_rows, int I_row, int i_off) {
+  const int total = O * I * 9;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int t = e % 9, r = e / 9;
+    int o, i;
+    if (transposed) { i = r / O; o = r - i * O; }
+    else { o = r / I; i = r - o * I; }
+    float v = w[e];
+    if (ROUND_TF32) v = __uint_as_float(f32_to_tf32_rna(v));
+    wp[((int64_t)t * O_rows + o) * I_row + i_off + i] = from_f32<OT>(v);
+  }
+}
+
+// ---- per (sample, channel) sum and sum of squares over the pixels of an NHWC tensor (or channel slice) ----------------
+// Thread = one 16-byte channel vector x a strided set of pixels; fp32 partials per thread (<= ~64 pixels), combined in
+// double (shared memory, then one atomicAdd(double) pair per channel and block).
+template <typename OT>
+__global__ void __launch_bounds__(256) instnorm_stats_kernel(const OT* __restrict__ x, int64_t pix_stride, int64_t img_stride,
+                                                             int HW, int C, double* __restrict__ sums /*[B][C][2]*/) {
+  constexpr int VEC = 16 / sizeof(OT);
+  const int nvec = C / VEC;
+  const int lanes = 256 / nvec;              // pixel lanes per block
+  const int v = threadIdx.x % nvec, pl = threadIdx.x / nvec;
+  const int b = blockIdx.y;
+  float s[VEC], q[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) s[k] = q[k] = 0.f;
+  if (pl < lanes) {
+    const OT* xb = x + (int64_t)b * img_stride + v * VEC;
+    for (int pp = blockIdx.x * lanes + pl; pp < HW; pp += gridDim.x * lanes) {
+      const Vec16<OT> t = ld_vec16(xb + (int64_t)pp * pix_stride);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        const float f = to_f32<OT>(t.e[k]);
+        s[k] += f;
+        q[k] = fmaf(f, f, q[k]);
+      }
+    }
+  }
+  __shared__ float sh[256][2 * VEC + 1];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) { sh[threadIdx.x][k] = s[k]; sh[threadIdx.x][VEC + k] = q[k]; }
+  __syncthreads();
+  // thread e < C*2 reduces one (channel, sum|sq) over the pixel lanes
+  for (int e = threadIdx.x; e < 2 * C; e += 256) {
+    const int c = e >> 1, which = e & 1;
+    const int vv = c / VEC, k = c % VEC;
+    double acc = 0.0;
+    for (int l = 0; l < lanes; ++l) acc += (double)sh[l * nvec + vv][which * VEC + k];
+    atomicAdd(&sums[((int64_t)b * C + c) * 2 + which], acc);
+  }
+}
+
+// scale[b,c] = gamma[c] * rstd, shift[b,c] = beta[c] - mean * scale   (so that IN(x) = x * scale + shift)
+__global__ void __launch_bounds__(256) instnorm_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta, float* __restrict__ ss, int B,
+                                                                int C, double inv_n, float eps) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= B * C) return;
+  const int c = e % C;
+  const double mean = sums[2 * (int64_t)e] * inv_n;
+  double var = sums[2 * (int64_t)e + 1] * inv_n - mean * mean;   // biased variance (F.instance_norm)
+  if (var < 0.0) var = 0.0;
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float sc = (gamma ? gamma[c] : 1.f) * rstd;
+  ss[2 * (int64_t)e] = sc;
+  ss[2 * (int64_t)e + 1] = (beta ? beta[c] : 0.f) - (float)mean * sc;
+}
+
+// ---- y = lrelu(x * scale + shift)  (scale/shift NULL: y = lrelu(x)); x and y are NHWC tensors or channel slices ----------
+template <typename OT, bool ROUND_TF32>
+__global__ void __launch_bounds__(256) norm_act_kernel(const OT* __restrict__ x, int64_t x_pix, int64_t x_img,
+                                                       OT* __restrict__ y, int64_t y_pix, int64_t y_img,
+                                                       const float* __restrict__ ss /*[B][C][2]*/, int HW, int C, float slope) {
+  constexpr int VEC = 16 / sizeof(OT);
+  const int nvec = C / VEC;
+  const int b = blockIdx.y;
+  const int64_t total = (int64_t)HW * nvec;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pp = e / nvec;
+    const int c = (int)(e - pp * nvec) * VEC;
+    const Vec16<OT> t = ld_vec16_stream(x + (int64_t)b * x_img + pp * x_pix + c);
+    Vec16<OT> o;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      float f = to_f32<OT>(t.e[k]);
+      if (ss) {
+        const float2 a = *reinterpret_cast<const float2*>(ss + 2 * ((int64_t)b * C + c + k));
+        f = fmaf(f, a.x, a.y);
+      }
+      f = f > 0.f ? f : f * slope;
+      if (ROUND_TF32) f = __uint_as_float(f32_to_tf32_rna(f));
+      o.e[k] = from_f32<OT>(f);
+    }
+    st_vec16(y + (int64_t)b * y_img + pp * y_pix + c, o);
+  }
+}
+
+// ---- ReflectionPad2d(1) border of a [B, H+2, W+2, C] buffer whose interior is already written ------------------------
+template <typename OT>
+__global__ void __launch_bounds__(256) reflect_border_kernel(OT* __restrict__ y, int H, int W, int C) {
+  constexpr int VEC = 16 / sizeof(OT);
+  const int nvec = C / VEC;
+  const int PH = H + 2, PW = W + 2;
+  const int border = 2 * PW + 2 * H;  // top row, bottom row, then left / right columns of the interior rows
+  const int b = blockIdx.y;
+  const int64_t total = (int64_t)border * nvec;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(e / nvec), c = (int)(e - (int64_t)j * nvec) * VEC;
+    int py, px;
+    if (j < PW) { py = 0; px = j; }
+    else if (j < 2 * PW) { py = PH - 1; px = j - PW; }
+    else { const int r = j - 2 * PW; py = 1 + (r >> 1); px = (r & 1) ? PW - 1 : 0; }
+    // padded (py, px) <- image (reflect(py - 1), reflect(px - 1)), image pixel (iy, ix) lives at padded (iy + 1, ix + 1)
+    int iy = py - 1, ix = px - 1;
+    iy = iy < 0 ? -iy : (iy >= H ? 2 * H - 2 - iy : iy);
+    ix = ix < 0 ? -ix : (ix >= W ? 2 * W - 2 - ix : ix);
+    OT* base = y + (int64_t)b * PH * PW * C;
+    st_vec16(base + ((int64_t)py * PW + px) * C + c, ld_vec16(base + ((int64_t)(iy + 1) * PW + ix + 1) * C + c));
+  }
+}
+
+template <typename TI, typename OT, bool ROUND_TF32>
+__global__ void __launch_bounds__(256) nchw_to_nhwc_slice_kernel(const TI* __restrict__ x, OT* __restrict__ y, int C, int HW,
+                                                                 int64_t y_pix, int64_t y_img) {
+  __shared__ float t[32][33];
+  const int b = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j, pp = p0 + tx;
+    t[j][tx] = (c < C && pp < HW) ? to_f32<TI>(x[((int64_t)b * C + c) * HW + pp]) : 0.f;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int pp = p0 + j, c = c0 + tx;
+    if (pp < HW && c < C) {
+      float v = t[tx][j];
+      if (ROUND_TF32) v = __uint_as_float(f32_to_tf32_rna(v));
+      y[(int64_t)b * y_img + (int64_t)pp * y_pix + c] = from_f32<OT>(v);
+    }
+  }
+}
+
+inline int stream_grid(int64_t work_items, int per_block) {
+  int64_t g = (work_items + per_block - 1) / per_block;
+  const int64_t cap = (int64_t)FMI_NUM_SMS * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace
+
+// =====================================================================================================================
+// C ABI
+// =====================================================================================================================
+extern "C" int fmi_conv_weight_prep(const float* weight, void* wp, int O, int I, int transposed, int O_rows, int I_row,
+                                    int i_off, int mma, void* stream) {
+  FMI_REQUIRE(mma == FMI_MMA_TF32 || mma == FMI_MMA_BF16, "conv_weight_prep: bad mma");
+  FMI_REQUIRE(weight && wp && O >= 1 && I >= 1 && O_rows >= O && i_off >= 0 && I_row >= i_off + I,
+              "conv_weight_prep: bad arguments (O=%d I=%d O_rows=%d I_row=%d i_off=%d)", O, I, O_rows, I_row, i_off);
+  const int grid = stream_grid((int64_t)O * I * 9, 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mma == FMI_MMA_TF32)
+    conv_weight_prep_kernel<float, true><<<grid, 256, 0, st>>>(weight, (float*)wp, O, I, transposed, O_rows, I_row, i_off);
+  else
+    conv_weight_prep_kernel<__nv_bfloat16, false><<<grid, 256, 0, st>>>(weight, (__nv_bfloat16*)wp, O, I, transposed, O_rows,
+                                                                        I_row, i_off);
+  return fmi_launched("conv_weight_prep");
+}
+
+extern "C" int fmi_nchw_to_nhwc_slice(const void* x, void* y, int B, int C, int H, int W, int64_t y_pixel_stride, int dtype,
+                                      int mma, void* stream) {
+  FMI_REQUIRE(fmi_dtype_ok(dtype) && (mma == FMI_MMA_TF32 || mma == FMI_MMA_BF16), "nchw_to_nhwc_slice: bad dtype/mma");
+  if (B == 0) return FMI_OK;
+  FMI_REQUIRE(x && y && C >= 1 && H >= 1 && W >= 1 && y_pixel_stride >= C, "nchw_to_nhwc_slice: bad arguments");
+  const int HW = H * W;
+  dim3 grid((HW + 31) / 32, (C + 31) / 32, B);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t yi = (int64_t)HW * y_pixel_stride;
+  FMI_DISPATCH_DTYPE(dtype, T, {
+    if (mma == FMI_MMA_TF32)
+      nchw_to_nhwc_slice_kernel<T, float, true><<<grid, 256, 0, st>>>((const T*)x, (float*)y, C, HW, y_pixel_stride, yi);
+    else
+      nchw_to_nhwc_slice_kernel<T, __nv_bfloat16, false><<<grid, 256, 0, st>>>((const T*)x, (__nv_bfloat16*)y, C, HW,
+                                                                               y_pixel_stride, yi);
+  });
+  return fmi_launched("nchw_to_nhwc_slice");
+}
+
+// IN statistics of x [B, H*W, C] (pixel stride x_pixel_stride elements) folded with the affine parameters:
+// scale_shift [B][C][2] fp32. `sums` is B*C*2 doubles of scratch.
+extern "C" int fmi_instnorm_stats_nhwc(const void* x, int64_t x_pixel_stride, const float* gamma, const float* beta,
+                                       float* scale_shift, double* sums, int B, int C, int HW, float eps, int mma,
+                                       void* stream) {
+  FMI_REQUIRE(mma == FMI_MMA_TF32 || mma == FMI_MMA_BF16, "instnorm_stats: bad mma");
+  if (B == 0) return FMI_OK;
+  const int vec = 16 / esz_of(mma);
+  FMI_REQUIRE(x && scale_shift && sums && HW >= 1 && C >= vec && C % vec == 0 && C / vec <= 256 && x_pixel_stride >= C &&
+                  x_pixel_stride % vec == 0 && fmi_aligned(x, 16),
+              "instnorm_stats: unsupported shape C=%d stride=%lld", C, (long long)x_pixel_stride);
+  cudaStream_t st = (cudaStream_t)stream;
+  FMI_CUDA(cudaMemsetAsync(sums, 0, (size_t)B * C * 2 * sizeof(double), st));
+  const int lanes = 256 / (C / vec);
+  int gx = (HW + lanes * 32 - 1) / (lanes * 32);   // ~32 pixels per thread
+  const int cap = (FMI_NUM_SMS * 8 + B - 1) / B;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  const int64_t img = (int64_t)HW * x_pixel_stride;
+  if (mma == FMI_MMA_TF32)
+    instnorm_stats_kernel<float><<<dim3(gx, B), 256, 0, st>>>((const float*)x, x_pixel_stride, img, HW, C, sums);
+  else
+    instnorm_stats_kernel<__nv_bfloat16><<<dim3(gx, B), 256, 0, st>>>((const __nv_bfloat16*)x, x_pixel_stride, img, HW, C, sums);
+  int rc = fmi_launched("instnorm_stats");
+  if (rc) return rc;
+  instnorm_finalize_kernel<<<(B * C + 255) / 256, 256, 0, st>>>(sums, gamma, beta, scale_shift, B, C, 1.0 / (double)HW, eps);
+  return fmi_launched("instnorm_finalize");
+}
+
+// y = lrelu_slope(x * scale + shift) per (sample, channel); scale_shift NULL = activation only.
+extern "C" int fmi_norm_act_nhwc(const void* x, int64_t x_pixel_stride, void* y, int64_t y_pixel_stride,
+                                 const float* scale_shift, int B, int C, int HW, float slope, int mma, void* stream) {
+  FMI_REQUIRE(mma == FMI_MMA_TF32 || mma == FMI_MMA_BF16, "norm_act: bad mma");
+  if (B == 0) return FMI_OK;
+  const int vec = 16 / esz_of(mma);
+  FMI_REQUIRE(x && y && HW >= 1 && C >= vec && C % vec == 0 && x_pixel_stride % vec == 0 && y_pixel_stride % vec == 0 &&
+                  x_pixel_stride >= C && y_pixel_stride >= C && fmi_aligned(x, 16) && fmi_aligned(y, 16),
+              "norm_act: unsupported shape C=%d strides %lld / %lld", C, (long long)x_pixel_stride, (long long)y_pixel_stride);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t work = (int64_t)HW * (C / vec);
+  int gx = stream_grid(work, 256 * 4);
+  const int cap = (FMI_NUM_SMS * 16 + B - 1) / B;
+  if (gx > cap) gx = cap;
+  if (mma == FMI_MMA_TF32)
+    norm_act_kernel<float, true><<<dim3(gx, B), 256, 0, st>>>((const float*)x, x_pixel_stride, (int64_t)HW * x_pixel_stride,
+                                                              (float*)y, y_pixel_stride, (int64_t)HW * y_pixel_stride,
+                                                              scale_shift, HW, C, slope);
+  else
+    norm_act_kernel<__nv_bfloat16, false><<<dim3(gx, B), 256, 0, st>>>(
+        (const __nv_bfloat16*)x, x_pixel_stride, (int64_t)HW * x_pixel_stride, (__nv_bfloat16*)y, y_pixel_stride,
+        (int64_t)HW * y_pixel_stride, scale_shift, HW, C, slope);
+  return fmi_launched("norm_act");
+}
+
+extern "C" int fmi_reflect_border_nhwc(void* y, int B, int C, int H, int W, int mma, void* stream) {
+  FMI_REQUIRE(mma == FMI_MMA_TF32 || mma == FMI_MMA_BF16, "reflect_border: bad mma");
+  if (B == 0) return FMI_OK;
+  const int vec = 16 / esz_of(mma);
+  FMI_REQUIRE(y && H >= 2 && W >= 2 && C % vec == 0 && fmi_aligned(y, 16), "reflect_border: unsupported shape");
+  const int64_t work = (int64_t)(2 * (W + 2) + 2 * H) * (C / vec);
+  const int gx = stream_grid(work, 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mma == FMI_MMA_TF32) reflect_border_kernel<float><<<dim3(gx, B), 256, 0, st>>>((float*)y, H, W, C);
+  else reflect_border_kernel<__nv_bfloat16><<<dim3(gx, B), 256, 0, st>>>((__nv_bfloat16*)y, H, W, C);
+  return fmi_launched("reflect_border");
+}
+
+// 3x3 convolution / stride-2 transposed convolution with batch-shared weights on the implicit-GEMM kernel.
+//   mode 0: Conv2d(3, stride 1, padding 1)                              x [B,H,W,*]      -> y [B,H,W,*]
+//   mode 1: Conv2d(3, stride 1, padding 0) on a pre-padded input        x [B,H+2,W+2,*]  -> y [B,H,W,*]
+//   mode 2: ConvTranspose2d(3, stride 2, padding 1, output_padding 1)   x [B,H,W,*]      -> y [B,2H,2W,*]
+//   x: I channels per pixel out of x_pixel_stride; wp [9][O][I] from fmi_conv_weight_prep (O a multiple of 32, rows >= the
+//   real output channels zero); bias [O] fp32 or NULL; act 2: y = acc + bias, 1: lrelu_slope(acc + bias), 3: tanh(acc + bias).
+//   y: NHWC in the operand type, O channels per pixel out of y_pixel_stride, written at the interior of a buffer padded by
+//   y_pad pixels on each side (0 or 1); may be NULL when y_nchw is given. y_nchw: fp32 [B, nchw_C, OH, OW] or NULL.
+extern "C" int fmi_conv3x3_nhwc(const void* x, int64_t x_pixel_stride, const void* wp, const float* bias, void* y,
+                                int64_t y_pixel_stride, int y_pad, float* y_nchw, int nchw_C, int B, int I, int O, int H,
+                                int W, int mode, int act, float slope, int mma, void* stream) {
+  FMI_REQUIRE(mma == FMI_MMA_TF32 || mma == FMI_MMA_BF16, "conv3x3: bad mma");
+  if (B == 0) return FMI_OK;
+  FMI_REQUIRE(x && wp && (y || y_nchw), "conv3x3: null pointer");
+  FMI_REQUIRE(mode >= 0 && mode <= 2 && act >= 1 && act <= 3 && (y_pad == 0 || y_pad == 1), "conv3x3: bad mode/act/pad");
+  const int esz = esz_of(mma);
+  FMI_REQUIRE(I >= 16 && O >= 32 && O % 32 == 0 && (O <= 256 || O % 256 == 0) && H >= 1 && W >= 1,
+              "conv3x3: unsupported shape I=%d O=%d H=%d W=%d (O must be a multiple of 32, <= 256 or a multiple of 256)", I, O, H, W);
+  FMI_REQUIRE((I * esz) % 16 == 0 && (x_pixel_stride * esz) % 16 == 0 && x_pixel_stride >= I && fmi_aligned(x, 16) &&
+                  fmi_aligned(wp, 16),
+              "conv3x3: input rows must be 16-byte multiples");
+  FMI_REQUIRE(!y || ((y_pixel_stride * esz) % 16 == 0 && y_pixel_stride >= O && fmi_aligned(y, 16)),
+              "conv3x3: output rows must be 16-byte multiples");
+  FMI_REQUIRE(!y_nchw || (nchw_C >= 1 && nchw_C <= O), "conv3x3: bad nchw_C");
+  int rc = fmi_device_check();
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool tf32 = mma == FMI_MMA_TF32;
+  const uint32_t epa = 128 / esz;
+  const CUtensorMapDataType dt = tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const int IH = mode == 1 ? H + 2 : H, IW = mode == 1 ? W + 2 : W;   // input extents
+  const int OH = mode == 2 ? 2 * H : H, OW = mode == 2 ? 2 * W : W;
+
+  ConvGemmParams p{};
+  p.B = B; p.I = I; p.O = O; p.H = IH; p.W = IW; p.T = 9;
+  p.w_shared = 1;
+  p.n_tile = O <= 256 ? O : 256;
+  p.k_chunks = (I + epa - 1) / epa;
+  p.bias = bias; p.act = act; p.slope = slope; p.gain = 1.f;
+  p.OH = OH; p.OW = OW;
+  p.nchw_out = y_nchw; p.nchw_C = nchw_C;
+  if (y) {
+    const int64_t PW = OW + 2 * y_pad, PH = OH + 2 * y_pad;
+    p.out_pstride = (int)y_pixel_stride;
+    p.out_rstride = PW * y_pixel_stride;
+    p.out_bstride = PH * PW * y_pixel_stride;
+    p.out = (uint8_t*)y + ((int64_t)y_pad * PW + y_pad) * y_pixel_stride * esz;
+  } else {
+    p.out = nullptr;
+    p.out_pstride = O; p.out_rstride = (int64_t)OW * O; p.out_bstride = (int64_t)OH * OW * O;
+  }
+
+  CUtensorMap mw;
+  {
+    uint64_t dims[2] = {(uint64_t)I, (uint64_t)9 * O};
+    uint64_t str[1] = {(uint64_t)I * esz};
+    uint32_t box[2] = {epa, (uint32_t)p.n_tile};
+    int e = make_tensor_map(&mw, dt, 2, wp, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    FMI_REQUIRE(e == 0, "conv3x3: cuTensorMapEncodeTiled(weights) failed (%d)", e);
+  }
+  auto make_x_map = [&](CUtensorMap* m, int th, int tw) -> int {
+    uint64_t dims[4] = {(uint64_t)I, (uint64_t)IW, (uint64_t)IH, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)x_pixel_stride * esz, (uint64_t)IW * x_pixel_stride * esz,
+                       (uint64_t)IH * IW * x_pixel_stride * esz};
+    uint32_t box[4] = {epa, (uint32_t)tw, (uint32_t)th, 1};
+    return make_tensor_map(m, dt, 4, x, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+  };
+
+  if (mode != 2) {
+    p.Mh = H; p.Mw = W; p.sy = p.sx = 1; p.py = p.px = 0;
+    p.ntaps = 9;
+    const int off = mode == 1 ? 0 : -1;   // valid conv on the padded input: taps 0..2; padding 1: taps -1..1 (TMA zero fill)
+    for (int t = 0; t < 9; ++t) { p.tap_dy[t] = t / 3 + off; p.tap_dx[t] = t % 3 + off; p.tap_slab[t] = t; }
+    TilePlan tp = pick_tile(p.Mh, p.Mw);
+    CUtensorMap mx;
+    int e = make_x_map(&mx, tp.TH, tp.TW);
+    FMI_REQUIRE(e == 0, "conv3x3: cuTensorMapEncodeTiled(x) failed (%d)", e);
+    return tf32 ? launch_gemm_class<true>(mx, mw, p, st) : launch_gemm_class<false>(mx, mw, p, st);
+  }
+  p.sy = p.sx = 2; p.Mh = H; p.Mw = W;
+  TilePlan tp = pick_tile(p.Mh, p.Mw);
+  CUtensorMap mx;
+  int e = make_x_map(&mx, tp.TH, tp.TW);
+  FMI_REQUIRE(e == 0, "conv3x3: cuTensorMapEncodeTiled(x) failed (%d)", e);
+  for (int py = 0; py < 2; ++py)
+    for (int px = 0; px < 2; ++px) {
+      // out[2m+py, 2n+px] = sum over (ky, iy) with 2*iy - 1 + ky = 2m + py:  py = 0: (1, m);  py = 1: (0, m+1), (2, m)
+      p.py = py; p.px = px;
+      int nt = 0;
+      for (int a = 0; a < (py ? 2 : 1); ++a)
+        for (int c = 0; c < (px ? 2 : 1); ++c) {
+          const int ky = py ? (a ? 2 : 0) : 1, kx = px ? (c ? 2 : 0) : 1;
+          p.tap_dy[nt] = ky == 0 ? 1 : 0;
+          p.tap_dx[nt] = kx == 0 ? 1 : 0;
+          p.tap_slab[nt] = ky * 3 + kx;
+          ++nt;
+        }
+      p.ntaps = nt;
+      rc = tf32 ? launch_gemm_class<true>(mx, mw, p, st) : launch_gemm_class<false>(mx, mw, p, st);
+      if (rc) return rc;
+    }
+  return FMI_OK;
+}

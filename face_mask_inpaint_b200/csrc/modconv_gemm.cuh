@@ -32,7 +32,14 @@ struct ConvGemmParams {
   int T;               // weight slabs per sample
   int sy, sx, py, px;  // output pixel = (m*sy + py, n*sx + px)
   int n_tile, k_chunks, stages, tmem_cols;
-  int act;             // 0: raw accumulator, 1: noise + bias + leaky relu
+  int act;             // 0: raw accumulator, 1: noise + bias + leaky relu, 2: + bias, 3: tanh(+ bias)
+  int w_shared;        // 1: one weight set [T][O][I] for the whole batch (plain convolutions, conv_blocks.cu)
+  // output addressing in elements (0 = dense NHWC [B, OH, OW, O]): a channel slice of a wider buffer and / or the interior
+  // of a padded one — the base pointer `out` is pre-offset by the caller
+  int64_t out_bstride, out_rstride;
+  int out_pstride;
+  float* nchw_out;     // optional fp32 NCHW copy of the first nchw_C output channels ([B, nchw_C, OH, OW]); `out` may be NULL
+  int nchw_C;
   const float* noise;
   int noise_batched;
   const float* noise_w;
@@ -109,6 +116,7 @@ __global__ void __launch_bounds__(kGemmThreads, 3)
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         int b, o0, m0, n0;
         decode(t, b, o0, m0, n0);
+        const int wb = p.w_shared ? 0 : b;
         for (int it = 0; it < iters; ++it, ++g) {
           const int st = g % p.stages;
           const int tap = it / p.k_chunks, kc = it % p.k_chunks;
@@ -119,12 +127,12 @@ __global__ void __launch_bounds__(kGemmThreads, 3)
             tma_load_4d(sA, &map_x, &full[st], kc * EPA, n0 - 1, m0 + tap - 1, b);
             for (int dxi = 0; dxi < 3; ++dxi)
               tma_load_2d(sA + A_HALO_BYTES + dxi * b_stage_bytes, &map_w, &full[st], kc * EPA,
-                          (b * p.T + p.halo_slab[tap][dxi]) * p.O + o0);
+                          (wb * p.T + p.halo_slab[tap][dxi]) * p.O + o0);
             continue;
           }
           mbar_arrive_expect_tx(&full[st], bytes);
           tma_load_4d(sA, &map_x, &full[st], kc * EPA, n0 + p.tap_dx[tap], m0 + p.tap_dy[tap], b + p.tap_boff[tap]);
-          tma_load_2d(sA + A_STAGE_BYTES, &map_w, &full[st], kc * EPA, (b * p.T + p.tap_slab[tap]) * p.O + o0);
+          tma_load_2d(sA + A_STAGE_BYTES, &map_w, &full[st], kc * EPA, (wb * p.T + p.tap_slab[tap]) * p.O + o0);
         }
       }
     }
@@ -192,11 +200,11 @@ __global__ void __launch_bounds__(kGemmThreads, 3)
       const bool valid = r < p.TH * p.TW && m < p.Mh && n < p.Mw;
       const int oy = m * p.sy + p.py, ox = n * p.sx + p.px;
       float nz = 0.f;
-      if (p.act && valid && p.noise) {
+      if (p.act == 1 && valid && p.noise) {
         const float nw = p.noise_w ? *p.noise_w : 1.f;
         nz = nw * p.noise[(int64_t)(p.noise_batched ? b : 0) * p.OH * p.OW + (int64_t)oy * p.OW + ox];
       }
-      OT* out = (OT*)p.out + (((int64_t)b * p.OH + oy) * p.OW + ox) * p.O + o0;
+      OT* out = (OT*)p.out + (int64_t)b * p.out_bstride + (int64_t)oy * p.out_rstride + (int64_t)ox * p.out_pstride + o0;
       // fused ToRGB (model.py:360-369): the 1x1 modulated conv to 3 channels reads exactly the activations this thread
       // holds, so it is 3 dot products in the epilogue instead of a kernel that re-reads the whole layer output from HBM
       if (p.rgb_out && (b != cur_b || o0 != cur_o0)) {
@@ -224,12 +232,25 @@ __global__ void __launch_bounds__(kGemmThreads, 3)
         float f[32];
 #pragma unroll
         for (int k = 0; k < 32; ++k) f[k] = __uint_as_float(v[k]);
-        if (p.act) {
+        if (p.act == 1) {
 #pragma unroll
           for (int k = 0; k < 32; ++k) {
             float tt = f[k] + nz + (p.bias ? __ldg(p.bias + o0 + c0 + k) : 0.f);
             f[k] = (tt > 0.f ? tt : tt * p.slope) * p.gain;
           }
+        } else if (p.act >= 2) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            const float tt = f[k] + (p.bias ? __ldg(p.bias + o0 + c0 + k) : 0.f);
+            f[k] = p.act == 3 ? tanhf(tt) : tt;
+          }
+        }
+        if (p.nchw_out) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k)
+            if (o0 + c0 + k < p.nchw_C)
+              p.nchw_out[(((int64_t)b * p.nchw_C + o0 + c0 + k) * p.OH + oy) * p.OW + ox] = f[k];
+          if (!p.out) continue;
         }
         if (p.rgb_out) {
 #pragma unroll
@@ -342,6 +363,11 @@ int launch_gemm_class(const CUtensorMap& mx, const CUtensorMap& mw, ConvGemmPara
   const int64_t total = (int64_t)p.tiles_per_img * p.n_otiles * p.B;
   FMI_REQUIRE(total < (1ll << 31), "modconv_gemm: too many tiles");
   p.total_tiles = (int)total;
+  if (p.out_pstride == 0) {
+    p.out_pstride = p.O;
+    p.out_rstride = (int64_t)p.OW * p.O;
+    p.out_bstride = (int64_t)p.OH * p.OW * p.O;
+  }
   int grid = (int)imin64(total, (int64_t)FMI_NUM_SMS * ctas_per_sm);
   {  // debug: FMI_MODCONV_ONE_TILE=1 launches one CTA per tile (no tile loop) — must be bit-identical to the persistent run
     static const bool one_tile = [] { const char* e = getenv("FMI_MODCONV_ONE_TILE"); return e && e[0] == '1'; }();

@@ -7,8 +7,9 @@ with the SAME attribute / parameter names and shapes, so a reference checkpoint 
 What runs where:
   * `ExampleGuidedAttention` at 32^2 and `Auto_Attn` at 128^2 (58 % of the generator FLOPs), mask scaling and
     compositing: the sm_100a kernels of this package;
-  * the spectral-normalised conv / conv-transpose blocks: PyTorch + cuDNN exactly as in the reference (they are the
-    next row of the scope table, not yet kernels here).
+  * the decoder's spectral-normalised conv / conv-transpose blocks and its Output block: the implicit-GEMM
+    kernels of csrc/conv_blocks.cu when autograd is off (picnet_fast.py); under autograd (training) and in the two encoders
+    they are PyTorch + cuDNN exactly as in the reference.
 
 Blocks are assembled from two small helpers instead of one class per variant: `_sn` wraps a conv in SpectralNorm
 (external_function.py:16-72, one power iteration per forward, also in eval) and `_ResidualPair` is "main path + shortcut"
@@ -24,6 +25,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from .. import ops
+from . import picnet_fast
 from .attention import Auto_Attn, ExampleGuidedAttention
 from .picnet_blocks import SpectralNorm
 
@@ -226,6 +228,8 @@ class ResGenerator(nn.Module):
             for i in range(self.L):
                 f = getattr(self, f'generator{i}')(f)
             out = encoded + f
+        if picnet_fast.supported(self, out):   # inference: the conv blocks on the implicit-GEMM kernels (csrc/conv_blocks.cu)
+            return picnet_fast.decoder_forward(self, out, f_e, mask)
         output = None
         for i in range(self.layers):
             out = getattr(self, f'decoder{i}')(out)
@@ -240,8 +244,10 @@ class ResGenerator(nn.Module):
         """network.py:270-293: reparameterised samples of the prior (source) and posterior (reference)."""
         p_mu, p_sigma = ref_distribution
         q_mu, q_sigma = src_distribution
-        z_p = torch.distributions.Normal(p_mu, p_sigma).rsample()
-        z_q = torch.distributions.Normal(q_mu, q_sigma).rsample()
+        # argument validation reads a flag back to the host: kept in eager mode, skipped while a CUDA graph is capturing
+        check = not (p_mu.is_cuda and torch.cuda.is_current_stream_capturing())
+        z_p = torch.distributions.Normal(p_mu, p_sigma, validate_args=check).rsample()
+        z_q = torch.distributions.Normal(q_mu, q_sigma, validate_args=check).rsample()
         return z_q if return_zq else torch.cat([z_q, z_p], dim=1)
 
 

@@ -17,7 +17,9 @@ def _l2normalize(v, eps=1e-12):
 
 
 class SpectralNorm(nn.Module):
-    """external_function.py:16-72 — one power iteration per forward (u, v mutate even in eval, as upstream)."""
+    """external_function.py:16-72 — one power iteration per forward (u, v mutate even in eval, as upstream).
+    u and v are updated IN PLACE (the reference re-binds `.data`; same values) so that a CUDA-graph replay of the forward
+    keeps advancing them (graphs.py)."""
 
     def __init__(self, module, name='weight', power_iterations=1):
         super().__init__()
@@ -41,8 +43,8 @@ class SpectralNorm(nn.Module):
         w = getattr(self.module, self.name + "_bar")
         height = w.data.shape[0]
         for _ in range(self.power_iterations):
-            v.data = _l2normalize(torch.mv(torch.t(w.view(height, -1).data), u.data))
-            u.data = _l2normalize(torch.mv(w.view(height, -1).data, v.data))
+            v.data.copy_(_l2normalize(torch.mv(torch.t(w.view(height, -1).data), u.data)))
+            u.data.copy_(_l2normalize(torch.mv(w.view(height, -1).data, v.data)))
         sigma = u.dot(w.view(height, -1).mv(v))
         setattr(self.module, self.name, w / sigma.expand_as(w))
 

@@ -1,0 +1,231 @@
+"""Inference path of the PICNet decoder conv blocks on the sm_100a kernels (csrc/conv_blocks.cu).
+
+`ResGenerator.forward` (modules/pluralistic_model/network.py:247-268) runs, per ResBlockDecoder
+(base_function.py:308-366):  IN -> LeakyReLU -> Conv2d(3,1,1) -> IN -> LeakyReLU -> ConvTranspose2d(3,2,1,1), plus a
+ConvTranspose2d(3,2,1,1) shortcut of the block input, every conv wrapped in SpectralNorm; then Auto_Attn after block 1
+and Output (LeakyReLU -> ReflectionPad2d(1) -> Conv2d(3) -> Tanh, :369-398) after the last block. Here the activations stay
+NHWC in the tensor-core operand type from the first block to the image, each block is 2 statistics passes, 2
+normalise+activate passes and 5 implicit-GEMM launches (conv, then the 4 output-parity classes of the transposed conv with
+main path and shortcut concatenated along the input channels so that their sum is the accumulator), and every GEMM writes
+straight into the buffer the next consumer reads (channel slice of the next block's [a2 | x] buffer, or the interior of the
+reflection-padded buffer of the Output conv).
+
+Used when autograd is off, the tensors are CUDA and TF32 convolutions are allowed (torch.backends.cudnn.allow_tf32, PyTorch's
+default — i.e. whenever the reference itself would run these convolutions with TF32 operands) or FMI_PRECISION=bf16; training
+differentiates the cuDNN formulation of the same blocks (picnet.py), whose backward is not a kernel of this package yet.
+SpectralNorm (external_function.py:44-57) keeps its one power iteration per forward: `_update_u_v()` of the mirror is called
+as in the eager path and the resulting `w_bar / sigma` is what the weight-prep kernel re-lays out.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+from torch import nn
+
+from .. import _lib, ops
+from .picnet_blocks import SpectralNorm
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _effective(conv):
+    """(weight fp32 contiguous, bias) of a conv that may be wrapped in SpectralNorm (advances u/v like a forward would)."""
+    if isinstance(conv, SpectralNorm):
+        conv._update_u_v()
+        conv = conv.module
+    w = conv.weight
+    b = conv.bias
+    return w.detach().float().contiguous(), (None if b is None else b.detach().float().contiguous())
+
+
+def _plain(conv):
+    return conv.module if isinstance(conv, SpectralNorm) else conv
+
+
+def _slope(act):
+    if isinstance(act, nn.LeakyReLU):
+        return float(act.negative_slope)
+    if isinstance(act, nn.ReLU):
+        return 0.0
+    return None
+
+
+def _block_layout(blk):
+    """(norm1, act, norm2) of a ResBlockDecoder's `model` Sequential, or None if it is not IN/none + (Leaky)ReLU."""
+    mods = list(blk.model)
+    if len(mods) == 6:
+        n1, a1, _, n2, a2, _ = mods
+    elif len(mods) == 4:
+        n1 = n2 = None
+        a1, _, a2, _ = mods
+    else:
+        return None
+    for n in (n1, n2):
+        if n is not None and not (isinstance(n, nn.InstanceNorm2d) and not n.track_running_stats):
+            return None
+    if _slope(a1) is None or _slope(a2) is None:
+        return None
+    return n1, a1, n2
+
+
+def supported(gen, x) -> bool:
+    """True when `ResGenerator.forward` can take the kernel path for this call."""
+    if os.environ.get("FMI_PICNET_CUDNN") == "1" or torch.is_grad_enabled() or not x.is_cuda or x.dtype != torch.float32:
+        return False
+    # Operand precision follows the switch that governs the reference's own GPU numerics for these convolutions: with
+    # torch.backends.cudnn.allow_tf32 (PyTorch's default) cuDNN runs them with TF32 operands, and so do the kernels here
+    # (measured on the README configuration, image vs strict fp32: cuDNN-TF32 1.4e-2, these kernels 1.0e-2). With TF32
+    # switched off the caller asked for strict fp32 convolutions: those stay on cuDNN.
+    if not torch.backends.cudnn.allow_tf32 and ops.mma_mode(torch.float32) != _lib.MMA_BF16:
+        return False
+    cached = getattr(gen, "_fmi_fast_ok", None)
+    if cached is None:
+        ok = True
+        for i in range(gen.layers):
+            blk = getattr(gen, f"decoder{i}")
+            ok = ok and _block_layout(blk) is not None
+            c1, c2, bp = _plain(blk.conv1), _plain(blk.conv2), _plain(blk.bypass)
+            ok = ok and isinstance(c1, nn.Conv2d) and isinstance(c2, nn.ConvTranspose2d) and isinstance(bp, nn.ConvTranspose2d)
+            if ok:
+                cin, ch, co = c1.in_channels, c1.out_channels, c2.out_channels
+                ok = cin % 32 == 0 and ch % 32 == 0 and co % 32 == 0 and max(cin, ch) <= 1024 and (co <= 256 or co % 256 == 0) \
+                    and (ch <= 256 or ch % 256 == 0)
+        out = getattr(gen, f"out{gen.layers - 1}", None)
+        if out is None or len(list(out.model)) != 4 or _slope(out.model[0]) is None or _plain(out.conv1).out_channels > 32:
+            ok = False
+        for i in range(gen.layers - 1):
+            if hasattr(gen, f"out{i}"):
+                ok = False
+        if gen.use_attn and gen.layers < 3:   # attention after block 1 must not be the last block
+            ok = False
+        gen._fmi_fast_ok = cached = ok
+    return cached
+
+
+class _Ctx:
+    def __init__(self, dev):
+        self.lib = _lib.load()
+        self.mma = ops.mma_mode(torch.float32)
+        self.dt = torch.float32 if self.mma == _lib.MMA_TF32 else torch.bfloat16
+        self.dev = dev
+        self.st = ops._stream()
+
+    def empty(self, *shape):
+        return torch.empty(shape, dtype=self.dt, device=self.dev)
+
+    def weights(self, parts, o_rows):
+        """parts: [(weight, transposed)] concatenated along the input channels -> wp [9][o_rows][sum I]."""
+        itot = sum((w.shape[0] if tr else w.shape[1]) for w, tr in parts)
+        o_real = parts[0][0].shape[1] if parts[0][1] else parts[0][0].shape[0]
+        wp = (torch.zeros if o_rows != o_real else torch.empty)((9, o_rows, itot), dtype=self.dt, device=self.dev)
+        off = 0
+        for w, tr in parts:
+            i = w.shape[0] if tr else w.shape[1]
+            _lib.check(self.lib.fmi_conv_weight_prep(_p(w), _p(wp), o_real, i, int(tr), o_rows, itot, off, self.mma, self.st),
+                       "fmi_conv_weight_prep")
+            off += i
+        return wp
+
+    def norm_act(self, x, x_stride, y, y_stride, norm, b, c, hw, slope):
+        ss = None
+        if norm is not None:
+            ss = torch.empty((b, c, 2), dtype=torch.float32, device=self.dev)
+            sums = torch.empty((b, c, 2), dtype=torch.float64, device=self.dev)
+            g = None if norm.weight is None else norm.weight.detach().float().contiguous()
+            be = None if norm.bias is None else norm.bias.detach().float().contiguous()
+            _lib.check(self.lib.fmi_instnorm_stats_nhwc(x, x_stride, _p(g), _p(be), _p(ss), _p(sums), b, c, hw, float(norm.eps),
+                                                        self.mma, self.st), "fmi_instnorm_stats_nhwc")
+        _lib.check(self.lib.fmi_norm_act_nhwc(x, x_stride, y, y_stride, _p(ss), b, c, hw, slope, self.mma, self.st),
+                   "fmi_norm_act_nhwc")
+        return ss
+
+    def conv(self, x, x_stride, wp, bias, y, y_stride, y_pad, y_nchw, nchw_c, b, i, o, h, w, mode, act, slope=0.0):
+        _lib.check(self.lib.fmi_conv3x3_nhwc(x, x_stride, _p(wp), _p(bias), y, y_stride, y_pad, _p(y_nchw), nchw_c, b, i, o, h, w,
+                                             mode, act, slope, self.mma, self.st), "fmi_conv3x3_nhwc")
+
+
+def decoder_forward(gen, x, f_e=None, mask=None, taps=None):
+    """The decoder loop of ResGenerator.forward (network.py:256-268) for `x` = encoded (+ f) [B, C, H, W] fp32 NCHW.
+    Returns the image [B, 3, H * 2^layers, W * 2^layers] fp32. `taps` (diagnostics, tests/diag_picnet_blocks.py): a dict that
+    receives an fp32 NCHW copy of every block output."""
+    k = _Ctx(x.device)
+    esz = 4 if k.mma == _lib.MMA_TF32 else 2
+    b, c_in, h, w = x.shape
+    x = x.contiguous()
+    blocks = [getattr(gen, f"decoder{i}") for i in range(gen.layers)]
+    ch0 = _plain(blocks[0].conv1).out_channels
+    cat = k.empty(b, h, w, ch0 + c_in)            # [a2 | x] of the first block
+    _lib.check(k.lib.fmi_nchw_to_nhwc_slice(_p(x), cat.data_ptr() + ch0 * esz, b, c_in, h, w, ch0 + c_in, _lib.F32, k.mma, k.st),
+               "fmi_nchw_to_nhwc_slice")
+    image = None
+    for i, blk in enumerate(blocks):
+        n1, act, n2 = _block_layout(blk)
+        slope = _slope(act)
+        w1, b1 = _effective(blk.conv1)
+        w2, b2 = _effective(blk.conv2)
+        ws, bs = _effective(blk.bypass)
+        ch, co = w1.shape[0], w2.shape[1]
+        if w1.shape[1] != c_in or ws.shape[0] != c_in:
+            raise RuntimeError("fmi_b200: decoder block channel mismatch")
+        ctot, hw = ch + c_in, h * w
+        x_ptr = cat.data_ptr() + ch * esz
+        # a1 = lrelu(IN(x)); h1 = conv1(a1) + b1
+        a1 = k.empty(b, h, w, c_in)
+        k.norm_act(x_ptr, ctot, a1.data_ptr(), c_in, n1, b, c_in, hw, slope)
+        h1 = k.empty(b, h, w, ch)
+        k.conv(a1.data_ptr(), c_in, k.weights([(w1, False)], ch), b1, h1.data_ptr(), ch, 0, None, 0, b, c_in, ch, h, w, 0, 2)
+        del a1
+        # a2 = lrelu(IN(h1)) into channels [0, ch) next to x
+        k.norm_act(h1.data_ptr(), ch, cat.data_ptr(), ctot, n2, b, ch, hw, slope)
+        del h1
+        # y = convT(a2) + b2 + convT_shortcut(x) + bs: one GEMM over [a2 | x]
+        bias = b2 if bs is None else (bs if b2 is None else b2 + bs)
+        wcat = k.weights([(w2, True), (ws, True)], co)
+        oh, ow = 2 * h, 2 * w
+        last = i == gen.layers - 1
+        attn = getattr(gen, f"attn{i}", None) if (i == 1 and gen.use_attn) else None
+        if last:
+            out_blk = getattr(gen, f"out{i}")
+            o_slope = _slope(out_blk.model[0])
+            padded = k.empty(b, oh + 2, ow + 2, co)
+            # Output's activation fused into the epilogue (the raw block output has no other reader: network.py:266-268)
+            k.conv(cat.data_ptr(), ctot, wcat, bias, padded.data_ptr(), co, 1, None, 0, b, ctot, co, h, w, 2, 1, o_slope)
+            _lib.check(k.lib.fmi_reflect_border_nhwc(padded.data_ptr(), b, co, oh, ow, k.mma, k.st), "fmi_reflect_border_nhwc")
+            if taps is not None:
+                taps[f"decoder{i}:lrelu"] = padded[:, 1:-1, 1:-1].float().permute(0, 3, 1, 2).contiguous()
+            wo, bo = _effective(out_blk.conv1)
+            n_img = wo.shape[0]
+            bo_pad = None
+            if bo is not None:
+                bo_pad = torch.zeros(32, dtype=torch.float32, device=x.device)
+                bo_pad[:n_img] = bo
+            image = torch.empty((b, n_img, oh, ow), dtype=torch.float32, device=x.device)
+            k.conv(padded.data_ptr(), co, k.weights([(wo, False)], 32), bo_pad, None, 32, 0, image, n_img, b, co, 32, oh, ow, 1, 3)
+        elif attn is not None:
+            y = k.empty(b, oh, ow, co)
+            k.conv(cat.data_ptr(), ctot, wcat, bias, y.data_ptr(), co, 0, None, 0, b, ctot, co, h, w, 2, 2)
+            y_nchw = torch.empty((b, co, oh, ow), dtype=torch.float32, device=x.device)
+            _lib.check(k.lib.fmi_nhwc_to_nchw(y.data_ptr(), _p(y_nchw), b, co, oh, ow, k.mma, _lib.F32, k.st), "fmi_nhwc_to_nchw")
+            del y
+            y_nchw, _ = attn(y_nchw, f_e, mask)
+            y_nchw = y_nchw.contiguous()
+            ch_next = _plain(blocks[i + 1].conv1).out_channels
+            nxt = k.empty(b, oh, ow, ch_next + co)
+            _lib.check(k.lib.fmi_nchw_to_nhwc_slice(_p(y_nchw), nxt.data_ptr() + ch_next * esz, b, co, oh, ow, ch_next + co,
+                                                    _lib.F32, k.mma, k.st), "fmi_nchw_to_nhwc_slice")
+            cat = nxt
+            if taps is not None:
+                taps[f"decoder{i}+attn"] = y_nchw
+        else:
+            ch_next = _plain(blocks[i + 1].conv1).out_channels
+            nxt = k.empty(b, oh, ow, ch_next + co)
+            k.conv(cat.data_ptr(), ctot, wcat, bias, nxt.data_ptr() + ch_next * esz, ch_next + co, 0, None, 0, b, ctot, co, h, w,
+                   2, 2)
+            cat = nxt
+            if taps is not None:
+                taps[f"decoder{i}"] = nxt[..., ch_next:].float().permute(0, 3, 1, 2).contiguous()
+        c_in, h, w = co, oh, ow
+    return image

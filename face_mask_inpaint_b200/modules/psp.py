@@ -198,7 +198,9 @@ class pSp(nn.Module):
         else:
             codes = self.encoder(x, ref=ref, mask=src_mask)  # [N, n_styles, 512]
             if self.opts.start_from_latent_avg and self.latent_avg is not None:
-                avg = self.latent_avg.to(codes.device)
+                if self.latent_avg.device != codes.device:   # moved once and kept: no host copy on later calls (graph capture)
+                    self.latent_avg = self.latent_avg.to(codes.device)
+                avg = self.latent_avg
                 codes = codes + (avg.repeat(codes.shape[0], 1) if self.opts.learn_in_w else avg.repeat(codes.shape[0], 1, 1))
         if latent_mask is not None:
             for i in latent_mask:

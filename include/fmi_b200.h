@@ -237,6 +237,48 @@ int fmi_styled_conv_bwd_nhwc(const void* x, const void* y, const void* dy, const
 int fmi_torgb_bwd_nhwc(const void* x, const float* drgb, const float* rgb_w, void* dx, float* d_rgbw, float* dbias,
                        int B, int I, int H, int W, int mma, void* stream);
 
+/* ---- f1: PICNet decoder conv blocks, inference ------------------------------------------------------
+ * Replaces the cuDNN calls behind ResBlockDecoder.forward / Output.forward (modules/pluralistic_model/base_function.py:
+ * 308-398) as assembled by ResGenerator.forward (network.py:247-268): nn.Conv2d(3,1,1), nn.ConvTranspose2d(3,2,1,1),
+ * nn.InstanceNorm2d(affine=True), LeakyReLU, ReflectionPad2d(1), Tanh. Activations are NHWC in the tensor-core operand
+ * type (mma = FMI_MMA_TF32: tf32-rounded fp32, FMI_MMA_BF16: bf16); "pixel stride" = elements between consecutive
+ * pixels, so a tensor may be a channel slice of a wider buffer. */
+
+/* wp[t][o][i_off + i] = weight[o,i,t] (Conv2d layout [O,I,3,3], transposed = 0) or weight[i,o,t] (ConvTranspose2d
+ *   layout [I,O,3,3], transposed = 1) in the operand type; wp is [9][O_rows][I_row], rows / columns not written stay as
+ *   the caller initialised them (zero). Writing two weights at different i_off concatenates them along the input
+ *   channels. weight is the effective fp32 weight (SpectralNorm already applied: w_bar / sigma, external_function.py:55-57). */
+int fmi_conv_weight_prep(const float* weight, void* wp, int O, int I, int transposed, int O_rows, int I_row, int i_off,
+                         int mma, void* stream);
+
+/* NCHW (dtype) -> NHWC operand type into a channel slice: y[b, p, c] at y + (b*H*W + p) * y_pixel_stride + c. */
+int fmi_nchw_to_nhwc_slice(const void* x, void* y, int B, int C, int H, int W, int64_t y_pixel_stride, int dtype, int mma,
+                           void* stream);
+
+/* InstanceNorm2d statistics (biased variance over H*W per sample and channel, F.instance_norm) folded with the affine
+ *   parameters: scale_shift[b][c] = (gamma[c]*rstd, beta[c] - mean*gamma[c]*rstd). sums: B*C*2 doubles of scratch. */
+int fmi_instnorm_stats_nhwc(const void* x, int64_t x_pixel_stride, const float* gamma, const float* beta,
+                            float* scale_shift, double* sums, int B, int C, int HW, float eps, int mma, void* stream);
+
+/* y = leaky_relu(x * scale + shift, slope) per (sample, channel); scale_shift = NULL: activation only. */
+int fmi_norm_act_nhwc(const void* x, int64_t x_pixel_stride, void* y, int64_t y_pixel_stride, const float* scale_shift,
+                      int B, int C, int HW, float slope, int mma, void* stream);
+
+/* ReflectionPad2d(1): fills the one-pixel border of y [B,H+2,W+2,C] from its interior. */
+int fmi_reflect_border_nhwc(void* y, int B, int C, int H, int W, int mma, void* stream);
+
+/* 3x3 convolution with batch-shared weights as a tcgen05 implicit GEMM.
+ *   mode 0: Conv2d(3, stride 1, padding 1)                              x [B,H,W,*]      -> y [B,H,W,*]
+ *   mode 1: Conv2d(3, stride 1, padding 0) on a pre-padded input        x [B,H+2,W+2,*]  -> y [B,H,W,*]
+ *   mode 2: ConvTranspose2d(3, stride 2, padding 1, output_padding 1)   x [B,H,W,*]      -> y [B,2H,2W,*]
+ *   wp [9][O][I] from fmi_conv_weight_prep (O a multiple of 32: pad with zero rows); bias [O] fp32 or NULL;
+ *   act 2: y = acc + bias;  act 1: leaky_relu(acc + bias, slope);  act 3: tanh(acc + bias).
+ *   y (may be NULL if y_nchw is given): NHWC operand type, pixel stride y_pixel_stride, written to the interior of a
+ *   buffer padded by y_pad (0 or 1) pixels per side. y_nchw (or NULL): fp32 [B, nchw_C, OH, OW], the first nchw_C channels. */
+int fmi_conv3x3_nhwc(const void* x, int64_t x_pixel_stride, const void* wp, const float* bias, void* y,
+                     int64_t y_pixel_stride, int y_pad, float* y_nchw, int nchw_C, int B, int I, int O, int H, int W,
+                     int mode, int act, float slope, int mma, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

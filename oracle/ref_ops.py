@@ -273,6 +273,44 @@ def generator_synthesis(sd: dict, latent: torch.Tensor, noises: Optional[Sequenc
 
 
 # --------------------------------------------------------------------------------------------
+# f1  PICNet decoder conv blocks
+# --------------------------------------------------------------------------------------------
+def spectral_norm_weight(w_bar: torch.Tensor, u: torch.Tensor, v: torch.Tensor, power_iterations: int = 1):
+    """SpectralNorm._update_u_v (modules/pluralistic_model/external_function.py:44-57): one power iteration, then
+    w = w_bar / sigma. Returns (w, u', v'); the reference stores u', v' back into the module."""
+    height = w_bar.shape[0]
+    wm = w_bar.reshape(height, -1)
+    for _ in range(power_iterations):
+        v = torch.mv(wm.t(), u)
+        v = v / (v.norm() + 1e-12)                     # l2normalize, :11-12
+        u = torch.mv(wm, v)
+        u = u / (u.norm() + 1e-12)
+    sigma = u.dot(wm.mv(v))
+    return w_bar / sigma, u, v
+
+
+def res_block_decoder(x, conv1_w, conv1_b, conv2_w, conv2_b, bypass_w, bypass_b, norm1=None, norm2=None, slope=0.1):
+    """ResBlockDecoder.forward (base_function.py:308-366) given the EFFECTIVE conv weights (after SpectralNorm):
+    [IN] lrelu conv3x3 [IN] lrelu convT3x3(s2,p1,op1)  +  convT3x3(s2,p1,op1) shortcut. norm1 / norm2 = (gamma, beta) of
+    nn.InstanceNorm2d(affine=True) (eps 1e-5, instance statistics also in eval) or None."""
+    up = dict(stride=2, padding=1, output_padding=1)
+    h = x
+    if norm1 is not None:
+        h = F.instance_norm(h, weight=norm1[0], bias=norm1[1], eps=1e-5)
+    h = F.conv2d(F.leaky_relu(h, slope), conv1_w, conv1_b, padding=1)
+    if norm2 is not None:
+        h = F.instance_norm(h, weight=norm2[0], bias=norm2[1], eps=1e-5)
+    h = F.conv_transpose2d(F.leaky_relu(h, slope), conv2_w, conv2_b, **up)
+    return h + F.conv_transpose2d(x, bypass_w, bypass_b, **up)
+
+
+def output_block(x, conv_w, conv_b, slope=0.1):
+    """Output.forward with norm_layer=None (base_function.py:369-398): lrelu, ReflectionPad2d(1), conv3x3, tanh."""
+    h = F.pad(F.leaky_relu(x, slope), (1, 1, 1, 1), mode='reflect')
+    return torch.tanh(F.conv2d(h, conv_w, conv_b))
+
+
+# --------------------------------------------------------------------------------------------
 # bounded samples of the attention workload for the CPU baseline legs of bench.py
 # --------------------------------------------------------------------------------------------
 def example_guided_attention_rows(src_mask, src_feature, ref_feature, conv_weight, rows: torch.Tensor):

@@ -228,6 +228,33 @@ def gen_picnet():
                         keys=np.array(keys), n_params=np.array(sum(p.numel() for p in model.parameters())))
 
 
+def gen_picnet_blocks():
+    """the reference's own ResBlockDecoder and Output (modules/pluralistic_model/base_function.py:308-398)
+    with SpectralNorm, InstanceNorm2d(affine) and LeakyReLU(0.1) exactly as ResGenerator builds them (network.py:225-241),
+    parameters filled by name, one eval forward on a seeded non-square input. Stored: input, every parameter (w_bar, u, v,
+    biases, norm scales) BEFORE the forward, the block output, and Output applied to it."""
+    import functools
+    from golden_util import fill_by_name
+    from modules.pluralistic_model import base_function as BF
+    norm = functools.partial(nn.InstanceNorm2d, affine=True)
+    act = nn.LeakyReLU(0.1)
+    torch.manual_seed(0)
+    blk = fill_by_name(BF.ResBlockDecoder(64, 32, 32, norm, act, True, False).eval(), seed=3)
+    out = fill_by_name(BF.Output(32, 3, 3, None, act, True, False).eval(), seed=4)
+    d = {}
+    for tag, m in (("blk", blk), ("out", out)):
+        for k, v in m.state_dict().items():   # convs are registered twice (conv1 and model.2, ...): keep the first name
+            if ".module." in k and (k.startswith("model.") or k.startswith("shortcut.")):
+                continue
+            d[f"{tag}.{k}"] = np_(v.clone())
+    x = torch.randn(2, 64, 12, 20, generator=torch.Generator().manual_seed(21))
+    with torch.no_grad():
+        y = blk(x)
+        img = out(y)
+    d.update(x=np_(x), y=np_(y), img=np_(img))
+    np.savez_compressed(OUT / "picnet_blocks.npz", **d)
+
+
 def gen_refpsp(size=256):
     """BASELINE config 3 (reduced output size for the fixture): the reference's pSp (modules/psp/psp.py) with
     GradualStyleEncoder(50, 'ir_se') + attention and its StyleGAN2 decoder, `load_weights` bypassed (no pretrained files
@@ -254,9 +281,11 @@ def gen_refpsp(size=256):
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    if len(sys.argv) > 1 and sys.argv[1] in ("picnet", "refpsp"):
+    if len(sys.argv) > 1 and sys.argv[1] in ("picnet", "refpsp", "picnet_blocks"):
         if sys.argv[1] == "picnet":
             gen_picnet()
+        elif sys.argv[1] == "picnet_blocks":
+            gen_picnet_blocks()
         else:
             gen_refpsp()
         for f in sorted(OUT.glob("*.npz")):
@@ -266,6 +295,7 @@ if __name__ == "__main__":
     gen_upfirdn2d_and_composite()
     gen_stylegan2()
     gen_picnet()
+    gen_picnet_blocks()
     gen_refpsp()
     for f in sorted(OUT.glob("*.npz")):
         print(f.name, f.stat().st_size)

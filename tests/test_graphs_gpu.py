@@ -1,0 +1,72 @@
+"""CUDA-graph replay of the whole-model forwards (face_mask_inpaint_b200/graphs.py) equals the eager forward: same kernels,
+same order, bit-identical where no atomics are involved. SpectralNorm's u/v advance by one power iteration per call in both
+(external_function.py:44-57), so call k of the eager model is compared with call k of the captured one."""
+import copy
+import types
+
+import pytest
+import torch
+
+from conftest import rel_err
+from golden_util import fill_by_name, mean_z, picnet_inputs, refpsp_inputs
+
+pytestmark = pytest.mark.gpu
+
+
+def _picnet():
+    from face_mask_inpaint_b200.modules.picnet import build_picnet_ref
+    m = fill_by_name(build_picnet_ref()).eval()
+    m.decoder.get_z = types.MethodType(mean_z, m.decoder)
+    return m
+
+
+def test_picnet_graph_replay_matches_eager():
+    from face_mask_inpaint_b200.graphs import CapturedForward
+    base = _picnet()
+    eager, graphed = copy.deepcopy(base).cuda(), copy.deepcopy(base).cuda()
+    eager.decoder.get_z = types.MethodType(mean_z, eager.decoder)
+    graphed.decoder.get_z = types.MethodType(mean_z, graphed.decoder)
+    src, ref, mask = (t.cuda() for t in picnet_inputs(2))
+    src2, ref2, mask2 = (t.cuda() for t in picnet_inputs(2, seed=8))
+    fwd = CapturedForward(graphed, src, ref, mask, warmup=3)     # 3 eager calls inside; capture itself runs nothing
+    with torch.no_grad():
+        for _ in range(3):
+            eager(src, ref, mask)
+        want1 = eager(src, ref, mask)
+        want2 = eager(src2, ref2, mask2)
+    got1 = fwd(src, ref, mask).clone()
+    got2 = fwd(src2, ref2, mask2).clone()
+    assert got1.shape == want1.shape == (2, 3, 256, 256)
+    assert rel_err(got1, want1) <= 1e-5, rel_err(got1, want1)
+    assert rel_err(got2, want2) <= 1e-5, rel_err(got2, want2)
+    assert rel_err(got1, got2) > 1e-3          # the replay really consumed the new inputs
+    u_e = eager.decoder.decoder0.conv1.module.weight_u
+    u_g = graphed.decoder.decoder0.conv1.module.weight_u
+    assert rel_err(u_g, u_e) <= 1e-5           # power-iteration state advanced under replay as in eager mode
+
+
+def test_picnet_graph_rejects_other_shapes():
+    from face_mask_inpaint_b200.graphs import CapturedForward
+    m = _picnet().cuda()
+    src, ref, mask = (t.cuda() for t in picnet_inputs(1))
+    fwd = CapturedForward(m, src, ref, mask, warmup=1)
+    with pytest.raises(RuntimeError):
+        fwd(*(t.cuda() for t in picnet_inputs(2)))
+    with pytest.raises(RuntimeError):
+        CapturedForward(m, src.cpu(), ref.cpu(), mask.cpu())
+
+
+def test_refpsp_graph_replay_matches_eager():
+    from face_mask_inpaint_b200.graphs import CapturedForward
+    from face_mask_inpaint_b200.modules.psp import pSp, refpsp_opts
+    net = fill_by_name(pSp(refpsp_opts(output_size=256))).eval().cuda()
+    x, ref, mask = (t.cuda() for t in refpsp_inputs(2))
+    x2, ref2, mask2 = (t.cuda() for t in refpsp_inputs(2, seed=12))
+    fwd = CapturedForward(net, x, ref=ref, src_mask=mask, resize=True, randomize_noise=False)
+    with torch.no_grad():
+        want1 = net(x, ref=ref, src_mask=mask, resize=True, randomize_noise=False)
+        want2 = net(x2, ref=ref2, src_mask=mask2, resize=True, randomize_noise=False)
+    got1 = fwd(x, ref=ref, src_mask=mask).clone()
+    got2 = fwd(x2, ref=ref2, src_mask=mask2).clone()
+    assert rel_err(got1, want1) <= 1e-5, rel_err(got1, want1)
+    assert rel_err(got2, want2) <= 1e-5, rel_err(got2, want2)

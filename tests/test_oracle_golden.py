@@ -115,3 +115,23 @@ def test_fused_bias_act_semantics():
     assert torch.allclose(O.fused_bias_act(x, b, None, 1, 0, 0.2, 2.0), (x + b) * 2)
     gi, gb = O.fused_leaky_relu_backward(torch.ones(2, 2, 1, 1), torch.tensor([[[[1.0]], [[-1.0]]], [[[-1.0]], [[1.0]]]]))
     assert torch.allclose(gb, torch.tensor([1.2 * 2 ** 0.5, 1.2 * 2 ** 0.5]))
+
+
+def _sn(g, prefix):
+    w, _, _ = O.spectral_norm_weight(g[f"{prefix}.module.weight_bar"], g[f"{prefix}.module.weight_u"],
+                                     g[f"{prefix}.module.weight_v"])
+    return w, g[f"{prefix}.module.bias"]
+
+
+def test_picnet_decoder_blocks_match_reference():
+    """f1: SpectralNorm + ResBlockDecoder + Output restatements against the reference's own classes
+    (base_function.py:308-398, external_function.py:44-57)."""
+    g = load("picnet_blocks.npz")
+    w1, b1 = _sn(g, "blk.conv1")
+    w2, b2 = _sn(g, "blk.conv2")
+    ws, bs = _sn(g, "blk.bypass")
+    y = O.res_block_decoder(g["x"], w1, b1, w2, b2, ws, bs, (g["blk.model.0.weight"], g["blk.model.0.bias"]),
+                            (g["blk.model.3.weight"], g["blk.model.3.bias"]), slope=0.1)
+    assert rel_err(y, g["y"]) <= 1e-6
+    wo, bo = _sn(g, "out.conv1")
+    assert rel_err(O.output_block(y, wo, bo, slope=0.1), g["img"]) <= 1e-6
