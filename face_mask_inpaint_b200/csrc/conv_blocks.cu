@@ -24,9 +24,12 @@ using namespace fmi_conv;
 namespace {
 
 // ---- Wp[t][o][i_off + i] = OT(w[o,i,t])  (Conv2d weight [O,I,3,3])  or  OT(w[i,o,t])  (ConvTranspose2d weight [I,O,3,3]) ----
+// merged (transposed only): slab = input shift 2*dy + dx, row = (2*py + px) * O + o, where tap ky serves output parity py =
+// (ky != 1) from input row m + dy, dy = (ky == 0)  (out[2m+py] = sum x[iy] w[ky] with 2*iy - 1 + ky = 2m + py); wp is
+// [4][4*O][I_row], rows of classes that do not use a shift stay zero.
 template <typename OT, bool ROUND_TF32>
 __global__ void __launch_bounds__(256) conv_weight_prep_kernel(const float* __restrict__ w, OT* __restrict__ wp, int O, int I,
-                                                               int transposed, int O_rows, int I_row, int i_off) {
+                                                               int transposed, int O_rows, int I_row, int i_off, int merged) {
   const int total = O * I * 9;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
     const int t = e % 9, r = e / 9;
@@ -35,7 +38,13 @@ __global__ void __launch_bounds__(256) conv_weight_prep_kernel(const float* __re
     else { o = r / I; i = r - o * I; }
     float v = w[e];
     if (ROUND_TF32) v = __uint_as_float(f32_to_tf32_rna(v));
-    wp[((int64_t)t * O_rows + o) * I_row + i_off + i] = from_f32<OT>(v);
+    int slab = t, row = o;
+    if (merged) {
+      const int ky = t / 3, kx = t - ky * 3;
+      slab = (ky == 0 ? 2 : 0) + (kx == 0 ? 1 : 0);
+      row = ((ky != 1 ? 2 : 0) + (kx != 1 ? 1 : 0)) * O + o;
+    }
+    wp[((int64_t)slab * O_rows + row) * I_row + i_off + i] = from_f32<OT>(v);
   }
 }
 
@@ -181,22 +190,23 @@ inline int stream_grid(int64_t work_items, int per_block) {
 // C ABI
 // =====================================================================================================================
 extern "C" int fmi_conv_weight_prep(const float* weight, void* wp, int O, int I, int transposed, int O_rows, int I_row,
-                                    int i_off, int mma, void* stream) {
+                                    int i_off, int merged, int mma, void* stream) {
   FMI_REQUIRE(mma == FMI_MMA_TF32 || mma == FMI_MMA_BF16, "conv_weight_prep: bad mma");
+  FMI_REQUIRE(!merged || (transposed && O_rows == 4 * O), "conv_weight_prep: merged layout is for transposed convs, O_rows = 4*O");
   FMI_REQUIRE(weight && wp && O >= 1 && I >= 1 && O_rows >= O && i_off >= 0 && I_row >= i_off + I,
               "conv_weight_prep: bad arguments (O=%d I=%d O_rows=%d I_row=%d i_off=%d)", O, I, O_rows, I_row, i_off);
   const int grid = stream_grid((int64_t)O * I * 9, 256);
   cudaStream_t st = (cudaStream_t)stream;
   if (mma == FMI_MMA_TF32)
-    conv_weight_prep_kernel<float, true><<<grid, 256, 0, st>>>(weight, (float*)wp, O, I, transposed, O_rows, I_row, i_off);
+    conv_weight_prep_kernel<float, true><<<grid, 256, 0, st>>>(weight, (float*)wp, O, I, transposed, O_rows, I_row, i_off, merged);
   else
     conv_weight_prep_kernel<__nv_bfloat16, false><<<grid, 256, 0, st>>>(weight, (__nv_bfloat16*)wp, O, I, transposed, O_rows,
-                                                                        I_row, i_off);
+                                                                        I_row, i_off, merged);
   return fmi_launched("conv_weight_prep");
 }
 
 extern "C" int fmi_nchw_to_nhwc_slice(const void* x, void* y, int B, int C, int H, int W, int64_t y_pixel_stride, int dtype,
-                                      int mma, void* stream) {
+                                      int round_y, int mma, void* stream) {
   FMI_REQUIRE(fmi_dtype_ok(dtype) && (mma == FMI_MMA_TF32 || mma == FMI_MMA_BF16), "nchw_to_nhwc_slice: bad dtype/mma");
   if (B == 0) return FMI_OK;
   FMI_REQUIRE(x && y && C >= 1 && H >= 1 && W >= 1 && y_pixel_stride >= C, "nchw_to_nhwc_slice: bad arguments");
@@ -205,8 +215,10 @@ extern "C" int fmi_nchw_to_nhwc_slice(const void* x, void* y, int B, int C, int 
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t yi = (int64_t)HW * y_pixel_stride;
   FMI_DISPATCH_DTYPE(dtype, T, {
-    if (mma == FMI_MMA_TF32)
+    if (mma == FMI_MMA_TF32 && round_y)
       nchw_to_nhwc_slice_kernel<T, float, true><<<grid, 256, 0, st>>>((const T*)x, (float*)y, C, HW, y_pixel_stride, yi);
+    else if (mma == FMI_MMA_TF32)
+      nchw_to_nhwc_slice_kernel<T, float, false><<<grid, 256, 0, st>>>((const T*)x, (float*)y, C, HW, y_pixel_stride, yi);
     else
       nchw_to_nhwc_slice_kernel<T, __nv_bfloat16, false><<<grid, 256, 0, st>>>((const T*)x, (__nv_bfloat16*)y, C, HW,
                                                                                y_pixel_stride, yi);
@@ -285,17 +297,23 @@ extern "C" int fmi_reflect_border_nhwc(void* y, int B, int C, int H, int W, int 
 //   mode 0: Conv2d(3, stride 1, padding 1)                              x [B,H,W,*]      -> y [B,H,W,*]
 //   mode 1: Conv2d(3, stride 1, padding 0) on a pre-padded input        x [B,H+2,W+2,*]  -> y [B,H,W,*]
 //   mode 2: ConvTranspose2d(3, stride 2, padding 1, output_padding 1)   x [B,H,W,*]      -> y [B,2H,2W,*]
+//   mode 3: the same transposed conv as ONE GEMM (O <= 64): N = 4*O columns = the 4 output-parity classes, 4 taps = the 4
+//           input shifts, wp [4][4*O][I] from fmi_conv_weight_prep(merged = 1). 4/9 of the MMA instructions of mode 2 —
+//           narrow layers sit on the per-instruction floor of the tensor pipe (~85 clk for any N <= 64), not on its FLOPs.
 //   x: I channels per pixel out of x_pixel_stride; wp [9][O][I] from fmi_conv_weight_prep (O a multiple of 32, rows >= the
 //   real output channels zero); bias [O] fp32 or NULL; act 2: y = acc + bias, 1: lrelu_slope(acc + bias), 3: tanh(acc + bias).
+//   round_y = 0 (TF32 mode): y keeps the exact fp32 accumulator instead of its tf32 rounding — for outputs that feed
+//   InstanceNorm (a rounding of x is amplified by |mean| / std there); an MMA reading such a tensor truncates it instead.
 //   y: NHWC in the operand type, O channels per pixel out of y_pixel_stride, written at the interior of a buffer padded by
 //   y_pad pixels on each side (0 or 1); may be NULL when y_nchw is given. y_nchw: fp32 [B, nchw_C, OH, OW] or NULL.
 extern "C" int fmi_conv3x3_nhwc(const void* x, int64_t x_pixel_stride, const void* wp, const float* bias, void* y,
                                 int64_t y_pixel_stride, int y_pad, float* y_nchw, int nchw_C, int B, int I, int O, int H,
-                                int W, int mode, int act, float slope, int mma, void* stream) {
+                                int W, int mode, int act, float slope, int round_y, int mma, void* stream) {
   FMI_REQUIRE(mma == FMI_MMA_TF32 || mma == FMI_MMA_BF16, "conv3x3: bad mma");
   if (B == 0) return FMI_OK;
   FMI_REQUIRE(x && wp && (y || y_nchw), "conv3x3: null pointer");
-  FMI_REQUIRE(mode >= 0 && mode <= 2 && act >= 1 && act <= 3 && (y_pad == 0 || y_pad == 1), "conv3x3: bad mode/act/pad");
+  FMI_REQUIRE(mode >= 0 && mode <= 3 && act >= 1 && act <= 3 && (y_pad == 0 || y_pad == 1), "conv3x3: bad mode/act/pad");
+  FMI_REQUIRE(mode != 3 || (O <= 64 && y && !y_nchw), "conv3x3: mode 3 (merged parity classes) needs O <= 64 and an NHWC output");
   const int esz = esz_of(mma);
   FMI_REQUIRE(I >= 16 && O >= 32 && O % 32 == 0 && (O <= 256 || O % 256 == 0) && H >= 1 && W >= 1,
               "conv3x3: unsupported shape I=%d O=%d H=%d W=%d (O must be a multiple of 32, <= 256 or a multiple of 256)", I, O, H, W);
@@ -312,12 +330,19 @@ extern "C" int fmi_conv3x3_nhwc(const void* x, int64_t x_pixel_stride, const voi
   const uint32_t epa = 128 / esz;
   const CUtensorMapDataType dt = tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   const int IH = mode == 1 ? H + 2 : H, IW = mode == 1 ? W + 2 : W;   // input extents
-  const int OH = mode == 2 ? 2 * H : H, OW = mode == 2 ? 2 * W : W;
+  const int OH = mode >= 2 ? 2 * H : H, OW = mode >= 2 ? 2 * W : W;
 
   ConvGemmParams p{};
   p.B = B; p.I = I; p.O = O; p.H = IH; p.W = IW; p.T = 9;
   p.w_shared = 1;
+  p.raw_out = !round_y;
   p.n_tile = O <= 256 ? O : 256;
+  if (mode == 3) {   // one GEMM for the 4 parity classes: N = 4*O, weights [4 shifts][4*O][I]
+    p.merge_o = O;
+    p.O = 4 * O;
+    p.n_tile = 4 * O;
+    p.T = 4;
+  }
   p.k_chunks = (I + epa - 1) / epa;
   p.bias = bias; p.act = act; p.slope = slope; p.gain = 1.f;
   p.OH = OH; p.OW = OW;
@@ -335,7 +360,7 @@ extern "C" int fmi_conv3x3_nhwc(const void* x, int64_t x_pixel_stride, const voi
 
   CUtensorMap mw;
   {
-    uint64_t dims[2] = {(uint64_t)I, (uint64_t)9 * O};
+    uint64_t dims[2] = {(uint64_t)I, (uint64_t)p.T * p.O};
     uint64_t str[1] = {(uint64_t)I * esz};
     uint32_t box[2] = {epa, (uint32_t)p.n_tile};
     int e = make_tensor_map(&mw, dt, 2, wp, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -349,6 +374,16 @@ extern "C" int fmi_conv3x3_nhwc(const void* x, int64_t x_pixel_stride, const voi
     return make_tensor_map(m, dt, 4, x, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
   };
 
+  if (mode == 3) {
+    p.Mh = H; p.Mw = W; p.sy = p.sx = 2; p.py = p.px = 0;
+    p.ntaps = 4;
+    for (int t = 0; t < 4; ++t) { p.tap_dy[t] = t >> 1; p.tap_dx[t] = t & 1; p.tap_slab[t] = t; }
+    TilePlan tp = pick_tile(p.Mh, p.Mw);
+    CUtensorMap mx;
+    int e = make_x_map(&mx, tp.TH, tp.TW);
+    FMI_REQUIRE(e == 0, "conv3x3: cuTensorMapEncodeTiled(x) failed (%d)", e);
+    return tf32 ? launch_gemm_class<true>(mx, mw, p, st) : launch_gemm_class<false>(mx, mw, p, st);
+  }
   if (mode != 2) {
     p.Mh = H; p.Mw = W; p.sy = p.sx = 1; p.py = p.px = 0;
     p.ntaps = 9;
@@ -383,4 +418,149 @@ extern "C" int fmi_conv3x3_nhwc(const void* x, int64_t x_pixel_stride, const voi
       if (rc) return rc;
     }
   return FMI_OK;
+}
+
+// =====================================================================================================================
+// Output block convolution (base_function.py:369-398): Conv2d(C -> <=4 channels, 3x3, padding 0) on the reflection-padded
+// activations + tanh. 2*9*C*3 FLOPs per pixel for 128*C bytes read: HBM-bound, and on the tensor pipe every 128-pixel
+// tile costs 9*C/8 instructions of ~85 clk for N = 3 useful columns (measured 0.91 ms at 1024^2 x 8, the largest launch of
+// the decoder). SIMT instead: weights live in __constant__ memory so every FFMA takes its weight as a constant-bank
+// operand (no load instruction), activations are staged per 16-channel chunk in shared memory as [channel vector][row][col]
+// float4 planes (a warp reads 32 consecutive float4: conflict-free), each thread owns a 4-row x 1-column strip x 3 outputs
+// (12 independent accumulators; 18 LDS.128 per 432 FFMA). fp32 accumulation of operand-type inputs: more accurate than the
+// TF32 GEMM it replaces. Optional fused 4x4 average pooling (AdaptiveAvgPool2d(256) of the 1024^2 image, model.py:111).
+// =====================================================================================================================
+namespace {
+constexpr int OC_MAX_C = 64;
+__constant__ float c_out_w[3 * 9 * OC_MAX_C];  // [o][tap][c]
+__constant__ float c_out_b[4];
+
+__global__ void __launch_bounds__(256) out_weight_to_const_layout_kernel(const float* __restrict__ w, const float* __restrict__ b,
+                                                                         float* __restrict__ dst, int O, int C) {
+  // w [O][C][3][3] -> dst [3][9][C] (rows o >= O zero), then 4 bias floats at dst + 3*9*C
+  for (int e = threadIdx.x; e < 3 * 9 * C; e += blockDim.x) {
+    const int c = e % C, t = (e / C) % 9, o = e / (9 * C);
+    dst[e] = o < O ? w[((int64_t)o * C + c) * 9 + t] : 0.f;
+  }
+  if (threadIdx.x < 4) dst[3 * 9 * C + threadIdx.x] = (b && (int)threadIdx.x < O) ? b[threadIdx.x] : 0.f;
+}
+
+constexpr int OC_TH = 16, OC_TW = 32;                       // output tile per CTA (128 threads: 4 warps x 4 rows)
+constexpr int OC_PLANE = ((OC_TH + 2) * (OC_TW + 2) + 7) / 8 * 8 + 1;   // float4 per channel-vector plane, = 1 mod 8
+
+template <typename OT, int C>
+__global__ void __launch_bounds__(128) out_conv_tanh_kernel(const OT* __restrict__ xpad /*[B,H+2,W+2,C]*/,
+                                                            float* __restrict__ img /*[B,O,H,W] or NULL*/,
+                                                            float* __restrict__ pooled /*[B,O,H/4,W/4] or NULL*/, int O, int H,
+                                                            int W) {
+  constexpr int CH = 16;                 // channels per staged chunk (4 float4 planes)
+  __shared__ float4 tile[4 * OC_PLANE];
+  const int b = blockIdx.z, y0 = blockIdx.y * OC_TH, x0 = blockIdx.x * OC_TW;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int PW = W + 2;
+  const OT* xb = xpad + (int64_t)b * (H + 2) * PW * C;
+  float acc[4][3];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int o = 0; o < 3; ++o) acc[r][o] = c_out_b[o];
+#pragma unroll
+  for (int cc = 0; cc < C; cc += CH) {
+    if (cc) __syncthreads();
+    // stage (TH+2) x (TW+2) pixels x 16 channels: thread = (pixel, channel vector of 4), channel vector fastest
+    for (int e = threadIdx.x; e < (OC_TH + 2) * (OC_TW + 2) * 4; e += 128) {
+      const int v = e & 3, pix = e >> 2;
+      const int ty = pix / (OC_TW + 2), tx = pix - ty * (OC_TW + 2);
+      const int gy = y0 + ty, gx = x0 + tx;   // padded coordinates
+      float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gy < H + 2 && gx < PW) {
+        const OT* src = xb + ((int64_t)gy * PW + gx) * C + cc + v * 4;
+        if constexpr (sizeof(OT) == 4) {
+          val = *reinterpret_cast<const float4*>(src);
+        } else {
+          const uint2 u = *reinterpret_cast<const uint2*>(src);
+          const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&u.x);
+          const __nv_bfloat162 c2 = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+          val = make_float4(__low2float(a), __high2float(a), __low2float(c2), __high2float(c2));
+        }
+      }
+      tile[v * OC_PLANE + pix] = val;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const float4* plane = tile + v * OC_PLANE + (warp * 4) * (OC_TW + 2) + lane;
+#pragma unroll
+      for (int ry = 0; ry < 6; ++ry) {        // input rows of the strip (4 outputs + 2)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const float4 d = plane[ry * (OC_TW + 2) + kx];
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const int ky = ry - r;
+            if (ky < 0 || ky > 2) continue;
+#pragma unroll
+            for (int o = 0; o < 3; ++o) {
+              const float* wv = c_out_w + (o * 9 + ky * 3 + kx) * C + cc + v * 4;
+              acc[r][o] = fmaf(d.x, wv[0], acc[r][o]);
+              acc[r][o] = fmaf(d.y, wv[1], acc[r][o]);
+              acc[r][o] = fmaf(d.z, wv[2], acc[r][o]);
+              acc[r][o] = fmaf(d.w, wv[3], acc[r][o]);
+            }
+          }
+        }
+      }
+    }
+  }
+  const int x = x0 + lane, yb = y0 + warp * 4;
+  float ps[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int o = 0; o < 3; ++o) {
+      const float t = tanhf(acc[r][o]);
+      ps[o] += t;
+      if (img && o < O && x < W && yb + r < H) img[(((int64_t)b * O + o) * H + yb + r) * W + x] = t;
+    }
+  if (pooled) {   // 4 rows in the thread, 4 columns across lanes (H, W multiples of 4: checked by the host)
+#pragma unroll
+    for (int o = 0; o < 3; ++o) {
+      ps[o] += __shfl_xor_sync(0xffffffffu, ps[o], 1);
+      ps[o] += __shfl_xor_sync(0xffffffffu, ps[o], 2);
+    }
+    if ((lane & 3) == 0 && x < W && yb < H)
+      for (int o = 0; o < O; ++o)
+        pooled[(((int64_t)b * O + o) * (H / 4) + yb / 4) * (W / 4) + x / 4] = ps[o] * (1.f / 16.f);
+  }
+}
+}  // namespace
+
+// Output block: img = tanh(conv3x3_valid(xpad) + bias), xpad [B,H+2,W+2,C] NHWC operand type (leaky-ReLU and reflection
+// padding already applied), weight [O,C,3,3] fp32 (O <= 3), bias [O] or NULL. img [B,O,H,W] fp32 and / or pooled
+// [B,O,H/4,W/4] fp32 (4x4 means; H, W multiples of 4) — either may be NULL. scratch: (27*C + 4) floats.
+extern "C" int fmi_output_conv_tanh(const void* xpad, const float* weight, const float* bias, float* img, float* pooled,
+                                    float* scratch, int B, int C, int O, int H, int W, int mma, void* stream) {
+  FMI_REQUIRE(mma == FMI_MMA_TF32 || mma == FMI_MMA_BF16, "output_conv_tanh: bad mma");
+  if (B == 0) return FMI_OK;
+  FMI_REQUIRE(xpad && weight && scratch && (img || pooled), "output_conv_tanh: null pointer");
+  FMI_REQUIRE((C == 32 || C == 64 || C == 16) && O >= 1 && O <= 3 && H >= 1 && W >= 1 && B <= 65535,
+              "output_conv_tanh: unsupported shape C=%d O=%d (C in {16,32,64}, O <= 3)", C, O);
+  FMI_REQUIRE(!pooled || (H % 4 == 0 && W % 4 == 0), "output_conv_tanh: pooling needs H, W multiples of 4");
+  FMI_REQUIRE(fmi_aligned(xpad, 16), "output_conv_tanh: xpad must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  out_weight_to_const_layout_kernel<<<1, 256, 0, st>>>(weight, bias, scratch, O, C);
+  int rc = fmi_launched("out_weight_layout");
+  if (rc) return rc;
+  FMI_CUDA(cudaMemcpyToSymbolAsync(c_out_w, scratch, (size_t)27 * C * sizeof(float), 0, cudaMemcpyDeviceToDevice, st));
+  FMI_CUDA(cudaMemcpyToSymbolAsync(c_out_b, scratch + 27 * C, 4 * sizeof(float), 0, cudaMemcpyDeviceToDevice, st));
+  dim3 grid((W + OC_TW - 1) / OC_TW, (H + OC_TH - 1) / OC_TH, B);
+  FMI_REQUIRE(grid.y <= 65535, "output_conv_tanh: image too tall");
+#define FMI_OC_LAUNCH(OT, CC) out_conv_tanh_kernel<OT, CC><<<grid, 128, 0, st>>>((const OT*)xpad, img, pooled, O, H, W)
+  if (mma == FMI_MMA_TF32) {
+    if (C == 16) FMI_OC_LAUNCH(float, 16); else if (C == 32) FMI_OC_LAUNCH(float, 32); else FMI_OC_LAUNCH(float, 64);
+  } else {
+    if (C == 16) FMI_OC_LAUNCH(__nv_bfloat16, 16); else if (C == 32) FMI_OC_LAUNCH(__nv_bfloat16, 32); else FMI_OC_LAUNCH(__nv_bfloat16, 64);
+  }
+#undef FMI_OC_LAUNCH
+  return fmi_launched("out_conv_tanh");
 }

@@ -38,6 +38,11 @@ struct ConvGemmParams {
   // of a padded one — the base pointer `out` is pre-offset by the caller
   int64_t out_bstride, out_rstride;
   int out_pstride;
+  // merged parity classes of a stride-2 transposed conv (conv_blocks.cu): the N tile is 4 x merge_o columns, column block
+  // cls = 2*py + px holds the merge_o output channels of output pixel (2m + py, 2n + px); taps are the 4 input shifts
+  int merge_o;
+  int raw_out;         // TF32 mode: store the fp32 accumulator as is instead of rounding it to tf32 (the consumer is not an MMA,
+                       // or must see the exact value: InstanceNorm statistics amplify a rounding of x by |mean| / std)
   float* nchw_out;     // optional fp32 NCHW copy of the first nchw_C output channels ([B, nchw_C, OH, OW]); `out` may be NULL
   int nchw_C;
   const float* noise;
@@ -229,19 +234,26 @@ __global__ void __launch_bounds__(kGemmThreads, 3)
           mbar_arrive(&acc_empty[as]);
         }
         if (!valid) continue;
+        OT* outp = out + c0;
+        int bofs = o0 + c0;
+        if (p.merge_o) {
+          const int cls = c0 / p.merge_o;
+          bofs = c0 - cls * p.merge_o;
+          outp = out + (cls >> 1) * p.out_rstride + (cls & 1) * p.out_pstride + bofs;
+        }
         float f[32];
 #pragma unroll
         for (int k = 0; k < 32; ++k) f[k] = __uint_as_float(v[k]);
         if (p.act == 1) {
 #pragma unroll
           for (int k = 0; k < 32; ++k) {
-            float tt = f[k] + nz + (p.bias ? __ldg(p.bias + o0 + c0 + k) : 0.f);
+            float tt = f[k] + nz + (p.bias ? __ldg(p.bias + bofs + k) : 0.f);
             f[k] = (tt > 0.f ? tt : tt * p.slope) * p.gain;
           }
         } else if (p.act >= 2) {
 #pragma unroll
           for (int k = 0; k < 32; ++k) {
-            const float tt = f[k] + (p.bias ? __ldg(p.bias + o0 + c0 + k) : 0.f);
+            const float tt = f[k] + (p.bias ? __ldg(p.bias + bofs + k) : 0.f);
             f[k] = p.act == 3 ? tanhf(tt) : tt;
           }
         }
@@ -267,9 +279,10 @@ __global__ void __launch_bounds__(kGemmThreads, 3)
 #pragma unroll
           for (int k = 0; k < 32; k += 4)
             if (k < ncols)
-              *reinterpret_cast<float4*>(out + c0 + k) =
-                  make_float4(__uint_as_float(f32_to_tf32_rna(f[k])), __uint_as_float(f32_to_tf32_rna(f[k + 1])),
-                              __uint_as_float(f32_to_tf32_rna(f[k + 2])), __uint_as_float(f32_to_tf32_rna(f[k + 3])));
+              *reinterpret_cast<float4*>(outp + k) =
+                  p.raw_out ? make_float4(f[k], f[k + 1], f[k + 2], f[k + 3])
+                            : make_float4(__uint_as_float(f32_to_tf32_rna(f[k])), __uint_as_float(f32_to_tf32_rna(f[k + 1])),
+                                          __uint_as_float(f32_to_tf32_rna(f[k + 2])), __uint_as_float(f32_to_tf32_rna(f[k + 3])));
         } else {
 #pragma unroll
           for (int k = 0; k < 32; k += 8)
@@ -279,7 +292,7 @@ __global__ void __launch_bounds__(kGemmThreads, 3)
               u.y = pack_bf16x2(f[k + 2], f[k + 3]);
               u.z = pack_bf16x2(f[k + 4], f[k + 5]);
               u.w = pack_bf16x2(f[k + 6], f[k + 7]);
-              *reinterpret_cast<uint4*>(out + c0 + k) = u;
+              *reinterpret_cast<uint4*>(outp + k) = u;
             }
         }
       }

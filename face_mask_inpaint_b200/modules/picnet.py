@@ -221,7 +221,9 @@ class ResGenerator(nn.Module):
                 self.add_module(f'attn{i}', Auto_Attn(ch, None))
             prev = ch
 
-    def forward(self, encoded, z=None, f_e=None, mask=None):
+    def forward(self, encoded, z=None, f_e=None, mask=None, pool_to=None):
+        """`pool_to` (not in the reference's signature; ReferenceFill passes its AdaptiveAvgPool2d size): return the pooled
+        image, which the kernel path fuses into the Output block instead of writing and re-reading the full-size image."""
         out = encoded
         if z is not None:
             f = self.generator(z)
@@ -229,7 +231,7 @@ class ResGenerator(nn.Module):
                 f = getattr(self, f'generator{i}')(f)
             out = encoded + f
         if picnet_fast.supported(self, out):   # inference: the conv blocks on the implicit-GEMM kernels (csrc/conv_blocks.cu)
-            return picnet_fast.decoder_forward(self, out, f_e, mask)
+            return picnet_fast.decoder_forward(self, out, f_e, mask, pool_to=pool_to)
         output = None
         for i in range(self.layers):
             out = getattr(self, f'decoder{i}')(out)
@@ -238,6 +240,8 @@ class ResGenerator(nn.Module):
             if i > self.layers - 2:
                 output = getattr(self, f'out{i}')(out)
                 out = torch.cat([out, output], dim=1)
+        if pool_to is not None:
+            output = F.adaptive_avg_pool2d(output, pool_to)
         return output
 
     def get_z(self, src_distribution, ref_distribution, return_zq=False, mask=None):
@@ -318,12 +322,10 @@ class ReferenceFill(nn.Module):
             dec_image = self.decoder(enc_features)
         else:
             z = self.decoder.get_z(src_dist, ref_dist, return_zq=not self.use_att)
-            dec_image = self.decoder(enc_features, z=z)
-        if resize:
-            if no_prior:
-                dec_image = F.interpolate(dec_image, size=(218, 178), mode='bilinear', align_corners=True)
-            else:
-                dec_image = self.pool(dec_image)
+            # model.py:111 (`self.pool(dec_image)`) handed to the decoder so that its kernel path can fuse it
+            dec_image = self.decoder(enc_features, z=z, pool_to=self.pool.output_size if resize else None)
+        if resize and no_prior:
+            dec_image = F.interpolate(dec_image, size=(218, 178), mode='bilinear', align_corners=True)
         return dec_image
 
 

@@ -116,16 +116,20 @@ class _Ctx:
     def empty(self, *shape):
         return torch.empty(shape, dtype=self.dt, device=self.dev)
 
-    def weights(self, parts, o_rows):
-        """parts: [(weight, transposed)] concatenated along the input channels -> wp [9][o_rows][sum I]."""
+    def weights(self, parts, o_rows, merged=False):
+        """parts: [(weight, transposed)] concatenated along the input channels -> wp [9][o_rows][sum I], or with `merged`
+        (transposed convs, fmi_conv3x3_nhwc mode 3) [4 input shifts][4 parity classes * O][sum I]."""
         itot = sum((w.shape[0] if tr else w.shape[1]) for w, tr in parts)
         o_real = parts[0][0].shape[1] if parts[0][1] else parts[0][0].shape[0]
-        wp = (torch.zeros if o_rows != o_real else torch.empty)((9, o_rows, itot), dtype=self.dt, device=self.dev)
+        if merged:
+            o_rows = 4 * o_real
+        wp = (torch.zeros if (merged or o_rows != o_real) else torch.empty)((4 if merged else 9, o_rows, itot), dtype=self.dt,
+                                                                           device=self.dev)
         off = 0
         for w, tr in parts:
             i = w.shape[0] if tr else w.shape[1]
-            _lib.check(self.lib.fmi_conv_weight_prep(_p(w), _p(wp), o_real, i, int(tr), o_rows, itot, off, self.mma, self.st),
-                       "fmi_conv_weight_prep")
+            _lib.check(self.lib.fmi_conv_weight_prep(_p(w), _p(wp), o_real, i, int(tr), o_rows, itot, off, int(merged), self.mma,
+                                                     self.st), "fmi_conv_weight_prep")
             off += i
         return wp
 
@@ -142,15 +146,16 @@ class _Ctx:
                    "fmi_norm_act_nhwc")
         return ss
 
-    def conv(self, x, x_stride, wp, bias, y, y_stride, y_pad, y_nchw, nchw_c, b, i, o, h, w, mode, act, slope=0.0):
+    def conv(self, x, x_stride, wp, bias, y, y_stride, y_pad, y_nchw, nchw_c, b, i, o, h, w, mode, act, slope=0.0, round_y=1):
         _lib.check(self.lib.fmi_conv3x3_nhwc(x, x_stride, _p(wp), _p(bias), y, y_stride, y_pad, _p(y_nchw), nchw_c, b, i, o, h, w,
-                                             mode, act, slope, self.mma, self.st), "fmi_conv3x3_nhwc")
+                                             mode, act, slope, round_y, self.mma, self.st), "fmi_conv3x3_nhwc")
 
 
-def decoder_forward(gen, x, f_e=None, mask=None, taps=None):
+def decoder_forward(gen, x, f_e=None, mask=None, taps=None, pool_to=None):
     """The decoder loop of ResGenerator.forward (network.py:256-268) for `x` = encoded (+ f) [B, C, H, W] fp32 NCHW.
     Returns the image [B, 3, H * 2^layers, W * 2^layers] fp32. `taps` (diagnostics, tests/diag_picnet_blocks.py): a dict that
-    receives an fp32 NCHW copy of every block output."""
+    receives an fp32 NCHW copy of every block output. `pool_to` = (h, w): return AdaptiveAvgPool2d(pool_to) of the image
+    instead (modules/model.py:111), fused into the Output kernel when it is an exact 4x4 mean."""
     k = _Ctx(x.device)
     esz = 4 if k.mma == _lib.MMA_TF32 else 2
     b, c_in, h, w = x.shape
@@ -158,7 +163,8 @@ def decoder_forward(gen, x, f_e=None, mask=None, taps=None):
     blocks = [getattr(gen, f"decoder{i}") for i in range(gen.layers)]
     ch0 = _plain(blocks[0].conv1).out_channels
     cat = k.empty(b, h, w, ch0 + c_in)            # [a2 | x] of the first block
-    _lib.check(k.lib.fmi_nchw_to_nhwc_slice(_p(x), cat.data_ptr() + ch0 * esz, b, c_in, h, w, ch0 + c_in, _lib.F32, k.mma, k.st),
+    # block inputs / conv1 outputs feed InstanceNorm: stored exact (round_y = 0), see fmi_conv3x3_nhwc
+    _lib.check(k.lib.fmi_nchw_to_nhwc_slice(_p(x), cat.data_ptr() + ch0 * esz, b, c_in, h, w, ch0 + c_in, _lib.F32, 0, k.mma, k.st),
                "fmi_nchw_to_nhwc_slice")
     image = None
     for i, blk in enumerate(blocks):
@@ -176,14 +182,17 @@ def decoder_forward(gen, x, f_e=None, mask=None, taps=None):
         a1 = k.empty(b, h, w, c_in)
         k.norm_act(x_ptr, ctot, a1.data_ptr(), c_in, n1, b, c_in, hw, slope)
         h1 = k.empty(b, h, w, ch)
-        k.conv(a1.data_ptr(), c_in, k.weights([(w1, False)], ch), b1, h1.data_ptr(), ch, 0, None, 0, b, c_in, ch, h, w, 0, 2)
+        k.conv(a1.data_ptr(), c_in, k.weights([(w1, False)], ch), b1, h1.data_ptr(), ch, 0, None, 0, b, c_in, ch, h, w, 0, 2,
+               round_y=0)
         del a1
         # a2 = lrelu(IN(h1)) into channels [0, ch) next to x
         k.norm_act(h1.data_ptr(), ch, cat.data_ptr(), ctot, n2, b, ch, hw, slope)
         del h1
         # y = convT(a2) + b2 + convT_shortcut(x) + bs: one GEMM over [a2 | x]
         bias = b2 if bs is None else (bs if b2 is None else b2 + bs)
-        wcat = k.weights([(w2, True), (ws, True)], co)
+        # narrow layers: one GEMM for the 4 parity classes (mode 3: 4/9 of the MMA instructions), else one per class (mode 2)
+        up_mode = 3 if (co <= 64 and os.environ.get("FMI_CONVT_MERGE", "1") != "0") else 2
+        wcat = k.weights([(w2, True), (ws, True)], co, merged=up_mode == 3)
         oh, ow = 2 * h, 2 * w
         last = i == gen.layers - 1
         attn = getattr(gen, f"attn{i}", None) if (i == 1 and gen.use_attn) else None
@@ -192,21 +201,33 @@ def decoder_forward(gen, x, f_e=None, mask=None, taps=None):
             o_slope = _slope(out_blk.model[0])
             padded = k.empty(b, oh + 2, ow + 2, co)
             # Output's activation fused into the epilogue (the raw block output has no other reader: network.py:266-268)
-            k.conv(cat.data_ptr(), ctot, wcat, bias, padded.data_ptr(), co, 1, None, 0, b, ctot, co, h, w, 2, 1, o_slope)
+            k.conv(cat.data_ptr(), ctot, wcat, bias, padded.data_ptr(), co, 1, None, 0, b, ctot, co, h, w, up_mode, 1, o_slope)
             _lib.check(k.lib.fmi_reflect_border_nhwc(padded.data_ptr(), b, co, oh, ow, k.mma, k.st), "fmi_reflect_border_nhwc")
             if taps is not None:
                 taps[f"decoder{i}:lrelu"] = padded[:, 1:-1, 1:-1].float().permute(0, 3, 1, 2).contiguous()
             wo, bo = _effective(out_blk.conv1)
             n_img = wo.shape[0]
-            bo_pad = None
-            if bo is not None:
-                bo_pad = torch.zeros(32, dtype=torch.float32, device=x.device)
-                bo_pad[:n_img] = bo
-            image = torch.empty((b, n_img, oh, ow), dtype=torch.float32, device=x.device)
-            k.conv(padded.data_ptr(), co, k.weights([(wo, False)], 32), bo_pad, None, 32, 0, image, n_img, b, co, 32, oh, ow, 1, 3)
+            fuse_pool = pool_to is not None and tuple(pool_to) == (oh // 4, ow // 4) and oh % 4 == 0 and ow % 4 == 0
+            if co in (16, 32, 64) and n_img <= 3 and os.environ.get("FMI_OUTCONV_GEMM") != "1":
+                # SIMT kernel (HBM-bound layer; fp32 accumulation), optionally with the 4x4 average pooling fused
+                scratch = torch.empty(27 * co + 4, dtype=torch.float32, device=x.device)
+                pooled = torch.empty((b, n_img, oh // 4, ow // 4), dtype=torch.float32, device=x.device) if fuse_pool else None
+                image = None if fuse_pool else torch.empty((b, n_img, oh, ow), dtype=torch.float32, device=x.device)
+                _lib.check(k.lib.fmi_output_conv_tanh(padded.data_ptr(), _p(wo), _p(bo), _p(image), _p(pooled), _p(scratch), b, co,
+                                                      n_img, oh, ow, k.mma, k.st), "fmi_output_conv_tanh")
+                if fuse_pool:
+                    return pooled
+            else:
+                bo_pad = None
+                if bo is not None:
+                    bo_pad = torch.zeros(32, dtype=torch.float32, device=x.device)
+                    bo_pad[:n_img] = bo
+                image = torch.empty((b, n_img, oh, ow), dtype=torch.float32, device=x.device)
+                k.conv(padded.data_ptr(), co, k.weights([(wo, False)], 32), bo_pad, None, 32, 0, image, n_img, b, co, 32, oh, ow, 1,
+                       3)
         elif attn is not None:
             y = k.empty(b, oh, ow, co)
-            k.conv(cat.data_ptr(), ctot, wcat, bias, y.data_ptr(), co, 0, None, 0, b, ctot, co, h, w, 2, 2)
+            k.conv(cat.data_ptr(), ctot, wcat, bias, y.data_ptr(), co, 0, None, 0, b, ctot, co, h, w, up_mode, 2, round_y=0)
             y_nchw = torch.empty((b, co, oh, ow), dtype=torch.float32, device=x.device)
             _lib.check(k.lib.fmi_nhwc_to_nchw(y.data_ptr(), _p(y_nchw), b, co, oh, ow, k.mma, _lib.F32, k.st), "fmi_nhwc_to_nchw")
             del y
@@ -215,7 +236,7 @@ def decoder_forward(gen, x, f_e=None, mask=None, taps=None):
             ch_next = _plain(blocks[i + 1].conv1).out_channels
             nxt = k.empty(b, oh, ow, ch_next + co)
             _lib.check(k.lib.fmi_nchw_to_nhwc_slice(_p(y_nchw), nxt.data_ptr() + ch_next * esz, b, co, oh, ow, ch_next + co,
-                                                    _lib.F32, k.mma, k.st), "fmi_nchw_to_nhwc_slice")
+                                                    _lib.F32, 0, k.mma, k.st), "fmi_nchw_to_nhwc_slice")
             cat = nxt
             if taps is not None:
                 taps[f"decoder{i}+attn"] = y_nchw
@@ -223,9 +244,11 @@ def decoder_forward(gen, x, f_e=None, mask=None, taps=None):
             ch_next = _plain(blocks[i + 1].conv1).out_channels
             nxt = k.empty(b, oh, ow, ch_next + co)
             k.conv(cat.data_ptr(), ctot, wcat, bias, nxt.data_ptr() + ch_next * esz, ch_next + co, 0, None, 0, b, ctot, co, h, w,
-                   2, 2)
+                   up_mode, 2, round_y=0)
             cat = nxt
             if taps is not None:
                 taps[f"decoder{i}"] = nxt[..., ch_next:].float().permute(0, 3, 1, 2).contiguous()
         c_in, h, w = co, oh, ow
+    if pool_to is not None:
+        image = torch.nn.functional.adaptive_avg_pool2d(image, pool_to)
     return image

@@ -247,13 +247,14 @@ int fmi_torgb_bwd_nhwc(const void* x, const float* drgb, const float* rgb_w, voi
 /* wp[t][o][i_off + i] = weight[o,i,t] (Conv2d layout [O,I,3,3], transposed = 0) or weight[i,o,t] (ConvTranspose2d
  *   layout [I,O,3,3], transposed = 1) in the operand type; wp is [9][O_rows][I_row], rows / columns not written stay as
  *   the caller initialised them (zero). Writing two weights at different i_off concatenates them along the input
- *   channels. weight is the effective fp32 weight (SpectralNorm already applied: w_bar / sigma, external_function.py:55-57). */
+ *   channels. merged = 1 (transposed only, O_rows = 4*O): the layout of fmi_conv3x3_nhwc mode 3, wp [4][4*O][I_row] with
+ *   slab = input shift 2*dy + dx and row = (2*py + px)*O + o. weight is the effective fp32 weight (SpectralNorm already applied: w_bar / sigma, external_function.py:55-57). */
 int fmi_conv_weight_prep(const float* weight, void* wp, int O, int I, int transposed, int O_rows, int I_row, int i_off,
-                         int mma, void* stream);
+                         int merged, int mma, void* stream);
 
 /* NCHW (dtype) -> NHWC operand type into a channel slice: y[b, p, c] at y + (b*H*W + p) * y_pixel_stride + c. */
-int fmi_nchw_to_nhwc_slice(const void* x, void* y, int B, int C, int H, int W, int64_t y_pixel_stride, int dtype, int mma,
-                           void* stream);
+int fmi_nchw_to_nhwc_slice(const void* x, void* y, int B, int C, int H, int W, int64_t y_pixel_stride, int dtype,
+                           int round_y, int mma, void* stream);
 
 /* InstanceNorm2d statistics (biased variance over H*W per sample and channel, F.instance_norm) folded with the affine
  *   parameters: scale_shift[b][c] = (gamma[c]*rstd, beta[c] - mean*gamma[c]*rstd). sums: B*C*2 doubles of scratch. */
@@ -271,13 +272,24 @@ int fmi_reflect_border_nhwc(void* y, int B, int C, int H, int W, int mma, void* 
  *   mode 0: Conv2d(3, stride 1, padding 1)                              x [B,H,W,*]      -> y [B,H,W,*]
  *   mode 1: Conv2d(3, stride 1, padding 0) on a pre-padded input        x [B,H+2,W+2,*]  -> y [B,H,W,*]
  *   mode 2: ConvTranspose2d(3, stride 2, padding 1, output_padding 1)   x [B,H,W,*]      -> y [B,2H,2W,*]
+ *   mode 3: mode 2 as one GEMM over the 4 output-parity classes (O <= 64, wp from fmi_conv_weight_prep(merged = 1))
  *   wp [9][O][I] from fmi_conv_weight_prep (O a multiple of 32: pad with zero rows); bias [O] fp32 or NULL;
  *   act 2: y = acc + bias;  act 1: leaky_relu(acc + bias, slope);  act 3: tanh(acc + bias).
+ *   round_y: 1 = y rounded to the operand type (tf32 / bf16); 0 (TF32 mode only) = exact fp32 values, for tensors that
+ *   feed InstanceNorm statistics (a later MMA truncates them instead). Same flag on fmi_nchw_to_nhwc_slice.
  *   y (may be NULL if y_nchw is given): NHWC operand type, pixel stride y_pixel_stride, written to the interior of a
  *   buffer padded by y_pad (0 or 1) pixels per side. y_nchw (or NULL): fp32 [B, nchw_C, OH, OW], the first nchw_C channels. */
 int fmi_conv3x3_nhwc(const void* x, int64_t x_pixel_stride, const void* wp, const float* bias, void* y,
                      int64_t y_pixel_stride, int y_pad, float* y_nchw, int nchw_C, int B, int I, int O, int H, int W,
-                     int mode, int act, float slope, int mma, void* stream);
+                     int mode, int act, float slope, int round_y, int mma, void* stream);
+
+/* Output block (base_function.py:369-398 after the leaky-ReLU and ReflectionPad2d(1) that fmi_conv3x3_nhwc(act = 1,
+ *   y_pad = 1) + fmi_reflect_border_nhwc produce): img = tanh(Conv2d(C -> O <= 3, 3x3, padding 0)(xpad) + bias), fp32
+ *   accumulation on the CUDA cores (HBM-bound: 128*C bytes per 54*C FLOPs). xpad [B,H+2,W+2,C] NHWC operand type, C in
+ *   {16,32,64}; weight [O,C,3,3], bias [O] fp32. img [B,O,H,W] fp32 and / or pooled [B,O,H/4,W/4] (4x4 means =
+ *   AdaptiveAvgPool2d of modules/model.py:111 for a 1024^2 -> 256^2 image); either may be NULL. scratch: 27*C + 4 floats. */
+int fmi_output_conv_tanh(const void* xpad, const float* weight, const float* bias, float* img, float* pooled,
+                         float* scratch, int B, int C, int O, int H, int W, int mma, void* stream);
 
 #ifdef __cplusplus
 }

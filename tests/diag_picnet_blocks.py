@@ -53,13 +53,16 @@ def main():
     print(f"cuDNN TF32 (torch default) vs cuDNN fp32: image rel err {rel(got_tf32, want):.3e}")
     for i in range(5):
         print(f"  cuDNN TF32 accumulated decoder{i} rel err {rel(outs_tf32[i], outs[i]):.3e}")
+    print(f"  cuDNN TF32 accumulated decoder1+attn rel err {rel(outs_tf32['attn'], outs['attn']):.3e}")
     ours = copy.deepcopy(base).cuda()
     ours.decoder.get_z = types.MethodType(mean_z, ours.decoder)
     taps = {}
     orig = PF.decoder_forward
-    PF.decoder_forward = lambda gen, x, f_e=None, mask=None: orig(gen, x, f_e, mask, taps=taps)
+    PF.decoder_forward = lambda gen, x, f_e=None, mask=None, pool_to=None: orig(gen, x, f_e, mask, taps=taps, pool_to=pool_to)
+    torch.backends.cudnn.allow_tf32 = True     # the kernel path is taken when TF32 convolutions are allowed
     with torch.no_grad():
         got = ours(src, ref, mask, resize=False)
+    torch.backends.cudnn.allow_tf32 = False
     PF.decoder_forward = orig
     print(f"image: rel err {rel(got, want):.3e}")
     for key, t in taps.items():
@@ -80,6 +83,11 @@ def main():
         t2 = {}
         with torch.no_grad():
             w = blk_c(ins[i])
+            blk_t = copy.deepcopy(getattr(base.decoder, f"decoder{i}")).cuda()
+            torch.backends.cudnn.allow_tf32 = True
+            wt = blk_t(ins[i])
+            torch.backends.cudnn.allow_tf32 = False
+            print(f"isolated     decoder{i}  cuDNN TF32 rel err {rel(wt, w):.3e}")
             try:
                 orig(gen, ins[i], taps=t2)
                 print(f"isolated     decoder{i}  rel err {rel(t2['decoder0'], w):.3e}")

@@ -38,34 +38,38 @@ def _to_nhwc(k, x, stride=None, offset=0):
     buf = torch.full((b, h, w, stride), float("nan"), dtype=k.dt, device="cuda")
     esz = buf.element_size()
     _lib.check(k.lib.fmi_nchw_to_nhwc_slice(x.contiguous().data_ptr(), buf.data_ptr() + offset * esz, b, c, h, w, stride,
-                                            _lib.F32, k.mma, k.st), "fmi_nchw_to_nhwc_slice")
+                                            _lib.F32, 1, k.mma, k.st), "fmi_nchw_to_nhwc_slice")
     return buf
 
 
 @pytest.mark.parametrize("mma", [0, 1])
 @pytest.mark.parametrize("shape", [(2, 64, 32, 12, 20), (1, 96, 64, 33, 17), (3, 32, 256, 8, 8), (1, 512, 512, 4, 4)])
-@pytest.mark.parametrize("mode", [0, 2])
+@pytest.mark.parametrize("mode", [0, 2, 3])
 def test_conv3x3_matches_oracle(mma, shape, mode):
     b, i, o, h, w = shape
+    if mode == 3 and o > 64:
+        pytest.skip("merged parity classes need O <= 64")
     g = torch.Generator().manual_seed(b * 1000 + i + o + h)
     x = torch.randn(b, i, h, w, generator=g)
-    wt = torch.randn((i, o, 3, 3) if mode == 2 else (o, i, 3, 3), generator=g) / (i * 9) ** 0.5
+    wt = torch.randn((i, o, 3, 3) if mode >= 2 else (o, i, 3, 3), generator=g) / (i * 9) ** 0.5
     bias = 0.1 * torch.randn(o, generator=g)
-    if mode == 2:
+    if mode >= 2:
         want = torch.nn.functional.conv_transpose2d(x, wt, bias, stride=2, padding=1, output_padding=1)
     else:
         want = torch.nn.functional.conv2d(x, wt, bias, padding=1)
     k = _ctx(mma)
     xin = _to_nhwc(k, x.cuda(), stride=i + 32, offset=32)                # input is a channel slice of a wider buffer
-    wp = k.weights([(wt.cuda().contiguous(), mode == 2)], o)
+    wp = k.weights([(wt.cuda().contiguous(), mode >= 2)], o, merged=mode == 3)
     oh, ow = want.shape[-2:]
     y = torch.full((b, oh, ow, o + 64), float("nan"), dtype=k.dt, device="cuda")   # output slice [64, 64 + o)
     nchw = torch.empty((b, o, oh, ow), dtype=torch.float32, device="cuda")
     esz = y.element_size()
-    k.conv(xin.data_ptr() + 32 * esz, i + 32, wp, bias.cuda(), y.data_ptr() + 64 * esz, o + 64, 0, nchw, o, b, i, o, h, w, mode, 2)
+    k.conv(xin.data_ptr() + 32 * esz, i + 32, wp, bias.cuda(), y.data_ptr() + 64 * esz, o + 64, 0, None if mode == 3 else nchw,
+           0 if mode == 3 else o, b, i, o, h, w, mode, 2)
     got = y[..., 64:].float().permute(0, 3, 1, 2).cpu()
     assert rel_err(got, want) <= TOL[mma], rel_err(got, want)
-    assert rel_err(nchw.cpu(), want) <= TOL[mma]
+    if mode != 3:
+        assert rel_err(nchw.cpu(), want) <= TOL[mma]
     assert torch.isnan(y[..., :64].float()).all()                        # nothing written outside the slice
 
 
@@ -94,6 +98,37 @@ def test_valid_conv_tanh_on_reflect_padded_input(mma):
     img = torch.empty((b, 3, h, w), dtype=torch.float32, device="cuda")
     k.conv(padded.data_ptr(), c, k.weights([(wt.cuda().contiguous(), False)], 32), bo, None, 32, 0, img, 3, b, c, 32, h, w, 1, 3)
     assert rel_err(img.cpu(), want) <= TOL[mma], rel_err(img.cpu(), want)
+
+
+@pytest.mark.parametrize("mma", [0, 1])
+@pytest.mark.parametrize("shape", [(2, 32, 3, 40, 72), (1, 64, 3, 16, 36), (2, 16, 1, 20, 20), (1, 32, 2, 5, 9)])
+def test_output_conv_tanh_kernel_matches_oracle(mma, shape):
+    """fmi_output_conv_tanh (SIMT, fp32 accumulation) on a reflection-padded input, full image and fused 4x4 pooling."""
+    from face_mask_inpaint_b200 import _lib
+    b, c, o, h, w = shape
+    g = torch.Generator().manual_seed(c + h + o)
+    x = torch.randn(b, c, h, w, generator=g)
+    wt = torch.randn(o, c, 3, 3, generator=g) / (c * 9) ** 0.5
+    bias = 0.1 * torch.randn(o, generator=g)
+    k = _ctx(mma)
+    xp = torch.nn.functional.pad(torch.nn.functional.leaky_relu(x, 0.1), (1, 1, 1, 1), mode="reflect")
+    xin = _to_nhwc(k, xp.cuda())                                      # [B, H+2, W+2, C] operand type
+    xr = xin.float().permute(0, 3, 1, 2).cpu()                        # what the kernel reads (bf16 / tf32 rounded)
+    want = torch.tanh(torch.nn.functional.conv2d(xr, wt, bias))
+    pool_ok = h % 4 == 0 and w % 4 == 0
+    img = torch.empty((b, o, h, w), dtype=torch.float32, device="cuda")
+    pooled = torch.empty((b, o, h // 4, w // 4), dtype=torch.float32, device="cuda") if pool_ok else None
+    scratch = torch.empty(27 * c + 4, dtype=torch.float32, device="cuda")
+    _lib.check(k.lib.fmi_output_conv_tanh(xin.data_ptr(), wt.cuda().data_ptr(), bias.cuda().data_ptr(), img.data_ptr(),
+                                          None if pooled is None else pooled.data_ptr(), scratch.data_ptr(), b, c, o, h, w,
+                                          k.mma, k.st), "fmi_output_conv_tanh")
+    assert rel_err(img.cpu(), want) <= 2e-5, rel_err(img.cpu(), want)   # fp32 arithmetic on identical inputs
+    if pool_ok:
+        assert rel_err(pooled.cpu(), torch.nn.functional.avg_pool2d(want, 4)) <= 2e-5
+        only = torch.empty_like(pooled)                                # pooled output alone (no full-size image written)
+        _lib.check(k.lib.fmi_output_conv_tanh(xin.data_ptr(), wt.cuda().data_ptr(), bias.cuda().data_ptr(), None, only.data_ptr(),
+                                              scratch.data_ptr(), b, c, o, h, w, k.mma, k.st), "fmi_output_conv_tanh")
+        assert torch.equal(only, pooled)
 
 
 @pytest.mark.parametrize("mma", [0, 1])
@@ -188,3 +223,10 @@ def test_whole_generator_kernel_path_vs_cudnn_paths():
     e_ours, e_ref = rel_err(ours, truth), rel_err(ref_gpu, truth)
     assert e_ours <= 1.2 * e_ref + 1e-3, (e_ours, e_ref)
     assert e_ours <= 2e-2, e_ours
+    # resize=True: the 4x4 average pooling is fused into the Output kernel
+    m = copy.deepcopy(base).cuda()
+    m.decoder.get_z = types.MethodType(mean_z, m.decoder)
+    with torch.no_grad():
+        small = m(src, ref, mask)
+    assert small.shape == (2, 3, 256, 256)
+    assert rel_err(small, torch.nn.functional.avg_pool2d(ours, 4)) <= 1e-5
