@@ -564,3 +564,120 @@ extern "C" int fmi_output_conv_tanh(const void* xpad, const float* weight, const
 #undef FMI_OC_LAUNCH
   return fmi_launched("out_conv_tanh");
 }
+
+// =====================================================================================================================
+// SpectralNorm power iteration (external_function.py:44-57) in two kernels instead of ~13 ATen launches per convolution:
+//   v_raw = W^T u                                  (sn_wt_u_kernel)
+//   v = v_raw / (|v_raw| + eps);  u_raw = W v      (sn_w_v_kernel; |v_raw| recomputed per CTA, CTA 0 stores v)
+//   u = u_raw / (|u_raw| + eps);  sigma = u . (W v) = u . u_raw   -> fmi_conv_weight_prep_sn divides by it and stores u.
+// W = w_bar viewed as [Hh][Wd] (Hh = weight.shape[0]).
+// =====================================================================================================================
+namespace {
+__device__ __forceinline__ float block_sum_256(float v, float* red /*[8]*/) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = threadIdx.x < 8 ? red[threadIdx.x] : 0.f;
+  if (threadIdx.x < 32) {
+    t = warp_sum(t);
+    if (threadIdx.x == 0) red[0] = t;
+  }
+  __syncthreads();
+  return red[0];
+}
+
+__global__ void __launch_bounds__(128) sn_wt_u_kernel(const float* __restrict__ w, const float* __restrict__ u,
+                                                      float* __restrict__ v_raw, int Hh, int Wd) {
+  const int j = blockIdx.x * 128 + threadIdx.x;
+  if (j >= Wd) return;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int i = 0;
+  for (; i + 4 <= Hh; i += 4) {
+    a0 = fmaf(w[(int64_t)i * Wd + j], u[i], a0);
+    a1 = fmaf(w[(int64_t)(i + 1) * Wd + j], u[i + 1], a1);
+    a2 = fmaf(w[(int64_t)(i + 2) * Wd + j], u[i + 2], a2);
+    a3 = fmaf(w[(int64_t)(i + 3) * Wd + j], u[i + 3], a3);
+  }
+  for (; i < Hh; ++i) a0 = fmaf(w[(int64_t)i * Wd + j], u[i], a0);
+  v_raw[j] = (a0 + a1) + (a2 + a3);
+}
+
+__global__ void __launch_bounds__(256) sn_w_v_kernel(const float* __restrict__ w, const float* __restrict__ v_raw,
+                                                     float* __restrict__ v, float* __restrict__ u_raw, int Hh, int Wd) {
+  __shared__ float red[8];
+  float q = 0.f;
+  for (int j = threadIdx.x; j < Wd; j += 256) q = fmaf(v_raw[j], v_raw[j], q);
+  const float inv = 1.f / (sqrtf(block_sum_256(q, red)) + 1e-12f);
+  if (blockIdx.x == 0)
+    for (int j = threadIdx.x; j < Wd; j += 256) v[j] = v_raw[j] * inv;
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= Hh) return;
+  float a = 0.f;
+  for (int j = lane; j < Wd; j += 32) a = fmaf(w[(int64_t)row * Wd + j], v_raw[j] * inv, a);
+  a = warp_sum(a);
+  if (lane == 0) u_raw[row] = a;
+}
+
+// conv_weight_prep with the SpectralNorm division: sigma from u_raw (Hh <= 1024 values), CTA 0 stores the new u
+template <typename OT, bool ROUND_TF32>
+__global__ void __launch_bounds__(256) conv_weight_prep_sn_kernel(const float* __restrict__ w, OT* __restrict__ wp, int O, int I,
+                                                                  int transposed, int O_rows, int I_row, int i_off, int merged,
+                                                                  const float* __restrict__ u_raw, float* __restrict__ u, int Hh) {
+  __shared__ float red[8];
+  float q = 0.f;
+  for (int i = threadIdx.x; i < Hh; i += 256) q = fmaf(u_raw[i], u_raw[i], q);
+  const float n2 = block_sum_256(q, red);
+  const float inv = 1.f / (sqrtf(n2) + 1e-12f);
+  const float sigma = n2 * inv;                       // u . u_raw with u = u_raw * inv
+  if (blockIdx.x == 0)
+    for (int i = threadIdx.x; i < Hh; i += 256) u[i] = u_raw[i] * inv;
+  const int total = O * I * 9;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int t = e % 9, r = e / 9;
+    int o, i;
+    if (transposed) { i = r / O; o = r - i * O; }
+    else { o = r / I; i = r - o * I; }
+    float v = w[e] / sigma;
+    if (ROUND_TF32) v = __uint_as_float(f32_to_tf32_rna(v));
+    int slab = t, row = o;
+    if (merged) {
+      const int ky = t / 3, kx = t - ky * 3;
+      slab = (ky == 0 ? 2 : 0) + (kx == 0 ? 1 : 0);
+      row = ((ky != 1 ? 2 : 0) + (kx != 1 ? 1 : 0)) * O + o;
+    }
+    wp[((int64_t)slab * O_rows + row) * I_row + i_off + i] = from_f32<OT>(v);
+  }
+}
+}  // namespace
+
+// fmi_conv_weight_prep for a SpectralNorm-wrapped 3x3 conv: one power iteration on (w_bar, u, v) — u and v are updated in
+// place exactly as SpectralNorm._update_u_v does — and wp receives w_bar / sigma. scratch: (Wd + Hh) floats, Hh =
+// w_bar.shape[0], Wd = numel / Hh.
+extern "C" int fmi_conv_weight_prep_sn(const float* w_bar, float* u, float* v, float* scratch, void* wp, int O, int I,
+                                       int transposed, int O_rows, int I_row, int i_off, int merged, int mma, void* stream) {
+  FMI_REQUIRE(mma == FMI_MMA_TF32 || mma == FMI_MMA_BF16, "conv_weight_prep_sn: bad mma");
+  FMI_REQUIRE(w_bar && u && v && scratch && wp && O >= 1 && I >= 1 && O_rows >= O && i_off >= 0 && I_row >= i_off + I,
+              "conv_weight_prep_sn: bad arguments");
+  FMI_REQUIRE(!merged || (transposed && O_rows == 4 * O), "conv_weight_prep_sn: merged layout is for transposed convs");
+  const int Hh = transposed ? I : O;       // weight.shape[0]
+  const int Wd = (transposed ? O : I) * 9;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* v_raw = scratch;
+  float* u_raw = scratch + Wd;
+  sn_wt_u_kernel<<<(Wd + 127) / 128, 128, 0, st>>>(w_bar, u, v_raw, Hh, Wd);
+  int rc = fmi_launched("sn_wt_u");
+  if (rc) return rc;
+  sn_w_v_kernel<<<(Hh + 7) / 8, 256, 0, st>>>(w_bar, v_raw, v, u_raw, Hh, Wd);
+  rc = fmi_launched("sn_w_v");
+  if (rc) return rc;
+  const int grid = stream_grid((int64_t)O * I * 9, 256);
+  if (mma == FMI_MMA_TF32)
+    conv_weight_prep_sn_kernel<float, true><<<grid, 256, 0, st>>>(w_bar, (float*)wp, O, I, transposed, O_rows, I_row, i_off,
+                                                                  merged, u_raw, u, Hh);
+  else
+    conv_weight_prep_sn_kernel<__nv_bfloat16, false><<<grid, 256, 0, st>>>(w_bar, (__nv_bfloat16*)wp, O, I, transposed, O_rows,
+                                                                           I_row, i_off, merged, u_raw, u, Hh);
+  return fmi_launched("conv_weight_prep_sn");
+}

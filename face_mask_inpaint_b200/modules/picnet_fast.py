@@ -117,17 +117,32 @@ class _Ctx:
         return torch.empty(shape, dtype=self.dt, device=self.dev)
 
     def weights(self, parts, o_rows, merged=False):
-        """parts: [(weight, transposed)] concatenated along the input channels -> wp [9][o_rows][sum I], or with `merged`
-        (transposed convs, fmi_conv3x3_nhwc mode 3) [4 input shifts][4 parity classes * O][sum I]."""
-        itot = sum((w.shape[0] if tr else w.shape[1]) for w, tr in parts)
-        o_real = parts[0][0].shape[1] if parts[0][1] else parts[0][0].shape[0]
+        """parts: [(weight tensor or conv module (possibly SpectralNorm-wrapped), transposed)] concatenated along the input
+        channels -> wp [9][o_rows][sum I], or with `merged` (transposed convs, fmi_conv3x3_nhwc mode 3)
+        [4 input shifts][4 parity classes * O][sum I]. A SpectralNorm conv gets its power iteration here
+        (fmi_conv_weight_prep_sn: u, v advanced in place, wp = w_bar / sigma)."""
+        shape = lambda w: (_plain(w).weight_bar if isinstance(w, SpectralNorm) else (w if torch.is_tensor(w) else w.weight)).shape
+        itot = sum((shape(w)[0] if tr else shape(w)[1]) for w, tr in parts)
+        o_real = shape(parts[0][0])[1] if parts[0][1] else shape(parts[0][0])[0]
         if merged:
             o_rows = 4 * o_real
         wp = (torch.zeros if (merged or o_rows != o_real) else torch.empty)((4 if merged else 9, o_rows, itot), dtype=self.dt,
                                                                            device=self.dev)
         off = 0
         for w, tr in parts:
-            i = w.shape[0] if tr else w.shape[1]
+            i = shape(w)[0] if tr else shape(w)[1]
+            if isinstance(w, SpectralNorm) and w.power_iterations == 1 and os.environ.get("FMI_SN_TORCH") != "1":
+                m = w.module
+                wb, u, v = m.weight_bar.data, m.weight_u.data, m.weight_v.data
+                if not (wb.is_contiguous() and u.is_contiguous() and v.is_contiguous() and wb.dtype == torch.float32):
+                    raise RuntimeError("fmi_b200: SpectralNorm parameters must be contiguous fp32")
+                scratch = torch.empty(u.numel() + v.numel(), dtype=torch.float32, device=self.dev)
+                _lib.check(self.lib.fmi_conv_weight_prep_sn(_p(wb), _p(u), _p(v), _p(scratch), _p(wp), o_real, i, int(tr), o_rows,
+                                                            itot, off, int(merged), self.mma, self.st), "fmi_conv_weight_prep_sn")
+                off += i
+                continue
+            if not torch.is_tensor(w):
+                w = _effective(w)[0]
             _lib.check(self.lib.fmi_conv_weight_prep(_p(w), _p(wp), o_real, i, int(tr), o_rows, itot, off, int(merged), self.mma,
                                                      self.st), "fmi_conv_weight_prep")
             off += i
@@ -170,11 +185,10 @@ def decoder_forward(gen, x, f_e=None, mask=None, taps=None, pool_to=None):
     for i, blk in enumerate(blocks):
         n1, act, n2 = _block_layout(blk)
         slope = _slope(act)
-        w1, b1 = _effective(blk.conv1)
-        w2, b2 = _effective(blk.conv2)
-        ws, bs = _effective(blk.bypass)
-        ch, co = w1.shape[0], w2.shape[1]
-        if w1.shape[1] != c_in or ws.shape[0] != c_in:
+        c1, c2, cs = _plain(blk.conv1), _plain(blk.conv2), _plain(blk.bypass)
+        b1, b2, bs = (None if c.bias is None else c.bias.detach().float().contiguous() for c in (c1, c2, cs))
+        ch, co = c1.out_channels, c2.out_channels
+        if c1.in_channels != c_in or cs.in_channels != c_in or c2.in_channels != ch or cs.out_channels != co:
             raise RuntimeError("fmi_b200: decoder block channel mismatch")
         ctot, hw = ch + c_in, h * w
         x_ptr = cat.data_ptr() + ch * esz
@@ -182,7 +196,7 @@ def decoder_forward(gen, x, f_e=None, mask=None, taps=None, pool_to=None):
         a1 = k.empty(b, h, w, c_in)
         k.norm_act(x_ptr, ctot, a1.data_ptr(), c_in, n1, b, c_in, hw, slope)
         h1 = k.empty(b, h, w, ch)
-        k.conv(a1.data_ptr(), c_in, k.weights([(w1, False)], ch), b1, h1.data_ptr(), ch, 0, None, 0, b, c_in, ch, h, w, 0, 2,
+        k.conv(a1.data_ptr(), c_in, k.weights([(blk.conv1, False)], ch), b1, h1.data_ptr(), ch, 0, None, 0, b, c_in, ch, h, w, 0, 2,
                round_y=0)
         del a1
         # a2 = lrelu(IN(h1)) into channels [0, ch) next to x
@@ -192,7 +206,7 @@ def decoder_forward(gen, x, f_e=None, mask=None, taps=None, pool_to=None):
         bias = b2 if bs is None else (bs if b2 is None else b2 + bs)
         # narrow layers: one GEMM for the 4 parity classes (mode 3: 4/9 of the MMA instructions), else one per class (mode 2)
         up_mode = 3 if (co <= 64 and os.environ.get("FMI_CONVT_MERGE", "1") != "0") else 2
-        wcat = k.weights([(w2, True), (ws, True)], co, merged=up_mode == 3)
+        wcat = k.weights([(blk.conv2, True), (blk.bypass, True)], co, merged=up_mode == 3)
         oh, ow = 2 * h, 2 * w
         last = i == gen.layers - 1
         attn = getattr(gen, f"attn{i}", None) if (i == 1 and gen.use_attn) else None

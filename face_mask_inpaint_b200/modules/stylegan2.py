@@ -379,9 +379,6 @@ class ModulatedConv2d(nn.Module):
                 f'upsample={self.upsample}, downsample={self.downsample})')
 
     def _check(self):
-        if self.downsample:
-            raise NotImplementedError("fmi_b200: ModulatedConv2d(downsample=True) is not reachable from the reference's "
-                                      "scripts and has no kernel")
         if self.upsample and (self.blur.kernel.shape != (4, 4) or self.blur.pad != (1, 1)):
             raise NotImplementedError("fmi_b200: upsampling modulated conv supports the 4-tap blur with pad (1,1) only")
 
@@ -403,6 +400,19 @@ class ModulatedConv2d(nn.Module):
                 raise NotImplementedError("fmi_b200: 1x1 modulated conv is implemented for ToRGB (3 channels, no demod)")
             zero = torch.zeros(3, device=input.device)
             return _ToRGBFn.apply(to_nhwc(input, mma), self.weight, s, zero, mma).to(input.dtype)
+        if self.downsample:
+            # model.py:265-273: blur with pad (2,2) -> [B,I,H+1,W+1], then conv2d(padding 0, stride 2, groups = batch).
+            # Not reachable from the reference's scripts, so no dedicated kernel: the stride-2 valid conv is read out of the
+            # stride-1 'same' implicit GEMM on the blurred input (valid output j = same output j + 1; 4x the FLOPs).
+            if self.kernel_size != 3:
+                raise NotImplementedError("fmi_b200: downsampling modulated conv supports 3x3 kernels")
+            xb = self.blur(input)
+            up, self.upsample = self.upsample, False
+            try:
+                y = self.forward_nhwc(to_nhwc(xb, mma), s, mma)
+            finally:
+                self.upsample = up
+            return to_nchw(y, mma, input.dtype)[:, :, 1::2, 1::2].contiguous()
         y = self.forward_nhwc(to_nhwc(input, mma), s, mma)
         return to_nchw(y, mma, input.dtype)
 

@@ -252,6 +252,12 @@ int fmi_torgb_bwd_nhwc(const void* x, const float* drgb, const float* rgb_w, voi
 int fmi_conv_weight_prep(const float* weight, void* wp, int O, int I, int transposed, int O_rows, int I_row, int i_off,
                          int merged, int mma, void* stream);
 
+/* The same for a SpectralNorm-wrapped conv (external_function.py:16-72): one power iteration on (w_bar, u, v) — u [Hh] and
+ *   v [Wd] are updated in place as SpectralNorm._update_u_v does (Hh = w_bar.shape[0], Wd = numel / Hh) — and wp receives
+ *   w_bar / sigma, sigma = u . (W v). scratch: (Wd + Hh) floats. */
+int fmi_conv_weight_prep_sn(const float* w_bar, float* u, float* v, float* scratch, void* wp, int O, int I, int transposed,
+                            int O_rows, int I_row, int i_off, int merged, int mma, void* stream);
+
 /* NCHW (dtype) -> NHWC operand type into a channel slice: y[b, p, c] at y + (b*H*W + p) * y_pixel_stride + c. */
 int fmi_nchw_to_nhwc_slice(const void* x, void* y, int B, int C, int H, int W, int64_t y_pixel_stride, int dtype,
                            int round_y, int mma, void* stream);

@@ -189,8 +189,8 @@ def equal_linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Ten
 
 def modulated_conv2d(x: torch.Tensor, style: torch.Tensor, weight: torch.Tensor, mod_weight: torch.Tensor,
                      mod_bias: torch.Tensor, demodulate: bool = True, upsample: bool = False,
-                     blur_kernel: Sequence[int] = (1, 3, 3, 1)) -> torch.Tensor:
-    """modules/psp/stylegan2/model.py:241-279 (downsample branch unused by this repo's scripts: omitted).
+                     blur_kernel: Sequence[int] = (1, 3, 3, 1), downsample: bool = False) -> torch.Tensor:
+    """modules/psp/stylegan2/model.py:241-279 (the downsample branch :265-272 is not reachable from the repo's scripts).
     weight is the parameter [1, O, I, k, k]; style is the latent [B, style_dim]."""
     batch, in_channel, height, width = x.shape
     _, out_channel, _, ksize, _ = weight.shape
@@ -212,6 +212,13 @@ def modulated_conv2d(x: torch.Tensor, style: torch.Tensor, weight: torch.Tensor,
         pad0, pad1 = (p + 1) // 2 + factor - 1, p // 2 + 1
         k = make_kernel(list(blur_kernel)) * (factor ** 2)                              # :78-82
         out = upfirdn2d(out, k.to(out), pad=(pad0, pad1))                         # :263
+    elif downsample:
+        factor = 2
+        p = (len(blur_kernel) - factor) + (ksize - 1)                                   # :217-221
+        xb = upfirdn2d(x, make_kernel(list(blur_kernel)).to(x), pad=((p + 1) // 2, p // 2))   # :266
+        xin = xb.reshape(1, batch * in_channel, xb.shape[-2], xb.shape[-1])             # :267-268
+        out = F.conv2d(xin, w, padding=0, stride=2, groups=batch)                       # :269
+        out = out.view(batch, out_channel, out.shape[-2], out.shape[-1])                # :270-271
     else:
         xin = x.reshape(1, batch * in_channel, height, width)                           # :274
         out = F.conv2d(xin, w, padding=ksize // 2, groups=batch)                        # :275

@@ -176,6 +176,14 @@ def gen_stylegan2():
         out.update({f"sc.{tag}.x": np_(x), f"sc.{tag}.style": np_(style), f"sc.{tag}.noise": np_(noise),
                     f"sc.{tag}.conv": np_(conv), f"sc.{tag}.out": np_(y)})
         out.update({f"sc.{tag}.sd.{k}": np_(v) for k, v in mod.state_dict().items()})
+    # ModulatedConv2d(downsample=True) (model.py:265-272; not reachable from the scripts, part of the signature)
+    torch.manual_seed(8)
+    mod = sg2.ModulatedConv2d(16, 32, 3, 24, downsample=True)
+    randomize(mod, g)
+    x = torch.randn(2, 16, 12, 8, generator=g)
+    style = torch.randn(2, 24, generator=g)
+    out.update({"down.x": np_(x), "down.style": np_(style), "down.out": np_(mod(x, style))})
+    out.update({f"down.sd.{k}": np_(v) for k, v in mod.state_dict().items()})
     torch.manual_seed(4)
     mod = sg2.ToRGB(16, 24)
     randomize(mod, g)

@@ -53,5 +53,50 @@ def main():
             print(f"  {n:22s} {ms:8.3f} ms")
 
 
+def graphed_pieces():
+    """The same forward split into three CUDA graphs (encoders + ExampleGuidedAttention, z -> f ResBlock, decoder): eager
+    per-module times above are host-launch bound, these are the GPU times."""
+    from face_mask_inpaint_b200 import ops
+    from face_mask_inpaint_b200.graphs import CapturedForward
+    torch.backends.cudnn.allow_tf32 = True
+    net = fill_by_name(build_picnet_ref()).eval().cuda()
+    net.decoder.get_z = types.MethodType(mean_z, net.decoder)
+
+    def timed(fn, *a):
+        g = CapturedForward(fn, *a)
+        for _ in range(3):
+            g(*a)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            g(*a)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / 10
+
+    for batch in (8, 4):
+        src, ref, mask = (t.cuda() for t in picnet_inputs(batch))
+
+        def encoders(src, ref, mask):
+            sd, sf = net.src_encoder(src)
+            rd, rf = net.ref_encoder(ref)
+            enc = net.attention(ops.scale_img(mask.unsqueeze(1), sf.shape[-2:]), sf, rf)
+            return enc, sd[0], rd[0]
+
+        with torch.no_grad():
+            enc, smu, rmu = (t.clone() for t in encoders(src, ref, mask))
+            z = torch.cat([smu, rmu], dim=1)
+            f = net.decoder.generator(z).clone()
+            x = (enc + f).clone()
+        t_enc = timed(encoders, src, ref, mask)
+        t_gen = timed(lambda z: net.decoder.generator(z), z)
+        t_dec = timed(lambda x: net.decoder(x, pool_to=(256, 256)), x)
+        t_all = timed(lambda a, b, c: net(a, b, c), src, ref, mask)
+        print(f"graphed, batch {batch}: whole forward {t_all:.2f} ms | encoders + EGA {t_enc:.2f} | z->f ResBlock {t_gen:.2f} | "
+              f"decoder blocks + Auto_Attn + Output + pool {t_dec:.2f}")
+
+
 if __name__ == "__main__":
+    graphed_pieces()
     main()

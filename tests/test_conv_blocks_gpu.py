@@ -153,6 +153,35 @@ def test_instance_norm_act_matches_oracle(mma, shape):
     assert rel_err(got, want) <= (5e-4 if mma == 0 else 8e-3), rel_err(got, want)
 
 
+@pytest.mark.parametrize("transposed", [False, True])
+@pytest.mark.parametrize("shape", [(32, 64), (256, 256), (3, 32)])
+def test_spectral_norm_weight_prep_matches_oracle(transposed, shape):
+    """fmi_conv_weight_prep_sn = SpectralNorm._update_u_v (one power iteration, u / v updated in place) + w_bar / sigma in the
+    operand layout, against oracle.spectral_norm_weight (external_function.py:44-57)."""
+    from face_mask_inpaint_b200 import _lib
+    o, i = shape
+    g = torch.Generator().manual_seed(o + i)
+    wshape = (i, o, 3, 3) if transposed else (o, i, 3, 3)
+    w_bar = torch.randn(wshape, generator=g) / (i * 9) ** 0.5
+    hh = wshape[0]
+    u = torch.randn(hh, generator=g)
+    u /= u.norm()
+    v = torch.randn(w_bar.numel() // hh, generator=g)
+    v /= v.norm()
+    w_eff, u_new, v_new = O.spectral_norm_weight(w_bar, u, v)
+    k = _ctx(0)
+    o_rows = max(32, o)
+    wp = torch.zeros((9, o_rows, i), dtype=torch.float32, device="cuda")
+    wb_d, u_d, v_d = w_bar.cuda(), u.cuda(), v.cuda()
+    scratch = torch.empty(u.numel() + v.numel(), dtype=torch.float32, device="cuda")
+    _lib.check(k.lib.fmi_conv_weight_prep_sn(wb_d.data_ptr(), u_d.data_ptr(), v_d.data_ptr(), scratch.data_ptr(), wp.data_ptr(),
+                                             o, i, int(transposed), o_rows, i, 0, 0, k.mma, k.st), "fmi_conv_weight_prep_sn")
+    want = (w_eff.permute(2, 3, 1, 0) if transposed else w_eff.permute(2, 3, 0, 1)).reshape(9, o, i)
+    assert rel_err(wp[:, :o].cpu(), want) <= 5e-4            # tf32 rounding of the stored weights (2^-11)
+    assert rel_err(u_d.cpu(), u_new) <= 1e-5 and rel_err(v_d.cpu(), v_new) <= 1e-5
+    assert float(wp[:, o:].abs().max()) == 0.0 if o_rows > o else True
+
+
 def _mirror_from_golden():
     from face_mask_inpaint_b200.modules import picnet as P
     g = {k: torch.from_numpy(v) for k, v in np.load(GOLD).items()}

@@ -84,6 +84,15 @@ def test_styled_conv_matches_reference(tag, up):
     assert rel_err(out, g[f"sc.{tag}.out"]) <= 1e-5
 
 
+def test_modulated_conv_downsample_matches_reference():
+    g = load("stylegan2_layers.npz")
+    sd = {k[len("down.sd."):]: v for k, v in g.items() if k.startswith("down.sd.")}
+    out = O.modulated_conv2d(g["down.x"], g["down.style"], sd["weight"], sd["modulation.weight"], sd["modulation.bias"], True,
+                             False, downsample=True)
+    assert out.shape == g["down.out"].shape == (2, 32, 6, 4)
+    assert rel_err(out, g["down.out"]) <= 1e-5
+
+
 def test_to_rgb_matches_reference():
     g = load("stylegan2_layers.npz")
     sd = {k[len("rgb.sd."):]: v for k, v in g.items() if k.startswith("rgb.sd.")}

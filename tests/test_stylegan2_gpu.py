@@ -60,6 +60,28 @@ def test_modulated_conv2d(cfg, mode):
     assert err <= tol, f"rel err {err:.3e}"
 
 
+@pytest.mark.parametrize("cfg", [(2, 32, 64, 16, 16), (1, 64, 32, 12, 20)])
+@pytest.mark.parametrize("mode", MODES, ids=[m[0] for m in MODES])
+def test_modulated_conv2d_downsample(cfg, mode):
+    """model.py:265-272 (blur pad (2,2), then stride-2 valid conv): served by the blur kernel + the stride-1 implicit GEMM."""
+    SG = _mods()
+    b, i, o, h, w = cfg
+    _, dtype, tol = mode
+    g = torch.Generator().manual_seed(2)
+    mod = SG.ModulatedConv2d(i, o, 3, 512, downsample=True)
+    _randomize(mod, g)
+    x = torch.randn(b, i, h, w, generator=g).to(dtype).float()
+    style = torch.randn(b, 512, generator=g)
+    want = O.modulated_conv2d(x, style, mod.weight.detach(), mod.modulation.weight.detach(),
+                              mod.modulation.bias.detach(), True, False, downsample=True)
+    mod = mod.to(DEV)
+    with torch.no_grad():
+        got = mod(x.to(dtype).to(DEV), style.to(DEV))
+    assert got.shape == want.shape == (b, o, h // 2, w // 2)
+    err = rel_err(got, want)
+    assert err <= tol, f"rel err {err:.3e}"
+
+
 @pytest.mark.parametrize("up", [False, True])
 @pytest.mark.parametrize("batched_noise", [False, True])
 @pytest.mark.parametrize("mode", MODES, ids=[m[0] for m in MODES])
