@@ -80,7 +80,41 @@ class CapturedForward:
         self.replays += 1
         return self._static_out
 
+    def matches(self, *args, **kwargs) -> bool:
+        tensors = _flatten((args, [kwargs[k] for k in self._kw_order if k in kwargs]), [])
+        return len(tensors) == len(self._static_in) and all(
+            d.shape == s.shape and d.dtype == s.dtype and d.device == s.device for d, s in zip(self._static_in, tensors))
+
     @property
     def static_inputs(self):
         """The graph's own input buffers, in argument order: write into them directly to skip the copy."""
         return self._static_in
+
+
+def auto_graph(forward):
+    """Decorator for an nn.Module.forward: in inference (autograd off, module in eval mode, CUDA tensor arguments) the call
+    is served by a CapturedForward keyed by the argument shapes / dtypes and the non-tensor arguments; anything else falls
+    through to the eager forward. The returned tensors are clones (the scripts keep results across iterations)."""
+    import functools
+
+    @functools.wraps(forward)
+    def wrapper(self, *args, **kwargs):
+        tensors = _flatten((args, kwargs), [])
+        if torch.is_grad_enabled() or self.training or not tensors or not all(t.is_cuda for t in tensors):
+            return forward(self, *args, **kwargs)
+        try:
+            key = (tuple((tuple(t.shape), t.dtype) for t in tensors),
+                   tuple(a for a in args if not isinstance(a, (torch.Tensor, list, tuple, dict))),
+                   tuple(sorted((k, v) for k, v in kwargs.items() if not isinstance(v, (torch.Tensor, list, tuple, dict)))))
+            hash(key)
+        except TypeError:
+            return forward(self, *args, **kwargs)
+        cache = self.__dict__.setdefault("_fmi_graphs", {})
+        g = cache.get(key)
+        if g is None:
+            g = cache[key] = CapturedForward(functools.partial(forward, self), *args, **kwargs)
+        out = g(*args, **kwargs)
+        return out.clone() if isinstance(out, torch.Tensor) else type(out)(o.clone() if isinstance(o, torch.Tensor) else o
+                                                                           for o in out)
+
+    return wrapper

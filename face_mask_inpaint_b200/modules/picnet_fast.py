@@ -24,7 +24,20 @@ import torch
 from torch import nn
 
 from .. import _lib, ops
-from .picnet_blocks import SpectralNorm
+
+
+class _SpectralNormMeta(type):
+    """isinstance(x, SpectralNorm) for this package's SpectralNorm AND the reference's own class
+    (external_function.py:16-72) when the package is installed over the reference: same attributes either way."""
+
+    def __instancecheck__(cls, obj):
+        m = getattr(obj, "module", None)
+        return (m is not None and hasattr(obj, "power_iterations") and getattr(obj, "name", None) == "weight"
+                and hasattr(m, "weight_bar") and hasattr(m, "weight_u") and hasattr(m, "weight_v"))
+
+
+class SpectralNorm(metaclass=_SpectralNormMeta):
+    pass
 
 
 def _p(t):
@@ -34,7 +47,7 @@ def _p(t):
 def _effective(conv):
     """(weight fp32 contiguous, bias) of a conv that may be wrapped in SpectralNorm (advances u/v like a forward would)."""
     if isinstance(conv, SpectralNorm):
-        conv._update_u_v()
+        conv._update_u_v()          # sets module.weight = w_bar / sigma (a tensor, not a Parameter)
         conv = conv.module
     w = conv.weight
     b = conv.bias

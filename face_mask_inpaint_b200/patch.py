@@ -19,6 +19,7 @@ Everything else (encoders, decoder conv blocks, losses, data loading, CLI) is th
 from __future__ import annotations
 
 import importlib
+import os
 import sys
 import types
 
@@ -149,12 +150,19 @@ def _install_compositing_callers():
         if self.encoder_type == 'drn' or no_prior:
             out = self.decoder(enc)
         else:
-            out = self.decoder(enc, z=self.decoder.get_z(src_dist, ref_dist, return_zq=not self.use_att))
+            z = self.decoder.get_z(src_dist, ref_dist, return_zq=not self.use_att)
+            if resize and getattr(type(self.decoder), "_fmi_pool_to", False):
+                return self.decoder(enc, z=z, pool_to=self.pool.output_size)   # pooling fused into the Output kernel
+            out = self.decoder(enc, z=z)
         if resize:
             out = _scale_img_any(out, (218, 178)) if no_prior else self.pool(out)
         return out
 
     model.ReferenceFill.forward = reference_fill_forward
+    _install_picnet_decoder()
+    if os.environ.get("FMI_CUDA_GRAPH") == "1":   # one graph replay per inference forward (fixed shapes are keyed)
+        from .graphs import auto_graph
+        model.ReferenceFill.forward = auto_graph(model.ReferenceFill.forward)
 
     try:
         enc_mod = importlib.import_module("modules.psp.encoders.psp_encoders")
@@ -194,6 +202,32 @@ def _install_compositing_callers():
         return torch.stack(latents, dim=1)
 
     enc_mod.GradualStyleEncoder.forward = gradual_style_encoder_forward
+
+
+def _install_picnet_decoder():
+    """f1: ResGenerator.forward (modules/pluralistic_model/network.py:247-268) runs its ResBlockDecoder /
+    Output blocks on the implicit-GEMM kernels in inference (modules/picnet_fast.py); under autograd, for unsupported
+    configurations or with TF32 convolutions switched off it is the reference's own forward."""
+    import torch
+    import torch.nn.functional as F
+    from .modules import picnet_fast
+    net = importlib.import_module("modules.pluralistic_model.network")
+    ref_forward = net.ResGenerator.forward
+
+    def res_generator_forward(self, encoded, z=None, f_e=None, mask=None, pool_to=None):
+        if not picnet_fast.supported(self, encoded):
+            out = ref_forward(self, encoded, z, f_e, mask)
+            return F.adaptive_avg_pool2d(out, pool_to) if pool_to is not None else out
+        out = encoded
+        if z is not None:                                   # network.py:249-254
+            f = self.generator(z)
+            for i in range(self.L):
+                f = getattr(self, 'generator' + str(i))(f)
+            out = encoded + f
+        return picnet_fast.decoder_forward(self, out, f_e, mask, pool_to=pool_to)
+
+    net.ResGenerator.forward = res_generator_forward
+    net.ResGenerator._fmi_pool_to = True
 
 
 def _blend(src, ref, full_mask):

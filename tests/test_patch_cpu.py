@@ -63,6 +63,28 @@ def test_state_dict_layout_is_unchanged_by_the_patch():
     g = network.define_g(ngf=8, z_nc=16, img_f=32, L=0, layers=3, norm='instance', activation='LeakyReLU',
                          init_type='orthogonal')
     assert isinstance(g.attn1, my_att.Auto_Attn)
+    # 4) f1: the reference's ResGenerator.forward is the installer's (kernel path in CUDA inference); its blocks are recognised
+    #    by the kernel path (the reference's own SpectralNorm / ResBlockDecoder / Output classes, duck-typed), and off the GPU
+    #    or under autograd it is the reference's forward, pooled on request
+    from face_mask_inpaint_b200.modules import picnet_fast
+    assert network.ResGenerator.forward.__name__ == "res_generator_forward"
+    g32 = network.define_g(ngf=32, z_nc=64, img_f=128, L=0, layers=3, norm='instance', activation='LeakyReLU',
+                           init_type='orthogonal', use_attn=False).eval()
+    assert isinstance(g32.decoder0.conv1, picnet_fast.SpectralNorm) and not isinstance(g32.decoder0.conv1.module,
+                                                                                     picnet_fast.SpectralNorm)
+    assert picnet_fast._block_layout(g32.decoder0) is not None
+    x = torch.randn(1, 128, 4, 4)
+    assert not picnet_fast.supported(g32, x)                      # CPU tensor: never the kernel path
+    with torch.no_grad():
+        full = g32(x)
+    assert full.shape == (1, 3, 32, 32)
+    g32b = network.define_g(ngf=32, z_nc=64, img_f=128, L=0, layers=3, norm='instance', activation='LeakyReLU',
+                            init_type='orthogonal', use_attn=False).eval()
+    g32b.load_state_dict(g32.state_dict())                        # incl. the SpectralNorm u / v advanced by the call above
+    with torch.no_grad():
+        pooled = g32b(x, pool_to=(8, 8))
+        want_pooled = F.adaptive_avg_pool2d(g32(x), (8, 8))
+    assert torch.allclose(pooled, want_pooled, atol=1e-6)
     _fresh_reference_modules()
     patch.uninstall_flag_for_tests()
 
