@@ -56,12 +56,13 @@ PROTOTYPES = {
     "fmi_torgb_bwd_nhwc": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "fmi_styled_conv_torgb_nhwc": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i,
                                         _vp]),
-    "fmi_conv_weight_prep": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
-    "fmi_conv_weight_prep_sn": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "fmi_conv_weight_prep": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "fmi_conv_weight_prep_sn": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "fmi_nchw_to_nhwc_slice": (_i, [_vp, _vp, _i, _i, _i, _i, _i64, _i, _i, _i, _vp]),
     "fmi_instnorm_stats_nhwc": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _vp]),
     "fmi_norm_act_nhwc": (_i, [_vp, _i64, _vp, _i64, _vp, _i, _i, _i, _f, _i, _vp]),
     "fmi_output_conv_tanh": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "fmi_avgpool2_nhwc": (_i, [_vp, _i64, _vp, _i64, _i, _i, _i, _i, _i, _i, _vp]),
     "fmi_reflect_border_nhwc": (_i, [_vp, _i, _i, _i, _i, _i, _vp]),
     "fmi_conv3x3_nhwc": (_i, [_vp, _i64, _vp, _vp, _vp, _i64, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _i, _vp]),
 }

@@ -29,10 +29,11 @@ namespace {
 // [4][4*O][I_row], rows of classes that do not use a shift stay zero.
 template <typename OT, bool ROUND_TF32>
 __global__ void __launch_bounds__(256) conv_weight_prep_kernel(const float* __restrict__ w, OT* __restrict__ wp, int O, int I,
-                                                               int transposed, int O_rows, int I_row, int i_off, int merged) {
-  const int total = O * I * 9;
+                                                               int transposed, int O_rows, int I_row, int i_off, int merged,
+                                                               int T) {
+  const int total = O * I * T;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
-    const int t = e % 9, r = e / 9;
+    const int t = e % T, r = e / T;
     int o, i;
     if (transposed) { i = r / O; o = r - i * O; }
     else { o = r / I; i = r - o * I; }
@@ -190,18 +191,21 @@ inline int stream_grid(int64_t work_items, int per_block) {
 // C ABI
 // =====================================================================================================================
 extern "C" int fmi_conv_weight_prep(const float* weight, void* wp, int O, int I, int transposed, int O_rows, int I_row,
-                                    int i_off, int merged, int mma, void* stream) {
+                                    int i_off, int merged, int ksize, int mma, void* stream) {
   FMI_REQUIRE(mma == FMI_MMA_TF32 || mma == FMI_MMA_BF16, "conv_weight_prep: bad mma");
+  FMI_REQUIRE(ksize == 3 || (ksize == 1 && !merged), "conv_weight_prep: ksize must be 3, or 1 (not merged)");
+  const int T = ksize * ksize;
   FMI_REQUIRE(!merged || (transposed && O_rows == 4 * O), "conv_weight_prep: merged layout is for transposed convs, O_rows = 4*O");
   FMI_REQUIRE(weight && wp && O >= 1 && I >= 1 && O_rows >= O && i_off >= 0 && I_row >= i_off + I,
               "conv_weight_prep: bad arguments (O=%d I=%d O_rows=%d I_row=%d i_off=%d)", O, I, O_rows, I_row, i_off);
-  const int grid = stream_grid((int64_t)O * I * 9, 256);
+  const int grid = stream_grid((int64_t)O * I * T, 256);
   cudaStream_t st = (cudaStream_t)stream;
   if (mma == FMI_MMA_TF32)
-    conv_weight_prep_kernel<float, true><<<grid, 256, 0, st>>>(weight, (float*)wp, O, I, transposed, O_rows, I_row, i_off, merged);
+    conv_weight_prep_kernel<float, true><<<grid, 256, 0, st>>>(weight, (float*)wp, O, I, transposed, O_rows, I_row, i_off, merged,
+                                                               T);
   else
     conv_weight_prep_kernel<__nv_bfloat16, false><<<grid, 256, 0, st>>>(weight, (__nv_bfloat16*)wp, O, I, transposed, O_rows,
-                                                                        I_row, i_off, merged);
+                                                                        I_row, i_off, merged, T);
   return fmi_launched("conv_weight_prep");
 }
 
@@ -300,6 +304,8 @@ extern "C" int fmi_reflect_border_nhwc(void* y, int B, int C, int H, int W, int 
 //   mode 3: the same transposed conv as ONE GEMM (O <= 64): N = 4*O columns = the 4 output-parity classes, 4 taps = the 4
 //           input shifts, wp [4][4*O][I] from fmi_conv_weight_prep(merged = 1). 4/9 of the MMA instructions of mode 2 —
 //           narrow layers sit on the per-instruction floor of the tensor pipe (~85 clk for any N <= 64), not on its FLOPs.
+//   mode 4: Conv2d(1, stride 1, padding 0): wp [1][O][I] (fmi_conv_weight_prep with ksize 1)
+//   act + 10 (with act 2): y += acc + bias — the residual sum of a ResBlock (conv2(a2) onto the stored shortcut).
 //   x: I channels per pixel out of x_pixel_stride; wp [9][O][I] from fmi_conv_weight_prep (O a multiple of 32, rows >= the
 //   real output channels zero); bias [O] fp32 or NULL; act 2: y = acc + bias, 1: lrelu_slope(acc + bias), 3: tanh(acc + bias).
 //   round_y = 0 (TF32 mode): y keeps the exact fp32 accumulator instead of its tf32 rounding — for outputs that feed
@@ -312,7 +318,10 @@ extern "C" int fmi_conv3x3_nhwc(const void* x, int64_t x_pixel_stride, const voi
   FMI_REQUIRE(mma == FMI_MMA_TF32 || mma == FMI_MMA_BF16, "conv3x3: bad mma");
   if (B == 0) return FMI_OK;
   FMI_REQUIRE(x && wp && (y || y_nchw), "conv3x3: null pointer");
-  FMI_REQUIRE(mode >= 0 && mode <= 3 && act >= 1 && act <= 3 && (y_pad == 0 || y_pad == 1), "conv3x3: bad mode/act/pad");
+  const int add_y = act >= 10;          // act + 10: y += result (residual sum; y must hold the other term already)
+  if (add_y) act -= 10;
+  FMI_REQUIRE(mode >= 0 && mode <= 4 && act >= 1 && act <= 3 && (y_pad == 0 || y_pad == 1), "conv3x3: bad mode/act/pad");
+  FMI_REQUIRE(!add_y || (y && act == 2 && mode != 3), "conv3x3: the residual sum needs an NHWC output and act 2");
   FMI_REQUIRE(mode != 3 || (O <= 64 && y && !y_nchw), "conv3x3: mode 3 (merged parity classes) needs O <= 64 and an NHWC output");
   const int esz = esz_of(mma);
   FMI_REQUIRE(I >= 16 && O >= 32 && O % 32 == 0 && (O <= 256 || O % 256 == 0) && H >= 1 && W >= 1,
@@ -336,6 +345,8 @@ extern "C" int fmi_conv3x3_nhwc(const void* x, int64_t x_pixel_stride, const voi
   p.B = B; p.I = I; p.O = O; p.H = IH; p.W = IW; p.T = 9;
   p.w_shared = 1;
   p.raw_out = !round_y;
+  p.add_out = add_y;
+  if (mode == 4) p.T = 1;               // 1x1 convolution: one tap, wp [1][O][I]
   p.n_tile = O <= 256 ? O : 256;
   if (mode == 3) {   // one GEMM for the 4 parity classes: N = 4*O, weights [4 shifts][4*O][I]
     p.merge_o = O;
@@ -378,6 +389,16 @@ extern "C" int fmi_conv3x3_nhwc(const void* x, int64_t x_pixel_stride, const voi
     p.Mh = H; p.Mw = W; p.sy = p.sx = 2; p.py = p.px = 0;
     p.ntaps = 4;
     for (int t = 0; t < 4; ++t) { p.tap_dy[t] = t >> 1; p.tap_dx[t] = t & 1; p.tap_slab[t] = t; }
+    TilePlan tp = pick_tile(p.Mh, p.Mw);
+    CUtensorMap mx;
+    int e = make_x_map(&mx, tp.TH, tp.TW);
+    FMI_REQUIRE(e == 0, "conv3x3: cuTensorMapEncodeTiled(x) failed (%d)", e);
+    return tf32 ? launch_gemm_class<true>(mx, mw, p, st) : launch_gemm_class<false>(mx, mw, p, st);
+  }
+  if (mode == 4) {
+    p.Mh = H; p.Mw = W; p.sy = p.sx = 1; p.py = p.px = 0;
+    p.ntaps = 1;
+    p.tap_dy[0] = p.tap_dx[0] = p.tap_slab[0] = 0;
     TilePlan tp = pick_tile(p.Mh, p.Mw);
     CUtensorMap mx;
     int e = make_x_map(&mx, tp.TH, tp.TW);
@@ -624,7 +645,8 @@ __global__ void __launch_bounds__(256) sn_w_v_kernel(const float* __restrict__ w
 template <typename OT, bool ROUND_TF32>
 __global__ void __launch_bounds__(256) conv_weight_prep_sn_kernel(const float* __restrict__ w, OT* __restrict__ wp, int O, int I,
                                                                   int transposed, int O_rows, int I_row, int i_off, int merged,
-                                                                  const float* __restrict__ u_raw, float* __restrict__ u, int Hh) {
+                                                                  const float* __restrict__ u_raw, float* __restrict__ u, int Hh,
+                                                                  int T) {
   __shared__ float red[8];
   float q = 0.f;
   for (int i = threadIdx.x; i < Hh; i += 256) q = fmaf(u_raw[i], u_raw[i], q);
@@ -633,9 +655,9 @@ __global__ void __launch_bounds__(256) conv_weight_prep_sn_kernel(const float* _
   const float sigma = n2 * inv;                       // u . u_raw with u = u_raw * inv
   if (blockIdx.x == 0)
     for (int i = threadIdx.x; i < Hh; i += 256) u[i] = u_raw[i] * inv;
-  const int total = O * I * 9;
+  const int total = O * I * T;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
-    const int t = e % 9, r = e / 9;
+    const int t = e % T, r = e / T;
     int o, i;
     if (transposed) { i = r / O; o = r - i * O; }
     else { o = r / I; i = r - o * I; }
@@ -656,13 +678,16 @@ __global__ void __launch_bounds__(256) conv_weight_prep_sn_kernel(const float* _
 // place exactly as SpectralNorm._update_u_v does — and wp receives w_bar / sigma. scratch: (Wd + Hh) floats, Hh =
 // w_bar.shape[0], Wd = numel / Hh.
 extern "C" int fmi_conv_weight_prep_sn(const float* w_bar, float* u, float* v, float* scratch, void* wp, int O, int I,
-                                       int transposed, int O_rows, int I_row, int i_off, int merged, int mma, void* stream) {
+                                       int transposed, int O_rows, int I_row, int i_off, int merged, int ksize, int mma,
+                                       void* stream) {
   FMI_REQUIRE(mma == FMI_MMA_TF32 || mma == FMI_MMA_BF16, "conv_weight_prep_sn: bad mma");
+  FMI_REQUIRE(ksize == 3 || (ksize == 1 && !merged), "conv_weight_prep_sn: ksize must be 3, or 1 (not merged)");
+  const int T = ksize * ksize;
   FMI_REQUIRE(w_bar && u && v && scratch && wp && O >= 1 && I >= 1 && O_rows >= O && i_off >= 0 && I_row >= i_off + I,
               "conv_weight_prep_sn: bad arguments");
   FMI_REQUIRE(!merged || (transposed && O_rows == 4 * O), "conv_weight_prep_sn: merged layout is for transposed convs");
   const int Hh = transposed ? I : O;       // weight.shape[0]
-  const int Wd = (transposed ? O : I) * 9;
+  const int Wd = (transposed ? O : I) * T;
   cudaStream_t st = (cudaStream_t)stream;
   float* v_raw = scratch;
   float* u_raw = scratch + Wd;
@@ -672,12 +697,62 @@ extern "C" int fmi_conv_weight_prep_sn(const float* w_bar, float* u, float* v, f
   sn_w_v_kernel<<<(Hh + 7) / 8, 256, 0, st>>>(w_bar, v_raw, v, u_raw, Hh, Wd);
   rc = fmi_launched("sn_w_v");
   if (rc) return rc;
-  const int grid = stream_grid((int64_t)O * I * 9, 256);
+  const int grid = stream_grid((int64_t)O * I * T, 256);
   if (mma == FMI_MMA_TF32)
     conv_weight_prep_sn_kernel<float, true><<<grid, 256, 0, st>>>(w_bar, (float*)wp, O, I, transposed, O_rows, I_row, i_off,
-                                                                  merged, u_raw, u, Hh);
+                                                                  merged, u_raw, u, Hh, T);
   else
     conv_weight_prep_sn_kernel<__nv_bfloat16, false><<<grid, 256, 0, st>>>(w_bar, (__nv_bfloat16*)wp, O, I, transposed, O_rows,
-                                                                           I_row, i_off, merged, u_raw, u, Hh);
+                                                                           I_row, i_off, merged, u_raw, u, Hh, T);
   return fmi_launched("conv_weight_prep_sn");
+}
+
+// ---- AvgPool2d(2, 2) on NHWC (the 'down' ResBlocks and the first encoder block, base_function.py:238-239, 290-298) ------
+namespace {
+template <typename OT, bool ROUND_TF32>
+__global__ void __launch_bounds__(256) avgpool2_nhwc_kernel(const OT* __restrict__ x, int64_t x_pix, OT* __restrict__ y,
+                                                            int64_t y_pix, int C, int H, int W) {
+  constexpr int VEC = 16 / sizeof(OT);
+  const int nvec = C / VEC, OH = H / 2, OW = W / 2;
+  const int b = blockIdx.y;
+  const int64_t total = (int64_t)OH * OW * nvec;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pp = e / nvec;
+    const int c = (int)(e - pp * nvec) * VEC;
+    const int oy = (int)(pp / OW), ox = (int)(pp - (int64_t)oy * OW);
+    const OT* src = x + ((int64_t)b * H * W + (int64_t)(2 * oy) * W + 2 * ox) * x_pix + c;
+    const Vec16<OT> a = ld_vec16_stream(src), bb = ld_vec16_stream(src + x_pix);
+    const Vec16<OT> cc = ld_vec16_stream(src + (int64_t)W * x_pix), d = ld_vec16_stream(src + (int64_t)(W + 1) * x_pix);
+    Vec16<OT> o;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      float f = 0.25f * ((to_f32<OT>(a.e[k]) + to_f32<OT>(bb.e[k])) + (to_f32<OT>(cc.e[k]) + to_f32<OT>(d.e[k])));
+      if (ROUND_TF32) f = __uint_as_float(f32_to_tf32_rna(f));
+      o.e[k] = from_f32<OT>(f);
+    }
+    st_vec16(y + ((int64_t)b * OH * OW + pp) * y_pix + c, o);
+  }
+}
+}  // namespace
+
+extern "C" int fmi_avgpool2_nhwc(const void* x, int64_t x_pixel_stride, void* y, int64_t y_pixel_stride, int B, int C, int H,
+                                 int W, int round_y, int mma, void* stream) {
+  FMI_REQUIRE(mma == FMI_MMA_TF32 || mma == FMI_MMA_BF16, "avgpool2: bad mma");
+  if (B == 0) return FMI_OK;
+  const int vec = 16 / esz_of(mma);
+  FMI_REQUIRE(x && y && H >= 2 && W >= 2 && H % 2 == 0 && W % 2 == 0 && C >= vec && C % vec == 0 &&
+                  x_pixel_stride % vec == 0 && y_pixel_stride % vec == 0 && x_pixel_stride >= C && y_pixel_stride >= C &&
+                  fmi_aligned(x, 16) && fmi_aligned(y, 16) && B <= 65535,
+              "avgpool2: unsupported shape C=%d H=%d W=%d", C, H, W);
+  const int64_t work = (int64_t)(H / 2) * (W / 2) * (C / vec);
+  int gx = stream_grid(work, 256 * 2);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mma == FMI_MMA_TF32 && round_y)
+    avgpool2_nhwc_kernel<float, true><<<dim3(gx, B), 256, 0, st>>>((const float*)x, x_pixel_stride, (float*)y, y_pixel_stride, C, H, W);
+  else if (mma == FMI_MMA_TF32)
+    avgpool2_nhwc_kernel<float, false><<<dim3(gx, B), 256, 0, st>>>((const float*)x, x_pixel_stride, (float*)y, y_pixel_stride, C, H, W);
+  else
+    avgpool2_nhwc_kernel<__nv_bfloat16, false><<<dim3(gx, B), 256, 0, st>>>((const __nv_bfloat16*)x, x_pixel_stride,
+                                                                            (__nv_bfloat16*)y, y_pixel_stride, C, H, W);
+  return fmi_launched("avgpool2");
 }

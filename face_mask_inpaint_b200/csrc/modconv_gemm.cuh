@@ -41,6 +41,7 @@ struct ConvGemmParams {
   // merged parity classes of a stride-2 transposed conv (conv_blocks.cu): the N tile is 4 x merge_o columns, column block
   // cls = 2*py + px holds the merge_o output channels of output pixel (2m + py, 2n + px); taps are the 4 input shifts
   int merge_o;
+  int add_out;         // the epilogue adds the values already stored at the output location (residual sum: y += conv(x))
   int raw_out;         // TF32 mode: store the fp32 accumulator as is instead of rounding it to tf32 (the consumer is not an MMA,
                        // or must see the exact value: InstanceNorm statistics amplify a rounding of x by |mean| / std)
   float* nchw_out;     // optional fp32 NCHW copy of the first nchw_C output channels ([B, nchw_C, OH, OW]); `out` may be NULL
@@ -275,6 +276,29 @@ __global__ void __launch_bounds__(kGemmThreads, 3)
           }
         }
         const int ncols = min(32, p.n_tile - c0);
+        if (p.add_out) {
+          if constexpr (TF32) {
+#pragma unroll
+            for (int k = 0; k < 32; k += 4)
+              if (k < ncols) {
+                const float4 prev = *reinterpret_cast<const float4*>(outp + k);
+                f[k] += prev.x; f[k + 1] += prev.y; f[k + 2] += prev.z; f[k + 3] += prev.w;
+              }
+          } else {
+#pragma unroll
+            for (int k = 0; k < 32; k += 8)
+              if (k < ncols) {
+                const uint4 prev = *reinterpret_cast<const uint4*>(outp + k);
+                const uint32_t pw[4] = {prev.x, prev.y, prev.z, prev.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&pw[q]);
+                  f[k + 2 * q] += __low2float(h2);
+                  f[k + 2 * q + 1] += __high2float(h2);
+                }
+              }
+          }
+        }
         if constexpr (TF32) {
 #pragma unroll
           for (int k = 0; k < 32; k += 4)

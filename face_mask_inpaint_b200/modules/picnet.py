@@ -189,6 +189,8 @@ class ResEncoder(nn.Module):
         return self._distribution(self.posterior(encoded))
 
     def forward(self, img):
+        if picnet_fast.encoder_supported(self, img):   # inference: the residual blocks on the implicit-GEMM kernels
+            return picnet_fast.encoder_forward(self, img)
         out = self.block0(img)
         for i in range(self.layers - 1):
             out = getattr(self, f'encoder{i}')(out)

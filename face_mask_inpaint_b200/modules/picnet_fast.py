@@ -129,7 +129,7 @@ class _Ctx:
     def empty(self, *shape):
         return torch.empty(shape, dtype=self.dt, device=self.dev)
 
-    def weights(self, parts, o_rows, merged=False):
+    def weights(self, parts, o_rows, merged=False, i_row=None):
         """parts: [(weight tensor or conv module (possibly SpectralNorm-wrapped), transposed)] concatenated along the input
         channels -> wp [9][o_rows][sum I], or with `merged` (transposed convs, fmi_conv3x3_nhwc mode 3)
         [4 input shifts][4 parity classes * O][sum I]. A SpectralNorm conv gets its power iteration here
@@ -139,8 +139,11 @@ class _Ctx:
         o_real = shape(parts[0][0])[1] if parts[0][1] else shape(parts[0][0])[0]
         if merged:
             o_rows = 4 * o_real
-        wp = (torch.zeros if (merged or o_rows != o_real) else torch.empty)((4 if merged else 9, o_rows, itot), dtype=self.dt,
-                                                                           device=self.dev)
+        ksize = shape(parts[0][0])[-1]
+        i_row = max(itot, i_row or 0)       # the input tensor may carry zero-padded channels (3-channel images)
+        wp = (torch.zeros if (merged or o_rows != o_real or i_row != itot) else torch.empty)(
+            (4 if merged else ksize * ksize, o_rows, i_row), dtype=self.dt, device=self.dev)
+        itot = i_row
         off = 0
         for w, tr in parts:
             i = shape(w)[0] if tr else shape(w)[1]
@@ -151,12 +154,12 @@ class _Ctx:
                     raise RuntimeError("fmi_b200: SpectralNorm parameters must be contiguous fp32")
                 scratch = torch.empty(u.numel() + v.numel(), dtype=torch.float32, device=self.dev)
                 _lib.check(self.lib.fmi_conv_weight_prep_sn(_p(wb), _p(u), _p(v), _p(scratch), _p(wp), o_real, i, int(tr), o_rows,
-                                                            itot, off, int(merged), self.mma, self.st), "fmi_conv_weight_prep_sn")
+                                                            itot, off, int(merged), ksize, self.mma, self.st), "fmi_conv_weight_prep_sn")
                 off += i
                 continue
             if not torch.is_tensor(w):
                 w = _effective(w)[0]
-            _lib.check(self.lib.fmi_conv_weight_prep(_p(w), _p(wp), o_real, i, int(tr), o_rows, itot, off, int(merged), self.mma,
+            _lib.check(self.lib.fmi_conv_weight_prep(_p(w), _p(wp), o_real, i, int(tr), o_rows, itot, off, int(merged), ksize, self.mma,
                                                      self.st), "fmi_conv_weight_prep")
             off += i
         return wp
@@ -279,3 +282,113 @@ def decoder_forward(gen, x, f_e=None, mask=None, taps=None, pool_to=None):
     if pool_to is not None:
         image = torch.nn.functional.adaptive_avg_pool2d(image, pool_to)
     return image
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# ResEncoder (network.py:73-172) on the same kernels: ResBlockEncoderOptimized / ResBlock with norm 'none'
+# (base_function.py:207-305). Per block:  a2 = lrelu(conv1(a1) + b1) (activation fused into the GEMM epilogue: conv1's raw
+# output has no other reader), y = bypass1x1(x) + bs, y += conv2(a2) + b2 (residual sum in the epilogue), then AvgPool2d(2)
+# of the SUM for the 'down' blocks and the first block — pooling is linear and commutes with the 1x1 shortcut conv, so
+# pool(main) + pool(shortcut) (:267) and pool(main) + bypass(pool(x)) (:300-303) are both pool(main + bypass(x)).
+# ------------------------------------------------------------------------------------------------------------------------
+def _enc_block_layout(blk):
+    """(pre_activation, slope, pooled) or None. `model` is [act, conv1, act, conv2] (ResBlock, norm none) or
+    [conv1, act, conv2, AvgPool2d] (ResBlockEncoderOptimized, norm none)."""
+    mods = list(blk.model)
+    pool = lambda m: isinstance(m, nn.AvgPool2d) and m.kernel_size in (2, (2, 2)) and m.stride in (2, (2, 2))
+    if len(mods) == 4 and _slope(mods[0]) is not None and _slope(mods[2]) is not None:
+        post = getattr(blk, "pool", None) if getattr(blk, "sample", False) else None
+        if post is not None and not pool(post):
+            return None
+        if len(list(blk.shortcut)) != 1:
+            return None
+        return True, _slope(mods[0]), post is not None
+    if len(mods) == 4 and _slope(mods[1]) is not None and pool(mods[3]):
+        sc = list(blk.shortcut)
+        if len(sc) != 2 or not pool(sc[0]):
+            return None
+        return False, _slope(mods[1]), True
+    return None
+
+
+def _enc_blocks(enc):
+    blocks = [enc.block0] + [getattr(enc, f"encoder{i}") for i in range(enc.layers - 1)]
+    if enc.ecnoder_type == 'src':
+        heads = [getattr(enc, f"infer_prior{i}") for i in range(enc.L)] + [enc.prior]
+    elif enc.ecnoder_type == 'ref':
+        heads = [enc.posterior]
+    else:
+        return None, None
+    return blocks, heads
+
+
+def encoder_supported(enc, img) -> bool:
+    if os.environ.get("FMI_PICNET_CUDNN") == "1" or torch.is_grad_enabled() or not img.is_cuda or img.dtype != torch.float32:
+        return False
+    if not torch.backends.cudnn.allow_tf32 and ops.mma_mode(torch.float32) != _lib.MMA_BF16:   # see `supported`
+        return False
+    cached = getattr(enc, "_fmi_fast_ok", None)
+    if cached is None:
+        blocks, heads = _enc_blocks(enc)
+        ok = blocks is not None
+        for n, blk in enumerate((blocks or []) + (heads or [])):
+            lay = _enc_block_layout(blk)
+            c1, c2, bp = _plain(blk.conv1), _plain(blk.conv2), _plain(blk.bypass)
+            ok = ok and lay is not None and all(isinstance(c, nn.Conv2d) for c in (c1, c2, bp))
+            if ok:
+                ok = (c1.kernel_size == (3, 3) and c2.kernel_size == (3, 3) and bp.kernel_size == (1, 1)
+                      and (c1.in_channels % 32 == 0 or (n == 0 and c1.in_channels <= 32))
+                      and all(c.out_channels % 32 == 0 and (c.out_channels <= 256 or c.out_channels % 256 == 0) for c in (c1, c2)))
+        enc._fmi_fast_ok = cached = bool(ok)
+    return cached
+
+
+def _res_block(k, blk, x, cbuf, b, h, w, exact_out=False):
+    """One encoder-style residual block on x [B,h,w,cbuf] (operand type; channels beyond the conv's in_channels are zero).
+    Returns (y [B,h',w',co], co, h', w')."""
+    pre_act, slope, pooled = _enc_block_layout(blk)
+    c1, c2, bp = _plain(blk.conv1), _plain(blk.conv2), _plain(blk.bypass)
+    b1, b2, bs = (None if c.bias is None else c.bias.detach().float().contiguous() for c in (c1, c2, bp))
+    ch, co = c1.out_channels, c2.out_channels
+    a1 = x
+    if pre_act:
+        a1 = k.empty(b, h, w, cbuf)
+        k.norm_act(x.data_ptr(), cbuf, a1.data_ptr(), cbuf, None, b, cbuf, h * w, slope)
+    a2 = k.empty(b, h, w, ch)
+    k.conv(a1.data_ptr(), cbuf, k.weights([(blk.conv1, False)], ch, i_row=cbuf), b1, a2.data_ptr(), ch, 0, None, 0, b, cbuf, ch, h, w,
+           0, 1, slope)
+    y = k.empty(b, h, w, co)
+    k.conv(x.data_ptr(), cbuf, k.weights([(blk.bypass, False)], co, i_row=cbuf), bs, y.data_ptr(), co, 0, None, 0, b, cbuf, co, h, w,
+           4, 2, round_y=0)
+    k.conv(a2.data_ptr(), ch, k.weights([(blk.conv2, False)], co), b2, y.data_ptr(), co, 0, None, 0, b, ch, co, h, w, 0, 12,
+           round_y=0 if (pooled or exact_out) else 1)
+    if pooled:
+        yp = k.empty(b, h // 2, w // 2, co)
+        _lib.check(k.lib.fmi_avgpool2_nhwc(y.data_ptr(), co, yp.data_ptr(), co, b, co, h, w, 0 if exact_out else 1, k.mma, k.st),
+                   "fmi_avgpool2_nhwc")
+        return yp, co, h // 2, w // 2
+    return y, co, h, w
+
+
+def encoder_forward(enc, img):
+    """ResEncoder.forward (network.py:133-172): returns ([mu, softplus(std)], features) with NCHW fp32 tensors."""
+    k = _Ctx(img.device)
+    b, c_img, h, w = img.shape
+    if h % (2 ** ((enc.layers + 1) // 2)) or w % (2 ** ((enc.layers + 1) // 2)):
+        raise RuntimeError("fmi_b200: encoder input size must be divisible by its total down-sampling factor")
+    blocks, heads = _enc_blocks(enc)
+    cbuf = 32                                        # the image's channels zero-padded to one 128-byte fp32 row
+    x = torch.zeros((b, h, w, cbuf), dtype=k.dt, device=img.device)
+    _lib.check(k.lib.fmi_nchw_to_nhwc_slice(_p(img.contiguous()), x.data_ptr(), b, c_img, h, w, cbuf, _lib.F32, 1, k.mma, k.st),
+               "fmi_nchw_to_nhwc_slice")
+    for n, blk in enumerate(blocks):
+        x, cbuf, h, w = _res_block(k, blk, x, cbuf, b, h, w, exact_out=n == len(blocks) - 1)
+    feats = torch.empty((b, cbuf, h, w), dtype=torch.float32, device=img.device)
+    _lib.check(k.lib.fmi_nhwc_to_nchw(x.data_ptr(), _p(feats), b, cbuf, h, w, k.mma, _lib.F32, k.st), "fmi_nhwc_to_nchw")
+    o = x
+    for n, blk in enumerate(heads):
+        o, co, _, _ = _res_block(k, blk, o, cbuf if n == 0 else co, b, h, w, exact_out=n == len(heads) - 1)
+    dist = torch.empty((b, co, h, w), dtype=torch.float32, device=img.device)
+    _lib.check(k.lib.fmi_nhwc_to_nchw(o.data_ptr(), _p(dist), b, co, h, w, k.mma, _lib.F32, k.st), "fmi_nhwc_to_nchw")
+    mu, std = torch.split(dist, enc.z_nc, dim=1)
+    return [mu, torch.nn.functional.softplus(std)], feats

@@ -228,6 +228,14 @@ def _install_picnet_decoder():
 
     net.ResGenerator.forward = res_generator_forward
     net.ResGenerator._fmi_pool_to = True
+    ref_enc_forward = net.ResEncoder.forward
+
+    def res_encoder_forward(self, img):                        # network.py:133-172
+        if picnet_fast.encoder_supported(self, img):
+            return picnet_fast.encoder_forward(self, img)
+        return ref_enc_forward(self, img)
+
+    net.ResEncoder.forward = res_encoder_forward
 
 
 def _blend(src, ref, full_mask):

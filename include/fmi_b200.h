@@ -245,18 +245,19 @@ int fmi_torgb_bwd_nhwc(const void* x, const float* drgb, const float* rgb_w, voi
  * pixels, so a tensor may be a channel slice of a wider buffer. */
 
 /* wp[t][o][i_off + i] = weight[o,i,t] (Conv2d layout [O,I,3,3], transposed = 0) or weight[i,o,t] (ConvTranspose2d
- *   layout [I,O,3,3], transposed = 1) in the operand type; wp is [9][O_rows][I_row], rows / columns not written stay as
+ *   layout [I,O,3,3], transposed = 1) in the operand type; wp is [9][O_rows][I_row] (ksize = 3; [1][O_rows][I_row] for the
+ *   1x1 convs of the ResBlock shortcuts, ksize = 1), rows / columns not written stay as
  *   the caller initialised them (zero). Writing two weights at different i_off concatenates them along the input
  *   channels. merged = 1 (transposed only, O_rows = 4*O): the layout of fmi_conv3x3_nhwc mode 3, wp [4][4*O][I_row] with
  *   slab = input shift 2*dy + dx and row = (2*py + px)*O + o. weight is the effective fp32 weight (SpectralNorm already applied: w_bar / sigma, external_function.py:55-57). */
 int fmi_conv_weight_prep(const float* weight, void* wp, int O, int I, int transposed, int O_rows, int I_row, int i_off,
-                         int merged, int mma, void* stream);
+                         int merged, int ksize, int mma, void* stream);
 
 /* The same for a SpectralNorm-wrapped conv (external_function.py:16-72): one power iteration on (w_bar, u, v) — u [Hh] and
  *   v [Wd] are updated in place as SpectralNorm._update_u_v does (Hh = w_bar.shape[0], Wd = numel / Hh) — and wp receives
  *   w_bar / sigma, sigma = u . (W v). scratch: (Wd + Hh) floats. */
 int fmi_conv_weight_prep_sn(const float* w_bar, float* u, float* v, float* scratch, void* wp, int O, int I, int transposed,
-                            int O_rows, int I_row, int i_off, int merged, int mma, void* stream);
+                            int O_rows, int I_row, int i_off, int merged, int ksize, int mma, void* stream);
 
 /* NCHW (dtype) -> NHWC operand type into a channel slice: y[b, p, c] at y + (b*H*W + p) * y_pixel_stride + c. */
 int fmi_nchw_to_nhwc_slice(const void* x, void* y, int B, int C, int H, int W, int64_t y_pixel_stride, int dtype,
@@ -271,6 +272,10 @@ int fmi_instnorm_stats_nhwc(const void* x, int64_t x_pixel_stride, const float* 
 int fmi_norm_act_nhwc(const void* x, int64_t x_pixel_stride, void* y, int64_t y_pixel_stride, const float* scale_shift,
                       int B, int C, int HW, float slope, int mma, void* stream);
 
+/* nn.AvgPool2d(2, 2) on NHWC operand-type tensors (base_function.py:238-239, 290-298): y [B,H/2,W/2,C]. */
+int fmi_avgpool2_nhwc(const void* x, int64_t x_pixel_stride, void* y, int64_t y_pixel_stride, int B, int C, int H, int W,
+                      int round_y, int mma, void* stream);
+
 /* ReflectionPad2d(1): fills the one-pixel border of y [B,H+2,W+2,C] from its interior. */
 int fmi_reflect_border_nhwc(void* y, int B, int C, int H, int W, int mma, void* stream);
 
@@ -279,6 +284,8 @@ int fmi_reflect_border_nhwc(void* y, int B, int C, int H, int W, int mma, void* 
  *   mode 1: Conv2d(3, stride 1, padding 0) on a pre-padded input        x [B,H+2,W+2,*]  -> y [B,H,W,*]
  *   mode 2: ConvTranspose2d(3, stride 2, padding 1, output_padding 1)   x [B,H,W,*]      -> y [B,2H,2W,*]
  *   mode 3: mode 2 as one GEMM over the 4 output-parity classes (O <= 64, wp from fmi_conv_weight_prep(merged = 1))
+ *   mode 4: Conv2d(1, stride 1, padding 0), wp [1][O][I]
+ *   act + 10 (act 2 only): y += acc + bias, the residual sum of a ResBlock onto the shortcut already stored in y
  *   wp [9][O][I] from fmi_conv_weight_prep (O a multiple of 32: pad with zero rows); bias [O] fp32 or NULL;
  *   act 2: y = acc + bias;  act 1: leaky_relu(acc + bias, slope);  act 3: tanh(acc + bias).
  *   round_y: 1 = y rounded to the operand type (tf32 / bf16); 0 (TF32 mode only) = exact fp32 values, for tensors that

@@ -175,11 +175,77 @@ def test_spectral_norm_weight_prep_matches_oracle(transposed, shape):
     wb_d, u_d, v_d = w_bar.cuda(), u.cuda(), v.cuda()
     scratch = torch.empty(u.numel() + v.numel(), dtype=torch.float32, device="cuda")
     _lib.check(k.lib.fmi_conv_weight_prep_sn(wb_d.data_ptr(), u_d.data_ptr(), v_d.data_ptr(), scratch.data_ptr(), wp.data_ptr(),
-                                             o, i, int(transposed), o_rows, i, 0, 0, k.mma, k.st), "fmi_conv_weight_prep_sn")
+                                             o, i, int(transposed), o_rows, i, 0, 0, 3, k.mma, k.st), "fmi_conv_weight_prep_sn")
     want = (w_eff.permute(2, 3, 1, 0) if transposed else w_eff.permute(2, 3, 0, 1)).reshape(9, o, i)
     assert rel_err(wp[:, :o].cpu(), want) <= 5e-4            # tf32 rounding of the stored weights (2^-11)
     assert rel_err(u_d.cpu(), u_new) <= 1e-5 and rel_err(v_d.cpu(), v_new) <= 1e-5
     assert float(wp[:, o:].abs().max()) == 0.0 if o_rows > o else True
+
+
+@pytest.mark.parametrize("mma", [0, 1])
+def test_conv1x1_and_residual_sum_epilogue(mma):
+    """mode 4 (1x1 conv) writes the shortcut, a 3x3 conv with act + 10 adds the main path onto it (ResBlock sum,
+    base_function.py:262-268), then AvgPool2d(2) of the sum."""
+    from face_mask_inpaint_b200 import _lib
+    g = torch.Generator().manual_seed(9)
+    b, cin, ch, co, h, w = 2, 64, 32, 96, 12, 20
+    x, a2 = torch.randn(b, cin, h, w, generator=g), torch.randn(b, ch, h, w, generator=g)
+    wb = torch.randn(co, cin, 1, 1, generator=g) / cin ** 0.5
+    w2 = torch.randn(co, ch, 3, 3, generator=g) / (ch * 9) ** 0.5
+    bb, b2 = 0.1 * torch.randn(co, generator=g), 0.1 * torch.randn(co, generator=g)
+    F = torch.nn.functional
+    want = F.conv2d(x, wb, bb) + F.conv2d(a2, w2, b2, padding=1)
+    k = _ctx(mma)
+    xin, ain = _to_nhwc(k, x.cuda()), _to_nhwc(k, a2.cuda())
+    y = torch.full((b, h, w, co), float("nan"), dtype=k.dt, device="cuda")
+    k.conv(xin.data_ptr(), cin, k.weights([(wb.cuda().contiguous(), False)], co), bb.cuda(), y.data_ptr(), co, 0, None, 0, b, cin,
+           co, h, w, 4, 2, round_y=0)
+    short = y.float().permute(0, 3, 1, 2).cpu()
+    assert rel_err(short, F.conv2d(x, wb, bb)) <= TOL[mma]
+    k.conv(ain.data_ptr(), ch, k.weights([(w2.cuda().contiguous(), False)], co), b2.cuda(), y.data_ptr(), co, 0, None, 0, b, ch, co,
+           h, w, 0, 12, round_y=0)
+    assert rel_err(y.float().permute(0, 3, 1, 2).cpu(), want) <= TOL[mma]
+    yp = torch.empty((b, h // 2, w // 2, co), dtype=k.dt, device="cuda")
+    _lib.check(k.lib.fmi_avgpool2_nhwc(y.data_ptr(), co, yp.data_ptr(), co, b, co, h, w, 0, k.mma, k.st), "fmi_avgpool2_nhwc")
+    assert rel_err(yp.float().permute(0, 3, 1, 2).cpu(), F.avg_pool2d(y.float().permute(0, 3, 1, 2).cpu(), 2)) <= (1e-6 if mma == 0 else 4e-3)
+
+
+@pytest.mark.parametrize("kind", ["src_encoder", "ref_encoder"])
+def test_res_encoder_kernel_path_matches_cudnn_fp32(kind):
+    """ResEncoder.forward (network.py:133-172; 5 trunk blocks + 7 / 1 distribution-head blocks) on the kernels vs the same
+    module on cuDNN in strict fp32, same weights, same fresh SpectralNorm state."""
+    import copy
+    from face_mask_inpaint_b200 import _lib
+    from face_mask_inpaint_b200.modules.picnet import build_picnet_ref
+    from golden_util import fill_by_name
+    base = getattr(fill_by_name(build_picnet_ref()).eval(), kind)
+    img = torch.rand(2, 3, 64, 96, generator=torch.Generator().manual_seed(3)).cuda()
+    old = torch.backends.cudnn.allow_tf32
+
+    def run(force_cudnn, tf32):
+        m = copy.deepcopy(base).cuda()
+        os.environ["FMI_PICNET_CUDNN"] = "1" if force_cudnn else "0"
+        torch.backends.cudnn.allow_tf32 = tf32
+        n0 = _lib.load().fmi_kernel_launch_count()
+        with torch.no_grad():
+            (mu, std), feats = m(img)
+        return mu, std, feats, _lib.load().fmi_kernel_launch_count() - n0, m
+
+    try:
+        t_mu, t_std, t_f, n_c, m_c = run(True, False)
+        r_mu, r_std, r_f, _, _ = run(True, True)
+        o_mu, o_std, o_f, n_o, m_o = run(False, True)
+    finally:
+        os.environ.pop("FMI_PICNET_CUDNN", None)
+        torch.backends.cudnn.allow_tf32 = old
+    assert n_c == 0 and n_o > 40
+    assert o_f.shape == t_f.shape == (2, 128, 8, 12) and o_mu.shape == t_mu.shape == (2, 128, 8, 12)
+    for got, ref_gpu, want, name in ((o_f, r_f, t_f, "features"), (o_mu, r_mu, t_mu, "mu"), (o_std, r_std, t_std, "std")):
+        e, e_ref = rel_err(got, want), rel_err(ref_gpu, want)
+        assert e <= 1.5 * e_ref + 1e-3, (name, e, e_ref)
+    # the power iteration advanced u / v exactly as the module's own forward does
+    u_c, u_o = m_c.block0.conv1.module.weight_u, m_o.block0.conv1.module.weight_u
+    assert rel_err(u_o, u_c) <= 1e-5
 
 
 def _mirror_from_golden():
