@@ -169,8 +169,9 @@ def run_reference(args, rank, world):
 def whole_model_throughput(dev, world, barrier, max_over_ranks):
     """images/sec of the two generators BASELINE.json's metric names, forward only, synthetic inputs resident on the
     device, per-GPU batch fixed (weak scaling), max over ranks: PICNet-ref 256^2 (modules/picnet.py, per-GPU batch 4, fp32
-    contract) and RefpSp 1024^2 (modules/psp.py, per-GPU batch 8, bf16 operands). The conv trunks of both are cuDNN (out of
-    the kernel scope); attention, compositing and the whole StyleGAN2 decoder are this package's kernels.
+    contract) and RefpSp 1024^2 (modules/psp.py, per-GPU batch 8, bf16 operands). PICNet: attention, compositing and the
+    encoder / decoder conv blocks are this package's kernels. RefpSp: attention, compositing and the whole
+    StyleGAN2 decoder are; its IR-SE50 trunk is cuDNN (8f rank 2, not started). Each forward is one CUDA-graph replay.
     Failures are reported, not raised: the bench line above does not depend on this block."""
     out = {}
     iters = 5
@@ -206,9 +207,11 @@ def whole_model_throughput(dev, world, barrier, max_over_ranks):
             out["picnet_ref_256"] = {"value": world * b / (ms * 1e-3), "unit": "img/s", "per_gpu_batch": b, "ms_per_step": ms,
                                      "launch": "one CUDA-graph replay per forward (graphs.CapturedForward)",
                                      "eager_ms_per_step": ms_eager, "eager_value": world * b / (ms_eager * 1e-3),
-                                     "precision": "fp32 I/O, TF32 attention operands, cuDNN convs (TF32 allowed)",
+                                     "precision": "fp32 I/O; TF32 tensor-core operands (attention and conv blocks), fp32 "
+                                                  "accumulation, fp32 Output conv",
                                      "what": "ReferenceFill forward: 2 encoders, ExampleGuidedAttention@32^2, decoder with "
-                                             "Auto_Attn@128^2 up to 1024^2, pooled to 256^2"}
+                                             "Auto_Attn@128^2 up to 1024^2, pooled to 256^2; encoder / decoder conv blocks on "
+                                             "this package's implicit-GEMM kernels (SURVEY 8f rank 1), z->f ResBlock on cuDNN"}
             del net, fwd
             from face_mask_inpaint_b200.modules.psp import pSp, refpsp_opts
             os.environ["FMI_PRECISION"] = "bf16"

@@ -339,7 +339,8 @@ extern "C" int fmi_conv3x3_nhwc(const void* x, int64_t x_pixel_stride, const voi
   const uint32_t epa = 128 / esz;
   const CUtensorMapDataType dt = tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   const int IH = mode == 1 ? H + 2 : H, IW = mode == 1 ? W + 2 : W;   // input extents
-  const int OH = mode >= 2 ? 2 * H : H, OW = mode >= 2 ? 2 * W : W;
+  const bool up = mode == 2 || mode == 3;
+  const int OH = up ? 2 * H : H, OW = up ? 2 * W : W;
 
   ConvGemmParams p{};
   p.B = B; p.I = I; p.O = O; p.H = IH; p.W = IW; p.T = 9;

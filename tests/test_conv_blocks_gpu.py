@@ -119,14 +119,15 @@ def test_output_conv_tanh_kernel_matches_oracle(mma, shape):
     img = torch.empty((b, o, h, w), dtype=torch.float32, device="cuda")
     pooled = torch.empty((b, o, h // 4, w // 4), dtype=torch.float32, device="cuda") if pool_ok else None
     scratch = torch.empty(27 * c + 4, dtype=torch.float32, device="cuda")
-    _lib.check(k.lib.fmi_output_conv_tanh(xin.data_ptr(), wt.cuda().data_ptr(), bias.cuda().data_ptr(), img.data_ptr(),
+    wt_d, bias_d = wt.cuda(), bias.cuda()       # keep the device copies alive: the launches are asynchronous
+    _lib.check(k.lib.fmi_output_conv_tanh(xin.data_ptr(), wt_d.data_ptr(), bias_d.data_ptr(), img.data_ptr(),
                                           None if pooled is None else pooled.data_ptr(), scratch.data_ptr(), b, c, o, h, w,
                                           k.mma, k.st), "fmi_output_conv_tanh")
     assert rel_err(img.cpu(), want) <= 2e-5, rel_err(img.cpu(), want)   # fp32 arithmetic on identical inputs
     if pool_ok:
         assert rel_err(pooled.cpu(), torch.nn.functional.avg_pool2d(want, 4)) <= 2e-5
         only = torch.empty_like(pooled)                                # pooled output alone (no full-size image written)
-        _lib.check(k.lib.fmi_output_conv_tanh(xin.data_ptr(), wt.cuda().data_ptr(), bias.cuda().data_ptr(), None, only.data_ptr(),
+        _lib.check(k.lib.fmi_output_conv_tanh(xin.data_ptr(), wt_d.data_ptr(), bias_d.data_ptr(), None, only.data_ptr(),
                                               scratch.data_ptr(), b, c, o, h, w, k.mma, k.st), "fmi_output_conv_tanh")
         assert torch.equal(only, pooled)
 
