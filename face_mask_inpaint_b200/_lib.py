@@ -58,6 +58,7 @@ PROTOTYPES = {
                                         _vp]),
     "fmi_conv_weight_prep": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "fmi_conv_weight_prep_sn": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "fmi_conv_weight_prep_sn_batch": (_i, [_vp, _i, _i, _i, _i, _i, _vp]),
     "fmi_nchw_to_nhwc_slice": (_i, [_vp, _vp, _i, _i, _i, _i, _i64, _i, _i, _i, _vp]),
     "fmi_instnorm_stats_nhwc": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _vp]),
     "fmi_norm_act_nhwc": (_i, [_vp, _i64, _vp, _i64, _vp, _i, _i, _i, _f, _i, _vp]),

@@ -757,3 +757,123 @@ extern "C" int fmi_avgpool2_nhwc(const void* x, int64_t x_pixel_stride, void* y,
                                                                             (__nv_bfloat16*)y, y_pixel_stride, C, H, W);
   return fmi_launched("avgpool2");
 }
+
+// =====================================================================================================================
+// Batched SpectralNorm + weight layout: the power iterations and re-layouts of ALL convolutions of a network do not depend
+// on activations, so they run as three launches at the start of the forward (blockIdx.y = convolution) instead of three
+// small launches per convolution (69 convs in the PICNet generator: 207 launches, 1.9 ms of mostly idle GPU).
+// =====================================================================================================================
+struct FmiSnPrepDesc {           // mirrored by picnet_fast._WeightPlan (struct format "6Q12i", 96 bytes)
+  const float* w_bar;
+  float* u;
+  float* v;
+  float* v_part;                 // [4][Wd] partial products of W^T u (row quarters), summed in fixed order
+  float* u_raw;                  // [Hh]
+  void* wp;
+  int O, I, transposed, O_rows, I_row, i_off, merged, T, Hh, Wd, pad0, pad1;
+};
+
+namespace {
+constexpr int SN_ZSPLIT = 4;
+
+__global__ void __launch_bounds__(128) sn_batch_wt_u_kernel(const FmiSnPrepDesc* __restrict__ descs) {
+  const FmiSnPrepDesc d = descs[blockIdx.y];
+  const int j = blockIdx.x * 128 + threadIdx.x;
+  if (j >= d.Wd) return;
+  const int rows = (d.Hh + SN_ZSPLIT - 1) / SN_ZSPLIT;
+  const int i0 = blockIdx.z * rows, i1 = min(d.Hh, i0 + rows);
+  float a[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) a[q] = 0.f;
+  int i = i0;
+  for (; i + 8 <= i1; i += 8) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) a[q] = fmaf(d.w_bar[(int64_t)(i + q) * d.Wd + j], d.u[i + q], a[q]);
+  }
+  for (; i < i1; ++i) a[0] = fmaf(d.w_bar[(int64_t)i * d.Wd + j], d.u[i], a[0]);
+  d.v_part[(int64_t)blockIdx.z * d.Wd + j] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+}
+
+__global__ void __launch_bounds__(256) sn_batch_w_v_kernel(const FmiSnPrepDesc* __restrict__ descs) {
+  const FmiSnPrepDesc d = descs[blockIdx.y];
+  if ((int)blockIdx.x * 8 >= d.Hh) return;
+  __shared__ float red[8];
+  extern __shared__ float sv[];     // v_raw of this convolution (Wd floats)
+  float q = 0.f;
+  for (int j = threadIdx.x; j < d.Wd; j += 256) {
+    const float t = (d.v_part[j] + d.v_part[d.Wd + j]) + (d.v_part[2 * (int64_t)d.Wd + j] + d.v_part[3 * (int64_t)d.Wd + j]);
+    sv[j] = t;
+    q = fmaf(t, t, q);
+  }
+  const float inv = 1.f / (sqrtf(block_sum_256(q, red)) + 1e-12f);   // block_sum_256 synchronises: sv is complete
+  if (blockIdx.x == 0)
+    for (int j = threadIdx.x; j < d.Wd; j += 256) d.v[j] = sv[j] * inv;
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= d.Hh) return;
+  float a0 = 0.f, a1 = 0.f;
+  int j = lane;
+  for (; j + 32 < d.Wd; j += 64) {
+    a0 = fmaf(d.w_bar[(int64_t)row * d.Wd + j], sv[j], a0);
+    a1 = fmaf(d.w_bar[(int64_t)row * d.Wd + j + 32], sv[j + 32], a1);
+  }
+  if (j < d.Wd) a0 = fmaf(d.w_bar[(int64_t)row * d.Wd + j], sv[j], a0);
+  const float a = warp_sum(a0 + a1) * inv;
+  if (lane == 0) d.u_raw[row] = a;
+}
+
+template <typename OT, bool ROUND_TF32>
+__global__ void __launch_bounds__(256) sn_batch_prep_kernel(const FmiSnPrepDesc* __restrict__ descs) {
+  const FmiSnPrepDesc d = descs[blockIdx.y];
+  const int total = d.O * d.I * d.T;
+  if ((int)blockIdx.x * 256 >= total) return;
+  __shared__ float red[8];
+  float q = 0.f;
+  for (int i = threadIdx.x; i < d.Hh; i += 256) q = fmaf(d.u_raw[i], d.u_raw[i], q);
+  const float n2 = block_sum_256(q, red);
+  const float inv = 1.f / (sqrtf(n2) + 1e-12f);
+  const float sigma = n2 * inv;
+  if (blockIdx.x == 0)
+    for (int i = threadIdx.x; i < d.Hh; i += 256) d.u[i] = d.u_raw[i] * inv;
+  OT* wp = (OT*)d.wp;
+  for (int e = blockIdx.x * 256 + threadIdx.x; e < total; e += gridDim.x * 256) {
+    const int t = e % d.T, r = e / d.T;
+    int o, i;
+    if (d.transposed) { i = r / d.O; o = r - i * d.O; }
+    else { o = r / d.I; i = r - o * d.I; }
+    float v = d.w_bar[e] / sigma;
+    if (ROUND_TF32) v = __uint_as_float(f32_to_tf32_rna(v));
+    int slab = t, row = o;
+    if (d.merged) {
+      const int ky = t / 3, kx = t - ky * 3;
+      slab = (ky == 0 ? 2 : 0) + (kx == 0 ? 1 : 0);
+      row = ((ky != 1 ? 2 : 0) + (kx != 1 ? 1 : 0)) * d.O + o;
+    }
+    wp[((int64_t)slab * d.O_rows + row) * d.I_row + d.i_off + i] = from_f32<OT>(v);
+  }
+}
+}  // namespace
+
+// descs: n FmiSnPrepDesc in DEVICE memory (include/fmi_b200.h documents the layout); max_wd / max_hh / max_elems: the largest
+// Wd, Hh and O*I*T among them. Same results as n calls of fmi_conv_weight_prep_sn.
+extern "C" int fmi_conv_weight_prep_sn_batch(const void* descs, int n, int max_wd, int max_hh, int max_elems, int mma,
+                                             void* stream) {
+  FMI_REQUIRE(mma == FMI_MMA_TF32 || mma == FMI_MMA_BF16, "conv_weight_prep_sn_batch: bad mma");
+  if (n == 0) return FMI_OK;
+  FMI_REQUIRE(descs && n > 0 && n <= 65535 && max_wd >= 1 && max_hh >= 1 && max_elems >= 1 && max_wd <= 12288,
+              "conv_weight_prep_sn_batch: bad arguments");
+  static_assert(sizeof(FmiSnPrepDesc) == 96, "descriptor layout");
+  cudaStream_t st = (cudaStream_t)stream;
+  const FmiSnPrepDesc* d = (const FmiSnPrepDesc*)descs;
+  sn_batch_wt_u_kernel<<<dim3((max_wd + 127) / 128, n, SN_ZSPLIT), 128, 0, st>>>(d);
+  int rc = fmi_launched("sn_batch_wt_u");
+  if (rc) return rc;
+  sn_batch_w_v_kernel<<<dim3((max_hh + 7) / 8, n), 256, (size_t)max_wd * sizeof(float), st>>>(d);
+  rc = fmi_launched("sn_batch_w_v");
+  if (rc) return rc;
+  int gx = (max_elems + 256 * 8 - 1) / (256 * 8);
+  if (gx < 1) gx = 1;
+  if (mma == FMI_MMA_TF32) sn_batch_prep_kernel<float, true><<<dim3(gx, n), 256, 0, st>>>(d);
+  else sn_batch_prep_kernel<__nv_bfloat16, false><<<dim3(gx, n), 256, 0, st>>>(d);
+  return fmi_launched("sn_batch_prep");
+}

@@ -118,13 +118,102 @@ def supported(gen, x) -> bool:
     return cached
 
 
+class _WeightPlan:
+    """All SpectralNorm power iterations + weight re-layouts of one network as three launches at the start of its forward
+    (fmi_conv_weight_prep_sn_batch). The first forward runs them one convolution at a time and records, in call order, what
+    `_Ctx.weights` was asked for; `finalize` then allocates persistent wp / scratch buffers and the device descriptor table.
+    Later forwards call `run()` once and get the buffers back in the same order."""
+
+    def __init__(self):
+        self.entries, self.ok, self.ready, self.cursor = [], True, False, 0
+
+    def record(self, parts, o_rows, merged, i_row, ksize, shape, dtype):
+        if not all(isinstance(w, SpectralNorm) and w.power_iterations == 1 for w, _ in parts):
+            self.ok = False
+        self.entries.append((parts, o_rows, merged, i_row, ksize, shape, dtype))
+
+    def finalize(self, dev, mma):
+        import struct
+        if not self.ok or not self.entries or os.environ.get("FMI_SN_TORCH") == "1" or os.environ.get("FMI_SN_BATCH") == "0":
+            self.ok = False
+            return
+        self.wps, rows, scratch_floats = [], [], 0
+        for parts, o_rows, merged, i_row, ksize, shape, dtype in self.entries:
+            wp = torch.zeros(shape, dtype=dtype, device=dev)
+            self.wps.append(wp)
+            off = 0
+            o_real = None
+            for w, tr in parts:
+                m = w.module
+                wb = m.weight_bar.data
+                o, i = (wb.shape[1], wb.shape[0]) if tr else (wb.shape[0], wb.shape[1])
+                hh, wd = wb.shape[0], wb.numel() // wb.shape[0]
+                rows.append([m, wp, o, i, int(tr), o_rows, i_row, off, int(merged), ksize * ksize, hh, wd, scratch_floats])
+                scratch_floats += 4 * wd + hh
+                off += i
+        self.scratch = torch.empty(scratch_floats, dtype=torch.float32, device=dev)
+        blob = b""
+        self.ptrs = []
+        for m, wp, o, i, tr, o_rows, i_row, off, merged, t, hh, wd, soff in rows:
+            wb, u, v = m.weight_bar.data, m.weight_u.data, m.weight_v.data
+            if not (wb.is_contiguous() and u.is_contiguous() and v.is_contiguous() and wb.dtype == torch.float32
+                    and wb.device == wp.device):
+                self.ok = False
+                return
+            base = self.scratch.data_ptr() + 4 * soff
+            blob += struct.pack("6Q12i", wb.data_ptr(), u.data_ptr(), v.data_ptr(), base, base + 16 * wd, wp.data_ptr(), o, i, tr,
+                                o_rows, i_row, off, merged, t, hh, wd, 0, 0)
+            self.ptrs.append((m, wb.data_ptr(), u.data_ptr(), v.data_ptr()))
+        self.table = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(dev)
+        self.n = len(rows)
+        self.max_wd = max(r[11] for r in rows)
+        self.max_hh = max(r[10] for r in rows)
+        self.max_elems = max(r[2] * r[3] * r[9] for r in rows)
+        self.mma = mma
+        self.ready = self.max_wd <= 12288
+
+    def valid(self):
+        return all(m.weight_bar.data_ptr() == a and m.weight_u.data_ptr() == b and m.weight_v.data_ptr() == c
+                   for m, a, b, c in self.ptrs)
+
+    def run(self, lib, st):
+        _lib.check(lib.fmi_conv_weight_prep_sn_batch(self.table.data_ptr(), self.n, self.max_wd, self.max_hh, self.max_elems,
+                                                     self.mma, st), "fmi_conv_weight_prep_sn_batch")
+        self.cursor = 0
+
+    def next(self):
+        wp = self.wps[self.cursor]
+        self.cursor += 1
+        return wp
+
+
 class _Ctx:
-    def __init__(self, dev):
+    def __init__(self, dev, owner=None):
         self.lib = _lib.load()
         self.mma = ops.mma_mode(torch.float32)
         self.dt = torch.float32 if self.mma == _lib.MMA_TF32 else torch.bfloat16
         self.dev = dev
         self.st = ops._stream()
+        # weight plan of the owning network (per operand type and device); None = prepare weights call by call
+        self.plan = self.recording = None
+        if owner is not None:
+            plans = owner.__dict__.setdefault("_fmi_weight_plans", {})
+            key = (self.mma, dev.index)
+            plan = plans.get(key)
+            if plan is not None and plan.ready and not plan.valid():    # parameters were moved / replaced: rebuild
+                plan = None
+            if plan is None:
+                plan = plans[key] = _WeightPlan()
+                self.recording = plan
+            elif plan.ready:
+                plan.run(self.lib, self.st)
+                self.plan = plan
+
+    def finish(self):
+        """End of the owner's forward: turn the recorded weight requests into the batched plan."""
+        if self.recording is not None:
+            self.recording.finalize(self.dev, self.mma)
+            self.recording = None
 
     def empty(self, *shape):
         return torch.empty(shape, dtype=self.dt, device=self.dev)
@@ -141,8 +230,13 @@ class _Ctx:
             o_rows = 4 * o_real
         ksize = shape(parts[0][0])[-1]
         i_row = max(itot, i_row or 0)       # the input tensor may carry zero-padded channels (3-channel images)
-        wp = (torch.zeros if (merged or o_rows != o_real or i_row != itot) else torch.empty)(
-            (4 if merged else ksize * ksize, o_rows, i_row), dtype=self.dt, device=self.dev)
+        if self.plan is not None:
+            return self.plan.next()         # prepared by fmi_conv_weight_prep_sn_batch at the start of this forward
+        wshape = (4 if merged else ksize * ksize, o_rows, i_row)
+        if self.recording is not None:
+            self.recording.record(parts, o_rows, merged, i_row, ksize, wshape, self.dt)
+        wp = (torch.zeros if (merged or o_rows != o_real or i_row != itot) else torch.empty)(wshape, dtype=self.dt,
+                                                                                            device=self.dev)
         itot = i_row
         off = 0
         for w, tr in parts:
@@ -187,7 +281,7 @@ def decoder_forward(gen, x, f_e=None, mask=None, taps=None, pool_to=None):
     Returns the image [B, 3, H * 2^layers, W * 2^layers] fp32. `taps` (diagnostics, tests/diag_picnet_blocks.py): a dict that
     receives an fp32 NCHW copy of every block output. `pool_to` = (h, w): return AdaptiveAvgPool2d(pool_to) of the image
     instead (modules/model.py:111), fused into the Output kernel when it is an exact 4x4 mean."""
-    k = _Ctx(x.device)
+    k = _Ctx(x.device, owner=gen)
     esz = 4 if k.mma == _lib.MMA_TF32 else 2
     b, c_in, h, w = x.shape
     x = x.contiguous()
@@ -220,8 +314,9 @@ def decoder_forward(gen, x, f_e=None, mask=None, taps=None, pool_to=None):
         del h1
         # y = convT(a2) + b2 + convT_shortcut(x) + bs: one GEMM over [a2 | x]
         bias = b2 if bs is None else (bs if b2 is None else b2 + bs)
-        # narrow layers: one GEMM for the 4 parity classes (mode 3: 4/9 of the MMA instructions), else one per class (mode 2)
-        up_mode = 3 if (co <= 64 and os.environ.get("FMI_CONVT_MERGE", "1") != "0") else 2
+        # O <= 32: one GEMM for the 4 parity classes (mode 3: 4/9 of the MMA instructions; measured 0.79 vs 0.95 ms on the last block).
+        # O = 64 (N = 256, one CTA per SM) measured slower than the 4 per-class launches (0.84 vs 0.60 ms): mode 2 there
+        up_mode = 3 if (co <= int(os.environ.get("FMI_CONVT_MERGE_MAX", "32"))) else 2
         wcat = k.weights([(blk.conv2, True), (blk.bypass, True)], co, merged=up_mode == 3)
         oh, ow = 2 * h, 2 * w
         last = i == gen.layers - 1
@@ -246,6 +341,7 @@ def decoder_forward(gen, x, f_e=None, mask=None, taps=None, pool_to=None):
                 _lib.check(k.lib.fmi_output_conv_tanh(padded.data_ptr(), _p(wo), _p(bo), _p(image), _p(pooled), _p(scratch), b, co,
                                                       n_img, oh, ow, k.mma, k.st), "fmi_output_conv_tanh")
                 if fuse_pool:
+                    k.finish()
                     return pooled
             else:
                 bo_pad = None
@@ -279,6 +375,7 @@ def decoder_forward(gen, x, f_e=None, mask=None, taps=None, pool_to=None):
             if taps is not None:
                 taps[f"decoder{i}"] = nxt[..., ch_next:].float().permute(0, 3, 1, 2).contiguous()
         c_in, h, w = co, oh, ow
+    k.finish()
     if pool_to is not None:
         image = torch.nn.functional.adaptive_avg_pool2d(image, pool_to)
     return image
@@ -372,7 +469,7 @@ def _res_block(k, blk, x, cbuf, b, h, w, exact_out=False):
 
 def encoder_forward(enc, img):
     """ResEncoder.forward (network.py:133-172): returns ([mu, softplus(std)], features) with NCHW fp32 tensors."""
-    k = _Ctx(img.device)
+    k = _Ctx(img.device, owner=enc)
     b, c_img, h, w = img.shape
     if h % (2 ** ((enc.layers + 1) // 2)) or w % (2 ** ((enc.layers + 1) // 2)):
         raise RuntimeError("fmi_b200: encoder input size must be divisible by its total down-sampling factor")
@@ -390,5 +487,6 @@ def encoder_forward(enc, img):
         o, co, _, _ = _res_block(k, blk, o, cbuf if n == 0 else co, b, h, w, exact_out=n == len(heads) - 1)
     dist = torch.empty((b, co, h, w), dtype=torch.float32, device=img.device)
     _lib.check(k.lib.fmi_nhwc_to_nchw(o.data_ptr(), _p(dist), b, co, h, w, k.mma, _lib.F32, k.st), "fmi_nhwc_to_nchw")
+    k.finish()
     mu, std = torch.split(dist, enc.z_nc, dim=1)
     return [mu, torch.nn.functional.softplus(std)], feats

@@ -259,6 +259,13 @@ int fmi_conv_weight_prep(const float* weight, void* wp, int O, int I, int transp
 int fmi_conv_weight_prep_sn(const float* w_bar, float* u, float* v, float* scratch, void* wp, int O, int I, int transposed,
                             int O_rows, int I_row, int i_off, int merged, int ksize, int mma, void* stream);
 
+/* n calls of fmi_conv_weight_prep_sn as three launches (the power iterations of a network's convolutions are independent of
+ *   its activations: they run once at the start of the forward). descs: n descriptors in DEVICE memory, 96 bytes each:
+ *   { const float* w_bar; float* u; float* v; float* v_part ( 4*Wd floats ); float* u_raw ( Hh floats ); void* wp;
+ *     int O, I, transposed, O_rows, I_row, i_off, merged, T ( ksize^2 ), Hh, Wd, 0, 0; }
+ *   max_wd, max_hh, max_elems: the largest Wd, Hh and O*I*T among them (max_wd <= 12288). */
+int fmi_conv_weight_prep_sn_batch(const void* descs, int n, int max_wd, int max_hh, int max_elems, int mma, void* stream);
+
 /* NCHW (dtype) -> NHWC operand type into a channel slice: y[b, p, c] at y + (b*H*W + p) * y_pixel_stride + c. */
 int fmi_nchw_to_nhwc_slice(const void* x, void* y, int B, int C, int H, int W, int64_t y_pixel_stride, int dtype,
                            int round_y, int mma, void* stream);
