@@ -412,6 +412,16 @@ extern "C" int fmi_conv3x3_nhwc(const void* x, int64_t x_pixel_stride, const voi
     const int off = mode == 1 ? 0 : -1;   // valid conv on the padded input: taps 0..2; padding 1: taps -1..1 (TMA zero fill)
     for (int t = 0; t < 9; ++t) { p.tap_dy[t] = t / 3 + off; p.tap_dx[t] = t % 3 + off; p.tap_slab[t] = t; }
     TilePlan tp = pick_tile(p.Mh, p.Mw);
+    // halo mode (modconv_gemm.cuh): one 130-pixel TMA box per kernel row instead of three 128-pixel boxes. ncu on the
+    // 64 -> 32 @512^2 layer without it: 6.0 GB through TMA for 0.54 GB of DRAM reads, L2 throughput 64 % (max 80 %) — these
+    // fp32-operand layers are bound by L2 -> SM operand ingest. FMI_CONV_HALO=0 switches it off (A/B measurements).
+    static const bool halo_off = [] { const char* e = getenv("FMI_CONV_HALO"); return e && e[0] == '0'; }();
+    p.halo = mode == 0 && !halo_off && W >= 128 && p.n_tile <= 128;
+    if (p.halo) {
+      for (int a = 0; a < 3; ++a)
+        for (int c = 0; c < 3; ++c) p.halo_slab[a][c] = a * 3 + c;
+      tp = TilePlan{1, 130, 0, 0};
+    }
     CUtensorMap mx;
     int e = make_x_map(&mx, tp.TH, tp.TW);
     FMI_REQUIRE(e == 0, "conv3x3: cuTensorMapEncodeTiled(x) failed (%d)", e);

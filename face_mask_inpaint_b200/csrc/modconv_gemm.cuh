@@ -118,27 +118,32 @@ __global__ void __launch_bounds__(kGemmThreads, 3)
       tma_prefetch_desc(&map_x);
       tma_prefetch_desc(&map_w);
       const uint32_t bytes = (uint32_t)(p.TH * p.TW * 128 + b_stage_bytes);
-      int g = 0;
+      // ring position and parity are carried as counters: `g % stages`, `g / stages`, `it / k_chunks` with run-time
+      // divisors cost ~30 instructions each on the single issuing thread of this warp
+      int st = 0;
+      uint32_t ph = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         int b, o0, m0, n0;
         decode(t, b, o0, m0, n0);
         const int wb = p.w_shared ? 0 : b;
-        for (int it = 0; it < iters; ++it, ++g) {
-          const int st = g % p.stages;
-          const int tap = it / p.k_chunks, kc = it % p.k_chunks;
-          mbar_wait(&empty[st], ((g / p.stages) & 1) ^ 1);
+        int tap = 0, kc = 0;
+        for (int it = 0; it < iters; ++it) {
+          mbar_wait(&empty[st], ph ^ 1);
           uint8_t* sA = smem + st * stage_bytes;
+          const int tap_c = tap, kc_c = kc, st_c = st;
+          if (++kc == p.k_chunks) { kc = 0; ++tap; }
+          if (++st == p.stages) { st = 0; ph ^= 1; }
           if (p.halo) {  // `tap` is the kernel row here
-            mbar_arrive_expect_tx(&full[st], (uint32_t)(130 * 128 + 3 * b_stage_bytes));
-            tma_load_4d(sA, &map_x, &full[st], kc * EPA, n0 - 1, m0 + tap - 1, b);
+            mbar_arrive_expect_tx(&full[st_c], (uint32_t)(130 * 128 + 3 * b_stage_bytes));
+            tma_load_4d(sA, &map_x, &full[st_c], kc_c * EPA, n0 - 1, m0 + tap_c - 1, b);
             for (int dxi = 0; dxi < 3; ++dxi)
-              tma_load_2d(sA + A_HALO_BYTES + dxi * b_stage_bytes, &map_w, &full[st], kc * EPA,
-                          (wb * p.T + p.halo_slab[tap][dxi]) * p.O + o0);
+              tma_load_2d(sA + A_HALO_BYTES + dxi * b_stage_bytes, &map_w, &full[st_c], kc_c * EPA,
+                          (wb * p.T + p.halo_slab[tap_c][dxi]) * p.O + o0);
             continue;
           }
-          mbar_arrive_expect_tx(&full[st], bytes);
-          tma_load_4d(sA, &map_x, &full[st], kc * EPA, n0 + p.tap_dx[tap], m0 + p.tap_dy[tap], b + p.tap_boff[tap]);
-          tma_load_2d(sA + A_STAGE_BYTES, &map_w, &full[st], kc * EPA, (wb * p.T + p.tap_slab[tap]) * p.O + o0);
+          mbar_arrive_expect_tx(&full[st_c], bytes);
+          tma_load_4d(sA, &map_x, &full[st_c], kc_c * EPA, n0 + p.tap_dx[tap_c], m0 + p.tap_dy[tap_c], b + p.tap_boff[tap_c]);
+          tma_load_2d(sA + A_STAGE_BYTES, &map_w, &full[st_c], kc_c * EPA, (wb * p.T + p.tap_slab[tap_c]) * p.O + o0);
         }
       }
     }
@@ -148,19 +153,29 @@ __global__ void __launch_bounds__(kGemmThreads, 3)
       const uint32_t idesc = make_idesc(TF32 ? KIND_TF32 : KIND_BF16, 128, p.n_tile);
       const int last_valid = p.I - (p.k_chunks - 1) * EPA;               // channels in the last chunk
       const int last_ksteps = (last_valid + EPA / 4 - 1) / (EPA / 4);     // MMA K = EPA / 4 elements
-      int g = 0, i = 0;
+      // shared-memory descriptors advance by a constant per ring stage (the address field holds addr >> 4): one add per
+      // stage instead of rebuilding them; ring position / parity / channel-chunk index are counters (no run-time div / mod)
+      const uint64_t adesc0 = make_sdesc_k_sw128(smem_u32(smem));
+      const uint64_t bdesc0 = make_sdesc_k_sw128(smem_u32(smem + A_STAGE_BYTES));
+      const uint64_t stage_step = (uint64_t)(stage_bytes >> 4);
+      int i = 0, st = 0;
+      uint32_t ph = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++i) {
         const int as = i & 1;
         mbar_wait(&acc_empty[as], ((i >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem + as * p.n_tile;
-        for (int it = 0; it < iters; ++it, ++g) {
-          const int st = g % p.stages;
-          mbar_wait(&full[st], (g / p.stages) & 1);
+        int kc = 0;
+        for (int it = 0; it < iters; ++it) {
+          mbar_wait(&full[st], ph);
           tc_fence_after();
           uint8_t* sA = smem + st * stage_bytes;
+          const bool last_chunk = kc == p.k_chunks - 1;
+          const int st_c = st;
+          if (++kc == p.k_chunks) kc = 0;
+          if (++st == p.stages) { st = 0; ph ^= 1; }
           if (p.halo) {
-            const int ksteps_h = (it % p.k_chunks == p.k_chunks - 1) ? last_ksteps : 4;
+            const int ksteps_h = last_chunk ? last_ksteps : 4;
             for (int dxi = 0; dxi < 3; ++dxi) {
               const uint64_t ad = make_sdesc_k_sw128(smem_u32(sA) + dxi * 128);  // window shifted by dxi pixel rows
               const uint64_t bd = make_sdesc_k_sw128(smem_u32(sA + A_HALO_BYTES + dxi * b_stage_bytes));
@@ -172,14 +187,14 @@ __global__ void __launch_bounds__(kGemmThreads, 3)
                 else mma_ss_f16(d_tmem, ad + 2 * s, bd + 2 * s, idesc, acc);
               }
             }
-            tc_commit(&empty[st]);
+            tc_commit(&empty[st_c]);
             continue;
           }
-          const uint64_t adesc = make_sdesc_k_sw128(smem_u32(sA));
-          const uint64_t bdesc = make_sdesc_k_sw128(smem_u32(sA + A_STAGE_BYTES));
+          const uint64_t adesc = adesc0 + stage_step * (uint64_t)st_c;
+          const uint64_t bdesc = bdesc0 + stage_step * (uint64_t)st_c;
           // the last channel chunk of a narrow layer is partly TMA zero fill (I = 32 bf16 fills half a 128-byte row):
           // skip the K steps that would only multiply zeros (each N <= 64 MMA costs ~85 clk whatever it multiplies)
-          const int ksteps = (it % p.k_chunks == p.k_chunks - 1) ? last_ksteps : 4;
+          const int ksteps = last_chunk ? last_ksteps : 4;
 #pragma unroll
           for (int s = 0; s < 4; ++s) {
             if (s >= ksteps) break;
@@ -187,7 +202,7 @@ __global__ void __launch_bounds__(kGemmThreads, 3)
             if (TF32) mma_ss_tf32(d_tmem, adesc + 2 * s, bdesc + 2 * s, idesc, acc);
             else mma_ss_f16(d_tmem, adesc + 2 * s, bdesc + 2 * s, idesc, acc);
           }
-          tc_commit(&empty[st]);
+          tc_commit(&empty[st_c]);
         }
         tc_commit(&acc_full[as]);
       }

@@ -2,11 +2,13 @@
 
     python tests/perf_picnet.py > gpurun_out/perf_picnet.txt
 
-`ours`   : modules/picnet.py::ReferenceFill — ExampleGuidedAttention @32^2, Auto_Attn @128^2, mask scaling on the sm_100a
-           kernels; spectral-norm conv blocks on cuDNN as in the reference.
+`ours`   : modules/picnet.py::ReferenceFill — ExampleGuidedAttention @32^2, Auto_Attn @128^2, mask scaling and (when TF32
+           convolutions are allowed or FMI_PRECISION=bf16) the encoder / decoder conv blocks on the sm_100a kernels; with
+           cudnn_tf32=0 and the fp32 contract the conv blocks are strict-fp32 cuDNN as in the reference.
 `ref-GPU`: the SAME network and weights with the two attention modules computed the reference's way (oracle functions =
            the reference's bmm / softmax / bmm formulation with the S x S map materialised, modules/example_guided_att.py:15-41,
-           base_function.py:420-448) — what the unmodified reference executes on this GPU.
+           base_function.py:420-448) and every conv block on cuDNN (FMI_PICNET_CUDNN=1) — what the unmodified reference
+           executes on this GPU.
 `ref-CPU`: that formulation on the host cores (the reference's CPU path), batch 4, one forward.
 """
 import copy
@@ -86,7 +88,10 @@ def main():
                     if model is refm and batch * 16384 * 16384 * 4 * 2 > 100e9:
                         print(f"{name} B={batch}: skipped (S x S maps would need {batch * 2} GiB+)")
                         continue
-                    fn = lambda: model(src, ref, mask)
+                    def fn(model=model):
+                        # the reference arm keeps its conv blocks on cuDNN (the kernel path would otherwise serve it too)
+                        os.environ["FMI_PICNET_CUDNN"] = "1" if model is refm else "0"
+                        return model(src, ref, mask)
                     t = time_cuda(fn)
                     extra = ""
                     if model is ours:
@@ -110,7 +115,8 @@ def main():
             src, ref, mask = (t.cuda() for t in picnet_inputs(batch))
             for name, model in (("ours, bf16 autocast, channels_last activations", ours_cl),
                                 ("ref-GPU, bf16 autocast, channels_last activations", ref_cl)):
-                def fn():
+                def fn(model=model):
+                    os.environ["FMI_PICNET_CUDNN"] = "1" if model is ref_cl else "0"
                     with torch.autocast("cuda", dtype=torch.bfloat16):
                         return model(src.contiguous(memory_format=torch.channels_last),
                                      ref.contiguous(memory_format=torch.channels_last), mask)
@@ -131,6 +137,7 @@ def main():
             return m
 
         src, ref, mask = (t.cuda() for t in picnet_inputs(1))
+        os.environ["FMI_PICNET_CUDNN"] = "1"      # strict fp32 on both sides: only the attention formulation differs
         a = fresh(False).cuda()(src, ref, mask)
         b = fresh(True).cuda()(src, ref, mask)
         print(f"ours vs ref-GPU output image (same weights, fresh SpectralNorm state, B=1): rel err "

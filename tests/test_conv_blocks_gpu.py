@@ -43,7 +43,8 @@ def _to_nhwc(k, x, stride=None, offset=0):
 
 
 @pytest.mark.parametrize("mma", [0, 1])
-@pytest.mark.parametrize("shape", [(2, 64, 32, 12, 20), (1, 96, 64, 33, 17), (3, 32, 256, 8, 8), (1, 512, 512, 4, 4)])
+@pytest.mark.parametrize("shape", [(2, 64, 32, 12, 20), (1, 96, 64, 33, 17), (3, 32, 256, 8, 8), (1, 512, 512, 4, 4),
+                                   (1, 64, 32, 6, 260), (2, 32, 128, 3, 128)])   # the last two: halo mode of the plain conv (W >= 128)
 @pytest.mark.parametrize("mode", [0, 2, 3])
 def test_conv3x3_matches_oracle(mma, shape, mode):
     b, i, o, h, w = shape
