@@ -226,14 +226,19 @@ class ResGenerator(nn.Module):
     def forward(self, encoded, z=None, f_e=None, mask=None, pool_to=None):
         """`pool_to` (not in the reference's signature; ReferenceFill passes its AdaptiveAvgPool2d size): return the pooled
         image, which the kernel path fuses into the Output block instead of writing and re-reading the full-size image."""
+        if picnet_fast.supported(self, encoded):   # inference: the conv blocks on the implicit-GEMM kernels (csrc/conv_blocks.cu)
+            if z is not None and not self._fmi_z_ok:     # unusual z -> f blocks: cuDNN, then the kernels
+                f = self.generator(z)
+                for i in range(self.L):
+                    f = getattr(self, f'generator{i}')(f)
+                encoded, z = encoded + f, None
+            return picnet_fast.decoder_forward(self, encoded, f_e, mask, pool_to=pool_to, z=z)
         out = encoded
         if z is not None:
             f = self.generator(z)
             for i in range(self.L):
                 f = getattr(self, f'generator{i}')(f)
             out = encoded + f
-        if picnet_fast.supported(self, out):   # inference: the conv blocks on the implicit-GEMM kernels (csrc/conv_blocks.cu)
-            return picnet_fast.decoder_forward(self, out, f_e, mask, pool_to=pool_to)
         output = None
         for i in range(self.layers):
             out = getattr(self, f'decoder{i}')(out)

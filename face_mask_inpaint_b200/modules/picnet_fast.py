@@ -114,6 +114,12 @@ def supported(gen, x) -> bool:
                 ok = False
         if gen.use_attn and gen.layers < 3:   # attention after block 1 must not be the last block
             ok = False
+        # the z -> f blocks (network.py:213-220) run on the kernels too when they are plain ResBlocks without norm
+        zb = [getattr(gen, "generator", None)] + [getattr(gen, f"generator{i}", None) for i in range(getattr(gen, "L", 0))]
+        gen._fmi_z_ok = all(bk is not None and _enc_block_layout(bk) is not None and _enc_block_layout(bk)[2] is False
+                            and all(isinstance(_plain(c), nn.Conv2d) for c in (bk.conv1, bk.conv2, bk.bypass))
+                            and _plain(bk.conv1).in_channels % 32 == 0 and _plain(bk.conv1).out_channels % 32 == 0
+                            and _plain(bk.conv2).out_channels % 32 == 0 for bk in zb)
         gen._fmi_fast_ok = cached = ok
     return cached
 
@@ -276,11 +282,13 @@ class _Ctx:
                                              mode, act, slope, round_y, self.mma, self.st), "fmi_conv3x3_nhwc")
 
 
-def decoder_forward(gen, x, f_e=None, mask=None, taps=None, pool_to=None):
+def decoder_forward(gen, x, f_e=None, mask=None, taps=None, pool_to=None, z=None):
     """The decoder loop of ResGenerator.forward (network.py:256-268) for `x` = encoded (+ f) [B, C, H, W] fp32 NCHW.
     Returns the image [B, 3, H * 2^layers, W * 2^layers] fp32. `taps` (diagnostics, tests/diag_picnet_blocks.py): a dict that
     receives an fp32 NCHW copy of every block output. `pool_to` = (h, w): return AdaptiveAvgPool2d(pool_to) of the image
-    instead (modules/model.py:111), fused into the Output kernel when it is an exact 4x4 mean."""
+    instead (modules/model.py:111), fused into the Output kernel when it is an exact 4x4 mean. `z` [B, z_nc, H, W]: the
+    latent of network.py:249-254 — f = generator(z) (+ generator{i}) is computed here and added to `x` (the residual-sum
+    epilogue of f's last convolutions accumulates straight onto x in the first block's buffer)."""
     k = _Ctx(x.device, owner=gen)
     esz = 4 if k.mma == _lib.MMA_TF32 else 2
     b, c_in, h, w = x.shape
@@ -291,6 +299,17 @@ def decoder_forward(gen, x, f_e=None, mask=None, taps=None, pool_to=None):
     # block inputs / conv1 outputs feed InstanceNorm: stored exact (round_y = 0), see fmi_conv3x3_nhwc
     _lib.check(k.lib.fmi_nchw_to_nhwc_slice(_p(x), cat.data_ptr() + ch0 * esz, b, c_in, h, w, ch0 + c_in, _lib.F32, 0, k.mma, k.st),
                "fmi_nchw_to_nhwc_slice")
+    if z is not None:
+        zblocks = [gen.generator] + [getattr(gen, f"generator{i}") for i in range(gen.L)]
+        zc = z.shape[1]
+        zx = k.empty(b, h, w, zc)
+        _lib.check(k.lib.fmi_nchw_to_nhwc_slice(_p(z.contiguous()), zx.data_ptr(), b, zc, h, w, zc, _lib.F32, 1, k.mma, k.st),
+                   "fmi_nchw_to_nhwc_slice")
+        for n, blk in enumerate(zblocks):
+            if n == len(zblocks) - 1:   # x += bypass(zx) + conv2(lrelu(conv1(lrelu(zx)))): both GEMMs accumulate onto x
+                _res_block(k, blk, zx, zc, b, h, w, onto=(cat.data_ptr() + ch0 * esz, ch0 + c_in))
+            else:
+                zx, zc, _, _ = _res_block(k, blk, zx, zc, b, h, w)
     image = None
     for i, blk in enumerate(blocks):
         n1, act, n2 = _block_layout(blk)
@@ -440,9 +459,10 @@ def encoder_supported(enc, img) -> bool:
     return cached
 
 
-def _res_block(k, blk, x, cbuf, b, h, w, exact_out=False):
+def _res_block(k, blk, x, cbuf, b, h, w, exact_out=False, onto=None):
     """One encoder-style residual block on x [B,h,w,cbuf] (operand type; channels beyond the conv's in_channels are zero).
-    Returns (y [B,h',w',co], co, h', w')."""
+    Returns (y [B,h',w',co], co, h', w'). `onto` = (pointer, pixel stride) of an NHWC tensor (slice) that already holds
+    values: the block's result is ADDED to it (exact fp32 in TF32 mode) instead of being written to a new tensor."""
     pre_act, slope, pooled = _enc_block_layout(blk)
     c1, c2, bp = _plain(blk.conv1), _plain(blk.conv2), _plain(blk.bypass)
     b1, b2, bs = (None if c.bias is None else c.bias.detach().float().contiguous() for c in (c1, c2, bp))
@@ -454,6 +474,14 @@ def _res_block(k, blk, x, cbuf, b, h, w, exact_out=False):
     a2 = k.empty(b, h, w, ch)
     k.conv(a1.data_ptr(), cbuf, k.weights([(blk.conv1, False)], ch, i_row=cbuf), b1, a2.data_ptr(), ch, 0, None, 0, b, cbuf, ch, h, w,
            0, 1, slope)
+    if onto is not None:
+        if pooled:
+            raise RuntimeError("fmi_b200: a pooled block cannot accumulate onto an existing tensor")
+        k.conv(x.data_ptr(), cbuf, k.weights([(blk.bypass, False)], co, i_row=cbuf), bs, onto[0], onto[1], 0, None, 0, b, cbuf, co,
+               h, w, 4, 12, round_y=0)
+        k.conv(a2.data_ptr(), ch, k.weights([(blk.conv2, False)], co), b2, onto[0], onto[1], 0, None, 0, b, ch, co, h, w, 0, 12,
+               round_y=0)
+        return None, co, h, w
     y = k.empty(b, h, w, co)
     k.conv(x.data_ptr(), cbuf, k.weights([(blk.bypass, False)], co, i_row=cbuf), bs, y.data_ptr(), co, 0, None, 0, b, cbuf, co, h, w,
            4, 2, round_y=0)

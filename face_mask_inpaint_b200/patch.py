@@ -218,13 +218,12 @@ def _install_picnet_decoder():
         if not picnet_fast.supported(self, encoded):
             out = ref_forward(self, encoded, z, f_e, mask)
             return F.adaptive_avg_pool2d(out, pool_to) if pool_to is not None else out
-        out = encoded
-        if z is not None:                                   # network.py:249-254
+        if z is not None and not self._fmi_z_ok:            # network.py:249-254 on cuDNN for unusual z -> f blocks
             f = self.generator(z)
             for i in range(self.L):
                 f = getattr(self, 'generator' + str(i))(f)
-            out = encoded + f
-        return picnet_fast.decoder_forward(self, out, f_e, mask, pool_to=pool_to)
+            encoded, z = encoded + f, None
+        return picnet_fast.decoder_forward(self, encoded, f_e, mask, pool_to=pool_to, z=z)
 
     net.ResGenerator.forward = res_generator_forward
     net.ResGenerator._fmi_pool_to = True

@@ -58,7 +58,7 @@ def main():
     ours.decoder.get_z = types.MethodType(mean_z, ours.decoder)
     taps = {}
     orig = PF.decoder_forward
-    PF.decoder_forward = lambda gen, x, f_e=None, mask=None, pool_to=None: orig(gen, x, f_e, mask, taps=taps, pool_to=pool_to)
+    PF.decoder_forward = lambda gen, x, f_e=None, mask=None, pool_to=None, z=None: orig(gen, x, f_e, mask, taps=taps, pool_to=pool_to, z=z)
     torch.backends.cudnn.allow_tf32 = True     # the kernel path is taken when TF32 convolutions are allowed
     with torch.no_grad():
         got = ours(src, ref, mask, resize=False)
