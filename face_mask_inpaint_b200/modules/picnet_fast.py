@@ -188,13 +188,15 @@ class _WeightPlan:
         self.cursor = 0
 
     def next(self):
+        if self.cursor >= len(self.wps):
+            raise RuntimeError("fmi_b200: weight plan out of step with the forward that recorded it")
         wp = self.wps[self.cursor]
         self.cursor += 1
         return wp
 
 
 class _Ctx:
-    def __init__(self, dev, owner=None):
+    def __init__(self, dev, owner=None, sig=None):
         self.lib = _lib.load()
         self.mma = ops.mma_mode(torch.float32)
         self.dt = torch.float32 if self.mma == _lib.MMA_TF32 else torch.bfloat16
@@ -204,7 +206,7 @@ class _Ctx:
         self.plan = self.recording = None
         if owner is not None:
             plans = owner.__dict__.setdefault("_fmi_weight_plans", {})
-            key = (self.mma, dev.index)
+            key = (self.mma, dev.index, sig)   # sig: which convolutions this call pattern uses (e.g. with / without z)
             plan = plans.get(key)
             if plan is not None and plan.ready and not plan.valid():    # parameters were moved / replaced: rebuild
                 plan = None
@@ -289,7 +291,7 @@ def decoder_forward(gen, x, f_e=None, mask=None, taps=None, pool_to=None, z=None
     instead (modules/model.py:111), fused into the Output kernel when it is an exact 4x4 mean. `z` [B, z_nc, H, W]: the
     latent of network.py:249-254 — f = generator(z) (+ generator{i}) is computed here and added to `x` (the residual-sum
     epilogue of f's last convolutions accumulates straight onto x in the first block's buffer)."""
-    k = _Ctx(x.device, owner=gen)
+    k = _Ctx(x.device, owner=gen, sig=z is not None)
     esz = 4 if k.mma == _lib.MMA_TF32 else 2
     b, c_in, h, w = x.shape
     x = x.contiguous()

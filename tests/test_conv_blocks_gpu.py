@@ -280,6 +280,23 @@ def test_batched_weight_plan_matches_per_conv_path(monkeypatch):
     assert rel_err(outs[0], outs[2]) <= 2e-2 and rel_err(outs[1], outs[3]) <= 2e-2
 
 
+def test_weight_plan_is_keyed_by_call_pattern():
+    """The same ResGenerator called with and without z (the z -> f block's convolutions are only used with z) keeps one
+    weight plan per call pattern."""
+    from face_mask_inpaint_b200.modules.picnet import build_picnet_ref
+    from golden_util import fill_by_name
+    dec = fill_by_name(build_picnet_ref()).eval().cuda().decoder
+    x = torch.randn(1, 256, 8, 8, device="cuda")
+    z = torch.randn(1, 256, 8, 8, device="cuda")
+    with torch.no_grad():
+        for _ in range(2):
+            a = dec(x, z=z)
+            b = dec(x)
+            c = dec(x, z=z, pool_to=(64, 64))
+    assert a.shape == b.shape == (1, 3, 256, 256) and c.shape == (1, 3, 64, 64)
+    assert torch.isfinite(a).all() and torch.isfinite(b).all() and rel_err(a, b) > 1e-3
+
+
 def _mirror_from_golden():
     from face_mask_inpaint_b200.modules import picnet as P
     g = {k: torch.from_numpy(v) for k, v in np.load(GOLD).items()}
