@@ -344,6 +344,8 @@ def decoder_forward(gen, x, f_e=None, mask=None, taps=None, pool_to=None, z=None
         attn = getattr(gen, f"attn{i}", None) if (i == 1 and gen.use_attn) else None
         if last:
             out_blk = getattr(gen, f"out{i}")
+            if _plain(out_blk.conv1).in_channels != co:
+                raise RuntimeError("fmi_b200: Output block channel mismatch")
             o_slope = _slope(out_blk.model[0])
             padded = k.empty(b, oh + 2, ow + 2, co)
             # Output's activation fused into the epilogue (the raw block output has no other reader: network.py:266-268)
@@ -469,6 +471,9 @@ def _res_block(k, blk, x, cbuf, b, h, w, exact_out=False, onto=None):
     c1, c2, bp = _plain(blk.conv1), _plain(blk.conv2), _plain(blk.bypass)
     b1, b2, bs = (None if c.bias is None else c.bias.detach().float().contiguous() for c in (c1, c2, bp))
     ch, co = c1.out_channels, c2.out_channels
+    if c1.in_channels > cbuf or bp.in_channels != c1.in_channels or c2.in_channels != ch or bp.out_channels != co or \
+            (c1.in_channels != cbuf and cbuf != 32):
+        raise RuntimeError("fmi_b200: residual block channel mismatch")
     a1 = x
     if pre_act:
         a1 = k.empty(b, h, w, cbuf)

@@ -78,8 +78,10 @@ def main():
         blk_k = copy.deepcopy(getattr(base.decoder, f"decoder{i}")).cuda()
         blk_c = copy.deepcopy(getattr(base.decoder, f"decoder{i}")).cuda()
         nxt = copy.deepcopy(getattr(base.decoder, f"decoder{i + 1}")).cuda()
+        from face_mask_inpaint_b200.modules import picnet as P
+        nxt_co = PF._plain(nxt.conv2).out_channels
         gen = types.SimpleNamespace(layers=2, use_attn=False, decoder0=blk_k, decoder1=nxt,
-                                    out1=copy.deepcopy(base.decoder.out4).cuda())
+                                    out1=P.Output(nxt_co, 3, 3, None, torch.nn.LeakyReLU(0.1), True, False).cuda())
         t2 = {}
         with torch.no_grad():
             w = blk_c(ins[i])

@@ -1,4 +1,4 @@
-"""Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list: python tools/launch_summary.py <csv> [n_forwards] [min_us]
+"""Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list: python tools/launch_summary.py <csv> [n_forwards] [min_us] [end-of-forward kernel]
 Prints the per-kernel totals of the LAST forward (the list covers n_forwards identical forwards) and every launch above min_us."""
 import collections
 import csv
@@ -12,6 +12,12 @@ with open(path) as f:
     rows = list(csv.DictReader([l for l in f if not l.startswith('==')]))
 per = len(rows) // nfw
 last = rows[(nfw - 1) * per:]
+marker = sys.argv[4] if len(sys.argv) > 4 else None   # a kernel that runs once, at the end of every forward
+if marker:
+    idx = [i for i, r in enumerate(rows) if marker in r['Kernel Name']]
+    if len(idx) >= 2:
+        last = rows[idx[-2] + 1:]
+        per = len(last)
 
 
 def us(row):
