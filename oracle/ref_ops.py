@@ -318,6 +318,28 @@ def output_block(x, conv_w, conv_b, slope=0.1):
 
 
 # --------------------------------------------------------------------------------------------
+# SSIM (north_star: "plus SSIM parity on generated images")
+# --------------------------------------------------------------------------------------------
+def ssim(img1: torch.Tensor, img2: torch.Tensor, window_size: int = 11, size_average: bool = True):
+    """modules/evaluations/ssim.py:8-68 (`ssim`): per-channel 11x11 Gaussian (sigma 1.5) window, zero padding, C1 = 0.01^2,
+    C2 = 0.03^2 (images in [0, 1] or [-1, 1]: the constants are used as they are, as in the reference)."""
+    channel = img1.shape[1]
+    g = torch.tensor([math.exp(-(x - window_size // 2) ** 2 / float(2 * 1.5 ** 2)) for x in range(window_size)])   # :8-10
+    g = (g / g.sum()).unsqueeze(1)
+    window = g.mm(g.t()).float().expand(channel, 1, window_size, window_size).contiguous().to(img1)                # :12-16
+    pad = window_size // 2
+    mu1 = F.conv2d(img1, window, padding=pad, groups=channel)                                                       # :19-20
+    mu2 = F.conv2d(img2, window, padding=pad, groups=channel)
+    mu1_sq, mu2_sq, mu1_mu2 = mu1.pow(2), mu2.pow(2), mu1 * mu2                                                     # :22-24
+    sigma1_sq = F.conv2d(img1 * img1, window, padding=pad, groups=channel) - mu1_sq                                 # :26-28
+    sigma2_sq = F.conv2d(img2 * img2, window, padding=pad, groups=channel) - mu2_sq
+    sigma12 = F.conv2d(img1 * img2, window, padding=pad, groups=channel) - mu1_mu2
+    c1, c2 = 0.01 ** 2, 0.03 ** 2                                                                                   # :30-31
+    ssim_map = ((2 * mu1_mu2 + c1) * (2 * sigma12 + c2)) / ((mu1_sq + mu2_sq + c1) * (sigma1_sq + sigma2_sq + c2))  # :33
+    return ssim_map.mean() if size_average else ssim_map.mean(1).mean(1).mean(1)                                    # :35-38
+
+
+# --------------------------------------------------------------------------------------------
 # bounded samples of the attention workload for the CPU baseline legs of bench.py
 # --------------------------------------------------------------------------------------------
 def example_guided_attention_rows(src_mask, src_feature, ref_feature, conv_weight, rows: torch.Tensor):

@@ -263,6 +263,16 @@ def gen_picnet_blocks():
     np.savez_compressed(OUT / "picnet_blocks.npz", **d)
 
 
+def gen_ssim():
+    """The reference's own SSIM (modules/evaluations/ssim.py) on two seeded image pairs: pins oracle.ssim."""
+    from modules.evaluations.ssim import ssim as ref_ssim
+    g = torch.Generator().manual_seed(77)
+    a = torch.rand(2, 3, 40, 56, generator=g)
+    b = (a + 0.05 * torch.randn(a.shape, generator=g)).clamp(0, 1)
+    np.savez_compressed(OUT / "ssim.npz", a=np_(a), b=np_(b), ssim=np_(ref_ssim(a, b)), ssim_same=np_(ref_ssim(a, a)),
+                        ssim_per_image=np_(ref_ssim(a, b, size_average=False)))
+
+
 def gen_refpsp(size=256):
     """BASELINE config 3 (reduced output size for the fixture): the reference's pSp (modules/psp/psp.py) with
     GradualStyleEncoder(50, 'ir_se') + attention and its StyleGAN2 decoder, `load_weights` bypassed (no pretrained files
@@ -289,11 +299,13 @@ def gen_refpsp(size=256):
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    if len(sys.argv) > 1 and sys.argv[1] in ("picnet", "refpsp", "picnet_blocks"):
+    if len(sys.argv) > 1 and sys.argv[1] in ("picnet", "refpsp", "picnet_blocks", "ssim"):
         if sys.argv[1] == "picnet":
             gen_picnet()
         elif sys.argv[1] == "picnet_blocks":
             gen_picnet_blocks()
+        elif sys.argv[1] == "ssim":
+            gen_ssim()
         else:
             gen_refpsp()
         for f in sorted(OUT.glob("*.npz")):
@@ -304,6 +316,7 @@ if __name__ == "__main__":
     gen_stylegan2()
     gen_picnet()
     gen_picnet_blocks()
+    gen_ssim()
     gen_refpsp()
     for f in sorted(OUT.glob("*.npz")):
         print(f.name, f.stat().st_size)

@@ -144,3 +144,11 @@ def test_picnet_decoder_blocks_match_reference():
     assert rel_err(y, g["y"]) <= 1e-6
     wo, bo = _sn(g, "out.conv1")
     assert rel_err(O.output_block(y, wo, bo, slope=0.1), g["img"]) <= 1e-6
+
+
+def test_ssim_matches_reference():
+    """oracle.ssim against the reference's own modules/evaluations/ssim.py (the metric behind north_star's SSIM parity)."""
+    g = load("ssim.npz")
+    assert abs(float(O.ssim(g["a"], g["b"])) - float(g["ssim"])) <= 1e-6
+    assert abs(float(O.ssim(g["a"], g["a"])) - float(g["ssim_same"])) <= 1e-6 and float(g["ssim_same"]) > 0.999999
+    assert rel_err(O.ssim(g["a"], g["b"], size_average=False), g["ssim_per_image"]) <= 1e-6
