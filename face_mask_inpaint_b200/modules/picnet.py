@@ -296,6 +296,26 @@ def define_g(output_nc=3, ngf=64, z_nc=512, img_f=512, L=1, layers=5, norm='inst
                                         use_attn))
 
 
+def two_encoders(model, src_image, ref_image):
+    """model.py:87-88: the source and reference encoders are independent. In inference they run concurrently on two streams
+    (each is a chain of ~60 small dependent kernels that leaves most of the GPU idle); under CUDA-graph capture the fork / join
+    becomes two parallel branches of the graph. The side stream always waits for the current stream before it starts, so
+    blocks of its allocator pool are only reused after every earlier consumer has been enqueued."""
+    import os
+    if (torch.is_grad_enabled() or not src_image.is_cuda or os.environ.get("FMI_ENCODER_STREAMS") == "0"):
+        return model.src_encoder(src_image), model.ref_encoder(ref_image)
+    cur = torch.cuda.current_stream()
+    side = model.__dict__.get("_fmi_side_stream")
+    if side is None or side.device != src_image.device:
+        side = model.__dict__["_fmi_side_stream"] = torch.cuda.Stream(device=src_image.device)
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        ref_out = model.ref_encoder(ref_image)
+    src_out = model.src_encoder(src_image)
+    cur.wait_stream(side)
+    return src_out, ref_out
+
+
 class ReferenceFill(nn.Module):
     """modules/model.py:15-112 with encoder type 'pluralistic' (the README / PICNet_inference.py configuration)."""
 
@@ -317,8 +337,7 @@ class ReferenceFill(nn.Module):
     def forward(self, src_image, ref_image, src_mask=None, resize=True, no_prior=False):
         if src_mask is None:
             src_mask = self.mask_detector(src_image, mode='eval')
-        src_dist, src_features = self.src_encoder(src_image)
-        ref_dist, ref_features = self.ref_encoder(ref_image)
+        (src_dist, src_features), (ref_dist, ref_features) = two_encoders(self, src_image, ref_image)
         mask_full = src_mask.unsqueeze(1)
         if self.use_att:
             scaled = ops.scale_img(mask_full, src_features.shape[-2:])           # model.py:96 -> fmi_scale_mask

@@ -140,8 +140,8 @@ def _install_compositing_callers():
             src_dist = ref_dist = None
             src_features, ref_features = self.src_encoder(src_image), self.ref_encoder(ref_image)
         else:
-            src_dist, src_features = self.src_encoder(src_image)
-            ref_dist, ref_features = self.ref_encoder(ref_image)
+            from .modules.picnet import two_encoders    # concurrent streams in inference
+            (src_dist, src_features), (ref_dist, ref_features) = two_encoders(self, src_image, ref_image)
         full_mask = src_mask.unsqueeze(1)
         if self.use_att:
             enc = self.attention(_scale_img_any(full_mask, src_features.shape[-2:]), src_features, ref_features)
