@@ -18,6 +18,24 @@ from __future__ import annotations
 import torch
 
 
+class NoCopyCache(dict):
+    """Per-module run-time caches (weight plans, side streams, captured graphs) that must not travel with the module:
+    `copy.deepcopy(model)` / `torch.save(model)` get a fresh empty cache instead of CUDA streams, graphs and device pointers."""
+
+    def __deepcopy__(self, memo):
+        return NoCopyCache()
+
+    def __reduce__(self):
+        return (NoCopyCache, ())
+
+
+def module_cache(module) -> "NoCopyCache":
+    c = module.__dict__.get("_fmi_cache")
+    if c is None:
+        c = module.__dict__["_fmi_cache"] = NoCopyCache()
+    return c
+
+
 def _flatten(obj, out):
     if isinstance(obj, torch.Tensor):
         out.append(obj)
@@ -109,7 +127,7 @@ def auto_graph(forward):
             hash(key)
         except TypeError:
             return forward(self, *args, **kwargs)
-        cache = self.__dict__.setdefault("_fmi_graphs", {})
+        cache = module_cache(self).setdefault("graphs", {})
         g = cache.get(key)
         if g is None:
             g = cache[key] = CapturedForward(functools.partial(forward, self), *args, **kwargs)

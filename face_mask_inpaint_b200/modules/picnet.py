@@ -305,9 +305,11 @@ def two_encoders(model, src_image, ref_image):
     if (torch.is_grad_enabled() or not src_image.is_cuda or os.environ.get("FMI_ENCODER_STREAMS") == "0"):
         return model.src_encoder(src_image), model.ref_encoder(ref_image)
     cur = torch.cuda.current_stream()
-    side = model.__dict__.get("_fmi_side_stream")
+    from ..graphs import module_cache
+    cache = module_cache(model)
+    side = cache.get("side_stream")
     if side is None or side.device != src_image.device:
-        side = model.__dict__["_fmi_side_stream"] = torch.cuda.Stream(device=src_image.device)
+        side = cache["side_stream"] = torch.cuda.Stream(device=src_image.device)
     side.wait_stream(cur)
     with torch.cuda.stream(side):
         ref_out = model.ref_encoder(ref_image)

@@ -205,7 +205,8 @@ class _Ctx:
         # weight plan of the owning network (per operand type and device); None = prepare weights call by call
         self.plan = self.recording = None
         if owner is not None:
-            plans = owner.__dict__.setdefault("_fmi_weight_plans", {})
+            from ..graphs import module_cache
+            plans = module_cache(owner).setdefault("weight_plans", {})
             key = (self.mma, dev.index, sig)   # sig: which convolutions this call pattern uses (e.g. with / without z)
             plan = plans.get(key)
             if plan is not None and plan.ready and not plan.valid():    # parameters were moved / replaced: rebuild

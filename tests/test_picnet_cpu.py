@@ -25,3 +25,17 @@ def test_fill_by_name_is_deterministic():
     for (ka, va), (kb, vb) in zip(a.state_dict().items(), b.state_dict().items()):
         assert ka == kb and torch.equal(va, vb)
     assert float(a.decoder.attn1.gamma) == 1.0
+
+
+def test_runtime_caches_do_not_travel_with_the_module():
+    """Weight plans, side streams and captured graphs live in a per-module cache that deepcopy / pickle replace by an empty one
+    (a model that has run on the GPU must stay deep-copyable: EMA copies, torch.save(model))."""
+    import copy
+    import pickle
+    import torch
+    from face_mask_inpaint_b200.graphs import NoCopyCache, module_cache
+    m = torch.nn.Linear(2, 2)
+    module_cache(m)["side_stream"] = object()          # stands for a torch.cuda.Stream (not picklable)
+    for clone in (copy.deepcopy(m), pickle.loads(pickle.dumps(m))):
+        assert isinstance(clone.__dict__["_fmi_cache"], NoCopyCache) and len(clone.__dict__["_fmi_cache"]) == 0
+    assert "side_stream" in module_cache(m)
