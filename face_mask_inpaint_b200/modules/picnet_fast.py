@@ -1,20 +1,23 @@
-"""Inference path of the PICNet decoder conv blocks on the sm_100a kernels (csrc/conv_blocks.cu).
+"""Inference path of the PICNet conv blocks — decoder, encoders, z -> f block — on the sm_100a kernels (SURVEY §8f rank 1;
+csrc/conv_blocks.cu).
 
 `ResGenerator.forward` (modules/pluralistic_model/network.py:247-268) runs, per ResBlockDecoder
 (base_function.py:308-366):  IN -> LeakyReLU -> Conv2d(3,1,1) -> IN -> LeakyReLU -> ConvTranspose2d(3,2,1,1), plus a
 ConvTranspose2d(3,2,1,1) shortcut of the block input, every conv wrapped in SpectralNorm; then Auto_Attn after block 1
 and Output (LeakyReLU -> ReflectionPad2d(1) -> Conv2d(3) -> Tanh, :369-398) after the last block. Here the activations stay
 NHWC in the tensor-core operand type from the first block to the image, each block is 2 statistics passes, 2
-normalise+activate passes and 5 implicit-GEMM launches (conv, then the 4 output-parity classes of the transposed conv with
-main path and shortcut concatenated along the input channels so that their sum is the accumulator), and every GEMM writes
-straight into the buffer the next consumer reads (channel slice of the next block's [a2 | x] buffer, or the interior of the
-reflection-padded buffer of the Output conv).
+normalise+activate passes and 2-5 implicit-GEMM launches (conv, then the transposed conv — one launch over its 4 merged
+output-parity classes when O <= 32, else one per class — with main path and shortcut concatenated along the input channels so
+that their sum is the accumulator), and every GEMM writes straight into the buffer the next consumer reads (channel slice of
+the next block's [a2 | x] buffer, or the interior of the reflection-padded buffer of the Output kernel, which also does the
+final 4x4 average pooling). `encoder_forward` (second half of this file) does the same for ResEncoder.
 
 Used when autograd is off, the tensors are CUDA and TF32 convolutions are allowed (torch.backends.cudnn.allow_tf32, PyTorch's
 default — i.e. whenever the reference itself would run these convolutions with TF32 operands) or FMI_PRECISION=bf16; training
 differentiates the cuDNN formulation of the same blocks (picnet.py), whose backward is not a kernel of this package yet.
-SpectralNorm (external_function.py:44-57) keeps its one power iteration per forward: `_update_u_v()` of the mirror is called
-as in the eager path and the resulting `w_bar / sigma` is what the weight-prep kernel re-lays out.
+SpectralNorm (external_function.py:44-57) keeps its one power iteration per forward, u and v advanced in place: per conv
+(fmi_conv_weight_prep_sn) on a network's first forward, then for all of its convs at once (`_WeightPlan`,
+fmi_conv_weight_prep_sn_batch).
 """
 from __future__ import annotations
 
