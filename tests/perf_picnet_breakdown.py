@@ -1,5 +1,7 @@
-"""Where a PICNet-ref forward spends its time, per block (CUDA events around each sub-module, eager launch, batch 8 and 4) —
-NOT a pytest file:  python tests/perf_picnet_breakdown.py > gpurun_out/perf_picnet_breakdown.txt"""
+"""Where a PICNet-ref forward spends its time — NOT a pytest file:  python tests/perf_picnet_breakdown.py
+First two lines: the forward split into CUDA graphs (encoders + EGA / decoder) = GPU times. Then per sub-module CUDA events in
+eager mode (host-launch bound; the decoder blocks show 0 there because the kernel path replaces `ResGenerator.forward` as a
+whole and does not call the block modules — set FMI_PICNET_CUDNN=1 to see the cuDNN blocks)."""
 import sys
 import types
 from pathlib import Path
@@ -93,7 +95,7 @@ def graphed_pieces():
         t_gen = timed(lambda z: net.decoder.generator(z), z)
         t_dec = timed(lambda x: net.decoder(x, pool_to=(256, 256)), x)
         t_all = timed(lambda a, b, c: net(a, b, c), src, ref, mask)
-        print(f"graphed, batch {batch}: whole forward {t_all:.2f} ms | encoders + EGA {t_enc:.2f} | z->f ResBlock {t_gen:.2f} | "
+        print(f"graphed, batch {batch}: whole forward {t_all:.2f} ms | encoders + EGA {t_enc:.2f} | z->f ResBlock as a stand-alone cuDNN module {t_gen:.2f} (inside the forward it is part of the decoder graph, on the kernels) | "
               f"decoder blocks + Auto_Attn + Output + pool {t_dec:.2f}")
 
 
