@@ -255,7 +255,19 @@ def run_ours(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL writes its version banner to file descriptor 1 when its communicator is created, whatever NCCL_DEBUG says on
+        # some boxes: point fd 1 at stderr for the initialisation so that stdout carries nothing but the JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier(device_ids=[local_rank])
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     lib = _lib.load()
     _lib.check(lib.fmi_device_check(), "fmi_device_check")
 
