@@ -188,6 +188,21 @@ def whole_model_throughput(dev, world, barrier, max_over_ranks):
         barrier()
         return max_over_ranks(e0.elapsed_time(e1) / iters)
 
+    def e2e(fwd, host_in, out_dev):
+        """The same forward from pinned HOST inputs to a pinned HOST result, every step: H2D of the step's inputs into the
+        graph's static buffers, one replay, D2H of the image — all on the current stream, no host synchronisation inside."""
+        host_out = torch.empty(out_dev.shape, dtype=out_dev.dtype, pin_memory=True)
+        stat = fwd.static_inputs
+
+        def step():
+            for dst, src in zip(stat, host_in):
+                dst.copy_(src, non_blocking=True)
+            fwd.replay()
+            host_out.copy_(out_dev, non_blocking=True)
+
+        ms = timed(step)
+        return ms, sum(t.numel() * t.element_size() for t in host_in), host_out.numel() * host_out.element_size()
+
     prev = os.environ.get("FMI_PRECISION")
     try:
         with torch.no_grad():
@@ -204,7 +219,10 @@ def whole_model_throughput(dev, world, barrier, max_over_ranks):
             ms_eager = timed(lambda: net(src, ref, mask))
             fwd = CapturedForward(net, src, ref, mask)
             ms = timed(lambda: fwd(src, ref, mask))
+            ms_e2e, bi, bo = e2e(fwd, [t.cpu().pin_memory() for t in (src, ref, mask)], fwd(src, ref, mask))
             out["picnet_ref_256"] = {"value": world * b / (ms * 1e-3), "unit": "img/s", "per_gpu_batch": b, "ms_per_step": ms,
+                                     "e2e": {"value": world * b / (ms_e2e * 1e-3), "unit": "img/s", "ms_per_step": ms_e2e,
+                                             "h2d_bytes_per_step": bi, "d2h_bytes_per_step": bo},
                                      "launch": "one CUDA-graph replay per forward (graphs.CapturedForward)",
                                      "eager_ms_per_step": ms_eager, "eager_value": world * b / (ms_eager * 1e-3),
                                      "precision": "fp32 I/O; TF32 tensor-core operands (attention and conv blocks), fp32 "
@@ -223,11 +241,15 @@ def whole_model_throughput(dev, world, barrier, max_over_ranks):
             ms_eager = timed(lambda: net(x, ref=ref, src_mask=mask, resize=True, randomize_noise=False))
             fwd = CapturedForward(net, x, ref=ref, src_mask=mask, resize=True, randomize_noise=False)
             ms = timed(lambda: fwd(x, ref=ref, src_mask=mask))
+            ms_e2e, bi, bo = e2e(fwd, [t.cpu().pin_memory() for t in (x, ref, mask)], fwd(x, ref=ref, src_mask=mask))
+            psp_e2e = {"value": world * b / (ms_e2e * 1e-3), "unit": "img/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": bi,
+                       "d2h_bytes_per_step": bo}
             del fwd
             codes = net.encoder(x, ref=ref, mask=mask)
             ms_dec = timed(lambda: net.decoder([codes], input_is_latent=True, randomize_noise=False))
             out["refpsp_1024"] = {"value": world * b / (ms * 1e-3), "unit": "img/s", "per_gpu_batch": b, "ms_per_step": ms,
                                   "launch": "one CUDA-graph replay per forward (graphs.CapturedForward)",
+                                  "e2e": psp_e2e,
                                   "eager_ms_per_step": ms_eager, "eager_value": world * b / (ms_eager * 1e-3),
                                   "decoder_only_ms": ms_dec, "decoder_only_img_s": world * b / (ms_dec * 1e-3),
                                   "precision": "bf16 tensor-core operands in the decoder and attention, cuDNN trunk fp32/TF32",

@@ -98,6 +98,12 @@ class CapturedForward:
         self.replays += 1
         return self._static_out
 
+    def replay(self):
+        """Replay on whatever the static inputs currently hold (written through `static_inputs`)."""
+        self._graph.replay()
+        self.replays += 1
+        return self._static_out
+
     def matches(self, *args, **kwargs) -> bool:
         tensors = _flatten((args, [kwargs[k] for k in self._kw_order if k in kwargs]), [])
         return len(tensors) == len(self._static_in) and all(
