@@ -70,3 +70,40 @@ def test_refpsp_graph_replay_matches_eager():
     got2 = fwd(x2, ref=ref2, src_mask=mask2).clone()
     assert rel_err(got1, want1) <= 1e-5, rel_err(got1, want1)
     assert rel_err(got2, want2) <= 1e-5, rel_err(got2, want2)
+
+
+def test_auto_graph_wrapper_keys_graphs_by_shape_and_falls_back_under_autograd():
+    """graphs.auto_graph (what the installer puts around ReferenceFill.forward with FMI_CUDA_GRAPH=1): one captured graph per
+    input shape, clones returned, eager forward whenever autograd is on or the module is in training mode."""
+    from face_mask_inpaint_b200.graphs import auto_graph, module_cache
+    from face_mask_inpaint_b200.modules.picnet import ReferenceFill
+    base = _picnet()
+    eager, wrapped = copy.deepcopy(base).cuda(), copy.deepcopy(base).cuda()
+    for m in (eager, wrapped):
+        m.decoder.get_z = types.MethodType(mean_z, m.decoder)
+
+    class Graphed(ReferenceFill):
+        forward = auto_graph(ReferenceFill.forward)
+
+    wrapped.__class__ = Graphed
+    a1 = tuple(t.cuda() for t in picnet_inputs(1))
+    a2 = tuple(t.cuda() for t in picnet_inputs(2, seed=9))
+    with torch.no_grad():
+        got = [wrapped(*a1), wrapped(*a2), wrapped(*a1)]
+        assert len(module_cache(wrapped)["graphs"]) == 2           # one graph per shape, the third call replays the first
+    assert got[0].shape == (1, 3, 256, 256) and got[1].shape == (2, 3, 256, 256)
+    assert got[0].data_ptr() != got[2].data_ptr()                  # clones, not the graph's static output
+    # the eager model with the same number of forwards (= SpectralNorm power iterations): a capture is 3 warm-up calls, then
+    # every wrapped call is one replay
+    with torch.no_grad():
+        want = []
+        for args, calls in ((a1, 4), (a2, 4), (a1, 1)):
+            for _ in range(calls):
+                o = eager(*args)
+            want.append(o)
+    for g, w in zip(got, want):
+        assert rel_err(g, w) <= 1e-5, rel_err(g, w)
+    # autograd on: no graph, gradients flow
+    wrapped.train()
+    out = wrapped(*a1)
+    assert out.requires_grad and len(module_cache(wrapped)["graphs"]) == 2
