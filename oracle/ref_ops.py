@@ -14,7 +14,9 @@ below cites the reference file:line (relative to the reference root) that it res
 Pinning: the reference ships NO tests / golden vectors / KATs. This oracle is pinned
 instead against outputs of the reference's own modules imported from /root/reference in the build
 container: `tests/golden/make_golden.py` generated `tests/golden/*.npz`, and
-`tests/test_oracle_golden.py` checks every function here against them.
+`tests/test_oracle_golden.py` checks every function here against them. `fused_bias_act` and `upfirdn2d`,
+whose reference implementations are CUDA kernels, are additionally pinned on the GPU against the reference's
+own compiled ops (oracle/build_ref.py -> oracle/_ref/*.so, tests/test_reference_ops_gpu.py).
 """
 from __future__ import annotations
 

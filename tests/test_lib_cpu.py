@@ -41,3 +41,18 @@ def test_ops_refuse_cpu_tensors():
         ops.fused_leaky_relu(torch.zeros(1, 4, 2, 2), torch.zeros(4))
     with pytest.raises(RuntimeError):
         ops.upfirdn2d(torch.zeros(1, 1, 4, 4), torch.ones(4, 4))
+
+
+def test_reference_checker_libraries_load_when_built():
+    """oracle/_ref/*.so (the reference's own CUDA ops compiled by oracle/build_ref.py) import on a CPU-only box and export the
+    two pybind ops the GPU parity tests call. Skipped where they were never built (no /root/reference)."""
+    import sys
+    from pathlib import Path
+    import pytest
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+    from oracle import build_ref
+    have = build_ref.built()
+    if len(have) < 2:
+        pytest.skip("oracle/_ref not built")
+    assert hasattr(build_ref.load_built("fmi_ref_fused"), "fused_bias_act")
+    assert hasattr(build_ref.load_built("fmi_ref_upfirdn2d"), "upfirdn2d")
