@@ -275,6 +275,47 @@ __global__ void __launch_bounds__(256) torgb_nhwc_kernel(const OT* __restrict__ 
 }
 
 
+// ---- combined weights of "conv_transpose2d(stride 2, 3x3) then 4x4 blur (pad 1,1)" per output-parity class ------------
+// out[2m+py, 2n+px] = sum_{dy,dx in {-1,0,1}} x[m+dy, n+dx] * Wc[py - 2dy][px - 2dx],
+// Wc[u][v] = sum_{a,e} kfl[a][e] * w[u+a-1][v+e-1]  (w = the 3x3 per-sample weights, zero outside; kfl = flipped blur kernel,
+// upfirdn2d_kernel.cu:77). wpc[b][shift = (dy+1)*3 + (dx+1)][cls*O + o][i], cls = 2*py + px. One block per (o, b).
+template <typename OT, bool ROUND_TF32>
+__global__ void __launch_bounds__(128) upblur_weight_kernel(const OT* __restrict__ wp /*[B][9][O][I]*/,
+                                                            const float* __restrict__ kf /*4x4 blur.kernel*/,
+                                                            OT* __restrict__ wpc /*[B][9][4*O][I]*/, int O, int I) {
+  __shared__ float skf[16];
+  if (threadIdx.x < 16) skf[threadIdx.x] = kf[15 - threadIdx.x];  // kfl[a][e] = kf[3-a][3-e]
+  __syncthreads();
+  const int o = blockIdx.x, b = blockIdx.y;
+  for (int i = threadIdx.x; i < I; i += blockDim.x) {
+    float w[3][3];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) w[t / 3][t % 3] = to_f32<OT>(wp[(((int64_t)b * 9 + t) * O + o) * I + i]);
+#pragma unroll
+    for (int sh = 0; sh < 9; ++sh) {
+      const int dy = sh / 3 - 1, dx = sh % 3 - 1;
+#pragma unroll
+      for (int cls = 0; cls < 4; ++cls) {
+        const int u = (cls >> 1) - 2 * dy, v = (cls & 1) - 2 * dx;
+        float acc = 0.f;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          const int ky = u + a - 1;
+          if (ky < 0 || ky > 2) continue;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int kx = v + e - 1;
+            if (kx < 0 || kx > 2) continue;
+            acc = fmaf(skf[a * 4 + e], w[ky][kx], acc);
+          }
+        }
+        if (ROUND_TF32) acc = __uint_as_float(f32_to_tf32_rna(acc));
+        wpc[(((int64_t)b * 9 + sh) * (4 * O) + cls * O + o) * I + i] = from_f32<OT>(acc);
+      }
+    }
+  }
+}
+
 }  // namespace
 
 // =====================================================================================================================
@@ -470,13 +511,52 @@ int styled_conv_impl(const void* x, const void* wp, void* y, const float* noise,
     return tf32 ? launch_gemm_class<true>(mx, mw, p, st) : launch_gemm_class<false>(mx, mw, p, st);
   }
   FMI_REQUIRE(!rgb, "styled_conv: ToRGB fusion is for plain (non-upsampling) layers");
+  FMI_REQUIRE(blur_k, "styled_conv: upsample needs the 4x4 blur kernel");
+
+  // ---- upsample, narrow layers (O <= 64): conv_transpose2d(stride 2, 3x3) followed by the 4x4 blur IS one transposed conv
+  // with the 6x6 kernel Wc = w (*) blur, i.e. per output-parity class a 3x3 conv on the input (i = m-1..m+1). All four
+  // classes read the same nine input shifts, so the layer is ONE implicit GEMM with N = 4*O columns (merged parity classes,
+  // modconv_gemm.cuh) whose epilogue adds noise + bias + leaky-ReLU: the same number of MMA instructions as the four
+  // per-class launches below (9 taps, now 4x wider), no (2H+1)^2 intermediate and no blur pass (0.6 ms of a batch-8
+  // 1024^2 layer). The combined per-sample weights are built from wp in the workspace. FMI_UPBLUR_FUSED=0: the two-pass path.
+  {
+    const bool off = [] { const char* e = getenv("FMI_UPBLUR_FUSED"); return e && e[0] == '0'; }();  // read per call
+    const int64_t need_w = (int64_t)B * 9 * 4 * O * I * esz;
+    if (!off && O <= 64 && workspace && workspace_bytes >= need_w) {
+      if (tf32)
+        upblur_weight_kernel<float, true><<<dim3(O, B), 128, 0, st>>>((const float*)wp, blur_k, (float*)workspace, O, I);
+      else
+        upblur_weight_kernel<__nv_bfloat16, false><<<dim3(O, B), 128, 0, st>>>((const __nv_bfloat16*)wp, blur_k,
+                                                                              (__nv_bfloat16*)workspace, O, I);
+      rc = fmi_launched("upblur_weight");
+      if (rc) return rc;
+      CUtensorMap mwc;
+      {
+        uint64_t dims[2] = {(uint64_t)I, (uint64_t)B * 9 * 4 * O};
+        uint64_t str[1] = {(uint64_t)I * esz};
+        uint32_t box[2] = {epa, (uint32_t)(4 * O)};
+        int e = make_tensor_map(&mwc, dt, 2, workspace, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+        FMI_REQUIRE(e == 0, "styled_conv: cuTensorMapEncodeTiled(combined weights) failed (%d)", e);
+      }
+      p.merge_o = O; p.O = 4 * O; p.n_tile = 4 * O; p.T = 9;
+      p.OH = 2 * H; p.OW = 2 * W; p.sy = p.sx = 2; p.py = p.px = 0; p.Mh = H; p.Mw = W;
+      p.out_pstride = O; p.out_rstride = (int64_t)p.OW * O; p.out_bstride = (int64_t)p.OH * p.OW * O;
+      p.act = act; p.out = y;
+      p.ntaps = 9;
+      for (int t = 0; t < 9; ++t) { p.tap_dy[t] = t / 3 - 1; p.tap_dx[t] = t % 3 - 1; p.tap_slab[t] = t; }
+      TilePlan tp = pick_tile(p.Mh, p.Mw);
+      CUtensorMap mx;
+      int e = make_x_map(&mx, tp.TH, tp.TW);
+      FMI_REQUIRE(e == 0, "styled_conv: cuTensorMapEncodeTiled(x) failed (%d)", e);
+      return tf32 ? launch_gemm_class<true>(mx, mwc, p, st) : launch_gemm_class<false>(mx, mwc, p, st);
+    }
+  }
 
   // ---- upsample: conv_transpose2d(stride 2) by output parity class, then blur + epilogue
   const int MH = 2 * H + 1, MW = 2 * W + 1;
   const int64_t need = (int64_t)B * MH * MW * O * esz;
   FMI_REQUIRE(workspace && workspace_bytes >= need, "styled_conv: workspace too small (%lld < %lld)",
               (long long)workspace_bytes, (long long)need);
-  FMI_REQUIRE(blur_k, "styled_conv: upsample needs the 4x4 blur kernel");
   p.OH = MH; p.OW = MW; p.sy = p.sx = 2; p.act = 0; p.out = workspace;
   for (int py = 0; py < 2; ++py)
     for (int px = 0; px < 2; ++px) {

@@ -252,10 +252,14 @@ __global__ void __launch_bounds__(kGemmThreads, 3)
         if (!valid) continue;
         OT* outp = out + c0;
         int bofs = o0 + c0;
+        float nzc = nz;
         if (p.merge_o) {
           const int cls = c0 / p.merge_o;
           bofs = c0 - cls * p.merge_o;
           outp = out + (cls >> 1) * p.out_rstride + (cls & 1) * p.out_pstride + bofs;
+          if (p.act == 1 && p.noise && cls)   // the noise plane is indexed by the output pixel of this parity class
+            nzc = (p.noise_w ? *p.noise_w : 1.f) * p.noise[(int64_t)(p.noise_batched ? b : 0) * p.OH * p.OW +
+                                                          (int64_t)(oy + (cls >> 1)) * p.OW + ox + (cls & 1)];
         }
         float f[32];
 #pragma unroll
@@ -263,7 +267,7 @@ __global__ void __launch_bounds__(kGemmThreads, 3)
         if (p.act == 1) {
 #pragma unroll
           for (int k = 0; k < 32; ++k) {
-            float tt = f[k] + nz + (p.bias ? __ldg(p.bias + bofs + k) : 0.f);
+            float tt = f[k] + nzc + (p.bias ? __ldg(p.bias + bofs + k) : 0.f);
             f[k] = (tt > 0.f ? tt : tt * p.slope) * p.gain;
           }
         } else if (p.act >= 2) {

@@ -106,6 +106,45 @@ def test_styled_conv(up, batched_noise, mode):
     assert err <= tol, f"rel err {err:.3e}"
 
 
+@pytest.mark.parametrize("cfg", [(2, 64, 32, 32, 40), (1, 128, 64, 24, 24), (2, 32, 32, 17, 33)])
+@pytest.mark.parametrize("batched_noise", [False, True])
+@pytest.mark.parametrize("fused", ["1", "0"])
+@pytest.mark.parametrize("mode", MODES, ids=[m[0] for m in MODES])
+def test_styled_conv_upsample_narrow_layers(cfg, batched_noise, fused, mode, monkeypatch):
+    """Up-sampling StyledConv with O <= 64: conv_transpose + blur as ONE merged-parity implicit GEMM with the combined 6x6
+    weights (FMI_UPBLUR_FUSED=1, default) and as the two-pass path (=0), both against the oracle; ragged and odd extents."""
+    SG = _mods()
+    monkeypatch.setenv("FMI_UPBLUR_FUSED", fused)
+    _, dtype, tol = mode
+    b, i, o, h, w = cfg
+    g = torch.Generator().manual_seed(11)
+    mod = SG.StyledConv(i, o, 3, 512, upsample=True)
+    _randomize(mod, g)
+    x = torch.randn(b, i, h, w, generator=g).to(dtype).float()
+    style = torch.randn(b, 512, generator=g)
+    noise = torch.randn(b if batched_noise else 1, 1, 2 * h, 2 * w, generator=g)
+    sd = {k: v.detach() for k, v in mod.state_dict().items()}
+    want = O.styled_conv(x, style, sd['conv.weight'], sd['conv.modulation.weight'], sd['conv.modulation.bias'],
+                         sd['noise.weight'], sd['activate.bias'], noise, upsample=True)
+    mod = mod.to(DEV)
+    n0 = _launches()
+    with torch.no_grad():
+        got = mod(x.to(dtype).to(DEV), style.to(DEV), noise=noise.to(DEV))
+    used = _launches() - n0
+    assert got.shape == want.shape == (b, o, 2 * h, 2 * w)
+    err = rel_err(got, want)
+    assert err <= tol, f"rel err {err:.3e}"
+    # style modulation + weight prep + layout changes are common; the conv itself is 2 launches (combined weights + one GEMM)
+    # fused, 5 (four parity-class GEMMs + blur) two-pass
+    base = 4                                            # nchw_to_nhwc, style_mod, weight_prep, nhwc_to_nchw
+    assert used == base + (2 if fused == "1" else 5), used
+
+
+def _launches():
+    from face_mask_inpaint_b200 import _lib
+    return _lib.load().fmi_kernel_launch_count()
+
+
 @pytest.mark.parametrize("with_skip", [False, True])
 @pytest.mark.parametrize("mode", MODES, ids=[m[0] for m in MODES])
 def test_to_rgb(with_skip, mode):
