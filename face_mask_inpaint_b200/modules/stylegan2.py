@@ -26,6 +26,12 @@ def _p(t):
     return None if t is None else t.data_ptr()
 
 
+def _TORGB_FUSE_MIN_O():
+    """Smallest output width whose ToRGB rides in the conv epilogue (A/B switch, FMI_TORGB_FUSE_MIN_O; default: always)."""
+    import os
+    return int(os.environ.get("FMI_TORGB_FUSE_MIN_O", "0"))
+
+
 def _wants_grad(*tensors):
     return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
 
@@ -631,7 +637,7 @@ class Generator(nn.Module):
         for conv1, conv2, noise1, noise2, to_rgb in zip(self.convs[::2], self.convs[1::2], noise[1::2], noise[2::2],
                                                         self.to_rgbs):
             out = conv1.forward_nhwc(out, lat[:, i], mma, noise=noise1, wp=pre(i))
-            if conv2.conv.out_channel <= 256 and not conv2.conv.upsample and not train:
+            if _TORGB_FUSE_MIN_O() <= conv2.conv.out_channel <= 256 and not conv2.conv.upsample and not train:
                 # conv2 + ToRGB in one kernel (the RGB projection rides in conv2's epilogue)
                 b, h, w, _ = out.shape
                 conv2.conv._check()
