@@ -85,6 +85,30 @@ __global__ void __launch_bounds__(256) weight_prep_kernel(const float* __restric
       __syncthreads();
       d = demod_s;
     }
+    if ((I & 7) == 0) {
+      // 8 consecutive input channels per thread: one 16-byte (bf16) / two 16-byte (tf32) stores and one division per vector.
+      // (The scalar version below wrote 2 bytes per lane: 50 us for a 512 x 512 layer whose 38 MB take 8 us at HBM speed.)
+      const int vec_per_tap = I >> 3;
+      for (int ev = threadIdx.x; ev < T * vec_per_tap; ev += 256) {
+        const int t = ev / vec_per_tap, i0 = (ev - t * vec_per_tap) << 3;
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          v[k] = sw[(i0 + k) * T + t] * sb[i0 + k] * d;
+          if (ROUND_TF32) v[k] = __uint_as_float(f32_to_tf32_rna(v[k]));
+        }
+        OT* dst = wp + (((int64_t)b * T + t) * O + o) * I + i0;
+        if constexpr (sizeof(OT) == 2) {
+          uint4 u;
+          u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]); u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+          *reinterpret_cast<uint4*>(dst) = u;
+        } else {
+          *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+          *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        }
+      }
+      continue;
+    }
     for (int e = threadIdx.x; e < n; e += 256) {
       const int t = e / I, i = e - t * I;  // write order: i fastest (coalesced); smem read is a stride-T gather (T = 9: no conflicts)
       float v = sw[i * T + t] * sb[i] * d;
