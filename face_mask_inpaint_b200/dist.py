@@ -60,7 +60,7 @@ def broadcast_module_state(module: torch.nn.Module, src: int = 0, group=None) ->
 
 
 class _Bucket:
-    __slots__ = ("params", "pending", "flat", "work", "launched")
+    __slots__ = ("params", "pending", "flat", "work", "launched", "averaged")
 
     def __init__(self, params):
         self.params: List[torch.nn.Parameter] = params
@@ -68,6 +68,7 @@ class _Bucket:
         self.flat = None
         self.work = None
         self.launched = False
+        self.averaged = False
 
 
 class GradientAllReducer:
@@ -107,12 +108,16 @@ class GradientAllReducer:
         if not live:
             return
         b.flat = torch.cat([p.grad.reshape(-1) for p in live])
+        # NCCL averages inside the collective; gloo has no AVG: sum here, one division per bucket in finish()
+        avg = b.flat.is_cuda and dist.get_backend(self.group) == "nccl"
+        b.averaged = avg
+        op = dist.ReduceOp.AVG if avg else dist.ReduceOp.SUM
         if self._comm_stream is not None:
             self._comm_stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self._comm_stream):
-                b.work = dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+                b.work = dist.all_reduce(b.flat, op=op, group=self.group, async_op=True)
         else:
-            b.work = dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            b.work = dist.all_reduce(b.flat, op=op, group=self.group, async_op=True)
 
     def attach(self, optimizer: torch.optim.Optimizer):
         optimizer.register_step_pre_hook(lambda opt, args, kwargs: self.finish())
@@ -132,11 +137,12 @@ class GradientAllReducer:
                 if self._comm_stream is not None:
                     torch.cuda.current_stream().wait_stream(self._comm_stream)
                 live = [p for p in b.params if p.grad is not None]
-                off = 0
-                for p in live:
-                    n = p.numel()
-                    p.grad.copy_(b.flat[off:off + n].view_as(p.grad) / self.world)
-                    off += n
+                if not b.averaged:
+                    b.flat.div_(self.world)
+                # one multi-tensor copy per bucket (a division + a copy per parameter was ~400 tiny launches per step: 3 ms
+                # of a 10 ms StyleGAN2 decoder step)
+                views = [v.view_as(p.grad) for v, p in zip(b.flat.split([p.numel() for p in live]), live)]
+                torch._foreach_copy_([p.grad for p in live], views)
             b.pending, b.flat, b.work, b.launched = len(b.params), None, None, False
 
     def remove(self):
