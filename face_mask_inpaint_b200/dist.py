@@ -3,13 +3,20 @@ inference needs no collective; training adds ONE gradient all-reduce (sum, then 
 
 The reference's train scripts call `backward()` and `optimizer.step()` inside `GANOptimizer.__call__`
 (modules/loss.py:126-132), so the all-reduce cannot be inserted by the caller. `GradientAllReducer` therefore hangs on
- * `Tensor.register_post_accumulate_grad_hook` of every trainable parameter — when all parameters of a bucket have their
-   gradient, the bucket is flattened and `all_reduce` is launched asynchronously (NCCL over NVLink/NVSwitch on GPUs, gloo
-   in the CPU tests), overlapping the rest of backward;
- * `Optimizer.register_step_pre_hook` — flushes buckets whose members never produced a gradient (14 tensors in PICNet:
-   `Auto_Attn.alpha`, `Auto_Attn.model.*`), waits, divides by the world size and writes the averaged
-   gradients back before the optimizer reads them.
-torch.distributed is plumbing here; no arithmetic of the hot path lives in this file.
+ * `Tensor.register_post_accumulate_grad_hook` of every trainable parameter — when every parameter a bucket expects has its
+   gradient, the bucket's PERSISTENT flat buffer is all-reduced in place, asynchronously (NCCL over NVLink/NVSwitch on GPUs,
+   gloo in the CPU tests), overlapping the rest of backward. `.grad` of every parameter is a VIEW into that buffer, so there is
+   no flatten and no copy back; a gradient that autograd allocated afresh (after `zero_grad(set_to_none=True)`) is moved into
+   its view with one multi-tensor copy per bucket;
+ * `Tensor.register_hook` (fires BEFORE accumulation) — a second backward between two optimizer steps (the GANOptimizer order:
+   G_loss.backward() runs through the unfrozen discriminator, then zero_grad, then D_loss.backward(); or plain gradient
+   accumulation) makes the compute stream wait for the bucket's in-flight collective and marks the bucket dirty;
+ * `Optimizer.register_step_pre_hook` — launches buckets whose members never produced a gradient (14 tensors in PICNet:
+   `Auto_Attn.alpha`, `Auto_Attn.model.*`), RE-reduces dirty buckets from the current gradients (averaging is
+   linear and idempotent on values already equal on all ranks, so avg(avg(g1) + g2) = avg(g1) + avg(g2)), and makes the
+   optimizer's stream wait for the collectives.
+Collectives are issued in bucket order on every rank. torch.distributed is plumbing here; no arithmetic of the hot path lives
+in this file.
 """
 from __future__ import annotations
 
@@ -60,90 +67,181 @@ def broadcast_module_state(module: torch.nn.Module, src: int = 0, group=None) ->
 
 
 class _Bucket:
-    __slots__ = ("params", "pending", "flat", "work", "launched", "averaged")
+    __slots__ = ("params", "flat", "views", "arrived", "n_arrived", "expect", "work", "launched", "dirty", "index")
 
-    def __init__(self, params):
+    def __init__(self, params, index):
         self.params: List[torch.nn.Parameter] = params
-        self.pending = len(params)
-        self.flat = None
+        self.index = index
+        p0 = params[0]
+        self.flat = torch.zeros(sum(p.numel() for p in params), dtype=p0.dtype, device=p0.device)
+        self.views = [v.view_as(p) for v, p in zip(self.flat.split([p.numel() for p in params]), params)]
+        self.arrived = [False] * len(params)
+        self.n_arrived = 0
+        self.expect = len(params)      # how many members must report before the bucket is launched from the hooks
         self.work = None
         self.launched = False
-        self.averaged = False
+        self.dirty = False
 
 
 class GradientAllReducer:
-    def __init__(self, params: Iterable[torch.nn.Parameter], bucket_bytes: int = 32 << 20, group=None):
+    """See the module docstring. `bucket_bytes` caps a bucket; the first bucket (the LAST layers, whose gradients arrive
+    first) and the last one (the first layers, whose collective cannot overlap anything) are capped at `edge_bytes`, so the
+    first collective starts early and the exposed tail after backward is short."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], bucket_bytes: int = 32 << 20, group=None,
+                 edge_bytes: Optional[int] = None):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         ps = [p for p in params if p.requires_grad]
         ps.reverse()  # gradients arrive roughly in reverse registration order
         self.buckets: List[_Bucket] = []
-        cur, cur_bytes = [], 0
-        for p in ps:
-            nbytes = p.numel() * p.element_size()
-            if cur and (cur_bytes + nbytes > bucket_bytes or p.dtype != cur[0].dtype or p.device != cur[0].device):
-                self.buckets.append(_Bucket(cur))
+        self._handles = []
+        self.enabled = True
+        self._comm_stream = None
+        self._next = 0
+        if self.world == 1 or not ps:
+            return
+        edge = min(bucket_bytes, edge_bytes if edge_bytes is not None else max(bucket_bytes // 16, 1 << 20))
+        sizes = [p.numel() * p.element_size() for p in ps]
+        # members of the tail bucket: the last parameters (in arrival order) that fit into `edge`
+        tail_from, acc = len(ps), 0
+        while tail_from > 1 and acc + sizes[tail_from - 1] <= edge:
+            tail_from -= 1
+            acc += sizes[tail_from]
+        groups, cur, cur_bytes = [], [], 0
+        for i, p in enumerate(ps):
+            cap = edge if not groups else bucket_bytes
+            if cur and (cur_bytes + sizes[i] > cap or i == tail_from or p.dtype != cur[0].dtype
+                        or p.device != cur[0].device):
+                groups.append(cur)
                 cur, cur_bytes = [], 0
             cur.append(p)
-            cur_bytes += nbytes
+            cur_bytes += sizes[i]
         if cur:
-            self.buckets.append(_Bucket(cur))
-        self._owner = {id(p): b for b in self.buckets for p in b.params}
-        self._handles = [p.register_post_accumulate_grad_hook(self._on_grad) for p in ps]
-        self._comm_stream = torch.cuda.Stream() if ps and ps[0].is_cuda else None
-        self.enabled = True
+            groups.append(cur)
+        self.buckets = [_Bucket(g, i) for i, g in enumerate(groups)]
+        self._owner = {id(p): (b, i) for b in self.buckets for i, p in enumerate(b.params)}
+        for p in ps:
+            self._handles.append(p.register_hook(self._make_pre(p)))
+            self._handles.append(p.register_post_accumulate_grad_hook(self._on_grad))
+        self._comm_stream = torch.cuda.Stream(ps[0].device) if ps[0].is_cuda else None
+        self._nccl_avg = ps[0].is_cuda and dist.get_backend(self.group) == "nccl"
 
     # ------------------------------------------------------------------ hooks
+    def _make_pre(self, p):
+        b, _ = self._owner[id(p)]
+
+        def pre(grad):                      # before autograd accumulates `grad` into p.grad
+            if self.enabled and b.launched:
+                self._wait(b)               # p.grad may be the buffer an in-flight collective is working on
+                b.dirty = True
+            return None
+        return pre
+
     def _on_grad(self, p):
-        if not self.enabled or self.world == 1:
+        if not self.enabled:
             return
-        b = self._owner[id(p)]
-        b.pending -= 1
-        if b.pending == 0:
-            self._launch(b)
+        b, i = self._owner[id(p)]
+        if b.launched:
+            b.dirty = True
+            return
+        if not b.arrived[i]:
+            b.arrived[i] = True
+            b.n_arrived += 1
+        # in bucket order only, so that every rank issues the same sequence of collectives
+        while self._next < len(self.buckets):
+            nb = self.buckets[self._next]
+            if nb.launched:
+                self._next += 1
+            elif nb.n_arrived >= nb.expect and nb.n_arrived > 0:
+                self._launch(nb)
+                self._next += 1
+            else:
+                break
+
+    def _adopt(self, b: _Bucket):
+        """Make every existing gradient of the bucket the view into its flat buffer (one multi-tensor copy for those that
+        are not). Members without a gradient keep `.grad is None` (the optimizer skips them); their slice holds zeros."""
+        src, dst = [], []
+        for p, v in zip(b.params, b.views):
+            g = p.grad
+            if g is None:
+                continue
+            if g.data_ptr() != v.data_ptr() or g.shape != v.shape or not g.is_contiguous():
+                src.append(g.detach())
+                dst.append(v)
+                p.grad = v
+        if src:
+            torch._foreach_copy_(dst, src)
+
+    def _wait(self, b: _Bucket):
+        if b.work is not None:
+            b.work.wait()                   # NCCL: the current stream waits for the collective; no host block
+            b.work = None
 
     def _launch(self, b: _Bucket):
-        live = [p for p in b.params if p.grad is not None]
-        b.launched = True
-        if not live:
-            return
-        b.flat = torch.cat([p.grad.reshape(-1) for p in live])
-        # NCCL averages inside the collective; gloo has no AVG: sum here, one division per bucket in finish()
-        avg = b.flat.is_cuda and dist.get_backend(self.group) == "nccl"
-        b.averaged = avg
-        op = dist.ReduceOp.AVG if avg else dist.ReduceOp.SUM
-        if self._comm_stream is not None:
+        self._wait(b)
+        self._adopt(b)
+        b.launched, b.dirty = True, False
+        if self._nccl_avg:
             self._comm_stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self._comm_stream):
-                b.work = dist.all_reduce(b.flat, op=op, group=self.group, async_op=True)
+                b.work = dist.all_reduce(b.flat, op=dist.ReduceOp.AVG, group=self.group, async_op=True)
         else:
-            b.work = dist.all_reduce(b.flat, op=op, group=self.group, async_op=True)
+            # gloo (CPU tests) has no AVG: sum, then divide at once so that the buffer always holds averaged values
+            if self._comm_stream is not None:
+                torch.cuda.current_stream().synchronize()
+            dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.group)
+            b.flat.div_(self.world)
 
-    def attach(self, optimizer: torch.optim.Optimizer):
+    def attach(self, optimizer: torch.optim.Optimizer, keep_views: bool = True):
+        """finish() before every optimizer.step(); and (keep_views) `optimizer.zero_grad()` keeps the gradient views alive (it
+        zeroes the flat buffers — one memset per bucket — instead of dropping the gradients) when every parameter of the
+        optimizer is managed here. Parameters that never had a gradient keep `.grad is None` either way."""
         optimizer.register_step_pre_hook(lambda opt, args, kwargs: self.finish())
+        if self.world > 1 and keep_views:
+            mine = {id(p) for b in self.buckets for p in b.params}
+            theirs = [p for g in optimizer.param_groups for p in g["params"] if p.requires_grad]
+            if all(id(p) in mine for p in theirs) and len(theirs) == len(mine):
+                plain = optimizer.zero_grad
+
+                def zero_grad(set_to_none: bool = True):
+                    if not self.enabled:
+                        return plain(set_to_none=set_to_none)
+                    self.zero_grad()
+                optimizer.zero_grad = zero_grad
         return self
 
     @torch.no_grad()
+    def zero_grad(self):
+        for b in self.buckets:
+            self._wait(b)
+            stray = [p for p, v in zip(b.params, b.views) if p.grad is not None and p.grad.data_ptr() != v.data_ptr()]
+            for p in stray:                 # gradients that are not views (assigned by the caller): drop them
+                p.grad = None
+            b.flat.zero_()
+            # whatever was reduced so far is gone: re-arm, so that the next backward launches from its hooks again
+            b.arrived = [False] * len(b.params)
+            b.n_arrived, b.launched, b.dirty = 0, False, False
+        self._next = 0
+
+    @torch.no_grad()
     def finish(self):
-        """Flush, wait, average, write back, re-arm. Called right before optimizer.step()."""
-        if self.world == 1:
+        """Launch what the hooks could not, re-reduce dirty buckets, make the current stream wait for every collective, and
+        re-arm. Called right before optimizer.step() (and callable by hand: gradients are final when it returns)."""
+        if self.world == 1 or not self.enabled:
             return
         for b in self.buckets:
-            if not b.launched:
+            if not b.launched or b.dirty or any(
+                    p.grad is not None and p.grad.data_ptr() != v.data_ptr() for p, v in zip(b.params, b.views)):
                 self._launch(b)
         for b in self.buckets:
-            if b.work is not None:
-                b.work.wait()
-                if self._comm_stream is not None:
-                    torch.cuda.current_stream().wait_stream(self._comm_stream)
-                live = [p for p in b.params if p.grad is not None]
-                if not b.averaged:
-                    b.flat.div_(self.world)
-                # one multi-tensor copy per bucket (a division + a copy per parameter was ~400 tiny launches per step: 3 ms
-                # of a 10 ms StyleGAN2 decoder step)
-                views = [v.view_as(p.grad) for v, p in zip(b.flat.split([p.numel() for p in live]), live)]
-                torch._foreach_copy_([p.grad for p in live], views)
-            b.pending, b.flat, b.work, b.launched = len(b.params), None, None, False
+            self._wait(b)
+            got = b.n_arrived
+            b.expect = got if got > 0 else len(b.params)
+            b.arrived = [False] * len(b.params)
+            b.n_arrived, b.launched, b.dirty = 0, False, False
+        self._next = 0
 
     def remove(self):
         for h in self._handles:

@@ -91,6 +91,108 @@ def test_gradient_allreduce_matches_single_process_step():
             assert torch.allclose(torch.from_numpy(sd[k]), want[k], atol=1e-6), (rank, k)
 
 
+class _G(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.a = torch.nn.Linear(6, 8)
+        self.b = torch.nn.Linear(8, 5)
+        self.alpha = torch.nn.Parameter(torch.zeros(1))     # never used, like Auto_Attn.alpha
+
+    def forward(self, x):
+        return self.b(torch.tanh(self.a(x)))
+
+
+class _D(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.a = torch.nn.Linear(5, 7)
+        self.b = torch.nn.Linear(7, 1)
+
+    def forward(self, x):
+        return self.b(torch.nn.functional.leaky_relu(self.a(x), 0.1))
+
+
+def _gan_steps(G, D, optG, optD, x, real, steps, set_to_none=True):
+    """The GANOptimizer.__call__ order (modules/loss.py:120-134): G_loss.backward() runs through the UNFROZEN discriminator
+    (freeze=False), then optimizer_D.zero_grad(), D_loss.backward(), optimizer_D.step()."""
+    for _ in range(steps):
+        fake = G(x)
+        g_loss = (D(fake) - 1).square().mean() + (fake - real).abs().mean()
+        optG.zero_grad(set_to_none=set_to_none)
+        g_loss.backward()
+        optG.step()
+        d_loss = 0.5 * ((D(real) - 1).square().mean() + D(fake.detach()).square().mean())
+        optD.zero_grad(set_to_none=set_to_none)
+        d_loss.backward()
+        optD.step()
+
+
+def _accum_steps(net, opt, x, y, steps, micro):
+    """Gradient accumulation: `micro` backwards, one step."""
+    for _ in range(steps):
+        opt.zero_grad()
+        for xs, ys in zip(x.chunk(micro), y.chunk(micro)):
+            (torch.nn.functional.mse_loss(net(xs), ys) / micro).backward()
+        opt.step()
+
+
+def _gan_data():
+    g = torch.Generator().manual_seed(3)
+    return torch.randn(8, 6, generator=g), torch.randn(8, 5, generator=g), torch.randn(8, 3, generator=g)
+
+
+def _worker_gan(rank, world, port, q, keep_views, set_to_none):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from face_mask_inpaint_b200 import dist as fd
+    fd.init_from_env("gloo")
+    torch.manual_seed(7)
+    G, D, net = _G(), _D(), Net()
+    x, real, y = _gan_data()
+    idx = list(fd.shard_batch(8, rank, world))
+    optG, optD = torch.optim.SGD(G.parameters(), lr=0.1), torch.optim.SGD(D.parameters(), lr=0.1)
+    fd.GradientAllReducer(G.parameters(), bucket_bytes=128).attach(optG, keep_views=keep_views)
+    rd = fd.GradientAllReducer(D.parameters(), bucket_bytes=128).attach(optD, keep_views=keep_views)
+    _gan_steps(G, D, optG, optD, x[idx], real[idx], 3, set_to_none)
+    opt = torch.optim.SGD(net.parameters(), lr=0.1)
+    fd.GradientAllReducer(net.parameters(), bucket_bytes=128).attach(opt, keep_views=keep_views)
+    # every rank accumulates over 2 micro-batches of its shard; shard mean = mean of the two micro means
+    _accum_steps(net, opt, x[idx], y[idx], 2, 2)
+    q.put((rank, {f"{n}.{k}": v.detach().numpy().copy() for n, m in (("G", G), ("D", D), ("net", net))
+                  for k, v in m.state_dict().items()}, len(rd.buckets)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("keep_views,set_to_none", [(True, True), (False, True), (False, False)])
+def test_gan_order_and_gradient_accumulation(keep_views, set_to_none):
+    """a parameter that gets more than one backward between optimizer steps. The discriminator's buckets are
+    reduced during G_loss.backward() (stale), then zero_grad + D_loss.backward(): the step must use the averaged D-loss
+    gradient. Same for gradient accumulation. Equality with the single-process step on the whole batch."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_gan, args=(r, world, port, q, keep_views, set_to_none)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    torch.manual_seed(7)
+    G, D, net = _G(), _D(), Net()
+    x, real, y = _gan_data()
+    optG, optD = torch.optim.SGD(G.parameters(), lr=0.1), torch.optim.SGD(D.parameters(), lr=0.1)
+    _gan_steps(G, D, optG, optD, x, real, 3)
+    opt = torch.optim.SGD(net.parameters(), lr=0.1)
+    _accum_steps(net, opt, x, y, 2, 1)
+    want = {f"{n}.{k}": v for n, m in (("G", G), ("D", D), ("net", net)) for k, v in m.state_dict().items()}
+    assert res[0][2] >= 2
+    for rank, sd, _ in res:
+        for k in want:
+            assert torch.allclose(torch.from_numpy(sd[k]), want[k], atol=2e-6), (rank, k)
+
+
 def test_shard_batch_covers_everything():
     from face_mask_inpaint_b200.dist import shard_batch
     for n in (0, 1, 7, 8, 13):
