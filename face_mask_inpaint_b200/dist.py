@@ -66,6 +66,36 @@ def broadcast_module_state(module: torch.nn.Module, src: int = 0, group=None) ->
         dist.broadcast(t.data, src=src, group=group)
 
 
+def enable_for_scripts() -> tuple[int, int, int]:
+    """Data-parallel training of an UNCHANGED reference script under torchrun (run.py): the scripts build their optimizers
+    themselves and call backward() / step() inside callees (modules/loss.py:126-132, train_psp.py:333-335), so the hooks go
+    on `torch.optim.Optimizer.__init__`: every optimizer gets its parameters broadcast from rank 0 (SpectralNorm's u / v are
+    parameters there, external_function.py:36-41) and a GradientAllReducer. Model construction runs under one common seed;
+    after the first optimizer exists every rank is re-seeded with its own seed, so DataLoader shuffling, rsample() and the
+    StyleGAN2 noise differ per rank (each rank trains on its own random batches). Only rank 0 writes checkpoints."""
+    import random
+    rank, local_rank, world = init_from_env()
+    if world == 1:
+        return rank, local_rank, world
+    torch.manual_seed(0)
+    random.seed(0)
+    plain_init = torch.optim.Optimizer.__init__
+
+    def init(self, params, defaults):
+        plain_init(self, params, defaults)
+        ps = [p for g in self.param_groups for p in g["params"]]
+        for p in ps:
+            dist.broadcast(p.data, src=0)
+        self._fmi_reducer = GradientAllReducer([p for p in ps if p.requires_grad]).attach(self)
+        torch.manual_seed(1000 + rank)
+        random.seed(1000 + rank)
+
+    torch.optim.Optimizer.__init__ = init
+    if rank != 0:
+        torch.save = lambda *a, **k: None
+    return rank, local_rank, world
+
+
 class _Bucket:
     __slots__ = ("params", "flat", "views", "arrived", "n_arrived", "expect", "work", "launched", "dirty", "index")
 

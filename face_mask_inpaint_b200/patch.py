@@ -53,6 +53,10 @@ def _rebind_everywhere(name: str, old, new):
 
 
 def _ensure_msssim_shim():
+    """`pytorch_msssim` (scripts: `from pytorch_msssim import SSIM, MS_SSIM`; dataloader.py:16) is not installed in every
+    environment and there is no network: provide the published algorithm (Gaussian 11-tap window, sigma 1.5, separable
+    valid-mode filtering; MS-SSIM = 5 scales, weights (0.0448, 0.2856, 0.3001, 0.2363, 0.1333), 2x2 average pooling between
+    scales). Metric code only — not on the hot path, runs on whatever device the tensors live on."""
     try:
         import pytorch_msssim  # noqa: F401
         return
@@ -61,30 +65,75 @@ def _ensure_msssim_shim():
     import torch
     import torch.nn.functional as F
 
-    def _gauss(size=11, sigma=1.5):
+    def _window(size, sigma, ch, like):
         c = torch.arange(size, dtype=torch.float32) - size // 2
         g = torch.exp(-(c ** 2) / (2 * sigma ** 2))
-        return g / g.sum()
+        g = (g / g.sum()).to(like.device, like.dtype)
+        return g.view(1, 1, 1, size).repeat(ch, 1, 1, 1)
 
-    def ssim(X, Y, data_range=255, size_average=True, **_):
-        ch = X.shape[1]
-        g = _gauss().to(X.device, X.dtype)
-        w = (g[:, None] * g[None, :]).expand(ch, 1, 11, 11).contiguous()
-        c1, c2 = (0.01 * data_range) ** 2, (0.03 * data_range) ** 2
-        mu_x, mu_y = F.conv2d(X, w, groups=ch), F.conv2d(Y, w, groups=ch)
-        sxx = F.conv2d(X * X, w, groups=ch) - mu_x ** 2
-        syy = F.conv2d(Y * Y, w, groups=ch) - mu_y ** 2
-        sxy = F.conv2d(X * Y, w, groups=ch) - mu_x * mu_y
-        m = ((2 * mu_x * mu_y + c1) * (2 * sxy + c2)) / ((mu_x ** 2 + mu_y ** 2 + c1) * (sxx + syy + c2))
-        v = m.flatten(1).mean(1)
+    def _filter(x, win):
+        ch = x.shape[1]
+        if x.shape[2] >= win.shape[-1]:
+            x = F.conv2d(x, win.transpose(2, 3), groups=ch)
+        if x.shape[3] >= win.shape[-1]:
+            x = F.conv2d(x, win, groups=ch)
+        return x
+
+    def _ssim_cs(X, Y, data_range, win, K=(0.01, 0.03)):
+        c1, c2 = (K[0] * data_range) ** 2, (K[1] * data_range) ** 2
+        mu_x, mu_y = _filter(X, win), _filter(Y, win)
+        sxx = _filter(X * X, win) - mu_x * mu_x
+        syy = _filter(Y * Y, win) - mu_y * mu_y
+        sxy = _filter(X * Y, win) - mu_x * mu_y
+        cs = (2 * sxy + c2) / (sxx + syy + c2)
+        sm = ((2 * mu_x * mu_y + c1) / (mu_x * mu_x + mu_y * mu_y + c1)) * cs
+        return sm.flatten(2).mean(-1), cs.flatten(2).mean(-1)
+
+    def ssim(X, Y, data_range=255, size_average=True, win_size=11, win_sigma=1.5, K=(0.01, 0.03), **_):
+        win = _window(win_size, win_sigma, X.shape[1], X)
+        v = _ssim_cs(X, Y, data_range, win, K)[0].mean(1)
         return v.mean() if size_average else v
 
-    def ms_ssim(X, Y, data_range=255, size_average=True, **kw):
-        # single-scale stand-in when the image is too small for 5 scales; metric only, not on the hot path
-        return ssim(X, Y, data_range=data_range, size_average=size_average)
+    def ms_ssim(X, Y, data_range=255, size_average=True, win_size=11, win_sigma=1.5, weights=None, K=(0.01, 0.03), **_):
+        if weights is None:
+            weights = [0.0448, 0.2856, 0.3001, 0.2363, 0.1333]
+        if min(X.shape[-2:]) <= (win_size - 1) * 2 ** (len(weights) - 1):
+            raise AssertionError("Image size should be larger than %d due to the 4 downsamplings in ms-ssim"
+                                 % ((win_size - 1) * 2 ** (len(weights) - 1)))
+        w = torch.tensor(weights, device=X.device, dtype=X.dtype)
+        win = _window(win_size, win_sigma, X.shape[1], X)
+        mcs = []
+        for i in range(len(weights)):
+            s, cs = _ssim_cs(X, Y, data_range, win, K)
+            if i < len(weights) - 1:
+                mcs.append(torch.relu(cs))
+                pad = [d % 2 for d in X.shape[2:]]
+                X, Y = F.avg_pool2d(X, 2, padding=pad), F.avg_pool2d(Y, 2, padding=pad)
+        vals = torch.stack(mcs + [torch.relu(s)], dim=0)                 # [levels, N, C]
+        v = torch.prod(vals ** w.view(-1, 1, 1), dim=0).mean(1)
+        return v.mean() if size_average else v
+
+    class SSIM(torch.nn.Module):
+        def __init__(self, data_range=255, size_average=True, win_size=11, win_sigma=1.5, channel=3, spatial_dims=2,
+                     K=(0.01, 0.03), nonnegative_ssim=False):
+            super().__init__()
+            self.kw = dict(data_range=data_range, size_average=size_average, win_size=win_size, win_sigma=win_sigma, K=K)
+
+        def forward(self, X, Y):
+            return ssim(X, Y, **self.kw)
+
+    class MS_SSIM(torch.nn.Module):
+        def __init__(self, data_range=255, size_average=True, win_size=11, win_sigma=1.5, channel=3, spatial_dims=2,
+                     weights=None, K=(0.01, 0.03)):
+            super().__init__()
+            self.kw = dict(data_range=data_range, size_average=size_average, win_size=win_size, win_sigma=win_sigma,
+                           weights=weights, K=K)
+
+        def forward(self, X, Y):
+            return ms_ssim(X, Y, **self.kw)
 
     shim = types.ModuleType("pytorch_msssim")
-    shim.ssim, shim.ms_ssim = ssim, ms_ssim
+    shim.ssim, shim.ms_ssim, shim.SSIM, shim.MS_SSIM = ssim, ms_ssim, SSIM, MS_SSIM
     sys.modules["pytorch_msssim"] = shim
 
 
