@@ -1,21 +1,28 @@
 #!/usr/bin/env python
-"""bench.py — headline measurement of the B200-native hot path.
+"""bench.py — images/sec of the generator hot path on B200 (BASELINE.json's metric, on BASELINE.json's configs).
 
-Workload (BASELINE.json configs[1], the reference-attention microbench at its largest shape):
-  ExampleGuidedAttention(256) forward on C=256 feature maps at 128x128 (S = 16384, d = 64, 512 value channels),
-  per-GPU batch 8, fp32 inputs/outputs (TF32 tensor-core operands, fp32 softmax/accumulation — the fp32 parity
-  contract, max rel err <= 1e-3). One "step" = one forward over one batch. Metric: images/sec.
+    python bench.py --gpus N --steps K --warmup W [--workload NAME] [--impl ours|reference|gpu_reference] [--no-extras]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
-  value       device-resident inputs, CUDA-event timed, max over ranks
-  e2e         the same step through the public module API from pinned HOST buffers (H2D of src/ref/mask and D2H of the
-              output inside the timed region)
-  roofline    the dominant kernel (attn_fwd2_kernel) timed live with CUDA events on its own launch stream
-  cpu_baseline / --impl reference : the reference's algorithm (oracle/ref_ops.py, PyTorch CPU, all host threads) on a
-              bounded sample of the same workload
-  whole_models  (extra key, not the bench line) forward img/s of the two generators BASELINE.json's metric names:
-              PICNet-ref 256^2 (per-GPU batch 4) and RefpSp 1024^2 (per-GPU batch 8, bf16 operands); --no-models skips it
+Workloads (one "step" = one pass over one per-GPU batch of synthetic inputs; per-GPU batch fixed = weak scaling):
+  picnet_ref    (default, headline) configs[0]: PICNet-ref `ReferenceFill` forward, 256^2, batch 4, fp32 I/O
+  refpsp        configs[2]: RefpSp `pSp` forward (IR-SE50 encoder x2 + attention + StyleGAN2-1024), batch 8, bf16 operands
+  train_picnet  configs[3]: train_reference_fill.py's step — G forward, GANOptimizer (D forward x2, VGG perceptual / style /
+                contextual losses, both backwards, both Adam steps), batch 4 per GPU, NCCL gradient all-reduce when N > 1
+  train_psp     configs[4]: train_psp.py's step with --train_decoder --use_ref --use_attention --randomize_noise, batch 2 per
+                GPU, bf16 operands, NCCL gradient all-reduce when N > 1
+The default run prints ONE JSON line for `picnet_ref` and carries the other three as full records under "records"
+(--no-extras skips them), so the driver's 1/2/4/8-GPU runs also time the training steps with their collectives.
 
-  python bench.py --gpus N --steps K --warmup W [--impl reference]
+Keys of a record:
+  value         whole-job img/s, inputs resident in HBM, CUDA events per step, L2 flushed between steps, max over ranks
+  e2e           the same through the public call from pinned HOST buffers: H2D of the step's inputs + forward (+ loss /
+                backward / optimizer) + D2H of the result inside the timed region
+  roofline      the dominant kernel of the step, timed per launch with CUDA events on its launch stream (fmi_profile_*) in an
+                eager pass of the same step; `kernels` lists every timed kernel with its share of the step
+  cpu_baseline  (N = 1) the UNMODIFIED reference (baseline/_ref, a verbatim copy) on the host cores, bounded sample
+  gpu_reference the UNMODIFIED reference on the same B200 (its own formulation: ATen / cuBLAS / cuDNN + its two CUDA ops)
+`--impl reference`: the reference arm — the unmodified reference module(s) of the workload on the host cores, same `config`.
 """
 from __future__ import annotations
 
@@ -34,29 +41,42 @@ import torch
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-C, HW, D, BATCH = 256, 128, 64, 8
-S = HW * HW
-WORKLOAD = ("configs[1]: ExampleGuidedAttention(256) forward, 128x128 feature maps (S=16384, d=64, 512 value "
-            "channels), per-GPU batch 8, fp32 I/O")
+WORKLOADS = {
+    "picnet_ref": dict(batch=4, dtype="tf32", cfg="configs[0]: PICNet ref-guided generator (ReferenceFill) forward, 256x256, "
+                       "use_att=1, decoder_img_f=256 decoder_z_nc=256, random-init, synthetic masked / reference / mask inputs"),
+    "refpsp": dict(batch=8, dtype="bf16", cfg="configs[2]: RefpSp inference (pSp: IR-SE50 GradualStyleEncoder on source + "
+                   "reference, attention1/2, StyleGAN2 1024x1024 decoder, face_pool to 256x256), randomize_noise=False"),
+    "train_picnet": dict(batch=4, dtype="tf32", cfg="configs[3]: PICNet reference-fill GAN train step (train_reference_fill.py: "
+                         "generator forward + GANOptimizer: D forward x2, VGG16 perceptual/style/contextual losses, G and D "
+                         "backward, Adam x2), 256x256, random-init VGG16"),
+    "train_psp": dict(batch=2, dtype="bf16", cfg="configs[4]: RefpSp decoder + attention training step (train_psp.py "
+                      "--train_decoder 1 --use_ref --use_attention --randomize_noise 1: pSp forward 1024x1024, pSpLoss "
+                      "(masked L2 + LPIPS-alex + VGG style/contextual), backward, Adam), random-init loss networks"),
+}
 
 
-def algorithmic_flops_per_image() -> float:
-    """2*S^2*d (QK^T) + 2*S^2*Cv (both value products, Cv = 2C) + q-conv 2*C*d*S."""
-    return 2.0 * S * S * D + 2.0 * S * S * (2 * C) + 2.0 * C * D * S
+def workload_config(name: str, n_gpus: int) -> dict:
+    """The `config` object — identical in both arms (the driver compares them)."""
+    w = WORKLOADS[name]
+    return {"workload": w["cfg"], "name": name, "per_gpu_batch": w["batch"], "global_batch": w["batch"] * n_gpus,
+            "image": "256x256 inputs" + (", 1024x1024 synthesis" if "psp" in name else ", 1024x1024 decoder output pooled to 256x256"),
+            "l2": "a 256 MiB buffer is overwritten between timed steps (L2 = 126 MB); per-step activations are > 1 GB anyway",
+            "parallelism": f"batch-sharded x{n_gpus}" + (", NCCL gradient all-reduce" if name.startswith("train") and n_gpus > 1
+                                                          else ", no collective")}
 
 
-def make_inputs(device, seed):
+# ------------------------------------------------------------------------------------------------------------ inputs
+def make_inputs(name: str, batch: int, seed: int):
+    """U[0,1) images (PICNet) / U[-1,1) (pSp), binary mask = lower-face rectangle (+ Bernoulli(0.3) speckle)."""
     g = torch.Generator(device="cpu").manual_seed(seed)
-    src = torch.randn(BATCH, C, HW, HW, generator=g)
-    ref = torch.randn(BATCH, C, HW, HW, generator=g)
-    mask = (torch.rand(BATCH, 1, 256, 256, generator=g) < 0.3).float()
-    mask[:, :, 128:230, 50:206] = 1.0
-    mask = torch.nn.functional.interpolate(mask, size=(HW, HW), mode="bilinear", align_corners=True)
-    wq = torch.randn(D, C, 1, 1, generator=g) / C ** 0.5
-    # scale the query weight so the logit std is ~1 (near-uniform softmax would make the work trivial to fake)
-    q = torch.nn.functional.conv2d(src[:1, :, :32, :32], wq).flatten(2)
-    wq = wq * (1.0 / (q.transpose(1, 2) @ q).std().clamp_min(1e-6)) ** 0.5
-    return src, ref, mask, wq
+    src = torch.rand(batch, 3, 256, 256, generator=g)
+    ref = torch.rand(batch, 3, 256, 256, generator=g)
+    gt = torch.rand(batch, 3, 256, 256, generator=g)
+    mask = (torch.rand(batch, 256, 256, generator=g) < 0.3).float() if "picnet" in name else torch.zeros(batch, 256, 256)
+    mask[:, 128:230, 50:206] = 1.0
+    if "psp" in name:
+        src, ref, gt = src * 2 - 1, ref * 2 - 1, gt * 2 - 1
+    return src, ref, gt, mask
 
 
 class ClockSampler:
@@ -114,365 +134,615 @@ def measured_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
         d = json.loads(p.read_text())
-        return d.get("bf16_tflops_sustained", 1403.9), d.get("hbm_gbs", 6456.8), "measured"
-    return 1400.0, 6650.0, "fallback"
+        return {"hbm_gbs": d.get("hbm_gbs", 6456.8), "bf16_tflops": d.get("bf16_tflops", 1667.1),
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", 1403.9), "source": "MEASURED_PEAKS.json (measured)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1400.0, "bf16_tflops_sustained": 1400.0,
+            "source": "B200_PROFILING.md fallback (MEASURED_PEAKS.json absent)"}
 
 
-def cpu_reference_images_per_sec(budget_s: float, rows: int | None, steps: int | None, warmup: int = 0):
-    """Times the oracle (the reference's PyTorch algorithm) on the host cores on a bounded sample: `rows` query pixels
-    of one image per step (all S keys, both value products, the blend). Returns (img/s, description, cores)."""
-    from oracle import ref_ops as O
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    src, ref, mask, wq = make_inputs("cpu", 0)
-    src, ref, mask = src[:1], ref[:1], mask[:1]
-    if rows is None:
-        rows = 1024
-    idx = torch.arange(0, S, S // rows)[:rows]
-    with torch.no_grad():
-        for _ in range(max(1, warmup)):
-            O.example_guided_attention_rows(mask, src, ref, wq, idx)
-        t0 = time.perf_counter()
-        n = 0
-        while True:
-            O.example_guided_attention_rows(mask, src, ref, wq, idx)
-            n += 1
-            el = time.perf_counter() - t0
-            if (steps is not None and n >= steps) or (steps is None and el >= budget_s):
-                break
-    el = time.perf_counter() - t0
-    value = n * (rows / S) / el
-    sample = (f"{n} steps x {rows} of {S} query rows of one 256-ch 128x128 image (q-conv over all pixels, softmax over "
-              f"all {S} keys, both value products, masked blend), PyTorch CPU fp32, {cores} threads")
-    return value, sample, cores, el / n * 1e3
+# ------------------------------------------------------------------------------------------------------------ harness
+class Harness:
+    def __init__(self, args):
+        import torch.distributed as dist
+        self.dist = dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        if not torch.cuda.is_available():
+            raise RuntimeError("bench.py: no CUDA device — the product path has no CPU fallback")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1 and not dist.is_initialized():
+            import datetime
+            dist.init_process_group("nccl", device_id=self.dev, timeout=datetime.timedelta(minutes=30))
+            dist.barrier(device_ids=[self.local_rank])
+        self.steps, self.warmup = args.steps, max(3, args.warmup)
+        self._flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)
+        from face_mask_inpaint_b200 import _lib
+        self.lib = _lib.load()
+        _lib.check(self.lib.fmi_device_check(), "fmi_device_check")
 
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier(device_ids=[self.local_rank])
+        torch.cuda.synchronize()
 
-def run_reference(args, rank, world):
-    if rank != 0:
-        return
-    # per-step sample sized so that (steps + warmup) steps end within ~2 minutes
-    _, _, _, ms1 = cpu_reference_images_per_sec(0.0, 256, 1, 1)
-    per_row_ms = ms1 / 256
-    budget_ms = 120e3 / max(1, args.steps + args.warmup)
-    rows = int(max(64, min(S, budget_ms / max(per_row_ms, 1e-6))))
-    rows = 1 << (rows.bit_length() - 1)  # power of two divides S
-    value, sample, cores, ms = cpu_reference_images_per_sec(0.0, rows, args.steps, args.warmup)
-    line = {"impl": "reference", "metric": "images/sec", "value": value, "unit": "img/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "per_gpu_batch": BATCH, "C": C, "H": HW, "W": HW, "d": D},
-            "cpu_baseline": {"value": value, "unit": "img/s", "cores": cores, "kind": "port", "sample": sample},
-            "e2e": {"value": value, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    def max_over_ranks(self, ms: float) -> float:
+        if self.world == 1:
+            return ms
+        t = torch.tensor([ms], device=self.dev, dtype=torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
 
+    def timed(self, step, steps=None, warmup=None) -> float:
+        """W untimed steps, then exactly K steps, each between its own pair of CUDA events with the L2 overwritten before it;
+        barrier + synchronize on both sides; mean step time, max over ranks."""
+        steps = steps or self.steps
+        for _ in range(self.warmup if warmup is None else warmup):
+            step()
+        self.barrier()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for e0, e1 in evs:
+            self._flush.fill_(1)
+            e0.record()
+            step()
+            e1.record()
+        self.barrier()
+        return self.max_over_ranks(sum(e0.elapsed_time(e1) for e0, e1 in evs) / steps)
 
-def whole_model_throughput(dev, world, barrier, max_over_ranks):
-    """images/sec of the two generators BASELINE.json's metric names, forward only, synthetic inputs resident on the
-    device, per-GPU batch fixed (weak scaling), max over ranks: PICNet-ref 256^2 (modules/picnet.py, per-GPU batch 4, fp32
-    contract) and RefpSp 1024^2 (modules/psp.py, per-GPU batch 8, bf16 operands). PICNet: attention, compositing and the
-    encoder / decoder conv blocks are this package's kernels. RefpSp: attention, compositing and the whole
-    StyleGAN2 decoder are; its IR-SE50 trunk is cuDNN (8f rank 2, not started). Each forward is one CUDA-graph replay.
-    Failures are reported, not raised: the bench line above does not depend on this block."""
-    out = {}
-    iters = 5
-
-    def timed(fn):
-        for _ in range(2):
-            fn()
-        barrier()
+    # ---- per-kernel records of an eager pass (fmi_profile_dump) -> kernel table + roofline of the dominant kernel
+    def profile(self, step, steps, tensor_peak_tf, peaks):
+        lib = self.lib
+        for k in range(lib.fmi_profile_kinds()):     # drop anything recorded earlier
+            n = ctypes.c_int(0)
+            lib.fmi_profile_dump(k, None, None, None, 0, ctypes.byref(n))
+        step()
+        torch.cuda.synchronize()
+        lib.fmi_profile_enable(1)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(iters):
-            fn()
+        for _ in range(steps):
+            step()
         e1.record()
-        barrier()
-        return max_over_ranks(e0.elapsed_time(e1) / iters)
+        torch.cuda.synchronize()
+        lib.fmi_profile_enable(0)
+        eager_ms = e0.elapsed_time(e1) / steps
+        cap = 1 << 16
+        ms_b, fl_b, by_b = (ctypes.c_double * cap)(), (ctypes.c_double * cap)(), (ctypes.c_double * cap)()
+        kernels = []
+        for k in range(lib.fmi_profile_kinds()):
+            n = ctypes.c_int(0)
+            lib.fmi_profile_dump(k, ms_b, fl_b, by_b, cap, ctypes.byref(n))
+            if n.value == 0:
+                continue
+            recs = [(ms_b[i], fl_b[i], by_b[i]) for i in range(n.value)]
+            t = sum(r[0] for r in recs) * 1e-3
+            fl, by = sum(r[1] for r in recs), sum(r[2] for r in recs)
+            sol = sum(max(r[2] / (peaks["hbm_gbs"] * 1e9), r[1] / (tensor_peak_tf * 1e12)) for r in recs)
+            hbm_sol = sum(r[2] / (peaks["hbm_gbs"] * 1e9) for r in recs
+                          if r[2] / (peaks["hbm_gbs"] * 1e9) >= r[1] / (tensor_peak_tf * 1e12))
+            groups = {}
+            for ms, f, b in recs:
+                g = groups.setdefault((f, b), [0, 0.0])
+                g[0] += 1
+                g[1] += ms
+            top = sorted(groups.items(), key=lambda kv: -kv[1][1])[:4]
+            kernels.append({
+                "kernel": lib.fmi_profile_kind_name(k).decode(), "launches_per_step": n.value / steps,
+                "ms_per_step": t * 1e3 / steps, "algorithmic_gflop_per_step": fl / steps / 1e9,
+                "algorithmic_mb_per_step": by / steps / 1e6, "tflops": fl / t / 1e12 if t > 0 else 0.0,
+                "gbs": by / t / 1e9 if t > 0 else 0.0, "sol_frac": sol / t if t > 0 else 0.0,
+                "hbm_bound_share_of_sol": hbm_sol / sol if sol > 0 else 0.0,
+                "top_launches": [{"count_per_step": c / steps, "avg_us": 1e3 * ms / c, "gflop": f / 1e9, "mb": b / 1e6,
+                                  "tflops": f / (ms / c * 1e-3) / 1e12, "gbs": b / (ms / c * 1e-3) / 1e9,
+                                  "sol_frac": max(b / (peaks["hbm_gbs"] * 1e9), f / (tensor_peak_tf * 1e12)) / (ms / c * 1e-3)}
+                                 for (f, b), (c, ms) in top]})
+        timed_ms = sum(k["ms_per_step"] for k in kernels)
+        for k in kernels:
+            k["share_of_timed_kernels"] = k["ms_per_step"] / timed_ms if timed_ms else 0.0
+            k["share_of_eager_step"] = k["ms_per_step"] / eager_ms if eager_ms else 0.0
+        kernels.sort(key=lambda k: -k["ms_per_step"])
+        return kernels, eager_ms
 
-    def e2e(fwd, host_in, out_dev):
-        """The same forward from pinned HOST inputs to a pinned HOST result, every step: H2D of the step's inputs into the
-        graph's static buffers, one replay, D2H of the image — all on the current stream, no host synchronisation inside."""
+
+def roofline_of(kernels, peaks, tensor_peak_tf, operand, traffic=None):
+    """The dominant kernel (largest summed duration per step) on its roofline. A kernel with heterogeneous launches (the
+    implicit-GEMM conv serves HBM-bound 1024^2 layers and tensor-bound 64^2 layers) is put on the roofline that bounds most
+    of its speed-of-light time; `sol_frac` = sum over launches of max(bytes / HBM, flops / tensor) / measured time."""
+    if not kernels:
+        return None
+    k = kernels[0]
+    hbm = k["hbm_bound_share_of_sol"] >= 0.5
+    out = {"bound": "hbm" if hbm else "tensor", "kernel": k["kernel"], "achieved": k["gbs"] if hbm else k["tflops"],
+           "peak": peaks["hbm_gbs"] if hbm else tensor_peak_tf, "unit": "GB/s" if hbm else "TFLOP/s",
+           "traffic": traffic, "sol_frac": k["sol_frac"], "ms_per_step": k["ms_per_step"],
+           "launches_per_step": k["launches_per_step"], "share_of_timed_kernels": k["share_of_timed_kernels"],
+           "algorithmic_bytes_per_step": k["algorithmic_mb_per_step"] * 1e6,
+           "algorithmic_flops_per_step": k["algorithmic_gflop_per_step"] * 1e9,
+           "peak_source": f"{peaks['source']}: HBM copy {peaks['hbm_gbs']} GB/s; tensor {tensor_peak_tf:.0f} TFLOP/s = burst bf16 "
+                          f"{peaks['bf16_tflops']}" + (" / 2 (kind::tf32 MMAs run at half the bf16 rate)" if operand == "tf32" else ""),
+           "how": "CUDA events around every launch on its own stream during an eager pass of the same step (the timed `value` "
+                  "replays a CUDA graph of the same launches); algorithmic bytes = inputs once + outputs once + weights once"}
+    out["frac"] = out["achieved"] / out["peak"]
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------ ours: forward
+def _forward_record(h: Harness, name, net, call_args, kw_tensors, kw_other, dtype, what):
+    """`call_args` / `kw_tensors`: HOST tensors (positional / keyword) of one step; `kw_other`: the non-tensor keywords."""
+    from face_mask_inpaint_b200.graphs import CapturedForward
+    w = WORKLOADS[name]
+    b = w["batch"]
+    peaks = measured_peaks()
+    tensor_peak = peaks["bf16_tflops"] / (2.0 if dtype == "tf32" else 1.0)
+    with torch.no_grad():
+        host_in = [t.pin_memory() for t in list(call_args) + list(kw_tensors.values())]   # CapturedForward's flatten order
+        dev_in = [t.to(h.dev) for t in call_args]
+        call_kwargs = {**{k: t.to(h.dev) for k, t in kw_tensors.items()}, **kw_other}
+        for _ in range(2):
+            out = net(*dev_in, **call_kwargs)
+        torch.cuda.synchronize()
+        n0 = h.lib.fmi_kernel_launch_count()
+        out = net(*dev_in, **call_kwargs)
+        torch.cuda.synchronize()
+        launches = h.lib.fmi_kernel_launch_count() - n0
+        kernels, eager_ms = h.profile(lambda: net(*dev_in, **call_kwargs), min(h.steps, 5), tensor_peak, peaks)
+        fwd = CapturedForward(net, *dev_in, **call_kwargs)
+        sampler = ClockSampler(h.local_rank) if h.rank == 0 else None
+        ms = h.timed(fwd.replay)
+        # end to end: pinned host inputs -> the graph's static inputs, one replay, result -> pinned host
+        out_dev = fwd.replay()
+        out_dev = out_dev[0] if isinstance(out_dev, (tuple, list)) else out_dev
         host_out = torch.empty(out_dev.shape, dtype=out_dev.dtype, pin_memory=True)
         stat = fwd.static_inputs
 
-        def step():
+        def e2e_step():
             for dst, src in zip(stat, host_in):
                 dst.copy_(src, non_blocking=True)
             fwd.replay()
             host_out.copy_(out_dev, non_blocking=True)
 
-        ms = timed(step)
-        return ms, sum(t.numel() * t.element_size() for t in host_in), host_out.numel() * host_out.element_size()
+        ms_e2e = h.timed(e2e_step)
+        clocks = sampler.stop() if sampler else None
+        if not torch.isfinite(host_out).all():
+            raise RuntimeError(f"{name}: non-finite output")
+    rec = {"metric": "images/sec", "value": h.world * b / (ms * 1e-3), "unit": "img/s", "n_gpus": h.world, "steps": h.steps,
+           "warmup": h.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": dtype, "data": "synthetic", "config": workload_config(name, h.world), "clocks": clocks,
+           "e2e": {"value": h.world * b / (ms_e2e * 1e-3), "unit": "img/s", "ms_per_step": ms_e2e,
+                   "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in host_in),
+                   "d2h_bytes_per_step": host_out.numel() * host_out.element_size(),
+                   "api": "pinned host tensors -> static inputs of graphs.CapturedForward(model.forward) -> pinned host image"},
+           "gpu_launches": int(launches) * h.steps,
+           "launch": f"one CUDA-graph replay per forward capturing {int(launches)} sm_100a kernel launches of this package",
+           "eager_ms_per_step": eager_ms, "what": what,
+           "roofline": roofline_of(kernels, peaks, tensor_peak, dtype), "kernels": kernels}
+    del fwd
+    return rec
 
+
+def ours_picnet_ref(h: Harness):
+    from face_mask_inpaint_b200.modules.picnet import build_picnet_ref
+    torch.manual_seed(7)
+    net = build_picnet_ref().eval().to(h.dev)
+    with torch.no_grad():
+        net.decoder.attn1.gamma.fill_(1.0)     # init 0 would switch the attention branch off (SURVEY §7 'random init hides bugs')
+    src, ref, _, mask = make_inputs("picnet_ref", WORKLOADS["picnet_ref"]["batch"], 1000 + h.rank)
+    rec = _forward_record(h, "picnet_ref", net, [src, ref, mask], {}, {}, "tf32",
+                          "ReferenceFill.forward (modules/model.py:81-112): 2 ResEncoders, ExampleGuidedAttention@32^2, ResGenerator "
+                          "with Auto_Attn@128^2 up to 1024^2, AdaptiveAvgPool to 256^2 — every conv block, both attentions, the "
+                          "compositing and the pooling on this package's sm_100a kernels")
+    rec["precision"] = ("fp32 I/O; TF32 tensor-core operands where the reference's own GPU run has them (cuDNN allow_tf32 default) "
+                        "and in the attention (hi/lo split logits), fp32 accumulation / softmax / InstanceNorm")
+    return rec
+
+
+def ours_refpsp(h: Harness):
+    from face_mask_inpaint_b200.modules.psp import pSp, refpsp_opts
     prev = os.environ.get("FMI_PRECISION")
+    os.environ["FMI_PRECISION"] = "bf16"
     try:
-        with torch.no_grad():
-            from face_mask_inpaint_b200.graphs import CapturedForward
-            from face_mask_inpaint_b200.modules.picnet import build_picnet_ref
-            torch.manual_seed(7)
-            net = build_picnet_ref().eval().to(dev)
-            with torch.no_grad():
-                net.decoder.attn1.gamma.fill_(1.0)
-            b = 4
-            src, ref = torch.rand(b, 3, 256, 256, device=dev), torch.rand(b, 3, 256, 256, device=dev)
-            mask = torch.zeros(b, 256, 256, device=dev)
-            mask[:, 128:230, 50:206] = 1.0
-            ms_eager = timed(lambda: net(src, ref, mask))
-            fwd = CapturedForward(net, src, ref, mask)
-            ms = timed(lambda: fwd(src, ref, mask))
-            ms_e2e, bi, bo = e2e(fwd, [t.cpu().pin_memory() for t in (src, ref, mask)], fwd(src, ref, mask))
-            out["picnet_ref_256"] = {"value": world * b / (ms * 1e-3), "unit": "img/s", "per_gpu_batch": b, "ms_per_step": ms,
-                                     "e2e": {"value": world * b / (ms_e2e * 1e-3), "unit": "img/s", "ms_per_step": ms_e2e,
-                                             "h2d_bytes_per_step": bi, "d2h_bytes_per_step": bo},
-                                     "launch": "one CUDA-graph replay per forward (graphs.CapturedForward)",
-                                     "eager_ms_per_step": ms_eager, "eager_value": world * b / (ms_eager * 1e-3),
-                                     "precision": "fp32 I/O; TF32 tensor-core operands (attention and conv blocks), fp32 "
-                                                  "accumulation, fp32 Output conv",
-                                     "what": "ReferenceFill forward: 2 encoders, ExampleGuidedAttention@32^2, decoder with "
-                                             "Auto_Attn@128^2 up to 1024^2, pooled to 256^2; encoder / decoder conv blocks on "
-                                             "this package's implicit-GEMM kernels (SURVEY 8f rank 1), z->f ResBlock on cuDNN"}
-            del net, fwd
-            from face_mask_inpaint_b200.modules.psp import pSp, refpsp_opts
-            os.environ["FMI_PRECISION"] = "bf16"
-            net = pSp(refpsp_opts(output_size=1024)).eval().to(dev)
-            b = 8
-            x, ref = torch.rand(b, 3, 256, 256, device=dev) * 2 - 1, torch.rand(b, 3, 256, 256, device=dev) * 2 - 1
-            mask = torch.zeros(b, 256, 256, device=dev)
-            mask[:, 128:230, 50:206] = 1.0
-            ms_eager = timed(lambda: net(x, ref=ref, src_mask=mask, resize=True, randomize_noise=False))
-            fwd = CapturedForward(net, x, ref=ref, src_mask=mask, resize=True, randomize_noise=False)
-            ms = timed(lambda: fwd(x, ref=ref, src_mask=mask))
-            ms_e2e, bi, bo = e2e(fwd, [t.cpu().pin_memory() for t in (x, ref, mask)], fwd(x, ref=ref, src_mask=mask))
-            psp_e2e = {"value": world * b / (ms_e2e * 1e-3), "unit": "img/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": bi,
-                       "d2h_bytes_per_step": bo}
-            del fwd
-            codes = net.encoder(x, ref=ref, mask=mask)
-            ms_dec = timed(lambda: net.decoder([codes], input_is_latent=True, randomize_noise=False))
-            out["refpsp_1024"] = {"value": world * b / (ms * 1e-3), "unit": "img/s", "per_gpu_batch": b, "ms_per_step": ms,
-                                  "launch": "one CUDA-graph replay per forward (graphs.CapturedForward)",
-                                  "e2e": psp_e2e,
-                                  "eager_ms_per_step": ms_eager, "eager_value": world * b / (ms_eager * 1e-3),
-                                  "decoder_only_ms": ms_dec, "decoder_only_img_s": world * b / (ms_dec * 1e-3),
-                                  "precision": "bf16 tensor-core operands in the decoder and attention, cuDNN trunk fp32/TF32",
-                                  "what": "pSp forward: IR-SE50 GradualStyleEncoder on source+reference, attention1/2, masked "
-                                          "blend, StyleGAN2-1024 decoder, face_pool to 256^2"}
-            del net
-    except Exception as ex:  # noqa: BLE001
-        out["error"] = f"{type(ex).__name__}: {str(ex)[:300]}"
+        torch.manual_seed(11)
+        net = pSp(refpsp_opts(output_size=1024)).eval().to(h.dev)
+        x, ref, _, mask = make_inputs("refpsp", WORKLOADS["refpsp"]["batch"], 2000 + h.rank)
+        rec = _forward_record(h, "refpsp", net, [x], dict(ref=ref, src_mask=mask), dict(resize=True, randomize_noise=False), "bf16", "pSp.forward (modules/psp/psp.py:72-130): IR-SE50 GradualStyleEncoder on source + reference "
+                              "(one 2N batch), attention1/2, masked blend, 18 map2style heads, StyleGAN2-1024 decoder, face_pool")
+        rec["precision"] = "fp32 I/O; bf16 tensor-core operands (FMI_PRECISION=bf16), fp32 accumulation"
+        return rec
     finally:
         if prev is None:
             os.environ.pop("FMI_PRECISION", None)
         else:
             os.environ["FMI_PRECISION"] = prev
-        torch.cuda.empty_cache()
-    return out
 
 
-def run_ours(args, rank, local_rank, world):
-    import torch.distributed as dist
-    from face_mask_inpaint_b200 import _lib
-    from face_mask_inpaint_b200.modules import ExampleGuidedAttention
+# ------------------------------------------------------------------------------------------------------------ ours: training
+def _patched_reference():
+    """The reference's own training harness (GANOptimizer, pSpLoss, define_d, ReferenceFill / pSp classes) from the verbatim copy
+    baseline/_ref with this package's drop-ins installed over it — what `python -m face_mask_inpaint_b200.run train_*.py` runs."""
+    from baseline import reference as R
+    if not R.available():
+        raise FileNotFoundError("baseline/_ref is missing (made by __graft_entry__.build() where /root/reference exists)")
+    from face_mask_inpaint_b200 import patch
+    from face_mask_inpaint_b200.offline import stub_pretrained
+    patch.install(str(R.REF))
+    stub_pretrained()
+    return R
 
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py: no CUDA device — the product path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        # NCCL writes its version banner to file descriptor 1 when its communicator is created, whatever NCCL_DEBUG says on
-        # some boxes: point fd 1 at stderr for the initialisation so that stdout carries nothing but the JSON line
-        sys.stdout.flush()
-        saved = os.dup(1)
-        os.dup2(2, 1)
-        try:
-            dist.init_process_group("nccl", device_id=dev)
-            dist.barrier(device_ids=[local_rank])
-            torch.cuda.synchronize()
-        finally:
-            sys.stdout.flush()
-            os.dup2(saved, 1)
-            os.close(saved)
-    lib = _lib.load()
-    _lib.check(lib.fmi_device_check(), "fmi_device_check")
 
-    src_h, ref_h, mask_h, wq = make_inputs("cpu", 1000 + rank)
-    mod = ExampleGuidedAttention(C).to(dev)
-    with torch.no_grad():
-        mod.conv.weight.copy_(wq)
-    src, ref, mask = src_h.to(dev), ref_h.to(dev), mask_h.to(dev)
+def _train_record(h: Harness, name, step_dev, step_host, params, dtype, what, extra):
+    peaks = measured_peaks()
+    tensor_peak = peaks["bf16_tflops"] / (2.0 if dtype == "tf32" else 1.0)
+    b = WORKLOADS[name]["batch"]
+    for _ in range(2):
+        step_dev()
+    torch.cuda.synchronize()
+    n0 = h.lib.fmi_kernel_launch_count()
+    step_dev()
+    torch.cuda.synchronize()
+    launches = h.lib.fmi_kernel_launch_count() - n0
+    sampler = ClockSampler(h.local_rank) if h.rank == 0 else None
+    ms = h.timed(step_dev)
+    ms_e2e, h2d, d2h = step_host(h)
+    clocks = sampler.stop() if sampler else None
+    kernels, eager_ms = h.profile(step_dev, min(h.steps, 3), tensor_peak, peaks)
+    nparam = sum(p.numel() for p in params)
+    rec = {"metric": "images/sec", "value": h.world * b / (ms * 1e-3), "unit": "img/s", "n_gpus": h.world, "steps": h.steps,
+           "warmup": h.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": dtype, "data": "synthetic", "config": workload_config(name, h.world), "clocks": clocks,
+           "e2e": {"value": h.world * b / (ms_e2e * 1e-3), "unit": "img/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
+                   "d2h_bytes_per_step": d2h, "api": "pinned host batch -> device, the reference's own train-step calls over the "
+                   "installed drop-ins, loss scalars -> host"},
+           "gpu_launches": int(launches) * h.steps, "launch": f"eager: {int(launches)} sm_100a kernel launches of this package per step",
+           "what": what, "trainable_params": nparam, "allreduce_bytes_per_step": nparam * 4 if h.world > 1 else 0,
+           "roofline": roofline_of(kernels, peaks, tensor_peak, dtype), "kernels": kernels}
+    rec.update(extra)
+    return rec
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
-    def max_over_ranks(ms: float) -> float:
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+def ours_train_picnet(h: Harness):
+    R = _patched_reference()
+    from face_mask_inpaint_b200 import dist as fdist
+    from modules.loss import GANOptimizer
+    torch.manual_seed(21)
+    G = R.reference_fill().to(h.dev)
+    D = R.discriminator().to(h.dev)
+    fdist.broadcast_module_state(G)
+    fdist.broadcast_module_state(D)
+    optG, optD = torch.optim.Adam(G.parameters(), lr=1e-5), torch.optim.Adam(D.parameters(), lr=1e-5)
+    nb = 0
+    if h.world > 1:
+        rg = fdist.GradientAllReducer([p for p in G.parameters() if p.requires_grad]).attach(optG)
+        rd = fdist.GradientAllReducer([p for p in D.parameters() if p.requires_grad]).attach(optD)
+        nb = len(rg.buckets) + len(rd.buckets)
+    gan = GANOptimizer(optD, optG).to(h.dev)
+    G.train()
+    D.train()
+    torch.manual_seed(100 + h.rank)
+    host = [t.pin_memory() for t in make_inputs("train_picnet", WORKLOADS["train_picnet"]["batch"], 3000 + h.rank)]
+    dev = [t.to(h.dev) for t in host]
+    losses_host = torch.empty(5, pin_memory=True)
 
-    with torch.no_grad():
-        for _ in range(max(3, args.warmup)):
-            out = mod(mask, src, ref)
-        barrier()
-        sampler = ClockSampler(local_rank) if rank == 0 else None
-        # ---------------- device-resident timing (value) + live CUDA-event timing of the dominant kernel
-        lib.fmi_profile_enable(1)
-        launches0 = lib.fmi_kernel_launch_count()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        e0.record()
-        for _ in range(args.steps):
-            out = mod(mask, src, ref)
-        e1.record()
-        barrier()
-        ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
-        launches = lib.fmi_kernel_launch_count() - launches0
-        lib.fmi_profile_enable(0)
-        tot, n = ctypes.c_double(0), ctypes.c_int(0)
-        lib.fmi_profile_collect(0, ctypes.byref(tot), ctypes.byref(n))
-        kern_ms = tot.value / max(1, n.value)
-        if n.value != args.steps:  # exactly one dominant-kernel launch per step, or the average below means nothing
-            raise RuntimeError(f"bench: {n.value} attention main-kernel launches timed for {args.steps} steps")
-        tot_fb, n_fb = ctypes.c_double(0), ctypes.c_int(0)
-        lib.fmi_profile_collect(2, ctypes.byref(tot_fb), ctypes.byref(n_fb))  # robust kernel as fallback: exits at once
-        fallback_ms = tot_fb.value / max(1, n_fb.value)
+    def run(src, ref, gt, mask):      # train_reference_fill.py:342-346
+        gen = G(src, ref, src_mask=mask)
+        return gan(D, src, gt, ref, gen, mask)
 
-        # ---------------- end to end from pinned host memory through the public module API
-        # Every step moves its own inputs host -> device (pinned, 269 MB) and its own result device -> host (268 MB) inside the
-        # timed region. The three phases run on three streams with two buffer sets, so the H2D of step i+1 and the D2H of
-        # step i-1 overlap the kernels of step i (PCIe is full duplex): the step time tends to max(H2D, compute, D2H)
-        # instead of their sum. The module call itself is the public API, unchanged.
-        src_p, ref_p, mask_p = src_h.pin_memory(), ref_h.pin_memory(), mask_h.pin_memory()
-        out_p = [torch.empty(out.shape, dtype=out.dtype).pin_memory() for _ in range(2)]
-        e2e_steps = max(1, min(args.steps, 50))
-        s_in, s_cmp, s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
-        d_in = [tuple(torch.empty_like(t, device=dev) for t in (src_h, ref_h, mask_h)) for _ in range(2)]
-        ev_in = [torch.cuda.Event() for _ in range(2)]       # inputs of the set have landed
-        ev_used = [torch.cuda.Event() for _ in range(2)]     # the kernels have consumed the set
-        ev_out = [torch.cuda.Event() for _ in range(2)]      # the result of the set has reached the host
-        for e in ev_used + ev_out:
-            e.record()
+    def step_host(hh):
+        def st():
+            d = [t.to(hh.dev, non_blocking=True) for t in host]
+            ls = run(*d)
+            losses_host.copy_(torch.stack([l.detach().float().reshape(()) for l in ls]), non_blocking=True)
+        ms = hh.timed(st)
+        return ms, sum(t.numel() * t.element_size() for t in host), 20
 
-        def e2e_step(i):
-            k = i & 1
-            with torch.cuda.stream(s_in):
-                s_in.wait_event(ev_used[k])
-                for dst, srcp in zip(d_in[k], (src_p, ref_p, mask_p)):
-                    dst.copy_(srcp, non_blocking=True)
-                ev_in[k].record(s_in)
-            with torch.cuda.stream(s_cmp):
-                s_cmp.wait_event(ev_in[k])
-                o = mod(d_in[k][2], d_in[k][0], d_in[k][1])
-                ev_used[k].record(s_cmp)
-            with torch.cuda.stream(s_out):
-                s_out.wait_event(ev_used[k])
-                s_out.wait_event(ev_out[k])   # (same stream: ordering only) the host buffer of this set is free again
-                out_p[k].copy_(o, non_blocking=True)
-                o.record_stream(s_out)
-                ev_out[k].record(s_out)
+    rec = _train_record(h, "train_picnet", lambda: run(*dev), step_host,
+                        [p for m in (G, D) for p in m.parameters() if p.requires_grad], "tf32",
+                        "train_reference_fill.py:342-346 — ReferenceFill forward (train mode) + GANOptimizer.__call__ "
+                        "(modules/loss.py:120-134) over the installed drop-ins; attention forward/backward on the sm_100a kernels",
+                        {"buckets": nb})
+    if not torch.isfinite(losses_host).all():
+        raise RuntimeError("train_picnet: non-finite losses")
+    return rec
 
-        for i in range(4):
-            e2e_step(i)
-        barrier()
-        e0.record()
-        for st in (s_in, s_cmp, s_out):
-            st.wait_event(e0)
-        for i in range(e2e_steps):
-            e2e_step(i)
-        for st in (s_in, s_cmp, s_out):
-            torch.cuda.current_stream().wait_stream(st)
-        e1.record()
-        barrier()
-        ms_e2e = max_over_ranks(e0.elapsed_time(e1) / e2e_steps)
-        # the pipelined steps must have produced the same result as the device-resident run (same inputs every step)
-        ref_out = out.float().cpu()
-        for k in range(2):
-            diff = (out_p[k].float() - ref_out).abs().max().item()
-            if not diff <= 1e-5 * ref_out.abs().max().item():
-                raise RuntimeError(f"bench: pipelined e2e output of buffer set {k} differs from the resident run by {diff}")
-        # serial variant (copy in, run, copy out, one stream) for the record
-        def e2e_serial():
-            s_d = src_p.to(dev, non_blocking=True)
-            r_d = ref_p.to(dev, non_blocking=True)
-            m_d = mask_p.to(dev, non_blocking=True)
-            out_p[0].copy_(mod(m_d, s_d, r_d), non_blocking=True)
 
-        e2e_serial()
-        barrier()
-        e0.record()
-        for _ in range(min(e2e_steps, 10)):
-            e2e_serial()
-        e1.record()
-        barrier()
-        ms_e2e_serial = max_over_ranks(e0.elapsed_time(e1) / min(e2e_steps, 10))
-        clocks = sampler.stop() if sampler else None
+def ours_train_psp(h: Harness):
+    from argparse import Namespace
+    prev = os.environ.get("FMI_PRECISION")
+    os.environ["FMI_PRECISION"] = "bf16"
+    try:
+        R = _patched_reference()
+        from face_mask_inpaint_b200 import dist as fdist
+        from modules.psp.criteria import pSpLoss
+        torch.manual_seed(31)
+        G = R.psp(output_size=1024, use_attention=1, train_decoder=1).to(h.dev)
+        G.latent_avg = G.latent_avg.to(h.dev)
+        fdist.broadcast_module_state(G)
+        params = list(G.encoder.parameters()) + list(G.decoder.parameters())      # train_psp.py:287-289
+        opt = torch.optim.Adam(params, lr=1e-5)
+        nb = 0
+        if h.world > 1:
+            red = fdist.GradientAllReducer([p for p in params if p.requires_grad]).attach(opt)
+            nb = len(red.buckets)
+        largs = Namespace(id_lambda=0, lpips_lambda=0.8, l2_lambda=1.0, style_lambda=250.0, lpips_lambda_ref=0, l2_lambda_ref=0,
+                          cx_lambda=1.0, w_norm_lambda=0, start_from_latent_avg=1)
+        loss_fn = pSpLoss(largs).to(h.dev)
+        G.train()
+        torch.manual_seed(200 + h.rank)
+        host = [t.pin_memory() for t in make_inputs("train_psp", WORKLOADS["train_psp"]["batch"], 4000 + h.rank)]
+        dev = [t.to(h.dev) for t in host]
+        loss_host = torch.empty(1, pin_memory=True)
 
-    # ---------------- whole-model numbers of BASELINE.json's metric (not the bench line; reported beside it)
-    models = None if args.no_models else whole_model_throughput(dev, world, barrier, max_over_ranks)
+        def run(src, ref, gt, mask):      # train_psp.py:307-335
+            gen, latent = G(src, ref=ref, src_mask=mask, return_latents=True, randomize_noise=1)
+            loss, _, _ = loss_fn(src, gt, gen, latent, latent_avg=G.latent_avg, ref=ref, mask=mask)
+            if fdist.all_ranks_finite(loss):
+                opt.zero_grad()
+                loss.backward()
+                opt.step()
+            return loss
 
-    if world > 1:
-        dist.destroy_process_group()
+        def step_host(hh):
+            def st():
+                d = [t.to(hh.dev, non_blocking=True) for t in host]
+                loss_host.copy_(run(*d).detach().float().reshape(1), non_blocking=True)
+            ms = hh.timed(st)
+            return ms, sum(t.numel() * t.element_size() for t in host), 4
+
+        rec = _train_record(h, "train_psp", lambda: run(*dev), step_host, [p for p in params if p.requires_grad], "bf16",
+                            "train_psp.py:307-335 — pSp forward (train mode, encoder + decoder trainable), pSpLoss, backward, Adam over "
+                            "the installed drop-ins; StyleGAN2 decoder + attention forward/backward on the sm_100a kernels",
+                            {"buckets": nb})
+        if not torch.isfinite(loss_host).all():
+            raise RuntimeError("train_psp: non-finite loss")
+        return rec
+    finally:
+        if prev is None:
+            os.environ.pop("FMI_PRECISION", None)
+        else:
+            os.environ["FMI_PRECISION"] = prev
+
+
+OURS = {"picnet_ref": ours_picnet_ref, "refpsp": ours_refpsp, "train_picnet": ours_train_picnet, "train_psp": ours_train_psp}
+
+
+# ------------------------------------------------------------------------------------------------------------ the unmodified reference
+def _reference_step(name, device, batch):
+    """(step function, description) running the UNMODIFIED reference for `name` on `device` with `batch` images per step."""
+    from baseline import reference as R
+    cuda = device.type == "cuda"
+    R.import_unpatched("none" if "picnet" in name else ("cuda" if cuda else "cpu"))
+    src, ref, gt, mask = (t.to(device) for t in make_inputs(name, batch, 1000))
+    if name == "picnet_ref":
+        torch.manual_seed(7)
+        net = R.reference_fill().eval().to(device)
+        with torch.no_grad():
+            net.decoder.attn1.gamma.fill_(1.0)
+
+        def step():
+            with torch.no_grad():
+                return net(src, ref, src_mask=mask)
+        return step, "modules/model.py ReferenceFill.forward, unmodified", "reference"
+    if name == "refpsp":
+        torch.manual_seed(11)
+        net = R.psp(output_size=1024).eval().to(device)
+        net.latent_avg = net.latent_avg.to(device)
+
+        def step():
+            with torch.no_grad():
+                return net(src, ref=ref, src_mask=mask, resize=True, randomize_noise=False)
+        ops = "its own compiled CUDA ops (oracle/_ref)" if cuda else \
+            "upfirdn2d = its own upfirdn2d_native, fused_leaky_relu restated (the reference has no CPU path for these two ops)"
+        return step, f"modules/psp/psp.py pSp.forward, unmodified, fp32; {ops}", "reference" if cuda else "port"
+    if name == "train_picnet":
+        from modules.loss import GANOptimizer
+        torch.manual_seed(21)
+        G, D = R.reference_fill().to(device), R.discriminator().to(device)
+        optG, optD = torch.optim.Adam(G.parameters(), lr=1e-5), torch.optim.Adam(D.parameters(), lr=1e-5)
+        gan = GANOptimizer(optD, optG).to(device)
+        G.train()
+        D.train()
+
+        def step():
+            gen = G(src, ref, src_mask=mask)
+            return gan(D, src, gt, ref, gen, mask)
+        return step, "train_reference_fill.py:342-346 with the unmodified modules, random-init VGG16", "reference"
+    if name == "train_psp":
+        if not cuda:
+            raise RuntimeError("the reference's LPIPS hard-codes .to('cuda') (modules/psp/criteria/lpips/lpips.py:24-27): no CPU path")
+        from argparse import Namespace
+        from modules.psp.criteria import pSpLoss
+        torch.manual_seed(31)
+        G = R.psp(output_size=1024, use_attention=1, train_decoder=1).to(device)
+        G.latent_avg = G.latent_avg.to(device)
+        params = list(G.encoder.parameters()) + list(G.decoder.parameters())
+        opt = torch.optim.Adam(params, lr=1e-5)
+        loss_fn = pSpLoss(Namespace(id_lambda=0, lpips_lambda=0.8, l2_lambda=1.0, style_lambda=250.0, lpips_lambda_ref=0,
+                                    l2_lambda_ref=0, cx_lambda=1.0, w_norm_lambda=0, start_from_latent_avg=1)).to(device)
+        G.train()
+
+        def step():
+            gen, latent = G(src, ref=ref, src_mask=mask, return_latents=True, randomize_noise=1)
+            loss, _, _ = loss_fn(src, gt, gen, latent, latent_avg=G.latent_avg, ref=ref, mask=mask)
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            return loss
+        return step, "train_psp.py:307-335 with the unmodified modules (fp32: the reference's CUDA ops reject bf16)", "reference"
+    raise ValueError(name)
+
+
+def _oracle_port_cpu(args, cores):
+    """Fallback of the reference arm when baseline/_ref is absent: oracle/ref_ops.py (the CPU restatement of the reference's
+    algorithm) on the pieces of one PICNet-ref image that dominate its forward — ExampleGuidedAttention @32^2, Auto_Attn C=256
+    @128^2 (58 % of the generator's FLOPs), the five ResBlockDecoders and the Output block; the encoders are left out."""
+    from oracle import ref_ops as O
+    g = torch.Generator().manual_seed(0)
+    r = lambda *s: torch.randn(*s, generator=g)
+    src, ref, m = r(1, 128, 32, 32), r(1, 128, 32, 32), torch.rand(1, 1, 32, 32, generator=g)
+    chans = [(256, 256, 256), (256, 256, 256), (256, 128, 128), (128, 64, 64), (64, 32, 32)]
+
+    def step():
+        with torch.no_grad():
+            x = O.example_guided_attention(m, src, ref, r(32, 128, 1, 1) * 0.1)
+            for i, (ci, ch, co) in enumerate(chans):
+                x = O.res_block_decoder(x, r(ch, ci, 3, 3) / (3 * ci ** 0.5), None, r(ch, co, 3, 3) / (3 * ch ** 0.5), None,
+                                        r(ci, co, 3, 3) / (3 * ci ** 0.5), None)
+                if i == 1:
+                    x = O.auto_attn(x, r(64, 256, 1, 1) * 0.02, torch.zeros(64), torch.ones(1))[0]
+            return O.output_block(x, r(3, 32, 3, 3) * 0.05, torch.zeros(3))
+
+    step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    ms = (time.perf_counter() - t0) / args.steps * 1e3
+    return 1.0 / (ms * 1e-3), ms, (f"{args.steps} steps x 1 image: oracle/ref_ops.py restatement of EGA@32^2 + Auto_Attn@128^2 + 5 "
+                                   f"ResBlockDecoder + Output (encoders left out; baseline/_ref absent), PyTorch CPU fp32, {cores} threads")
+
+
+def run_reference_cpu(args, rank):
+    """The reference arm: the unmodified reference on the box's host cores, all threads, same config / metric / unit. Each step
+    is the full per-GPU batch when K + W steps fit in ~3 minutes, otherwise a bounded sample of it (fewer images per step)."""
     if rank != 0:
         return
+    from baseline import reference as R
+    name = args.workload
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    base = {"impl": "reference", "metric": "images/sec", "unit": "img/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(name, args.gpus)}
+    if not R.available():
+        # no copy of the reference travelled to this box: the oracle's restatement of the generator pieces stands in (kind "port")
+        value, ms, sample = _oracle_port_cpu(args, cores)
+        base.update({"value": value, "ms_per_step": ms,
+                     "cpu_baseline": {"value": value, "unit": "img/s", "cores": cores, "kind": "port", "sample": sample},
+                     "e2e": {"value": value, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+        print(json.dumps(base), flush=True)
+        return
+    b_full = WORKLOADS[name]["batch"]
+    try:
+        step, what, kind = _reference_step(name, torch.device("cpu"), b_full)
+        t0 = time.perf_counter()
+        step()
+        t1 = time.perf_counter() - t0
+        b = b_full
+        total = args.steps + args.warmup
+        if t1 * total > 200.0 and b_full > 1:
+            b = max(1, int(b_full * 200.0 / (t1 * total)))
+            step, what, kind = _reference_step(name, torch.device("cpu"), b)
+        for _ in range(args.warmup):
+            step()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step()
+        ms = (time.perf_counter() - t0) / args.steps * 1e3
+    except Exception as ex:  # noqa: BLE001
+        base.update({"unavailable": f"{type(ex).__name__}: {str(ex)[:300]}"})
+        print(json.dumps(base), flush=True)
+        return
+    value = b / (ms * 1e-3)
+    sample = (f"{args.steps} steps x {b} of the {b_full} images of a per-GPU batch; {what}; PyTorch CPU fp32, {cores} threads")
+    base.update({"value": value, "ms_per_step": ms,
+                 "cpu_baseline": {"value": value, "unit": "img/s", "cores": cores, "kind": kind, "sample": sample},
+                 "e2e": {"value": value, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    print(json.dumps(base), flush=True)
 
-    peak_tf, _, peak_kind = measured_peaks()
-    flops_launch = algorithmic_flops_per_image() * BATCH
-    achieved = flops_launch / (kern_ms * 1e-3) / 1e12 if kern_ms > 0 else 0.0
-    h2d = src_h.numel() * 4 + ref_h.numel() * 4 + mask_h.numel() * 4
-    d2h = out.numel() * out.element_size()
-    line = {
-        "metric": "images/sec", "value": world * BATCH / (ms_step * 1e-3), "unit": "img/s", "n_gpus": world,
-        "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "per_gpu_batch": BATCH, "C": C, "H": HW, "W": HW, "d": D,
-                   "precision": "fp32 I/O, TF32 tcgen05 operands, fp32 softmax + accumulation",
-                   "l2": "inputs (2 x 128 MiB + staged operands) larger than the 126 MB L2; no flush needed",
-                   "parallelism": f"batch-sharded x{world}, no collective"},
-        "clocks": clocks,
-        "e2e": {"value": world * BATCH / (ms_e2e * 1e-3), "unit": "img/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": ms_e2e,
-                "pipelining": "3 streams, 2 buffer sets: H2D(i+1) and D2H(i-1) overlap the kernels of step i; every step "
-                              "moves all of its own bytes",
-                "serial_ms_per_step": ms_e2e_serial, "serial_value": world * BATCH / (ms_e2e_serial * 1e-3)},
-        "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "kernel": "attn_fwd2_kernel<TF32,float,cluster2>", "achieved": achieved,
-                     "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the round-1 `ncu --set full` capture of
-                     # this command (profiles/r01_ncu_attn_fwd2_tf32_summary.csv): 595 MB + 502 MB
-                     "traffic": 1.097e9, "traffic_unit": "bytes/launch (ncu)",
-                     "algorithmic_bytes_per_launch": 6.86e8,
-                     "kernel_ms": kern_ms, "launches_timed": n.value, "fallback_kernel_ms": fallback_ms,
-                     "algorithmic_flops_per_launch": flops_launch,
-                     "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peak_kind}); the kernel runs "
-                                    "kind::tf32 MMAs whose nominal rate is half the bf16 rate"},
-    }
-    if models is not None:
-        line["whole_models"] = models
-    if world == 1:
-        v, sample, cores, _ = cpu_reference_images_per_sec(12.0, 1024, None, 1)
-        line["cpu_baseline"] = {"value": v, "unit": "img/s", "cores": cores, "kind": "port", "sample": sample}
+
+def run_reference_gpu(args):
+    """The unmodified reference on the same B200 (single GPU, its own eager formulation) — the number to beat."""
+    name = args.workload
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    b = WORKLOADS[name]["batch"]
+    out = {"impl": "gpu_reference", "workload": name, "per_gpu_batch": b}
+    try:
+        step, what, kind = _reference_step(name, dev, b)
+        for _ in range(max(3, args.warmup)):
+            step()
+        torch.cuda.synchronize()
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for e0, e1 in evs:
+            flush.fill_(1)
+            e0.record()
+            step()
+            e1.record()
+        torch.cuda.synchronize()
+        ms = sum(e0.elapsed_time(e1) for e0, e1 in evs) / args.steps
+        out.update({"value": b / (ms * 1e-3), "unit": "img/s", "ms_per_step": ms, "steps": args.steps, "what": what,
+                    "precision": "fp32 tensors, PyTorch defaults (cuDNN convolutions may use TF32, matmul / bmm strict fp32)",
+                    "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30})
+    except Exception as ex:  # noqa: BLE001
+        out["unavailable"] = f"{type(ex).__name__}: {str(ex)[:300]}"
+    print(json.dumps(out), flush=True)
+
+
+def _subprocess_json(argv, timeout):
+    """Run bench.py in a fresh process (the unmodified reference cannot share a process with the installed drop-ins) and
+    return its last JSON line."""
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT",
+                                                             "LOCAL_WORLD_SIZE", "GROUP_RANK", "ROLE_RANK", "TORCHELASTIC_RUN_ID")}
+    try:
+        r = subprocess.run([sys.executable, str(ROOT / "bench.py")] + argv, capture_output=True, text=True, timeout=timeout, env=env)
+    except subprocess.TimeoutExpired:
+        return {"unavailable": f"timed out after {timeout} s"}
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    if not lines:
+        return {"unavailable": f"rc {r.returncode}: {r.stderr[-300:]}"}
+    return json.loads(lines[-1])
+
+
+# ------------------------------------------------------------------------------------------------------------ main
+def run_ours(args):
+    h = Harness(args)
+    name = args.workload
+    names = [name] + ([n for n in ("refpsp", "train_picnet", "train_psp") if n != name] if (name == "picnet_ref" and not args.no_extras) else [])
+    records = []
+    for n in names:
+        try:
+            rec = OURS[n](h)
+        except Exception as ex:  # noqa: BLE001
+            if n == name:
+                raise
+            rec = {"config": workload_config(n, h.world), "error": f"{type(ex).__name__}: {str(ex)[:400]}"}
+        torch.cuda.empty_cache()
+        # the unmodified reference on the same GPU / on the host cores, rank 0 only, in fresh processes; the other ranks wait
+        if h.rank == 0 and h.world == 1 and not args.no_reference:
+            k = min(args.steps, 10)
+            rec["gpu_reference"] = _subprocess_json(["--impl", "gpu_reference", "--workload", n, "--steps", str(k), "--warmup", "3"], 900)
+            if n in ("picnet_ref", "refpsp"):
+                cb = _subprocess_json(["--impl", "reference", "--workload", n, "--steps", "2", "--warmup", "1"], 900)
+                rec["cpu_baseline"] = cb.get("cpu_baseline", {"unavailable": cb.get("unavailable", "?")})
+        h.barrier()
+        records.append(rec)
+    if h.world > 1:
+        h.dist.destroy_process_group()
+    if h.rank != 0:
+        return
+    line = records[0]
+    if len(records) > 1:
+        line["records"] = records[1:]
     print(json.dumps(line), flush=True)
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-models", action="store_true", help="skip the whole-model (PICNet-ref / RefpSp) throughput block")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "gpu_reference"])
+    ap.add_argument("--workload", default="picnet_ref", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-extras", action="store_true", help="only the named workload (no refpsp / train records)")
+    ap.add_argument("--no-reference", action="store_true", help="skip the gpu_reference / cpu_baseline sub-runs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    # NCCL prints its version banner to STDOUT at NCCL_DEBUG=VERSION (set on the GPU boxes): keep stdout to the one JSON line
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference_cpu(args, rank)
+    elif args.impl == "gpu_reference":
+        run_reference_gpu(args)
     else:
-        run_ours(args, rank, local_rank, world)
+        run_ours(args)
 
 
 if __name__ == "__main__":

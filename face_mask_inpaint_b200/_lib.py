@@ -25,6 +25,9 @@ PROTOTYPES = {
     "fmi_kernel_launch_count": (C.c_longlong, []),
     "fmi_profile_enable": (_i, [_i]),
     "fmi_profile_collect": (_i, [_i, C.POINTER(C.c_double), C.POINTER(_i)]),
+    "fmi_profile_kinds": (_i, []),
+    "fmi_profile_kind_name": (C.c_char_p, [_i]),
+    "fmi_profile_dump": (_i, [_i, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), _i, C.POINTER(_i)]),
     "fmi_fused_bias_act": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _f, _i64, _i64, _i64, _i, _i, _vp]),
     "fmi_bias_act_bwd": (_i, [_vp, _vp, _vp, _vp, _f, _f, _i64, _i64, _i64, _i, _vp]),
     "fmi_upfirdn2d": (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),

@@ -519,6 +519,7 @@ struct AttnPlan {
   int dpad, d_atoms, split, cv_tile, k_stages, v_stages, esz;  // esz: element size of the V / P operands
   int k_stages2, v_stages2;                                    // ring depths of attn_fwd2_kernel
   int v_stages3;                                               // V ring depth of attn_fwd3_kernel (CTA pairs)
+  int d;                                                       // head dimension as given (dpad is its padded size)
   int64_t qt_bytes, vcat_bytes, qmax_bytes;
   size_t smem, smem2, smem3;
 };
@@ -530,6 +531,7 @@ int make_plan(int N, int d, int C0, int C1, int S, int mma, AttnPlan* pl) {
   FMI_REQUIRE(C0 % 32 == 0 && C1 % 32 == 0, "attn: value channel counts (%d, %d) must be multiples of 32", C0, C1);
   const int esz = mma == FMI_MMA_TF32 ? 4 : 2;
   pl->esz = esz;
+  pl->d = d;
   pl->split = mma == FMI_MMA_TF32 ? 1 : 0;  // fp32 contract: logits from [hi | lo] bf16 pairs
   pl->dpad = (d + 63) / 64 * 64;
   pl->d_atoms = pl->dpad / 64;
@@ -586,6 +588,15 @@ int launch_pack_values(const void* v0, const void* v1, void* vcat, int N, int C0
   return fmi_launched("pack_values");
 }
 
+// Algorithmic work of one attention launch: FLOPs = 2*S^2*d (QK^T) + 2*S^2*Cv (P.V); bytes = q + values read once +
+// outputs written once + mask, in the I/O element type.
+template <typename T>
+static inline void attn_work(const AttnParams& prm, const AttnPlan& pl, double* flops, double* bytes) {
+  const double S = prm.S, N = prm.N, Cv = prm.C0 + prm.C1;
+  *flops = N * (2.0 * S * S * pl.d + 2.0 * S * S * Cv);
+  *bytes = N * S * ((pl.d + 2.0 * Cv) * sizeof(T) + (prm.mask ? 4.0 : 0.0));
+}
+
 template <bool TF32, typename T, bool CLUSTER>
 int launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnParams& prm,
                 const AttnPlan& pl, cudaStream_t st) {
@@ -601,7 +612,9 @@ int launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap&
   dim3 grid(prm.S / BM, prm.N, (prm.C0 + prm.C1) / prm.cv_tile);
   // kind 0 = the kernel that does the work; as the fallback behind the fast kernel (qmax2 given: it exits at once for
   // every image the fast kernel took) it is timed separately so it cannot dilute the roofline average
-  FmiProfScope prof(prm.qmax2 ? 2 : 0, st);
+  double wf, wb;
+  attn_work<T>(prm, pl, &wf, &wb);
+  FmiProfScope prof(prm.qmax2 ? FMI_PROF_ATTN_FALLBACK : FMI_PROF_ATTN, st, wf, wb);
   if (CLUSTER) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
@@ -638,7 +651,9 @@ int launch_attn2(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap
   prm.k_stages = pl.k_stages2;
   prm.v_stages = pl.v_stages2;
   dim3 grid(prm.S / BM, prm.N, (prm.C0 + prm.C1) / prm.cv_tile);
-  FmiProfScope prof(0, st);
+  double wf, wb;
+  attn_work<T>(prm, pl, &wf, &wb);
+  FmiProfScope prof(FMI_PROF_ATTN, st, wf, wb);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = dim3(kAttn2Threads);
@@ -671,7 +686,9 @@ int launch_attn3(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap
   prm.k_stages = 2;
   prm.v_stages = pl.v_stages3;
   dim3 grid(prm.S / BM, prm.N, (prm.C0 + prm.C1) / prm.cv_tile);
-  FmiProfScope prof(0, st);
+  double wf, wb;
+  attn_work<T>(prm, pl, &wf, &wb);
+  FmiProfScope prof(FMI_PROF_ATTN, st, wf, wb);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = dim3(kAttn3Threads);

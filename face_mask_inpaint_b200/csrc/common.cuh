@@ -18,15 +18,25 @@ int fmi_check_cuda(cudaError_t e, const char* what);
 // Called right after every kernel launch: counts it (fmi_kernel_launch_count) and surfaces launch errors.
 int fmi_launched(const char* kernel_name);
 
-// Optional CUDA-event timing of the dominant kernels on their launch stream (fmi_profile_enable / _collect):
-// kind 0 = attention main kernel, kind 1 = modulated-conv implicit GEMM, kind 2 = attention robust kernel run as fallback.
+// Optional CUDA-event timing of kernels on their launch stream (fmi_profile_enable / _collect / _dump). A scope brackets one
+// launch (or one entry point's launches) with two events and carries the ALGORITHMIC work of that launch — the FLOPs and the
+// minimum HBM bytes (inputs read once + outputs written once) — so bench.py can put every launch on its roofline.
+// kinds: see g_prof_names in core.cu (0 attention main kernel, 1 implicit-GEMM conv, 2 attention fallback kernel, ...).
+#define FMI_PROF_KINDS 16
+enum {
+  FMI_PROF_ATTN = 0, FMI_PROF_GEMM = 1, FMI_PROF_ATTN_FALLBACK = 2, FMI_PROF_OUTCONV = 3, FMI_PROF_INSTATS = 4,
+  FMI_PROF_NORMACT = 5, FMI_PROF_WGRAD = 6, FMI_PROF_ATTN_BWD = 7, FMI_PROF_UPFIRDN = 8, FMI_PROF_BIASACT = 9,
+  FMI_PROF_BLURACT = 10, FMI_PROF_GEMM_IR = 11, FMI_PROF_SE = 12, FMI_PROF_STREAM = 13, FMI_PROF_ATTN_PRO = 14,
+  FMI_PROF_TORGB = 15
+};
 struct FmiProfScope {
-  FmiProfScope(int kind, cudaStream_t st);
+  FmiProfScope(int kind, cudaStream_t st, double flops = 0.0, double bytes = 0.0);
   ~FmiProfScope();
   int kind_;
   cudaStream_t st_;
   cudaEvent_t e0_, e1_;
   bool on_;
+  double flops_, bytes_;
 };
 
 #define FMI_REQUIRE(cond, ...)      \

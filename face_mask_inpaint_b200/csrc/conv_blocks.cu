@@ -249,6 +249,7 @@ extern "C" int fmi_instnorm_stats_nhwc(const void* x, int64_t x_pixel_stride, co
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
   const int64_t img = (int64_t)HW * x_pixel_stride;
+  FmiProfScope prof(FMI_PROF_INSTATS, st, 3.0 * B * HW * C, (double)B * HW * C * esz_of(mma));
   if (mma == FMI_MMA_TF32)
     instnorm_stats_kernel<float><<<dim3(gx, B), 256, 0, st>>>((const float*)x, x_pixel_stride, img, HW, C, sums);
   else
@@ -273,6 +274,7 @@ extern "C" int fmi_norm_act_nhwc(const void* x, int64_t x_pixel_stride, void* y,
   int gx = stream_grid(work, 256 * 4);
   const int cap = (FMI_NUM_SMS * 16 + B - 1) / B;
   if (gx > cap) gx = cap;
+  FmiProfScope prof(FMI_PROF_NORMACT, st, 3.0 * B * HW * C, 2.0 * B * HW * C * esz_of(mma));
   if (mma == FMI_MMA_TF32)
     norm_act_kernel<float, true><<<dim3(gx, B), 256, 0, st>>>((const float*)x, x_pixel_stride, (int64_t)HW * x_pixel_stride,
                                                               (float*)y, y_pixel_stride, (int64_t)HW * y_pixel_stride,
@@ -587,6 +589,9 @@ extern "C" int fmi_output_conv_tanh(const void* xpad, const float* weight, const
   FMI_CUDA(cudaMemcpyToSymbolAsync(c_out_b, scratch + 27 * C, 4 * sizeof(float), 0, cudaMemcpyDeviceToDevice, st));
   dim3 grid((W + OC_TW - 1) / OC_TW, (H + OC_TH - 1) / OC_TH, B);
   FMI_REQUIRE(grid.y <= 65535, "output_conv_tanh: image too tall");
+  FmiProfScope prof(FMI_PROF_OUTCONV, st, 2.0 * 9 * C * O * (double)B * H * W,
+                    (double)B * (H + 2) * (W + 2) * C * esz_of(mma) + (double)B * O * H * W * 4.0 * (img ? 1.0 : 0.0) +
+                        (pooled ? (double)B * O * H * W * 4.0 / 16.0 : 0.0));
 #define FMI_OC_LAUNCH(OT, CC) out_conv_tanh_kernel<OT, CC><<<grid, 128, 0, st>>>((const OT*)xpad, img, pooled, O, H, W)
   if (mma == FMI_MMA_TF32) {
     if (C == 16) FMI_OC_LAUNCH(float, 16); else if (C == 32) FMI_OC_LAUNCH(float, 32); else FMI_OC_LAUNCH(float, 64);

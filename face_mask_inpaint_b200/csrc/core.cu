@@ -28,7 +28,14 @@ int fmi_check_cuda(cudaError_t e, const char* what) {
 static std::atomic<long long> g_launches{0};
 static std::atomic<int> g_prof_on{0};
 static std::mutex g_prof_mu;
-static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events[3];
+struct ProfRec {
+  cudaEvent_t e0, e1;
+  double flops, bytes;
+};
+static std::vector<ProfRec> g_prof_events[FMI_PROF_KINDS];
+static const char* const g_prof_names[FMI_PROF_KINDS] = {
+    "attn_fwd", "conv_gemm", "attn_fwd_fallback", "out_conv_tanh", "instnorm_stats", "norm_act", "wgrad_gemm", "attn_bwd",
+    "upfirdn2d", "bias_act", "blur_act_nhwc", "conv_gemm_ir", "se_pool_scale", "streaming_other", "attn_prologue", "torgb"};
 
 int fmi_launched(const char* kernel_name) {
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -38,8 +45,11 @@ int fmi_launched(const char* kernel_name) {
   return FMI_ECUDA;
 }
 
-FmiProfScope::FmiProfScope(int kind, cudaStream_t st) : kind_(kind), st_(st), e0_(nullptr), e1_(nullptr), on_(false) {
-  if (!g_prof_on.load(std::memory_order_relaxed) || kind < 0 || kind > 2) return;
+FmiProfScope::FmiProfScope(int kind, cudaStream_t st, double flops, double bytes)
+    : kind_(kind), st_(st), e0_(nullptr), e1_(nullptr), on_(false), flops_(flops), bytes_(bytes) {
+  if (!g_prof_on.load(std::memory_order_relaxed) || kind < 0 || kind >= FMI_PROF_KINDS) return;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st_, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return;  // no timing inside a graph
   if (cudaEventCreate(&e0_) != cudaSuccess || cudaEventCreate(&e1_) != cudaSuccess) return;
   on_ = true;
   cudaEventRecord(e0_, st_);
@@ -48,7 +58,7 @@ FmiProfScope::~FmiProfScope() {
   if (!on_) return;
   cudaEventRecord(e1_, st_);
   std::lock_guard<std::mutex> lk(g_prof_mu);
-  g_prof_events[kind_].emplace_back(e0_, e1_);
+  g_prof_events[kind_].push_back(ProfRec{e0_, e1_, flops_, bytes_});
 }
 
 extern "C" long long fmi_kernel_launch_count(void) { return g_launches.load(); }
@@ -58,25 +68,56 @@ extern "C" int fmi_profile_enable(int on) {
   return FMI_OK;
 }
 
+extern "C" int fmi_profile_kinds(void) { return FMI_PROF_KINDS; }
+
+extern "C" const char* fmi_profile_kind_name(int kind) {
+  return (kind >= 0 && kind < FMI_PROF_KINDS) ? g_prof_names[kind] : "";
+}
+
 // Synchronises on the recorded events; returns the summed duration (ms) and number of launches of `kind`.
 extern "C" int fmi_profile_collect(int kind, double* total_ms, int* launches) {
-  FMI_REQUIRE(kind >= 0 && kind <= 2 && total_ms && launches, "profile_collect: bad arguments");
+  FMI_REQUIRE(kind >= 0 && kind < FMI_PROF_KINDS && total_ms && launches, "profile_collect: bad arguments");
   std::lock_guard<std::mutex> lk(g_prof_mu);
   double sum = 0;
   int n = 0;
   for (auto& pr : g_prof_events[kind]) {
     float ms = 0.f;
-    cudaEventSynchronize(pr.second);
-    if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) {
+    cudaEventSynchronize(pr.e1);
+    if (cudaEventElapsedTime(&ms, pr.e0, pr.e1) == cudaSuccess) {
       sum += ms;
       ++n;
     }
-    cudaEventDestroy(pr.first);
-    cudaEventDestroy(pr.second);
+    cudaEventDestroy(pr.e0);
+    cudaEventDestroy(pr.e1);
   }
   g_prof_events[kind].clear();
   *total_ms = sum;
   *launches = n;
+  return FMI_OK;
+}
+
+// Per-launch records of `kind` in launch order: duration (ms), algorithmic FLOPs and algorithmic bytes the launcher stated.
+// Writes at most `cap` records, returns the number written in *n, and clears the record of that kind.
+extern "C" int fmi_profile_dump(int kind, double* ms_out, double* flops_out, double* bytes_out, int cap, int* n) {
+  FMI_REQUIRE(kind >= 0 && kind < FMI_PROF_KINDS && n && (cap == 0 || (ms_out && flops_out && bytes_out)),
+              "profile_dump: bad arguments");
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  int k = 0;
+  for (auto& pr : g_prof_events[kind]) {
+    float ms = 0.f;
+    cudaEventSynchronize(pr.e1);
+    const bool ok = cudaEventElapsedTime(&ms, pr.e0, pr.e1) == cudaSuccess;
+    if (ok && k < cap) {
+      ms_out[k] = ms;
+      flops_out[k] = pr.flops;
+      bytes_out[k] = pr.bytes;
+      ++k;
+    }
+    cudaEventDestroy(pr.e0);
+    cudaEventDestroy(pr.e1);
+  }
+  g_prof_events[kind].clear();
+  *n = k;
   return FMI_OK;
 }
 

@@ -41,6 +41,7 @@ struct ConvGemmParams {
   // merged parity classes of a stride-2 transposed conv (conv_blocks.cu): the N tile is 4 x merge_o columns, column block
   // cls = 2*py + px holds the merge_o output channels of output pixel (2m + py, 2n + px); taps are the 4 input shifts
   int merge_o;
+  int prof_kind;       // FMI_PROF_* of this launch for the optional event timing (0: FMI_PROF_GEMM)
   int add_out;         // the epilogue adds the values already stored at the output location (residual sum: y += conv(x))
   int raw_out;         // TF32 mode: store the fp32 accumulator as is instead of rounding it to tf32 (the consumer is not an MMA,
                        // or must see the exact value: InstanceNorm statistics amplify a rounding of x by |mean| / std)
@@ -429,7 +430,18 @@ int launch_gemm_class(const CUtensorMap& mx, const CUtensorMap& mw, ConvGemmPara
     static const bool one_tile = [] { const char* e = getenv("FMI_MODCONV_ONE_TILE"); return e && e[0] == '1'; }();
     if (one_tile) grid = (int)total;
   }
-  FmiProfScope prof(1, st);
+  // algorithmic work of this launch: every input element read once, every output element written once, the weights once;
+  // FLOPs = 2 * pixels * taps * I * N (merged parity classes: the zero weight rows are not counted)
+  const double esz = TF32 ? 4.0 : 2.0;
+  const double pix = (double)p.B * p.Mh * p.Mw;
+  const double n_real = p.merge_o ? (double)p.merge_o * 9.0 / 4.0 : (double)p.O;   // merged: 9 real taps over 4 classes
+  const double taps = p.halo ? 9.0 : (double)p.ntaps;
+  const double wflops = 2.0 * pix * taps * p.I * (p.merge_o ? n_real * 4.0 / taps : n_real);
+  const double out_elems = pix * (p.merge_o ? 4.0 * p.merge_o : (double)p.O);
+  const double wbytes = ((double)p.B * p.H * p.W * p.I + out_elems * (p.add_out ? 2.0 : 1.0) +
+                         (double)p.T * p.O * p.I * (p.w_shared ? 1.0 : (double)p.B)) * esz +
+                        (p.nchw_out ? pix * p.nchw_C * 4.0 : 0.0);
+  FmiProfScope prof(p.prof_kind ? p.prof_kind : FMI_PROF_GEMM, st, wflops, wbytes);
   kern<<<grid, kGemmThreads, smem, st>>>(mx, mw, p);
   return fmi_launched("modconv_gemm");
 }

@@ -21,10 +21,12 @@ def stub_pretrained() -> None:
             continue
 
         def make(real=real, name=name):
-            def ctor(*a, pretrained=False, weights=None, **kw):
+            def ctor(pretrained=False, progress=True, weights=None, **kw):   # `models.alexnet(True)` passes it positionally
                 with torch.random.fork_rng(devices=[]):
                     torch.manual_seed(zlib.crc32(name.encode()) & 0xFFFF)
-                    return real(*a, weights=None, **kw)
+                    if name == "inception_v3":
+                        kw.setdefault("init_weights", True)
+                    return real(weights=None, **kw)
             return ctor
         setattr(torchvision.models, name, make())
     torchvision.models._fmi_offline = True

@@ -49,6 +49,12 @@ long long fmi_kernel_launch_count(void);
  * count, and clears the record. Off by default (no events are created). */
 int fmi_profile_enable(int on);
 int fmi_profile_collect(int kind, double* total_ms, int* launches);
+/* Kinds 0 .. fmi_profile_kinds()-1 (names: fmi_profile_kind_name). fmi_profile_dump returns the per-launch records of one
+ * kind in launch order — duration in ms, and the ALGORITHMIC FLOPs and HBM bytes (inputs once + outputs once) the launcher
+ * stated for that launch — at most `cap` of them, and clears the record. Launches inside a CUDA-graph capture are not timed. */
+int fmi_profile_kinds(void);
+const char* fmi_profile_kind_name(int kind);
+int fmi_profile_dump(int kind, double* ms_out, double* flops_out, double* bytes_out, int cap, int* n);
 
 /* ---------------------------------------------------------------------------------------------
  * a5  fused bias + activation.
