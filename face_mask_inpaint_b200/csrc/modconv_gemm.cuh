@@ -41,6 +41,14 @@ struct ConvGemmParams {
   // merged parity classes of a stride-2 transposed conv (conv_blocks.cu): the N tile is 4 x merge_o columns, column block
   // cls = 2*py + px holds the merge_o output channels of output pixel (2m + py, 2n + px); taps are the 4 input shifts
   int merge_o;
+  // several whole images per pixel tile (tiny planes: the map2style heads of the pSp encoder run 3x3 convs down to 1x1): the
+  // A box is {channels, Mw, Mh, TB} — TB consecutive images, TB * Mh * Mw <= 128 rows — and the tile index walks image groups
+  int TB;              // images per tile (0 / 1: one image, tiled by TH x TW)
+  int w_group;         // per-sample weights: images [g * w_group, (g+1) * w_group) share weight set g (0 / 1: one set per image)
+  int bias_classes;    // 9: bias is [9][O], indexed by the border class 3 * vy + vx of the output pixel (vy = 0 top row, 2 bottom
+                       // row, 1 inside) — an input-side BatchNorm folded into a zero-padded 3x3 conv (ir_encoder.cu); else [O]
+  int bias_set_stride; // per-sample weights: the bias of weight set g starts g * bias_set_stride floats into `bias` (0: one bias)
+  const float* slope_c;  // act 4: PReLU, negative slope per output channel
   int prof_kind;       // FMI_PROF_* of this launch for the optional event timing (0: FMI_PROF_GEMM)
   int add_out;         // the epilogue adds the values already stored at the output location (residual sum: y += conv(x))
   int raw_out;         // TF32 mode: store the fp32 accumulator as is instead of rounding it to tf32 (the consumer is not an MMA,
@@ -83,9 +91,12 @@ __global__ void __launch_bounds__(kGemmThreads, 3)
   const int tid = threadIdx.x, warp = tid >> 5;
   const int iters = (p.halo ? 3 : p.ntaps) * p.k_chunks;
   const int per_img = p.tiles_per_img * p.n_otiles;
+  const int TBi = p.TB > 1 ? p.TB : 1;
+  const int wgrp = p.w_group > 1 ? p.w_group : 1;
   auto decode = [&](int t, int& b, int& o0, int& m0, int& n0) {
     b = t / per_img;
     const int rem = t - b * per_img;
+    b *= TBi;
     const int oi = rem / p.tiles_per_img;
     const int tile = rem - oi * p.tiles_per_img;
     o0 = oi * p.n_tile;
@@ -118,7 +129,7 @@ __global__ void __launch_bounds__(kGemmThreads, 3)
     if (elect_one()) {
       tma_prefetch_desc(&map_x);
       tma_prefetch_desc(&map_w);
-      const uint32_t bytes = (uint32_t)(p.TH * p.TW * 128 + b_stage_bytes);
+      const uint32_t bytes = (uint32_t)(p.TH * p.TW * TBi * 128 + b_stage_bytes);
       // ring position and parity are carried as counters: `g % stages`, `g / stages`, `it / k_chunks` with run-time
       // divisors cost ~30 instructions each on the single issuing thread of this warp
       int st = 0;
@@ -126,7 +137,7 @@ __global__ void __launch_bounds__(kGemmThreads, 3)
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         int b, o0, m0, n0;
         decode(t, b, o0, m0, n0);
-        const int wb = p.w_shared ? 0 : b;
+        const int wb = p.w_shared ? 0 : b / wgrp;
         int tap = 0, kc = 0;
         for (int it = 0; it < iters; ++it) {
           mbar_wait(&empty[st], ph ^ 1);
@@ -218,9 +229,16 @@ __global__ void __launch_bounds__(kGemmThreads, 3)
       const int as = i & 1;
       int b, o0, m0, n0;
       decode(t, b, o0, m0, n0);
-      const int m = m0 + r / p.TW, n = n0 + r % p.TW;
-      const bool valid = r < p.TH * p.TW && m < p.Mh && n < p.Mw;
+      const int ppi = p.TH * p.TW;                 // rows of one image in the tile
+      const int bl = TBi > 1 ? r / ppi : 0, rr = r - bl * ppi;
+      const int m = m0 + rr / p.TW, n = n0 + rr % p.TW;
+      const bool valid = r < ppi * TBi && b + bl < p.B && m < p.Mh && n < p.Mw;
+      b += bl;
       const int oy = m * p.sy + p.py, ox = n * p.sx + p.px;
+      const float* biasp = p.bias;
+      if (biasp && p.bias_set_stride) biasp += (int64_t)(b / wgrp) * p.bias_set_stride;
+      if (p.bias_classes == 9 && biasp)
+        biasp += ((oy == 0 ? 0 : (oy == p.OH - 1 ? 2 : 1)) * 3 + (ox == 0 ? 0 : (ox == p.OW - 1 ? 2 : 1))) * p.O;
       float nz = 0.f;
       if (p.act == 1 && valid && p.noise) {
         const float nw = p.noise_w ? *p.noise_w : 1.f;
@@ -229,7 +247,7 @@ __global__ void __launch_bounds__(kGemmThreads, 3)
       OT* out = (OT*)p.out + (int64_t)b * p.out_bstride + (int64_t)oy * p.out_rstride + (int64_t)ox * p.out_pstride + o0;
       // fused ToRGB (model.py:360-369): the 1x1 modulated conv to 3 channels reads exactly the activations this thread
       // holds, so it is 3 dot products in the epilogue instead of a kernel that re-reads the whole layer output from HBM
-      if (p.rgb_out && (b != cur_b || o0 != cur_o0)) {
+      if (p.rgb_out && (b != cur_b || o0 != cur_o0)) {   // (never with TB > 1: b is the tile's image here)
         asm volatile("bar.sync 2, 128;" ::: "memory");  // readers of the previous image's weights are done
         for (int e = tid - 64; e < p.n_tile; e += 128) {
           const float* w = p.rgb_w + ((int64_t)b * 3) * p.O + o0 + e;
@@ -268,13 +286,19 @@ __global__ void __launch_bounds__(kGemmThreads, 3)
         if (p.act == 1) {
 #pragma unroll
           for (int k = 0; k < 32; ++k) {
-            float tt = f[k] + nzc + (p.bias ? __ldg(p.bias + bofs + k) : 0.f);
+            float tt = f[k] + nzc + (biasp ? __ldg(biasp + bofs + k) : 0.f);
             f[k] = (tt > 0.f ? tt : tt * p.slope) * p.gain;
+          }
+        } else if (p.act == 4) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            const float tt = f[k] + (biasp ? __ldg(biasp + bofs + k) : 0.f);
+            f[k] = tt > 0.f ? tt : tt * __ldg(p.slope_c + bofs + k);
           }
         } else if (p.act >= 2) {
 #pragma unroll
           for (int k = 0; k < 32; ++k) {
-            const float tt = f[k] + (p.bias ? __ldg(p.bias + bofs + k) : 0.f);
+            const float tt = f[k] + (biasp ? __ldg(biasp + bofs + k) : 0.f);
             f[k] = p.act == 3 ? tanhf(tt) : tt;
           }
         }
@@ -414,10 +438,15 @@ int launch_gemm_class(const CUtensorMap& mx, const CUtensorMap& mw, ConvGemmPara
   const size_t smem = (size_t)stages * stage_bytes + 1024;
   TilePlan tp = pick_tile(p.Mh, p.Mw);
   if (p.halo) tp = TilePlan{1, 128, p.Mh, (p.Mw + 127) / 128};
+  if (p.TB > 1) {
+    FMI_REQUIRE(!p.halo && !p.rgb_out && !p.merge_o && p.Mh * p.Mw * p.TB <= 128 && (p.w_shared || p.w_group % p.TB == 0),
+                "modconv_gemm: bad multi-image tile (TB=%d, %dx%d, w_group=%d)", p.TB, p.Mh, p.Mw, p.w_group);
+    tp = TilePlan{p.Mh, p.Mw, 1, 1};
+  }
   p.TH = tp.TH; p.TW = tp.TW; p.tiles_w = tp.tiles_w;
   p.tiles_per_img = tp.tiles_h * tp.tiles_w;
   p.n_otiles = p.O / p.n_tile;
-  const int64_t total = (int64_t)p.tiles_per_img * p.n_otiles * p.B;
+  const int64_t total = (int64_t)p.tiles_per_img * p.n_otiles * ((p.B + (p.TB > 1 ? p.TB : 1) - 1) / (p.TB > 1 ? p.TB : 1));
   FMI_REQUIRE(total < (1ll << 31), "modconv_gemm: too many tiles");
   p.total_tiles = (int)total;
   if (p.out_pstride == 0) {
@@ -439,7 +468,7 @@ int launch_gemm_class(const CUtensorMap& mx, const CUtensorMap& mw, ConvGemmPara
   const double wflops = 2.0 * pix * taps * p.I * (p.merge_o ? n_real * 4.0 / taps : n_real);
   const double out_elems = pix * (p.merge_o ? 4.0 * p.merge_o : (double)p.O);
   const double wbytes = ((double)p.B * p.H * p.W * p.I + out_elems * (p.add_out ? 2.0 : 1.0) +
-                         (double)p.T * p.O * p.I * (p.w_shared ? 1.0 : (double)p.B)) * esz +
+                         (double)p.T * p.O * p.I * (p.w_shared ? 1.0 : (double)(p.B / (p.w_group > 1 ? p.w_group : 1)))) * esz +
                         (p.nchw_out ? pix * p.nchw_C * 4.0 : 0.0);
   FmiProfScope prof(p.prof_kind ? p.prof_kind : FMI_PROF_GEMM, st, wflops, wbytes);
   kern<<<grid, kGemmThreads, smem, st>>>(mx, mw, p);

@@ -290,7 +290,7 @@ class _Ctx:
 
 def decoder_forward(gen, x, f_e=None, mask=None, taps=None, pool_to=None, z=None):
     """The decoder loop of ResGenerator.forward (network.py:256-268) for `x` = encoded (+ f) [B, C, H, W] fp32 NCHW.
-    Returns the image [B, 3, H * 2^layers, W * 2^layers] fp32. `taps` (diagnostics, tests/diag_picnet_blocks.py): a dict that
+    Returns the image [B, 3, H * 2^layers, W * 2^layers] fp32. `taps` (diagnostics, tools/debug/diag_picnet_blocks.py): a dict that
     receives an fp32 NCHW copy of every block output. `pool_to` = (h, w): return AdaptiveAvgPool2d(pool_to) of the image
     instead (modules/model.py:111), fused into the Output kernel when it is an exact 4x4 mean. `z` [B, z_nc, H, W]: the
     latent of network.py:249-254 — f = generator(z) (+ generator{i}) is computed here and added to `x` (the residual-sum

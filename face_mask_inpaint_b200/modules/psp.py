@@ -8,9 +8,9 @@ What runs where:
   * decoder = this package's StyleGAN2 `Generator` (modulated-conv / blur / ToRGB kernels, NHWC bf16 or tf32);
   * `attention1` (C=512 @16^2, out_conv) and `attention2` (C=256 @32^2): the fused attention kernel;
   * the masked source/reference blends (psp_encoders.py:127-138): `fmi_composite` with the mask sampled in the kernel;
-  * the IR-SE50 trunk and the 18 map2style heads: PyTorch + cuDNN as in the reference (next scope row, not kernels here).
-    In eval mode source and reference go through the trunk as ONE 2N batch (BatchNorm uses running statistics, so the
-    result is the reference's); in train mode they are two passes, as in the reference, because batch statistics differ.
+  * the IR-SE50 trunk, the FPN adds and the 18 map2style heads: in inference the implicit-GEMM kernels of
+    csrc/ir_encoder.cu (modules/psp_fast.py: eval-mode BatchNorm folded, source and reference as ONE 2N batch); under
+    autograd / in train mode PyTorch + cuDNN as in the reference (two passes, because batch statistics differ).
 """
 from __future__ import annotations
 
@@ -119,6 +119,9 @@ class GradualStyleEncoder(nn.Module):
         return F.interpolate(x, size=y.shape[-2:], mode='bilinear', align_corners=True) + y
 
     def forward(self, x, ref=None, mask=None):
+        from . import psp_fast
+        if psp_fast.supported(self, x, ref):      # inference: trunk, FPN and heads on the sm_100a kernels (psp_fast.py)
+            return psp_fast.encoder_forward(self, x, ref, mask)
         if ref is None:
             c1, c2, c3 = self._trunk(x)
         else:

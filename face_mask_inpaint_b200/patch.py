@@ -219,6 +219,9 @@ def _install_compositing_callers():
         return
 
     def gradual_style_encoder_forward(self, x, ref=None, mask=None):
+        from .modules import psp_fast
+        if psp_fast.supported(self, x, ref):      # inference: trunk, FPN adds and map2style heads on the sm_100a kernels
+            return psp_fast.encoder_forward(self, x, ref, mask)
         taps = {6: None, 20: None, 23: None}
 
         def trunk(t):

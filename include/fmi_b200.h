@@ -317,6 +317,41 @@ int fmi_conv3x3_nhwc(const void* x, int64_t x_pixel_stride, const void* wp, cons
 int fmi_output_conv_tanh(const void* xpad, const float* weight, const float* bias, float* img, float* pooled,
                          float* scratch, int B, int C, int O, int H, int W, int mma, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * f2  the pSp encoder: IR-SE50 trunk, FPN adds and map2style heads of GradualStyleEncoder
+ * (modules/psp/encoders/psp_encoders.py:13-37,100-152; units encoders/helpers.py:56-119), inference, NHWC in the operand type.
+ *
+ * fmi_conv_nhwc: Conv2d(ksize 1 or 3, padding ksize/2) on the tcgen05 implicit GEMM.
+ *   x      input, I channels per pixel, addressed by (pixel, row, image) strides in ELEMENTS — a strided view (every second
+ *          pixel and row) makes a stride-2 1x1 conv. With planes = 1 x holds the 4 pixel-parity planes [4][B][H][W][*] of the
+ *          real input (fmi_space_to_planes_nhwc) and the conv is the 3x3 STRIDE-2 conv of that input. H, W = OUTPUT extents.
+ *   wp     [sets][ksize^2][O][I] in the operand type (I contiguous; tap index ky*ksize + kx), sets = 1 when w_group = 0 (batch-
+ *          shared weights), else B / w_group: images [g*w_group, (g+1)*w_group) use set g (heads as batch entries).
+ *   bias   fp32 [O], or [9][O] with bias_classes = 9: indexed by the border class 3*vy + vx of the output pixel (vy: 0 first row,
+ *          2 last row, 1 otherwise; vx alike) — the shift of a BatchNorm that precedes a zero-padded 3x3 conv (helpers.py:107-109).
+ *          bias_per_set = 1 (with w_group >= 1): one such bias per weight set, concatenated.
+ *   act    2: y = acc + bias; 1: leaky_relu(slope); 4: PReLU with slope_c [O] per channel (helpers.py:110). add_y: y += result.
+ *   y      NHWC, O channels per pixel out of y_pixel_stride, dense rows / images. round_y as in fmi_conv3x3_nhwc.
+ */
+int fmi_conv_nhwc(const void* x, int64_t x_pixel_stride, int64_t x_row_stride, int64_t x_img_stride, const void* wp,
+                  const float* bias, int bias_classes, const float* slope_c, float slope, void* y, int64_t y_pixel_stride,
+                  int B, int I, int O, int H, int W, int ksize, int planes, int w_group, int bias_per_set, int act, int add_y,
+                  int round_y, int mma, void* stream);
+/* x [B][H][W][heads*C] (pixel stride x_pixel_stride) -> y [4][heads*B][H/2][W/2][C]: plane 2*(row&1) + (col&1), batch entry
+ * head*B + b (the input layout of fmi_conv_nhwc(planes = 1)). */
+int fmi_space_to_planes_nhwc(const void* x, int64_t x_pixel_stride, void* y, int B, int C, int H, int W, int heads, int mma,
+                             void* stream);
+/* SEModule (helpers.py:56-74): mean[b][c] = mean_hw r[b]; gate = sigmoid(w2 relu(w1 mean)), w1 [R][C], w2 [C][R] fp32;
+ * r dense [B][HW][C]; mean, gate: fp32 [B][C] scratch / result. */
+int fmi_se_gate_nhwc(const void* r, const float* w1, const float* w2, float* mean, float* gate, int B, int C, int R, int HW,
+                     int mma, void* stream);
+/* y = r * gate[b][c] + sc (helpers.py:116-119): r, y dense [B][H][W][C]; sc read through (pixel, row, image) element strides. */
+int fmi_se_scale_add_nhwc(const void* r, const float* gate, const void* sc, int64_t sc_pixel_stride, int64_t sc_row_stride,
+                          int64_t sc_img_stride, void* y, int B, int C, int H, int W, int mma, void* stream);
+/* y = bilinear_align_corners(x [B][h][w][C] -> OH x OW) + add  (psp_encoders.py:83-98 `_upsample_add`). */
+int fmi_upsample_add_nhwc(const void* x, const void* add, void* y, int B, int C, int h, int w, int OH, int OW, int mma,
+                          void* stream);
+
 #ifdef __cplusplus
 }
 #endif

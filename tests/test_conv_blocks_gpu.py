@@ -274,7 +274,7 @@ def test_batched_weight_plan_matches_per_conv_path(monkeypatch):
     assert launches[0] < launches[1] - 150, launches           # 69 convolutions x 3 launches -> 3 x 3 launches
     for a, b in zip(states[0], states[1]):
         assert rel_err(a, b) <= 1e-5                            # measured 3e-7: another summation order of the same products
-    # This random-weight generator amplifies a 3e-7 change of the weights to ~3e-3 of the image (tests/dbg_plan.py: two per-conv
+    # This random-weight generator amplifies a 3e-7 change of the weights to ~3e-3 of the image (tools/debug/dbg_plan.py: two per-conv
     # runs are bit-identical, batched vs per-conv differ by 3.6e-3), the same sensitivity that turns TF32 operand rounding into
     # 1e-2 (test_whole_generator_kernel_path_vs_cudnn_paths); the images are therefore only held to that scale here.
     assert rel_err(outs[0], outs[2]) <= 2e-2 and rel_err(outs[1], outs[3]) <= 2e-2

@@ -8,7 +8,7 @@ if len(sys.argv) == 1:
         print(f"dbg={dbg:2d} (1=no ld, 2=no exp, 4=no st, 8=no PV mma, 16=no QK mma): {out.stdout.strip()} {out.stderr.strip()[-200:]}")
 else:
     import torch
-    sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent.parent))
     from face_mask_inpaint_b200 import _lib, ops
     dev = "cuda"
     res = []

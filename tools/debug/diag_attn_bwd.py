@@ -2,7 +2,7 @@
 import sys
 from pathlib import Path
 import torch
-sys.path.insert(0, str(Path(__file__).resolve().parent.parent)); sys.path.insert(0, str(Path(__file__).resolve().parent))
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent.parent)); sys.path.insert(0, str(Path(__file__).resolve().parent.parent.parent / "tests"))
 from oracle import ref_ops as O
 from test_attention_gpu import _mask, _scaled_query_weight
 from face_mask_inpaint_b200.modules import ExampleGuidedAttention, Auto_Attn

@@ -1,5 +1,5 @@
 """Per-block comparison of the PICNet decoder kernel path (picnet_fast.decoder_forward) with the cuDNN path (fp32, TF32 off)
-on the real shapes — NOT a pytest file:  python tests/diag_picnet_blocks.py [fp32|bf16]
+on the real shapes — NOT a pytest file:  python tools/debug/diag_picnet_blocks.py [fp32|bf16]
 Each block of the kernel path is also re-run from the cuDNN path's input of that block, so the per-block error is separated
 from the accumulated one."""
 import copy
@@ -10,7 +10,7 @@ from pathlib import Path
 
 import torch
 
-ROOT = Path(__file__).resolve().parent.parent
+ROOT = Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 from face_mask_inpaint_b200.modules import picnet_fast as PF  # noqa: E402

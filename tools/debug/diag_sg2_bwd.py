@@ -1,12 +1,12 @@
 """Diagnostic (not a pytest file): run fmi_styled_conv_bwd_nhwc with act = 0 and read the per-sample weight gradient
-G[b][t][o][i] straight out of the workspace; compare with a torch reference. Usage: python tests/diag_sg2_bwd.py"""
+G[b][t][o][i] straight out of the workspace; compare with a torch reference. Usage: python tools/debug/diag_sg2_bwd.py"""
 import sys
 from pathlib import Path
 
 import torch
 import torch.nn.functional as F
 
-sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent.parent))
 from face_mask_inpaint_b200 import _lib, ops  # noqa: E402
 
 dev = "cuda"

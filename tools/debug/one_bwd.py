@@ -2,7 +2,7 @@
 import sys
 from pathlib import Path
 import torch
-sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent.parent))
 from face_mask_inpaint_b200.modules import Auto_Attn
 dev = "cuda"
 torch.manual_seed(0)

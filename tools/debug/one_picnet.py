@@ -1,5 +1,5 @@
 """One PICNet-ref 256^2 forward (batch 8 by default) after two warm-up forwards, for ncu launch lists:
-    python tests/one_picnet.py [batch] [fp32|bf16]"""
+    python tools/debug/one_picnet.py [batch] [fp32|bf16]"""
 import os
 import sys
 import types
@@ -7,8 +7,8 @@ from pathlib import Path
 
 import torch
 
-sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
-sys.path.insert(0, str(Path(__file__).resolve().parent))
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent.parent))
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent.parent / "tests"))
 batch = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 os.environ["FMI_PRECISION"] = sys.argv[2] if len(sys.argv) > 2 else "fp32"
 from face_mask_inpaint_b200.modules.picnet import build_picnet_ref  # noqa: E402

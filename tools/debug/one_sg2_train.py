@@ -1,11 +1,11 @@
-"""One StyleGAN2-1024 forward+backward (bf16 operands, batch 2) for ncu launch lists: python tests/one_sg2_train.py"""
+"""One StyleGAN2-1024 forward+backward (bf16 operands, batch 2) for ncu launch lists: python tools/debug/one_sg2_train.py"""
 import os
 import sys
 from pathlib import Path
 
 import torch
 
-sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent.parent))
 os.environ.setdefault("FMI_PRECISION", "bf16")
 from face_mask_inpaint_b200.modules import stylegan2 as SG  # noqa: E402
 

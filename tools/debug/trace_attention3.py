@@ -2,7 +2,7 @@
 import ctypes, sys
 from pathlib import Path
 import torch
-sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent.parent))
 from face_mask_inpaint_b200 import _lib, ops
 
 lib = _lib.load()

@@ -2,4 +2,4 @@
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_attention_gpu.py tests/test_golden_gpu.py -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 tail -6 gpurun_out/pytest_gpu.log
-python tests/perf_attention.py 2>&1 | tee gpurun_out/perf_attention.txt
+python tools/perf/perf_attention.py 2>&1 | tee gpurun_out/perf_attention.txt

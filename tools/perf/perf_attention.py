@@ -1,6 +1,6 @@
 """Attention microbenchmark (BASELINE config 2) — NOT a pytest file; run on the GPU box:
 
-    python tests/perf_attention.py > gpurun_out/perf_attention.txt
+    python tools/perf/perf_attention.py > gpurun_out/perf_attention.txt
 
 Times fmi_attn_fwd (prologue kernels + main kernel) with CUDA events and, beside it, the reference's PyTorch
 formulation (oracle functions executed on the same GPU: cuBLAS fp32 bmm + ATen softmax, the composition the
@@ -11,7 +11,7 @@ from pathlib import Path
 
 import torch
 
-sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent.parent))
 from face_mask_inpaint_b200 import _lib, ops  # noqa: E402
 from oracle import ref_ops as O  # noqa: E402
 

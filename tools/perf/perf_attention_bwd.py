@@ -5,7 +5,7 @@ from pathlib import Path
 
 import torch
 
-sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent.parent))
 from face_mask_inpaint_b200.modules import Auto_Attn, ExampleGuidedAttention  # noqa: E402
 from oracle import ref_ops as O  # noqa: E402
 

@@ -1,8 +1,8 @@
 """RefpSp decoder training step at BASELINE config 5's scale, batch-sharded over N GPUs — NOT a pytest file:
 
-    python tests/perf_dist_train.py                                   # one GPU
+    python tools/perf/perf_dist_train.py                                   # one GPU
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29555 \
-        tests/perf_dist_train.py                                      # N GPUs, NCCL
+        tools/perf/perf_dist_train.py                                      # N GPUs, NCCL
 
 Every rank: StyleGAN2-1024 Generator (train_decoder: all 30.4 M parameters trainable) forward + backward on its own batch of 2
 (train_psp.sh's per-GPU batch) through the modulated-conv / upfirdn2d / bias-act kernels and their backward kernels, the bucketed
@@ -18,7 +18,7 @@ from pathlib import Path
 import torch
 import torch.distributed as dist
 
-sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent.parent))
 os.environ.setdefault("FMI_PRECISION", "bf16")
 if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
     os.environ["NCCL_DEBUG"] = "WARN"

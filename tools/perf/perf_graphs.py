@@ -1,6 +1,6 @@
 """Whole-model forwards, eager launch vs one CUDA-graph replay (face_mask_inpaint_b200/graphs.py) — NOT a pytest file:
 
-    python tests/perf_graphs.py > gpurun_out/perf_graphs.txt
+    python tools/perf/perf_graphs.py > gpurun_out/perf_graphs.txt
 
 PICNet-ref 256^2 (BASELINE config 1; fp32 contract, cuDNN TF32 allowed) at batch 1 / 4 / 8 and RefpSp 1024^2 (config 3; bf16
 operands) at batch 2 / 8, plus the bf16-autocast variants of the cuDNN trunks. Same kernels in both columns: the difference is
@@ -13,7 +13,7 @@ from pathlib import Path
 
 import torch
 
-ROOT = Path(__file__).resolve().parent.parent
+ROOT = Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 from face_mask_inpaint_b200.graphs import CapturedForward  # noqa: E402

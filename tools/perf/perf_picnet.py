@@ -1,6 +1,6 @@
 """PICNet-ref generator forward, 256x256 inputs (BASELINE config 1) — NOT a pytest file; run on the GPU box:
 
-    python tests/perf_picnet.py > gpurun_out/perf_picnet.txt
+    python tools/perf/perf_picnet.py > gpurun_out/perf_picnet.txt
 
 `ours`   : modules/picnet.py::ReferenceFill — ExampleGuidedAttention @32^2, Auto_Attn @128^2, mask scaling and (when TF32
            convolutions are allowed or FMI_PRECISION=bf16) the encoder / decoder conv blocks on the sm_100a kernels; with
@@ -22,7 +22,7 @@ from pathlib import Path
 import torch
 from torch import nn
 
-ROOT = Path(__file__).resolve().parent.parent
+ROOT = Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 from face_mask_inpaint_b200 import _lib  # noqa: E402

@@ -1,4 +1,4 @@
-"""Where a PICNet-ref forward spends its time — NOT a pytest file:  python tests/perf_picnet_breakdown.py
+"""Where a PICNet-ref forward spends its time — NOT a pytest file:  python tools/perf/perf_picnet_breakdown.py
 First two lines: the forward split into CUDA graphs (encoders + EGA / decoder) = GPU times. Then per sub-module CUDA events in
 eager mode (host-launch bound; the decoder blocks show 0 there because the kernel path replaces `ResGenerator.forward` as a
 whole and does not call the block modules — set FMI_PICNET_CUDNN=1 to see the cuDNN blocks)."""
@@ -8,7 +8,7 @@ from pathlib import Path
 
 import torch
 
-ROOT = Path(__file__).resolve().parent.parent
+ROOT = Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 from face_mask_inpaint_b200.modules.picnet import build_picnet_ref  # noqa: E402

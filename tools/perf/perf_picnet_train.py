@@ -1,7 +1,7 @@
 """PICNet reference-fill generator TRAIN step (BASELINE config 4, generator side): ReferenceFill forward (z ~ N(mu, sigma) as in
 train_reference_fill.py:342), L1 reconstruction loss, backward, Adam(1e-5) step — NOT a pytest file:
 
-    python tests/perf_picnet_train.py > gpurun_out/perf_picnet_train.txt
+    python tools/perf/perf_picnet_train.py > gpurun_out/perf_picnet_train.txt
 
 `ours`   : both attention modules forward AND backward on the sm_100a kernels (fmi_attn_fwd / fmi_attn_bwd, no S x S map);
            the conv blocks under autograd are cuDNN (their backward is not a kernel of this package yet).
@@ -18,7 +18,7 @@ from pathlib import Path
 import torch
 from torch import nn
 
-ROOT = Path(__file__).resolve().parent.parent
+ROOT = Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 from face_mask_inpaint_b200.modules.picnet import build_picnet_ref  # noqa: E402

@@ -1,7 +1,7 @@
 """a4 / a5: this package's kernels next to the REFERENCE'S OWN CUDA kernels (oracle/_ref/*.so, built by oracle/build_ref.py from
 modules/psp/stylegan2/op/*.cu) on the same B200 and the same tensors — NOT a pytest file:
 
-    python tests/perf_reference_ops.py > gpurun_out/perf_reference_ops.txt
+    python tools/perf/perf_reference_ops.py > gpurun_out/perf_reference_ops.txt
 
 Shapes are the largest live call sites of the 1024^2 generator at batch 8. GB/s = algorithmic bytes (read + write
 once) / time; "of HBM" against the measured copy bandwidth in MEASURED_PEAKS.json (6456.8 GB/s)."""
@@ -10,7 +10,7 @@ from pathlib import Path
 
 import torch
 
-ROOT = Path(__file__).resolve().parent.parent
+ROOT = Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT))
 from face_mask_inpaint_b200 import ops  # noqa: E402
 from oracle import build_ref  # noqa: E402

@@ -1,5 +1,5 @@
 """RefpSp inference, 1024x1024 output (BASELINE config 3: pSp encoder + StyleGAN2 decoder with attention, batch 8) — NOT a
-pytest file; run on the GPU box:  python tests/perf_refpsp.py > gpurun_out/perf_refpsp.txt
+pytest file; run on the GPU box:  python tools/perf/perf_refpsp.py > gpurun_out/perf_refpsp.txt
 
 `ours`   : modules/psp.py::pSp — decoder, both attention modules and the masked blends on the sm_100a kernels (bf16 operands
            = the configuration's precision, and the fp32 contract); IR-SE50 trunk + map2style heads on cuDNN.
@@ -16,7 +16,7 @@ from pathlib import Path
 import torch
 from torch import nn
 
-ROOT = Path(__file__).resolve().parent.parent
+ROOT = Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 from face_mask_inpaint_b200 import _lib  # noqa: E402

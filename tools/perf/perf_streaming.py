@@ -1,6 +1,6 @@
 """HBM-bound kernels against the measured copy bandwidth — NOT a pytest file; run on the GPU box:
 
-    python tests/perf_streaming.py > gpurun_out/perf_streaming.txt
+    python tools/perf/perf_streaming.py > gpurun_out/perf_streaming.txt
 
 Each case is one C-ABI call at a StyleGAN2-1024 / PICNet shape; `GB/s` = algorithmic bytes (every input
 element read once, every output element written once) / CUDA-event time; `frac` = GB/s over MEASURED_PEAKS.json hbm_gbs.
@@ -13,7 +13,7 @@ from pathlib import Path
 
 import torch
 
-ROOT = Path(__file__).resolve().parent.parent
+ROOT = Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT))
 from face_mask_inpaint_b200 import ops  # noqa: E402
 from face_mask_inpaint_b200.modules import stylegan2 as SG  # noqa: E402

@@ -1,6 +1,6 @@
 """StyleGAN2-1024 decoder benchmark (BASELINE config 3, decoder only) — NOT a pytest file; run on the GPU box:
 
-    python tests/perf_stylegan2.py > gpurun_out/perf_stylegan2.txt
+    python tools/perf/perf_stylegan2.py > gpurun_out/perf_stylegan2.txt
 
 Times Generator.forward([codes], input_is_latent=True, randomize_noise=False) at batch 8 on our kernels (fp32 contract
 and bf16), the per-kernel-class split from the library's CUDA-event hooks, and — beside it — the reference formulation
@@ -13,7 +13,7 @@ from pathlib import Path
 
 import torch
 
-sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent.parent))
 from face_mask_inpaint_b200 import _lib  # noqa: E402
 from face_mask_inpaint_b200.modules import stylegan2 as SG  # noqa: E402
 from oracle import ref_ops as O  # noqa: E402

@@ -1,5 +1,5 @@
 """StyleGAN2-1024 decoder forward+backward (BASELINE config 5's decoder part: train_psp.py with train_decoder) — NOT a
-pytest file; run on the GPU box:  python tests/perf_stylegan2_train.py > gpurun_out/perf_stylegan2_train.txt
+pytest file; run on the GPU box:  python tools/perf/perf_stylegan2_train.py > gpurun_out/perf_stylegan2_train.txt
 
 Times Generator.forward([codes], input_is_latent=True, randomize_noise=False) + image.backward() on our kernels (fp32
 contract and bf16) and on the reference formulation (oracle functions under autograd on the same GPU: cuDNN grouped
@@ -11,7 +11,7 @@ from pathlib import Path
 
 import torch
 
-sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent.parent))
 from face_mask_inpaint_b200 import _lib  # noqa: E402
 from face_mask_inpaint_b200.modules import stylegan2 as SG  # noqa: E402
 from oracle import ref_ops as O  # noqa: E402
