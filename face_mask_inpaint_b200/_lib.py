@@ -72,7 +72,7 @@ PROTOTYPES = {
     "fmi_conv_nhwc": (_i, [_vp, _i64, _i64, _i64, _vp, _vp, _i, _vp, _f, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i,
                            _i, _i, _vp]),
     "fmi_space_to_planes_nhwc": (_i, [_vp, _i64, _vp, _i, _i, _i, _i, _i, _i, _vp]),
-    "fmi_se_gate_nhwc": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "fmi_se_gate_nhwc": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "fmi_se_scale_add_nhwc": (_i, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _i, _i, _i, _i, _i, _vp]),
     "fmi_upsample_add_nhwc": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
 }

@@ -12,7 +12,7 @@
 //                                      re-laid as its 4 pixel-parity planes [4][B][H/2][W/2][C] (space_to_planes); input row
 //                                      2m + dy then is row m + (dy < 0 ? -1 : 0) of plane (dy & 1), i.e. the 9 taps are plain
 //                                      TMA boxes again (zero fill at -1 = the padding)
-//   s  = sigmoid(fc2(relu(fc1(mean_hw(r)))))     channel_mean (atomics) + se_gate (one CTA per image)
+//   s  = sigmoid(fc2(relu(fc1(mean_hw(r)))))     channel_sum (slab partial sums, no atomics) + se_gate (one CTA per image)
 //   y  = r * s + shortcut(x)           se_scale_add; shortcut = x subsampled (MaxPool2d(1, s)) or BN(conv1x1_stride_s(x)) = ONE
 //                                      GEMM reading x through a strided tensor map
 // map2style heads (psp_encoders.py:13-37): log2(spatial) x [conv3x3 stride 2 + bias + LeakyReLU(0.01)] down to 1x1, then an
@@ -52,20 +52,20 @@ __global__ void __launch_bounds__(256) space_to_planes_kernel(const T* __restric
   }
 }
 
-// mean over H*W per (image, channel): x [B][HW][C] dense -> mean [B][C] fp32 (zeroed by the caller's memset). Each CTA sums a
-// slab of pixel rows: registers -> shared-memory atomics (threads of a CTA that hold the same channels) -> one global atomic per
-// channel and CTA.
+// Sum over a slab of pixel rows per (image, channel): x [B][HW][C] dense -> part [B][gridDim.x][C] fp32. No atomics: thread
+// partials go through shared memory and are added in a fixed order, so the result is bit-reproducible (eager run == CUDA-graph
+// replay; the sums feed a sigmoid gate whose product is then rounded to the operand type — a last-bit difference of the mean
+// would flip roundings downstream).
+constexpr int kSeMaxSlabs = 32;
 template <typename T>
-__global__ void __launch_bounds__(256) channel_mean_kernel(const T* __restrict__ x, float* __restrict__ mean, int C, int HW,
-                                                           int rows_per_block, float inv_hw) {
+__global__ void __launch_bounds__(256) channel_sum_kernel(const T* __restrict__ x, float* __restrict__ part, int C, int HW,
+                                                          int rows_per_block) {
   constexpr int V = 16 / sizeof(T);
-  __shared__ float sacc[2048];                // C <= 256 * V
-  const int cv = C / V;                       // vectors per pixel
+  __shared__ float sacc[256 * V];             // [lanes][C], lanes * C = 256 * V
+  const int cv = C / V;                       // vectors per pixel (<= 256)
   const int b = blockIdx.y;
-  const int lanes = 256 / cv;                 // pixel rows handled concurrently (cv <= 256)
+  const int lanes = 256 / cv;                 // pixel rows handled concurrently
   const int vc = threadIdx.x % cv, lane = threadIdx.x / cv;
-  for (int c = threadIdx.x; c < C; c += 256) sacc[c] = 0.f;
-  __syncthreads();
   if (lane < lanes) {
     const int r0 = blockIdx.x * rows_per_block, r1 = min(HW, r0 + rows_per_block);
     float acc[V];
@@ -78,20 +78,31 @@ __global__ void __launch_bounds__(256) channel_mean_kernel(const T* __restrict__
       for (int k = 0; k < V; ++k) acc[k] += to_f32<T>(v.e[k]);
     }
 #pragma unroll
-    for (int k = 0; k < V; ++k) atomicAdd(&sacc[vc * V + k], acc[k]);
+    for (int k = 0; k < V; ++k) sacc[lane * C + vc * V + k] = acc[k];
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += 256) atomicAdd(mean + (int64_t)b * C + c, sacc[c] * inv_hw);
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float t = 0.f;
+    for (int l = 0; l < lanes; ++l) t += sacc[l * C + c];
+    part[((int64_t)b * gridDim.x + blockIdx.x) * C + c] = t;
+  }
 }
 
-// SEModule gate (helpers.py:56-74): g[b][c] = sigmoid(W2 relu(W1 m[b])), W1 [R][C], W2 [C][R]; one CTA per image.
-__global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ mean, const float* __restrict__ w1,
-                                                      const float* __restrict__ w2, float* __restrict__ gate, int C, int R) {
+// SEModule gate (helpers.py:56-74): m = mean_hw r (the slab sums added in slab order), g[b][c] = sigmoid(W2 relu(W1 m[b])),
+// W1 [R][C], W2 [C][R]; one CTA per image.
+__global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ part, int slabs, float inv_hw,
+                                                      const float* __restrict__ w1, const float* __restrict__ w2,
+                                                      float* __restrict__ mean, float* __restrict__ gate, int C, int R) {
   extern __shared__ float sm[];   // [C] mean, [R] hidden
   float* m = sm;
   float* hid = sm + C;
   const int b = blockIdx.x;
-  for (int c = threadIdx.x; c < C; c += 256) m[c] = mean[(int64_t)b * C + c];
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float t = 0.f;
+    for (int s = 0; s < slabs; ++s) t += part[((int64_t)b * slabs + s) * C + c];
+    m[c] = t * inv_hw;
+    mean[(int64_t)b * C + c] = m[c];
+  }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int r = warp; r < R; r += 8) {
@@ -285,31 +296,31 @@ extern "C" int fmi_space_to_planes_nhwc(const void* x, int64_t x_pixel_stride, v
   return fmi_launched("space_to_planes");
 }
 
-extern "C" int fmi_se_gate_nhwc(const void* r, const float* w1, const float* w2, float* mean, float* gate, int B, int C, int R,
-                                int HW, int mma, void* stream) {
+extern "C" int fmi_se_gate_nhwc(const void* r, const float* w1, const float* w2, float* scratch, float* mean, float* gate, int B,
+                                int C, int R, int HW, int mma, void* stream) {
   FMI_REQUIRE(mma == FMI_MMA_TF32 || mma == FMI_MMA_BF16, "se_gate: bad mma");
   if (B == 0) return FMI_OK;
   const int vec = 16 / esz_of(mma);
-  FMI_REQUIRE(r && w1 && w2 && mean && gate && C >= vec && C % vec == 0 && C / vec <= 256 && R >= 1 && R <= 256 && HW >= 1 &&
-                  B <= 65535 && fmi_aligned(r, 16),
+  FMI_REQUIRE(r && w1 && w2 && scratch && mean && gate && C >= vec && C % vec == 0 && C / vec <= 256 && R >= 1 && R <= 256 &&
+                  HW >= 1 && B <= 65535 && fmi_aligned(r, 16),
               "se_gate: unsupported shape C=%d R=%d", C, R);
   cudaStream_t st = (cudaStream_t)stream;
   FmiProfScope prof(FMI_PROF_SE, st, 2.0 * B * HW * C, (double)B * HW * C * esz_of(mma));
-  FMI_CUDA(cudaMemsetAsync(mean, 0, (size_t)B * C * sizeof(float), st));
   const int lanes = 256 / (C / vec);
   int gx = (HW + lanes * 16 - 1) / (lanes * 16);     // ~16 pixel rows per thread
-  const int cap = (FMI_NUM_SMS * 8 + B - 1) / B;
+  int cap = (FMI_NUM_SMS * 8 + B - 1) / B;
+  if (cap > kSeMaxSlabs) cap = kSeMaxSlabs;
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
   const int rows = (HW + gx - 1) / gx;
   gx = (HW + rows - 1) / rows;
   if (mma == FMI_MMA_TF32)
-    channel_mean_kernel<float><<<dim3(gx, B), 256, 0, st>>>((const float*)r, mean, C, HW, rows, 1.f / (float)HW);
+    channel_sum_kernel<float><<<dim3(gx, B), 256, 0, st>>>((const float*)r, scratch, C, HW, rows);
   else
-    channel_mean_kernel<__nv_bfloat16><<<dim3(gx, B), 256, 0, st>>>((const __nv_bfloat16*)r, mean, C, HW, rows, 1.f / (float)HW);
-  int rc = fmi_launched("channel_mean");
+    channel_sum_kernel<__nv_bfloat16><<<dim3(gx, B), 256, 0, st>>>((const __nv_bfloat16*)r, scratch, C, HW, rows);
+  int rc = fmi_launched("channel_sum");
   if (rc) return rc;
-  se_gate_kernel<<<B, 256, (size_t)(C + R) * sizeof(float), st>>>(mean, w1, w2, gate, C, R);
+  se_gate_kernel<<<B, 256, (size_t)(C + R) * sizeof(float), st>>>(scratch, gx, 1.f / (float)HW, w1, w2, mean, gate, C, R);
   return fmi_launched("se_gate");
 }
 

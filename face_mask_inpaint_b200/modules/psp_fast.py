@@ -229,10 +229,10 @@ def _unit_forward(k: _Ctx, u: _Unit, x, b, h, w):
     if u.se1 is None:
         gate = torch.ones((b, u.depth), dtype=torch.float32, device=k.dev)
     else:
-        mean = torch.empty((b, u.depth), dtype=torch.float32, device=k.dev)
-        gate = torch.empty((b, u.depth), dtype=torch.float32, device=k.dev)
-        _lib.check(k.lib.fmi_se_gate_nhwc(r.data_ptr(), _p(u.se1), _p(u.se2), _p(mean), _p(gate), b, u.depth, u.red, oh * ow, k.mma,
-                                          k.st), "fmi_se_gate_nhwc")
+        scratch = torch.empty((b, 32, u.depth), dtype=torch.float32, device=k.dev)     # [b][32 slabs][C] partial sums
+        mean, gate = torch.empty((2, b, u.depth), dtype=torch.float32, device=k.dev)
+        _lib.check(k.lib.fmi_se_gate_nhwc(r.data_ptr(), _p(u.se1), _p(u.se2), scratch.data_ptr(), _p(mean), _p(gate), b, u.depth,
+                                          u.red, oh * ow, k.mma, k.st), "fmi_se_gate_nhwc")
     y = k.empty(b, oh, ow, u.depth)
     _lib.check(k.lib.fmi_se_scale_add_nhwc(r.data_ptr(), _p(gate), sc.data_ptr(), sc_str[0], sc_str[1], sc_str[2], y.data_ptr(), b,
                                            u.depth, oh, ow, k.mma, k.st), "fmi_se_scale_add_nhwc")

@@ -342,9 +342,10 @@ int fmi_conv_nhwc(const void* x, int64_t x_pixel_stride, int64_t x_row_stride, i
 int fmi_space_to_planes_nhwc(const void* x, int64_t x_pixel_stride, void* y, int B, int C, int H, int W, int heads, int mma,
                              void* stream);
 /* SEModule (helpers.py:56-74): mean[b][c] = mean_hw r[b]; gate = sigmoid(w2 relu(w1 mean)), w1 [R][C], w2 [C][R] fp32;
- * r dense [B][HW][C]; mean, gate: fp32 [B][C] scratch / result. */
-int fmi_se_gate_nhwc(const void* r, const float* w1, const float* w2, float* mean, float* gate, int B, int C, int R, int HW,
-                     int mma, void* stream);
+ * r dense [B][HW][C]; mean, gate: fp32 [B][C] results; scratch: fp32 [B][32][C] (slab partial sums — no atomics, so the
+ * result is bit-reproducible). */
+int fmi_se_gate_nhwc(const void* r, const float* w1, const float* w2, float* scratch, float* mean, float* gate, int B, int C,
+                     int R, int HW, int mma, void* stream);
 /* y = r * gate[b][c] + sc (helpers.py:116-119): r, y dense [B][H][W][C]; sc read through (pixel, row, image) element strides. */
 int fmi_se_scale_add_nhwc(const void* r, const float* gate, const void* sc, int64_t sc_pixel_stride, int64_t sc_row_stride,
                           int64_t sc_img_stride, void* y, int B, int C, int H, int W, int mma, void* stream);

@@ -38,7 +38,15 @@ def _nchw(y):
     return y.float().permute(0, 3, 1, 2).contiguous()
 
 
+@pytest.fixture(autouse=True)
+def _restore_tf32_switches():
+    a, b = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = a, b
+
+
 def _strict():
+    """The PyTorch reference of these tests runs in strict fp32 (restored after every test: other test files assert the default)."""
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
 
@@ -125,8 +133,9 @@ def test_se_gate_scale_add_and_upsample_add(mode):
     rs, xs = _nhwc(PF, k, r), _nhwc(PF, k, xfull)
     mean = torch.empty(b, c, device=dev)
     gate = torch.empty(b, c, device=dev)
-    _lib.check(k.lib.fmi_se_gate_nhwc(rs.data_ptr(), w1.data_ptr(), w2.data_ptr(), mean.data_ptr(), gate.data_ptr(), b, c, red, h * w,
-                                      k.mma, k.st), "fmi_se_gate_nhwc")
+    scratch = torch.empty(b, 32, c, device=dev)
+    _lib.check(k.lib.fmi_se_gate_nhwc(rs.data_ptr(), w1.data_ptr(), w2.data_ptr(), scratch.data_ptr(), mean.data_ptr(), gate.data_ptr(),
+                                      b, c, red, h * w, k.mma, k.st), "fmi_se_gate_nhwc")
     m_want = _nchw(rs).mean(dim=(2, 3))
     g_want = torch.sigmoid(F.linear(torch.relu(F.linear(m_want, w1)), w2))
     assert rel_err(mean, m_want) <= 1e-5 and rel_err(gate, g_want) <= 1e-5
