@@ -321,6 +321,47 @@ def _forward_record(h: Harness, name, net, call_args, kw_tensors, kw_other, dtyp
     return rec
 
 
+def _parity(h: Harness, name, mirror, call, ref_ops, tol):
+    """Whole-model parity of THIS run's model: the UNMODIFIED reference class (baseline/_ref) on the same GPU with the same
+    weights (strict state_dict load), inputs and RNG seed, run in strict fp32 (TF32 off everywhere) = `want`; this package's
+    forward = `got`. Also the reference's own default GPU execution (cuDNN TF32 allowed, PyTorch's default) against `want`, i.e.
+    the error the reference's users have on this GPU. Every forward starts from a deep copy (SpectralNorm u / v advance)."""
+    import copy
+    from baseline import reference as R
+    if not R.available():
+        return {"unavailable": "baseline/_ref is missing"}
+    try:
+        R.import_unpatched(ref_ops)
+        ref = (R.reference_fill() if name == "picnet_ref" else R.psp(output_size=1024)).eval()
+        ref.load_state_dict(mirror.state_dict(), strict=True)
+        ref = ref.to(h.dev)
+        if name == "refpsp":
+            ref.latent_avg = ref.latent_avg.to(h.dev)
+        a, b = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+        rel = lambda x, y: ((x.double() - y.double()).abs().max() / y.double().abs().max()).item()
+        with torch.no_grad():
+            torch.manual_seed(5)
+            ref_default = call(copy.deepcopy(ref), True)
+            torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+            try:
+                torch.manual_seed(5)
+                want = call(copy.deepcopy(ref), True)
+            finally:
+                torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = a, b
+            n0 = h.lib.fmi_kernel_launch_count()
+            torch.manual_seed(5)
+            got = call(copy.deepcopy(mirror), False)
+            n1 = h.lib.fmi_kernel_launch_count()
+        out = {"ours_vs_reference_fp32": rel(got, want), "reference_default_gpu_vs_reference_fp32": rel(ref_default, want),
+               "tolerance": tol, "kernel_launches_of_the_checked_forward": int(n1 - n0),
+               "how": "max|a-b|/max|b| of the output image; reference = the unmodified class from baseline/_ref on this GPU, same weights "
+                      "(strict state_dict load), inputs and RNG seed; fp32 = cuDNN / cuBLAS TF32 switched off"}
+        del ref
+        return out
+    except Exception as ex:  # noqa: BLE001
+        return {"unavailable": f"{type(ex).__name__}: {str(ex)[:300]}"}
+
+
 def ours_picnet_ref(h: Harness):
     from face_mask_inpaint_b200.modules.picnet import build_picnet_ref
     torch.manual_seed(7)
@@ -328,12 +369,17 @@ def ours_picnet_ref(h: Harness):
     with torch.no_grad():
         net.decoder.attn1.gamma.fill_(1.0)     # init 0 would switch the attention branch off (SURVEY §7 'random init hides bugs')
     src, ref, _, mask = make_inputs("picnet_ref", WORKLOADS["picnet_ref"]["batch"], 1000 + h.rank)
+    parity = None
+    if h.rank == 0:
+        s_d, r_d, m_d = src[:2].to(h.dev), ref[:2].to(h.dev), mask[:2].to(h.dev)
+        parity = _parity(h, "picnet_ref", net, lambda m, is_ref: m(s_d, r_d, src_mask=m_d) if is_ref else m(s_d, r_d, m_d), "none", 1e-3)
     rec = _forward_record(h, "picnet_ref", net, [src, ref, mask], {}, {}, "tf32",
                           "ReferenceFill.forward (modules/model.py:81-112): 2 ResEncoders, ExampleGuidedAttention@32^2, ResGenerator "
                           "with Auto_Attn@128^2 up to 1024^2, AdaptiveAvgPool to 256^2 — every conv block, both attentions, the "
                           "compositing and the pooling on this package's sm_100a kernels")
     rec["precision"] = ("fp32 I/O; TF32 tensor-core operands where the reference's own GPU run has them (cuDNN allow_tf32 default) "
                         "and in the attention (hi/lo split logits), fp32 accumulation / softmax / InstanceNorm")
+    rec["parity"] = parity
     return rec
 
 
@@ -345,9 +391,15 @@ def ours_refpsp(h: Harness):
         torch.manual_seed(11)
         net = pSp(refpsp_opts(output_size=1024)).eval().to(h.dev)
         x, ref, _, mask = make_inputs("refpsp", WORKLOADS["refpsp"]["batch"], 2000 + h.rank)
+        parity = None
+        if h.rank == 0:
+            x_d, r_d, m_d = x[:2].to(h.dev), ref[:2].to(h.dev), mask[:2].to(h.dev)
+            parity = _parity(h, "refpsp", net, lambda m, is_ref: m(x_d, ref=r_d, src_mask=m_d, resize=True, randomize_noise=False),
+                             "cuda", 2e-2)
         rec = _forward_record(h, "refpsp", net, [x], dict(ref=ref, src_mask=mask), dict(resize=True, randomize_noise=False), "bf16", "pSp.forward (modules/psp/psp.py:72-130): IR-SE50 GradualStyleEncoder on source + reference "
                               "(one 2N batch), attention1/2, masked blend, 18 map2style heads, StyleGAN2-1024 decoder, face_pool")
         rec["precision"] = "fp32 I/O; bf16 tensor-core operands (FMI_PRECISION=bf16), fp32 accumulation"
+        rec["parity"] = parity
         return rec
     finally:
         if prev is None:

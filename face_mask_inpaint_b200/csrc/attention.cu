@@ -614,7 +614,8 @@ int launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap&
   // every image the fast kernel took) it is timed separately so it cannot dilute the roofline average
   double wf, wb;
   attn_work<T>(prm, pl, &wf, &wb);
-  FmiProfScope prof(prm.qmax2 ? FMI_PROF_ATTN_FALLBACK : FMI_PROF_ATTN, st, wf, wb);
+  // (as the fallback it exits at once for every image the fast kernel took: no algorithmic work is attributed to it)
+  FmiProfScope prof(prm.qmax2 ? FMI_PROF_ATTN_FALLBACK : FMI_PROF_ATTN, st, prm.qmax2 ? 0.0 : wf, prm.qmax2 ? 0.0 : wb);
   if (CLUSTER) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;

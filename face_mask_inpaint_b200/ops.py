@@ -317,6 +317,64 @@ def conv1x1(x, weight, bias=None):
     return y
 
 
+_PAD_BETA = 4.0   # exactly representable in bf16: the marker channel adds no rounding error to the logits
+
+
+def _needs_padding(s, c0, c1):
+    cv = c0 + c1
+    return s % 128 != 0 or c0 % 32 != 0 or c1 % 32 != 0 or c0 < 32 or (cv > 256 and cv % 256 != 0)
+
+
+def _pad_attention_args(x, wq, bq, v0, v1, mask):
+    """Shapes the kernels do not take directly — H*W not a multiple of the 128-row tile (CelebA 218x178 inputs give 6x5 and
+    24x20 feature maps), value channels not a multiple of 32 — are embedded in the next shape they do take; the reference
+    accepts any size (example_guided_att.py:21-41, base_function.py:420-448). Pixels: zero-padded to S' = ceil(S / 128) * 128.
+    A padded KEY must get softmax weight 0: two marker channels are appended to x — t1 = 1 on real pixels / 0 on padding
+    (carries the query bias: column t1 of the augmented query weight is bq), t2 = +1 / -1 (row d of the augmented weight is
+    beta * t2) — so q' = [Wq x + bq ; beta] on real pixels and [0 ; -beta] on padding: real-real logits gain the constant
+    beta^2 (softmax-invariant), real-padding logits are -beta^2, i.e. at least e^(-2 beta^2) = e^-32 below the diagonal.
+    Padded QUERY rows and padded value channels produce rows / channels that are sliced off. Returns the padded arguments
+    and (S, S', c0', c1')."""
+    n, c = x.shape[0], x.shape[1]
+    s = x[0, 0].numel()
+    sp = (s + 127) // 128 * 128
+    d = wq.shape[0]
+    c0 = v0.shape[1]
+    c1 = v1.shape[1] if v1 is not None else 0
+    up32 = lambda k: max(32, (k + 31) // 32 * 32)
+    c0p, c1p = up32(c0), (up32(c1) if c1 else 0)
+    if c0p + c1p > 256 and (c0p + c1p) % 256:
+        extra = 256 - (c0p + c1p) % 256
+        if c1:
+            c1p += extra
+        else:
+            c0p += extra
+    dev, dt = x.device, x.dtype
+    xa = torch.zeros((n, c + 2, sp, 1), dtype=dt, device=dev)
+    xa[:, :c, :s, 0] = x.reshape(n, c, s)
+    xa[:, c, :s] = 1.0
+    xa[:, c + 1] = -1.0
+    xa[:, c + 1, :s] = 1.0
+    wa = torch.zeros((d + 1, c + 2), dtype=torch.float32, device=dev)
+    wa[:d, :c] = wq.reshape(d, c).float()
+    if bq is not None:
+        wa[:d, c] = bq.float()
+    wa[d, c + 1] = _PAD_BETA
+
+    def padv(v, cp):
+        if v is None:
+            return None
+        out = torch.zeros((n, cp, sp, 1), dtype=dt, device=dev)
+        out[:, :v.shape[1], :s, 0] = v.reshape(n, v.shape[1], s).to(dt)
+        return out
+
+    ma = None
+    if mask is not None:
+        ma = torch.zeros((n, 1, sp, 1), dtype=torch.float32, device=dev)
+        ma[:, 0, :s, 0] = mask.reshape(n, s).float()
+    return xa, wa, padv(v0, c0p), padv(v1, c1p), ma, (s, sp, c0, c1, c0p, c1p)
+
+
 def attention_forward(x, wq, bq, v0, v1=None, mask=None, a0=None, b0=0.0, masked0=False, a1=None, b1=0.0,
                       masked1=False, order=(0, 1), need_lse=False, mma=None, save_o=False):
     """One fused pass of fmi_attn_fwd. x [N,C,H,W]; v0/v1 value groups [N,C0|C1,H,W]; mask [N,1,H,W] or None.
@@ -324,6 +382,14 @@ def attention_forward(x, wq, bq, v0, v1=None, mask=None, a0=None, b0=0.0, masked
     _need_cuda(x, wq, bq, v0, v1, mask, a0, a1)
     if x.dtype not in (torch.float32, torch.bfloat16):
         raise RuntimeError("fmi_b200 attention: fp32 or bf16 activations only")
+    if _needs_padding(x[0, 0].numel(), v0.shape[1], v1.shape[1] if v1 is not None else 0):
+        xa, wa, v0a, v1a, ma, (s, sp, c0, c1, c0p, c1p) = _pad_attention_args(x, wq, bq, v0, v1, mask)
+        res = attention_forward(xa, wa, None, v0a, v1a, mask=ma, a0=a0, b0=b0, masked0=masked0, a1=a1, b1=b1, masked1=masked1,
+                                order=(0, 1), need_lse=need_lse, mma=mma if mma is not None else mma_mode(x.dtype), save_o=save_o)
+        g0, g1 = res[0][:, :c0, :s, 0], res[0][:, c0p:c0p + c1, :s, 0]
+        out = torch.cat([g0, g1] if order[0] == 0 else [g1, g0], dim=1).reshape((x.shape[0], c0 + c1) + tuple(x.shape[2:]))
+        # lse / o_saved stay in the padded layout: they are only handed back to attention_backward / attention_map
+        return (out.contiguous(),) + tuple(res[1:])
     xc = x.contiguous()
     v0c = xc if v0 is x else v0.contiguous().to(xc.dtype)
     v1c = v1.contiguous().to(xc.dtype) if v1 is not None else None
@@ -364,6 +430,9 @@ def attention_forward(x, wq, bq, v0, v1=None, mask=None, a0=None, b0=0.0, masked
 
 def attention_map(ws, lse, n, d, s, mma):
     """Opt-in S x S map (what Auto_Attn returns, base_function.py:448) from the staged q and the row lse."""
+    if lse.shape[1] != s:      # padded call (_pad_attention_args): one marker channel more, S' rows; padded keys have weight 0
+        sp = lse.shape[1]
+        return attention_map(ws, lse, n, d + 1, sp, mma)[:, :s, :s].contiguous()
     attn = torch.empty((n, s, s), dtype=torch.float32, device=lse.device)
     _lib.check(_lib.load().fmi_attn_materialize(ws.data_ptr(), _ptr(lse), _ptr(attn), n, d, s, mma, _stream()),
                "fmi_attn_materialize")
@@ -375,6 +444,25 @@ def attention_backward(x, wq, bq, v0, v1, mask, a0, b0, masked0, a1, b1, masked1
     """fmi_attn_bwd for the forward call with the same arguments; grad_out is [N, C0+C1, H, W] (groups concatenated in
     `order`). Returns (dq [N,d,H,W] fp32, dv0, dv1 (fp32 or None), da0, da1 (fp32 scalars))."""
     _need_cuda(x, wq, v0, grad_out)
+    if _needs_padding(x[0, 0].numel(), v0.shape[1], v1.shape[1] if v1 is not None else 0):
+        xa, wa, v0a, v1a, ma, (s, sp, c0, c1, c0p, c1p) = _pad_attention_args(x, wq, bq, v0, v1, mask)
+        n, d = x.shape[0], wq.shape[0]
+        spatial = tuple(x.shape[2:])
+        g = grad_out.reshape(n, c0 + c1, s)
+        g0, g1 = (g[:, :c0], g[:, c0:]) if order[0] == 0 else (g[:, c1:], g[:, :c1])
+        ga = torch.zeros((n, c0p + c1p, sp, 1), dtype=x.dtype, device=x.device)
+        ga[:, :c0, :s, 0] = g0
+        if c1:
+            ga[:, c0p:c0p + c1, :s, 0] = g1
+        dq, dv0, dv1, da0, da1 = attention_backward(xa, wa, None, v0a, v1a, ma, a0, b0, masked0, a1, b1, masked1, o_saved, lse, ga,
+                                                    order=(0, 1), need_dv0=need_dv0, need_dv1=need_dv1,
+                                                    mma=mma if mma is not None else mma_mode(x.dtype))
+        # dq of the marker row and of padded pixels is dropped: the query conv's own backward (qconv_backward) sees the
+        # real q gradient, from which dWq, dbq and dx follow as in the unpadded case
+        dq = dq[:, :d, :s, 0].reshape((n, d) + spatial).contiguous()
+        dv0 = dv0[:, :c0, :s, 0].reshape((n, c0) + spatial).contiguous() if dv0 is not None else None
+        dv1 = dv1[:, :c1, :s, 0].reshape((n, c1) + spatial).contiguous() if dv1 is not None else None
+        return dq, dv0, dv1, da0, da1
     xc = x.contiguous()
     v0c = xc if v0 is x else v0.contiguous().to(xc.dtype)
     v1c = v1.contiguous().to(xc.dtype) if v1 is not None else None

@@ -212,3 +212,71 @@ def test_example_guided_attention_pair_kernel(case, dtype, monkeypatch):
     tol = 1e-3 if dtype == torch.float32 else 2e-2
     assert rel_err(got, want) <= tol
     assert rel_err(got, base) <= tol / 2  # two TF32 evaluation orders of the same sums
+
+
+# the reference takes any spatial size and channel count (CelebA 218x178 inputs give 6x5 encoder features
+# and 24x20 at Auto_Attn); shapes the tiles do not take directly are padded in ops._pad_attention_args (algebra checked on CPU in
+# test_attention_padding_cpu.py). Forward and backward against the oracle, same tolerances as the aligned shapes.
+PADDED_CASES = [(2, 128, 6, 5), (1, 128, 24, 20), (2, 40, 9, 9), (1, 256, 12, 11)]
+
+
+@pytest.mark.parametrize("case", PADDED_CASES)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_padded_shapes_forward_and_backward(case, dtype):
+    from face_mask_inpaint_b200.modules import Auto_Attn, ExampleGuidedAttention
+    n, c, h, w = case
+    g = torch.Generator().manual_seed(21)
+    tol = 1e-3 if dtype == torch.float32 else 2e-2
+    src = torch.randn(n, c, h, w, generator=g).to(dtype).float()
+    ref = torch.randn(n, c, h, w, generator=g).to(dtype).float()
+    mask = torch.rand(n, 1, h, w, generator=g)
+    # ExampleGuidedAttention
+    ega = ExampleGuidedAttention(c)
+    with torch.no_grad():
+        ega.conv.weight.copy_(_scaled_query_weight(c, c // 4, src, 1.0, g))
+    go = torch.randn(n, 2 * c, h, w, generator=g).to(dtype).float()
+    ps = [src.clone().requires_grad_(True), ref.clone().requires_grad_(True), ega.conv.weight.detach().clone().requires_grad_(True)]
+    want = O.example_guided_attention(mask, ps[0], ps[1], ps[2])
+    want.backward(go)
+    ega = ega.to(DEV)
+    sd, rd = src.to(dtype).to(DEV).requires_grad_(True), ref.to(dtype).to(DEV).requires_grad_(True)
+    got = ega(mask.to(DEV), sd, rd)
+    got.backward(go.to(dtype).to(DEV))
+    assert got.shape == want.shape and rel_err(got, want.detach()) <= tol
+    assert rel_err(sd.grad, ps[0].grad) <= tol and rel_err(rd.grad, ps[1].grad) <= tol
+    assert rel_err(ega.conv.weight.grad, ps[2].grad) <= 30 * tol
+    # Auto_Attn (query bias, gamma)
+    aa = Auto_Attn(c, None)
+    with torch.no_grad():
+        aa.query_conv.weight.copy_(_scaled_query_weight(c, c // 4, src, 1.0, g))
+        aa.query_conv.bias.copy_(0.3 * torch.randn(c // 4, generator=g))
+        aa.gamma.fill_(0.7)
+    go = torch.randn(n, c, h, w, generator=g).to(dtype).float()
+    xs = src.clone().requires_grad_(True)
+    pw, pb, pg = (t.detach().clone().requires_grad_(True) for t in (aa.query_conv.weight, aa.query_conv.bias, aa.gamma))
+    want = O.auto_attn(xs, pw, pb, pg)[0]
+    want.backward(go)
+    aa = aa.to(DEV)
+    xd = src.to(dtype).to(DEV).requires_grad_(True)
+    got = aa(xd)[0]
+    got.backward(go.to(dtype).to(DEV))
+    assert rel_err(got, want.detach()) <= tol and rel_err(xd.grad, xs.grad) <= tol
+    assert rel_err(aa.query_conv.weight.grad, pw.grad) <= 30 * tol and rel_err(aa.query_conv.bias.grad, pb.grad) <= 30 * tol
+    assert rel_err(aa.gamma.grad, pg.grad) <= tol
+
+
+def test_padded_shape_attention_map(monkeypatch):
+    """FMI_MATERIALIZE_ATTN=1 returns the S x S map of the ORIGINAL problem (rows sum to one, padded keys carry no weight)."""
+    from face_mask_inpaint_b200.modules import Auto_Attn
+    monkeypatch.setenv("FMI_MATERIALIZE_ATTN", "1")
+    g = torch.Generator().manual_seed(22)
+    x = torch.randn(1, 64, 7, 9, generator=g)
+    aa = Auto_Attn(64, None)
+    with torch.no_grad():
+        aa.query_conv.weight.mul_(3.0)
+        aa.gamma.fill_(1.0)
+    want = O.auto_attn(x, aa.query_conv.weight.detach(), aa.query_conv.bias.detach(), aa.gamma.detach())[1]
+    with torch.no_grad():
+        got = aa.to(DEV)(x.to(DEV))[1]
+    assert got.shape == (1, 63, 63) and rel_err(got, want) <= 1e-3
+    assert float((got.sum(-1) - 1).abs().max()) <= 1e-3
