@@ -473,13 +473,13 @@ int styled_conv_impl(const void* x, const void* wp, void* y, const float* noise,
                      int mma, void* workspace, int64_t workspace_bytes, void* stream, const RgbFuse* rgb) {
   FMI_REQUIRE(mma == FMI_MMA_TF32 || mma == FMI_MMA_BF16, "styled_conv: bad mma");
   if (B == 0) return FMI_OK;
-  FMI_REQUIRE(x && wp && y, "styled_conv: null pointer");
+  FMI_REQUIRE(x && wp && (y || (rgb && !upsample)), "styled_conv: null pointer");   // y may be NULL when only the fused ToRGB is wanted
   FMI_REQUIRE(I >= 16 && O >= 32 && O % 32 == 0 && H >= 1 && W >= 1,
               "styled_conv: unsupported shape I=%d O=%d H=%d W=%d (O must be a multiple of 32)", I, O, H, W);
   const int esz = esz_of(mma);
   FMI_REQUIRE((I * esz) % 16 == 0 && (O * esz) % 16 == 0, "styled_conv: channel counts must give 16-byte rows");
   FMI_REQUIRE(O <= 256 || O % 256 == 0, "styled_conv: O=%d must be <= 256 or a multiple of 256", O);
-  FMI_REQUIRE(fmi_aligned(x, 16) && fmi_aligned(wp, 16) && fmi_aligned(y, 16), "styled_conv: buffers must be 16-byte aligned");
+  FMI_REQUIRE(fmi_aligned(x, 16) && fmi_aligned(wp, 16) && (!y || fmi_aligned(y, 16)), "styled_conv: buffers must be 16-byte aligned");
   int rc = fmi_device_check();
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;

@@ -319,6 +319,7 @@ __global__ void __launch_bounds__(kGemmThreads, 3)
             rgb2 = fmaf(a, w.z, rgb2);
           }
         }
+        if (!p.out) continue;   // fused ToRGB only (the last StyledConv of an inference forward: nothing else reads y)
         const int ncols = min(32, p.n_tile - c0);
         if (p.add_out) {
           if constexpr (TF32) {
@@ -430,7 +431,17 @@ int launch_gemm_class(const CUtensorMap& mx, const CUtensorMap& mw, ConvGemmPara
   // 2; the TMA ring is sized to the CTA's share of shared memory.
   p.tmem_cols = p.n_tile <= 16 ? 32 : p.n_tile <= 32 ? 64 : p.n_tile <= 64 ? 128 : p.n_tile <= 128 ? 256 : 512;
   // (a halo stage is 17 KB + three weight tiles and carries three taps: fewer, fatter CTAs)
-  const int ctas_per_sm = p.halo ? (p.n_tile <= 32 ? 2 : 1) : (p.n_tile <= 64 ? 3 : p.n_tile <= 128 ? 2 : 1);
+  int ctas_per_sm = p.halo ? (p.n_tile <= 32 ? 2 : 1) : (p.n_tile <= 64 ? 3 : p.n_tile <= 128 ? 2 : 1);
+  {
+    // a grid that does not fill the co-resident slots gets fewer CTAs per SM and a deeper TMA ring instead: a launch of <= 148
+    // tiles is a chain of k-iterations per CTA, and with 3 stages of 32 KB in flight it runs at TMA latency, not bandwidth
+    // (ncu, PICNet encoder convs at 32^2: 32 CTAs, 25-48 us for 5 us of MMA issue)
+    const int tb = p.TB > 1 ? p.TB : 1;
+    const TilePlan t0 = p.halo ? TilePlan{1, 128, p.Mh, (p.Mw + 127) / 128} : (tb > 1 ? TilePlan{p.Mh, p.Mw, 1, 1} : pick_tile(p.Mh, p.Mw));
+    const int64_t tiles = (int64_t)t0.tiles_h * t0.tiles_w * (p.O / p.n_tile) * ((p.B + tb - 1) / tb);
+    static const bool deep_off = [] { const char* e = getenv("FMI_GEMM_DEEP_RING"); return e && e[0] == '0'; }();
+    while (!deep_off && ctas_per_sm > 1 && tiles <= (int64_t)FMI_NUM_SMS * (ctas_per_sm - 1)) --ctas_per_sm;
+  }
   int stages = ((232448 - 6144) / ctas_per_sm - 2048) / stage_bytes;
   if (stages > 8) stages = 8;
   FMI_REQUIRE(stages >= 2, "modconv_gemm: stage of %d bytes does not fit twice", stage_bytes);
@@ -467,9 +478,9 @@ int launch_gemm_class(const CUtensorMap& mx, const CUtensorMap& mw, ConvGemmPara
   const double taps = p.halo ? 9.0 : (double)p.ntaps;
   const double wflops = 2.0 * pix * taps * p.I * (p.merge_o ? n_real * 4.0 / taps : n_real);
   const double out_elems = pix * (p.merge_o ? 4.0 * p.merge_o : (double)p.O);
-  const double wbytes = ((double)p.B * p.H * p.W * p.I + out_elems * (p.add_out ? 2.0 : 1.0) +
+  const double wbytes = ((double)p.B * p.H * p.W * p.I + (p.out ? out_elems * (p.add_out ? 2.0 : 1.0) : 0.0) +
                          (double)p.T * p.O * p.I * (p.w_shared ? 1.0 : (double)(p.B / (p.w_group > 1 ? p.w_group : 1)))) * esz +
-                        (p.nchw_out ? pix * p.nchw_C * 4.0 : 0.0);
+                        (p.nchw_out ? pix * p.nchw_C * 4.0 : 0.0) + (p.rgb_out ? pix * 3 * 4.0 * (p.rgb_skip ? 1.25 : 1.0) : 0.0);
   FmiProfScope prof(p.prof_kind ? p.prof_kind : FMI_PROF_GEMM, st, wflops, wbytes);
   kern<<<grid, kGemmThreads, smem, st>>>(mx, mw, p);
   return fmi_launched("modconv_gemm");

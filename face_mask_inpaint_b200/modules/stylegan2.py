@@ -246,12 +246,13 @@ def styled_conv_nhwc(x, wp, o, upsample, act, mma, noise=None, noise_w=None, act
     return y
 
 
-def styled_conv_torgb_nhwc(x, wp, o, mma, noise, noise_w, act_bias, rgb_weight, rgb_s, rgb_bias, skip, up_kernel):
+def styled_conv_torgb_nhwc(x, wp, o, mma, noise, noise_w, act_bias, rgb_weight, rgb_s, rgb_bias, skip, up_kernel, want_y=True):
     """Plain StyledConv + the ToRGB that follows it, one kernel (fmi_styled_conv_torgb_nhwc; O <= 256).
-    Returns (activations NHWC, rgb [B,3,H,W] fp32)."""
+    Returns (activations NHWC, rgb [B,3,H,W] fp32); with want_y=False the activations are not stored (None): the last layer
+    of an inference forward has no other reader (at 1024^2, batch 8 that is a 512 MiB write)."""
     b, h, w, i = x.shape
     lib = _lib.load()
-    y = torch.empty((b, h, w, o), dtype=x.dtype, device=x.device)
+    y = torch.empty((b, h, w, o), dtype=x.dtype, device=x.device) if want_y else None
     rgb = torch.empty((b, 3, h, w), dtype=torch.float32, device=x.device)
     rgb_w = torch.empty((b, 3, o), dtype=torch.float32, device=x.device)
     _lib.check(lib.fmi_torgb_weights(_p(rgb_weight), _p(rgb_s), _p(rgb_w), b, o, ops._stream()), "fmi_torgb_weights")
@@ -644,10 +645,11 @@ class Generator(nn.Module):
                 wp = pre(i + 1)
                 if wp is None:
                     wp = prep_weights(conv2.conv.weight, conv2.conv.styles(lat[:, i + 1]), conv2.conv.demodulate, mma)
+                last = to_rgb is self.to_rgbs[-1] and not return_features
                 out, skip = styled_conv_torgb_nhwc(
                     out, wp, conv2.conv.out_channel, mma, conv2._noise(noise2, b, h, w, out.device), conv2.noise.weight,
                     conv2.activate.bias, to_rgb.conv.weight, to_rgb.conv.styles(lat[:, i + 2]), to_rgb.bias, skip,
-                    to_rgb.upsample.kernel)
+                    to_rgb.upsample.kernel, want_y=not last)
             else:
                 out = conv2.forward_nhwc(out, lat[:, i + 1], mma, noise=noise2, wp=pre(i + 1))
                 skip = to_rgb.forward_nhwc(out, lat[:, i + 2], mma, skip)

@@ -210,7 +210,8 @@ int fmi_styled_conv_nhwc(const void* x, const void* wp, void* y, const float* no
 /* A plain StyledConv with the following ToRGB fused into its epilogue (StyledConv.forward :340-346 followed by
  *   ToRGB.forward :360-369 on its output, Generator.forward :537-539) for O <= 256: the 1x1 modulated conv to 3
  *   channels is accumulated from the activations the epilogue already holds, so the layer output is not re-read.
- *   rgb_w [B,3,O] = W[o,c]*s[b,c]/sqrt(O) from fmi_torgb_weights; rgb_skip [B,3,H/2,W/2] or NULL; rgb [B,3,H,W] fp32. */
+ *   rgb_w [B,3,O] = W[o,c]*s[b,c]/sqrt(O) from fmi_torgb_weights; rgb_skip [B,3,H/2,W/2] or NULL; rgb [B,3,H,W] fp32.
+ *   y may be NULL: only the RGB image is produced (the last layer of an inference forward — nothing else reads its activations). */
 int fmi_torgb_weights(const float* weight, const float* s, float* rgb_w, int B, int C, void* stream);
 int fmi_styled_conv_torgb_nhwc(const void* x, const void* wp, void* y, const float* noise, int noise_batched,
                                const float* noise_w, const float* act_bias, const float* rgb_w,
