@@ -10,7 +10,9 @@ namespace fmi_conv {
 using namespace sm100;
 
 
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;   // TMA warp, MMA warp, two epilogue warpgroups (one per TMEM accumulator)
+constexpr int kGemmStaticSmem = 10240;  // static shared memory of the kernel (barriers, 2 x 4 KB fused-ToRGB weights), rounded up
+__device__ __align__(16) const float kZeroBias[32] = {};   // stands in for an absent bias vector in the epilogue
 constexpr int kMaxTaps = 9;
 constexpr int A_STAGE_BYTES = 128 * 128;
 constexpr int A_HALO_BYTES = 17 * 1024;   // 130 pixel rows of 128 bytes, padded to the 1024-byte swizzle period
@@ -74,7 +76,7 @@ struct ConvGemmParams {
 // TMEM, so the epilogue of tile i overlaps the MMAs of tile i+1. (One tile per CTA left the tensor pipe 5 % active on the
 // 32 -> 32 @1024^2 layer — ncu: 27 % warps active, the CTA lifetime was prologue + TMA latency + epilogue.)
 template <bool TF32>
-__global__ void __launch_bounds__(kGemmThreads, 3)
+__global__ void __launch_bounds__(kGemmThreads, 2)
     modconv_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                         const ConvGemmParams p) {
   constexpr int EPA = TF32 ? 32 : 64;
@@ -86,7 +88,7 @@ __global__ void __launch_bounds__(kGemmThreads, 3)
   const int stage_bytes = a_bytes + (p.halo ? 3 : 1) * b_stage_bytes;
   __shared__ uint64_t full[8], empty[8], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
-  __shared__ float4 s_rgbw[256];  // fused ToRGB weights of the current image: (w_r, w_g, w_b, -) per output channel
+  __shared__ float4 s_rgbw[2][256];  // fused ToRGB weights of the current image, per epilogue group: (w_r, w_g, w_b, -) per channel
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int iters = (p.halo ? 3 : p.ntaps) * p.k_chunks;
@@ -221,12 +223,18 @@ __global__ void __launch_bounds__(kGemmThreads, 3)
     }
     __syncwarp();
   } else {
+    // Two epilogue warpgroups: warps 2-5 drain accumulator 0 (even tiles of this CTA), warps 6-9 accumulator 1 (odd tiles), so
+    // two tiles' epilogues run concurrently. (ncu: with one group the epilogue — TMEM load, bias / noise loads, activation,
+    // conversion, stores: ~800 instructions and several load latencies per tile — set the tile rate of every narrow layer.)
+    const int grp = (warp - 2) >> 2;
+    const int gtid = tid - 64 - grp * 128;
     const int lane_base = (warp & 3) * 32;
     const int r = lane_base + (tid & 31);  // tile row == TMEM lane
     const uint32_t lane_addr = (uint32_t)lane_base << 16;
     int cur_b = -1, cur_o0 = -1, i = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++i) {
       const int as = i & 1;
+      if (as != grp) continue;
       int b, o0, m0, n0;
       decode(t, b, o0, m0, n0);
       const int ppi = p.TH * p.TW;                 // rows of one image in the tile
@@ -248,12 +256,12 @@ __global__ void __launch_bounds__(kGemmThreads, 3)
       // fused ToRGB (model.py:360-369): the 1x1 modulated conv to 3 channels reads exactly the activations this thread
       // holds, so it is 3 dot products in the epilogue instead of a kernel that re-reads the whole layer output from HBM
       if (p.rgb_out && (b != cur_b || o0 != cur_o0)) {   // (never with TB > 1: b is the tile's image here)
-        asm volatile("bar.sync 2, 128;" ::: "memory");  // readers of the previous image's weights are done
-        for (int e = tid - 64; e < p.n_tile; e += 128) {
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");  // readers of the previous image's weights are done
+        for (int e = gtid; e < p.n_tile; e += 128) {
           const float* w = p.rgb_w + ((int64_t)b * 3) * p.O + o0 + e;
-          s_rgbw[e] = make_float4(w[0], w[p.O], w[2 * p.O], 0.f);
+          s_rgbw[grp][e] = make_float4(w[0], w[p.O], w[2 * p.O], 0.f);
         }
-        asm volatile("bar.sync 2, 128;" ::: "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");
         cur_b = b;
         cur_o0 = o0;
       }
@@ -288,45 +296,43 @@ __global__ void __launch_bounds__(kGemmThreads, 3)
         // per chunk: ncu (source page, 32 -> 32 @512^2 bf16) showed 820 instructions and ~8.6 k cycles per tile in the epilogue
         // warps for ~1.5 k cycles of MMA — the epilogue, not the mainloop, bounded every implicit GEMM.
         if (p.act != 0) {
-          float bv[32];
-          if (biasp && fmi_aligned_dev(biasp + bofs, 16)) {
-            const float4* b4 = reinterpret_cast<const float4*>(biasp + bofs);
+          // no bias: the same loads from a zero vector, so that the loop body has no branch (bias vectors are 16-byte aligned:
+          // cudaMalloc'd parameter tensors at offsets that are multiples of 32 floats)
+          const float4* b4 = reinterpret_cast<const float4*>(biasp ? biasp + bofs : kZeroBias);
+          if (p.act == 1) {
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
               const float4 t4 = __ldg(b4 + q);
-              bv[4 * q] = t4.x; bv[4 * q + 1] = t4.y; bv[4 * q + 2] = t4.z; bv[4 * q + 3] = t4.w;
-            }
-          } else if (biasp) {
-#pragma unroll
-            for (int k = 0; k < 32; ++k) bv[k] = __ldg(biasp + bofs + k);
-          } else {
-#pragma unroll
-            for (int k = 0; k < 32; ++k) bv[k] = 0.f;
-          }
-          if (p.act == 1) {
-#pragma unroll
-            for (int k = 0; k < 32; ++k) {
-              const float tt = f[k] + nzc + bv[k];
-              f[k] = (tt > 0.f ? tt : tt * p.slope) * p.gain;
-            }
-          } else if (p.act == 4) {
-            const float4* s4 = reinterpret_cast<const float4*>(p.slope_c + bofs);   // cudaMalloc'd parameter vector: 16-byte aligned
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 sl = __ldg(s4 + q);
-              const float sv[4] = {sl.x, sl.y, sl.z, sl.w};
+              const float bq[4] = {t4.x, t4.y, t4.z, t4.w};
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const float tt = f[4 * q + j] + bv[4 * q + j];
+                const float tt = f[4 * q + j] + nzc + bq[j];
+                f[4 * q + j] = (tt > 0.f ? tt : tt * p.slope) * p.gain;
+              }
+            }
+          } else if (p.act == 4) {
+            const float4* s4 = reinterpret_cast<const float4*>(p.slope_c + bofs);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 t4 = __ldg(b4 + q), sl = __ldg(s4 + q);
+              const float bq[4] = {t4.x, t4.y, t4.z, t4.w}, sv[4] = {sl.x, sl.y, sl.z, sl.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float tt = f[4 * q + j] + bq[j];
                 f[4 * q + j] = tt > 0.f ? tt : tt * sv[j];
               }
             }
-          } else if (p.act == 3) {
-#pragma unroll
-            for (int k = 0; k < 32; ++k) f[k] = tanhf(f[k] + bv[k]);
           } else {
 #pragma unroll
-            for (int k = 0; k < 32; ++k) f[k] += bv[k];
+            for (int q = 0; q < 8; ++q) {
+              const float4 t4 = __ldg(b4 + q);
+              const float bq[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float tt = f[4 * q + j] + bq[j];
+                f[4 * q + j] = p.act == 3 ? tanhf(tt) : tt;
+              }
+            }
           }
         }
         if (p.nchw_out) {
@@ -339,7 +345,7 @@ __global__ void __launch_bounds__(kGemmThreads, 3)
         if (p.rgb_out) {
 #pragma unroll
           for (int k = 0; k < 32; ++k) {
-            const float4 w = s_rgbw[c0 + k];
+            const float4 w = s_rgbw[grp][c0 + k];
             const float a = TF32 ? __uint_as_float(f32_to_tf32_rna(f[k])) : __bfloat162float(__float2bfloat16_rn(f[k]));
             rgb0 = fmaf(a, w.x, rgb0);
             rgb1 = fmaf(a, w.y, rgb1);
@@ -450,7 +456,7 @@ int launch_gemm_class(const CUtensorMap& mx, const CUtensorMap& mw, ConvGemmPara
   auto kern = modconv_gemm_kernel<TF32>;
   static bool attr_set = false;  // per translation unit and template instance
   if (!attr_set) {
-    FMI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 6144));  // static: 5 KB
+    FMI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - kGemmStaticSmem));  // static: 5 KB
     attr_set = true;
   }
   const int stage_bytes = p.halo ? A_HALO_BYTES + 3 * p.n_tile * 128 : A_STAGE_BYTES + p.n_tile * 128;
@@ -458,7 +464,7 @@ int launch_gemm_class(const CUtensorMap& mx, const CUtensorMap& mw, ConvGemmPara
   // 2; the TMA ring is sized to the CTA's share of shared memory.
   p.tmem_cols = p.n_tile <= 16 ? 32 : p.n_tile <= 32 ? 64 : p.n_tile <= 64 ? 128 : p.n_tile <= 128 ? 256 : 512;
   // (a halo stage is 17 KB + three weight tiles and carries three taps: fewer, fatter CTAs)
-  int ctas_per_sm = p.halo ? (p.n_tile <= 32 ? 2 : 1) : (p.n_tile <= 64 ? 3 : p.n_tile <= 128 ? 2 : 1);
+  int ctas_per_sm = p.halo ? (p.n_tile <= 32 ? 2 : 1) : (p.n_tile <= 128 ? 2 : 1);   // 320 threads x <= 102 registers: 2 per SM
   {
     // a grid that does not fill the co-resident slots gets fewer CTAs per SM and a deeper TMA ring instead: a launch of <= 148
     // tiles is a chain of k-iterations per CTA, and with 3 stages of 32 KB in flight it runs at TMA latency, not bandwidth
@@ -469,7 +475,7 @@ int launch_gemm_class(const CUtensorMap& mx, const CUtensorMap& mw, ConvGemmPara
     static const bool deep_off = [] { const char* e = getenv("FMI_GEMM_DEEP_RING"); return e && e[0] == '0'; }();
     while (!deep_off && ctas_per_sm > 1 && tiles <= (int64_t)FMI_NUM_SMS * (ctas_per_sm - 1)) --ctas_per_sm;
   }
-  int stages = ((232448 - 6144) / ctas_per_sm - 2048) / stage_bytes;
+  int stages = ((232448 - kGemmStaticSmem) / ctas_per_sm - 2048) / stage_bytes;
   if (stages > 8) stages = 8;
   FMI_REQUIRE(stages >= 2, "modconv_gemm: stage of %d bytes does not fit twice", stage_bytes);
   p.stages = stages;
