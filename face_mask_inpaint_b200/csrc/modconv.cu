@@ -519,11 +519,12 @@ int styled_conv_impl(const void* x, const void* wp, void* y, const float* noise,
       p.rgb_w = rgb->w; p.rgb_bias = rgb->bias; p.rgb_skip = rgb->skip; p.rgb_kf = rgb->kf; p.rgb_out = rgb->out;
     }
     TilePlan tp = pick_tile(p.Mh, p.Mw);
-    // halo mode (FMI_MODCONV_HALO=1): wide, narrow-channel layers re-read every activation once per tap from L2 (ncu: 10 GB
-    // of L2 reads for 0.6 GB of DRAM reads on 32 -> 32 @1024^2); loading each kernel row once cuts that 3x, is parity-green,
-    // but measured SLOWER (5.59 vs 5.37 ms per forward): L2 re-reads are not what bounds these layers
-    const bool halo_env = [] { const char* e = getenv("FMI_MODCONV_HALO"); return e && e[0] == '1'; }();  // opt-in (read per call): measured 4-7 % slower
-    p.halo = halo_env && W >= 128 && p.n_tile <= 128;
+    // halo mode: wide, narrow-channel layers re-read every activation once per tap from L2 (ncu: 10 GB of L2 reads for 0.6 GB
+    // of DRAM reads on 32 -> 32 @1024^2); one 130-pixel box per kernel row cuts that 3x. On by default for N <= 32 (round 2,
+    // after the epilogue stopped bounding the kernel: 32 -> 32 @1024^2 + ToRGB 866 -> 656 us; N = 64 layers get slower with it:
+    // 316 -> 417 us, one CTA per SM). FMI_MODCONV_HALO=1 forces it for every N <= 128, =0 switches it off.
+    const int halo_env = [] { const char* e = getenv("FMI_MODCONV_HALO"); return e ? (e[0] == '1' ? 1 : (e[0] == '0' ? 0 : -1)) : -1; }();
+    p.halo = W >= 128 && p.n_tile <= 128 && (halo_env == 1 || (halo_env == -1 && p.n_tile <= 32));
     if (p.halo) {
       for (int a = 0; a < 3; ++a)
         for (int c = 0; c < 3; ++c) p.halo_slab[a][c] = a * 3 + c;

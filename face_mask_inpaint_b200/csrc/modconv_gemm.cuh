@@ -402,20 +402,28 @@ __global__ void __launch_bounds__(kGemmThreads, 2)
         float r3[3] = {rgb0 + p.rgb_bias[0], rgb1 + p.rgb_bias[1], rgb2 + p.rgb_bias[2]};
         const int HW = p.OH * p.OW;
         if (p.rgb_skip) {
-          // Upsample of the previous RGB: zero-insert x2, pad (2,1), flipped 4x4 taps (model.py:30-49)
+          // Upsample of the previous RGB: zero-insert x2, pad (2,1), flipped 4x4 taps (model.py:30-49). Tap ky reaches a real
+          // sample iff oy + ky is even: ky in {py, py + 2} with py = oy & 1, source rows sy0 = (oy + py) / 2 - 1 and sy0 + 1 (same
+          // in x): exactly 2 x 2 source pixels. Out-of-range ones are clamped and weighted 0, so the 4 tap loads and 12 pixel
+          // loads are unconditional and issue together (same summation order as the tap loops).
           const int h2 = p.OH / 2, w2 = p.OW / 2;
+          const int py = oy & 1, px = ox & 1;
+          const int sy0 = ((oy + py) >> 1) - 1, sx0 = ((ox + px) >> 1) - 1;
+          const float* sk = p.rgb_skip + (int64_t)b * 3 * h2 * w2;
 #pragma unroll
-          for (int ky = 0; ky < 4; ++ky) {
-            const int uy = oy + ky - 2;
-            if (uy < 0 || (uy & 1) || (uy >> 1) >= h2) continue;
+          for (int a = 0; a < 2; ++a) {
+            const int sy = sy0 + a, ky = py + 2 * a;
+            const bool yok = sy >= 0 && sy < h2;
+            const int syc = min(max(sy, 0), h2 - 1);
 #pragma unroll
-            for (int kx = 0; kx < 4; ++kx) {
-              const int ux = ox + kx - 2;
-              if (ux < 0 || (ux & 1) || (ux >> 1) >= w2) continue;
-              const float kv = __ldg(p.rgb_kf + 15 - (ky * 4 + kx));
-              const int64_t si = ((int64_t)b * 3 * h2 + (uy >> 1)) * w2 + (ux >> 1);
+            for (int c = 0; c < 2; ++c) {
+              const int sx = sx0 + c, kx = px + 2 * c;
+              const bool ok = yok && sx >= 0 && sx < w2;
+              const int sxc = min(max(sx, 0), w2 - 1);
+              const float kv = ok ? __ldg(p.rgb_kf + 15 - (ky * 4 + kx)) : 0.f;
+              const int64_t si = (int64_t)syc * w2 + sxc;
 #pragma unroll
-              for (int o = 0; o < 3; ++o) r3[o] = fmaf(kv, p.rgb_skip[si + (int64_t)o * h2 * w2], r3[o]);
+              for (int o = 0; o < 3; ++o) r3[o] = fmaf(kv, __ldg(sk + si + (int64_t)o * h2 * w2), r3[o]);
             }
           }
         }
