@@ -351,6 +351,10 @@ extern "C" int fmi_conv3x3_nhwc(const void* x, int64_t x_pixel_stride, const voi
   p.add_out = add_y;
   if (mode == 4) p.T = 1;               // 1x1 convolution: one tap, wp [1][O][I]
   p.n_tile = O <= 256 ? O : 256;
+  if (mode != 3) {   // few pixel tiles: narrower output tiles on more SMs (pick_n_tile)
+    const TilePlan t0 = pick_tile(H, W);
+    p.n_tile = pick_n_tile(O, p.n_tile, (int64_t)B * t0.tiles_h * t0.tiles_w);
+  }
   if (mode == 3) {   // one GEMM for the 4 parity classes: N = 4*O, weights [4 shifts][4*O][I]
     p.merge_o = O;
     p.O = 4 * O;

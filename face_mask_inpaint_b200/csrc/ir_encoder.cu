@@ -252,6 +252,7 @@ extern "C" int fmi_conv_nhwc(const void* x, int64_t x_pixel_stride, int64_t x_ro
   }
   p.TB = tb;
   TilePlan tp = tb > 1 ? TilePlan{H, W, 1, 1} : pick_tile(H, W);
+  p.n_tile = pick_n_tile(O, p.n_tile, (int64_t)((B + tb - 1) / tb) * tp.tiles_h * tp.tiles_w);   // few tiles: narrower, on more SMs
   static const bool halo_off = [] { const char* e = getenv("FMI_CONV_HALO"); return e && e[0] == '0'; }();
   p.halo = ksize == 3 && !planes && tb == 1 && !halo_off && W >= 128 && p.n_tile <= 128 && w_group == 0;
   if (p.halo) {

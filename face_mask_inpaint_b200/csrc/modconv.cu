@@ -491,6 +491,10 @@ int styled_conv_impl(const void* x, const void* wp, void* y, const float* noise,
   ConvGemmParams p{};
   p.B = B; p.I = I; p.O = O; p.H = H; p.W = W; p.T = T;
   p.n_tile = O <= 256 ? O : 256;
+  if (!rgb) {   // (the fused ToRGB needs all O channels of a pixel in one tile) few pixel tiles: narrower tiles on more SMs
+    const TilePlan t0 = pick_tile(H, W);
+    p.n_tile = pick_n_tile(O, p.n_tile, (int64_t)B * t0.tiles_h * t0.tiles_w);
+  }
   p.k_chunks = (I + epa - 1) / epa;
   p.noise = noise; p.noise_batched = noise_batched; p.noise_w = noise_w; p.bias = act_bias;
   p.slope = 0.2f; p.gain = 1.4142135623730951f;

@@ -459,6 +459,24 @@ inline TilePlan pick_tile(int Mh, int Mw) {
   return best;
 }
 
+// Output-channel tile of a launch. The mainloop of a CTA runs at the SM's L2 -> shared-memory ingest (~45 B/clk measured: a
+// 128 x 256 x 2304 tile = 36 stages of 48 KB takes ~26 us whatever the tensor pipe could do), so a launch that leaves SMs idle is
+// faster with NARROWER tiles on more SMs, although every A tile is then fetched by several CTAs: per SM the cost is
+// ceil(CTAs / 148) * (A bytes + n * 128) per K step. Candidates: n0, n0/2, ... >= 32 (divisors of O that are multiples of 32).
+inline int pick_n_tile(int O, int n0, int64_t pixel_tiles) {
+  static const bool off = [] { const char* e = getenv("FMI_GEMM_NTILE_AUTO"); return e && e[0] == '0'; }();
+  if (off) return n0;
+  int best = n0;
+  int64_t best_cost = -1;
+  for (int n = n0; n >= 32; n >>= 1) {
+    if (O % n != 0 || n % 32 != 0) break;
+    const int64_t ctas = pixel_tiles * (O / n);
+    const int64_t cost = ((ctas + FMI_NUM_SMS - 1) / FMI_NUM_SMS) * (A_STAGE_BYTES + (int64_t)n * 128);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = n; }
+  }
+  return best;
+}
+
 template <bool TF32>
 int launch_gemm_class(const CUtensorMap& mx, const CUtensorMap& mw, ConvGemmParams p, cudaStream_t st) {
   auto kern = modconv_gemm_kernel<TF32>;
