@@ -89,14 +89,23 @@ def header_symbols() -> list[str]:
 
 
 def load(build_if_missing: bool = True) -> C.CDLL:
+    """dlopen libfmi_b200.so. A missing library is built with nvcc under an inter-process file lock (torchrun starts N ranks on a
+    fresh checkout at once) and renamed into place atomically (build.py). A library older than its sources is refused loudly
+    when nvcc is here to rebuild it (FMI_ALLOW_STALE=1 loads it anyway); on a box without the sources' toolchain the shipped
+    library is used as it is."""
     global _lib
     if _lib is not None:
         return _lib
+    from . import build as _build
     if not LIB_PATH.exists():
         if not build_if_missing:
             raise RuntimeError(f"{LIB_PATH} is missing; run `python -m face_mask_inpaint_b200.build`")
-        from . import build as _build
         _build.build(verbose=bool(os.environ.get("FMI_VERBOSE")))
+    elif _build.stale() and os.environ.get("FMI_ALLOW_STALE") != "1":
+        if build_if_missing and _build.have_nvcc():
+            _build.build(verbose=bool(os.environ.get("FMI_VERBOSE")))
+        else:
+            raise RuntimeError(f"{LIB_PATH} is older than csrc/ (run `python -m face_mask_inpaint_b200.build`, or FMI_ALLOW_STALE=1)")
     lib = C.CDLL(str(LIB_PATH))
     for name, (res, args) in PROTOTYPES.items():
         fn = getattr(lib, name)  # AttributeError here == header/library mismatch: fail loudly

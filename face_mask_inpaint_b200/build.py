@@ -67,10 +67,52 @@ def _compile_one(nvcc: str, src: Path, verbose: bool) -> Path:
     return obj
 
 
+def have_nvcc() -> bool:
+    try:
+        _nvcc()
+        return True
+    except RuntimeError:
+        return False
+
+
+DIGEST = LIB.with_name(LIB.name + ".digest")
+
+
+def source_digest() -> str:
+    h = hashlib.sha1()
+    h.update(" ".join(NVCC_FLAGS).replace(str(ROOT), "").encode())
+    for f in sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list((ROOT / "include").glob("*.h"))):
+        h.update(f.name.encode())
+        h.update(f.read_bytes())
+    return h.hexdigest()
+
+
+def stale() -> bool:
+    """True when the linked library was not built from the sources that are here now: the digest of csrc/ + include/ written
+    next to it at link time differs (content, not mtime: a copy of the tree to another box must not look stale)."""
+    if not LIB.exists() or not DIGEST.exists():
+        return True
+    return DIGEST.read_text().strip() != source_digest()
+
+
 def build(force: bool = False, verbose: bool = True) -> Path:
-    """Compile every csrc/*.cu for sm_100a and link face_mask_inpaint_b200/libfmi_b200.so."""
-    nvcc = _nvcc()
+    """Compile every csrc/*.cu for sm_100a and link face_mask_inpaint_b200/libfmi_b200.so — under an exclusive file lock (N ranks
+    of a torchrun job on a fresh checkout must not run nvcc into the same objects), linking to a temporary name that is renamed
+    into place, so that no process can dlopen a partially written library."""
+    import fcntl
     BUILD.mkdir(parents=True, exist_ok=True)
+    with open(BUILD / ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and LIB.exists() and not stale():
+                return LIB            # another process built it while this one waited for the lock
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force: bool, verbose: bool) -> Path:
+    nvcc = _nvcc()
     if force:
         for f in BUILD.glob("*.sha1"):
             f.unlink()
@@ -78,12 +120,16 @@ def build(force: bool = False, verbose: bool = True) -> Path:
     with cf.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = list(ex.map(lambda s: _compile_one(nvcc, s, verbose), srcs))
     newest = max(o.stat().st_mtime for o in objs)
-    if force or not LIB.exists() or LIB.stat().st_mtime < newest:
+    if force or stale() or LIB.stat().st_mtime < newest:
+        tmp = LIB.with_name(f".{LIB.name}.{os.getpid()}.tmp")
         cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC",
-               "-cudart", "static", "-o", str(LIB), *map(str, objs)]
+               "-cudart", "static", "-o", str(tmp), *map(str, objs)]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
+            tmp.unlink(missing_ok=True)
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+        os.replace(tmp, LIB)
+        DIGEST.write_text(source_digest())
         if verbose:
             sys.stderr.write(f"[fmi_b200.build] linked {LIB}\n")
     return LIB

@@ -601,13 +601,13 @@ template <bool TF32, typename T, bool CLUSTER>
 int launch_attn(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const AttnParams& prm,
                 const AttnPlan& pl, cudaStream_t st) {
   auto kern = attn_fwd_kernel<TF32, T, CLUSTER>;
-  static bool attr_set = false;  // per template instantiation
-  if (!attr_set) {
+  static FmiPerDeviceOnce attr_once;  // per template instantiation
+  if (attr_once.need()) {
     cudaFuncAttributes fa;
     FMI_CUDA(cudaFuncGetAttributes(&fa, kern));
     FMI_REQUIRE((int)fa.sharedSizeBytes <= kStaticSmem, "attn_fwd: static shared memory grew to %d bytes", (int)fa.sharedSizeBytes);
     FMI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-    attr_set = true;
+    attr_once.done();
   }
   dim3 grid(prm.S / BM, prm.N, (prm.C0 + prm.C1) / prm.cv_tile);
   // kind 0 = the kernel that does the work; as the fallback behind the fast kernel (qmax2 given: it exits at once for
@@ -640,14 +640,14 @@ template <bool TF32, typename T, bool CLUSTER>
 int launch_attn2(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, AttnParams prm, const AttnPlan& pl,
                  cudaStream_t st) {
   auto kern = attn_fwd2_kernel<TF32, T, CLUSTER>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static FmiPerDeviceOnce attr_once;
+  if (attr_once.need()) {
     cudaFuncAttributes fa;
     FMI_CUDA(cudaFuncGetAttributes(&fa, kern));
     FMI_REQUIRE((int)fa.sharedSizeBytes <= kAttn2StaticSmem, "attn_fwd2: static shared memory grew to %d bytes",
                 (int)fa.sharedSizeBytes);
     FMI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn2SmemBudget));
-    attr_set = true;
+    attr_once.done();
   }
   prm.k_stages = pl.k_stages2;
   prm.v_stages = pl.v_stages2;
@@ -675,14 +675,14 @@ template <bool TF32, typename T>
 int launch_attn3(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, AttnParams prm, const AttnPlan& pl,
                  cudaStream_t st) {
   auto kern = attn_fwd3_kernel<TF32, T>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static FmiPerDeviceOnce attr_once;
+  if (attr_once.need()) {
     cudaFuncAttributes fa;
     FMI_CUDA(cudaFuncGetAttributes(&fa, kern));
     FMI_REQUIRE((int)fa.sharedSizeBytes <= kAttn3StaticSmem, "attn_fwd3: static shared memory grew to %d bytes",
                 (int)fa.sharedSizeBytes);
     FMI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn3SmemBudget));
-    attr_set = true;
+    attr_once.done();
   }
   prm.k_stages = 2;
   prm.v_stages = pl.v_stages3;

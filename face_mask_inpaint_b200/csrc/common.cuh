@@ -39,6 +39,20 @@ struct FmiProfScope {
   double flops_, bytes_;
 };
 
+// One-time per-DEVICE setup of a kernel (cudaFuncSetAttribute is per device): a process that drives several GPUs must opt every
+// one of them into the larger dynamic shared memory (a per-process flag left the second device at the default limit).
+#include <atomic>
+struct FmiPerDeviceOnce {
+  std::atomic<unsigned long long> mask{0};
+  static unsigned long long bit() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return 1ull << (d & 63);
+  }
+  bool need() const { return !(mask.load(std::memory_order_acquire) & bit()); }
+  void done() { mask.fetch_or(bit(), std::memory_order_release); }
+};
+
 #define FMI_REQUIRE(cond, ...)      \
   do {                              \
     if (!(cond)) {                  \

@@ -246,10 +246,10 @@ int launch_gemm_nt(const void* A, int64_t lda, int64_t a_bs, const void* B, int6
     FMI_REQUIRE(e == 0, "gemm_nt: cuTensorMapEncodeTiled(B) failed (%d)", e);
   }
   auto kern = gemm_nt_kernel<TF32>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static FmiPerDeviceOnce attr_once;
+  if (attr_once.need()) {
     FMI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024));
-    attr_set = true;
+    attr_once.done();
   }
   dim3 grid((p.N + n_tile - 1) / n_tile, (p.M + 127) / 128, batch);
   kern<<<grid, kGemmThreads, (size_t)stages * stage_bytes, st>>>(ma, mb, p);

@@ -458,10 +458,10 @@ BwdLayout bwd_layout(int B, int I, int O, int H, int W, int upsample, int act, i
 template <bool TF32>
 int launch_wgrad(const CUtensorMap& ma, const CUtensorMap& mb, WgradParams p, cudaStream_t st) {
   auto kern = wgrad_gemm_kernel<TF32>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static FmiPerDeviceOnce attr_once;
+  if (attr_once.need()) {
     FMI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 2048));
-    attr_set = true;
+    attr_once.done();
   }
   constexpr int EPA = TF32 ? 32 : 64;
   const int box_bytes = p.TH * p.TW * 128;

@@ -480,10 +480,10 @@ inline int pick_n_tile(int O, int n0, int64_t pixel_tiles) {
 template <bool TF32>
 int launch_gemm_class(const CUtensorMap& mx, const CUtensorMap& mw, ConvGemmParams p, cudaStream_t st) {
   auto kern = modconv_gemm_kernel<TF32>;
-  static bool attr_set = false;  // per translation unit and template instance
-  if (!attr_set) {
+  static FmiPerDeviceOnce attr_once;  // per translation unit and template instance
+  if (attr_once.need()) {
     FMI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - kGemmStaticSmem));  // static: 5 KB
-    attr_set = true;
+    attr_once.done();
   }
   const int stage_bytes = p.halo ? A_HALO_BYTES + 3 * p.n_tile * 128 : A_STAGE_BYTES + p.n_tile * 128;
   // Two accumulators per CTA in TMEM. Narrow tiles (N <= 64: 128 columns) leave room for 3 co-resident CTAs, N <= 128 for
