@@ -335,6 +335,9 @@ extern "C" int fmi_attn_bwd(const void* x, const float* wq, const float* bq, con
   rc = fmi_device_check();
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  // whole backward of one attention call (all of its launches): 5 S x S products per value group + the row-role / column-role dQ
+  FmiProfScope prof(FMI_PROF_ATTN_BWD, st, (double)N * (4.0 * S * (double)S * d + 4.0 * S * (double)S * (C0 + C1)) * 1.0,
+                    (double)N * S * (d + 3.0 * (C0 + C1)) * (dtype == FMI_F32 ? 4.0 : 2.0));
   uint8_t* ws = (uint8_t*)workspace;
   rc = fmi_attn_stage_operands(x, wq, bq, v0, v1, ws + pl.qt, ws + pl.vcat, N, C, d, C0, C1, S, dtype, mma, st);
   if (rc) return rc;

@@ -509,6 +509,10 @@ extern "C" int fmi_styled_conv_bwd_nhwc(const void* x, const void* y, const void
   int rc = fmi_device_check();
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  // whole backward of one StyledConv (activation + blur backward, data gradient GEMM, weight-gradient GEMM, chain rule)
+  FmiProfScope prof(FMI_PROF_WGRAD, st, 4.0 * B * (double)H * W * (upsample ? 1.0 : 1.0) * 9.0 * I * O,
+                    (double)B * H * W * (2.0 * I + (upsample ? 8.0 : 2.0) * O) * (mma == FMI_MMA_TF32 ? 4.0 : 2.0));
+
   const bool tf32 = mma == FMI_MMA_TF32;
   const int esz = esz_of(mma);
   const int vec = 16 / esz;
