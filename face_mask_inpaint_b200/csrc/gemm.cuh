@@ -35,6 +35,16 @@ struct GemmParams {
 constexpr int kGemmThreads = 192;
 constexpr int A_TILE_BYTES = 128 * 128;
 
+// 32 consecutive floats as 8 independent 16-byte loads
+__device__ __forceinline__ void ld32f(const float* __restrict__ src, float (&dst)[32]) {
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 t = s4[q];
+    dst[4 * q] = t.x; dst[4 * q + 1] = t.y; dst[4 * q + 2] = t.z; dst[4 * q + 3] = t.w;
+  }
+}
+
 template <bool TF32>
 __global__ void __launch_bounds__(kGemmThreads, 2)
     gemm_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
@@ -127,9 +137,16 @@ __global__ void __launch_bounds__(kGemmThreads, 2)
         // out0[r] += sum_c aux[r,c] * acc[r,c]   (delta_i = sum_j P[i,j] dP[i,j] from the SAME P and dP as EPI_DS uses)
         const float* pa = (const float*)p.aux + (int64_t)bz * p.aux_bs + (int64_t)r * p.ld_aux + cbase;
         float part = 0.f;
+        if (ncols == 32 && fmi_aligned_dev(pa, 16)) {   // 8 independent 16-byte loads (a guarded scalar load per element
+          float a[32];                                    // compiles to a branch per element: 32 serialised load latencies)
+          ld32f(pa, a);
 #pragma unroll
-        for (int k = 0; k < 32; ++k)
-          if (k < ncols) part = fmaf(pa[k], f[k], part);
+          for (int k = 0; k < 32; ++k) part = fmaf(a[k], f[k], part);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 32; ++k)
+            if (k < ncols) part = fmaf(pa[k], f[k], part);
+        }
         atomicAdd((float*)p.out0 + (int64_t)bz * p.out_bs + r, part);
         continue;
       }
@@ -138,13 +155,21 @@ __global__ void __launch_bounds__(kGemmThreads, 2)
         if (p.epi == EPI_ADD_COLSCALE) {
           const float* cv = p.colvec + (int64_t)bz * p.vec_bs + cbase;
           const int64_t aoff = (int64_t)bz * p.aux_bs + (int64_t)r * p.ld_aux + cbase;
+          if (ncols == 32 && p.aux_dtype == FMI_F32 && fmi_aligned_dev((const float*)p.aux + aoff, 16) && fmi_aligned_dev(cv, 16)) {
+            float a[32], c[32];
+            ld32f((const float*)p.aux + aoff, a);
+            ld32f(cv, c);
 #pragma unroll
-          for (int k = 0; k < 32; ++k)
-            if (k < ncols) {
-              const float a = p.aux_dtype == FMI_F32 ? ((const float*)p.aux)[aoff + k]
-                                                     : __bfloat162float(((const __nv_bfloat16*)p.aux)[aoff + k]);
-              f[k] = fmaf(cv[k], a, f[k]);
-            }
+            for (int k = 0; k < 32; ++k) f[k] = fmaf(c[k], a[k], f[k]);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 32; ++k)
+              if (k < ncols) {
+                const float a = p.aux_dtype == FMI_F32 ? ((const float*)p.aux)[aoff + k]
+                                                       : __bfloat162float(((const __nv_bfloat16*)p.aux)[aoff + k]);
+                f[k] = fmaf(cv[k], a, f[k]);
+              }
+          }
         }
 #pragma unroll
         for (int k = 0; k < 32; k += 4)
@@ -161,10 +186,20 @@ __global__ void __launch_bounds__(kGemmThreads, 2)
         float g[32];
         if (p.epi == EPI_EXP_SYM) {
           const float* lc = p.rowvec + (int64_t)bz * p.vec_bs + cbase;
+          if (ncols == 32 && fmi_aligned_dev(lc, 16)) {
+            float l[32];
+            ld32f(lc, l);
 #pragma unroll
-          for (int k = 0; k < 32; ++k) {
-            g[k] = k < ncols ? __expf(f[k] - lc[k]) : 0.f;
-            f[k] = __expf(f[k] - rv);
+            for (int k = 0; k < 32; ++k) {
+              g[k] = __expf(f[k] - l[k]);
+              f[k] = __expf(f[k] - rv);
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+              g[k] = k < ncols ? __expf(f[k] - lc[k]) : 0.f;
+              f[k] = __expf(f[k] - rv);
+            }
           }
           // P (out0) is only ever an elementwise factor of dE: keep it UNROUNDED fp32 — rounding it before forming
           // P o (dP - delta) is what dominated the gradient error for peaked attention; P^T (out1) is a GEMM operand.
@@ -174,8 +209,15 @@ __global__ void __launch_bounds__(kGemmThreads, 2)
             if (k < ncols) *reinterpret_cast<float4*>(pf + k) = make_float4(f[k], f[k + 1], f[k + 2], f[k + 3]);
         } else if (p.epi == EPI_DS) {
           const float* pa = (const float*)p.aux + (int64_t)bz * p.aux_bs + (int64_t)r * p.ld_aux + cbase;
+          if (ncols == 32 && fmi_aligned_dev(pa, 16)) {
+            float a[32];
+            ld32f(pa, a);
 #pragma unroll
-          for (int k = 0; k < 32; ++k) f[k] = k < ncols ? pa[k] * (f[k] - rv) : 0.f;
+            for (int k = 0; k < 32; ++k) f[k] = a[k] * (f[k] - rv);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) f[k] = k < ncols ? pa[k] * (f[k] - rv) : 0.f;
+          }
         }
         auto store_row = [&](OT* dst, const float* x) {
           if constexpr (TF32) {
