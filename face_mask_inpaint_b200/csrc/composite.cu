@@ -184,3 +184,47 @@ extern "C" int fmi_composite_bwd(const void* grad_out, const float* mask, void* 
                                                                Hm, Wm, (cudaStream_t)stream)));
   return FMI_OK;
 }
+
+// ---- k x k average pooling of fp32 NCHW planes (psp.py:33,113-114 `face_pool`: AdaptiveAvgPool2d((256, 256)) of the 1024^2
+// synthesis = an exact 4 x 4 mean; model.py:79,111 likewise when the decoder's pooling is not fused into its Output kernel).
+// HBM-bound: every input element read once as part of a 16-byte vector, one output per thread (k = 4: one float4 per row).
+namespace {
+template <int K>
+__global__ void __launch_bounds__(256) avgpool_planes_kernel(const float* __restrict__ x, float* __restrict__ y, int H, int W,
+                                                             int64_t total) {
+  const int OW = W / K, OH = H / K;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int ox = (int)(e % OW);
+    const int64_t t = e / OW;
+    const int oy = (int)(t % OH);
+    const int64_t plane = t / OH;
+    const float* src = x + (plane * H + (int64_t)oy * K) * W + (int64_t)ox * K;
+    float acc = 0.f;
+#pragma unroll
+    for (int r = 0; r < K; ++r) {
+      if constexpr (K == 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(src + (int64_t)r * W));
+        acc += (v.x + v.y) + (v.z + v.w);
+      } else {
+        const float2 v = __ldg(reinterpret_cast<const float2*>(src + (int64_t)r * W));
+        acc += v.x + v.y;
+      }
+    }
+    y[e] = acc * (1.f / (K * K));
+  }
+}
+}  // namespace
+
+extern "C" int fmi_avgpool_planes(const float* x, float* y, int64_t planes, int H, int W, int k, void* stream) {
+  FMI_REQUIRE(planes >= 0 && H >= 1 && W >= 1 && (k == 2 || k == 4), "avgpool_planes: k must be 2 or 4");
+  if (planes == 0) return FMI_OK;
+  FMI_REQUIRE(x && y && H % k == 0 && W % k == 0 && W % 4 == 0 && fmi_aligned(x, 16),
+              "avgpool_planes: H, W must be multiples of k (W of 4) and x 16-byte aligned");
+  const int64_t total = planes * (H / k) * (W / k);
+  const int grid = (int)imin64((total + 255) / 256, (int64_t)FMI_NUM_SMS * 32);
+  cudaStream_t st = (cudaStream_t)stream;
+  FmiProfScope prof(FMI_PROF_STREAM, st, (double)planes * H * W, (double)planes * H * W * 4.0 * (1.0 + 1.0 / (k * k)));
+  if (k == 4) avgpool_planes_kernel<4><<<grid, 256, 0, st>>>(x, y, H, W, total);
+  else avgpool_planes_kernel<2><<<grid, 256, 0, st>>>(x, y, H, W, total);
+  return fmi_launched("avgpool_planes");
+}

@@ -216,7 +216,7 @@ class pSp(nn.Module):
         images, result_latent = self.decoder([codes], input_is_latent=not input_code, randomize_noise=randomize_noise,
                                              return_latents=return_latents)
         if resize:
-            images = self.face_pool(images)
+            images = ops.adaptive_avg_pool(images, self.face_pool.output_size)   # exact 4x4 mean: fmi_avgpool_planes
         return (images, result_latent) if return_latents else images
 
 

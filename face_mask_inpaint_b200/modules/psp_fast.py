@@ -123,6 +123,12 @@ class _Plan:
         self.units = [_prep_unit(u, mma) for u in enc.body]
         self.lat1 = (_taps(enc.latlayer1.weight.detach().float(), mma), enc.latlayer1.bias.detach().float().contiguous())
         self.lat2 = (_taps(enc.latlayer2.weight.detach().float(), mma), enc.latlayer2.bias.detach().float().contiguous())
+        # out_conv of the two attention modules (example_guided_att.py:13,38-39): a 1x1 GEMM on the NHWC copy of the concat
+        self.att_out = {}
+        for name in ("attention1", "attention2"):
+            att = getattr(enc, name, None)
+            if att is not None and getattr(att, "out_channels", None) is not None:
+                self.att_out[name] = (_taps(att.out_conv.weight.detach().float(), mma), att.out_conv.bias.detach().float().contiguous())
         # map2style heads grouped by the pyramid level they read
         groups = [(0, enc.coarse_ind), (enc.coarse_ind, enc.middle_ind), (enc.middle_ind, enc.style_count)]
         self.heads = []
@@ -253,6 +259,22 @@ def _to_nhwc(k, x):
     return y
 
 
+def _attention_nhwc(k: _Ctx, plan, name, att, mask_s, src, ref):
+    """ExampleGuidedAttention.forward (example_guided_att.py:21-41) -> NHWC operand-type features: the fused attention kernel on
+    the module's NCHW interface, then — when the module has an out_conv — that 1x1 convolution as an implicit GEMM on the NHWC
+    copy of the concat (the module's own out_conv is a SIMT fp32 kernel: 0.26 ms of a batch-8 forward for 2 x 2 GFLOP)."""
+    from .attention import _EGAFunction
+    ent = plan.att_out.get(name)
+    if ent is None:
+        return _to_nhwc(k, att(mask_s, src, ref))
+    cat = _to_nhwc(k, _EGAFunction.apply(mask_s, src, ref, att.conv.weight))
+    n, h, w, c2 = cat.shape
+    wp, bias = ent
+    y = k.empty(n, h, w, wp.shape[1])
+    k.conv(cat, c2, wp, bias, y, n, c2, wp.shape[1], h, w, ksize=1)
+    return y
+
+
 def _heads(k: _Ctx, group, feat, n, hw):
     """All map2style heads (psp_encoders.py:13-37) that read one pyramid level: feat [n, hw, hw, C] -> codes [n, heads, 512]
     fp32. Level 0 is ONE GEMM with the heads' weights concatenated along O; deeper levels run the heads as extra batch entries
@@ -313,13 +335,12 @@ def encoder_forward(enc, x, ref=None, mask=None):
         mask_full = mask.unsqueeze(1)
         n1, n2, n3 = (_to_nchw(k, f, b, f.shape[-1], hh, ww) for f, hh, ww in ((f1, h1, w1), (f2, h2, w2), (f3, h3, w3)))
         if enc.use_attention:
-            c3 = enc.attention1(ops.scale_img(mask_full, (h3, w3)), n3[:n], n3[n:])
-            c2 = enc.attention2(ops.scale_img(mask_full, (h2, w2)), n2[:n], n2[n:])
+            c3 = _attention_nhwc(k, plan, "attention1", enc.attention1, ops.scale_img(mask_full, (h3, w3)), n3[:n], n3[n:])
+            c2 = _attention_nhwc(k, plan, "attention2", enc.attention2, ops.scale_img(mask_full, (h2, w2)), n2[:n], n2[n:])
         else:
-            c3 = ops.composite(n3[:n].contiguous(), n3[n:].contiguous(), mask_full)
-            c2 = ops.composite(n2[:n].contiguous(), n2[n:].contiguous(), mask_full)
-        c1 = ops.composite(n1[:n].contiguous(), n1[n:].contiguous(), mask_full)
-        c1, c2, c3 = _to_nhwc(k, c1), _to_nhwc(k, c2), _to_nhwc(k, c3)
+            c3 = _to_nhwc(k, ops.composite(n3[:n].contiguous(), n3[n:].contiguous(), mask_full))
+            c2 = _to_nhwc(k, ops.composite(n2[:n].contiguous(), n2[n:].contiguous(), mask_full))
+        c1 = _to_nhwc(k, ops.composite(n1[:n].contiguous(), n1[n:].contiguous(), mask_full))
     codes = []
     if plan.heads[0] is not None:
         codes.append(_heads(k, plan.heads[0], c3, n, h3))

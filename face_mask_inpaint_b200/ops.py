@@ -237,6 +237,22 @@ def scale_img(img, size):
     return out.to(img.dtype)
 
 
+def adaptive_avg_pool(img, size):
+    """nn.AdaptiveAvgPool2d(size) of an image batch (psp.py:33,113-114 `face_pool`; model.py:79,111). The exact k x k case
+    (k = 2 or 4, fp32, inference) is fmi_avgpool_planes; anything else — other ratios, autograd — is ATen's own pooling (metric-
+    side resizing, not the hot path)."""
+    h, w = int(size[0]), int(size[1])
+    n, c, ih, iw = img.shape
+    k = ih // h if h else 0
+    if (img.is_cuda and img.dtype == torch.float32 and not (torch.is_grad_enabled() and img.requires_grad) and k in (2, 4)
+            and ih == k * h and iw == k * w and iw % 4 == 0):
+        x = img.contiguous()
+        out = torch.empty((n, c, h, w), dtype=torch.float32, device=img.device)
+        _lib.check(_lib.load().fmi_avgpool_planes(_ptr(x), _ptr(out), n * c, ih, iw, k, _stream()), "fmi_avgpool_planes")
+        return out
+    return torch.nn.functional.adaptive_avg_pool2d(img, (h, w))
+
+
 class _Composite(Function):
     @staticmethod
     def forward(ctx, src, ref, mask_full):

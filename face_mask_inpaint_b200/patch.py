@@ -255,6 +255,27 @@ def _install_compositing_callers():
 
     enc_mod.GradualStyleEncoder.forward = gradual_style_encoder_forward
 
+    # pSp.face_pool (psp.py:33,113-114): AdaptiveAvgPool2d((256, 256)) of the 1024^2 synthesis is an exact 4x4 mean
+    try:
+        psp_mod = importlib.import_module("modules.psp.psp")
+    except Exception:
+        return
+    import torch
+
+    class _FacePool(torch.nn.AdaptiveAvgPool2d):
+        def forward(self, x):
+            size = self.output_size if isinstance(self.output_size, (tuple, list)) else (self.output_size, self.output_size)
+            return ops.adaptive_avg_pool(x, size) if x.is_cuda else super().forward(x)
+
+    plain_init = psp_mod.pSp.__init__
+
+    def psp_init(self, opts):
+        plain_init(self, opts)
+        if type(self.face_pool) is torch.nn.AdaptiveAvgPool2d:
+            self.face_pool = _FacePool(self.face_pool.output_size)
+
+    psp_mod.pSp.__init__ = psp_init
+
 
 def _install_picnet_decoder():
     """f1: ResGenerator.forward (modules/pluralistic_model/network.py:247-268) runs its ResBlockDecoder /

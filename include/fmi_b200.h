@@ -354,6 +354,10 @@ int fmi_se_scale_add_nhwc(const void* r, const float* gate, const void* sc, int6
 int fmi_upsample_add_nhwc(const void* x, const void* add, void* y, int B, int C, int h, int w, int OH, int OW, int mma,
                           void* stream);
 
+/* k x k mean (k = 2 or 4) of fp32 planes [planes][H][W] -> [planes][H/k][W/k]: the exact case of the generators' final
+ * AdaptiveAvgPool2d (modules/psp/psp.py:33,113-114 `face_pool` 1024^2 -> 256^2; modules/model.py:79,111). */
+int fmi_avgpool_planes(const float* x, float* y, int64_t planes, int H, int W, int k, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
