@@ -76,10 +76,6 @@ PROTOTYPES = {
     "fmi_se_scale_add_nhwc": (_i, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _i, _i, _i, _i, _i, _vp]),
     "fmi_upsample_add_nhwc": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "fmi_avgpool_planes": (_i, [_vp, _vp, _i64, _i, _i, _i, _vp]),
-    "fmi_conv3x3_nhwc_stats": (_i, [_vp, _i64, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _i, _vp, _vp]),
-    "fmi_instnorm_finalize": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
-    "fmi_conv_nhwc_sums": (_i, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
-    "fmi_se_gate_from_sums": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
 }
 
 _lib = None

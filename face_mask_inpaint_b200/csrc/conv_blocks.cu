@@ -314,41 +314,9 @@ extern "C" int fmi_reflect_border_nhwc(void* y, int B, int C, int H, int W, int 
 //   InstanceNorm (a rounding of x is amplified by |mean| / std there); an MMA reading such a tensor truncates it instead.
 //   y: NHWC in the operand type, O channels per pixel out of y_pixel_stride, written at the interior of a buffer padded by
 //   y_pad pixels on each side (0 or 1); may be NULL when y_nchw is given. y_nchw: fp32 [B, nchw_C, OH, OW] or NULL.
-static int conv3x3_impl(const void* x, int64_t x_pixel_stride, const void* wp, const float* bias, void* y,
-                        int64_t y_pixel_stride, int y_pad, float* y_nchw, int nchw_C, int B, int I, int O, int H, int W,
-                        int mode, int act, float slope, int round_y, int mma, double* stat_sums, void* stream);
-
 extern "C" int fmi_conv3x3_nhwc(const void* x, int64_t x_pixel_stride, const void* wp, const float* bias, void* y,
                                 int64_t y_pixel_stride, int y_pad, float* y_nchw, int nchw_C, int B, int I, int O, int H,
                                 int W, int mode, int act, float slope, int round_y, int mma, void* stream) {
-  return conv3x3_impl(x, x_pixel_stride, wp, bias, y, y_pixel_stride, y_pad, y_nchw, nchw_C, B, I, O, H, W, mode, act, slope,
-                      round_y, mma, nullptr, stream);
-}
-
-// The same convolution, whose epilogue also accumulates the InstanceNorm statistics of its output — per (image, channel) sum
-// and sum of squares of the stored values into stat_sums (double [B][O][2], zeroed here) — so that the separate statistics
-// pass over the tensor (fmi_instnorm_stats_nhwc) is not needed; finish with fmi_instnorm_finalize.
-extern "C" int fmi_conv3x3_nhwc_stats(const void* x, int64_t x_pixel_stride, const void* wp, const float* bias, void* y,
-                                      int64_t y_pixel_stride, int y_pad, int B, int I, int O, int H, int W, int mode, int act,
-                                      float slope, int round_y, int mma, double* stat_sums, void* stream) {
-  FMI_REQUIRE(stat_sums && y, "conv3x3_stats: null pointer");
-  FMI_CUDA(cudaMemsetAsync(stat_sums, 0, (size_t)B * O * 2 * sizeof(double), (cudaStream_t)stream));
-  return conv3x3_impl(x, x_pixel_stride, wp, bias, y, y_pixel_stride, y_pad, nullptr, 0, B, I, O, H, W, mode, act, slope, round_y,
-                      mma, stat_sums, stream);
-}
-
-extern "C" int fmi_instnorm_finalize(const double* sums, const float* gamma, const float* beta, float* scale_shift, int B, int C,
-                                     int HW, float eps, void* stream) {
-  if (B == 0) return FMI_OK;
-  FMI_REQUIRE(sums && scale_shift && C >= 1 && HW >= 1, "instnorm_finalize: bad arguments");
-  instnorm_finalize_kernel<<<(B * C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(sums, gamma, beta, scale_shift, B, C,
-                                                                                  1.0 / (double)HW, eps);
-  return fmi_launched("instnorm_finalize");
-}
-
-static int conv3x3_impl(const void* x, int64_t x_pixel_stride, const void* wp, const float* bias, void* y,
-                        int64_t y_pixel_stride, int y_pad, float* y_nchw, int nchw_C, int B, int I, int O, int H, int W,
-                        int mode, int act, float slope, int round_y, int mma, double* stat_sums, void* stream) {
   FMI_REQUIRE(mma == FMI_MMA_TF32 || mma == FMI_MMA_BF16, "conv3x3: bad mma");
   if (B == 0) return FMI_OK;
   FMI_REQUIRE(x && wp && (y || y_nchw), "conv3x3: null pointer");
@@ -381,7 +349,6 @@ static int conv3x3_impl(const void* x, int64_t x_pixel_stride, const void* wp, c
   p.w_shared = 1;
   p.raw_out = !round_y;
   p.add_out = add_y;
-  p.stat_sums = stat_sums; p.stat_c = O; p.stat_sq = 1;
   if (mode == 4) p.T = 1;               // 1x1 convolution: one tap, wp [1][O][I]
   p.n_tile = O <= 256 ? O : 256;
   if (mode != 3) {   // few pixel tiles: narrower output tiles on more SMs (pick_n_tile)

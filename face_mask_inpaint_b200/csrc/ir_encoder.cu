@@ -90,8 +90,8 @@ __global__ void __launch_bounds__(256) channel_sum_kernel(const T* __restrict__ 
 
 // SEModule gate (helpers.py:56-74): m = mean_hw r (the slab sums added in slab order), g[b][c] = sigmoid(W2 relu(W1 m[b])),
 // W1 [R][C], W2 [C][R]; one CTA per image.
-__global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ part, int slabs, const double* __restrict__ dsums,
-                                                      float inv_hw, const float* __restrict__ w1, const float* __restrict__ w2,
+__global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ part, int slabs, float inv_hw,
+                                                      const float* __restrict__ w1, const float* __restrict__ w2,
                                                       float* __restrict__ mean, float* __restrict__ gate, int C, int R) {
   extern __shared__ float sm[];   // [C] mean, [R] hidden
   float* m = sm;
@@ -99,9 +99,7 @@ __global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ 
   const int b = blockIdx.x;
   for (int c = threadIdx.x; c < C; c += 256) {
     float t = 0.f;
-    if (dsums) t = (float)dsums[2 * ((int64_t)b * C + c)];   // sums accumulated by the producing GEMM's epilogue
-    else
-      for (int s = 0; s < slabs; ++s) t += part[((int64_t)b * slabs + s) * C + c];
+    for (int s = 0; s < slabs; ++s) t += part[((int64_t)b * slabs + s) * C + c];
     m[c] = t * inv_hw;
     mean[(int64_t)b * C + c] = m[c];
   }
@@ -186,34 +184,10 @@ __global__ void __launch_bounds__(256) upsample_add_kernel(const T* __restrict__
 // ---------------------------------------------------------------------------------------------------------------------
 // General NHWC convolution on the implicit-GEMM kernel (see include/fmi_b200.h).
 // ---------------------------------------------------------------------------------------------------------------------
-static int conv_nhwc_impl(const void* x, int64_t x_pixel_stride, int64_t x_row_stride, int64_t x_img_stride, const void* wp,
-                          const float* bias, int bias_classes, const float* slope_c, float slope, void* y,
-                          int64_t y_pixel_stride, int B, int I, int O, int H, int W, int ksize, int planes, int w_group,
-                          int bias_per_set, int act, int add_y, int round_y, int mma, double* stat_sums, void* stream);
-
 extern "C" int fmi_conv_nhwc(const void* x, int64_t x_pixel_stride, int64_t x_row_stride, int64_t x_img_stride, const void* wp,
                              const float* bias, int bias_classes, const float* slope_c, float slope, void* y,
                              int64_t y_pixel_stride, int B, int I, int O, int H, int W, int ksize, int planes, int w_group,
                              int bias_per_set, int act, int add_y, int round_y, int mma, void* stream) {
-  return conv_nhwc_impl(x, x_pixel_stride, x_row_stride, x_img_stride, wp, bias, bias_classes, slope_c, slope, y, y_pixel_stride,
-                        B, I, O, H, W, ksize, planes, w_group, bias_per_set, act, add_y, round_y, mma, nullptr, stream);
-}
-
-// fmi_conv_nhwc whose epilogue also accumulates the per-(image, channel) SUM of the stored values into stat_sums (double
-// [B][O][2], slot 0; zeroed here): the SEModule's average pooling without a pass over the tensor (fmi_se_gate_from_sums).
-extern "C" int fmi_conv_nhwc_sums(const void* x, int64_t x_pixel_stride, int64_t x_row_stride, int64_t x_img_stride,
-                                  const void* wp, const float* bias, void* y, int64_t y_pixel_stride, int B, int I, int O, int H,
-                                  int W, int ksize, int planes, int round_y, int mma, double* stat_sums, void* stream) {
-  FMI_REQUIRE(stat_sums, "conv_nhwc_sums: null pointer");
-  FMI_CUDA(cudaMemsetAsync(stat_sums, 0, (size_t)B * O * 2 * sizeof(double), (cudaStream_t)stream));
-  return conv_nhwc_impl(x, x_pixel_stride, x_row_stride, x_img_stride, wp, bias, 1, nullptr, 0.f, y, y_pixel_stride, B, I, O, H, W,
-                        ksize, planes, 0, 0, 2, 0, round_y, mma, stat_sums, stream);
-}
-
-static int conv_nhwc_impl(const void* x, int64_t x_pixel_stride, int64_t x_row_stride, int64_t x_img_stride, const void* wp,
-                          const float* bias, int bias_classes, const float* slope_c, float slope, void* y,
-                          int64_t y_pixel_stride, int B, int I, int O, int H, int W, int ksize, int planes, int w_group,
-                          int bias_per_set, int act, int add_y, int round_y, int mma, double* stat_sums, void* stream) {
   FMI_REQUIRE(mma == FMI_MMA_TF32 || mma == FMI_MMA_BF16, "conv_nhwc: bad mma");
   if (B == 0) return FMI_OK;
   FMI_REQUIRE(x && wp && y, "conv_nhwc: null pointer");
@@ -256,7 +230,6 @@ static int conv_nhwc_impl(const void* x, int64_t x_pixel_stride, int64_t x_row_s
   p.out_rstride = (int64_t)W * y_pixel_stride;
   p.out_bstride = (int64_t)H * W * y_pixel_stride;
   p.prof_kind = FMI_PROF_GEMM_IR;
-  p.stat_sums = stat_sums; p.stat_c = O; p.stat_sq = 0;
   p.ntaps = T;
   const int n_sets = w_group == 0 ? 1 : B / (w_group > 1 ? w_group : 1);
   for (int t = 0; t < T; ++t) {
@@ -273,7 +246,7 @@ static int conv_nhwc_impl(const void* x, int64_t x_pixel_stride, int64_t x_row_s
   }
   // several whole images per tile once a plane is much smaller than the 128-row tile
   int tb = 1;
-  if (H * W <= 64 && !stat_sums) {
+  if (H * W <= 64) {
     const int lim = w_group == 0 ? B : (w_group > 1 ? w_group : 1);
     while (tb * 2 * H * W <= 128 && tb * 2 <= lim && lim % (tb * 2) == 0) tb *= 2;
   }
@@ -348,19 +321,7 @@ extern "C" int fmi_se_gate_nhwc(const void* r, const float* w1, const float* w2,
     channel_sum_kernel<__nv_bfloat16><<<dim3(gx, B), 256, 0, st>>>((const __nv_bfloat16*)r, scratch, C, HW, rows);
   int rc = fmi_launched("channel_sum");
   if (rc) return rc;
-  se_gate_kernel<<<B, 256, (size_t)(C + R) * sizeof(float), st>>>(scratch, gx, nullptr, 1.f / (float)HW, w1, w2, mean, gate, C, R);
-  return fmi_launched("se_gate");
-}
-
-// SEModule gate from per-(image, channel) sums accumulated by the producing convolution (fmi_conv_nhwc_sums): sums double
-// [B][C][2] (slot 0); mean, gate fp32 [B][C].
-extern "C" int fmi_se_gate_from_sums(const double* sums, const float* w1, const float* w2, float* mean, float* gate, int B, int C,
-                                     int R, int HW, void* stream) {
-  if (B == 0) return FMI_OK;
-  FMI_REQUIRE(sums && w1 && w2 && mean && gate && C >= 1 && R >= 1 && R <= 256 && HW >= 1, "se_gate_from_sums: bad arguments");
-  cudaStream_t st = (cudaStream_t)stream;
-  FmiProfScope prof(FMI_PROF_SE, st, 4.0 * B * C * R, (double)B * C * 24.0);
-  se_gate_kernel<<<B, 256, (size_t)(C + R) * sizeof(float), st>>>(nullptr, 0, sums, 1.f / (float)HW, w1, w2, mean, gate, C, R);
+  se_gate_kernel<<<B, 256, (size_t)(C + R) * sizeof(float), st>>>(scratch, gx, 1.f / (float)HW, w1, w2, mean, gate, C, R);
   return fmi_launched("se_gate");
 }
 

@@ -11,7 +11,7 @@ using namespace sm100;
 
 
 constexpr int kGemmThreads = 320;   // TMA warp, MMA warp, two epilogue warpgroups (one per TMEM accumulator)
-constexpr int kGemmStaticSmem = 14336;  // static shared memory of the kernel (barriers, 2 x 4 KB fused-ToRGB weights), rounded up
+constexpr int kGemmStaticSmem = 10240;  // static shared memory of the kernel (barriers, 2 x 4 KB fused-ToRGB weights), rounded up
 __device__ __align__(16) const float kZeroBias[32] = {};   // stands in for an absent bias vector in the epilogue
 constexpr int kMaxTaps = 9;
 constexpr int A_STAGE_BYTES = 128 * 128;
@@ -51,11 +51,6 @@ struct ConvGemmParams {
                        // row, 1 inside) — an input-side BatchNorm folded into a zero-padded 3x3 conv (ir_encoder.cu); else [O]
   int bias_set_stride; // per-sample weights: the bias of weight set g starts g * bias_set_stride floats into `bias` (0: one bias)
   const float* slope_c;  // act 4: PReLU, negative slope per output channel
-  // per-(image, channel) sum and sum of squares of the STORED values, accumulated by the epilogue (InstanceNorm statistics of a
-  // conv output, SE average pooling) instead of a separate pass over the tensor: double [B][stat_c][2], zeroed by the caller
-  double* stat_sums;
-  int stat_c;          // real channels of the output tensor (O, or merge_o with merged parity classes)
-  int stat_sq;         // 1: also the sum of squares
   int prof_kind;       // FMI_PROF_* of this launch for the optional event timing (0: FMI_PROF_GEMM)
   int add_out;         // the epilogue adds the values already stored at the output location (residual sum: y += conv(x))
   int raw_out;         // TF32 mode: store the fp32 accumulator as is instead of rounding it to tf32 (the consumer is not an MMA,
@@ -80,23 +75,6 @@ struct ConvGemmParams {
 // channel tile, then sample). The TMA ring runs ahead across tile boundaries and the accumulator is double buffered in
 // TMEM, so the epilogue of tile i overlaps the MMAs of tile i+1. (One tile per CTA left the tensor pipe 5 % active on the
 // 32 -> 32 @1024^2 layer — ncu: 27 % warps active, the CTA lifetime was prologue + TMA latency + epilogue.)
-// Every lane holds 32 values (one per channel of a chunk); returns, in lane L, the sum over the warp's lanes of value L.
-// Butterfly: at offset `off` a lane keeps the half of its values whose index has the same `off` bit as its lane id and sends the
-// other half to its partner — 16 + 8 + 4 + 2 + 1 = 31 shuffles.
-__device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    const bool hi = (lane & off) != 0;
-#pragma unroll
-    for (int i = 0; i < off; ++i) {
-      const float keep = hi ? v[i + off] : v[i];
-      const float send = hi ? v[i] : v[i + off];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-    }
-  }
-  return v[0];
-}
-
 template <bool TF32>
 __global__ void __launch_bounds__(kGemmThreads, 2)
     modconv_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
@@ -110,7 +88,6 @@ __global__ void __launch_bounds__(kGemmThreads, 2)
   const int stage_bytes = a_bytes + (p.halo ? 3 : 1) * b_stage_bytes;
   __shared__ uint64_t full[8], empty[8], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
-  __shared__ float s_stat[2][2][256];   // per epilogue group: per-tile channel sums / sums of squares (stat_sums)
   __shared__ float4 s_rgbw[2][256];  // fused ToRGB weights of the current image, per epilogue group: (w_r, w_g, w_b, -) per channel
 
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -141,7 +118,6 @@ __global__ void __launch_bounds__(kGemmThreads, 2)
     }
     fence_barrier_init();
   }
-  for (int e = tid; e < 2 * 2 * 256; e += kGemmThreads) (&s_stat[0][0][0])[e] = 0.f;
   if (warp == 1) {
     tmem_alloc(&tmem_base_s, p.tmem_cols);  // two accumulators; narrow layers leave TMEM for co-resident CTAs
     tmem_relinquish();
@@ -300,7 +276,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2)
           tc_fence_before();
           mbar_arrive(&acc_empty[as]);
         }
-        if (!valid && !p.stat_sums) continue;   // (with statistics every lane takes part in the warp reduction below)
+        if (!valid) continue;
         OT* outp = out + c0;
         int bofs = o0 + c0;
         float nzc = nz;
@@ -308,7 +284,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2)
           const int cls = c0 / p.merge_o;
           bofs = c0 - cls * p.merge_o;
           outp = out + (cls >> 1) * p.out_rstride + (cls & 1) * p.out_pstride + bofs;
-          if (p.act == 1 && p.noise && cls && valid)   // the noise plane is indexed by the output pixel of this parity class
+          if (p.act == 1 && p.noise && cls)   // the noise plane is indexed by the output pixel of this parity class
             nzc = (p.noise_w ? *p.noise_w : 1.f) * p.noise[(int64_t)(p.noise_batched ? b : 0) * p.OH * p.OW +
                                                           (int64_t)(oy + (cls >> 1)) * p.OW + ox + (cls & 1)];
         }
@@ -358,22 +334,6 @@ __global__ void __launch_bounds__(kGemmThreads, 2)
               }
             }
           }
-        }
-        if (p.stat_sums) {
-          // lane L ends up with the sum over the warp's 32 pixels of channel L of this chunk (31 shuffles per quantity);
-          // the 4 warps of the group add into shared memory, one double atomic per channel and tile goes to global memory
-          float sv[32];
-#pragma unroll
-          for (int k = 0; k < 32; ++k) sv[k] = valid ? f[k] : 0.f;
-          const float s1 = warp_transpose_sum(sv, tid & 31);
-          const int slot = (p.merge_o ? bofs : c0) + (tid & 31);
-          atomicAdd(&s_stat[grp][0][slot], s1);
-          if (p.stat_sq) {
-#pragma unroll
-            for (int k = 0; k < 32; ++k) sv[k] = valid ? f[k] * f[k] : 0.f;
-            atomicAdd(&s_stat[grp][1][slot], warp_transpose_sum(sv, tid & 31));
-          }
-          if (!valid) continue;
         }
         if (p.nchw_out) {
 #pragma unroll
@@ -437,21 +397,6 @@ __global__ void __launch_bounds__(kGemmThreads, 2)
               *reinterpret_cast<uint4*>(outp + k) = u;
             }
         }
-      }
-      if (p.stat_sums) {
-        const int nslots = p.merge_o ? p.merge_o : p.n_tile;
-        asm volatile("bar.sync %0, 128;" ::"r"(4 + grp) : "memory");
-        for (int e = gtid; e < nslots; e += 128) {
-          const int ch = p.merge_o ? e : o0 + e;
-          double* dst = p.stat_sums + ((int64_t)b * p.stat_c + ch) * 2;
-          atomicAdd(dst, (double)s_stat[grp][0][e]);
-          s_stat[grp][0][e] = 0.f;
-          if (p.stat_sq) {
-            atomicAdd(dst + 1, (double)s_stat[grp][1][e]);
-            s_stat[grp][1][e] = 0.f;
-          }
-        }
-        asm volatile("bar.sync %0, 128;" ::"r"(4 + grp) : "memory");
       }
       if (p.rgb_out && valid) {
         float r3[3] = {rgb0 + p.rgb_bias[0], rgb1 + p.rgb_bias[1], rgb2 + p.rgb_bias[2]};
@@ -563,7 +508,6 @@ int launch_gemm_class(const CUtensorMap& mx, const CUtensorMap& mw, ConvGemmPara
   const size_t smem = (size_t)stages * stage_bytes + 1024;
   TilePlan tp = pick_tile(p.Mh, p.Mw);
   if (p.halo) tp = TilePlan{1, 128, p.Mh, (p.Mw + 127) / 128};
-  FMI_REQUIRE(!p.stat_sums || (p.TB <= 1 && p.stat_c >= 1), "modconv_gemm: channel statistics need one image per tile");
   if (p.TB > 1) {
     FMI_REQUIRE(!p.halo && !p.rgb_out && !p.merge_o && p.Mh * p.Mw * p.TB <= 128 && (p.w_shared || p.w_group % p.TB == 0),
                 "modconv_gemm: bad multi-image tile (TB=%d, %dx%d, w_group=%d)", p.TB, p.Mh, p.Mw, p.w_group);

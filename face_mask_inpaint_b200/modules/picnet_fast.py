@@ -270,39 +270,22 @@ class _Ctx:
             off += i
         return wp
 
-    def norm_act(self, x, x_stride, y, y_stride, norm, b, c, hw, slope, sums=None):
-        """`sums`: the (sum, sum of squares) the producing convolution's epilogue accumulated (`conv(..., stats=)`): only the
-        finalize step runs; else the statistics pass over x."""
+    def norm_act(self, x, x_stride, y, y_stride, norm, b, c, hw, slope):
         ss = None
         if norm is not None:
             ss = torch.empty((b, c, 2), dtype=torch.float32, device=self.dev)
+            sums = torch.empty((b, c, 2), dtype=torch.float64, device=self.dev)
             g = None if norm.weight is None else norm.weight.detach().float().contiguous()
             be = None if norm.bias is None else norm.bias.detach().float().contiguous()
-            if sums is not None:
-                _lib.check(self.lib.fmi_instnorm_finalize(_p(sums), _p(g), _p(be), _p(ss), b, c, hw, float(norm.eps), self.st),
-                           "fmi_instnorm_finalize")
-            else:
-                sums = torch.empty((b, c, 2), dtype=torch.float64, device=self.dev)
-                _lib.check(self.lib.fmi_instnorm_stats_nhwc(x, x_stride, _p(g), _p(be), _p(ss), _p(sums), b, c, hw, float(norm.eps),
-                                                            self.mma, self.st), "fmi_instnorm_stats_nhwc")
+            _lib.check(self.lib.fmi_instnorm_stats_nhwc(x, x_stride, _p(g), _p(be), _p(ss), _p(sums), b, c, hw, float(norm.eps),
+                                                        self.mma, self.st), "fmi_instnorm_stats_nhwc")
         _lib.check(self.lib.fmi_norm_act_nhwc(x, x_stride, y, y_stride, _p(ss), b, c, hw, slope, self.mma, self.st),
                    "fmi_norm_act_nhwc")
         return ss
 
-    def conv(self, x, x_stride, wp, bias, y, y_stride, y_pad, y_nchw, nchw_c, b, i, o, h, w, mode, act, slope=0.0, round_y=1,
-             stats=None):
-        """`stats`: a float64 [b, o, 2] tensor that receives the InstanceNorm statistics of the output from the epilogue."""
-        if stats is not None:
-            _lib.check(self.lib.fmi_conv3x3_nhwc_stats(x, x_stride, _p(wp), _p(bias), y, y_stride, y_pad, b, i, o, h, w, mode, act,
-                                                       slope, round_y, self.mma, _p(stats), self.st), "fmi_conv3x3_nhwc_stats")
-            return
+    def conv(self, x, x_stride, wp, bias, y, y_stride, y_pad, y_nchw, nchw_c, b, i, o, h, w, mode, act, slope=0.0, round_y=1):
         _lib.check(self.lib.fmi_conv3x3_nhwc(x, x_stride, _p(wp), _p(bias), y, y_stride, y_pad, _p(y_nchw), nchw_c, b, i, o, h, w,
                                              mode, act, slope, round_y, self.mma, self.st), "fmi_conv3x3_nhwc")
-
-    def stat_buffer(self, b, c):
-        if os.environ.get("FMI_EPILOGUE_STATS") == "0":
-            return None
-        return torch.empty((b, c, 2), dtype=torch.float64, device=self.dev)
 
 
 def decoder_forward(gen, x, f_e=None, mask=None, taps=None, pool_to=None, z=None):
@@ -334,7 +317,6 @@ def decoder_forward(gen, x, f_e=None, mask=None, taps=None, pool_to=None, z=None
             else:
                 zx, zc, _, _ = _res_block(k, blk, zx, zc, b, h, w)
     image = None
-    x_sums = None      # statistics of the current block input, when the producing GEMM's epilogue accumulated them
     for i, blk in enumerate(blocks):
         n1, act, n2 = _block_layout(blk)
         slope = _slope(act)
@@ -347,15 +329,13 @@ def decoder_forward(gen, x, f_e=None, mask=None, taps=None, pool_to=None, z=None
         x_ptr = cat.data_ptr() + ch * esz
         # a1 = lrelu(IN(x)); h1 = conv1(a1) + b1
         a1 = k.empty(b, h, w, c_in)
-        k.norm_act(x_ptr, ctot, a1.data_ptr(), c_in, n1, b, c_in, hw, slope, sums=x_sums)
-        x_sums = None
+        k.norm_act(x_ptr, ctot, a1.data_ptr(), c_in, n1, b, c_in, hw, slope)
         h1 = k.empty(b, h, w, ch)
-        h1_sums = k.stat_buffer(b, ch) if n2 is not None else None      # IN statistics of h1 from conv1's epilogue
         k.conv(a1.data_ptr(), c_in, k.weights([(blk.conv1, False)], ch), b1, h1.data_ptr(), ch, 0, None, 0, b, c_in, ch, h, w, 0, 2,
-               round_y=0, stats=h1_sums)
+               round_y=0)
         del a1
         # a2 = lrelu(IN(h1)) into channels [0, ch) next to x
-        k.norm_act(h1.data_ptr(), ch, cat.data_ptr(), ctot, n2, b, ch, hw, slope, sums=h1_sums)
+        k.norm_act(h1.data_ptr(), ch, cat.data_ptr(), ctot, n2, b, ch, hw, slope)
         del h1
         # y = convT(a2) + b2 + convT_shortcut(x) + bs: one GEMM over [a2 | x]
         bias = b2 if bs is None else (bs if b2 is None else b2 + bs)
@@ -416,9 +396,8 @@ def decoder_forward(gen, x, f_e=None, mask=None, taps=None, pool_to=None, z=None
         else:
             ch_next = _plain(blocks[i + 1].conv1).out_channels
             nxt = k.empty(b, oh, ow, ch_next + co)
-            x_sums = k.stat_buffer(b, co) if _block_layout(blocks[i + 1])[0] is not None else None   # next block's norm1 statistics
             k.conv(cat.data_ptr(), ctot, wcat, bias, nxt.data_ptr() + ch_next * esz, ch_next + co, 0, None, 0, b, ctot, co, h, w,
-                   up_mode, 2, round_y=0, stats=x_sums)
+                   up_mode, 2, round_y=0)
             cat = nxt
             if taps is not None:
                 taps[f"decoder{i}"] = nxt[..., ch_next:].float().permute(0, 3, 1, 2).contiguous()

@@ -220,19 +220,11 @@ def _unit_forward(k: _Ctx, u: _Unit, x, b, h, w):
     k.conv(x, u.in_c, u.w1, u.b1, a1, b, u.in_c, u.depth, h, w, act=4, slope_c=u.slope, classes=9)
     oh, ow = h // u.stride, w // u.stride
     r = k.empty(b, oh, ow, u.depth)
-    # SE average pooling: per-(image, channel) sums of r from conv2's epilogue (fmi_conv_nhwc_sums); FMI_EPILOGUE_STATS=0: the
-    # separate channel_sum pass
-    sums = None
-    if u.se1 is not None and os.environ.get("FMI_EPILOGUE_STATS") != "0":
-        sums = torch.empty((b, u.depth, 2), dtype=torch.float64, device=k.dev)
-    src = k.planes(a1, b, u.depth, h, w) if u.stride == 2 else a1
-    if sums is None:
-        k.conv(src, u.depth, u.w2, u.b2, r, b, u.depth, u.depth, oh, ow, planes=int(u.stride == 2))
+    if u.stride == 2:
+        k.conv(k.planes(a1, b, u.depth, h, w), u.depth, u.w2, u.b2, r, b, u.depth, u.depth, oh, ow, planes=1)
     else:
-        _lib.check(k.lib.fmi_conv_nhwc_sums(src.data_ptr(), u.depth, ow * u.depth, oh * ow * u.depth, _p(u.w2), _p(u.b2), r.data_ptr(),
-                                            u.depth, b, u.depth, u.depth, oh, ow, 3, int(u.stride == 2), 1, k.mma, _p(sums), k.st),
-                   "fmi_conv_nhwc_sums")
-    del a1, src
+        k.conv(a1, u.depth, u.w2, u.b2, r, b, u.depth, u.depth, oh, ow)
+    del a1
     sub = (u.stride * u.in_c, u.stride * w * u.in_c, h * w * u.in_c)      # x[:, ::s, ::s, :]
     if u.ws is None:
         sc, sc_str = x, sub
@@ -243,14 +235,10 @@ def _unit_forward(k: _Ctx, u: _Unit, x, b, h, w):
     if u.se1 is None:
         gate = torch.ones((b, u.depth), dtype=torch.float32, device=k.dev)
     else:
+        scratch = torch.empty((b, 32, u.depth), dtype=torch.float32, device=k.dev)     # [b][32 slabs][C] partial sums
         mean, gate = torch.empty((2, b, u.depth), dtype=torch.float32, device=k.dev)
-        if sums is not None:
-            _lib.check(k.lib.fmi_se_gate_from_sums(_p(sums), _p(u.se1), _p(u.se2), _p(mean), _p(gate), b, u.depth, u.red, oh * ow,
-                                                   k.st), "fmi_se_gate_from_sums")
-        else:
-            scratch = torch.empty((b, 32, u.depth), dtype=torch.float32, device=k.dev)     # [b][32 slabs][C] partial sums
-            _lib.check(k.lib.fmi_se_gate_nhwc(r.data_ptr(), _p(u.se1), _p(u.se2), scratch.data_ptr(), _p(mean), _p(gate), b,
-                                              u.depth, u.red, oh * ow, k.mma, k.st), "fmi_se_gate_nhwc")
+        _lib.check(k.lib.fmi_se_gate_nhwc(r.data_ptr(), _p(u.se1), _p(u.se2), scratch.data_ptr(), _p(mean), _p(gate), b, u.depth,
+                                          u.red, oh * ow, k.mma, k.st), "fmi_se_gate_nhwc")
     y = k.empty(b, oh, ow, u.depth)
     _lib.check(k.lib.fmi_se_scale_add_nhwc(r.data_ptr(), _p(gate), sc.data_ptr(), sc_str[0], sc_str[1], sc_str[2], y.data_ptr(), b,
                                            u.depth, oh, ow, k.mma, k.st), "fmi_se_scale_add_nhwc")

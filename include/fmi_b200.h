@@ -354,22 +354,6 @@ int fmi_se_scale_add_nhwc(const void* r, const float* gate, const void* sc, int6
 int fmi_upsample_add_nhwc(const void* x, const void* add, void* y, int B, int C, int h, int w, int OH, int OW, int mma,
                           void* stream);
 
-/* Channel statistics from the producing convolution's epilogue (round 2): the *_stats / *_sums variants of the two conv entry
- * points accumulate, per (image, output channel), the sum (and for _stats the sum of squares) of the values they store into
- * stat_sums (double [B][O][2], zeroed by the call), so that InstanceNorm statistics (base_function.py:46, F.instance_norm) and the
- * SEModule's average pooling (helpers.py:66) need no pass over the tensor. fmi_instnorm_finalize turns the sums into the
- * (scale, shift) pairs fmi_norm_act_nhwc takes; fmi_se_gate_from_sums into the SE gate. Arguments as in the plain entry points. */
-int fmi_conv3x3_nhwc_stats(const void* x, int64_t x_pixel_stride, const void* wp, const float* bias, void* y,
-                           int64_t y_pixel_stride, int y_pad, int B, int I, int O, int H, int W, int mode, int act, float slope,
-                           int round_y, int mma, double* stat_sums, void* stream);
-int fmi_instnorm_finalize(const double* sums, const float* gamma, const float* beta, float* scale_shift, int B, int C, int HW,
-                          float eps, void* stream);
-int fmi_conv_nhwc_sums(const void* x, int64_t x_pixel_stride, int64_t x_row_stride, int64_t x_img_stride, const void* wp,
-                       const float* bias, void* y, int64_t y_pixel_stride, int B, int I, int O, int H, int W, int ksize,
-                       int planes, int round_y, int mma, double* stat_sums, void* stream);
-int fmi_se_gate_from_sums(const double* sums, const float* w1, const float* w2, float* mean, float* gate, int B, int C, int R,
-                          int HW, void* stream);
-
 /* k x k mean (k = 2 or 4) of fp32 planes [planes][H][W] -> [planes][H/k][W/k]: the exact case of the generators' final
  * AdaptiveAvgPool2d (modules/psp/psp.py:33,113-114 `face_pool` 1024^2 -> 256^2; modules/model.py:79,111). */
 int fmi_avgpool_planes(const float* x, float* y, int64_t planes, int H, int W, int k, void* stream);

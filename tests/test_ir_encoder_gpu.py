@@ -191,61 +191,3 @@ def test_whole_encoder_matches_cudnn_formulation(mode, monkeypatch, use_ref):
     assert got.shape == want.shape == (2, 18, 512)
     assert n1 - n0 > 100 and n1 - n0 > (n2 - n1) + 80, (n1 - n0, n2 - n1)
     assert rel_err(got, want) <= (2e-3 if mode == "tf32" else 2e-2), rel_err(got, want)
-
-
-@pytest.mark.parametrize("b,i,o,h,w,stride", [(2, 64, 64, 20, 24, 1), (3, 128, 256, 16, 16, 1), (2, 64, 128, 16, 24, 2), (1, 32, 512, 9, 7, 1)])
-def test_conv_epilogue_channel_sums(mode, b, i, o, h, w, stride):
-    """fmi_conv_nhwc_sums: the per-(image, channel) sums of the stored output, accumulated by the GEMM epilogue (the SEModule's
-    average pooling without a pass over the tensor), equal the sums of the tensor it wrote."""
-    from face_mask_inpaint_b200 import _lib
-    PF, k = _ctx()
-    g = torch.Generator().manual_seed(31 + b)
-    x = torch.randn(b, i, h, w, generator=g).to(k.dev)
-    wt = (torch.randn(o, i, 3, 3, generator=g) / (3 * i ** 0.5)).to(k.dev)
-    bias = torch.randn(o, generator=g).to(k.dev)
-    xs = _nhwc(PF, k, x)
-    oh, ow = h // stride, w // stride
-    y = k.empty(b, oh, ow, o)
-    sums = torch.full((b, o, 2), float("nan"), dtype=torch.float64, device=k.dev)
-    src = k.planes(xs, b, i, h, w) if stride == 2 else xs
-    _lib.check(k.lib.fmi_conv_nhwc_sums(src.data_ptr(), i, ow * i, oh * ow * i, PF._taps(wt, k.mma).data_ptr(), bias.data_ptr(),
-                                        y.data_ptr(), o, b, i, o, oh, ow, 3, int(stride == 2), 1, k.mma, sums.data_ptr(), k.st),
-               "fmi_conv_nhwc_sums")
-    want = F.conv2d(_nchw(xs), PF._taps(wt, k.mma).float().reshape(3, 3, o, i).permute(2, 3, 0, 1), bias, stride=stride, padding=1)
-    assert rel_err(_nchw(y), want) <= TOL[mode]
-    # the sums are of the values the epilogue holds BEFORE rounding to the operand type; compare with the fp32 reference
-    assert rel_err(sums[..., 0].float(), want.sum(dim=(2, 3))) <= (2e-3 if mode == "tf32" else 2e-2)
-
-
-@pytest.mark.parametrize("case", [(2, 64, 32, 12, 16, 0), (2, 96, 32, 16, 16, 3), (1, 192, 64, 8, 12, 2)])
-def test_conv3x3_epilogue_instnorm_statistics(mode, case):
-    """fmi_conv3x3_nhwc_stats (plain conv, merged-parity transposed conv, per-class transposed conv): sum and sum of squares per
-    (image, channel) from the epilogue == those of the stored tensor; fmi_instnorm_finalize == F.instance_norm's scale / shift."""
-    from face_mask_inpaint_b200 import _lib
-    PF, k = _ctx()
-    b, i, o, h, w, conv_mode = case
-    g = torch.Generator().manual_seed(41 + conv_mode)
-    x = torch.randn(b, i, h, w, generator=g).to(k.dev)
-    up = conv_mode in (2, 3)
-    wt = (torch.randn(i, o, 3, 3, generator=g) if up else torch.randn(o, i, 3, 3, generator=g)).to(k.dev) / (3 * i ** 0.5)
-    bias = torch.randn(o, generator=g).to(k.dev)
-    xs = _nhwc(PF, k, x)
-    lib = k.lib
-    rows = 4 * o if conv_mode == 3 else o
-    wp = torch.zeros((4 if conv_mode == 3 else 9, rows, i), dtype=k.dt, device=k.dev)
-    _lib.check(lib.fmi_conv_weight_prep(wt.contiguous().data_ptr(), wp.data_ptr(), o, i, int(up), rows, i, 0, int(conv_mode == 3), 3,
-                                        k.mma, k.st), "fmi_conv_weight_prep")
-    oh, ow = (2 * h, 2 * w) if up else (h, w)
-    y = k.empty(b, oh, ow, o)
-    sums = torch.full((b, o, 2), float("nan"), dtype=torch.float64, device=k.dev)
-    _lib.check(lib.fmi_conv3x3_nhwc_stats(xs.data_ptr(), i, wp.data_ptr(), bias.data_ptr(), y.data_ptr(), o, 0, b, i, o, h, w,
-                                          conv_mode, 2, 0.0, 0, k.mma, sums.data_ptr(), k.st), "fmi_conv3x3_nhwc_stats")
-    yf = _nchw(y).double()
-    assert rel_err(sums[..., 0], yf.sum(dim=(2, 3))) <= 1e-4 and rel_err(sums[..., 1], (yf * yf).sum(dim=(2, 3))) <= 1e-4
-    gamma, beta = torch.rand(o, device=k.dev) + 0.5, torch.randn(o, device=k.dev)
-    ss = torch.empty(b, o, 2, device=k.dev)
-    _lib.check(lib.fmi_instnorm_finalize(sums.data_ptr(), gamma.data_ptr(), beta.data_ptr(), ss.data_ptr(), b, o, oh * ow, 1e-5, k.st),
-               "fmi_instnorm_finalize")
-    got = _nchw(y) * ss[..., 0].view(b, o, 1, 1) + ss[..., 1].view(b, o, 1, 1)
-    want = F.instance_norm(_nchw(y), weight=gamma, bias=beta, eps=1e-5)
-    assert rel_err(got, want) <= 1e-4

@@ -139,18 +139,3 @@ def test_composite_fwd_bwd(shape, dtype):
     assert rel_err(sd.grad, sr.grad) <= tol and rel_err(rd.grad, rr.grad) <= tol
     m_got = ops.scale_img(mask.to(DEV), (h, w))
     assert rel_err(m_got, O.scale_img(mask, (h, w))) <= 2e-6
-
-
-@pytest.mark.parametrize("k,shape", [(4, (2, 3, 64, 96)), (2, (1, 5, 32, 40)), (4, (8, 3, 1024, 1024))])
-def test_adaptive_avg_pool_exact_ratio(k, shape):
-    """face_pool (psp.py:33,113-114) / ReferenceFill.pool (model.py:79,111): the exact k x k case on fmi_avgpool_planes."""
-    from face_mask_inpaint_b200 import _lib, ops
-    x = torch.randn(*shape, device="cuda")
-    n0 = _lib.load().fmi_kernel_launch_count()
-    got = ops.adaptive_avg_pool(x, (shape[2] // k, shape[3] // k))
-    assert _lib.load().fmi_kernel_launch_count() == n0 + 1
-    want = torch.nn.functional.adaptive_avg_pool2d(x, (shape[2] // k, shape[3] // k))
-    assert got.shape == want.shape and float((got - want).abs().max()) <= 1e-6
-    # a ratio the kernel does not take stays on ATen
-    odd = ops.adaptive_avg_pool(x[:, :, :60, :60], (20, 20))
-    assert torch.equal(odd, torch.nn.functional.adaptive_avg_pool2d(x[:, :, :60, :60], (20, 20)))
