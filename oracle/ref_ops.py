@@ -356,3 +356,51 @@ def example_guided_attention_rows(src_mask, src_feature, ref_feature, conv_weigh
     m = src_mask.reshape(n, 1, -1)[:, :, rows]
     flow = (1 - m) * ref_att + m * ref_feature.reshape(n, c, -1)[:, :, rows]          # :34
     return torch.cat([flow, src_att], dim=1)                                          # :36
+
+
+# --------------------------------------------------------------------------------------------
+# f2  pSp encoder pieces: IR-SE unit, map2style head, FPN add — eval mode
+# --------------------------------------------------------------------------------------------
+def batch_norm_eval(x, weight, bias, mean, var, eps=1e-5):
+    """nn.BatchNorm2d in eval mode (running statistics): modules/psp/encoders/helpers.py:107,114."""
+    return F.batch_norm(x, mean, var, weight, bias, False, 0.0, eps)
+
+
+def se_module(x, fc1_w, fc2_w):
+    """modules/psp/encoders/helpers.py:56-74 — x * sigmoid(fc2(relu(fc1(avgpool(x)))))."""
+    m = x.mean(dim=(2, 3), keepdim=True)
+    return x * torch.sigmoid(F.conv2d(torch.relu(F.conv2d(m, fc1_w)), fc2_w))
+
+
+def bottleneck_ir_se(x, sd, stride):
+    """modules/psp/encoders/helpers.py:97-119 with the module's state_dict `sd` (keys as the reference names them:
+    res_layer.{0,1,2,3,4,5.fc1,5.fc2}, shortcut_layer.{0,1}); shortcut = MaxPool2d(1, stride) when in_channel == depth."""
+    bn = lambda t, p: batch_norm_eval(t, sd[f"{p}.weight"], sd[f"{p}.bias"], sd[f"{p}.running_mean"], sd[f"{p}.running_var"])
+    r = bn(x, "res_layer.0")
+    r = F.conv2d(r, sd["res_layer.1.weight"], None, 1, 1)
+    r = F.prelu(r, sd["res_layer.2.weight"])
+    r = F.conv2d(r, sd["res_layer.3.weight"], None, stride, 1)
+    r = bn(r, "res_layer.4")
+    if "res_layer.5.fc1.weight" in sd:
+        r = se_module(r, sd["res_layer.5.fc1.weight"], sd["res_layer.5.fc2.weight"])
+    if "shortcut_layer.0.weight" in sd:
+        sc = bn(F.conv2d(x, sd["shortcut_layer.0.weight"], None, stride), "shortcut_layer.1")
+    else:
+        sc = x[:, :, ::stride, ::stride]                     # MaxPool2d(kernel 1, stride)
+    return r + sc
+
+
+def gradual_style_block(x, sd, n_convs):
+    """modules/psp/encoders/psp_encoders.py:13-37 — n x [Conv2d(3, stride 2, padding 1) + LeakyReLU(0.01)] down to 1x1, then
+    EqualLinear (stylegan2/model.py:135-171: F.linear(x, weight * scale, bias * lr_mul), scale = 1/sqrt(in), lr_mul = 1)."""
+    for i in range(n_convs):
+        x = F.leaky_relu(F.conv2d(x, sd[f"convs.{2 * i}.weight"], sd[f"convs.{2 * i}.bias"], 2, 1), 0.01)
+    x = x.view(-1, x.shape[1])
+    w = sd["linear.weight"]
+    return F.linear(x, w * (1.0 / math.sqrt(w.shape[1])), sd["linear.bias"])
+
+
+def upsample_add(x, y):
+    """modules/psp/encoders/psp_encoders.py:83-98."""
+    return F.interpolate(x, size=y.shape[-2:], mode="bilinear", align_corners=True) + y
+

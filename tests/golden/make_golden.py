@@ -297,10 +297,53 @@ def gen_refpsp(size=256):
                         n_params=np.array(sum(p.numel() for p in net.parameters())))
 
 
+def gen_psp_encoder_pieces():
+    """bottleneck_IR_SE / bottleneck_IR units, a GradualStyleBlock and _upsample_add of the reference's own encoder classes
+    (modules/psp/encoders/helpers.py:77-119, psp_encoders.py:13-37,83-98), eval mode, randomised BatchNorm statistics."""
+    from modules.psp.encoders import helpers, psp_encoders
+    g = torch.Generator().manual_seed(300)
+    out = {}
+
+    def rand_bn(m):
+        for mod in m.modules():
+            if isinstance(mod, nn.BatchNorm2d):
+                mod.running_mean.copy_(0.5 * torch.randn(mod.running_mean.shape, generator=g))
+                mod.running_var.copy_(torch.rand(mod.running_var.shape, generator=g) + 0.5)
+                mod.weight.data.copy_(1 + 0.3 * torch.randn(mod.weight.shape, generator=g))
+                mod.bias.data.copy_(0.3 * torch.randn(mod.bias.shape, generator=g))
+
+    for tag, cls, cin, depth, stride in [("se_s1", helpers.bottleneck_IR_SE, 32, 32, 1), ("se_s2", helpers.bottleneck_IR_SE, 32, 64, 2),
+                                         ("se_pool", helpers.bottleneck_IR_SE, 32, 32, 2), ("ir_s1", helpers.bottleneck_IR, 16, 16, 1)]:
+        torch.manual_seed(301)
+        unit = cls(cin, depth, stride).eval()
+        rand_bn(unit)
+        x = torch.randn(2, cin, 12, 10, generator=g)
+        with torch.no_grad():
+            y = unit(x)
+        out[f"{tag}.x"], out[f"{tag}.y"], out[f"{tag}.stride"] = np_(x), np_(y), np.array(stride)
+        for k, v in unit.state_dict().items():
+            if "num_batches" not in k:
+                out[f"{tag}.sd.{k}"] = np_(v)
+    torch.manual_seed(302)
+    blk = psp_encoders.GradualStyleBlock(32, 32, 8).eval()
+    x = torch.randn(3, 32, 8, 8, generator=g)
+    with torch.no_grad():
+        out["head.x"], out["head.y"] = np_(x), np_(blk(x))
+    for k, v in blk.state_dict().items():
+        out[f"head.sd.{k}"] = np_(v)
+    a, b = torch.randn(2, 8, 5, 7, generator=g), torch.randn(2, 8, 10, 13, generator=g)
+    out["fpn.x"], out["fpn.y"] = np_(a), np_(b)
+    out["fpn.out"] = np_(psp_encoders.GradualStyleEncoder._upsample_add(None, a, b))
+    np.savez_compressed(OUT / "psp_encoder.npz", **out)
+    print("psp_encoder.npz", len(out), "arrays")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    if len(sys.argv) > 1 and sys.argv[1] in ("picnet", "refpsp", "picnet_blocks", "ssim"):
-        if sys.argv[1] == "picnet":
+    if len(sys.argv) > 1 and sys.argv[1] in ("picnet", "refpsp", "picnet_blocks", "ssim", "psp_encoder"):
+        if sys.argv[1] == "psp_encoder":
+            gen_psp_encoder_pieces()
+        elif sys.argv[1] == "picnet":
             gen_picnet()
         elif sys.argv[1] == "picnet_blocks":
             gen_picnet_blocks()
@@ -318,5 +361,6 @@ if __name__ == "__main__":
     gen_picnet_blocks()
     gen_ssim()
     gen_refpsp()
+    gen_psp_encoder_pieces()
     for f in sorted(OUT.glob("*.npz")):
         print(f.name, f.stat().st_size)

@@ -191,3 +191,26 @@ def test_whole_encoder_matches_cudnn_formulation(mode, monkeypatch, use_ref):
     assert got.shape == want.shape == (2, 18, 512)
     assert n1 - n0 > 100 and n1 - n0 > (n2 - n1) + 80, (n1 - n0, n2 - n1)
     assert rel_err(got, want) <= (2e-3 if mode == "tf32" else 2e-2), rel_err(got, want)
+
+
+@pytest.mark.parametrize("tag", ["se_s1", "se_s2", "se_pool", "ir_s1"])
+def test_ir_unit_kernels_match_the_reference_golden(mode, tag):
+    """One bottleneck_IR(_SE) unit on the kernels (psp_fast._unit_forward) against the output the REFERENCE's own class produced
+    for the same weights and input (tests/golden/psp_encoder.npz, recorded by make_golden.py from /root/reference)."""
+    import numpy as np
+    from face_mask_inpaint_b200.modules import psp as P
+    PF, k = _ctx()
+    g = {kk: torch.from_numpy(v) for kk, v in np.load(ROOT / "tests" / "golden" / "psp_encoder.npz").items()}
+    sd = {kk[len(tag) + 4:]: v for kk, v in g.items() if kk.startswith(f"{tag}.sd.")}
+    stride = int(g[f"{tag}.stride"])
+    cin, depth = sd["res_layer.1.weight"].shape[1], sd["res_layer.1.weight"].shape[0]
+    unit = P._IRUnit(cin, depth, stride, "res_layer.5.fc1.weight" in sd).eval()
+    unit.load_state_dict(sd, strict=False)
+    unit = unit.to(k.dev)
+    u = PF._prep_unit(unit, k.mma)
+    x = g[f"{tag}.x"].to(k.dev)
+    b, _, h, w = x.shape
+    y, oh, ow = PF._unit_forward(k, u, _nhwc(PF, k, x), b, h, w)
+    want = g[f"{tag}.y"]
+    assert (oh, ow) == tuple(want.shape[-2:])
+    assert rel_err(_nchw(y), want) <= (2e-3 if mode == "tf32" else 2e-2)

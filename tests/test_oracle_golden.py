@@ -152,3 +152,51 @@ def test_ssim_matches_reference():
     assert abs(float(O.ssim(g["a"], g["b"])) - float(g["ssim"])) <= 1e-6
     assert abs(float(O.ssim(g["a"], g["a"])) - float(g["ssim_same"])) <= 1e-6 and float(g["ssim_same"]) > 0.999999
     assert rel_err(O.ssim(g["a"], g["b"], size_average=False), g["ssim_per_image"]) <= 1e-6
+
+
+# ---- f2: pSp encoder pieces, recorded from the reference's own bottleneck_IR(_SE), GradualStyleBlock and _upsample_add
+def _sub(g, prefix):
+    return {k[len(prefix):]: v for k, v in g.items() if k.startswith(prefix)}
+
+
+@pytest.mark.parametrize("tag", ["se_s1", "se_s2", "se_pool", "ir_s1"])
+def test_ir_se_unit_matches_reference(tag):
+    g = load("psp_encoder.npz")
+    got = O.bottleneck_ir_se(g[f"{tag}.x"], _sub(g, f"{tag}.sd."), int(g[f"{tag}.stride"]))
+    assert got.shape == g[f"{tag}.y"].shape and rel_err(got, g[f"{tag}.y"]) <= 1e-6
+
+
+def test_gradual_style_block_and_fpn_add_match_reference():
+    g = load("psp_encoder.npz")
+    assert rel_err(O.gradual_style_block(g["head.x"], _sub(g, "head.sd."), 3), g["head.y"]) <= 1e-6
+    assert rel_err(O.upsample_add(g["fpn.x"], g["fpn.y"]), g["fpn.out"]) <= 1e-6
+
+
+@pytest.mark.parametrize("tag", ["se_s1", "se_s2", "se_pool", "ir_s1"])
+def test_folded_unit_of_the_kernel_path_matches_the_golden(tag, monkeypatch):
+    """The BatchNorm folding of modules/psp_fast.py (border-class bias, per-output scale) applied to the GOLDEN unit's weights and
+    evaluated densely on CPU reproduces the reference's own output: ties the host-side algebra to the reference, not only to
+    this package's mirror (tests/test_psp_fast_cpu.py)."""
+    from face_mask_inpaint_b200.modules import psp as P
+    from face_mask_inpaint_b200.modules import psp_fast as PF
+    from test_psp_fast_cpu import _conv_from_taps, _planes_conv
+    monkeypatch.setattr(PF, "_operand", lambda w, mma: w.contiguous())
+    g = load("psp_encoder.npz")
+    sd = _sub(g, f"{tag}.sd.")
+    stride = int(g[f"{tag}.stride"])
+    cin, depth = sd["res_layer.1.weight"].shape[1], sd["res_layer.1.weight"].shape[0]
+    unit = P._IRUnit(cin, depth, stride, "res_layer.5.fc1.weight" in sd).eval()
+    unit.load_state_dict(sd, strict=False)
+    u = PF._prep_unit(unit, 0)
+    x = g[f"{tag}.x"]
+    with torch.no_grad():
+        a1 = _conv_from_taps(x, u.w1, u.b1)
+        a1 = torch.where(a1 > 0, a1, a1 * u.slope.view(1, -1, 1, 1))
+        r = _planes_conv(a1, u.w2, u.b2) if stride == 2 else _conv_from_taps(a1, u.w2, u.b2)
+        xs = x[:, :, ::stride, ::stride]
+        sc = xs if u.ws is None else _conv_from_taps(xs, u.ws, u.bs)
+        if u.se1 is not None:
+            gate = torch.sigmoid(torch.nn.functional.linear(torch.relu(torch.nn.functional.linear(r.mean(dim=(2, 3)), u.se1)), u.se2))
+            r = r * gate.view(*gate.shape, 1, 1)
+        got = r + sc
+    assert rel_err(got, g[f"{tag}.y"]) <= 2e-5
