@@ -727,6 +727,89 @@ extern "C" int fmi_conv_weight_prep_sn(const float* w_bar, float* u, float* v, f
   return fmi_launched("conv_weight_prep_sn");
 }
 
+// ---- SpectralNorm in TRAINING (external_function.py:30-42): the same power iteration, then the plain weight w = w_bar / sigma in
+// the parameter's own layout for the framework's convolution, and its backward. With u, v held constant (they are updated from
+// .data) sigma = u^T W v, so  dL/dW_bar = (g - <g, w> u v^T) / sigma  for an upstream gradient g of w.
+namespace {
+__global__ void __launch_bounds__(256) sn_divide_kernel(const float* __restrict__ w, float* __restrict__ w_out,
+                                                        const float* __restrict__ u_raw, float* __restrict__ u,
+                                                        const float* __restrict__ v, float* __restrict__ snap, int Hh, int Wd) {
+  __shared__ float red[8];
+  float q = 0.f;
+  for (int i = threadIdx.x; i < Hh; i += 256) q = fmaf(u_raw[i], u_raw[i], q);
+  const float n2 = block_sum_256(q, red);
+  const float inv = 1.f / (sqrtf(n2) + 1e-12f);
+  const float sigma = n2 * inv;                       // u . u_raw with u = u_raw * inv
+  if (blockIdx.x == 0) {
+    for (int i = threadIdx.x; i < Hh; i += 256) {
+      const float un = u_raw[i] * inv;
+      u[i] = un;
+      snap[i] = un;
+    }
+    for (int j = threadIdx.x; j < Wd; j += 256) snap[Hh + j] = v[j];
+    if (threadIdx.x == 0) snap[Hh + Wd] = sigma;
+  }
+  const int64_t total = (int64_t)Hh * Wd;
+  const float rs = 1.f / sigma;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x)
+    w_out[e] = w[e] * rs;
+}
+
+__global__ void __launch_bounds__(256) sn_bwd_dot_kernel(const float* __restrict__ g, const float* __restrict__ w_out,
+                                                         float* __restrict__ dot, int64_t total) {
+  __shared__ float red[8];
+  float a = 0.f;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x)
+    a = fmaf(g[e], w_out[e], a);
+  a = block_sum_256(a, red);
+  if (threadIdx.x == 0) atomicAdd(dot, a);
+}
+
+__global__ void __launch_bounds__(256) sn_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ snap,
+                                                           const float* __restrict__ dot, float* __restrict__ grad, int Hh, int Wd) {
+  const int64_t total = (int64_t)Hh * Wd;
+  const float rs = 1.f / snap[Hh + Wd], d = *dot;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(e / Wd), c = (int)(e - (int64_t)r * Wd);
+    grad[e] = (g[e] - d * snap[r] * snap[Hh + c]) * rs;
+  }
+}
+}  // namespace
+
+// One power iteration on (w_bar [Hh][Wd], u [Hh], v [Wd]) — u, v updated in place as SpectralNorm._update_u_v does — and
+// w_out = w_bar / sigma (same layout). snap [Hh + Wd + 1] receives the new u, the new v and sigma for the backward.
+// scratch: (Wd + Hh) floats.
+extern "C" int fmi_spectral_norm_fwd(const float* w_bar, float* u, float* v, float* scratch, float* w_out, float* snap, int Hh,
+                                     int Wd, void* stream) {
+  FMI_REQUIRE(w_bar && u && v && scratch && w_out && snap && Hh >= 1 && Wd >= 1, "spectral_norm_fwd: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* v_raw = scratch;
+  float* u_raw = scratch + Wd;
+  sn_wt_u_kernel<<<(Wd + 127) / 128, 128, 0, st>>>(w_bar, u, v_raw, Hh, Wd);
+  int rc = fmi_launched("sn_wt_u");
+  if (rc) return rc;
+  sn_w_v_kernel<<<(Hh + 7) / 8, 256, 0, st>>>(w_bar, v_raw, v, u_raw, Hh, Wd);
+  rc = fmi_launched("sn_w_v");
+  if (rc) return rc;
+  sn_divide_kernel<<<stream_grid((int64_t)Hh * Wd, 256 * 4), 256, 0, st>>>(w_bar, w_out, u_raw, u, v, snap, Hh, Wd);
+  return fmi_launched("sn_divide");
+}
+
+// grad_w_bar = (g - <g, w_out> u v^T) / sigma with (u, v, sigma) = snap of the forward; dot: one zero-initialised float.
+extern "C" int fmi_spectral_norm_bwd(const float* g, const float* w_out, const float* snap, float* dot, float* grad_w_bar, int Hh,
+                                     int Wd, void* stream) {
+  FMI_REQUIRE(g && w_out && snap && dot && grad_w_bar && Hh >= 1 && Wd >= 1, "spectral_norm_bwd: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t total = (int64_t)Hh * Wd;
+  FMI_CUDA(cudaMemsetAsync(dot, 0, sizeof(float), st));
+  const int grid = stream_grid(total, 256 * 4);
+  sn_bwd_dot_kernel<<<grid, 256, 0, st>>>(g, w_out, dot, total);
+  int rc = fmi_launched("sn_bwd_dot");
+  if (rc) return rc;
+  sn_bwd_apply_kernel<<<grid, 256, 0, st>>>(g, snap, dot, grad_w_bar, Hh, Wd);
+  return fmi_launched("sn_bwd_apply");
+}
+
 // ---- AvgPool2d(2, 2) on NHWC (the 'down' ResBlocks and the first encoder block, base_function.py:238-239, 290-298) ------
 namespace {
 template <typename OT, bool ROUND_TF32>

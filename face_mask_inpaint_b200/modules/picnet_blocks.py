@@ -11,9 +11,19 @@ from __future__ import annotations
 import torch
 from torch import nn
 
+from .. import ops
+
 
 def _l2normalize(v, eps=1e-12):
     return v / (v.norm() + eps)
+
+
+def fused_spectral_norm_ok(sn, w, u, v) -> bool:
+    """The fused SpectralNorm kernels (fmi_spectral_norm_fwd / _bwd) apply: one power iteration, CUDA fp32 contiguous
+    parameters. FMI_SN_TORCH=1 keeps the reference's ATen formulation."""
+    import os
+    return (sn.power_iterations == 1 and w.is_cuda and w.dtype == torch.float32 and w.is_contiguous() and u.is_contiguous()
+            and v.is_contiguous() and u.dtype == torch.float32 and os.environ.get("FMI_SN_TORCH") != "1")
 
 
 class SpectralNorm(nn.Module):
@@ -41,6 +51,9 @@ class SpectralNorm(nn.Module):
         u = getattr(self.module, self.name + "_u")
         v = getattr(self.module, self.name + "_v")
         w = getattr(self.module, self.name + "_bar")
+        if fused_spectral_norm_ok(self, w, u, v):      # CUDA: power iteration + division as 3 kernels, backward as 2 (ops.py)
+            setattr(self.module, self.name, ops.spectral_norm_weight(w, u, v))
+            return
         height = w.data.shape[0]
         for _ in range(self.power_iterations):
             v.data.copy_(_l2normalize(torch.mv(torch.t(w.view(height, -1).data), u.data)))

@@ -237,6 +237,45 @@ def scale_img(img, size):
     return out.to(img.dtype)
 
 
+class _SpectralNormWeight(Function):
+    """w = w_bar / sigma(w_bar) with one in-place power iteration on (u, v): SpectralNorm._update_u_v
+    (modules/pluralistic_model/external_function.py:30-42) as 3 kernels forward, 2 backward."""
+
+    @staticmethod
+    def forward(ctx, w_bar, u, v):
+        hh = w_bar.shape[0]
+        wd = w_bar.numel() // hh
+        w_out = torch.empty_like(w_bar)
+        snap = torch.empty(hh + wd + 1, dtype=torch.float32, device=w_bar.device)
+        scratch = torch.empty(hh + wd, dtype=torch.float32, device=w_bar.device)
+        _lib.check(_lib.load().fmi_spectral_norm_fwd(_ptr(w_bar), _ptr(u), _ptr(v), _ptr(scratch), _ptr(w_out), _ptr(snap), hh, wd,
+                                                     _stream()), "fmi_spectral_norm_fwd")
+        ctx.save_for_backward(w_out, snap)
+        ctx.mark_non_differentiable(u, v)
+        return w_out
+
+    @staticmethod
+    def backward(ctx, g):
+        w_out, snap = ctx.saved_tensors
+        hh = w_out.shape[0]
+        wd = w_out.numel() // hh
+        g = g.contiguous().float()
+        grad = torch.empty_like(w_out)
+        dot = torch.empty(1, dtype=torch.float32, device=g.device)
+        _lib.check(_lib.load().fmi_spectral_norm_bwd(_ptr(g), _ptr(w_out), _ptr(snap), _ptr(dot), _ptr(grad), hh, wd, _stream()),
+                   "fmi_spectral_norm_bwd")
+        return grad, None, None
+
+
+def spectral_norm_weight(w_bar, u, v):
+    """The normalised weight of a SpectralNorm-wrapped layer; `u`, `v` (their storage) advance by one power iteration. CUDA
+    fp32 contiguous tensors only (no CPU path)."""
+    _need_cuda(w_bar, u, v)
+    if w_bar.dtype != torch.float32 or not (w_bar.is_contiguous() and u.is_contiguous() and v.is_contiguous()):
+        raise RuntimeError("fmi_b200.spectral_norm_weight: contiguous fp32 tensors only")
+    return _SpectralNormWeight.apply(w_bar, u.data, v.data)
+
+
 def adaptive_avg_pool(img, size):
     """nn.AdaptiveAvgPool2d(size) of an image batch (psp.py:33,113-114 `face_pool`; model.py:79,111). The exact k x k case
     (k = 2 or 4, fp32, inference) is fmi_avgpool_planes; anything else — other ratios, autograd — is ATen's own pooling (metric-

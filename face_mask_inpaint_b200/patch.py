@@ -309,6 +309,25 @@ def _install_picnet_decoder():
 
     net.ResEncoder.forward = res_encoder_forward
 
+    # SpectralNorm (external_function.py:16-72) on the paths that keep the reference's own block forwards (training, the
+    # discriminator): its power iteration + division — ~13 ATen launches per wrapped convolution and forward, ~160 wrapped
+    # forwards per GAN step, which left the step CPU-bound — as 3 kernels (fmi_spectral_norm_fwd), its backward as 2.
+    from . import ops
+    from .modules.picnet_blocks import fused_spectral_norm_ok
+    ext = importlib.import_module("modules.pluralistic_model.external_function")
+    plain_update = ext.SpectralNorm._update_u_v
+
+    def update_u_v(self):
+        u = getattr(self.module, self.name + "_u")
+        v = getattr(self.module, self.name + "_v")
+        w = getattr(self.module, self.name + "_bar")
+        if fused_spectral_norm_ok(self, w, u, v):
+            setattr(self.module, self.name, ops.spectral_norm_weight(w, u, v))
+        else:
+            plain_update(self)
+
+    ext.SpectralNorm._update_u_v = update_u_v
+
 
 def _blend(src, ref, full_mask):
     """mask * ref + (1 - mask) * src with the mask resized to the feature resolution (psp_encoders.py:135-138)."""

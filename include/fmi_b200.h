@@ -354,6 +354,15 @@ int fmi_se_scale_add_nhwc(const void* r, const float* gate, const void* sc, int6
 int fmi_upsample_add_nhwc(const void* x, const void* add, void* y, int B, int C, int h, int w, int OH, int OW, int mma,
                           void* stream);
 
+/* SpectralNorm in training (modules/pluralistic_model/external_function.py:30-42): one power iteration on (w_bar [Hh][Wd], u, v)
+ * — u, v updated in place — and w_out = w_bar / sigma in the parameter's own layout (3 launches instead of the reference's ~13 ATen
+ * launches per convolution and forward). snap [Hh + Wd + 1] keeps (u, v, sigma) of this call for the backward; scratch (Wd + Hh) floats.
+ * Backward (u, v constant as in the reference, sigma = u^T W v): grad_w_bar = (g - <g, w_out> u v^T) / sigma; dot: one float. */
+int fmi_spectral_norm_fwd(const float* w_bar, float* u, float* v, float* scratch, float* w_out, float* snap, int Hh, int Wd,
+                          void* stream);
+int fmi_spectral_norm_bwd(const float* g, const float* w_out, const float* snap, float* dot, float* grad_w_bar, int Hh, int Wd,
+                          void* stream);
+
 /* k x k mean (k = 2 or 4) of fp32 planes [planes][H][W] -> [planes][H/k][W/k]: the exact case of the generators' final
  * AdaptiveAvgPool2d (modules/psp/psp.py:33,113-114 `face_pool` 1024^2 -> 256^2; modules/model.py:79,111). */
 int fmi_avgpool_planes(const float* x, float* y, int64_t planes, int H, int W, int k, void* stream);

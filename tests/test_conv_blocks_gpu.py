@@ -380,3 +380,32 @@ def test_whole_generator_kernel_path_vs_cudnn_paths():
         small = m(src, ref, mask)
     assert small.shape == (2, 3, 256, 256)
     assert rel_err(small, torch.nn.functional.avg_pool2d(ours, 4)) <= 1e-5
+
+
+@pytest.mark.parametrize("shape", [(64, 32, 3, 3), (32, 96, 3, 3), (256, 128, 1, 1), (3, 32, 3, 3)])
+def test_fused_spectral_norm_forward_backward(shape):
+    """ops.spectral_norm_weight (fmi_spectral_norm_fwd / _bwd) == SpectralNorm._update_u_v of the reference
+    (external_function.py:30-42) restated in fp64 with autograd: the weight, the in-place u / v update and the gradient."""
+    from face_mask_inpaint_b200 import ops
+    g = torch.Generator().manual_seed(sum(shape))
+    w = torch.randn(*shape, generator=g)
+    hh = shape[0]
+    u = torch.nn.functional.normalize(torch.randn(hh, generator=g), dim=0)
+    v = torch.nn.functional.normalize(torch.randn(w.numel() // hh, generator=g), dim=0)
+    go = torch.randn(*shape, generator=g)
+    # reference formulation, fp64
+    wr = w.double().requires_grad_(True)
+    l2 = lambda t: t / (t.norm() + 1e-12)
+    vn = l2(torch.mv(wr.view(hh, -1).data.t(), u.double()))
+    un = l2(torch.mv(wr.view(hh, -1).data, vn))
+    sigma = un.dot(wr.view(hh, -1).mv(vn))
+    want = wr / sigma
+    want.backward(go.double())
+    # kernels
+    wd = w.cuda().requires_grad_(True)
+    ud, vd = u.cuda(), v.cuda()
+    got = ops.spectral_norm_weight(wd, ud, vd)
+    got.backward(go.cuda())
+    assert rel_err(got, want.detach().float()) <= 1e-5
+    assert rel_err(ud, un.float()) <= 1e-5 and rel_err(vd, vn.float()) <= 1e-5
+    assert rel_err(wd.grad, wr.grad.float()) <= 1e-5
