@@ -240,7 +240,10 @@ def test_res_encoder_kernel_path_matches_cudnn_fp32(kind):
     finally:
         os.environ.pop("FMI_PICNET_CUDNN", None)
         torch.backends.cudnn.allow_tf32 = old
-    assert n_c == 0 and n_o > 40
+    # the forced-cuDNN path still runs its SpectralNorm power iterations on this package's 3 kernels per wrapped convolution
+    from face_mask_inpaint_b200.modules.picnet_blocks import SpectralNorm
+    n_sn = sum(isinstance(mm, SpectralNorm) for mm in base.modules())
+    assert n_c == 3 * n_sn and n_o > 40
     assert o_f.shape == t_f.shape == (2, 128, 8, 12) and o_mu.shape == t_mu.shape == (2, 128, 8, 12)
     for got, ref_gpu, want, name in ((o_f, r_f, t_f, "features"), (o_mu, r_mu, t_mu, "mu"), (o_std, r_std, t_std, "std")):
         e, e_ref = rel_err(got, want), rel_err(ref_gpu, want)
