@@ -321,7 +321,7 @@ def _forward_record(h: Harness, name, net, call_args, kw_tensors, kw_other, dtyp
     return rec
 
 
-def _parity(h: Harness, name, mirror, call, ref_ops, tol):
+def _parity(h: Harness, name, mirror, call, ref_ops, tol, strict_too=False, full_call=None):
     """Whole-model parity of THIS run's model: the UNMODIFIED reference class (baseline/_ref) on the same GPU with the same
     weights (strict state_dict load), inputs and RNG seed, run in strict fp32 (TF32 off everywhere) = `want`; this package's
     forward = `got`. Also the reference's own default GPU execution (cuDNN TF32 allowed, PyTorch's default) against `want`, i.e.
@@ -332,7 +332,9 @@ def _parity(h: Harness, name, mirror, call, ref_ops, tol):
         return {"unavailable": "baseline/_ref is missing"}
     try:
         R.import_unpatched(ref_ops)
-        ref = (R.reference_fill() if name == "picnet_ref" else R.psp(output_size=1024)).eval()
+        import contextlib
+        with contextlib.redirect_stdout(sys.stderr):      # the reference's constructors print; stdout carries the JSON line only
+            ref = (R.reference_fill() if name == "picnet_ref" else R.psp(output_size=1024)).eval()
         ref.load_state_dict(mirror.state_dict(), strict=True)
         ref = ref.to(h.dev)
         if name == "refpsp":
@@ -346,6 +348,21 @@ def _parity(h: Harness, name, mirror, call, ref_ops, tol):
             try:
                 torch.manual_seed(5)
                 want = call(copy.deepcopy(ref), True)
+                if strict_too:      # this package under the same switch: conv blocks with 3xTF32 split operands
+                    torch.manual_seed(5)
+                    got_strict = call(copy.deepcopy(mirror), False)
+                    if full_call is not None:     # the reference's strict-fp32 GPU run timed on the workload's full batch
+                        r2 = copy.deepcopy(ref)
+                        for _ in range(2):
+                            full_call(r2, True)
+                        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+                        ev[0].record()
+                        for _ in range(5):
+                            full_call(r2, True)
+                        ev[1].record()
+                        torch.cuda.synchronize()
+                        ref_fp32_ms = ev[0].elapsed_time(ev[1]) / 5
+                        del r2
             finally:
                 torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = a, b
             n0 = h.lib.fmi_kernel_launch_count()
@@ -356,10 +373,40 @@ def _parity(h: Harness, name, mirror, call, ref_ops, tol):
                "tolerance": tol, "kernel_launches_of_the_checked_forward": int(n1 - n0),
                "how": "max|a-b|/max|b| of the output image; reference = the unmodified class from baseline/_ref on this GPU, same weights "
                       "(strict state_dict load), inputs and RNG seed; fp32 = cuDNN / cuBLAS TF32 switched off"}
+        if strict_too:
+            out["ours_strict_fp32_vs_reference_fp32"] = rel(got_strict, want)
+            if full_call is not None:
+                out["reference_fp32_gpu_ms_per_step"] = ref_fp32_ms
         del ref
         return out
     except Exception as ex:  # noqa: BLE001
         return {"unavailable": f"{type(ex).__name__}: {str(ex)[:300]}"}
+
+
+def _strict_fp32_forward(h: Harness, name, net, dev_in):
+    """The same forward under the strict-fp32 contract (torch.backends.cudnn.allow_tf32 = False, what `parity.want` is computed
+    with): this package's conv blocks switch to error-compensated 3xTF32 operands (ops.tf32_split, fmi_tf32_split3)."""
+    from face_mask_inpaint_b200.graphs import CapturedForward
+    a, b = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            for _ in range(2):
+                net(*dev_in)
+            torch.cuda.synchronize()
+            n0 = h.lib.fmi_kernel_launch_count()
+            net(*dev_in)
+            torch.cuda.synchronize()
+            launches = h.lib.fmi_kernel_launch_count() - n0
+            fwd = CapturedForward(net, *dev_in)
+            ms = h.timed(fwd.replay)
+            del fwd
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = a, b
+    bsz = WORKLOADS[name]["batch"]
+    return {"ms_per_step": ms, "value": h.world * bsz / (ms * 1e-3), "unit": "img/s", "kernel_launches_per_step": int(launches),
+            "precision": "fp32 I/O; conv blocks with error-compensated 3xTF32 operands (x = hi + lo, three exact-product terms per "
+                         "GEMM, fp32 accumulation) — selected by torch.backends.cudnn.allow_tf32 = False or FMI_PRECISION=tf32x3"}
 
 
 def ours_picnet_ref(h: Harness):
@@ -372,7 +419,9 @@ def ours_picnet_ref(h: Harness):
     parity = None
     if h.rank == 0:
         s_d, r_d, m_d = src[:2].to(h.dev), ref[:2].to(h.dev), mask[:2].to(h.dev)
-        parity = _parity(h, "picnet_ref", net, lambda m, is_ref: m(s_d, r_d, src_mask=m_d) if is_ref else m(s_d, r_d, m_d), "none", 1e-3)
+        f_d = [t.to(h.dev) for t in (src, ref, mask)]
+        parity = _parity(h, "picnet_ref", net, lambda m, is_ref: m(s_d, r_d, src_mask=m_d) if is_ref else m(s_d, r_d, m_d), "none", 1e-3,
+                         strict_too=True, full_call=lambda m, is_ref: m(f_d[0], f_d[1], src_mask=f_d[2]))
     rec = _forward_record(h, "picnet_ref", net, [src, ref, mask], {}, {}, "tf32",
                           "ReferenceFill.forward (modules/model.py:81-112): 2 ResEncoders, ExampleGuidedAttention@32^2, ResGenerator "
                           "with Auto_Attn@128^2 up to 1024^2, AdaptiveAvgPool to 256^2 — every conv block, both attentions, the "
@@ -380,6 +429,7 @@ def ours_picnet_ref(h: Harness):
     rec["precision"] = ("fp32 I/O; TF32 tensor-core operands where the reference's own GPU run has them (cuDNN allow_tf32 default) "
                         "and in the attention (hi/lo split logits), fp32 accumulation / softmax / InstanceNorm")
     rec["parity"] = parity
+    rec["strict_fp32"] = _strict_fp32_forward(h, "picnet_ref", net, [t.to(h.dev) for t in (src, ref, mask)])
     return rec
 
 

@@ -67,6 +67,9 @@ PROTOTYPES = {
     "fmi_norm_act_nhwc": (_i, [_vp, _i64, _vp, _i64, _vp, _i, _i, _i, _f, _i, _vp]),
     "fmi_output_conv_tanh": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "fmi_avgpool2_nhwc": (_i, [_vp, _i64, _vp, _i64, _i, _i, _i, _i, _i, _i, _vp]),
+    "fmi_tf32_split3": (_i, [_vp, _i64, _vp, _i64, _i, _i, _vp]),
+    "fmi_set_tf32_exact": (_i, [_i]),
+    "fmi_get_tf32_exact": (_i, []),
     "fmi_reflect_border_nhwc": (_i, [_vp, _i, _i, _i, _i, _i, _vp]),
     "fmi_conv3x3_nhwc": (_i, [_vp, _i64, _vp, _vp, _vp, _i64, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _i, _vp]),
     "fmi_conv_nhwc": (_i, [_vp, _i64, _i64, _i64, _vp, _vp, _i, _vp, _f, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i,

@@ -17,6 +17,8 @@ int fmi_check_cuda(cudaError_t e, const char* what);
 
 // Called right after every kernel launch: counts it (fmi_kernel_launch_count) and surfaces launch errors.
 int fmi_launched(const char* kernel_name);
+// fmi_set_tf32_exact: TF32-mode producers keep exact fp32 values (error-compensated 3xTF32 operands, fmi_tf32_split3)
+bool fmi_tf32_exact_on();
 
 // Optional CUDA-event timing of kernels on their launch stream (fmi_profile_enable / _collect / _dump). A scope brackets one
 // launch (or one entry point's launches) with two events and carries the ALGORITHMIC work of that launch — the FLOPs and the

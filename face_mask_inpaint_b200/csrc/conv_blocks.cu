@@ -200,7 +200,10 @@ extern "C" int fmi_conv_weight_prep(const float* weight, void* wp, int O, int I,
               "conv_weight_prep: bad arguments (O=%d I=%d O_rows=%d I_row=%d i_off=%d)", O, I, O_rows, I_row, i_off);
   const int grid = stream_grid((int64_t)O * I * T, 256);
   cudaStream_t st = (cudaStream_t)stream;
-  if (mma == FMI_MMA_TF32)
+  if (mma == FMI_MMA_TF32 && fmi_tf32_exact_on())
+    conv_weight_prep_kernel<float, false><<<grid, 256, 0, st>>>(weight, (float*)wp, O, I, transposed, O_rows, I_row, i_off,
+                                                                merged, T);
+  else if (mma == FMI_MMA_TF32)
     conv_weight_prep_kernel<float, true><<<grid, 256, 0, st>>>(weight, (float*)wp, O, I, transposed, O_rows, I_row, i_off, merged,
                                                                T);
   else
@@ -275,7 +278,11 @@ extern "C" int fmi_norm_act_nhwc(const void* x, int64_t x_pixel_stride, void* y,
   const int cap = (FMI_NUM_SMS * 16 + B - 1) / B;
   if (gx > cap) gx = cap;
   FmiProfScope prof(FMI_PROF_NORMACT, st, 3.0 * B * HW * C, 2.0 * B * HW * C * esz_of(mma));
-  if (mma == FMI_MMA_TF32)
+  if (mma == FMI_MMA_TF32 && fmi_tf32_exact_on())
+    norm_act_kernel<float, false><<<dim3(gx, B), 256, 0, st>>>((const float*)x, x_pixel_stride, (int64_t)HW * x_pixel_stride,
+                                                               (float*)y, y_pixel_stride, (int64_t)HW * y_pixel_stride,
+                                                               scale_shift, HW, C, slope);
+  else if (mma == FMI_MMA_TF32)
     norm_act_kernel<float, true><<<dim3(gx, B), 256, 0, st>>>((const float*)x, x_pixel_stride, (int64_t)HW * x_pixel_stride,
                                                               (float*)y, y_pixel_stride, (int64_t)HW * y_pixel_stride,
                                                               scale_shift, HW, C, slope);
@@ -718,7 +725,10 @@ extern "C" int fmi_conv_weight_prep_sn(const float* w_bar, float* u, float* v, f
   rc = fmi_launched("sn_w_v");
   if (rc) return rc;
   const int grid = stream_grid((int64_t)O * I * T, 256);
-  if (mma == FMI_MMA_TF32)
+  if (mma == FMI_MMA_TF32 && fmi_tf32_exact_on())
+    conv_weight_prep_sn_kernel<float, false><<<grid, 256, 0, st>>>(w_bar, (float*)wp, O, I, transposed, O_rows, I_row, i_off,
+                                                                   merged, u_raw, u, Hh, T);
+  else if (mma == FMI_MMA_TF32)
     conv_weight_prep_sn_kernel<float, true><<<grid, 256, 0, st>>>(w_bar, (float*)wp, O, I, transposed, O_rows, I_row, i_off,
                                                                   merged, u_raw, u, Hh, T);
   else
@@ -975,7 +985,54 @@ extern "C" int fmi_conv_weight_prep_sn_batch(const void* descs, int n, int max_w
   if (rc) return rc;
   int gx = (max_elems + 256 * 8 - 1) / (256 * 8);
   if (gx < 1) gx = 1;
-  if (mma == FMI_MMA_TF32) sn_batch_prep_kernel<float, true><<<dim3(gx, n), 256, 0, st>>>(d);
+  if (mma == FMI_MMA_TF32 && fmi_tf32_exact_on()) sn_batch_prep_kernel<float, false><<<dim3(gx, n), 256, 0, st>>>(d);
+  else if (mma == FMI_MMA_TF32) sn_batch_prep_kernel<float, true><<<dim3(gx, n), 256, 0, st>>>(d);
   else sn_batch_prep_kernel<__nv_bfloat16, false><<<dim3(gx, n), 256, 0, st>>>(d);
   return fmi_launched("sn_batch_prep");
+}
+
+// =====================================================================================================================
+// Error-compensated TF32 operands ("3xTF32"). kind::tf32 reads the upper 19 bits of an fp32 operand; with x = hi + lo,
+// hi = x with the low 13 mantissa bits cleared (exact in tf32) and lo = x - hi (exact in fp32, |lo| < 2^-10 |x|),
+//     x . w  =  hi_x . hi_w  +  hi_x . lo_w  +  lo_x . hi_w  +  O(2^-20 |x| |w|)
+// and every product is accumulated in fp32. The three terms are ONE implicit GEMM over three times the input channels:
+// activations [hi | hi | lo], weights [hi | lo | hi] along I — no change to the GEMM kernel, K is 3x. This is what the PICNet
+// conv blocks run when the caller asked for strict fp32 convolutions (torch.backends.cudnn.allow_tf32 = False) or
+// FMI_PRECISION=tf32x3: whole-image error vs the fp32 reference <= 1e-3 with every convolution on the tensor cores.
+// =====================================================================================================================
+namespace {
+template <int ORDER>   // 0: [hi | hi | lo] (activations), 1: [hi | lo | hi] (weights)
+__global__ void __launch_bounds__(256) tf32_split3_kernel(const float* __restrict__ x, int64_t x_stride, float* __restrict__ y,
+                                                          int64_t rows, int C) {
+  const int nvec = C >> 2;
+  const int64_t total = rows * nvec;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e / nvec;
+    const int c = (int)(e - r * nvec) << 2;
+    const float4 v = *reinterpret_cast<const float4*>(x + r * x_stride + c);
+    float4 hi, lo;
+    hi.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); lo.x = v.x - hi.x;
+    hi.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); lo.y = v.y - hi.y;
+    hi.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); lo.z = v.z - hi.z;
+    hi.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); lo.w = v.w - hi.w;
+    float* o = y + r * 3 * (int64_t)C + c;
+    *reinterpret_cast<float4*>(o) = hi;
+    *reinterpret_cast<float4*>(o + C) = ORDER ? lo : hi;
+    *reinterpret_cast<float4*>(o + 2 * (int64_t)C) = ORDER ? hi : lo;
+  }
+}
+}  // namespace
+
+// x: `rows` rows of C fp32 values, x_stride elements apart -> y [rows][3*C] fp32. order 0: [hi | hi | lo], 1: [hi | lo | hi].
+extern "C" int fmi_tf32_split3(const float* x, int64_t x_stride, float* y, int64_t rows, int C, int order, void* stream) {
+  if (rows == 0) return FMI_OK;
+  FMI_REQUIRE(x && y && rows > 0 && C >= 4 && C % 4 == 0 && x_stride >= C && x_stride % 4 == 0 && (order == 0 || order == 1) &&
+                  fmi_aligned(x, 16) && fmi_aligned(y, 16),
+              "tf32_split3: unsupported arguments (rows=%lld C=%d stride=%lld)", (long long)rows, C, (long long)x_stride);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = stream_grid(rows * (C / 4), 256 * 4);
+  FmiProfScope prof(FMI_PROF_STREAM, st, 4.0 * rows * C, 16.0 * rows * C);
+  if (order) tf32_split3_kernel<1><<<grid, 256, 0, st>>>(x, x_stride, y, rows, C);
+  else tf32_split3_kernel<0><<<grid, 256, 0, st>>>(x, x_stride, y, rows, C);
+  return fmi_launched("tf32_split3");
 }

@@ -125,6 +125,14 @@ extern "C" int fmi_version(void) { return 100; }
 
 extern "C" const char* fmi_last_error(void) { return g_err; }
 
+// ---- error-compensated TF32 ("3xTF32") switch ---------------------------------------------------------------------------------
+// Off (default): in FMI_MMA_TF32 mode the producers of GEMM operands (weight re-layouts, normalise + activate passes) round to
+// tf32. On: they keep the exact fp32 value, and the caller feeds each GEMM the split operands of fmi_tf32_split3 instead.
+static std::atomic<int> g_tf32_exact{0};
+bool fmi_tf32_exact_on() { return g_tf32_exact.load(std::memory_order_relaxed) != 0; }
+extern "C" int fmi_set_tf32_exact(int on) { return g_tf32_exact.exchange(on ? 1 : 0); }
+extern "C" int fmi_get_tf32_exact(void) { return g_tf32_exact.load(); }
+
 extern "C" int fmi_device_check(void) {
   int dev = -1;
   FMI_CUDA(cudaGetDevice(&dev));

@@ -94,8 +94,10 @@ def supported(gen, x) -> bool:
     # Operand precision follows the switch that governs the reference's own GPU numerics for these convolutions: with
     # torch.backends.cudnn.allow_tf32 (PyTorch's default) cuDNN runs them with TF32 operands, and so do the kernels here
     # (measured on the README configuration, image vs strict fp32: cuDNN-TF32 1.4e-2, these kernels 1.0e-2). With TF32
-    # switched off the caller asked for strict fp32 convolutions: those stay on cuDNN.
-    if not torch.backends.cudnn.allow_tf32 and ops.mma_mode(torch.float32) != _lib.MMA_BF16:
+    # switched off the caller asked for strict fp32 convolutions: those run with error-compensated 3xTF32 operands
+    # (ops.tf32_split, fmi_tf32_split3: fp32-class products on the same GEMM kernel, K tripled) unless FMI_PRECISION pins
+    # single-pass TF32, in which case they stay on cuDNN.
+    if not torch.backends.cudnn.allow_tf32 and ops.mma_mode(torch.float32) != _lib.MMA_BF16 and not ops.tf32_split():
         return False
     cached = getattr(gen, "_fmi_fast_ok", None)
     if cached is None:
@@ -205,12 +207,16 @@ class _Ctx:
         self.dt = torch.float32 if self.mma == _lib.MMA_TF32 else torch.bfloat16
         self.dev = dev
         self.st = ops._stream()
+        # strict-fp32 contract: exact fp32 activations / weights, every GEMM over the split operands (fmi_tf32_split3)
+        self.x3 = self.mma == _lib.MMA_TF32 and ops.tf32_split()
+        self.lib.fmi_set_tf32_exact(int(self.x3))
+        self.rnd = 0 if self.x3 else 1
         # weight plan of the owning network (per operand type and device); None = prepare weights call by call
         self.plan = self.recording = None
         if owner is not None:
             from ..graphs import module_cache
             plans = module_cache(owner).setdefault("weight_plans", {})
-            key = (self.mma, dev.index, sig)   # sig: which convolutions this call pattern uses (e.g. with / without z)
+            key = (self.mma, dev.index, sig, self.x3)   # sig: which convolutions this call pattern uses (e.g. with / without z)
             plan = plans.get(key)
             if plan is not None and plan.ready and not plan.valid():    # parameters were moved / replaced: rebuild
                 plan = None
@@ -226,11 +232,23 @@ class _Ctx:
         if self.recording is not None:
             self.recording.finalize(self.dev, self.mma)
             self.recording = None
+        if self.x3:
+            self.lib.fmi_set_tf32_exact(0)
 
     def empty(self, *shape):
         return torch.empty(shape, dtype=self.dt, device=self.dev)
 
     def weights(self, parts, o_rows, merged=False, i_row=None):
+        """`_weights` and, under the strict-fp32 contract, its [hi | lo | hi] split along the input channels."""
+        wp = self._weights(parts, o_rows, merged, i_row)
+        if not self.x3:
+            return wp
+        t, rows, ic = wp.shape
+        wp3 = torch.empty((t, rows, 3 * ic), dtype=torch.float32, device=self.dev)
+        _lib.check(self.lib.fmi_tf32_split3(wp.data_ptr(), ic, wp3.data_ptr(), t * rows, ic, 1, self.st), "fmi_tf32_split3")
+        return wp3
+
+    def _weights(self, parts, o_rows, merged=False, i_row=None):
         """parts: [(weight tensor or conv module (possibly SpectralNorm-wrapped), transposed)] concatenated along the input
         channels -> wp [9][o_rows][sum I], or with `merged` (transposed convs, fmi_conv3x3_nhwc mode 3)
         [4 input shifts][4 parity classes * O][sum I]. A SpectralNorm conv gets its power iteration here
@@ -284,6 +302,11 @@ class _Ctx:
         return ss
 
     def conv(self, x, x_stride, wp, bias, y, y_stride, y_pad, y_nchw, nchw_c, b, i, o, h, w, mode, act, slope=0.0, round_y=1):
+        if self.x3:     # activations [hi | hi | lo] against weights [hi | lo | hi]: three exact-product terms in one GEMM
+            rows = b * ((h + 2) * (w + 2) if mode == 1 else h * w)
+            xs = torch.empty((rows, 3 * i), dtype=torch.float32, device=self.dev)
+            _lib.check(self.lib.fmi_tf32_split3(x, x_stride, xs.data_ptr(), rows, i, 0, self.st), "fmi_tf32_split3")
+            x, x_stride, i, round_y = xs.data_ptr(), 3 * i, 3 * i, 0
         _lib.check(self.lib.fmi_conv3x3_nhwc(x, x_stride, _p(wp), _p(bias), y, y_stride, y_pad, _p(y_nchw), nchw_c, b, i, o, h, w,
                                              mode, act, slope, round_y, self.mma, self.st), "fmi_conv3x3_nhwc")
 
@@ -309,7 +332,7 @@ def decoder_forward(gen, x, f_e=None, mask=None, taps=None, pool_to=None, z=None
         zblocks = [gen.generator] + [getattr(gen, f"generator{i}") for i in range(gen.L)]
         zc = z.shape[1]
         zx = k.empty(b, h, w, zc)
-        _lib.check(k.lib.fmi_nchw_to_nhwc_slice(_p(z.contiguous()), zx.data_ptr(), b, zc, h, w, zc, _lib.F32, 1, k.mma, k.st),
+        _lib.check(k.lib.fmi_nchw_to_nhwc_slice(_p(z.contiguous()), zx.data_ptr(), b, zc, h, w, zc, _lib.F32, k.rnd, k.mma, k.st),
                    "fmi_nchw_to_nhwc_slice")
         for n, blk in enumerate(zblocks):
             if n == len(zblocks) - 1:   # x += bypass(zx) + conv2(lrelu(conv1(lrelu(zx)))): both GEMMs accumulate onto x
@@ -449,8 +472,8 @@ def _enc_blocks(enc):
 def encoder_supported(enc, img) -> bool:
     if os.environ.get("FMI_PICNET_CUDNN") == "1" or torch.is_grad_enabled() or not img.is_cuda or img.dtype != torch.float32:
         return False
-    if not torch.backends.cudnn.allow_tf32 and ops.mma_mode(torch.float32) != _lib.MMA_BF16:   # see `supported`
-        return False
+    if not torch.backends.cudnn.allow_tf32 and ops.mma_mode(torch.float32) != _lib.MMA_BF16 and not ops.tf32_split():
+        return False                                                                             # see `supported`
     cached = getattr(enc, "_fmi_fast_ok", None)
     if cached is None:
         blocks, heads = _enc_blocks(enc)
@@ -500,7 +523,7 @@ def _res_block(k, blk, x, cbuf, b, h, w, exact_out=False, onto=None):
            round_y=0 if (pooled or exact_out) else 1)
     if pooled:
         yp = k.empty(b, h // 2, w // 2, co)
-        _lib.check(k.lib.fmi_avgpool2_nhwc(y.data_ptr(), co, yp.data_ptr(), co, b, co, h, w, 0 if exact_out else 1, k.mma, k.st),
+        _lib.check(k.lib.fmi_avgpool2_nhwc(y.data_ptr(), co, yp.data_ptr(), co, b, co, h, w, 0 if (exact_out or k.x3) else 1, k.mma, k.st),
                    "fmi_avgpool2_nhwc")
         return yp, co, h // 2, w // 2
     return y, co, h, w
@@ -515,7 +538,7 @@ def encoder_forward(enc, img):
     blocks, heads = _enc_blocks(enc)
     cbuf = 32                                        # the image's channels zero-padded to one 128-byte fp32 row
     x = torch.zeros((b, h, w, cbuf), dtype=k.dt, device=img.device)
-    _lib.check(k.lib.fmi_nchw_to_nhwc_slice(_p(img.contiguous()), x.data_ptr(), b, c_img, h, w, cbuf, _lib.F32, 1, k.mma, k.st),
+    _lib.check(k.lib.fmi_nchw_to_nhwc_slice(_p(img.contiguous()), x.data_ptr(), b, c_img, h, w, cbuf, _lib.F32, k.rnd, k.mma, k.st),
                "fmi_nchw_to_nhwc_slice")
     for n, blk in enumerate(blocks):
         x, cbuf, h, w = _res_block(k, blk, x, cbuf, b, h, w, exact_out=n == len(blocks) - 1)

@@ -352,9 +352,21 @@ def mma_mode(dtype: torch.dtype) -> int:
     env = os.environ.get("FMI_PRECISION", "").lower()
     if env == "bf16":
         return _lib.MMA_BF16
-    if env in ("fp32", "tf32"):
+    if env in ("fp32", "tf32", "tf32x3"):
         return _lib.MMA_TF32
     return _lib.MMA_TF32 if dtype == torch.float32 else _lib.MMA_BF16
+
+
+def tf32_split() -> bool:
+    """True when fp32 convolutions run with error-compensated 3xTF32 operands (fmi_tf32_split3) instead of single TF32: the
+    caller switched TF32 convolutions off (torch.backends.cudnn.allow_tf32 = False — the switch that makes the reference's own
+    GPU run strict fp32), or FMI_PRECISION=tf32x3. FMI_PRECISION=bf16 / tf32 / fp32 pin the single-pass modes."""
+    env = os.environ.get("FMI_PRECISION", "").lower()
+    if env == "tf32x3":
+        return True
+    if env in ("bf16", "tf32", "fp32"):
+        return False
+    return not torch.backends.cudnn.allow_tf32
 
 
 def conv1x1(x, weight, bias=None):

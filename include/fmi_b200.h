@@ -290,6 +290,19 @@ int fmi_norm_act_nhwc(const void* x, int64_t x_pixel_stride, void* y, int64_t y_
 int fmi_avgpool2_nhwc(const void* x, int64_t x_pixel_stride, void* y, int64_t y_pixel_stride, int B, int C, int H, int W,
                       int round_y, int mma, void* stream);
 
+/* Error-compensated TF32 operands ("3xTF32") for the fp32 contract of the PICNet conv blocks (the reference's strict-fp32
+ * cuDNN run, torch.backends.cudnn.allow_tf32 = False, of base_function.py:207-398). kind::tf32 reads the upper 19 bits of an
+ * fp32 operand; with x = hi + lo (hi = x with the low 13 mantissa bits cleared, lo = x - hi exactly),
+ *   x.w = hi_x.hi_w + hi_x.lo_w + lo_x.hi_w + O(2^-20 |x||w|), every product accumulated in fp32,
+ * and the three terms are ONE fmi_conv3x3_nhwc call over 3*I input channels: activations [hi | hi | lo] (order 0), weights
+ * [hi | lo | hi] (order 1) along the channel axis. x: `rows` rows (pixels, or the tap x output-channel rows of wp) of C fp32
+ * values x_stride elements apart; y [rows][3*C]. C a multiple of 4.
+ * fmi_set_tf32_exact(1) makes the FMI_MMA_TF32 producers that otherwise round to tf32 (fmi_conv_weight_prep*,
+ * fmi_norm_act_nhwc) keep exact fp32 values for the split; it returns the previous setting. Process-wide, read at launch. */
+int fmi_tf32_split3(const float* x, int64_t x_stride, float* y, int64_t rows, int C, int order, void* stream);
+int fmi_set_tf32_exact(int on);
+int fmi_get_tf32_exact(void);
+
 /* ReflectionPad2d(1): fills the one-pixel border of y [B,H+2,W+2,C] from its interior. */
 int fmi_reflect_border_nhwc(void* y, int B, int C, int H, int W, int mma, void* stream);
 
