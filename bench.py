@@ -720,7 +720,7 @@ def run_reference_cpu(args, rank):
         base.update({"value": value, "ms_per_step": ms,
                      "cpu_baseline": {"value": value, "unit": "img/s", "cores": cores, "kind": "port", "sample": sample},
                      "e2e": {"value": value, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
-        print(json.dumps(base), flush=True)
+        print(json.dumps(base), file=sys.__stdout__, flush=True)
         return
     b_full = WORKLOADS[name]["batch"]
     try:
@@ -741,14 +741,14 @@ def run_reference_cpu(args, rank):
         ms = (time.perf_counter() - t0) / args.steps * 1e3
     except Exception as ex:  # noqa: BLE001
         base.update({"unavailable": f"{type(ex).__name__}: {str(ex)[:300]}"})
-        print(json.dumps(base), flush=True)
+        print(json.dumps(base), file=sys.__stdout__, flush=True)
         return
     value = b / (ms * 1e-3)
     sample = (f"{args.steps} steps x {b} of the {b_full} images of a per-GPU batch; {what}; PyTorch CPU fp32, {cores} threads")
     base.update({"value": value, "ms_per_step": ms,
                  "cpu_baseline": {"value": value, "unit": "img/s", "cores": cores, "kind": kind, "sample": sample},
                  "e2e": {"value": value, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
-    print(json.dumps(base), flush=True)
+    print(json.dumps(base), file=sys.__stdout__, flush=True)
 
 
 def run_reference_gpu(args):
@@ -777,7 +777,7 @@ def run_reference_gpu(args):
                     "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30})
     except Exception as ex:  # noqa: BLE001
         out["unavailable"] = f"{type(ex).__name__}: {str(ex)[:300]}"
-    print(json.dumps(out), flush=True)
+    print(json.dumps(out), file=sys.__stdout__, flush=True)
 
 
 def _subprocess_json(argv, timeout):
@@ -825,7 +825,7 @@ def run_ours(args):
     line = records[0]
     if len(records) > 1:
         line["records"] = records[1:]
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=sys.__stdout__, flush=True)
 
 
 def main():
@@ -839,6 +839,7 @@ def main():
     ap.add_argument("--no-reference", action="store_true", help="skip the gpu_reference / cpu_baseline sub-runs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
+    sys.stdout = sys.stderr      # library / reference chatter (constructors print) goes to stderr: stdout carries the JSON line only
     if args.impl == "reference":
         run_reference_cpu(args, rank)
     elif args.impl == "gpu_reference":

@@ -47,6 +47,7 @@ constexpr float kRescaleThreshold = 8.0f;  // log2 units
 struct AttnParams {
   int N, S, C0, C1, cv_tile;
   int d_atoms;  // 128-byte (64 x bf16) atoms per Qt component
+  int k_last;   // 16-element K slices of the last atom that hold data (1..4); the rest is zero padding
   int split;    // 1: Qt rows hold [hi | lo] bf16 components (fp32 contract), 0: hi only
   int k_stages, v_stages;
   const void* v0;
@@ -422,6 +423,32 @@ __global__ void __launch_bounds__(256) conv1x1_kernel(const TI* __restrict__ x, 
     }
     __syncthreads();
   }
+  if (OUT_QT) {
+    // Qt rows are [hi(dpad)] or, with SPLIT (= ROUND_TF32 slot of the template), [hi(dpad) | lo(dpad)]: stage the 64 x 64 tile
+    // through shared memory so that a warp writes whole rows (the direct store scattered 2-byte elements over 16 rows per
+    // instruction: 129 us for the 128^2 x 64 -> 16 query projection of the PICNet decoder, 25x its bytes)
+    __shared__ float stage[CT_S][CT_O + 1];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int o = o0 + ty * 4 + a;
+      const float bo = (bias && o < Cout) ? bias[o] : 0.f;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) stage[tx + 16 * b][ty * 4 + a] = o < Cout ? acc[a][b] + bo : 0.f;
+    }
+    __syncthreads();
+    const int ow = min(CT_O, dpad - o0);                  // columns of this tile inside the padded row
+    const int64_t rowlen = ROUND_TF32 ? 2 * dpad : dpad;
+    for (int i = threadIdx.x; i < CT_S * ow; i += 256) {
+      const int sl = i / ow, o = i - sl * ow;
+      if (s0 + sl >= S) continue;
+      const float v = stage[sl][o];
+      const TO hi = from_f32<TO>(v);
+      TO* row = y + ((int64_t)n * S + s0 + sl) * rowlen + o0 + o;
+      row[0] = hi;
+      if (ROUND_TF32) row[dpad] = from_f32<TO>(v - to_f32<TO>(hi));
+    }
+    return;
+  }
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
     const int o = o0 + ty * 4 + a;
@@ -430,19 +457,7 @@ __global__ void __launch_bounds__(256) conv1x1_kernel(const TI* __restrict__ x, 
     for (int b = 0; b < 4; ++b) {
       const int s = s0 + tx + 16 * b;
       if (s >= S) continue;
-      float v = acc[a][b] + bo;
-      if (OUT_QT) {
-        // Qt row = [hi(dpad)] or, with SPLIT (= ROUND_TF32 slot of the template), [hi(dpad) | lo(dpad)]
-        if (o < dpad) {
-          if (o >= Cout) v = 0.f;
-          const int64_t rowlen = ROUND_TF32 ? 2 * dpad : dpad;
-          const TO hi = from_f32<TO>(v);
-          y[((int64_t)n * S + s) * rowlen + o] = hi;
-          if (ROUND_TF32) y[((int64_t)n * S + s) * rowlen + dpad + o] = from_f32<TO>(v - to_f32<TO>(hi));
-        }
-      } else if (o < Cout) {
-        y[((int64_t)n * Cout + o) * S + s] = from_f32<TO>(v);
-      }
+      if (o < Cout) y[((int64_t)n * Cout + o) * S + s] = from_f32<TO>(acc[a][b] + bo);
     }
   }
 }
@@ -825,6 +840,8 @@ extern "C" int fmi_attn_fwd(const void* x, const float* wq, const float* bq, con
   }
   AttnParams prm;
   prm.N = N; prm.S = S; prm.C0 = C0; prm.C1 = C1; prm.cv_tile = pl.cv_tile; prm.d_atoms = pl.d_atoms; prm.split = pl.split;
+  prm.k_last = (pl.d - 64 * (pl.d_atoms - 1) + 15) / 16;
+  { static const bool full = [] { const char* e = getenv("FMI_ATTN_KTRIM"); return e && e[0] == '0'; }(); if (full) prm.k_last = 4; }
   prm.k_stages = pl.k_stages; prm.v_stages = pl.v_stages;
   prm.v0 = v0; prm.v1 = v1; prm.mask = mask; prm.a0 = a0; prm.a1 = a1; prm.b0 = b0; prm.b1 = b1;
   prm.masked0 = masked0; prm.masked1 = masked1;

@@ -23,7 +23,10 @@ constexpr int BS = 64;                  // keys per step
 // MMAs. tools/umma_rate.cu: with a lean issue loop a 128x64x16 MMA takes 48 clk (shared-memory operand bound), with address
 // arithmetic, predicate tests and descriptor construction between the MMAs the same instruction took 87 clk — for these small
 // MMAs the issuing thread's own instruction stream is the limiter, and the hi/lo-split logits need 12 of them per step.
-template <int D_ATOMS, int NPAIRS>
+// KLAST: 16-element K slices of the LAST atom that hold data (d = 64*(D_ATOMS-1) + 16*KLAST rounded up); the rest of the
+// 128-byte atom is zero padding and its MMAs are not issued — Auto_Attn of the PICNet decoder has d = 16: 3 instead of 12 MMAs
+// per step for the hi/lo-split logits, and every one of these small MMAs costs ~50-85 clk whatever it multiplies.
+template <int D_ATOMS, int NPAIRS, int KLAST>
 __device__ __forceinline__ void qk_step_mmas(uint32_t d_tmem, const uint64_t (&qa)[4], const uint64_t (&kb)[4], uint64_t hoff,
                                              uint32_t idesc) {
 #pragma unroll
@@ -32,10 +35,32 @@ __device__ __forceinline__ void qk_step_mmas(uint32_t d_tmem, const uint64_t (&q
 #pragma unroll
     for (int a = 0; a < D_ATOMS; ++a) {
       const uint64_t ad = qa[ca * D_ATOMS + a], bd = kb[cb * D_ATOMS + a] + hoff;
+      constexpr int kFull = 4;
+      const int ks = a == D_ATOMS - 1 ? KLAST : kFull;
       mma_ss_f16(d_tmem, ad, bd, idesc, (pr | a) ? 1u : 0u);
-      mma_ss_f16(d_tmem, ad + 2, bd + 2, idesc, 1u);
-      mma_ss_f16(d_tmem, ad + 4, bd + 4, idesc, 1u);
-      mma_ss_f16(d_tmem, ad + 6, bd + 6, idesc, 1u);
+      if (ks > 1) mma_ss_f16(d_tmem, ad + 2, bd + 2, idesc, 1u);
+      if (ks > 2) mma_ss_f16(d_tmem, ad + 4, bd + 4, idesc, 1u);
+      if (ks > 3) mma_ss_f16(d_tmem, ad + 6, bd + 6, idesc, 1u);
+    }
+  }
+}
+
+template <int NPAIRS>
+__device__ __forceinline__ void qk_step_dispatch(int d_atoms, int k_last, uint32_t d_tmem, const uint64_t (&qa)[4],
+                                                 const uint64_t (&kb)[4], uint64_t hoff, uint32_t idesc) {
+  if (d_atoms == 1) {
+    switch (k_last) {
+      case 1: qk_step_mmas<1, NPAIRS, 1>(d_tmem, qa, kb, hoff, idesc); break;
+      case 2: qk_step_mmas<1, NPAIRS, 2>(d_tmem, qa, kb, hoff, idesc); break;
+      case 3: qk_step_mmas<1, NPAIRS, 3>(d_tmem, qa, kb, hoff, idesc); break;
+      default: qk_step_mmas<1, NPAIRS, 4>(d_tmem, qa, kb, hoff, idesc); break;
+    }
+  } else {
+    switch (k_last) {
+      case 1: qk_step_mmas<2, NPAIRS, 1>(d_tmem, qa, kb, hoff, idesc); break;
+      case 2: qk_step_mmas<2, NPAIRS, 2>(d_tmem, qa, kb, hoff, idesc); break;
+      case 3: qk_step_mmas<2, NPAIRS, 3>(d_tmem, qa, kb, hoff, idesc); break;
+      default: qk_step_mmas<2, NPAIRS, 4>(d_tmem, qa, kb, hoff, idesc); break;
     }
   }
 }
@@ -203,11 +228,11 @@ __global__ void __launch_bounds__(kAttn2Threads, 1)
         const uint64_t hoff = (h & 1) ? half_tile : 0;
         const uint32_t d_s = tmem_S(b);
         if (slot == 0) {
-          if (p.split) { if (p.d_atoms == 1) qk_step_mmas<1, 3>(d_s, qa, kb[0], hoff, idesc_qk); else qk_step_mmas<2, 3>(d_s, qa, kb[0], hoff, idesc_qk); }
-          else { if (p.d_atoms == 1) qk_step_mmas<1, 1>(d_s, qa, kb[0], hoff, idesc_qk); else qk_step_mmas<2, 1>(d_s, qa, kb[0], hoff, idesc_qk); }
+          if (p.split) qk_step_dispatch<3>(p.d_atoms, p.k_last, d_s, qa, kb[0], hoff, idesc_qk);
+          else qk_step_dispatch<1>(p.d_atoms, p.k_last, d_s, qa, kb[0], hoff, idesc_qk);
         } else {
-          if (p.split) { if (p.d_atoms == 1) qk_step_mmas<1, 3>(d_s, qa, kb[1], hoff, idesc_qk); else qk_step_mmas<2, 3>(d_s, qa, kb[1], hoff, idesc_qk); }
-          else { if (p.d_atoms == 1) qk_step_mmas<1, 1>(d_s, qa, kb[1], hoff, idesc_qk); else qk_step_mmas<2, 1>(d_s, qa, kb[1], hoff, idesc_qk); }
+          if (p.split) qk_step_dispatch<3>(p.d_atoms, p.k_last, d_s, qa, kb[1], hoff, idesc_qk);
+          else qk_step_dispatch<1>(p.d_atoms, p.k_last, d_s, qa, kb[1], hoff, idesc_qk);
         }
         tc_commit(&s_full[b]);
         if (h & 1) {  // both halves of the K tile consumed

@@ -52,6 +52,7 @@ struct ConvGemmParams {
   int bias_set_stride; // per-sample weights: the bias of weight set g starts g * bias_set_stride floats into `bias` (0: one bias)
   const float* slope_c;  // act 4: PReLU, negative slope per output channel
   int prof_kind;       // FMI_PROF_* of this launch for the optional event timing (0: FMI_PROF_GEMM)
+  int st256;           // output rows are 32-byte aligned: 256-bit stores / residual loads (set by the launcher)
   int add_out;         // the epilogue adds the values already stored at the output location (residual sum: y += conv(x))
   int raw_out;         // TF32 mode: store the fp32 accumulator as is instead of rounding it to tf32 (the consumer is not an MMA,
                        // or must see the exact value: InstanceNorm statistics amplify a rounding of x by |mean| / std)
@@ -354,6 +355,39 @@ __global__ void __launch_bounds__(kGemmThreads, 2)
         }
         if (!p.out) continue;   // fused ToRGB only (the last StyledConv of an inference forward: nothing else reads y)
         const int ncols = min(32, p.n_tile - c0);
+        if (p.st256) {   // whole 32-byte sectors per lane (see st_global_v8)
+          constexpr int EPV = TF32 ? 8 : 16;   // elements per 32 bytes
+          if (p.add_out) {
+#pragma unroll
+            for (int k = 0; k < 32; k += EPV)
+              if (k < ncols) {
+                uint32_t pv[8];
+                ld_global_v8(outp + k, pv);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                  if constexpr (TF32) {
+                    f[k + q] += __uint_as_float(pv[q]);
+                  } else {
+                    const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&pv[q]);
+                    f[k + 2 * q] += __low2float(h2);
+                    f[k + 2 * q + 1] += __high2float(h2);
+                  }
+                }
+              }
+          }
+#pragma unroll
+          for (int k = 0; k < 32; k += EPV)
+            if (k < ncols) {
+              uint32_t u[8];
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                if constexpr (TF32) u[q] = p.raw_out ? __float_as_uint(f[k + q]) : f32_to_tf32_rna(f[k + q]);
+                else u[q] = pack_bf16x2(f[k + 2 * q], f[k + 2 * q + 1]);
+              }
+              st_global_v8(outp + k, u);
+            }
+          continue;
+        }
         if (p.add_out) {
           if constexpr (TF32) {
 #pragma unroll
@@ -523,6 +557,12 @@ int launch_gemm_class(const CUtensorMap& mx, const CUtensorMap& mw, ConvGemmPara
     p.out_pstride = p.O;
     p.out_rstride = (int64_t)p.OW * p.O;
     p.out_bstride = (int64_t)p.OH * p.OW * p.O;
+  }
+  {
+    static const bool st256_off = [] { const char* e = getenv("FMI_GEMM_ST256"); return e && e[0] == '0'; }();
+    const int64_t esz = TF32 ? 4 : 2;
+    p.st256 = !st256_off && p.out && ((uintptr_t)p.out & 31) == 0 && (p.out_pstride * esz) % 32 == 0 && (p.out_rstride * esz) % 32 == 0 &&
+              (p.out_bstride * esz) % 32 == 0 && p.n_tile % 16 == 0 && (!p.merge_o || p.merge_o % 16 == 0);
   }
   int grid = (int)imin64(total, (int64_t)FMI_NUM_SMS * ctas_per_sm);
   {  // debug: FMI_MODCONV_ONE_TILE=1 launches one CTA per tile (no tile loop) — must be bit-identical to the persistent run

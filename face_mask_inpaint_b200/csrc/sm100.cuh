@@ -412,4 +412,19 @@ inline int make_tensor_map(CUtensorMap* out, CUtensorMapDataType dt, int rank, c
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : (int)r;
 }
+
+// ---- 256-bit global accesses (sm_100: STG.E.ENL2.256 / LDG.E.ENL2.256). An epilogue thread owns one output pixel, so a 128-bit
+// store per lane touches 32 different lines with half a 32-byte sector each (ncu on the merged convT to 1024^2: 2x the ideal L2
+// sectors, "excessive sectors" est. speed-up 48 %); 32 bytes per lane writes whole sectors. p must be 32-byte aligned.
+__device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+               "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void ld_global_v8(const void* p, uint32_t (&v)[8]) {
+  asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "l"(p)
+               : "memory");
+}
 }  // namespace sm100
