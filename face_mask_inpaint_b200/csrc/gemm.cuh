@@ -35,14 +35,50 @@ struct GemmParams {
 constexpr int kGemmThreads = 192;
 constexpr int A_TILE_BYTES = 128 * 128;
 
-// 32 consecutive floats as 8 independent 16-byte loads
+// 32 consecutive floats as 4 independent 32-byte loads (src 32-byte aligned) or 8 16-byte loads. An epilogue thread owns one
+// row, so every access of a warp touches 32 different lines: 32 bytes per lane moves whole sectors (sm100.cuh, st_global_v8).
 __device__ __forceinline__ void ld32f(const float* __restrict__ src, float (&dst)[32]) {
+  if ((reinterpret_cast<uintptr_t>(src) & 31) == 0) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint32_t t[8];
+      sm100::ld_global_v8(src + 8 * q, t);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) dst[8 * q + e] = __uint_as_float(t[e]);
+    }
+    return;
+  }
   const float4* s4 = reinterpret_cast<const float4*>(src);
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     const float4 t = s4[q];
     dst[4 * q] = t.x; dst[4 * q + 1] = t.y; dst[4 * q + 2] = t.z; dst[4 * q + 3] = t.w;
   }
+}
+
+// ncols (a multiple of 4, <= 32) floats of x to dst (16-byte aligned): 32-byte stores when dst and ncols allow
+template <bool ROUND_TF32>
+__device__ __forceinline__ void st32f(float* __restrict__ dst, const float (&x)[32], int ncols) {
+  if ((reinterpret_cast<uintptr_t>(dst) & 31) == 0 && (ncols & 7) == 0) {
+#pragma unroll
+    for (int k = 0; k < 32; k += 8)
+      if (k < ncols) {
+        uint32_t u[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) u[e] = ROUND_TF32 ? sm100::f32_to_tf32_rna(x[k + e]) : __float_as_uint(x[k + e]);
+        sm100::st_global_v8(dst + k, u);
+      }
+    return;
+  }
+#pragma unroll
+  for (int k = 0; k < 32; k += 4)
+    if (k < ncols) {
+      if (ROUND_TF32)
+        *reinterpret_cast<float4*>(dst + k) = make_float4(__uint_as_float(sm100::f32_to_tf32_rna(x[k])), __uint_as_float(sm100::f32_to_tf32_rna(x[k + 1])),
+                                                          __uint_as_float(sm100::f32_to_tf32_rna(x[k + 2])), __uint_as_float(sm100::f32_to_tf32_rna(x[k + 3])));
+      else
+        *reinterpret_cast<float4*>(dst + k) = make_float4(x[k], x[k + 1], x[k + 2], x[k + 3]);
+    }
 }
 
 template <bool TF32>
@@ -171,16 +207,22 @@ __global__ void __launch_bounds__(kGemmThreads, 2)
               }
           }
         }
+        if (p.accumulate) {
+          if (ncols == 32) {
+            float old[32];
+            ld32f(o, old);
 #pragma unroll
-        for (int k = 0; k < 32; k += 4)
-          if (k < ncols) {
-            float4 t = make_float4(f[k], f[k + 1], f[k + 2], f[k + 3]);
-            if (p.accumulate) {
-              const float4 old = *reinterpret_cast<const float4*>(o + k);
-              t.x += old.x; t.y += old.y; t.z += old.z; t.w += old.w;
-            }
-            *reinterpret_cast<float4*>(o + k) = t;
+            for (int k = 0; k < 32; ++k) f[k] += old[k];
+          } else {
+#pragma unroll
+            for (int k = 0; k < 32; k += 4)
+              if (k < ncols) {
+                const float4 old = *reinterpret_cast<const float4*>(o + k);
+                f[k] += old.x; f[k + 1] += old.y; f[k + 2] += old.z; f[k + 3] += old.w;
+              }
           }
+        }
+        st32f<false>(o, f, ncols);
       } else {
         OT* o0 = (OT*)p.out0 + off;
         float g[32];
@@ -204,9 +246,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2)
           // P (out0) is only ever an elementwise factor of dE: keep it UNROUNDED fp32 — rounding it before forming
           // P o (dP - delta) is what dominated the gradient error for peaked attention; P^T (out1) is a GEMM operand.
           float* pf = (float*)p.out0 + off;
-#pragma unroll
-          for (int k = 0; k < 32; k += 4)
-            if (k < ncols) *reinterpret_cast<float4*>(pf + k) = make_float4(f[k], f[k + 1], f[k + 2], f[k + 3]);
+          st32f<false>(pf, f, ncols);
         } else if (p.epi == EPI_DS) {
           const float* pa = (const float*)p.aux + (int64_t)bz * p.aux_bs + (int64_t)r * p.ld_aux + cbase;
           if (ncols == 32 && fmi_aligned_dev(pa, 16)) {
@@ -219,14 +259,18 @@ __global__ void __launch_bounds__(kGemmThreads, 2)
             for (int k = 0; k < 32; ++k) f[k] = k < ncols ? pa[k] * (f[k] - rv) : 0.f;
           }
         }
-        auto store_row = [&](OT* dst, const float* x) {
+        auto store_row = [&](OT* dst, const float (&x)[32]) {
           if constexpr (TF32) {
+            st32f<true>(reinterpret_cast<float*>(dst), x, ncols);
+          } else if ((reinterpret_cast<uintptr_t>(dst) & 31) == 0 && (ncols & 15) == 0) {
 #pragma unroll
-            for (int k = 0; k < 32; k += 4)
-              if (k < ncols)
-                *reinterpret_cast<float4*>(dst + k) =
-                    make_float4(__uint_as_float(f32_to_tf32_rna(x[k])), __uint_as_float(f32_to_tf32_rna(x[k + 1])),
-                                __uint_as_float(f32_to_tf32_rna(x[k + 2])), __uint_as_float(f32_to_tf32_rna(x[k + 3])));
+            for (int k = 0; k < 32; k += 16)
+              if (k < ncols) {
+                uint32_t u[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) u[e] = pack_bf16x2(x[k + 2 * e], x[k + 2 * e + 1]);
+                st_global_v8(dst + k, u);
+              }
           } else {
 #pragma unroll
             for (int k = 0; k < 32; k += 8)
