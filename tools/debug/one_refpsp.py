@@ -22,6 +22,8 @@ with torch.no_grad():
     for _ in range(2):
         net(x, ref=ref, src_mask=mask, resize=True, randomize_noise=False)
     torch.cuda.synchronize()
+    torch.cuda.nvtx.range_push("measured")
     out = net(x, ref=ref, src_mask=mask, resize=True, randomize_noise=False)
     torch.cuda.synchronize()
+    torch.cuda.nvtx.range_pop()
 print(out.shape, float(out.abs().mean()))
