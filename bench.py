@@ -245,7 +245,33 @@ class Harness:
         return kernels, eager_ms
 
 
-def roofline_of(kernels, peaks, tensor_peak_tf, operand, traffic=None):
+_TRAFFIC_FILES = {"picnet_ref": "r02_traffic_picnet_b4.json", "refpsp": "r02_traffic_refpsp_b8.json"}
+_TRAFFIC_NAMES = {"conv_gemm": ("conv_gemm: ", "modconv_gemm_kernel"), "conv_gemm_ir": ("conv_gemm_ir: ",), "attn_fwd": ("attn_fwd2_kernel",),
+                  "norm_act": ("norm_act_kernel",), "out_conv_tanh": ("out_conv_tanh_kernel",), "instnorm_stats": ("instnorm_stats_kernel",)}
+
+
+def ncu_traffic(workload, kernel):
+    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of all launches of `kernel` in ONE step of `workload`, from the
+    committed ncu launch list of the same forward (tools/gpu_launchlists.sh -> tools/dram_summary.py -> profiles/r02_traffic_*.json;
+    same per-GPU batch as the bench). None when no capture of that workload / kernel is committed."""
+    f = ROOT / "profiles" / _TRAFFIC_FILES.get(workload, "")
+    if not f.is_file():
+        return None
+    try:
+        rows = json.loads(f.read_text())["kernels"]
+    except (ValueError, KeyError):
+        return None
+    for pat in _TRAFFIC_NAMES.get(kernel, ()):
+        hit = [r for r in rows if (r["kernel"].startswith(pat) if pat.endswith(": ") else pat in r["kernel"])]
+        if hit:
+            return {"bytes_per_step": sum(r["dram_read_bytes"] + r["dram_write_bytes"] for r in hit),
+                    "read_bytes_per_step": sum(r["dram_read_bytes"] for r in hit),
+                    "write_bytes_per_step": sum(r["dram_write_bytes"] for r in hit),
+                    "launches_per_step": sum(r["launches"] for r in hit), "source": "profiles/" + f.name}
+    return None
+
+
+def roofline_of(kernels, peaks, tensor_peak_tf, operand, traffic=None, workload=None):
     """The dominant kernel (largest summed duration per step) on its roofline. A kernel with heterogeneous launches (the
     implicit-GEMM conv serves HBM-bound 1024^2 layers and tensor-bound 64^2 layers) is put on the roofline that bounds most
     of its speed-of-light time; `sol_frac` = sum over launches of max(bytes / HBM, flops / tensor) / measured time."""
@@ -264,6 +290,10 @@ def roofline_of(kernels, peaks, tensor_peak_tf, operand, traffic=None):
            "how": "CUDA events around every launch on its own stream during an eager pass of the same step (the timed `value` "
                   "replays a CUDA graph of the same launches); algorithmic bytes = inputs once + outputs once + weights once"}
     out["frac"] = out["achieved"] / out["peak"]
+    t = ncu_traffic(workload, k["kernel"]) if traffic is None and workload else None
+    if t:
+        out["traffic"] = t["bytes_per_step"]
+        out["traffic_detail"] = t
     return out
 
 
@@ -316,7 +346,7 @@ def _forward_record(h: Harness, name, net, call_args, kw_tensors, kw_other, dtyp
            "gpu_launches": int(launches) * h.steps,
            "launch": f"one CUDA-graph replay per forward capturing {int(launches)} sm_100a kernel launches of this package",
            "eager_ms_per_step": eager_ms, "what": what,
-           "roofline": roofline_of(kernels, peaks, tensor_peak, dtype), "kernels": kernels}
+           "roofline": roofline_of(kernels, peaks, tensor_peak, dtype, workload=name), "kernels": kernels}
     del fwd
     return rec
 
@@ -497,7 +527,7 @@ def _train_record(h: Harness, name, step_dev, step_host, params, dtype, what, ex
                    "installed drop-ins, loss scalars -> host"},
            "gpu_launches": int(launches) * h.steps, "launch": f"eager: {int(launches)} sm_100a kernel launches of this package per step",
            "what": what, "trainable_params": nparam, "allreduce_bytes_per_step": nparam * 4 if h.world > 1 else 0,
-           "roofline": roofline_of(kernels, peaks, tensor_peak, dtype), "kernels": kernels}
+           "roofline": roofline_of(kernels, peaks, tensor_peak, dtype, workload=name), "kernels": kernels}
     rec.update(extra)
     return rec
 

@@ -10,6 +10,8 @@
 //  * upfirdn2d_generic_kernel — every other (up, down, pad, kernel <= 32x32, minor) configuration, gather
 //    form, taps in shared memory. (The reference launches nothing for configurations outside its six
 //    template modes; here all are computed.)
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -195,6 +197,234 @@ __global__ void __launch_bounds__(256) upfirdn2d_tile_kernel(const T* __restrict
   }
 }
 
+// ---- separable strip kernel: up = down = 1, taps <= 4x4, minor == 1 — Blur forward (pad 1,1) and backward (pad 2,2) ----------
+// The 16-FMA-per-output tile kernel above is instruction-issue bound (ncu: issue slots 75 % busy at 0.68 / 0.38 of the HBM
+// roofline in fp32 / bf16). Every blur kernel the models build is an outer product (stylegan2/model.py:19-27 make_kernel), so
+// this kernel factors the taps on the device (pivot row x pivot column / pivot; a CTA whose taps are not rank one falls back
+// to the 16-tap sum from the same staged tile) and runs a horizontal 4-tap pass on each staged row followed by a vertical
+// 4-tap pass over a rotating register window: 64 x 128 output tile per CTA, warp = 8 output rows x 128 columns, lane = 4
+// adjacent columns, per input row 2-3 LDS.128 + 16 + 16 FMA + one 16-byte store.
+// Rows of the (2H+1)-wide tensors are not 16-byte aligned: an odd-width INPUT is staged with coalesced scalar loads (any
+// alignment), an aligned one with 16-byte (fp32) / 8-byte (16-bit) vector loads from the aligned-down column (D = the offset
+// of the first needed column inside its vector, a launch constant); an odd-width OUTPUT row is bounced through a per-warp
+// shared-memory row so that the scalar stores of a warp are 32 consecutive elements.
+constexpr int kStripW = 128, kStripH = 64, kStripIH = kStripH + 3, kStripIW = 136;
+
+template <typename T> struct Vec4Of;  // 4 consecutive elements as one vector load
+template <> struct Vec4Of<float> { using type = float4; };
+template <> struct Vec4Of<__nv_bfloat16> { using type = uint2; };
+template <> struct Vec4Of<__half> { using type = uint2; };
+
+__device__ __forceinline__ float4 vec4_to_f32(float4 v, float) { return v; }
+__device__ __forceinline__ float4 vec4_to_f32(uint2 v, __nv_bfloat16) {
+  return make_float4(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u), __uint_as_float(v.y << 16),
+                     __uint_as_float(v.y & 0xffff0000u));
+}
+__device__ __forceinline__ float4 vec4_to_f32(uint2 v, __half) {
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void store4(float* dst, const float (&o)[4]) {
+  *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+}
+__device__ __forceinline__ void store4(__nv_bfloat16* dst, const float (&o)[4]) {
+  const __nv_bfloat162 a = __floats2bfloat162_rn(o[0], o[1]), b = __floats2bfloat162_rn(o[2], o[3]);
+  *reinterpret_cast<uint2*>(dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+}
+__device__ __forceinline__ void store4(__half* dst, const float (&o)[4]) {
+  const __half2 a = __floats2half2_rn(o[0], o[1]), b = __floats2half2_rn(o[2], o[3]);
+  *reinterpret_cast<uint2*>(dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+}
+
+template <typename T, bool VEC_IN, int D, bool VEC_OUT>
+__global__ void __launch_bounds__(256) upfirdn2d_blur_strip_kernel(const T* __restrict__ x, const float* __restrict__ k,
+                                                                   T* __restrict__ y, UfdParams p, int tiles_x,
+                                                                   float inv_tiles_x) {
+  static_assert(VEC_IN || D == 0, "scalar staging places the first needed column at shared-memory column 0");
+  __shared__ __align__(16) float sx[kStripIH][kStripIW];
+  __shared__ __align__(16) float sout[VEC_OUT ? 1 : 8][kStripW];
+  __shared__ float sk[16], skr[4], skc[4];
+  __shared__ int s_sep;
+  const int64_t plane = blockIdx.y;
+  const int ty_i = (int)(((float)blockIdx.x + 0.5f) * inv_tiles_x);
+  const int oy0 = ty_i * kStripH, ox0 = ((int)blockIdx.x - ty_i * tiles_x) * kStripW;
+  const int iy0 = oy0 - p.pad_y0, ix0 = ox0 - p.pad_x0 - D;  // global coordinates of sx[0][0]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  if (threadIdx.x < 16) {
+    const int ky = threadIdx.x >> 2, kx = threadIdx.x & 3;
+    float v = 0.f;
+    if (ky < p.kh && kx < p.kw) v = k[(p.kh - 1 - ky) * p.kw + (p.kw - 1 - kx)];  // flipped taps (upfirdn2d_kernel.cu:77)
+    sk[threadIdx.x] = v;
+    __syncwarp(0xffffu);
+    if (threadIdx.x == 0) {
+      int piv = 0;
+      for (int i = 1; i < 16; ++i)
+        if (fabsf(sk[i]) > fabsf(sk[piv])) piv = i;
+      const float pv = sk[piv];
+      const float inv = pv != 0.f ? 1.0f / pv : 0.f;
+      float kr[4], kc[4];
+      for (int i = 0; i < 4; ++i) {
+        kc[i] = sk[(piv >> 2) * 4 + i];
+        kr[i] = sk[i * 4 + (piv & 3)] * inv;
+      }
+      float dev = 0.f;
+      for (int i = 0; i < 16; ++i) dev = fmaxf(dev, fabsf(sk[i] - kr[i >> 2] * kc[i & 3]));
+      for (int i = 0; i < 4; ++i) {
+        skr[i] = kr[i];
+        skc[i] = kc[i];
+      }
+      s_sep = dev <= 1e-6f * fabsf(pv);
+    }
+  }
+
+  const T* xp = x + plane * p.in_h * (int64_t)p.in_w;
+  if constexpr (VEC_IN) {
+    // in_w % 4 == 0, ix0 % 4 == 0, plane base aligned: a 4-element vector is entirely inside or outside the row
+    using V = typename Vec4Of<T>::type;
+#pragma unroll 2
+    for (int r = warp; r < kStripIH; r += 8) {
+      const int iy = iy0 + r;
+      const bool row_ok = iy >= 0 && iy < p.in_h;
+      const T* row = xp + (int64_t)iy * p.in_w + ix0;
+#pragma unroll
+      for (int c = 0; c < kStripIW / 4; c += 32) {
+        const int v = c + lane;
+        if (v < kStripIW / 4) {
+          const int ix = ix0 + 4 * v;
+          float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row_ok && ix >= 0 && ix < p.in_w) f = vec4_to_f32(*reinterpret_cast<const V*>(row + 4 * v), T());
+          *reinterpret_cast<float4*>(&sx[r][4 * v]) = f;
+        }
+      }
+    }
+  } else if (iy0 >= 0 && iy0 + kStripIH <= p.in_h && ix0 >= 0 && ix0 + kStripW + 3 <= p.in_w) {
+    const T* src = xp + (int64_t)iy0 * p.in_w + ix0 + lane;
+#pragma unroll 2
+    for (int r = warp; r < kStripIH; r += 8) {
+      const T* row = src + (int64_t)r * p.in_w;
+      const T v0 = row[0], v1 = row[32], v2 = row[64], v3 = row[96];
+      sx[r][lane] = to_f32<T>(v0);
+      sx[r][lane + 32] = to_f32<T>(v1);
+      sx[r][lane + 64] = to_f32<T>(v2);
+      sx[r][lane + 96] = to_f32<T>(v3);
+      if (lane < 3) sx[r][lane + 128] = to_f32<T>(row[128]);
+    }
+  } else {
+    for (int r = warp; r < kStripIH; r += 8) {
+      const int iy = iy0 + r;
+      const bool row_ok = iy >= 0 && iy < p.in_h;
+      const T* row = xp + (int64_t)iy * p.in_w;
+#pragma unroll
+      for (int c = lane; c < kStripW + 3; c += 32) {
+        const int ix = ix0 + c;
+        float v = 0.f;
+        if (row_ok && ix >= 0 && ix < p.in_w) v = to_f32<T>(row[ix]);
+        sx[r][c] = v;
+      }
+    }
+  }
+  __syncthreads();
+
+  T* yp = y + plane * p.out_h * (int64_t)p.out_w;
+  const int ox = ox0 + 4 * lane;
+  auto store_row = [&](int a, const float (&o)[4]) {  // output row a (0..7) of this warp, columns ox .. ox + 3 of this lane
+    const int oy = oy0 + warp * 8 + a;
+    if constexpr (VEC_OUT) {
+      if (oy < p.out_h && ox < p.out_w) store4(yp + (int64_t)oy * p.out_w + ox, o);  // out_w % 4 == 0
+    } else {
+      *reinterpret_cast<float4*>(&sout[warp][4 * lane]) = make_float4(o[0], o[1], o[2], o[3]);
+      __syncwarp();
+      if (oy < p.out_h) {
+        T* dst = yp + (int64_t)oy * p.out_w + ox0 + lane;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (ox0 + 32 * j + lane < p.out_w) dst[32 * j] = from_f32<T>(sout[warp][32 * j + lane]);
+      }
+      __syncwarp();
+    }
+  };
+  constexpr int NV = D >= 2 ? 3 : 2;  // vectors that cover columns D .. D + 6 of the lane's window
+  const int r0 = warp * 8;
+  if (s_sep) {
+    float kr[4], kc[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      kr[i] = skr[i];
+      kc[i] = skc[i];
+    }
+    float acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+#pragma unroll
+    for (int r = 0; r < 11; ++r) {
+      float w[4 * NV];
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const float4 t = *reinterpret_cast<const float4*>(&sx[r0 + r][4 * lane + 4 * v]);
+        w[4 * v] = t.x; w[4 * v + 1] = t.y; w[4 * v + 2] = t.z; w[4 * v + 3] = t.w;
+      }
+      float h[4];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        h[b] = kc[0] * w[D + b];
+#pragma unroll
+        for (int kx = 1; kx < 4; ++kx) h[b] = fmaf(kc[kx], w[D + b + kx], h[b]);
+      }
+#pragma unroll
+      for (int ky = 0; ky < 4; ++ky) {
+        const int a = r - ky;  // input row r is tap ky of output row a
+        if (a < 0 || a >= 8) continue;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a & 3][b] = fmaf(kr[ky], h[b], acc[a & 3][b]);
+      }
+      if (r >= 3) {
+        store_row(r - 3, acc[(r - 3) & 3]);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[(r - 3) & 3][b] = 0.f;
+      }
+    }
+  } else {
+    for (int a = 0; a < 8; ++a) {
+      float o[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int ky = 0; ky < 4; ++ky)
+        for (int kx = 0; kx < 4; ++kx) {
+          const float t = sk[ky * 4 + kx];
+#pragma unroll
+          for (int b = 0; b < 4; ++b) o[b] = fmaf(t, sx[r0 + a + ky][4 * lane + D + b + kx], o[b]);
+        }
+      store_row(a, o);
+    }
+  }
+}
+
+template <typename T>
+int launch_blur_strip(const T* x, const float* k, T* y, const UfdParams& p, cudaStream_t st) {
+  const int tiles_x = (p.out_w + kStripW - 1) / kStripW, tiles_y = (p.out_h + kStripH - 1) / kStripH;
+  FMI_REQUIRE((int64_t)tiles_x * tiles_y < (1 << 23), "upfirdn2d: plane too large");
+  const dim3 grid(tiles_x * tiles_y, (unsigned)p.major);
+  const float inv_tx = 1.0f / (float)tiles_x;
+  const size_t vbytes = 4 * sizeof(T);
+  const bool vec_in = p.in_w % 4 == 0 && fmi_aligned(x, vbytes) && ((int64_t)p.in_h * p.in_w) % 4 == 0;
+  const bool vec_out = p.out_w % 4 == 0 && fmi_aligned(y, vbytes) && ((int64_t)p.out_h * p.out_w) % 4 == 0;
+  const int d = vec_in ? ((-p.pad_x0) % 4 + 4) % 4 : 0;
+#define FMI_STRIP_CASE(VI, DV)                                                                                               \
+  if (vec_in == VI && d == DV) {                                                                                             \
+    if (vec_out) upfirdn2d_blur_strip_kernel<T, VI, DV, true><<<grid, 256, 0, st>>>(x, k, y, p, tiles_x, inv_tx);            \
+    else upfirdn2d_blur_strip_kernel<T, VI, DV, false><<<grid, 256, 0, st>>>(x, k, y, p, tiles_x, inv_tx);                   \
+  }
+  FMI_STRIP_CASE(false, 0)
+  FMI_STRIP_CASE(true, 0)
+  FMI_STRIP_CASE(true, 1)
+  FMI_STRIP_CASE(true, 2)
+  FMI_STRIP_CASE(true, 3)
+#undef FMI_STRIP_CASE
+  return FMI_OK;
+}
+
 template <typename T, int UP, int DOWN, int OT>
 int launch_tile(const T* x, const float* k, T* y, const UfdParams& p, cudaStream_t st) {
   using F = FirTile<UP, DOWN, OT>;
@@ -247,11 +477,14 @@ extern "C" int fmi_upfirdn2d(const void* x, const float* kernel, void* y, int64_
   // live call sites: Blur fwd/bwd (1,1), Upsample of the RGB skip (up 2), its backward / Downsample (down 2)
   const bool tile = up_x == up_y && down_x == down_y && kh <= 4 && kw <= 4 && minor == 1 && major <= 65535 &&
                     ((up_x == 1 && down_x <= 2) || (up_x == 2 && down_x == 1));
+  // FMI_UPFIRDN_STRIP=0 (read per call) restores the 16-tap tile kernel for the blur configurations
+  const bool strip = tile && up_x == 1 && down_x == 1 && [] { const char* e = getenv("FMI_UPFIRDN_STRIP"); return !(e && e[0] == '0'); }();
   FMI_DISPATCH_DTYPE(dtype, T, {
     if (tile) {
       int rc;
       if (up_x == 2) rc = launch_tile<T, 2, 1, 4>((const T*)x, kernel, (T*)y, p, st);
       else if (down_x == 2) rc = launch_tile<T, 1, 2, 2>((const T*)x, kernel, (T*)y, p, st);
+      else if (strip) rc = launch_blur_strip<T>((const T*)x, kernel, (T*)y, p, st);
       else rc = launch_tile<T, 1, 1, 4>((const T*)x, kernel, (T*)y, p, st);
       if (rc) return rc;
     } else {
