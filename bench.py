@@ -502,7 +502,9 @@ def _patched_reference():
     return R
 
 
-def _train_record(h: Harness, name, step_dev, step_host, params, dtype, what, extra):
+def _train_record(h: Harness, name, step_dev, step_host, params, dtype, what, extra, timed_step=None):
+    """`step_dev`: the eager step (launch counting, per-kernel event profile); `timed_step`: what `value` times when the step was
+    captured into a CUDA graph (the same launches replayed), else the eager step itself."""
     peaks = measured_peaks()
     tensor_peak = peaks["bf16_tflops"] / (2.0 if dtype == "tf32" else 1.0)
     b = WORKLOADS[name]["batch"]
@@ -514,7 +516,7 @@ def _train_record(h: Harness, name, step_dev, step_host, params, dtype, what, ex
     torch.cuda.synchronize()
     launches = h.lib.fmi_kernel_launch_count() - n0
     sampler = ClockSampler(h.local_rank) if h.rank == 0 else None
-    ms = h.timed(step_dev)
+    ms = h.timed(timed_step or step_dev)
     ms_e2e, h2d, d2h = step_host(h)
     clocks = sampler.stop() if sampler else None
     kernels, eager_ms = h.profile(step_dev, min(h.steps, 3), tensor_peak, peaks)
@@ -525,7 +527,10 @@ def _train_record(h: Harness, name, step_dev, step_host, params, dtype, what, ex
            "e2e": {"value": h.world * b / (ms_e2e * 1e-3), "unit": "img/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                    "d2h_bytes_per_step": d2h, "api": "pinned host batch -> device, the reference's own train-step calls over the "
                    "installed drop-ins, loss scalars -> host"},
-           "gpu_launches": int(launches) * h.steps, "launch": f"eager: {int(launches)} sm_100a kernel launches of this package per step",
+           "gpu_launches": int(launches) * h.steps,
+           "launch": (f"one CUDA-graph replay per train step (graphs.CapturedStep) capturing {int(launches)} sm_100a kernel launches of "
+                      f"this package; eager step {eager_ms:.1f} ms" if timed_step is not None else
+                      f"eager: {int(launches)} sm_100a kernel launches of this package per step"),
            "what": what, "trainable_params": nparam, "allreduce_bytes_per_step": nparam * 4 if h.world > 1 else 0,
            "roofline": roofline_of(kernels, peaks, tensor_peak, dtype, workload=name), "kernels": kernels}
     rec.update(extra)
@@ -541,7 +546,8 @@ def ours_train_picnet(h: Harness):
     D = R.discriminator().to(h.dev)
     fdist.broadcast_module_state(G)
     fdist.broadcast_module_state(D)
-    optG, optD = torch.optim.Adam(G.parameters(), lr=1e-5), torch.optim.Adam(D.parameters(), lr=1e-5)
+    graph = os.environ.get("FMI_TRAIN_GRAPH", "1") != "0"
+    optG, optD = (torch.optim.Adam(m.parameters(), lr=1e-5, capturable=graph) for m in (G, D))
     nb = 0
     if h.world > 1:
         rg = fdist.GradientAllReducer([p for p in G.parameters() if p.requires_grad]).attach(optG)
@@ -567,11 +573,38 @@ def ours_train_picnet(h: Harness):
         ms = hh.timed(st)
         return ms, sum(t.numel() * t.element_size() for t in host), 20
 
-    rec = _train_record(h, "train_picnet", lambda: run(*dev), step_host,
+    captured = None
+    if graph:
+        # the whole step (generator forward, losses, both backwards, both Adam steps[, the NCCL gradient all-reduces]) as ONE
+        # CUDA graph (graphs.CapturedStep); a step that cannot be captured is timed eagerly and says so
+        from face_mask_inpaint_b200.graphs import CapturedStep
+        try:
+            for _ in range(2):
+                run(*dev)
+            torch.cuda.synchronize()
+            captured = CapturedStep(run, *dev)
+        except Exception as ex:  # noqa: BLE001
+            sys.stderr.write(f"[bench] train_picnet: CUDA-graph capture failed ({type(ex).__name__}: {str(ex)[:200]}); eager step\n")
+            captured = None
+            torch.cuda.synchronize()
+
+    def step_host_graph(hh):
+        stat = captured.static_inputs
+
+        def st():
+            for dst, src in zip(stat, host):
+                dst.copy_(src, non_blocking=True)
+            ls = captured.replay()
+            losses_host.copy_(torch.stack([l.detach().float().reshape(()) for l in ls]), non_blocking=True)
+        ms = hh.timed(st)
+        return ms, sum(t.numel() * t.element_size() for t in host), 20
+
+    rec = _train_record(h, "train_picnet", lambda: run(*dev), step_host_graph if captured else step_host,
                         [p for m in (G, D) for p in m.parameters() if p.requires_grad], "tf32",
                         "train_reference_fill.py:342-346 — ReferenceFill forward (train mode) + GANOptimizer.__call__ "
-                        "(modules/loss.py:120-134) over the installed drop-ins; attention forward/backward on the sm_100a kernels",
-                        {"buckets": nb})
+                        "(modules/loss.py:120-134) over the installed drop-ins; conv blocks, attention, SpectralNorm forward and "
+                        "backward on the sm_100a kernels",
+                        {"buckets": nb}, timed_step=captured.replay if captured else None)
     if not torch.isfinite(losses_host).all():
         raise RuntimeError("train_picnet: non-finite losses")
     return rec

@@ -169,6 +169,106 @@ __global__ void __launch_bounds__(256) norm_act_kernel(const OT* __restrict__ x,
   }
 }
 
+// ---- backward of y = lrelu(IN(x)) (training: ResBlockDecoder's norm + activation pairs, base_function.py:338-344) -------------
+// z = x * scale + shift (scale = gamma * rstd, shift = beta - mean * scale), y = lrelu(z):
+//   dz = dy * (z > 0 ? 1 : slope);  S1[b,c] = sum_p dz;  S2[b,c] = sum_p dz * xhat,  xhat = (x - mean) * rstd
+//   dx = scale * (dz - S1 / HW - xhat * S2 / HW);  dgamma[c] = sum_b S2;  dbeta[c] = sum_b S1
+// pass 1 (same thread layout as instnorm_stats_kernel): the two sums per (sample, channel) in double
+__global__ void __launch_bounds__(256) instnorm_act_bwd_stats_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                                     const float* __restrict__ ss, const float* __restrict__ mr,
+                                                                     int HW, int C, float slope, double* __restrict__ sums) {
+  constexpr int VEC = 4;
+  const int nvec = C / VEC;
+  const int lanes = 256 / nvec;
+  const int v = threadIdx.x % nvec, pl = threadIdx.x / nvec;
+  const int b = blockIdx.y;
+  float s1[VEC], s2[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) s1[k] = s2[k] = 0.f;
+  if (pl < lanes) {
+    const int64_t base = (int64_t)b * HW * C + v * VEC;
+    float sc[VEC], sh[VEC], mu[VEC], rs[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      const int64_t e = (int64_t)b * C + v * VEC + k;
+      sc[k] = ss[2 * e]; sh[k] = ss[2 * e + 1]; mu[k] = mr[2 * e]; rs[k] = mr[2 * e + 1];
+    }
+    const int step = gridDim.x * lanes;
+    int pp = blockIdx.x * lanes + pl;
+    auto acc = [&](const Vec16<float>& g, const Vec16<float>& t) {
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        const float z = fmaf(t.e[k], sc[k], sh[k]);
+        const float dz = z > 0.f ? g.e[k] : g.e[k] * slope;
+        s1[k] += dz;
+        s2[k] = fmaf(dz, (t.e[k] - mu[k]) * rs[k], s2[k]);
+      }
+    };
+    for (; pp + step < HW; pp += 2 * step) {   // four independent 16-byte loads in flight per thread
+      const Vec16<float> g0 = ld_vec16_stream(dy + base + (int64_t)pp * C), t0 = ld_vec16_stream(x + base + (int64_t)pp * C);
+      const Vec16<float> g1 = ld_vec16_stream(dy + base + (int64_t)(pp + step) * C),
+                         t1 = ld_vec16_stream(x + base + (int64_t)(pp + step) * C);
+      acc(g0, t0);
+      acc(g1, t1);
+    }
+    for (; pp < HW; pp += step) acc(ld_vec16_stream(dy + base + (int64_t)pp * C), ld_vec16_stream(x + base + (int64_t)pp * C));
+  }
+  __shared__ float shm[256][2 * VEC + 1];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) { shm[threadIdx.x][k] = s1[k]; shm[threadIdx.x][VEC + k] = s2[k]; }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 2 * C; e += 256) {
+    const int c = e >> 1, which = e & 1;
+    const int vv = c / VEC, k = c % VEC;
+    double a = 0.0;
+    for (int l = 0; l < lanes; ++l) a += (double)shm[l * nvec + vv][which * VEC + k];
+    atomicAdd(&sums[((int64_t)b * C + c) * 2 + which], a);
+  }
+}
+
+// pass 2: dx = scale * (dz - S1 / HW - xhat * S2 / HW)
+__global__ void __launch_bounds__(256) instnorm_act_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                                     const float* __restrict__ ss, const float* __restrict__ mr,
+                                                                     const double* __restrict__ sums, float* __restrict__ dx,
+                                                                     int HW, int C, float slope, float inv_hw) {
+  constexpr int VEC = 4;
+  const int nvec = C / VEC;
+  const int b = blockIdx.y;
+  const int64_t total = (int64_t)HW * nvec;
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  const int64_t img = (int64_t)b * HW * C;
+  auto one = [&](const Vec16<float>& g, const Vec16<float>& t, int64_t off, int c) {
+    Vec16<float> o;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      const int64_t e = (int64_t)b * C + c + k;
+      const float2 a = *reinterpret_cast<const float2*>(ss + 2 * e);
+      const float2 m = *reinterpret_cast<const float2*>(mr + 2 * e);
+      const float m1 = (float)sums[2 * e] * inv_hw, m2 = (float)sums[2 * e + 1] * inv_hw;
+      const float z = fmaf(t.e[k], a.x, a.y);
+      const float dz = z > 0.f ? g.e[k] : g.e[k] * slope;
+      o.e[k] = a.x * (dz - m1 - (t.e[k] - m.x) * m.y * m2);
+    }
+    st_vec16(dx + off, o);
+  };
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; e + step < total; e += 2 * step) {
+    const int64_t p0 = e / nvec, p1 = (e + step) / nvec;
+    const int c0 = (int)(e - p0 * nvec) * VEC, c1 = (int)(e + step - p1 * nvec) * VEC;
+    const int64_t o0 = img + p0 * C + c0, o1 = img + p1 * C + c1;
+    const Vec16<float> g0 = ld_vec16_stream(dy + o0), t0 = ld_vec16_stream(x + o0), g1 = ld_vec16_stream(dy + o1),
+                       t1 = ld_vec16_stream(x + o1);
+    one(g0, t0, o0, c0);
+    one(g1, t1, o1, c1);
+  }
+  for (; e < total; e += step) {
+    const int64_t pp = e / nvec;
+    const int c = (int)(e - pp * nvec) * VEC;
+    const int64_t o = img + pp * C + c;
+    one(ld_vec16_stream(dy + o), ld_vec16_stream(x + o), o, c);
+  }
+}
+
 // ---- ReflectionPad2d(1) border of a [B, H+2, W+2, C] buffer whose interior is already written ------------------------
 template <typename OT>
 __global__ void __launch_bounds__(256) reflect_border_kernel(OT* __restrict__ y, int H, int W, int C) {
@@ -326,6 +426,34 @@ extern "C" int fmi_norm_act_nhwc(const void* x, int64_t x_pixel_stride, void* y,
         (const __nv_bfloat16*)x, x_pixel_stride, (int64_t)HW * x_pixel_stride, (__nv_bfloat16*)y, y_pixel_stride,
         (int64_t)HW * y_pixel_stride, scale_shift, HW, C, slope);
   return fmi_launched("norm_act");
+}
+
+// Backward of fmi_instnorm_stats_nhwc + fmi_norm_act_nhwc (y = lrelu(IN(x)), fp32 dense NHWC, training): dx [B,HW,C] and
+// sums [B][C][2] doubles = (sum dz, sum dz * xhat) per sample and channel, from which the caller takes dgamma / dbeta.
+// scale_shift as produced by fmi_instnorm_stats_nhwc; mean_rstd [B][C][2] fp32 (mean, 1 / sqrt(var + eps)).
+extern "C" int fmi_instnorm_act_bwd_nhwc(const float* dy, const float* x, const float* scale_shift, const float* mean_rstd,
+                                         float* dx, double* sums, int B, int C, int HW, float slope, void* stream) {
+  if (B == 0) return FMI_OK;
+  FMI_REQUIRE(dy && x && scale_shift && mean_rstd && dx && sums && HW >= 1 && C >= 4 && C % 4 == 0 && C / 4 <= 256 &&
+                  fmi_aligned(dy, 16) && fmi_aligned(x, 16) && fmi_aligned(dx, 16),
+              "instnorm_act_bwd: unsupported shape C=%d", C);
+  cudaStream_t st = (cudaStream_t)stream;
+  FMI_CUDA(cudaMemsetAsync(sums, 0, (size_t)B * C * 2 * sizeof(double), st));
+  const int lanes = 256 / (C / 4);
+  int gx = (HW + lanes * 32 - 1) / (lanes * 32);
+  int cap = (FMI_NUM_SMS * 8 + B - 1) / B;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  FmiProfScope prof(FMI_PROF_NORMACT, st, 12.0 * B * HW * C, 5.0 * B * HW * C * 4);
+  instnorm_act_bwd_stats_kernel<<<dim3(gx, B), 256, 0, st>>>(dy, x, scale_shift, mean_rstd, HW, C, slope, sums);
+  int rc = fmi_launched("instnorm_act_bwd_stats");
+  if (rc) return rc;
+  int ga = stream_grid((int64_t)HW * (C / 4), 256 * 4);
+  cap = (FMI_NUM_SMS * 16 + B - 1) / B;
+  if (ga > cap) ga = cap;
+  instnorm_act_bwd_apply_kernel<<<dim3(ga, B), 256, 0, st>>>(dy, x, scale_shift, mean_rstd, sums, dx, HW, C, slope,
+                                                             1.0f / (float)HW);
+  return fmi_launched("instnorm_act_bwd_apply");
 }
 
 extern "C" int fmi_reflect_border_nhwc(void* y, int B, int C, int H, int W, int mma, void* stream) {

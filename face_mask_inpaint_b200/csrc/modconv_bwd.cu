@@ -156,7 +156,8 @@ struct WgradParams {
   int a_shared;                        // 1: one A tile per stage, G shifted B tiles (plain); 0: G A tiles, one B tile (up)
   int tap_ady[9], tap_adx[9], tap_aboff[9], tap_bdy[9], tap_bdx[9];
   int stages, tmem_cols;
-  float* dwp;                          // [B][9][O][I] fp32, zero-initialised
+  float* dwp;                          // [B][9][O][I] fp32, zero-initialised (dwp_img_stride = 9*O*I), or one [taps][O][I]
+  int64_t dwp_img_stride;              // shared by the batch (dwp_img_stride = 0: every image adds into the same gradient)
 };
 
 constexpr int kWgradThreads = 192;
@@ -264,7 +265,7 @@ __global__ void __launch_bounds__(kWgradThreads, 1)
     tc_fence_after();
     for (int tl = 0; tl < p.G; ++tl) {
       const int tap = grp * p.G + tl;
-      float* dst = p.dwp + (((int64_t)b * 9 + tap) * p.O + o) * p.I + nt * p.n_tile;
+      float* dst = p.dwp + (int64_t)b * p.dwp_img_stride + ((int64_t)tap * p.O + o) * p.I + nt * p.n_tile;
       for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(tmem + lane_addr + tl * p.n_tile + c0, v);
@@ -642,6 +643,7 @@ extern "C" int fmi_styled_conv_bwd_nhwc(const void* x, const void* y, const void
     if (ksplit < 1) ksplit = 1;
     p.ksplit = ksplit;
     p.dwp = (float*)(ws + L.dwp);
+    p.dwp_img_stride = (int64_t)9 * O * I;
     CUtensorMap ma, mb;
     // MN-major tf32 operands need the 32-byte-atom flavour of the 128-byte swizzle (sm100.cuh make_sdesc_mn_sw128)
     const CUtensorMapSwizzle wswz = tf32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
@@ -674,6 +676,87 @@ extern "C" int fmi_styled_conv_bwd_nhwc(const void* x, const void* y, const void
     if (rc) return rc;
   }
   return FMI_OK;
+}
+
+// Weight gradient of a batch-shared Conv2d(ksize 1 or 3, stride 1, padding ksize/2) — the PICNet conv blocks in training
+// (SpectralNorm-wrapped nn.Conv2d of base_function.py:207-305 / network.py:73-365, differentiated by ATen / cuDNN in the reference):
+//   dwp[t][o][i] += sum_{b, pixels} dy[b, p, o] * x[b, p + off_t, i]      (fp32, accumulated into the caller's zeroed buffer)
+// the pixel-contraction GEMM above with every image adding into ONE gradient. x [B,H,W,I], dy [B,H,W,O] dense NHWC in the
+// operand type (fp32 read as tf32 / bf16). transposed = 1: the weight gradient of ConvTranspose2d(3, stride 2, padding 1,
+// output_padding 1) (ResBlockDecoder's conv2 / bypass, base_function.py:330-336): `dy` is then the 4 pixel-parity planes
+// [4][B][H][W][O] of the [B,2H,2W,O] output gradient, dwp[t][o][i] = sum dy[b, 2m-1+ky, 2n-1+kx, o] * x[b,m,n,i].
+extern "C" int fmi_conv_wgrad_nhwc(const void* x, const void* dy, float* dwp, int B, int I, int O, int H, int W, int ksize,
+                                   int transposed, int mma, void* stream) {
+  FMI_REQUIRE(mma == FMI_MMA_TF32 || mma == FMI_MMA_BF16, "conv_wgrad: bad mma");
+  FMI_REQUIRE(ksize == 1 || ksize == 3, "conv_wgrad: ksize must be 1 or 3");
+  FMI_REQUIRE(!transposed || ksize == 3, "conv_wgrad: the transposed convolution is 3x3");
+  if (B == 0) return FMI_OK;
+  FMI_REQUIRE(x && dy && dwp, "conv_wgrad: null pointer");
+  FMI_REQUIRE(I >= 32 && I % 32 == 0 && O >= 32 && O % 32 == 0 && (I <= 256 || I % 256 == 0) && (O <= 128 || O % 128 == 0),
+              "conv_wgrad: unsupported channel counts I=%d O=%d", I, O);
+  FMI_REQUIRE(is_pow2(H) && is_pow2(W) && H * W >= 16 && W >= 4, "conv_wgrad: H=%d W=%d must be powers of two (>= 4)", H, W);
+  FMI_REQUIRE(fmi_aligned(x, 16) && fmi_aligned(dy, 16) && fmi_aligned(dwp, 16), "conv_wgrad: buffers must be 16-byte aligned");
+  int rc = fmi_device_check();
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool tf32 = mma == FMI_MMA_TF32;
+  const int esz = esz_of(mma);
+  const uint32_t epa = 128 / esz;
+  const int taps = ksize * ksize;
+  FmiProfScope prof(FMI_PROF_WGRAD, st, 2.0 * B * (double)H * W * taps * I * O, (double)B * H * W * (I + O) * esz + 4.0 * taps * I * O);
+  const CUtensorMapDataType dt = tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  WgradParams p{};
+  p.B = B; p.I = I; p.O = O; p.H = H; p.W = W;
+  int KT = tf32 ? 32 : 64;
+  if (KT > H * W) KT = H * W;
+  p.TW = W < KT ? W : KT;
+  p.TH = KT / p.TW;
+  p.kt_w = W / p.TW;
+  p.kt_total = (H / p.TH) * p.kt_w;
+  p.n_tile = I <= 256 ? I : 256;
+  p.n_tiles = I / p.n_tile;
+  p.m_tiles = (O + 127) / 128;
+  p.G = (taps == 9 && p.n_tile <= 128) ? 3 : 1;
+  p.ngroups = taps / p.G;
+  p.a_atoms = ((O < 128 ? O : 128) + (int)epa - 1) / (int)epa;
+  p.b_atoms = (p.n_tile + (int)epa - 1) / (int)epa;
+  p.a_shared = transposed ? 0 : 1;
+  for (int t = 0; t < taps; ++t) {
+    const int ky = t / 3, kx = t % 3;
+    if (transposed) {
+      // dy[2m - 1 + ky] = plane (ky + 1) & 1 at row m - (ky == 0): the parity planes of fmi_space_to_planes_nhwc
+      p.tap_ady[t] = ky == 0 ? -1 : 0;
+      p.tap_adx[t] = kx == 0 ? -1 : 0;
+      p.tap_aboff[t] = ((((ky + 1) & 1) << 1) | ((kx + 1) & 1)) * B;
+    } else {
+      p.tap_bdy[t] = ksize == 3 ? ky - 1 : 0;
+      p.tap_bdx[t] = ksize == 3 ? kx - 1 : 0;
+    }
+  }
+  const int base = B * p.ngroups * p.m_tiles * p.n_tiles;
+  int ksplit = (2 * FMI_NUM_SMS + base - 1) / base;
+  if (ksplit > p.kt_total / 4) ksplit = p.kt_total / 4;
+  if (ksplit < 1) ksplit = 1;
+  p.ksplit = ksplit;
+  p.dwp = dwp;
+  p.dwp_img_stride = 0;
+  CUtensorMap ma, mb;
+  const CUtensorMapSwizzle wswz = tf32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
+  {
+    uint64_t dims[4] = {(uint64_t)O, (uint64_t)W, (uint64_t)H, (uint64_t)(transposed ? 4 * B : B)};
+    uint64_t str[3] = {(uint64_t)O * esz, (uint64_t)W * O * esz, (uint64_t)H * W * O * esz};
+    uint32_t box[4] = {epa, (uint32_t)p.TW, (uint32_t)p.TH, 1};
+    int e = make_tensor_map(&ma, dt, 4, dy, dims, str, box, wswz);
+    FMI_REQUIRE(e == 0, "conv_wgrad: cuTensorMapEncodeTiled(dy) failed (%d)", e);
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)I, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)I * esz, (uint64_t)W * I * esz, (uint64_t)H * W * I * esz};
+    uint32_t box[4] = {epa, (uint32_t)p.TW, (uint32_t)p.TH, 1};
+    int e = make_tensor_map(&mb, dt, 4, x, dims, str, box, wswz);
+    FMI_REQUIRE(e == 0, "conv_wgrad: cuTensorMapEncodeTiled(x) failed (%d)", e);
+  }
+  return tf32 ? launch_wgrad<true>(ma, mb, p, st) : launch_wgrad<false>(ma, mb, p, st);
 }
 
 extern "C" int fmi_torgb_bwd_nhwc(const void* x, const float* drgb, const float* rgb_w, void* dx, float* d_rgbw,

@@ -198,32 +198,45 @@ __global__ void __launch_bounds__(256) upfirdn2d_tile_kernel(const T* __restrict
 }
 
 // ---- separable strip kernel: up = down = 1, taps <= 4x4, minor == 1 — Blur forward (pad 1,1) and backward (pad 2,2) ----------
-// The 16-FMA-per-output tile kernel above is instruction-issue bound (ncu: issue slots 75 % busy at 0.68 / 0.38 of the HBM
-// roofline in fp32 / bf16). Every blur kernel the models build is an outer product (stylegan2/model.py:19-27 make_kernel), so
-// this kernel factors the taps on the device (pivot row x pivot column / pivot; a CTA whose taps are not rank one falls back
-// to the 16-tap sum from the same staged tile) and runs a horizontal 4-tap pass on each staged row followed by a vertical
-// 4-tap pass over a rotating register window: 64 x 128 output tile per CTA, warp = 8 output rows x 128 columns, lane = 4
-// adjacent columns, per input row 2-3 LDS.128 + 16 + 16 FMA + one 16-byte store.
-// Rows of the (2H+1)-wide tensors are not 16-byte aligned: an odd-width INPUT is staged with coalesced scalar loads (any
-// alignment), an aligned one with 16-byte (fp32) / 8-byte (16-bit) vector loads from the aligned-down column (D = the offset
-// of the first needed column inside its vector, a launch constant); an odd-width OUTPUT row is bounced through a per-warp
-// shared-memory row so that the scalar stores of a warp are 32 consecutive elements.
-constexpr int kStripW = 128, kStripH = 64, kStripIH = kStripH + 3, kStripIW = 136;
+// The 16-FMA-per-output tile kernel above is instruction-issue bound AND keeps too few bytes in flight (its staging loads pass
+// through registers a row at a time): 0.68 / 0.38 of the HBM roofline in fp32 / bf16. Here:
+//  * staging is asynchronous: every thread issues ALL its global -> shared copies of the tile (cp.async, 4-byte units, zero fill
+//    outside the image = the padding) before it waits, so a CTA has its whole 67 x 131 input window in flight and the other
+//    CTAs of the SM compute meanwhile. Rows of the (2H+1)-wide tensors are not 16-byte aligned, 4-byte units always are for
+//    fp32; a 16-bit row is copied as the aligned 32-bit words that cover it, which leaves the row shifted by one slot when its
+//    first element sits at an odd index (the window reader funnel-shifts it back).
+//  * every blur kernel the models build is an outer product (stylegan2/model.py:19-27 make_kernel), so the taps are factored on
+//    the device (pivot row x pivot column / pivot; a CTA whose taps are not rank one takes the 16-tap sum from the same staged
+//    tile): a horizontal 4-tap pass on each staged row, then a vertical 4-tap pass over a rotating register window.
+//    64 x 128 output tile per CTA, warp = 8 output rows x 128 columns, lane = 4 adjacent columns.
+//  * an odd-width OUTPUT row is bounced through a per-warp shared-memory row so that the scalar stores of a warp are 32
+//    consecutive elements; aligned rows take one 16-byte (fp32) / 8-byte (16-bit) store per lane and row.
+constexpr int kStripW = 128, kStripH = 64, kStripIH = kStripH + 3, kStripSlots = 132;
 
-template <typename T> struct Vec4Of;  // 4 consecutive elements as one vector load
-template <> struct Vec4Of<float> { using type = float4; };
-template <> struct Vec4Of<__nv_bfloat16> { using type = uint2; };
-template <> struct Vec4Of<__half> { using type = uint2; };
-
-__device__ __forceinline__ float4 vec4_to_f32(float4 v, float) { return v; }
-__device__ __forceinline__ float4 vec4_to_f32(uint2 v, __nv_bfloat16) {
-  return make_float4(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u), __uint_as_float(v.y << 16),
-                     __uint_as_float(v.y & 0xffff0000u));
+__device__ __forceinline__ void cp_async_4(uint32_t smem_dst, const void* gsrc, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(src_bytes) : "memory");
 }
-__device__ __forceinline__ float4 vec4_to_f32(uint2 v, __half) {
-  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
-  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
-  return make_float4(a.x, a.y, b.x, b.y);
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+__device__ __forceinline__ float half_lo_to_f32(uint32_t w, __nv_bfloat16) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float half_hi_to_f32(uint32_t w, __nv_bfloat16) { return __uint_as_float(w & 0xffff0000u); }
+__device__ __forceinline__ float half_lo_to_f32(uint32_t w, __half) { return __low2float(*reinterpret_cast<const __half2*>(&w)); }
+__device__ __forceinline__ float half_hi_to_f32(uint32_t w, __half) { return __high2float(*reinterpret_cast<const __half2*>(&w)); }
+
+// columns 4*lane .. 4*lane + 7 of staged row `row` as fp32 (shift = 16 when the row was staged one slot to the right)
+__device__ __forceinline__ void strip_window(const float* row, int lane, uint32_t, float (&w)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(row + 4 * lane), b = *reinterpret_cast<const float4*>(row + 4 * lane + 4);
+  w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+}
+template <typename T>
+__device__ __forceinline__ void strip_window(const T* row, int lane, uint32_t shift, float (&w)[8]) {
+  const uint2 a = *reinterpret_cast<const uint2*>(row + 4 * lane), b = *reinterpret_cast<const uint2*>(row + 4 * lane + 4);
+  const uint32_t w0 = __funnelshift_r(a.x, a.y, shift), w1 = __funnelshift_r(a.y, b.x, shift),
+                 w2 = __funnelshift_r(b.x, b.y, shift), w3 = b.y >> shift;
+  w[0] = half_lo_to_f32(w0, T()); w[1] = half_hi_to_f32(w0, T()); w[2] = half_lo_to_f32(w1, T()); w[3] = half_hi_to_f32(w1, T());
+  w[4] = half_lo_to_f32(w2, T()); w[5] = half_hi_to_f32(w2, T()); w[6] = half_lo_to_f32(w3, T()); w[7] = half_hi_to_f32(w3, T());
 }
 __device__ __forceinline__ void store4(float* dst, const float (&o)[4]) {
   *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
@@ -237,95 +250,110 @@ __device__ __forceinline__ void store4(__half* dst, const float (&o)[4]) {
   *reinterpret_cast<uint2*>(dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
 }
 
-template <typename T, bool VEC_IN, int D, bool VEC_OUT>
-__global__ void __launch_bounds__(256) upfirdn2d_blur_strip_kernel(const T* __restrict__ x, const float* __restrict__ k,
+template <typename T, bool VEC_OUT>
+__global__ void __launch_bounds__(256, (sizeof(T) == 4 ? 6 : 7)) upfirdn2d_blur_strip_kernel(const T* __restrict__ x, const float* __restrict__ k,
                                                                    T* __restrict__ y, UfdParams p, int tiles_x,
                                                                    float inv_tiles_x) {
-  static_assert(VEC_IN || D == 0, "scalar staging places the first needed column at shared-memory column 0");
-  __shared__ __align__(16) float sx[kStripIH][kStripIW];
+  constexpr bool B16 = sizeof(T) == 2;
+  __shared__ __align__(16) T sx[kStripIH][kStripSlots];
   __shared__ __align__(16) float sout[VEC_OUT ? 1 : 8][kStripW];
   __shared__ float sk[16], skr[4], skc[4];
   __shared__ int s_sep;
   const int64_t plane = blockIdx.y;
   const int ty_i = (int)(((float)blockIdx.x + 0.5f) * inv_tiles_x);
   const int oy0 = ty_i * kStripH, ox0 = ((int)blockIdx.x - ty_i * tiles_x) * kStripW;
-  const int iy0 = oy0 - p.pad_y0, ix0 = ox0 - p.pad_x0 - D;  // global coordinates of sx[0][0]
+  const int iy0 = oy0 - p.pad_y0, ix0 = ox0 - p.pad_x0;  // image coordinates of tile column 0 / row 0
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t plane_off = plane * p.in_h * (int64_t)p.in_w;
+  const bool interior = iy0 >= 0 && iy0 + kStripIH <= p.in_h && ix0 >= 1 && ix0 + kStripW + 4 <= p.in_w;
+  // 16-bit rows: slot s of staged row r holds tile column s - m_r, m_r = parity of the row's first element index
+  const int m0 = B16 ? (int)((plane_off + (int64_t)iy0 * p.in_w + ix0) & 1) : 0;
+  const int modd = B16 ? (p.in_w & 1) : 0;
 
-  if (threadIdx.x < 16) {
-    const int ky = threadIdx.x >> 2, kx = threadIdx.x & 3;
-    float v = 0.f;
-    if (ky < p.kh && kx < p.kw) v = k[(p.kh - 1 - ky) * p.kw + (p.kw - 1 - kx)];  // flipped taps (upfirdn2d_kernel.cu:77)
-    sk[threadIdx.x] = v;
-    __syncwarp(0xffffu);
-    if (threadIdx.x == 0) {
-      int piv = 0;
-      for (int i = 1; i < 16; ++i)
-        if (fabsf(sk[i]) > fabsf(sk[piv])) piv = i;
-      const float pv = sk[piv];
-      const float inv = pv != 0.f ? 1.0f / pv : 0.f;
-      float kr[4], kc[4];
-      for (int i = 0; i < 4; ++i) {
-        kc[i] = sk[(piv >> 2) * 4 + i];
-        kr[i] = sk[i * 4 + (piv & 3)] * inv;
-      }
-      float dev = 0.f;
-      for (int i = 0; i < 16; ++i) dev = fmaxf(dev, fabsf(sk[i] - kr[i >> 2] * kc[i & 3]));
-      for (int i = 0; i < 4; ++i) {
-        skr[i] = kr[i];
-        skc[i] = kc[i];
-      }
-      s_sep = dev <= 1e-6f * fabsf(pv);
-    }
-  }
-
-  const T* xp = x + plane * p.in_h * (int64_t)p.in_w;
-  if constexpr (VEC_IN) {
-    // in_w % 4 == 0, ix0 % 4 == 0, plane base aligned: a 4-element vector is entirely inside or outside the row
-    using V = typename Vec4Of<T>::type;
-#pragma unroll 2
-    for (int r = warp; r < kStripIH; r += 8) {
-      const int iy = iy0 + r;
-      const bool row_ok = iy >= 0 && iy < p.in_h;
-      const T* row = xp + (int64_t)iy * p.in_w + ix0;
+  // ---- stage: all copies of the thread in flight, then one wait. Interior tiles (no bounds tests): one pointer per thread,
+  // immediate offsets; border tiles: zero fill through the source size (the address of a zero-size copy is not read).
+  const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(&sx[0][0]);
+  if constexpr (!B16) {
+    const T* src = x + plane_off + (int64_t)(iy0 + warp) * p.in_w + ix0 + lane;
+    uint32_t dst = s_base + (uint32_t)((warp * kStripSlots + lane) * 4);
+    if (interior) {
+      for (int r = warp; r < kStripIH; r += 8, src += 8 * (int64_t)p.in_w, dst += 8 * kStripSlots * 4) {
 #pragma unroll
-      for (int c = 0; c < kStripIW / 4; c += 32) {
-        const int v = c + lane;
-        if (v < kStripIW / 4) {
-          const int ix = ix0 + 4 * v;
-          float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (row_ok && ix >= 0 && ix < p.in_w) f = vec4_to_f32(*reinterpret_cast<const V*>(row + 4 * v), T());
-          *reinterpret_cast<float4*>(&sx[r][4 * v]) = f;
-        }
+        for (int c0 = 0; c0 < kStripW; c0 += 32) cp_async_4(dst + c0 * 4, src + c0, 4u);
+        if (lane < 3) cp_async_4(dst + kStripW * 4, src + kStripW, 4u);
       }
-    }
-  } else if (iy0 >= 0 && iy0 + kStripIH <= p.in_h && ix0 >= 0 && ix0 + kStripW + 3 <= p.in_w) {
-    const T* src = xp + (int64_t)iy0 * p.in_w + ix0 + lane;
-#pragma unroll 2
-    for (int r = warp; r < kStripIH; r += 8) {
-      const T* row = src + (int64_t)r * p.in_w;
-      const T v0 = row[0], v1 = row[32], v2 = row[64], v3 = row[96];
-      sx[r][lane] = to_f32<T>(v0);
-      sx[r][lane + 32] = to_f32<T>(v1);
-      sx[r][lane + 64] = to_f32<T>(v2);
-      sx[r][lane + 96] = to_f32<T>(v3);
-      if (lane < 3) sx[r][lane + 128] = to_f32<T>(row[128]);
+    } else {
+      const uint32_t span = (uint32_t)p.in_w;
+      const int t = ix0 + lane;  // image column of tile column `lane`
+      for (int r = warp; r < kStripIH; r += 8, src += 8 * (int64_t)p.in_w, dst += 8 * kStripSlots * 4) {
+        const uint32_t row_bytes = (iy0 + r >= 0 && iy0 + r < p.in_h) ? 4u : 0u;
+#pragma unroll
+        for (int c0 = 0; c0 < kStripW; c0 += 32) cp_async_4(dst + c0 * 4, src + c0, (uint32_t)(t + c0) < span ? row_bytes : 0u);
+        if (lane < 3) cp_async_4(dst + kStripW * 4, src + kStripW, (uint32_t)(t + kStripW) < span ? row_bytes : 0u);
+      }
     }
   } else {
-    for (int r = warp; r < kStripIH; r += 8) {
-      const int iy = iy0 + r;
-      const bool row_ok = iy >= 0 && iy < p.in_h;
-      const T* row = xp + (int64_t)iy * p.in_w;
-#pragma unroll
-      for (int c = lane; c < kStripW + 3; c += 32) {
-        const int ix = ix0 + c;
-        float v = 0.f;
-        if (row_ok && ix >= 0 && ix < p.in_w) v = to_f32<T>(row[ix]);
-        sx[r][c] = v;
+    const uint32_t* xw = reinterpret_cast<const uint32_t*>(x);
+    int64_t e = plane_off + (int64_t)(iy0 + warp) * p.in_w + ix0;  // element index of tile column 0 of row r (< 0 possible at the border)
+    uint32_t dst = s_base + (uint32_t)(warp * kStripSlots * 2 + lane * 4);
+    if (interior) {
+      for (int r = warp; r < kStripIH; r += 8, e += 8 * (int64_t)p.in_w, dst += 8 * kStripSlots * 2) {
+        const uint32_t* src = xw + (e >> 1) + lane;   // aligned word that holds element e (floor: e may be odd)
+        cp_async_4(dst, src, 4u);
+        cp_async_4(dst + 128, src + 32, 4u);
+        if (lane < 2) cp_async_4(dst + 256, src + 64, 4u);
+      }
+    } else {
+      const uint32_t span = (uint32_t)p.in_w + 1u;      // a word is copied when at least one of its two columns is inside
+      for (int r = warp; r < kStripIH; r += 8, e += 8 * (int64_t)p.in_w, dst += 8 * kStripSlots * 2) {
+        const uint32_t* src = xw + (e >> 1) + lane;
+        const uint32_t row_bytes = (iy0 + r >= 0 && iy0 + r < p.in_h) ? 4u : 0u;
+        const int t = ix0 - (int)(e & 1) + 2 * lane + 1;  // image column of the word's high half
+        cp_async_4(dst, src, (uint32_t)t < span ? row_bytes : 0u);
+        cp_async_4(dst + 128, src + 32, (uint32_t)(t + 64) < span ? row_bytes : 0u);
+        if (lane < 2) cp_async_4(dst + 256, src + 64, (uint32_t)(t + 128) < span ? row_bytes : 0u);
       }
     }
   }
+  if (warp == 0) {
+    // taps (flipped, upfirdn2d_kernel.cu:77) and their rank-one factors: lane i < 16 holds tap (i >> 2, i & 3)
+    const int ky = lane >> 2, kx = lane & 3;
+    float v = 0.f;
+    if (lane < 16 && ky < p.kh && kx < p.kw) v = k[(p.kh - 1 - ky) * p.kw + (p.kw - 1 - kx)];
+    float best = fabsf(v);
+    int piv = lane;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int op = __shfl_xor_sync(0xffffffffu, piv, o);
+      if (ob > best || (ob == best && op < piv)) { best = ob; piv = op; }
+    }
+    piv &= 15;
+    const float pv = __shfl_sync(0xffffffffu, v, piv);
+    const float inv = pv != 0.f ? 1.0f / pv : 0.f;
+    const float kc = __shfl_sync(0xffffffffu, v, (piv & 12) | kx);          // pivot row
+    const float kr = __shfl_sync(0xffffffffu, v, (ky << 2) | (piv & 3)) * inv;  // pivot column / pivot
+    const float dev = warp_max(lane < 16 ? fabsf(v - kr * kc) : 0.f);
+    if (lane < 16) sk[lane] = v;
+    if (lane < 4) skc[lane] = kc;           // lanes 0..3: ky = 0, kx = lane
+    if (lane < 16 && kx == 0) skr[ky] = kr;
+    if (lane == 0) s_sep = dev <= 1e-6f * fabsf(pv);
+  }
+  cp_async_wait_all();
   __syncthreads();
+  if constexpr (B16) {
+    if (!interior) {
+      // a word that straddles the image border brought one element of the neighbouring row / plane: the padding is zero
+      if (threadIdx.x < kStripIH) {
+        const int r = threadIdx.x;
+        const int m = m0 ^ (r & modd);
+        const int s_lo = -1 - ix0 + m, s_hi = p.in_w - ix0 + m;  // slots of image columns -1 and in_w
+        if (s_lo >= 0 && s_lo < kStripSlots) sx[r][s_lo] = from_f32<T>(0.f);
+        if (s_hi >= 0 && s_hi < kStripSlots) sx[r][s_hi] = from_f32<T>(0.f);
+      }
+      __syncthreads();
+    }
+  }
 
   T* yp = y + plane * p.out_h * (int64_t)p.out_w;
   const int ox = ox0 + 4 * lane;
@@ -345,7 +373,6 @@ __global__ void __launch_bounds__(256) upfirdn2d_blur_strip_kernel(const T* __re
       __syncwarp();
     }
   };
-  constexpr int NV = D >= 2 ? 3 : 2;  // vectors that cover columns D .. D + 6 of the lane's window
   const int r0 = warp * 8;
   if (s_sep) {
     float kr[4], kc[4];
@@ -361,18 +388,14 @@ __global__ void __launch_bounds__(256) upfirdn2d_blur_strip_kernel(const T* __re
       for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
 #pragma unroll
     for (int r = 0; r < 11; ++r) {
-      float w[4 * NV];
-#pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        const float4 t = *reinterpret_cast<const float4*>(&sx[r0 + r][4 * lane + 4 * v]);
-        w[4 * v] = t.x; w[4 * v + 1] = t.y; w[4 * v + 2] = t.z; w[4 * v + 3] = t.w;
-      }
+      float w[8];
+      strip_window(&sx[r0 + r][0], lane, (uint32_t)((m0 ^ ((r0 + r) & modd)) << 4), w);
       float h[4];
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
-        h[b] = kc[0] * w[D + b];
+        h[b] = kc[0] * w[b];
 #pragma unroll
-        for (int kx = 1; kx < 4; ++kx) h[b] = fmaf(kc[kx], w[D + b + kx], h[b]);
+        for (int kx = 1; kx < 4; ++kx) h[b] = fmaf(kc[kx], w[b + kx], h[b]);
       }
 #pragma unroll
       for (int ky = 0; ky < 4; ++ky) {
@@ -390,15 +413,23 @@ __global__ void __launch_bounds__(256) upfirdn2d_blur_strip_kernel(const T* __re
   } else {
     for (int a = 0; a < 8; ++a) {
       float o[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int ky = 0; ky < 4; ++ky)
-        for (int kx = 0; kx < 4; ++kx) {
-          const float t = sk[ky * 4 + kx];
+      for (int ky = 0; ky < 4; ++ky) {
+        float w[8];
+        strip_window(&sx[r0 + a + ky][0], lane, (uint32_t)((m0 ^ ((r0 + a + ky) & modd)) << 4), w);
 #pragma unroll
-          for (int b = 0; b < 4; ++b) o[b] = fmaf(t, sx[r0 + a + ky][4 * lane + D + b + kx], o[b]);
-        }
+        for (int kx = 0; kx < 4; ++kx)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) o[b] = fmaf(sk[ky * 4 + kx], w[b + kx], o[b]);
+      }
       store_row(a, o);
     }
   }
+}
+
+template <typename T>
+bool blur_strip_ok(const T* x, const UfdParams& p) {
+  // 16-bit rows are staged as aligned 32-bit words: the base must be word aligned and the tensor must end on a word
+  return sizeof(T) == 4 || (fmi_aligned(x, 4) && (p.major * p.in_h * (int64_t)p.in_w) % 2 == 0);
 }
 
 template <typename T>
@@ -407,21 +438,9 @@ int launch_blur_strip(const T* x, const float* k, T* y, const UfdParams& p, cuda
   FMI_REQUIRE((int64_t)tiles_x * tiles_y < (1 << 23), "upfirdn2d: plane too large");
   const dim3 grid(tiles_x * tiles_y, (unsigned)p.major);
   const float inv_tx = 1.0f / (float)tiles_x;
-  const size_t vbytes = 4 * sizeof(T);
-  const bool vec_in = p.in_w % 4 == 0 && fmi_aligned(x, vbytes) && ((int64_t)p.in_h * p.in_w) % 4 == 0;
-  const bool vec_out = p.out_w % 4 == 0 && fmi_aligned(y, vbytes) && ((int64_t)p.out_h * p.out_w) % 4 == 0;
-  const int d = vec_in ? ((-p.pad_x0) % 4 + 4) % 4 : 0;
-#define FMI_STRIP_CASE(VI, DV)                                                                                               \
-  if (vec_in == VI && d == DV) {                                                                                             \
-    if (vec_out) upfirdn2d_blur_strip_kernel<T, VI, DV, true><<<grid, 256, 0, st>>>(x, k, y, p, tiles_x, inv_tx);            \
-    else upfirdn2d_blur_strip_kernel<T, VI, DV, false><<<grid, 256, 0, st>>>(x, k, y, p, tiles_x, inv_tx);                   \
-  }
-  FMI_STRIP_CASE(false, 0)
-  FMI_STRIP_CASE(true, 0)
-  FMI_STRIP_CASE(true, 1)
-  FMI_STRIP_CASE(true, 2)
-  FMI_STRIP_CASE(true, 3)
-#undef FMI_STRIP_CASE
+  const bool vec_out = p.out_w % 4 == 0 && fmi_aligned(y, 4 * sizeof(T)) && ((int64_t)p.out_h * p.out_w) % 4 == 0;
+  if (vec_out) upfirdn2d_blur_strip_kernel<T, true><<<grid, 256, 0, st>>>(x, k, y, p, tiles_x, inv_tx);
+  else upfirdn2d_blur_strip_kernel<T, false><<<grid, 256, 0, st>>>(x, k, y, p, tiles_x, inv_tx);
   return FMI_OK;
 }
 
@@ -484,7 +503,7 @@ extern "C" int fmi_upfirdn2d(const void* x, const float* kernel, void* y, int64_
       int rc;
       if (up_x == 2) rc = launch_tile<T, 2, 1, 4>((const T*)x, kernel, (T*)y, p, st);
       else if (down_x == 2) rc = launch_tile<T, 1, 2, 2>((const T*)x, kernel, (T*)y, p, st);
-      else if (strip) rc = launch_blur_strip<T>((const T*)x, kernel, (T*)y, p, st);
+      else if (strip && blur_strip_ok<T>((const T*)x, p)) rc = launch_blur_strip<T>((const T*)x, kernel, (T*)y, p, st);
       else rc = launch_tile<T, 1, 1, 4>((const T*)x, kernel, (T*)y, p, st);
       if (rc) return rc;
     } else {

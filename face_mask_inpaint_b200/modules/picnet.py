@@ -73,9 +73,12 @@ class _ResidualPair(nn.Module):
         self.sample = post is not None
 
     def forward(self, x):
+        # under autograd the norm + activation pairs and the wrapped convolutions run forward AND backward on the kernels
+        # (ops.run_block_sequential / SpectralNorm.forward -> ops.conv_train); otherwise this is the reference's Sequential
+        main = ops.run_block_sequential(self.model, x)
         if self.sample:
-            return self.pool(self.model(x)) + self.pool(self.shortcut(x))
-        return self.model(x) + self.shortcut(x)
+            return self.pool(main) + self.pool(self.shortcut(x))
+        return main + self.shortcut(x)
 
 
 def _pre_act(norm, act, channels):

@@ -63,6 +63,8 @@ class SpectralNorm(nn.Module):
 
     def forward(self, *args):
         self._update_u_v()
+        if len(args) == 1 and ops.conv_train_supported(self.module, args[0]):   # training: forward + backward on the kernels
+            return ops.conv_train(self.module, args[0])
         return self.module.forward(*args)
 
 

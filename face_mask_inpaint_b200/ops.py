@@ -384,6 +384,246 @@ def conv1x1(x, weight, bias=None):
     return y
 
 
+# ------------------------------------------------------------------------------------------------
+# batch-shared convolutions of the PICNet conv blocks in TRAINING (SURVEY 8f rank 1 + row g)
+# ------------------------------------------------------------------------------------------------
+def _as_nhwc(t):
+    """[N,C,H,W] fp32 -> dense [N,H,W,C] (a view when `t` already is channels_last in memory)."""
+    v = t.permute(0, 2, 3, 1)
+    return v if v.is_contiguous() and t.dtype == torch.float32 else v.contiguous().float()
+
+
+def _conv_wp(weight, o, i, k, transposed, st):
+    """[k*k][o][i] operand-layout weights (tf32-rounded) of `weight` [o,i,k,k] (transposed = 0) or [i,o,k,k] (= 1)."""
+    wp = torch.empty((k * k, o, i), dtype=torch.float32, device=weight.device)
+    _lib.check(_lib.load().fmi_conv_weight_prep(_ptr(weight), _ptr(wp), o, i, transposed, o, i, 0, 0, k, _lib.MMA_TF32, st),
+               "fmi_conv_weight_prep")
+    return wp
+
+
+def _conv_nhwc_call(x, i, wp, bias, o, b, h, w, k, st):
+    y = torch.empty((b, h, w, o), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().fmi_conv_nhwc(_ptr(x), i, w * i, h * w * i, _ptr(wp), _ptr(bias), 1, None, 0.0, _ptr(y), o, b, i, o, h, w,
+                                         k, 0, 0, 0, 2, 0, 0, _lib.MMA_TF32, st), "fmi_conv_nhwc")
+    return y
+
+
+class _ConvShared(Function):
+    """nn.Conv2d(k in {1, 3}, stride 1, padding k // 2) with batch-shared weights, forward AND backward on the tcgen05 kernels
+    (the reference: F.conv2d + cudnn_convolution_backward behind SpectralNorm.forward, external_function.py:70-72). Tensors stay
+    channels_last in memory: the [N,H,W,C] buffers of the kernels are returned as [N,C,H,W] views, so the LeakyReLU / pooling /
+    residual adds between two convolutions run on that layout and nothing is transposed. TF32 operands (the reference's own
+    GPU numerics under torch.backends.cudnn.allow_tf32), fp32 accumulation and storage.
+      forward   fmi_conv_nhwc (implicit GEMM, bias in the epilogue)
+      dx        the same kernel on the flipped, transposed weights
+      dweight   fmi_conv_wgrad_nhwc (pixel-contraction GEMM, split-K, fp32 red.add)
+      dbias     one reduction of dy"""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        st = _stream()
+        o, i, k, _ = weight.shape
+        b, _, h, w = x.shape
+        xn = _as_nhwc(x)
+        wc = weight.detach().contiguous().float()
+        bc = None if bias is None else bias.detach().contiguous().float()
+        y = _conv_nhwc_call(xn, i, _conv_wp(wc, o, i, k, 0, st), bc, o, b, h, w, k, st)
+        ctx.save_for_backward(xn, wc)
+        ctx.has_bias = bias is not None
+        return y.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, gy):
+        xn, wc = ctx.saved_tensors
+        st = _stream()
+        o, i, k, _ = wc.shape
+        b, h, w, _ = xn.shape
+        g = _as_nhwc(gy)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            wf = wc.flip(2, 3).contiguous() if k == 3 else wc
+            dx = _conv_nhwc_call(g, o, _conv_wp(wf, i, o, k, 1, st), None, i, b, h, w, k, st).permute(0, 3, 1, 2)
+        if ctx.needs_input_grad[1]:
+            dwp = torch.zeros((k * k, o, i), dtype=torch.float32, device=g.device)
+            _lib.check(_lib.load().fmi_conv_wgrad_nhwc(_ptr(xn), _ptr(g), _ptr(dwp), b, i, o, h, w, k, 0, _lib.MMA_TF32, st),
+                       "fmi_conv_wgrad_nhwc")
+            dw = dwp.permute(1, 2, 0).reshape(o, i, k, k)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = g.sum((0, 1, 2))
+        return dx, dw, db
+
+
+class _ConvTShared(Function):
+    """nn.ConvTranspose2d(3, stride 2, padding 1, output_padding 1) with batch-shared weights [I,O,3,3] (ResBlockDecoder's conv2 /
+    bypass, base_function.py:330-336), forward and backward on the kernels, channels_last in memory like `_ConvShared`:
+      forward   fmi_conv3x3_nhwc mode 3 (O <= 32: one GEMM over the 4 output-parity classes) or mode 2 (one GEMM per class)
+      dx        the gradient's 4 pixel-parity planes (fmi_space_to_planes_nhwc) through the stride-2 implicit GEMM
+                fmi_conv_nhwc(planes = 1) — dx[m] = sum_ky dy[2m - 1 + ky] W[ky] is Conv2d(O -> I, 3, stride 2, padding 1) with W as it lies
+      dweight   fmi_conv_wgrad_nhwc(transposed = 1) on the same planes
+      dbias     one reduction of dy"""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        st = _stream()
+        lib = _lib.load()
+        i, o = weight.shape[0], weight.shape[1]
+        b, _, h, w = x.shape
+        xn = _as_nhwc(x)
+        wc = weight.detach().contiguous().float()
+        bc = None if bias is None else bias.detach().contiguous().float()
+        merged = o <= 32
+        wp = (torch.zeros if merged else torch.empty)((4, 4 * o, i) if merged else (9, o, i), dtype=torch.float32, device=x.device)
+        _lib.check(lib.fmi_conv_weight_prep(_ptr(wc), _ptr(wp), o, i, 1, 4 * o if merged else o, i, 0, int(merged), 3,
+                                            _lib.MMA_TF32, st), "fmi_conv_weight_prep")
+        y = torch.empty((b, 2 * h, 2 * w, o), dtype=torch.float32, device=x.device)
+        _lib.check(lib.fmi_conv3x3_nhwc(_ptr(xn), i, _ptr(wp), _ptr(bc), _ptr(y), o, 0, None, 0, b, i, o, h, w, 3 if merged else 2, 2,
+                                        0.0, 0, _lib.MMA_TF32, st), "fmi_conv3x3_nhwc")
+        ctx.save_for_backward(xn, wc)
+        ctx.has_bias = bias is not None
+        return y.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, gy):
+        xn, wc = ctx.saved_tensors
+        st = _stream()
+        lib = _lib.load()
+        i, o = wc.shape[0], wc.shape[1]
+        b, h, w, _ = xn.shape
+        g = _as_nhwc(gy)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            planes = torch.empty((4 * b, h, w, o), dtype=torch.float32, device=g.device)
+            _lib.check(lib.fmi_space_to_planes_nhwc(_ptr(g), o, _ptr(planes), b, o, 2 * h, 2 * w, 1, _lib.MMA_TF32, st),
+                       "fmi_space_to_planes_nhwc")
+        if ctx.needs_input_grad[0]:
+            wp = _conv_wp(wc, i, o, 3, 0, st)      # W [I,O,3,3] read as the Conv2d weight [out = I][in = O]
+            dxn = torch.empty((b, h, w, i), dtype=torch.float32, device=g.device)
+            _lib.check(lib.fmi_conv_nhwc(_ptr(planes), o, w * o, h * w * o, _ptr(wp), None, 1, None, 0.0, _ptr(dxn), i, b, o, i, h, w,
+                                         3, 1, 0, 0, 2, 0, 0, _lib.MMA_TF32, st), "fmi_conv_nhwc")
+            dx = dxn.permute(0, 3, 1, 2)
+        if ctx.needs_input_grad[1]:
+            dwp = torch.zeros((9, o, i), dtype=torch.float32, device=g.device)
+            _lib.check(lib.fmi_conv_wgrad_nhwc(_ptr(xn), _ptr(planes), _ptr(dwp), b, i, o, h, w, 3, 1, _lib.MMA_TF32, st),
+                       "fmi_conv_wgrad_nhwc")
+            dw = dwp.permute(2, 1, 0).reshape(i, o, 3, 3)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = g.sum((0, 1, 2))
+        return dx, dw, db
+
+
+class _NormAct(Function):
+    """leaky_relu(InstanceNorm2d(x)) — the norm + activation pairs of ResBlockDecoder (base_function.py:338-344) — forward
+    (fmi_instnorm_stats_nhwc + fmi_norm_act_nhwc: one statistics pass, one normalise + activate pass) and backward
+    (fmi_instnorm_act_bwd_nhwc: two passes over (dy, x)) on channels_last tensors; the output is tf32-rounded, which is what
+    the convolution that reads it would make of it anyway."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps, slope):
+        st = _stream()
+        lib = _lib.load()
+        b, c, h, w = x.shape
+        hw = h * w
+        xn = _as_nhwc(x)
+        ga = None if gamma is None else gamma.detach().contiguous().float()
+        be = None if beta is None else beta.detach().contiguous().float()
+        ss = torch.empty((b, c, 2), dtype=torch.float32, device=x.device)
+        sums = torch.empty((b, c, 2), dtype=torch.float64, device=x.device)
+        _lib.check(lib.fmi_instnorm_stats_nhwc(_ptr(xn), c, _ptr(ga), _ptr(be), _ptr(ss), _ptr(sums), b, c, hw, float(eps),
+                                               _lib.MMA_TF32, st), "fmi_instnorm_stats_nhwc")
+        y = torch.empty((b, h, w, c), dtype=torch.float32, device=x.device)
+        _lib.check(lib.fmi_norm_act_nhwc(_ptr(xn), c, _ptr(y), c, _ptr(ss), b, c, hw, float(slope), _lib.MMA_TF32, st),
+                   "fmi_norm_act_nhwc")
+        mean = sums[..., 0] / hw
+        rstd = ((sums[..., 1] / hw - mean * mean).clamp_min_(0.0) + eps).rsqrt_()
+        ctx.save_for_backward(xn, ss, torch.stack((mean, rstd), -1).float().contiguous())
+        ctx.slope, ctx.affine = float(slope), (gamma is not None, beta is not None)
+        return y.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, gy):
+        xn, ss, mr = ctx.saved_tensors
+        b, h, w, c = xn.shape
+        g = _as_nhwc(gy)
+        dx = torch.empty_like(xn)
+        s2 = torch.empty((b, c, 2), dtype=torch.float64, device=g.device)
+        _lib.check(_lib.load().fmi_instnorm_act_bwd_nhwc(_ptr(g), _ptr(xn), _ptr(ss), _ptr(mr), _ptr(dx), _ptr(s2), b, c, h * w,
+                                                         ctx.slope, _stream()), "fmi_instnorm_act_bwd_nhwc")
+        tot = s2.sum(0).float()
+        return (dx.permute(0, 3, 1, 2), tot[:, 1].contiguous() if ctx.affine[0] else None,
+                tot[:, 0].contiguous() if ctx.affine[1] else None, None, None)
+
+
+def _train_kernels_on(x) -> bool:
+    """The conv blocks' training path (forward + backward on the kernels) applies: CUDA fp32 batch under autograd, TF32
+    convolutions allowed (the reference's own GPU numerics), single-pass TF32 operand mode. FMI_CONV_TRAIN=0 switches it off."""
+    if not (torch.is_tensor(x) and x.is_cuda and x.dim() == 4 and x.dtype == torch.float32 and torch.is_grad_enabled()):
+        return False
+    if os.environ.get("FMI_CONV_TRAIN") == "0" or os.environ.get("FMI_PICNET_CUDNN") == "1":
+        return False
+    return torch.backends.cudnn.allow_tf32 and mma_mode(torch.float32) == _lib.MMA_TF32 and not tf32_split()
+
+
+def norm_act_supported(norm, act, x) -> bool:
+    if not (isinstance(norm, nn.InstanceNorm2d) and not norm.track_running_stats and isinstance(act, (nn.LeakyReLU, nn.ReLU))):
+        return False
+    return _train_kernels_on(x) and x.shape[1] % 4 == 0 and x.shape[1] <= 1024 and x.shape[1] == norm.num_features
+
+
+def norm_act(norm, act, x):
+    """act(norm(x)) for an (InstanceNorm2d, LeakyReLU / ReLU) pair through `_NormAct`."""
+    slope = float(act.negative_slope) if isinstance(act, nn.LeakyReLU) else 0.0
+    return _NormAct.apply(x, norm.weight, norm.bias, norm.eps, slope)
+
+
+def run_block_sequential(seq, x):
+    """`seq(x)` for the `model` Sequential of a PICNet block (base_function.py:207-366) with every (InstanceNorm2d, activation)
+    pair fused into `_NormAct` when the training kernels apply; the wrapped convolutions take their own kernel path in
+    SpectralNorm.forward."""
+    mods = list(seq)
+    i = 0
+    while i < len(mods):
+        if i + 1 < len(mods) and norm_act_supported(mods[i], mods[i + 1], x):
+            x = norm_act(mods[i], mods[i + 1], x)
+            i += 2
+        else:
+            x = mods[i](x)
+            i += 1
+    return x
+
+
+def _pow2(v):
+    return v > 0 and (v & (v - 1)) == 0
+
+
+def conv_train_supported(conv, x) -> bool:
+    """True when `conv(x)` can run (forward and backward) through `_ConvShared` / `_ConvTShared`: a plain 3x3 / 1x1 stride-1
+    nn.Conv2d or a ConvTranspose2d(3, 2, 1, 1) on a CUDA fp32 batch under autograd, TF32 convolutions allowed (with them switched
+    off, or FMI_PRECISION=bf16, the reference formulation on cuDNN stays), channel counts and extents the GEMM kernels take."""
+    if not _train_kernels_on(x):
+        return False
+    h, w = x.shape[2], x.shape[3]
+    if isinstance(conv, nn.ConvTranspose2d):
+        if (conv.kernel_size != (3, 3) or conv.stride != (2, 2) or conv.padding != (1, 1) or conv.output_padding != (1, 1)
+                or conv.dilation != (1, 1) or conv.groups != 1):
+            return False
+    elif isinstance(conv, nn.Conv2d):
+        k = conv.kernel_size[0]
+        if (conv.kernel_size not in ((1, 1), (3, 3)) or conv.stride != (1, 1) or conv.padding != (k // 2, k // 2)
+                or conv.dilation != (1, 1) or conv.groups != 1 or conv.padding_mode != "zeros"):
+            return False
+    else:
+        return False
+    i, o = conv.in_channels, conv.out_channels
+    return (i == x.shape[1] and i % 32 == 0 and o % 32 == 0 and (i <= 256 or i % 256 == 0) and (o <= 128 or o % 128 == 0)
+            and (o <= 256 or o % 256 == 0) and i <= 1024 and o <= 1024 and _pow2(h) and _pow2(w) and w >= 4 and h * w >= 16)
+
+
+def conv_train(conv, x):
+    """`conv.forward(x)` for a (SpectralNorm-wrapped) convolution whose `.weight` may be a plain tensor (external_function.py:57)."""
+    fn = _ConvTShared if isinstance(conv, nn.ConvTranspose2d) else _ConvShared
+    return fn.apply(x, conv.weight, conv.bias)
+
+
 _PAD_BETA = 4.0   # exactly representable in bf16: the marker channel adds no rounding error to the logits
 
 

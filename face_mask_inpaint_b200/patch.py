@@ -328,6 +328,33 @@ def _install_picnet_decoder():
 
     ext.SpectralNorm._update_u_v = update_u_v
 
+    # ... and, under autograd, the wrapped 3x3 / 1x1 convolutions themselves: forward, data gradient and weight gradient on the
+    # implicit-GEMM kernels (ops._ConvShared), channels_last between them (external_function.py:70-72 calls module.forward).
+    def sn_forward(self, *args):
+        self._update_u_v()
+        if len(args) == 1 and ops.conv_train_supported(self.module, args[0]):
+            return ops.conv_train(self.module, args[0])
+        return self.module.forward(*args)
+
+    ext.SpectralNorm.forward = sn_forward
+
+    # ... and the (InstanceNorm2d, LeakyReLU) pairs of the blocks' `model` Sequential (base_function.py:262-268,302-305,361-364) as
+    # one statistics + one normalise-activate kernel forward, two passes backward (ops._NormAct), channels_last throughout.
+    bf = importlib.import_module("modules.pluralistic_model.base_function")
+
+    def res_block_forward(self, x):                            # base_function.py:262-268
+        main = ops.run_block_sequential(self.model, x)
+        if self.sample:
+            return self.pool(main) + self.pool(self.shortcut(x))
+        return main + self.shortcut(x)
+
+    def plain_block_forward(self, x):                          # base_function.py:302-305, 361-364
+        return ops.run_block_sequential(self.model, x) + self.shortcut(x)
+
+    bf.ResBlock.forward = res_block_forward
+    bf.ResBlockEncoderOptimized.forward = plain_block_forward
+    bf.ResBlockDecoder.forward = plain_block_forward
+
 
 def _blend(src, ref, full_mask):
     """mask * ref + (1 - mask) * src with the mask resized to the feature resolution (psp_encoders.py:135-138)."""

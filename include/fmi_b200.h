@@ -331,6 +331,28 @@ int fmi_conv3x3_nhwc(const void* x, int64_t x_pixel_stride, const void* wp, cons
 int fmi_output_conv_tanh(const void* xpad, const float* weight, const float* bias, float* img, float* pooled,
                          float* scratch, int B, int C, int O, int H, int W, int mma, void* stream);
 
+/* ---- f1 in training: backward of the batch-shared convolutions of the PICNet conv blocks -------------------------------------
+ * The reference differentiates SpectralNorm(nn.Conv2d) (base_function.py:207-305, network.py:73-172,296-365) with ATen / cuDNN
+ * (cudnn_convolution_backward). Here the data gradient is the forward implicit GEMM on the flipped, transposed weights
+ * (fmi_conv_nhwc with wp from fmi_conv_weight_prep(transposed = 1) of weight.flip(2, 3)) and the weight gradient is
+ * fmi_conv_wgrad_nhwc: dwp[t][o][i] += sum_{b,p} dy[b,p,o] * x[b,p + off_t,i] — a tcgen05 GEMM whose contraction index is the
+ * pixel (both operands MN-major NHWC boxes), split-K over pixel ranges and images, fp32 red.add into the caller's ZEROED dwp
+ * [ksize^2][O][I]. x [B,H,W,I], dy [B,H,W,O]: dense NHWC in the operand type; ksize 1 or 3 (stride 1, padding ksize/2);
+ * H, W powers of two >= 4; I, O multiples of 32.
+ * transposed = 1: ConvTranspose2d(3, stride 2, padding 1, output_padding 1) (base_function.py:330-336): dy = the 4 pixel-parity
+ * planes [4][B][H][W][O] (fmi_space_to_planes_nhwc) of the [B,2H,2W,O] output gradient; the data gradient of that layer is the
+ * stride-2 convolution fmi_conv_nhwc(planes = 1) of the same planes. */
+int fmi_conv_wgrad_nhwc(const void* x, const void* dy, float* dwp, int B, int I, int O, int H, int W, int ksize, int transposed,
+                        int mma, void* stream);
+
+/* Backward of y = leaky_relu(InstanceNorm2d(affine)(x)) as computed by fmi_instnorm_stats_nhwc + fmi_norm_act_nhwc (the norm +
+ * activation pairs of ResBlockDecoder, base_function.py:338-344; the reference differentiates F.instance_norm / leaky_relu with
+ * ATen): two passes over (dy, x), fp32 dense NHWC [B, HW, C]. scale_shift: the forward's [B][C][2]; mean_rstd [B][C][2] fp32;
+ * dx [B, HW, C]; sums [B][C][2] doubles = (sum_p dz, sum_p dz * xhat) — dbeta[c] = sum_b sums[b][c][0], dgamma[c] = sum_b
+ * sums[b][c][1]. C a multiple of 4, <= 1024. */
+int fmi_instnorm_act_bwd_nhwc(const float* dy, const float* x, const float* scale_shift, const float* mean_rstd, float* dx,
+                              double* sums, int B, int C, int HW, float slope, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * f2  the pSp encoder: IR-SE50 trunk, FPN adds and map2style heads of GradualStyleEncoder
  * (modules/psp/encoders/psp_encoders.py:13-37,100-152; units encoders/helpers.py:56-119), inference, NHWC in the operand type.
