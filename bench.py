@@ -579,10 +579,8 @@ def ours_train_picnet(h: Harness):
         # CUDA graph (graphs.CapturedStep); a step that cannot be captured is timed eagerly and says so
         from face_mask_inpaint_b200.graphs import CapturedStep
         try:
-            for _ in range(2):
-                run(*dev)
-            torch.cuda.synchronize()
-            captured = CapturedStep(run, *dev)
+            torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+            captured = CapturedStep(run, *dev, modules=(G, D))
         except Exception as ex:  # noqa: BLE001
             sys.stderr.write(f"[bench] train_picnet: CUDA-graph capture failed ({type(ex).__name__}: {str(ex)[:200]}); eager step\n")
             captured = None

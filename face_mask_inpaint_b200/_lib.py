@@ -80,6 +80,7 @@ PROTOTYPES = {
     "fmi_upsample_add_nhwc": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "fmi_avgpool_planes": (_i, [_vp, _vp, _i64, _i, _i, _i, _vp]),
     "fmi_instnorm_act_bwd_nhwc": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
+    "fmi_gemm_nt": (_i, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _i, _i, _i, _i, _i, _i, _vp]),
     "fmi_conv_wgrad_nhwc": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "fmi_spectral_norm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "fmi_spectral_norm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),

@@ -349,3 +349,23 @@ extern "C" int fmi_attn_bwd(const void* x, const float* wq, const float* bq, con
   return tf32 ? FMI_RUN_BWD(__nv_bfloat16, true) : FMI_RUN_BWD(__nv_bfloat16, false);
 #undef FMI_RUN_BWD
 }
+
+// Batched C[b] = A[b] B[b]^T (fp32 out) on the tcgen05 GEMM above, as a C entry: the loss-side S x S and Gram products (SURVEY 8f
+// rank 3: contextual_loss' cosine similarities, GramMatrix — torch.bmm in external_function.py:180-185,249-252, fp32 SIMT GEMMs
+// in the reference since matmul TF32 is off by default). A [batch, M, K], B [batch, N, K], K contiguous, in the operand type.
+extern "C" int fmi_gemm_nt(const void* A, int64_t lda, int64_t a_bs, const void* B, int64_t ldb, int64_t b_bs, float* C,
+                           int64_t ldc, int64_t c_bs, int batch, int M, int N, int K, int accumulate, int mma, void* stream) {
+  FMI_REQUIRE(mma == FMI_MMA_TF32 || mma == FMI_MMA_BF16, "gemm_nt: bad mma");
+  if (batch == 0 || M == 0 || N == 0) return FMI_OK;
+  FMI_REQUIRE(A && B && C && ldc >= N && ldc % 4 == 0 && fmi_aligned(C, 16), "gemm_nt: bad output");
+  int rc = fmi_device_check();
+  if (rc) return rc;
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.epi = EPI_STORE_F32;
+  p.accumulate = accumulate;
+  p.out0 = C; p.ldo = ldc; p.out_bs = c_bs;
+  cudaStream_t st = (cudaStream_t)stream;
+  return mma == FMI_MMA_TF32 ? launch_gemm_nt<true>(A, lda, a_bs, B, ldb, b_bs, batch, p, st)
+                             : launch_gemm_nt<false>(A, lda, a_bs, B, ldb, b_bs, batch, p, st);
+}

@@ -251,7 +251,7 @@ __device__ __forceinline__ void store4(__half* dst, const float (&o)[4]) {
 }
 
 template <typename T, bool VEC_OUT>
-__global__ void __launch_bounds__(256, (sizeof(T) == 4 ? 6 : 7)) upfirdn2d_blur_strip_kernel(const T* __restrict__ x, const float* __restrict__ k,
+__global__ void __launch_bounds__(256) upfirdn2d_blur_strip_kernel(const T* __restrict__ x, const float* __restrict__ k,
                                                                    T* __restrict__ y, UfdParams p, int tiles_x,
                                                                    float inv_tiles_x) {
   constexpr bool B16 = sizeof(T) == 2;

@@ -68,9 +68,13 @@ class CapturedForward:
                 fn(*self._args, **self._kwargs)
         torch.cuda.current_stream().wait_stream(self._stream)
         torch.cuda.synchronize()
-        with self._grad_mode(), torch.cuda.graph(self._graph, stream=self._stream):
+        with self._grad_mode(), torch.cuda.graph(self._graph, stream=self._stream, capture_error_mode=self._capture_mode()):
             self._static_out = fn(*self._args, **self._kwargs)
         self.replays = 0
+
+    @staticmethod
+    def _capture_mode():
+        return "global"
 
     @staticmethod
     def _grad_mode():
@@ -128,9 +132,33 @@ class CapturedStep(CapturedForward):
     returned tensors (losses) are static outputs. SpectralNorm u / v, Adam moments and the parameters advance on every replay
     exactly as in the eager step."""
 
+    def __init__(self, fn, *args, modules=(), **kwargs):
+        release_autograd_state(*modules)
+        super().__init__(fn, *args, **kwargs)
+
     @staticmethod
     def _grad_mode():
         return torch.enable_grad()
+
+    @staticmethod
+    def _capture_mode():
+        # with a process group alive, NCCL's own threads touch the CUDA runtime while the step is being captured: only calls
+        # of the capturing thread (and the autograd workers it drives) may invalidate the capture
+        import torch.distributed as dist
+        return "thread_local" if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 else "global"
+
+
+def release_autograd_state(*modules):
+    """Drop what keeps the previous iteration's autograd graph alive inside `modules`: a SpectralNorm-wrapped layer holds its
+    normalised weight — a non-leaf tensor whose grad_fn references the AccumulateGrad node of `weight_bar` — as a plain
+    attribute until the next forward replaces it (external_function.py:57), so that node, and the stream it was created on,
+    would survive from iteration to iteration; a capture on another stream then has to synchronise with that stream and is
+    invalidated. Detaching the attribute lets the next forward (on the capture stream) create fresh nodes."""
+    for m in modules:
+        for sub in m.modules():
+            w = sub.__dict__.get("weight")
+            if isinstance(w, torch.Tensor) and w.grad_fn is not None and hasattr(sub, "weight_bar"):
+                sub.__dict__["weight"] = w.detach()
 
 
 def auto_graph(forward):

@@ -77,8 +77,8 @@ class _ResidualPair(nn.Module):
         # (ops.run_block_sequential / SpectralNorm.forward -> ops.conv_train); otherwise this is the reference's Sequential
         main = ops.run_block_sequential(self.model, x)
         if self.sample:
-            return self.pool(main) + self.pool(self.shortcut(x))
-        return main + self.shortcut(x)
+            return ops.pool_sum(self.pool, main, ops.run_block_sequential(self.shortcut, x))
+        return main + ops.run_block_sequential(self.shortcut, x)
 
 
 def _pre_act(norm, act, channels):
@@ -249,7 +249,8 @@ class ResGenerator(nn.Module):
                 out, _ = getattr(self, f'attn{i}')(out, f_e, mask)
             if i > self.layers - 2:
                 output = getattr(self, f'out{i}')(out)
-                out = torch.cat([out, output], dim=1)
+                if i + 1 < self.layers:     # network.py:272 also concatenates after the LAST layer, where nothing reads it
+                    out = torch.cat([out, output], dim=1)     # (35 channels at 1024^2, written and differentiated for nothing)
         if pool_to is not None:
             output = F.adaptive_avg_pool2d(output, pool_to)
         return output

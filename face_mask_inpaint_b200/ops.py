@@ -449,8 +449,22 @@ class _ConvShared(Function):
                        "fmi_conv_wgrad_nhwc")
             dw = dwp.permute(1, 2, 0).reshape(o, i, k, k)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = g.sum((0, 1, 2))
+            db = _channel_sum(g)
         return dx, dw, db
+
+
+def _channel_sum(g):
+    """sum over (batch, rows, columns) of a dense NHWC fp32 tensor — a bias gradient — with the streaming statistics kernel of
+    InstanceNorm (fmi_instnorm_stats_nhwc: per-(image, channel) sums in double, 0.89 of the HBM rate) instead of ATen's
+    column reduction."""
+    b, h, w, c = g.shape
+    if c % 4 or c > 1024 or os.environ.get("FMI_CONV_TRAIN_DBIAS") == "0":
+        return g.sum((0, 1, 2))
+    ss = torch.empty((b, c, 2), dtype=torch.float32, device=g.device)
+    sums = torch.empty((b, c, 2), dtype=torch.float64, device=g.device)
+    _lib.check(_lib.load().fmi_instnorm_stats_nhwc(_ptr(g), c, None, None, _ptr(ss), _ptr(sums), b, c, h * w, 1e-5, _lib.MMA_TF32,
+                                                   _stream()), "fmi_instnorm_stats_nhwc")
+    return sums[..., 0].sum(0).float()
 
 
 class _ConvTShared(Function):
@@ -507,7 +521,7 @@ class _ConvTShared(Function):
                        "fmi_conv_wgrad_nhwc")
             dw = dwp.permute(2, 1, 0).reshape(i, o, 3, 3)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = g.sum((0, 1, 2))
+            db = _channel_sum(g)
         return dx, dw, db
 
 
@@ -524,26 +538,34 @@ class _NormAct(Function):
         b, c, h, w = x.shape
         hw = h * w
         xn = _as_nhwc(x)
+        y = torch.empty((b, h, w, c), dtype=torch.float32, device=x.device)
+        ctx.slope, ctx.affine, ctx.normed = float(slope), (gamma is not None, beta is not None), eps is not None
+        if eps is None:     # activation only (blocks without normalisation): y = tf32(lrelu(x))
+            _lib.check(lib.fmi_norm_act_nhwc(_ptr(xn), c, _ptr(y), c, None, b, c, hw, float(slope), _lib.MMA_TF32, st),
+                       "fmi_norm_act_nhwc")
+            ctx.save_for_backward(xn)
+            return y.permute(0, 3, 1, 2)
         ga = None if gamma is None else gamma.detach().contiguous().float()
         be = None if beta is None else beta.detach().contiguous().float()
         ss = torch.empty((b, c, 2), dtype=torch.float32, device=x.device)
         sums = torch.empty((b, c, 2), dtype=torch.float64, device=x.device)
         _lib.check(lib.fmi_instnorm_stats_nhwc(_ptr(xn), c, _ptr(ga), _ptr(be), _ptr(ss), _ptr(sums), b, c, hw, float(eps),
                                                _lib.MMA_TF32, st), "fmi_instnorm_stats_nhwc")
-        y = torch.empty((b, h, w, c), dtype=torch.float32, device=x.device)
         _lib.check(lib.fmi_norm_act_nhwc(_ptr(xn), c, _ptr(y), c, _ptr(ss), b, c, hw, float(slope), _lib.MMA_TF32, st),
                    "fmi_norm_act_nhwc")
         mean = sums[..., 0] / hw
         rstd = ((sums[..., 1] / hw - mean * mean).clamp_min_(0.0) + eps).rsqrt_()
         ctx.save_for_backward(xn, ss, torch.stack((mean, rstd), -1).float().contiguous())
-        ctx.slope, ctx.affine = float(slope), (gamma is not None, beta is not None)
         return y.permute(0, 3, 1, 2)
 
     @staticmethod
     def backward(ctx, gy):
+        g = _as_nhwc(gy)
+        if not ctx.normed:
+            xn, = ctx.saved_tensors
+            return torch.ops.aten.leaky_relu_backward(g, xn, ctx.slope, False).permute(0, 3, 1, 2), None, None, None, None
         xn, ss, mr = ctx.saved_tensors
         b, h, w, c = xn.shape
-        g = _as_nhwc(gy)
         dx = torch.empty_like(xn)
         s2 = torch.empty((b, c, 2), dtype=torch.float64, device=g.device)
         _lib.check(_lib.load().fmi_instnorm_act_bwd_nhwc(_ptr(g), _ptr(xn), _ptr(ss), _ptr(mr), _ptr(dx), _ptr(s2), b, c, h * w,
@@ -551,6 +573,29 @@ class _NormAct(Function):
         tot = s2.sum(0).float()
         return (dx.permute(0, 3, 1, 2), tot[:, 1].contiguous() if ctx.affine[0] else None,
                 tot[:, 0].contiguous() if ctx.affine[1] else None, None, None)
+
+
+class _RoundTF32(Function):
+    """x rounded to TF32 (round to nearest), gradient passed through: for a convolution input that no kernel of this package
+    produced (a block input read by the shortcut convolution): see `act_round`."""
+
+    @staticmethod
+    def forward(ctx, x):
+        b, c, h, w = x.shape
+        xn = _as_nhwc(x)
+        y = torch.empty((b, h, w, c), dtype=torch.float32, device=x.device)
+        _lib.check(_lib.load().fmi_norm_act_nhwc(_ptr(xn), c, _ptr(y), c, None, b, c, h * w, 1.0, _lib.MMA_TF32, _stream()),
+                   "fmi_norm_act_nhwc")
+        return y.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, gy):
+        return gy
+
+
+def _mark_tf32(t):
+    t._fmi_tf32 = True      # values are TF32-representable: a convolution reading it needs no rounding pass
+    return t
 
 
 def _train_kernels_on(x) -> bool:
@@ -572,7 +617,53 @@ def norm_act_supported(norm, act, x) -> bool:
 def norm_act(norm, act, x):
     """act(norm(x)) for an (InstanceNorm2d, LeakyReLU / ReLU) pair through `_NormAct`."""
     slope = float(act.negative_slope) if isinstance(act, nn.LeakyReLU) else 0.0
-    return _NormAct.apply(x, norm.weight, norm.bias, norm.eps, slope)
+    return _mark_tf32(_NormAct.apply(x, norm.weight, norm.bias, norm.eps, slope))
+
+
+def act_round_supported(act, x) -> bool:
+    return isinstance(act, (nn.LeakyReLU, nn.ReLU)) and not act.inplace and _train_kernels_on(x) and x.shape[1] % 4 == 0
+
+
+def act_round(act, x):
+    """act(x) with the result rounded to TF32 (round to nearest): the convolution that reads it would otherwise TRUNCATE the fp32
+    values (kind::tf32 ignores the low 13 mantissa bits), a bias of -3e-4 per operand that does not average out over the
+    pixel sum of a weight gradient."""
+    slope = float(act.negative_slope) if isinstance(act, nn.LeakyReLU) else 0.0
+    return _mark_tf32(_NormAct.apply(x, None, None, None, slope))
+
+
+class _AvgPool2(Function):
+    """nn.AvgPool2d(2, 2) with the gradient as a nearest-neighbour up-sampling (ATen's avg_pool2d_backward kernel measured 55 us
+    per call on the encoder / discriminator maps, 2 ms per GAN step)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return torch.nn.functional.avg_pool2d(x, 2, 2)
+
+    @staticmethod
+    def backward(ctx, g):
+        return torch.nn.functional.interpolate(g, scale_factor=2, mode="nearest") * 0.25
+
+
+def _is_pool2(m) -> bool:
+    def two(v):
+        return v in (2, (2, 2))
+    return (isinstance(m, nn.AvgPool2d) and two(m.kernel_size) and two(m.stride) and m.padding in (0, (0, 0)) and not m.ceil_mode
+            and m.divisor_override is None)
+
+
+def avg_pool2(pool, x):
+    if _is_pool2(pool) and _train_kernels_on(x) and x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0:
+        return _AvgPool2.apply(x)
+    return pool(x)
+
+
+def pool_sum(pool, a, b):
+    """pool(a) + pool(b) (ResBlock with sample_type 'down', base_function.py:262-264); average pooling is linear, so under the
+    training kernels the sum is pooled once."""
+    if _is_pool2(pool) and _train_kernels_on(a) and a.shape == b.shape and a.shape[2] % 2 == 0 and a.shape[3] % 2 == 0:
+        return _AvgPool2.apply(a + b)
+    return pool(a) + pool(b)
 
 
 def run_block_sequential(seq, x):
@@ -585,6 +676,12 @@ def run_block_sequential(seq, x):
         if i + 1 < len(mods) and norm_act_supported(mods[i], mods[i + 1], x):
             x = norm_act(mods[i], mods[i + 1], x)
             i += 2
+        elif act_round_supported(mods[i], x):
+            x = act_round(mods[i], x)
+            i += 1
+        elif isinstance(mods[i], nn.AvgPool2d):
+            x = avg_pool2(mods[i], x)
+            i += 1
         else:
             x = mods[i](x)
             i += 1
@@ -621,7 +718,96 @@ def conv_train_supported(conv, x) -> bool:
 def conv_train(conv, x):
     """`conv.forward(x)` for a (SpectralNorm-wrapped) convolution whose `.weight` may be a plain tensor (external_function.py:57)."""
     fn = _ConvTShared if isinstance(conv, nn.ConvTranspose2d) else _ConvShared
+    if not getattr(x, "_fmi_tf32", False) and x.shape[1] % 4 == 0 and os.environ.get("FMI_CONV_TRAIN_ROUND") != "0":
+        x = _RoundTF32.apply(x)     # the MMA would truncate instead (a bias that survives the pixel sum of the weight gradient)
     return fn.apply(x, conv.weight, conv.bias)
+
+
+# ------------------------------------------------------------------------------------------------
+# f3 (SURVEY 8f rank 3): loss-side S x S / Gram products
+# ------------------------------------------------------------------------------------------------
+def _split3(t, order):
+    """[B, R, K] fp32 -> [B, R, 3K]: x = hi + lo (hi = the TF32 part), laid out [hi | hi | lo] (order 0) or [hi | lo | hi]
+    (order 1) along K, so that one TF32 GEMM over 3K sums hi*hi + hi*lo + lo*hi: fp32-class products (fmi_tf32_split3)."""
+    b, r, k = t.shape
+    out = torch.empty((b, r, 3 * k), dtype=torch.float32, device=t.device)
+    _lib.check(_lib.load().fmi_tf32_split3(_ptr(t), k, _ptr(out), b * r, k, order, _stream()), "fmi_tf32_split3")
+    return out
+
+
+def _bmm_nt_raw(a, b):
+    a, b = a.contiguous().float(), b.contiguous().float()
+    bs, m, k = a.shape
+    n = b.shape[1]
+    c = torch.empty((bs, m, n), dtype=torch.float32, device=a.device)
+    a3, b3 = _split3(a, 0), _split3(b, 1)
+    _lib.check(_lib.load().fmi_gemm_nt(_ptr(a3), 3 * k, m * 3 * k, _ptr(b3), 3 * k, n * 3 * k, _ptr(c), n, m * n, bs, m, n, 3 * k, 0,
+                                       _lib.MMA_TF32, _stream()), "fmi_gemm_nt")
+    return c
+
+
+class _BmmNT(Function):
+    """C[b] = A[b] @ B[b]^T for [B,M,K] x [B,N,K] fp32 (K contiguous) on the tcgen05 GEMM with error-compensated 3xTF32 operands;
+    backward dA = G @ B, dB = G^T @ A through the same kernel (on transposed copies)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        ctx.save_for_backward(a, b)
+        return _bmm_nt_raw(a, b)
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        da = db = None
+        if ctx.needs_input_grad[0]:
+            da = _bmm_nt_raw(g, b.transpose(1, 2))          # [B,M,N] x [B,K,N]^T
+        if ctx.needs_input_grad[1]:
+            db = _bmm_nt_raw(g.transpose(1, 2), a.transpose(1, 2))
+        return da, db
+
+
+def bmm_nt_supported(a, b) -> bool:
+    return (torch.is_tensor(a) and a.is_cuda and b.is_cuda and a.dim() == 3 and b.dim() == 3 and a.dtype == torch.float32
+            and b.dtype == torch.float32 and a.shape[0] == b.shape[0] and a.shape[2] == b.shape[2] and a.shape[2] % 4 == 0
+            and a.shape[1] % 8 == 0 and b.shape[1] % 8 == 0 and os.environ.get("FMI_LOSS_KERNELS") != "0")
+
+
+def bmm_nt(a, b):
+    """torch.bmm(a, b.transpose(1, 2)) (the reference's loss-side products) on the tensor cores at fp32-class accuracy."""
+    _need_cuda(a, b)
+    return _BmmNT.apply(a, b)
+
+
+def gram_matrix(input):
+    """GramMatrix (modules/pluralistic_model/external_function.py:180-185): features @ features^T / (C H W) per image."""
+    s = input.size()
+    f = input.reshape(s[0], s[1], s[2] * s[3])
+    g = bmm_nt(f, f) if bmm_nt_supported(f, f) else torch.bmm(f, f.transpose(1, 2))
+    return g.div(s[1] * s[2] * s[3])
+
+
+def contextual_loss(x, y, h=0.5):
+    """contextual_loss (external_function.py:231-274), same arithmetic; the S x S cosine similarities — torch.bmm there, an fp32
+    SIMT GEMM — on the tcgen05 GEMM (3xTF32 operands: d / (d_min + 1e-5) amplifies any error of the similarities)."""
+    assert x.size() == y.size()
+    n, c, hh, ww = x.size()
+    y_mu = y.mean(3).mean(2).mean(0).reshape(1, -1, 1, 1)
+    x_centered, y_centered = x - y_mu, y - y_mu
+    x_normalized = x_centered / torch.norm(x_centered, p=2, dim=1, keepdim=True)
+    y_normalized = y_centered / torch.norm(y_centered, p=2, dim=1, keepdim=True)
+    xt = x_normalized.reshape(n, c, -1).transpose(1, 2)       # [N, S, C]
+    yt = y_normalized.reshape(n, c, -1).transpose(1, 2)
+    if bmm_nt_supported(xt, yt):
+        cosine_sim = bmm_nt(xt.contiguous(), yt.contiguous())
+    else:
+        cosine_sim = torch.bmm(xt, yt.transpose(1, 2))
+    d = 1 - cosine_sim
+    d_min, _ = torch.min(d, dim=2, keepdim=True)
+    d_tilde = d / (d_min + 1e-5)
+    w = torch.exp((1 - d_tilde) / h)
+    cx_ij = w / torch.sum(w, dim=2, keepdim=True)
+    cx = torch.mean(torch.max(cx_ij, dim=1)[0], dim=1)
+    return torch.mean(-torch.log(cx + 1e-5))
 
 
 _PAD_BETA = 4.0   # exactly representable in bf16: the marker channel adds no rounding error to the logits

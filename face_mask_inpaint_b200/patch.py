@@ -287,8 +287,13 @@ def _install_picnet_decoder():
     net = importlib.import_module("modules.pluralistic_model.network")
     ref_forward = net.ResGenerator.forward
 
+    from .modules.picnet import ResGenerator as _MirrorGen
+
     def res_generator_forward(self, encoded, z=None, f_e=None, mask=None, pool_to=None):
         if not picnet_fast.supported(self, encoded):
+            if type(self).forward is res_generator_forward and os.environ.get("FMI_PICNET_CUDNN") != "1":
+                # the mirror's loop: network.py:247-268 without the concatenation after the last layer that nothing reads
+                return _MirrorGen.forward(self, encoded, z, f_e, mask, pool_to)
             out = ref_forward(self, encoded, z, f_e, mask)
             return F.adaptive_avg_pool2d(out, pool_to) if pool_to is not None else out
         if z is not None and not self._fmi_z_ok:            # network.py:249-254 on cuDNN for unusual z -> f blocks
@@ -308,6 +313,11 @@ def _install_picnet_decoder():
         return ref_enc_forward(self, img)
 
     net.ResEncoder.forward = res_encoder_forward
+
+    # ResGenerator.get_z (network.py:270-293): torch.distributions' argument validation reads a flag back to the host, which a
+    # CUDA-graph capture cannot contain; the mirror's get_z is the same sampling with the validation skipped while capturing
+    from .modules.picnet import ResGenerator as _MirrorGenerator
+    net.ResGenerator.get_z = _MirrorGenerator.get_z
 
     # SpectralNorm (external_function.py:16-72) on the paths that keep the reference's own block forwards (training, the
     # discriminator): its power iteration + division — ~13 ATen launches per wrapped convolution and forward, ~160 wrapped
@@ -345,11 +355,20 @@ def _install_picnet_decoder():
     def res_block_forward(self, x):                            # base_function.py:262-268
         main = ops.run_block_sequential(self.model, x)
         if self.sample:
-            return self.pool(main) + self.pool(self.shortcut(x))
-        return main + self.shortcut(x)
+            return ops.pool_sum(self.pool, main, ops.run_block_sequential(self.shortcut, x))
+        return main + ops.run_block_sequential(self.shortcut, x)
 
     def plain_block_forward(self, x):                          # base_function.py:302-305, 361-364
-        return ops.run_block_sequential(self.model, x) + self.shortcut(x)
+        return ops.run_block_sequential(self.model, x) + ops.run_block_sequential(self.shortcut, x)
+
+    # f3: the loss-side S x S / Gram products (torch.bmm = fp32 SIMT GEMMs in the reference) on the tcgen05 GEMM; modules.loss binds
+    # StyleLoss / contextual_loss by name at import time (loss.py:10-11), so they are rebound everywhere
+    def style_loss(input, target):                             # external_function.py:188-192
+        return torch.nn.functional.l1_loss(ops.gram_matrix(input), ops.gram_matrix(target).detach())
+
+    _rebind_everywhere("GramMatrix", ext.GramMatrix, ops.gram_matrix)
+    _rebind_everywhere("StyleLoss", ext.StyleLoss, style_loss)
+    _rebind_everywhere("contextual_loss", ext.contextual_loss, ops.contextual_loss)
 
     bf.ResBlock.forward = res_block_forward
     bf.ResBlockEncoderOptimized.forward = plain_block_forward

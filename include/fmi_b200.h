@@ -353,6 +353,15 @@ int fmi_conv_wgrad_nhwc(const void* x, const void* dy, float* dwp, int B, int I,
 int fmi_instnorm_act_bwd_nhwc(const float* dy, const float* x, const float* scale_shift, const float* mean_rstd, float* dx,
                               double* sums, int B, int C, int HW, float slope, void* stream);
 
+/* ---- f3: loss-side S x S and Gram products ----------------------------------------------------------------
+ * C[b] = A[b] * B[b]^T, fp32 out, on the tcgen05 GEMM (csrc/gemm.cuh): replaces torch.bmm in contextual_loss (cosine similarities
+ * of VGG features, external_function.py:249-252) and GramMatrix (:180-185), which the reference runs as fp32 SIMT GEMMs (matmul TF32
+ * is off by default). A [batch, M, K] / B [batch, N, K]: K contiguous, row pitches lda / ldb and batch strides in ELEMENTS of the
+ * operand type (mma = FMI_MMA_TF32: fp32 read as tf32; pass fmi_tf32_split3 operands, K tripled, for fp32-class products);
+ * C [batch, M, ldc] fp32, accumulate = 1 adds to it. N a multiple of 8, rows 16-byte aligned. */
+int fmi_gemm_nt(const void* A, int64_t lda, int64_t a_bs, const void* B, int64_t ldb, int64_t b_bs, float* C, int64_t ldc,
+                int64_t c_bs, int batch, int M, int N, int K, int accumulate, int mma, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * f2  the pSp encoder: IR-SE50 trunk, FPN adds and map2style heads of GradualStyleEncoder
  * (modules/psp/encoders/psp_encoders.py:13-37,100-152; units encoders/helpers.py:56-119), inference, NHWC in the operand type.

@@ -404,3 +404,30 @@ def upsample_add(x, y):
     """modules/psp/encoders/psp_encoders.py:83-98."""
     return F.interpolate(x, size=y.shape[-2:], mode="bilinear", align_corners=True) + y
 
+
+def gram_matrix(x):
+    """modules/pluralistic_model/external_function.py:180-185 (GramMatrix): features @ features^T / (C*H*W) per image."""
+    n, c, h, w = x.shape
+    f = x.reshape(n, c, h * w)
+    return torch.bmm(f, f.transpose(1, 2)) / (c * h * w)
+
+
+def style_loss(x, target):
+    """external_function.py:188-192 (StyleLoss): L1 between the Gram matrices."""
+    return F.l1_loss(gram_matrix(x), gram_matrix(target).detach())
+
+
+def contextual_loss(x, y, h=0.5):
+    """external_function.py:231-274: channel-centred (batch mean of y), L2-normalised features, S x S cosine similarities,
+    d = 1 - cos, d~ = d / (min_j d + 1e-5), w = exp((1 - d~) / h), cx = w / sum_j w, loss = mean_n -log(mean_j max_i cx + 1e-5)."""
+    n, c = x.shape[:2]
+    y_mu = y.mean(3).mean(2).mean(0).reshape(1, -1, 1, 1)
+    xc, yc = x - y_mu, y - y_mu
+    xn = (xc / torch.norm(xc, p=2, dim=1, keepdim=True)).reshape(n, c, -1)
+    yn = (yc / torch.norm(yc, p=2, dim=1, keepdim=True)).reshape(n, c, -1)
+    d = 1 - torch.bmm(xn.transpose(1, 2), yn)
+    d_min, _ = torch.min(d, dim=2, keepdim=True)
+    w = torch.exp((1 - d / (d_min + 1e-5)) / h)
+    cx_ij = w / torch.sum(w, dim=2, keepdim=True)
+    cx = torch.mean(torch.max(cx_ij, dim=1)[0], dim=1)
+    return torch.mean(-torch.log(cx + 1e-5))

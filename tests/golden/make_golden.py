@@ -273,6 +273,17 @@ def gen_ssim():
                         ssim_per_image=np_(ref_ssim(a, b, size_average=False)))
 
 
+def gen_loss_side():
+    """f3: the reference's own GramMatrix / StyleLoss / contextual_loss (modules/pluralistic_model/external_function.py:180-192,
+    231-274) on seeded VGG-like feature maps: pins oracle.gram_matrix / style_loss / contextual_loss."""
+    from modules.pluralistic_model.external_function import GramMatrix, StyleLoss, contextual_loss
+    g = torch.Generator().manual_seed(91)
+    x = torch.relu(torch.randn(2, 64, 12, 8, generator=g))
+    y = torch.relu(x + 0.5 * torch.randn(x.shape, generator=g))
+    np.savez_compressed(OUT / "loss_side.npz", x=np_(x), y=np_(y), gram=np_(GramMatrix(x)), style=np_(StyleLoss(x, y)),
+                        cx=np_(contextual_loss(x, y)), cx_h1=np_(contextual_loss(y, x, h=1.0)))
+
+
 def gen_refpsp(size=256):
     """BASELINE config 3 (reduced output size for the fixture): the reference's pSp (modules/psp/psp.py) with
     GradualStyleEncoder(50, 'ir_se') + attention and its StyleGAN2 decoder, `load_weights` bypassed (no pretrained files
@@ -340,9 +351,11 @@ def gen_psp_encoder_pieces():
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    if len(sys.argv) > 1 and sys.argv[1] in ("picnet", "refpsp", "picnet_blocks", "ssim", "psp_encoder"):
+    if len(sys.argv) > 1 and sys.argv[1] in ("picnet", "refpsp", "picnet_blocks", "ssim", "psp_encoder", "loss_side"):
         if sys.argv[1] == "psp_encoder":
             gen_psp_encoder_pieces()
+        elif sys.argv[1] == "loss_side":
+            gen_loss_side()
         elif sys.argv[1] == "picnet":
             gen_picnet()
         elif sys.argv[1] == "picnet_blocks":
@@ -362,5 +375,6 @@ if __name__ == "__main__":
     gen_ssim()
     gen_refpsp()
     gen_psp_encoder_pieces()
+    gen_loss_side()
     for f in sorted(OUT.glob("*.npz")):
         print(f.name, f.stat().st_size)

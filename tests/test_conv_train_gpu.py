@@ -93,7 +93,7 @@ def test_spectral_norm_block_trains_on_the_kernels():
     # forward within the fp32 contract; gradients pass through leaky-ReLU' of the hidden activation, which is discontinuous: an
     # element within TF32 rounding of zero takes the other slope (cuDNN's own TF32 run is 2e-2 from strict fp32 on dx for the same
     # reason), so gradients are held to the error of the reference's own default GPU numerics
-    assert errs[0] <= 1e-3 and all(e <= 3 * c + 1e-3 for e, c in zip(errs, errs_cudnn)), (errs, errs_cudnn)
+    assert errs[0] <= 1e-3 and all(e <= 3 * c + 1e-3 for e, c in zip(errs, errs_cudnn)), " ".join(f"{e:.1e}/{c:.1e}" for e, c in zip(errs, errs_cudnn))
 
 
 def test_conv_train_keeps_cudnn_where_it_must():
@@ -102,7 +102,8 @@ def test_conv_train_keeps_cudnn_where_it_must():
     assert ops.conv_train_supported(nn.Conv2d(32, 32, 3, 1, 1), x)
     assert not ops.conv_train_supported(nn.Conv2d(3, 32, 3, 1, 1), torch.randn(2, 3, 16, 16, device=DEV))    # image channels
     assert not ops.conv_train_supported(nn.Conv2d(32, 32, 3, 2, 1), x)                                        # stride
-    assert not ops.conv_train_supported(nn.ConvTranspose2d(32, 32, 3, 2, 1, 1), x)
+    assert ops.conv_train_supported(nn.ConvTranspose2d(32, 32, 3, 2, 1, 1), x)                               # decoder up-conv
+    assert not ops.conv_train_supported(nn.ConvTranspose2d(32, 32, 4, 2, 1), x)
     assert not ops.conv_train_supported(nn.Conv2d(32, 32, 3, 1, 1), torch.randn(2, 32, 12, 12, device=DEV))   # extents
     with torch.no_grad():
         assert not ops.conv_train_supported(nn.Conv2d(32, 32, 3, 1, 1), x)                                   # inference path
@@ -204,4 +205,27 @@ def test_decoder_block_trains_on_the_kernels():
     tf32 = step("0")
     errs = [rel_err(a, r) for a, r in zip(got, want)]
     errs_cudnn = [rel_err(a, r) for a, r in zip(tf32, want)]
-    assert len(got) == len(want) and errs[0] <= 1e-3 and all(e <= 3 * c + 1e-3 for e, c in zip(errs, errs_cudnn)), (errs, errs_cudnn)
+    assert len(got) == len(want) and errs[0] <= 1e-3 and all(e <= 3 * c + 1e-3 for e, c in zip(errs, errs_cudnn)), \
+        " ".join(f"{e:.1e}/{c:.1e}" for e, c in zip(errs, errs_cudnn))
+
+
+def test_pooling_and_bias_sum_helpers():
+    from face_mask_inpaint_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    a = torch.randn(2, 32, 16, 8, generator=g).to(DEV).requires_grad_(True)
+    b = torch.randn(2, 32, 16, 8, generator=g).to(DEV).requires_grad_(True)
+    pool = nn.AvgPool2d(kernel_size=2, stride=2)
+    gy = torch.randn(2, 32, 8, 4, generator=g).to(DEV)
+    want = pool(a) + pool(b)
+    want.backward(gy)
+    ga, gb = a.grad.clone(), b.grad.clone()
+    a.grad = b.grad = None
+    got = ops.pool_sum(pool, a, b)          # pooled once: average pooling is linear
+    got.backward(gy)
+    assert rel_err(got, want) <= 1e-6 and rel_err(a.grad, ga) <= 1e-6 and rel_err(b.grad, gb) <= 1e-6
+    a.grad = None
+    ops.avg_pool2(pool, a).backward(gy)
+    assert rel_err(a.grad, ga) <= 1e-6
+    assert ops.pool_sum(nn.AvgPool2d(3, 1, 1), a, b).shape == a.shape      # anything else stays ATen's pooling
+    x = torch.randn(3, 20, 24, 64, generator=g).to(DEV)                   # NHWC
+    assert rel_err(ops._channel_sum(x), x.double().sum((0, 1, 2))) <= 1e-6

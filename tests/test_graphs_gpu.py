@@ -107,3 +107,39 @@ def test_auto_graph_wrapper_keys_graphs_by_shape_and_falls_back_under_autograd()
     wrapped.train()
     out = wrapped(*a1)
     assert out.requires_grad and len(module_cache(wrapped)["graphs"]) == 2
+
+
+def test_captured_train_step_matches_eager():
+    """graphs.CapturedStep: forward + loss + backward + Adam(capturable) of a SpectralNorm conv block as ONE CUDA graph; after k
+    replays parameters, Adam state and SpectralNorm's u / v equal k eager steps (same kernels, same order)."""
+    import copy
+    from torch import nn
+    from face_mask_inpaint_b200.graphs import CapturedStep
+    from face_mask_inpaint_b200.modules.picnet import ResBlock
+    torch.manual_seed(1)
+    net = ResBlock(32, 32, 32, norm_layer=None, nonlinearity=nn.LeakyReLU(0.1), sample_type='down', use_spect=True).cuda()
+    ref = copy.deepcopy(net)
+    x = torch.randn(2, 32, 16, 16, device="cuda")
+    xs = [torch.randn(2, 32, 16, 16, device="cuda") for _ in range(3)]
+
+    def make_step(m, opt):
+        def step(inp):
+            loss = (m(inp) ** 2).mean()
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            return loss
+        return step
+
+    opt_a = torch.optim.Adam(net.parameters(), lr=1e-3, capturable=True)
+    opt_b = torch.optim.Adam(ref.parameters(), lr=1e-3, capturable=True)
+    cap = CapturedStep(make_step(net, opt_a), x, warmup=3, modules=(net,))     # 3 warm-up steps on x (the capture itself runs nothing)
+    eager = make_step(ref, opt_b)
+    for _ in range(3):
+        eager(x)
+    for inp in xs:
+        lg = cap(inp).clone()
+        le = eager(inp)
+        assert abs(float(lg) - float(le)) <= 1e-5 * max(1.0, abs(float(le)))
+    for (n1, p1), (_, p2) in zip(net.named_parameters(), ref.named_parameters()):
+        assert (p1 - p2).abs().max().item() <= 1e-5 * max(1.0, p2.abs().max().item()), n1

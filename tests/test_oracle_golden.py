@@ -200,3 +200,13 @@ def test_folded_unit_of_the_kernel_path_matches_the_golden(tag, monkeypatch):
             r = r * gate.view(*gate.shape, 1, 1)
         got = r + sc
     assert rel_err(got, g[f"{tag}.y"]) <= 2e-5
+
+
+def test_loss_side_ops_match_reference():
+    """f3: oracle.gram_matrix / style_loss / contextual_loss against the reference's own functions
+    (modules/pluralistic_model/external_function.py:180-192, 231-274; golden from tests/golden/make_golden.py loss_side)."""
+    g = load("loss_side.npz")
+    assert rel_err(O.gram_matrix(g["x"]), g["gram"]) <= 1e-6
+    assert rel_err(O.style_loss(g["x"], g["y"]), g["style"]) <= 1e-6
+    assert rel_err(O.contextual_loss(g["x"], g["y"]), g["cx"]) <= 1e-6
+    assert rel_err(O.contextual_loss(g["y"], g["x"], h=1.0), g["cx_h1"]) <= 1e-6
