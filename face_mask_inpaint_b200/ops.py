@@ -388,9 +388,21 @@ def conv1x1(x, weight, bias=None):
 # batch-shared convolutions of the PICNet conv blocks in TRAINING (SURVEY 8f rank 1 + row g)
 # ------------------------------------------------------------------------------------------------
 def _as_nhwc(t):
-    """[N,C,H,W] fp32 -> dense [N,H,W,C] (a view when `t` already is channels_last in memory)."""
+    """[N,C,H,W] fp32 -> dense [N,H,W,C]: a view when `t` already is channels_last in memory, else one copy that is remembered
+    on the tensor (keyed by its version counter) — a block input or a gradient in NCHW layout is read by two Functions (main
+    path and shortcut), which would otherwise transpose it twice."""
     v = t.permute(0, 2, 3, 1)
-    return v if v.is_contiguous() and t.dtype == torch.float32 else v.contiguous().float()
+    if v.is_contiguous() and t.dtype == torch.float32:
+        return v
+    hit = getattr(t, "_fmi_nhwc", None)
+    if hit is not None and hit[0] == t._version:
+        return hit[1]
+    out = v.contiguous().float()
+    try:
+        t._fmi_nhwc = (t._version, out)
+    except (AttributeError, RuntimeError):
+        pass
+    return out
 
 
 def _conv_wp(weight, o, i, k, transposed, st):
@@ -739,11 +751,28 @@ def _bmm_nt_raw(a, b):
     a, b = a.contiguous().float(), b.contiguous().float()
     bs, m, k = a.shape
     n = b.shape[1]
-    c = torch.empty((bs, m, n), dtype=torch.float32, device=a.device)
+    lib, st = _lib.load(), _stream()
     a3, b3 = _split3(a, 0), _split3(b, 1)
-    _lib.check(_lib.load().fmi_gemm_nt(_ptr(a3), 3 * k, m * 3 * k, _ptr(b3), 3 * k, n * 3 * k, _ptr(c), n, m * n, bs, m, n, 3 * k, 0,
-                                       _lib.MMA_TF32, _stream()), "fmi_gemm_nt")
-    return c
+    k3 = 3 * k
+    # Gram matrices (C x C outputs over H*W up to 65536 pixels) have few output tiles and a very long contraction: split K over
+    # `s` chunks that run as extra batch entries of the one launch (operands re-laid [image, chunk, row, k]), partial products
+    # summed afterwards — without it one CTA per image walks the whole contraction (measured 1 ms per 64 x 64 Gram)
+    tiles = bs * ((m + 127) // 128) * ((n + 127) // 128)
+    s = 1
+    while tiles * s < 148 and k3 % (2 * s * 32) == 0 and k3 // (2 * s) >= 1024:
+        s *= 2
+    if s == 1:
+        c = torch.empty((bs, m, n), dtype=torch.float32, device=a.device)
+        _lib.check(lib.fmi_gemm_nt(_ptr(a3), k3, m * k3, _ptr(b3), k3, n * k3, _ptr(c), n, m * n, bs, m, n, k3, 0, _lib.MMA_TF32, st),
+                   "fmi_gemm_nt")
+        return c
+    part = torch.empty((bs, s, m, n), dtype=torch.float32, device=a.device)
+    kc = k3 // s
+    ac = a3.view(bs, m, s, kc).permute(0, 2, 1, 3).contiguous()      # [image, chunk, row, kc]: chunks as batch entries
+    bc = b3.view(bs, n, s, kc).permute(0, 2, 1, 3).contiguous()
+    _lib.check(lib.fmi_gemm_nt(_ptr(ac), kc, m * kc, _ptr(bc), kc, n * kc, _ptr(part), n, m * n, bs * s, m, n, kc, 0, _lib.MMA_TF32, st),
+               "fmi_gemm_nt")
+    return part.sum(1)
 
 
 class _BmmNT(Function):
@@ -768,7 +797,7 @@ class _BmmNT(Function):
 
 def bmm_nt_supported(a, b) -> bool:
     return (torch.is_tensor(a) and a.is_cuda and b.is_cuda and a.dim() == 3 and b.dim() == 3 and a.dtype == torch.float32
-            and b.dtype == torch.float32 and a.shape[0] == b.shape[0] and a.shape[2] == b.shape[2] and a.shape[2] % 4 == 0
+            and b.dtype == torch.float32 and a.shape[0] == b.shape[0] and a.shape[2] == b.shape[2] and a.shape[2] % 8 == 0
             and a.shape[1] % 8 == 0 and b.shape[1] % 8 == 0 and os.environ.get("FMI_LOSS_KERNELS") != "0")
 
 

@@ -20,7 +20,7 @@ def load(name):
     return {k: torch.from_numpy(v) for k, v in np.load(GOLD / name).items()}
 
 
-@pytest.mark.parametrize("shape", [(2, 64, 40, 128), (4, 1024, 1024, 512), (1, 8, 8, 4), (3, 136, 72, 260)])
+@pytest.mark.parametrize("shape", [(2, 64, 40, 128), (4, 1024, 1024, 512), (1, 8, 8, 8), (3, 136, 72, 264), (2, 64, 64, 16384)])
 def test_bmm_nt_forward_backward(shape):
     from face_mask_inpaint_b200 import _lib, ops
     bs, m, n, k = shape
@@ -31,7 +31,7 @@ def test_bmm_nt_forward_backward(shape):
     assert ops.bmm_nt_supported(a, b)
 
     def run(fn, dt):
-        a_, b_ = a.to(dt).requires_grad_(True), b.to(dt).requires_grad_(True)
+        a_, b_ = a.detach().clone().to(dt).requires_grad_(True), b.detach().clone().to(dt).requires_grad_(True)
         c = fn(a_, b_)
         c.backward(gc.to(dt))
         return c.detach(), a_.grad, b_.grad
@@ -41,6 +41,7 @@ def test_bmm_nt_forward_backward(shape):
     got = run(ops.bmm_nt, torch.float32)
     torch.cuda.synchronize()
     assert _lib.load().fmi_kernel_launch_count() - n0 >= 9        # 3 GEMMs, 2 operand splits each
+    assert not ops.bmm_nt_supported(a[:, :, :4], b[:, :, :4])      # K must be a multiple of 8 (it is the N of the backward GEMMs)
     for name, x, r in zip(("c", "da", "db"), got, want):
         assert rel_err(x, r) <= 2e-5, (name, rel_err(x, r))
 
@@ -63,7 +64,7 @@ def test_contextual_and_style_loss_gradients(shape):
     y = torch.relu(x.cpu() + 0.7 * torch.randn(*shape, generator=g)).to(DEV)
 
     def run(fn, dt):
-        x_ = x.to(dt).requires_grad_(True)
+        x_ = x.detach().clone().to(dt).requires_grad_(True)
         loss = fn(x_, y.to(dt))
         loss.backward()
         return loss.detach(), x_.grad

@@ -33,3 +33,10 @@ with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA, to
     step()
     torch.cuda.synchronize()
 print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=70))
+# GPU kernels only, all of them that matter: name, total us, launches
+from torch.autograd import DeviceType  # noqa: E402
+kern = sorted((e for e in prof.key_averages() if e.device_type == DeviceType.CUDA), key=lambda e: -e.self_device_time_total)
+tot = sum(e.self_device_time_total for e in kern)
+print(f"--- GPU kernels: {tot / 1e3:.2f} ms in {sum(e.count for e in kern)} launches")
+for e in kern[:70]:
+    print(f"{e.self_device_time_total / 1e3:9.3f} ms {e.count:5d}  {e.key[:110]}")
