@@ -605,6 +605,10 @@ def ours_train_picnet(h: Harness):
                         {"buckets": nb}, timed_step=captured.replay if captured else None)
     if not torch.isfinite(losses_host).all():
         raise RuntimeError("train_picnet: non-finite losses")
+    if h.world > 1:     # replicas must still agree after all those steps (each rank trained on its own batch)
+        rec["replicas_in_sync"] = fdist.replicas_in_sync([p for m in (G, D) for p in m.parameters() if p.requires_grad])
+        if not rec["replicas_in_sync"]:
+            sys.stderr.write("[bench] train_picnet: replicas DIVERGED — the gradient all-reduce did not run in every step\n")
     return rec
 
 
@@ -657,6 +661,10 @@ def ours_train_psp(h: Harness):
                             {"buckets": nb})
         if not torch.isfinite(loss_host).all():
             raise RuntimeError("train_psp: non-finite loss")
+        if h.world > 1:
+            rec["replicas_in_sync"] = fdist.replicas_in_sync([p for p in params if p.requires_grad])
+            if not rec["replicas_in_sync"]:
+                sys.stderr.write("[bench] train_psp: replicas DIVERGED — the gradient all-reduce did not run in every step\n")
         return rec
     finally:
         if prev is None:

@@ -121,8 +121,8 @@ template <typename OT> inline int64_t P_stride_elems(int64_t SS) { return SS * 4
 //   BF16: QA = QB = hi (K = dpad), Qn [dpad, S] = hi transposed
 template <typename OT, bool TF32>
 __global__ void __launch_bounds__(256) q_operands_kernel(const __nv_bfloat16* __restrict__ qt, OT* __restrict__ qa,
-                                                         OT* __restrict__ qb, OT* __restrict__ qn, int S, int dpad,
-                                                         int split) {
+                                                         OT* __restrict__ qb, OT* __restrict__ qn, OT* __restrict__ qr, int S,
+                                                         int dpad, int split) {
   const int rowlen = dpad * (1 + split);
   const int kq = TF32 ? 3 * dpad : dpad;
   const int64_t total = (int64_t)S * dpad;
@@ -131,6 +131,7 @@ __global__ void __launch_bounds__(256) q_operands_kernel(const __nv_bfloat16* __
   qa += (int64_t)b * S * kq;
   if (TF32) qb += (int64_t)b * S * kq;
   qn += (int64_t)b * dpad * S;
+  qr += (int64_t)b * S * dpad;    // Qr [S, dpad] = the same values as Qn, pixel-major (the column-role term of dq contracts over i)
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int64_t s = e / dpad;
     const int k = (int)(e % dpad);
@@ -144,9 +145,11 @@ __global__ void __launch_bounds__(256) q_operands_kernel(const __nv_bfloat16* __
       qb[s * kq + dpad + k] = lo;
       qb[s * kq + 2 * dpad + k] = hi;
       qn[(int64_t)k * S + s] = to_op<OT, TF32>(hi + lo);
+      qr[s * dpad + k] = to_op<OT, TF32>(hi + lo);
     } else {
       qa[s * kq + k] = __float2bfloat16_rn(hi);
       qn[(int64_t)k * S + s] = __float2bfloat16_rn(hi);
+      qr[s * dpad + k] = __float2bfloat16_rn(hi);
     }
   }
 }
@@ -159,7 +162,7 @@ inline int64_t al(int64_t b) { return (b + 1023) / 1024 * 1024; }
 
 struct BwdPlan {
   int dpad, split, esz, kq, nb;  // nb = images processed per group of batched launches
-  int64_t qt, vcat, qa, qb, qn, dop, dot, vt, delta, rvec, p, pt, ds, total;
+  int64_t qt, vcat, qa, qb, qn, qr, dop, dot, vt, delta, rvec, p, pt, ds, total;
 };
 
 int make_bwd_plan(int N, int d, int C0, int C1, int S, int mma, BwdPlan* pl) {
@@ -189,6 +192,7 @@ int make_bwd_plan(int N, int d, int C0, int C1, int S, int mma, BwdPlan* pl) {
   pl->qa = take(nb * S * pl->kq * esz);
   pl->qb = take(nb * S * pl->kq * esz);
   pl->qn = take(nb * pl->dpad * S * esz);
+  pl->qr = take(nb * S * pl->dpad * esz);
   pl->dot = take(nb * S * Cv * esz);
   pl->vt = take(nb * S * Cv * esz);
   pl->p = take(nb * S * S * 4);  // P stays fp32 (unrounded); later reused for G
@@ -217,7 +221,7 @@ int run_bwd(const BwdPlan& pl, uint8_t* ws, const float* mask, const float* a0, 
   OT* dop = (OT*)(ws + pl.dop);
   float* delta = (float*)(ws + pl.delta);
   float* rvec = (float*)(ws + pl.rvec);
-  OT *qa = (OT*)(ws + pl.qa), *qb = TF32 ? (OT*)(ws + pl.qb) : qa, *qn = (OT*)(ws + pl.qn);
+  OT *qa = (OT*)(ws + pl.qa), *qb = TF32 ? (OT*)(ws + pl.qb) : qa, *qn = (OT*)(ws + pl.qn), *qr = (OT*)(ws + pl.qr);
   OT *dot = (OT*)(ws + pl.dot), *vt = (OT*)(ws + pl.vt), *PT = (OT*)(ws + pl.pt), *dS = (OT*)(ws + pl.ds);
   float* P = (float*)(ws + pl.p);   // fp32 P; the buffer is reused for G (operand type) once dE exists
   OT* G = (OT*)(ws + pl.p);
@@ -237,7 +241,7 @@ int run_bwd(const BwdPlan& pl, uint8_t* ws, const float* mask, const float* a0, 
     const int nb = N - n0 < pl.nb ? N - n0 : pl.nb;
     {
       dim3 qg((unsigned)imin64(((int64_t)S * pl.dpad + 255) / 256, (int64_t)FMI_NUM_SMS * 8), nb);
-      q_operands_kernel<OT, TF32><<<qg, 256, 0, st>>>(qt + (int64_t)n0 * S * rowlen, qa, qb, qn, S, pl.dpad, pl.split);
+      q_operands_kernel<OT, TF32><<<qg, 256, 0, st>>>(qt + (int64_t)n0 * S * rowlen, qa, qb, qn, qr, S, pl.dpad, pl.split);
       if ((rc = fmi_launched("q_operands"))) return rc;
       dim3 tg((S + 31) / 32, (Cv + 31) / 32, nb);
       transpose_kernel<OT><<<tg, 256, 0, st>>>(dop + (int64_t)n0 * Cv * S, S, (int64_t)Cv * S, dot, Cv, (int64_t)S * Cv, Cv, S);
@@ -294,8 +298,25 @@ int run_bwd(const BwdPlan& pl, uint8_t* ws, const float* mask, const float* a0, 
       }
       if ((rc = launch_gemm_nt<TF32>(dop + ((int64_t)n0 * Cv + cofs) * S, S, (int64_t)Cv * S, PT, S, SS, nb, g, st))) return rc;
     }
-    // 4: G = dE + dE^T (into the P buffer), dq = G . q
-    if (dq) {
+    // 4: dq[t,:] = sum_j (dE[t,j] + dE[j,t]) q[j,:]  (keys == queries: q plays the row and the column role).
+    // The row-role term is a gemm_nt on dE as it lies; the column-role term sum_i dE[i,t] q[i,:] contracts over the ROW index of
+    // dE — the pixel-contraction GEMM of the convolution weight gradient (fmi_conv_wgrad_nhwc: "pixels" = i, "output channels" =
+    // t, "input channels" = the head dimension), accumulated onto dq with red.add. This replaces the explicit G = dE + dE^T
+    // (sym_add_kernel: 2 GB read + 1 GB written per 128^2 image, 4.7 ms per PICNet GAN step). S must be a power of two for the
+    // pixel tiling; other sizes keep the transpose-add.
+    static const bool sym_env = [] { const char* e = getenv("FMI_ATTN_BWD_SYM"); return e && e[0] == '1'; }();
+    const bool pix = !sym_env && (S & (S - 1)) == 0 && S >= 1024;
+    if (dq && pix) {
+      g = GemmParams{};
+      g.M = S; g.N = pl.dpad; g.K = S; g.epi = EPI_STORE_F32; g.out0 = dq + (int64_t)n0 * S * pl.dpad; g.ldo = pl.dpad;
+      g.out_bs = (int64_t)S * pl.dpad;
+      if ((rc = launch_gemm_nt<TF32>(dS, S, SS, qn, S, (int64_t)pl.dpad * S, nb, g, st))) return rc;
+      for (int b = 0; b < nb; ++b) {
+        rc = fmi_conv_wgrad_nhwc(qr + (int64_t)b * S * pl.dpad, dS + (int64_t)b * SS, dq + (int64_t)(n0 + b) * S * pl.dpad, 1, pl.dpad, S,
+                                 S / 128, 128, 1, 0, TF32 ? FMI_MMA_TF32 : FMI_MMA_BF16, (void*)st);
+        if (rc) return rc;
+      }
+    } else if (dq) {
       dim3 sg(S / 32, S / 32, nb);
       sym_add_kernel<OT, TF32><<<sg, 256, 0, st>>>(dS, G, S, SS, P_stride_elems<OT>(SS));
       if ((rc = fmi_launched("sym_add"))) return rc;

@@ -58,6 +58,20 @@ def all_ranks_finite(value: torch.Tensor, group=None) -> bool:
     return bool(ok.item() > 0)
 
 
+def replicas_in_sync(params, group=None, rtol: float = 0.0) -> bool:
+    """True when every rank holds the same values in `params` (data-parallel replicas after N optimizer steps on averaged
+    gradients): max over ranks == min over ranks of a per-tensor fingerprint (sum and sum of squares in double). Used by the
+    bench after the timed region — a gradient all-reduce that silently dropped out of a captured CUDA graph would show here."""
+    ps = [p.detach() for p in params]
+    if not ps or not (dist.is_initialized() and dist.get_world_size(group) > 1):
+        return True
+    fp = torch.stack([torch.stack((p.double().sum(), (p.double() ** 2).sum())) for p in ps]).reshape(-1)
+    hi, lo = fp.clone(), fp.clone()
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
+    return bool(((hi - lo).abs() <= rtol * hi.abs().clamp_min(1e-30)).all().item())
+
+
 def broadcast_module_state(module: torch.nn.Module, src: int = 0, group=None) -> None:
     """Parameters AND buffers (incl. SpectralNorm u/v, which mutate every forward) from rank `src`."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:

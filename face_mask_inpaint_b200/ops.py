@@ -387,13 +387,17 @@ def conv1x1(x, weight, bias=None):
 # ------------------------------------------------------------------------------------------------
 # batch-shared convolutions of the PICNet conv blocks in TRAINING (SURVEY 8f rank 1 + row g)
 # ------------------------------------------------------------------------------------------------
-def _as_nhwc(t):
-    """[N,C,H,W] fp32 -> dense [N,H,W,C]: a view when `t` already is channels_last in memory, else one copy that is remembered
-    on the tensor (keyed by its version counter) — a block input or a gradient in NCHW layout is read by two Functions (main
-    path and shortcut), which would otherwise transpose it twice."""
+def _as_nhwc(t, fresh=False):
+    """[N,C,H,W] fp32 -> dense [N,H,W,C]: a view when `t` already is channels_last in memory, else one copy. A block input or a
+    gradient in NCHW layout is read by two Functions (main path and shortcut), which would otherwise transpose it twice: the copy
+    is remembered on the tensor (keyed by its version counter) — but only for tensors that live for ONE iteration (`fresh`: a
+    gradient handed to backward; or an intermediate with a grad_fn). A leaf that persists across iterations (a model input, the
+    static input buffer of a captured CUDA graph, rewritten in place before every replay) is converted every time."""
     v = t.permute(0, 2, 3, 1)
     if v.is_contiguous() and t.dtype == torch.float32:
         return v
+    if not (fresh or t.grad_fn is not None):
+        return v.contiguous().float()
     hit = getattr(t, "_fmi_nhwc", None)
     if hit is not None and hit[0] == t._version:
         return hit[1]
@@ -450,7 +454,7 @@ class _ConvShared(Function):
         st = _stream()
         o, i, k, _ = wc.shape
         b, h, w, _ = xn.shape
-        g = _as_nhwc(gy)
+        g = _as_nhwc(gy, fresh=True)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             wf = wc.flip(2, 3).contiguous() if k == 3 else wc
@@ -515,7 +519,7 @@ class _ConvTShared(Function):
         lib = _lib.load()
         i, o = wc.shape[0], wc.shape[1]
         b, h, w, _ = xn.shape
-        g = _as_nhwc(gy)
+        g = _as_nhwc(gy, fresh=True)
         dx = dw = db = None
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
             planes = torch.empty((4 * b, h, w, o), dtype=torch.float32, device=g.device)
@@ -572,7 +576,7 @@ class _NormAct(Function):
 
     @staticmethod
     def backward(ctx, gy):
-        g = _as_nhwc(gy)
+        g = _as_nhwc(gy, fresh=True)
         if not ctx.normed:
             xn, = ctx.saved_tensors
             return torch.ops.aten.leaky_relu_backward(g, xn, ctx.slope, False).permute(0, 3, 1, 2), None, None, None, None

@@ -199,3 +199,30 @@ def test_shard_batch_covers_everything():
         for w in (1, 2, 4, 8):
             got = [i for r in range(w) for i in shard_batch(n, r, w)]
             assert got == list(range(n))
+
+
+def _sync_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from face_mask_inpaint_b200 import dist as fd
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    same = [torch.nn.Parameter(torch.arange(6.0)), torch.nn.Parameter(torch.ones(3, 2))]
+    diff = [torch.nn.Parameter(torch.arange(6.0) + (1e-3 if rank else 0.0))]
+    q.put((rank, fd.replicas_in_sync(same), fd.replicas_in_sync(same + diff)))
+    dist.destroy_process_group()
+
+
+def test_replicas_in_sync_detects_divergence():
+    """dist.replicas_in_sync (the bench's post-run check that the captured gradient all-reduce really ran): equal replicas pass,
+    a rank whose parameters drifted is detected — on every rank."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 400) + 37
+    procs = [ctx.Process(target=_sync_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(60)
+    assert got == [(0, True, False), (1, True, False)]

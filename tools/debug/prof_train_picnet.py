@@ -29,7 +29,8 @@ def step():
 for _ in range(3):
     step()
 torch.cuda.synchronize()
-with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA, torch.profiler.ProfilerActivity.CPU]) as prof:
+with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA, torch.profiler.ProfilerActivity.CPU],
+                            record_shapes=True) as prof:
     step()
     torch.cuda.synchronize()
 print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=70))
@@ -40,3 +41,8 @@ tot = sum(e.self_device_time_total for e in kern)
 print(f"--- GPU kernels: {tot / 1e3:.2f} ms in {sum(e.count for e in kern)} launches")
 for e in kern[:70]:
     print(f"{e.self_device_time_total / 1e3:9.3f} ms {e.count:5d}  {e.key[:110]}")
+# where the layout copies come from: aten::copy_ / contiguous / clone by input shape
+print("--- copies by input shape (device time of the op incl. children)")
+byshape = [e for e in prof.key_averages(group_by_input_shape=True) if e.key in ("aten::copy_", "aten::contiguous", "aten::clone")]
+for e in sorted(byshape, key=lambda e: -e.device_time_total)[:25]:
+    print(f"{e.device_time_total / 1e3:9.3f} ms {e.count:5d}  {e.key:18s} {str(e.input_shapes)[:120]}")
