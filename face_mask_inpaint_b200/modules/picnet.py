@@ -149,7 +149,7 @@ class Output(nn.Module):
                                      + [nn.ReflectionPad2d(kernel_size // 2), self.conv1, nn.Tanh()]))
 
     def forward(self, x):
-        return self.model(x)
+        return ops.run_block_sequential(self.model, x)     # training: activation + reflection padding without leaving NHWC
 
 
 def _width(ngf, img_f, level):

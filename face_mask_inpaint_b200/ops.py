@@ -682,6 +682,41 @@ def pool_sum(pool, a, b):
     return pool(a) + pool(b)
 
 
+class _ActReflectPad(Function):
+    """ReflectionPad2d(1)(leaky_relu(x)) — the head of the Output block (base_function.py:387-393) — on channels_last tensors:
+    the activation is written straight into the interior of the padded [N,H+2,W+2,C] buffer and fmi_reflect_border_nhwc fills the
+    border; the gradient folds the border back with four thin slice-adds. ATen's reflection_pad2d wants NCHW: on the 32-channel
+    1024^2 activation of the PICNet decoder its `.contiguous()` alone was a 2.4 ms strided copy per GAN step."""
+
+    @staticmethod
+    def forward(ctx, x, slope):
+        b, c, h, w = x.shape
+        xn = _as_nhwc(x)
+        pad = torch.empty((b, h + 2, w + 2, c), dtype=torch.float32, device=x.device)
+        torch.ops.aten.leaky_relu.out(xn, slope, out=pad[:, 1:-1, 1:-1, :])
+        _lib.check(_lib.load().fmi_reflect_border_nhwc(_ptr(pad), b, c, h, w, _lib.MMA_TF32, _stream()), "fmi_reflect_border_nhwc")
+        ctx.save_for_backward(xn)
+        ctx.slope = float(slope)
+        return pad.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, gy):
+        xn, = ctx.saved_tensors
+        g = _as_nhwc(gy, fresh=True)                      # [N, H+2, W+2, C]
+        r = g[:, 1:-1].clone()                            # padded row 0 mirrors image row 1, padded row H+1 mirrors row H-2
+        r[:, 1] += g[:, 0]
+        r[:, -2] += g[:, -1]
+        gx = r[:, :, 1:-1].contiguous()
+        gx[:, :, 1] += r[:, :, 0]
+        gx[:, :, -2] += r[:, :, -1]
+        return torch.ops.aten.leaky_relu_backward(gx, xn, ctx.slope, False).permute(0, 3, 1, 2), None
+
+
+def act_reflect_pad_supported(act, pad, x) -> bool:
+    return (isinstance(act, (nn.LeakyReLU, nn.ReLU)) and isinstance(pad, nn.ReflectionPad2d) and tuple(pad.padding) == (1, 1, 1, 1)
+            and _train_kernels_on(x) and x.shape[1] % 4 == 0 and x.shape[2] >= 2 and x.shape[3] >= 2)
+
+
 def run_block_sequential(seq, x):
     """`seq(x)` for the `model` Sequential of a PICNet block (base_function.py:207-366) with every (InstanceNorm2d, activation)
     pair fused into `_NormAct` when the training kernels apply; the wrapped convolutions take their own kernel path in
@@ -691,6 +726,10 @@ def run_block_sequential(seq, x):
     while i < len(mods):
         if i + 1 < len(mods) and norm_act_supported(mods[i], mods[i + 1], x):
             x = norm_act(mods[i], mods[i + 1], x)
+            i += 2
+        elif i + 1 < len(mods) and act_reflect_pad_supported(mods[i], mods[i + 1], x):
+            slope = float(mods[i].negative_slope) if isinstance(mods[i], nn.LeakyReLU) else 0.0
+            x = _ActReflectPad.apply(x, slope)
             i += 2
         elif act_round_supported(mods[i], x):
             x = act_round(mods[i], x)
@@ -751,6 +790,9 @@ def _split3(t, order):
     return out
 
 
+_CHUNK_VIEW_OK = None     # None: not tried yet; whether cuTensorMapEncodeTiled takes a batch stride below the row pitch
+
+
 def _bmm_nt_raw(a, b):
     a, b = a.contiguous().float(), b.contiguous().float()
     bs, m, k = a.shape
@@ -772,6 +814,22 @@ def _bmm_nt_raw(a, b):
         return c
     part = torch.empty((bs, s, m, n), dtype=torch.float32, device=a.device)
     kc = k3 // s
+    global _CHUNK_VIEW_OK
+    if _CHUNK_VIEW_OK is not False:
+        # chunks as batch entries of a strided VIEW: row pitch k3, batch stride kc (a tensor map whose outer stride is smaller
+        # than its row pitch); one launch per image, no re-layout of the operands
+        rc = 0
+        for i in range(bs):
+            rc = lib.fmi_gemm_nt(a3[i].data_ptr(), k3, kc, b3[i].data_ptr(), k3, kc, part[i].data_ptr(), n, m * n, s, m, n, kc, 0,
+                                 _lib.MMA_TF32, st)
+            if rc:
+                break
+        if rc == 0:
+            _CHUNK_VIEW_OK = True
+            return part.sum(1)
+        if _CHUNK_VIEW_OK:      # worked before: a real error
+            _lib.check(rc, "fmi_gemm_nt")
+        _CHUNK_VIEW_OK = False  # the driver refused that tensor map: re-lay the operands instead
     ac = a3.view(bs, m, s, kc).permute(0, 2, 1, 3).contiguous()      # [image, chunk, row, kc]: chunks as batch entries
     bc = b3.view(bs, n, s, kc).permute(0, 2, 1, 3).contiguous()
     _lib.check(lib.fmi_gemm_nt(_ptr(ac), kc, m * kc, _ptr(bc), kc, n * kc, _ptr(part), n, m * n, bs * s, m, n, kc, 0, _lib.MMA_TF32, st),

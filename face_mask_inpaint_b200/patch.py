@@ -373,6 +373,7 @@ def _install_picnet_decoder():
     bf.ResBlock.forward = res_block_forward
     bf.ResBlockEncoderOptimized.forward = plain_block_forward
     bf.ResBlockDecoder.forward = plain_block_forward
+    bf.Output.forward = lambda self, x: ops.run_block_sequential(self.model, x)     # base_function.py:395-398
 
 
 def _blend(src, ref, full_mask):

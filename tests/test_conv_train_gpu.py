@@ -229,3 +229,27 @@ def test_pooling_and_bias_sum_helpers():
     assert ops.pool_sum(nn.AvgPool2d(3, 1, 1), a, b).shape == a.shape      # anything else stays ATen's pooling
     x = torch.randn(3, 20, 24, 64, generator=g).to(DEV)                   # NHWC
     assert rel_err(ops._channel_sum(x), x.double().sum((0, 1, 2))) <= 1e-6
+
+
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_act_reflect_pad_forward_backward(channels_last):
+    """Output block head (base_function.py:387-393): ReflectionPad2d(1)(LeakyReLU(x)) and its gradient, NHWC, vs ATen."""
+    from face_mask_inpaint_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(2, 32, 12, 20, generator=g).to(DEV)
+    gy = torch.randn(2, 32, 14, 22, generator=g).to(DEV)
+    if channels_last:
+        x, gy = x.contiguous(memory_format=torch.channels_last), gy.contiguous(memory_format=torch.channels_last)
+    act, pad = nn.LeakyReLU(0.1), nn.ReflectionPad2d(1)
+
+    def run(fn):
+        xs = x.clone().requires_grad_(True)
+        y = fn(xs)
+        y.backward(gy)
+        return y.detach(), xs.grad
+
+    want = run(lambda a: pad(act(a)))
+    assert ops.act_reflect_pad_supported(act, pad, x.clone().requires_grad_(True))
+    got = run(lambda a: ops.run_block_sequential(nn.Sequential(act, pad), a))
+    assert got[0].shape == want[0].shape and rel_err(got[0], want[0]) <= 1e-6 and rel_err(got[1], want[1]) <= 1e-6
+    assert not ops.act_reflect_pad_supported(act, nn.ReflectionPad2d(2), x.clone().requires_grad_(True))
