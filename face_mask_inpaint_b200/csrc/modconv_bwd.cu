@@ -154,6 +154,7 @@ struct WgradParams {
   int m_tiles, n_tiles, n_tile;
   int a_atoms, b_atoms;                // 128-byte channel atoms loaded per A / B tile
   int a_shared;                        // 1: one A tile per stage, G shifted B tiles (plain); 0: G A tiles, one B tile (up)
+  int stack, apt;                      // plain 3x3, O <= 64: `stack` kernel ROWS share one A tile (apt atoms each), see wgrad_stack()
   int tap_ady[9], tap_adx[9], tap_aboff[9], tap_bdy[9], tap_bdx[9];
   int stages, tmem_cols;
   float* dwp;                          // [B][9][O][I] fp32, zero-initialised (dwp_img_stride = 9*O*I), or one [taps][O][I]
@@ -216,9 +217,22 @@ __global__ void __launch_bounds__(kWgradThreads, 1)
         const int it = kt - kt0, st = it % p.stages;
         const int m0 = (kt / p.kt_w) * p.TH, n0 = (kt % p.kt_w) * p.TW;
         mbar_wait(&empty[st], ((it / p.stages) & 1) ^ 1);
-        mbar_arrive_expect_tx(&full[st], bytes);
         uint8_t* sA = smem + st * stage_bytes;
         uint8_t* sB = sA + nA * a_tile_bytes;
+        if (p.stack > 1) {
+          // stacked kernel rows: atom group j of the A tile = g shifted by 1 - ky rows (ky = grp * stack + j), the three B tiles
+          // = x shifted by kx - 1 columns: D rows [j * apt * EPA, ...) of accumulator kx are the gradient of tap (ky, kx)
+          const int nvalid = (3 - grp * p.stack) < p.stack ? (3 - grp * p.stack) : p.stack;
+          mbar_arrive_expect_tx(&full[st], (uint32_t)((nvalid * p.apt + 3 * p.b_atoms) * box_bytes));
+          for (int j = 0; j < nvalid; ++j)
+            for (int at = 0; at < p.apt; ++at)
+              tma_load_4d(sA + (j * p.apt + at) * box_bytes, &map_a, &full[st], at * EPA, n0, m0 + 1 - (grp * p.stack + j), b);
+          for (int tb = 0; tb < 3; ++tb)
+            for (int at = 0; at < p.b_atoms; ++at)
+              tma_load_4d(sB + tb * b_tile_bytes + at * box_bytes, &map_b, &full[st], nt * p.n_tile + at * EPA, n0 + tb - 1, m0, b);
+          continue;
+        }
+        mbar_arrive_expect_tx(&full[st], bytes);
         for (int ta = 0; ta < nA; ++ta) {
           const int tap = grp * p.G + ta;
           for (int at = 0; at < p.a_atoms; ++at)
@@ -266,14 +280,18 @@ __global__ void __launch_bounds__(kWgradThreads, 1)
     const uint32_t lane_addr = (uint32_t)lane_base << 16;
     mbar_wait(&acc_full, 0);
     tc_fence_after();
+    const int row = lane_base + (tid & 31);          // accumulator row of this thread
+    const int sj = p.stack > 1 ? row / (p.apt * EPA) : 0, so = p.stack > 1 ? row % (p.apt * EPA) : o;
+    const int sky = grp * p.stack + sj;
+    const bool s_ok = p.stack > 1 ? (sj < p.stack && sky < 3 && so < p.O) : (o < p.O);
     for (int tl = 0; tl < p.G; ++tl) {
-      const int tap = grp * p.G + tl;
-      float* dst = p.dwp + (int64_t)b * p.dwp_img_stride + ((int64_t)tap * p.O + o) * p.I + nt * p.n_tile;
+      const int tap = p.stack > 1 ? sky * 3 + tl : grp * p.G + tl;
+      float* dst = p.dwp + (int64_t)b * p.dwp_img_stride + ((int64_t)tap * p.O + so) * p.I + nt * p.n_tile;
       for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(tmem + lane_addr + tl * p.n_tile + c0, v);
         tc_wait_ld();
-        if (o < p.O) {
+        if (s_ok) {
 #pragma unroll
           for (int k = 0; k < 32; k += 4)
             red_add_v4(dst + c0 + k, __uint_as_float(v[k]), __uint_as_float(v[k + 1]), __uint_as_float(v[k + 2]),
@@ -459,6 +477,22 @@ BwdLayout bwd_layout(int B, int I, int O, int H, int W, int upsample, int act, i
   return L;
 }
 
+// Plain 3x3 convolutions with few output channels: the A tile always spans M = 128 accumulator rows, of which O <= 64 were in use —
+// and the kernel is bound by the MMA-issuing thread (ncu, 64 -> 32 @512^2: 536 us, tensor pipe 28 %, DRAM 10 %: 12 instructions of
+// 128 x N x 8 per 32 pixels). Stacking kernel ROWS along M (row ky = the gradient tile shifted by 1 - ky image rows, a different
+// TMA coordinate per atom group) makes one instruction produce up to three taps: 3 instead of 9 per 8 pixels for O <= 32
+// (tf32), 6 for O <= 64, and the activations are read once per CTA instead of once per tap group.
+inline void wgrad_stack(WgradParams& p, int O, int epa, int taps) {
+  static const bool off = [] { const char* e = getenv("FMI_WGRAD_STACK"); return e && e[0] == '0'; }();
+  p.stack = 0; p.apt = 0;
+  if (off || !p.a_shared || taps != 9 || p.G != 3 || p.m_tiles != 1) return;
+  const int apt = (O + epa - 1) / epa, fit = (128 / epa) / apt;
+  if (fit < 2) return;
+  p.stack = fit > 3 ? 3 : fit;
+  p.apt = apt;
+  p.ngroups = (3 + p.stack - 1) / p.stack;
+}
+
 template <bool TF32>
 int launch_wgrad(const CUtensorMap& ma, const CUtensorMap& mb, WgradParams p, cudaStream_t st) {
   auto kern = wgrad_gemm_kernel<TF32>;
@@ -636,6 +670,7 @@ extern "C" int fmi_styled_conv_bwd_nhwc(const void* x, const void* y, const void
     p.a_atoms = ((O < 128 ? O : 128) + (int)epa - 1) / (int)epa;
     p.b_atoms = (p.n_tile + (int)epa - 1) / (int)epa;
     p.a_shared = upsample ? 0 : 1;
+    wgrad_stack(p, O, (int)epa, 9);
     for (int t = 0; t < 9; ++t) {
       if (upsample) { p.tap_ady[t] = tap_dy[t]; p.tap_adx[t] = tap_dx[t]; p.tap_aboff[t] = tap_boff[t]; }
       else { p.tap_bdy[t] = tap_dy[t]; p.tap_bdx[t] = tap_dx[t]; }
@@ -724,6 +759,7 @@ extern "C" int fmi_conv_wgrad_nhwc(const void* x, const void* dy, float* dwp, in
   p.a_atoms = ((O < 128 ? O : 128) + (int)epa - 1) / (int)epa;
   p.b_atoms = (p.n_tile + (int)epa - 1) / (int)epa;
   p.a_shared = transposed ? 0 : 1;
+  wgrad_stack(p, O, (int)epa, taps);
   for (int t = 0; t < taps; ++t) {
     const int ky = t / 3, kx = t % 3;
     if (transposed) {
