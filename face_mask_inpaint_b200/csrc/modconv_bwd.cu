@@ -178,7 +178,9 @@ __global__ void __launch_bounds__(kWgradThreads, 1)
   const int tid = threadIdx.x, warp = tid >> 5;
   const int KT = p.TH * p.TW;
   const int box_bytes = KT * 128;
-  const int nA = p.a_shared ? 1 : p.G, nB = p.a_shared ? p.G : 1;
+  const bool ustack = p.stack > 1 && !p.a_shared;   // up-sampling layers: the taps of a group stacked along M (one A tile, one MMA)
+  const int nA = (p.a_shared || ustack) ? 1 : p.G, nB = p.a_shared ? p.G : 1;
+  const int nacc = ustack ? 1 : p.G;                // accumulators (of n_tile columns) per CTA
   const int a_tile_bytes = A_ATOMS_FULL * box_bytes, b_tile_bytes = p.b_atoms * box_bytes;
   const int stage_bytes = nA * a_tile_bytes + nB * b_tile_bytes;
   // tap group fastest: the CTAs that read the SAME pixel range of x / g (3 tap groups x output tiles, tap-shifted by one pixel) are
@@ -219,6 +221,20 @@ __global__ void __launch_bounds__(kWgradThreads, 1)
         mbar_wait(&empty[st], ((it / p.stages) & 1) ^ 1);
         uint8_t* sA = smem + st * stage_bytes;
         uint8_t* sB = sA + nA * a_tile_bytes;
+        if (ustack) {
+          // stacked taps: atom group j of the one A tile = the parity plane / shift of tap grp * stack + j, one un-shifted B tile
+          const int nvalid = (9 - grp * p.stack) < p.stack ? (9 - grp * p.stack) : p.stack;
+          mbar_arrive_expect_tx(&full[st], (uint32_t)((nvalid * p.apt + p.b_atoms) * box_bytes));
+          for (int j = 0; j < nvalid; ++j) {
+            const int tap = grp * p.stack + j;
+            for (int at = 0; at < p.apt; ++at)
+              tma_load_4d(sA + (j * p.apt + at) * box_bytes, &map_a, &full[st], at * EPA, n0 + p.tap_adx[tap], m0 + p.tap_ady[tap],
+                          b + p.tap_aboff[tap]);
+          }
+          for (int at = 0; at < p.b_atoms; ++at)
+            tma_load_4d(sB + at * box_bytes, &map_b, &full[st], nt * p.n_tile + at * EPA, n0, m0, b);
+          continue;
+        }
         if (p.stack > 1) {
           // stacked kernel rows: atom group j of the A tile = g shifted by 1 - ky rows (ky = grp * stack + j), the three B tiles
           // = x shifted by kx - 1 columns: D rows [j * apt * EPA, ...) of accumulator kx are the gradient of tap (ky, kx)
@@ -258,7 +274,7 @@ __global__ void __launch_bounds__(kWgradThreads, 1)
         tc_fence_after();
         const uint32_t sA = smem_u32(smem + st * stage_bytes);
         const uint32_t sB = sA + nA * a_tile_bytes;
-        for (int tl = 0; tl < p.G; ++tl) {
+        for (int tl = 0; tl < nacc; ++tl) {
           const uint32_t aBase = sA + (p.a_shared ? 0 : tl) * a_tile_bytes;
           const uint32_t bBase = sB + (p.a_shared ? tl : 0) * b_tile_bytes;
           for (int ks = 0; ks < ksteps; ++ks) {
@@ -282,10 +298,10 @@ __global__ void __launch_bounds__(kWgradThreads, 1)
     tc_fence_after();
     const int row = lane_base + (tid & 31);          // accumulator row of this thread
     const int sj = p.stack > 1 ? row / (p.apt * EPA) : 0, so = p.stack > 1 ? row % (p.apt * EPA) : o;
-    const int sky = grp * p.stack + sj;
-    const bool s_ok = p.stack > 1 ? (sj < p.stack && sky < 3 && so < p.O) : (o < p.O);
-    for (int tl = 0; tl < p.G; ++tl) {
-      const int tap = p.stack > 1 ? sky * 3 + tl : grp * p.G + tl;
+    const int sky = grp * p.stack + sj;               // plain: kernel row; up: tap
+    const bool s_ok = p.stack > 1 ? (sj < p.stack && sky < (ustack ? 9 : 3) && so < p.O) : (o < p.O);
+    for (int tl = 0; tl < nacc; ++tl) {
+      const int tap = ustack ? sky : (p.stack > 1 ? sky * 3 + tl : grp * p.G + tl);
       float* dst = p.dwp + (int64_t)b * p.dwp_img_stride + ((int64_t)tap * p.O + so) * p.I + nt * p.n_tile;
       for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
         uint32_t v[32];
@@ -485,12 +501,24 @@ BwdLayout bwd_layout(int B, int I, int O, int H, int W, int upsample, int act, i
 inline void wgrad_stack(WgradParams& p, int O, int epa, int taps) {
   static const bool off = [] { const char* e = getenv("FMI_WGRAD_STACK"); return e && e[0] == '0'; }();
   p.stack = 0; p.apt = 0;
-  if (off || !p.a_shared || taps != 9 || p.G != 3 || p.m_tiles != 1) return;
+  if (off || taps != 9 || p.m_tiles != 1) return;
   const int apt = (O + epa - 1) / epa, fit = (128 / epa) / apt;
   if (fit < 2) return;
-  p.stack = fit > 3 ? 3 : fit;
-  p.apt = apt;
-  p.ngroups = (3 + p.stack - 1) / p.stack;
+  if (p.a_shared) {
+    if (p.G != 3) return;
+    p.stack = fit > 3 ? 3 : fit;
+    p.apt = apt;
+    p.ngroups = (3 + p.stack - 1) / p.stack;
+  } else {
+    // up-sampling layers (one A tile per tap from the gradient's parity planes, one un-shifted B tile): the taps of a CTA stacked
+    // along M — one MMA per 8 pixels yields `stack` taps and the CTA needs one accumulator
+    static const bool uoff = [] { const char* e = getenv("FMI_WGRAD_STACK_UP"); return e && e[0] == '0'; }();
+    if (uoff) return;
+    p.stack = fit > 3 ? 3 : fit;
+    p.apt = apt;
+    p.G = p.stack;
+    p.ngroups = (9 + p.stack - 1) / p.stack;
+  }
 }
 
 template <bool TF32>
@@ -503,13 +531,14 @@ int launch_wgrad(const CUtensorMap& ma, const CUtensorMap& mb, WgradParams p, cu
   }
   constexpr int EPA = TF32 ? 32 : 64;
   const int box_bytes = p.TH * p.TW * 128;
-  const int nA = p.a_shared ? 1 : p.G, nB = p.a_shared ? p.G : 1;
+  const bool ustack = p.stack > 1 && !p.a_shared;
+  const int nA = (p.a_shared || ustack) ? 1 : p.G, nB = p.a_shared ? p.G : 1;
   const int stage_bytes = nA * (128 / EPA) * box_bytes + nB * p.b_atoms * box_bytes;
   int stages = (232448 - 4096) / stage_bytes;
   if (stages > 8) stages = 8;
   FMI_REQUIRE(stages >= 2, "modconv wgrad: stage of %d bytes does not fit twice in shared memory", stage_bytes);
   p.stages = stages;
-  const int cols = p.G * p.n_tile;
+  const int cols = (ustack ? 1 : p.G) * p.n_tile;
   p.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
   dim3 grid(p.ngroups * p.m_tiles * p.n_tiles, p.ksplit, p.B);
   kern<<<grid, kWgradThreads, (size_t)stages * stage_bytes + 1024, st>>>(ma, mb, p);
