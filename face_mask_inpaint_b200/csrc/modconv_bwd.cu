@@ -521,6 +521,26 @@ inline void wgrad_stack(WgradParams& p, int O, int epa, int taps) {
   }
 }
 
+// The pixels of a K tile per stage: 32 (tf32) / 64 (bf16) pixels make 4 KB TMA boxes, and the single producer thread issues about one
+// box per 200 ns (measured: 5 boxes per stage -> 1.35 us per stage whatever the MMAs do) — twice the pixels per box halves the
+// instruction count. Grown while at least 4 stages still fit in shared memory. Call after wgrad_stack().
+inline void wgrad_grow_ktile(WgradParams& p, bool tf32, int H, int W) {
+  static const bool off = [] { const char* e = getenv("FMI_WGRAD_KTILE"); return e && e[0] == '0'; }();
+  if (off) return;
+  const bool ustack = p.stack > 1 && !p.a_shared;
+  const int nA = (p.a_shared || ustack) ? 1 : p.G, nB = p.a_shared ? p.G : 1;
+  const int atoms = nA * (tf32 ? 4 : 2) + nB * p.b_atoms;
+  int KT = p.TH * p.TW;
+  while (2 * KT <= 256 && 2 * KT <= H * W && (int64_t)atoms * 2 * KT * 128 * 4 <= 232448 - 4096) {
+    const int tw = W < 2 * KT ? W : 2 * KT, th = 2 * KT / tw;
+    if (W % tw || H % th || (H / th) * (W / tw) < 8) break;
+    KT *= 2;
+    p.TW = tw; p.TH = th;
+  }
+  p.kt_w = W / p.TW;
+  p.kt_total = (H / p.TH) * p.kt_w;
+}
+
 template <bool TF32>
 int launch_wgrad(const CUtensorMap& ma, const CUtensorMap& mb, WgradParams p, cudaStream_t st) {
   auto kern = wgrad_gemm_kernel<TF32>;
@@ -700,6 +720,7 @@ extern "C" int fmi_styled_conv_bwd_nhwc(const void* x, const void* y, const void
     p.b_atoms = (p.n_tile + (int)epa - 1) / (int)epa;
     p.a_shared = upsample ? 0 : 1;
     wgrad_stack(p, O, (int)epa, 9);
+    wgrad_grow_ktile(p, tf32, H, W);
     for (int t = 0; t < 9; ++t) {
       if (upsample) { p.tap_ady[t] = tap_dy[t]; p.tap_adx[t] = tap_dx[t]; p.tap_aboff[t] = tap_boff[t]; }
       else { p.tap_bdy[t] = tap_dy[t]; p.tap_bdx[t] = tap_dx[t]; }
@@ -789,6 +810,7 @@ extern "C" int fmi_conv_wgrad_nhwc(const void* x, const void* dy, float* dwp, in
   p.b_atoms = (p.n_tile + (int)epa - 1) / (int)epa;
   p.a_shared = transposed ? 0 : 1;
   wgrad_stack(p, O, (int)epa, taps);
+  wgrad_grow_ktile(p, tf32, H, W);
   for (int t = 0; t < taps; ++t) {
     const int ky = t / 3, kx = t % 3;
     if (transposed) {
