@@ -7,9 +7,11 @@ with the SAME attribute / parameter names and shapes, so a reference checkpoint 
 What runs where:
   * `ExampleGuidedAttention` at 32^2 and `Auto_Attn` at 128^2 (58 % of the generator FLOPs), mask scaling and
     compositing: the sm_100a kernels of this package;
-  * the decoder's spectral-normalised conv / conv-transpose blocks and its Output block: the implicit-GEMM
-    kernels of csrc/conv_blocks.cu when autograd is off (picnet_fast.py); under autograd (training) and in the two encoders
-    they are PyTorch + cuDNN exactly as in the reference.
+  * the spectral-normalised conv / conv-transpose blocks of the decoder and of the two encoders, and the Output block (SURVEY 8f
+    rank 1): in inference one fused whole-network routine on the implicit-GEMM kernels of csrc/conv_blocks.cu (picnet_fast.py);
+    under autograd (training) every wrapped convolution and every InstanceNorm + LeakyReLU pair runs forward AND backward through
+    the per-layer Functions of ops.py (_ConvShared / _ConvTShared / _NormAct, channels_last between them). Only the 3-channel
+    convolutions at the image boundary and anything with TF32 convolutions switched off stay PyTorch + cuDNN as in the reference.
 
 Blocks are assembled from two small helpers instead of one class per variant: `_sn` wraps a conv in SpectralNorm
 (external_function.py:16-72, one power iteration per forward, also in eval) and `_ResidualPair` is "main path + shortcut"

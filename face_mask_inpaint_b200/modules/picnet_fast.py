@@ -14,7 +14,8 @@ final 4x4 average pooling). `encoder_forward` (second half of this file) does th
 
 Used when autograd is off, the tensors are CUDA and TF32 convolutions are allowed (torch.backends.cudnn.allow_tf32, PyTorch's
 default — i.e. whenever the reference itself would run these convolutions with TF32 operands) or FMI_PRECISION=bf16; training
-differentiates the cuDNN formulation of the same blocks (picnet.py), whose backward is not a kernel of this package yet.
+(autograd on) goes layer by layer through the Functions of ops.py instead (forward, data gradient, weight gradient on the same
+kernels; SpectralNorm.forward and the block forwards route there).
 SpectralNorm (external_function.py:44-57) keeps its one power iteration per forward, u and v advanced in place: per conv
 (fmi_conv_weight_prep_sn) on a network's first forward, then for all of its convs at once (`_WeightPlan`,
 fmi_conv_weight_prep_sn_batch).
