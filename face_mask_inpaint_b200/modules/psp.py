@@ -30,6 +30,18 @@ _IR50 = ((64, 64, 3), (64, 128, 4), (128, 256, 14), (256, 512, 3))
 _TAPS = {6: 'c1', 20: 'c2', 23: 'c3'}   # trunk outputs used by the pyramid (psp_encoders.py:103-108)
 
 
+def _trunk_layout(x):
+    """The IR-SE50 trunk under autograd stays cuDNN / ATen (helpers.py:97-119 with BatchNorm batch statistics); fed an NCHW batch,
+    cuDNN's TF32 kernels transpose every activation to NHWC and back (torch.profiler, RefpSp train step: 1 600 launches of its
+    nchwToNhwc / nhwcToNchw kernels = 9.2 of 54 ms of GPU time). A channels_last input keeps the whole trunk — convolutions,
+    BatchNorm, PReLU, pooling, SE — in NHWC. FMI_PSP_CHANNELS_LAST=0 keeps the reference's layout."""
+    import os
+    if x.is_cuda and x.dim() == 4 and torch.is_grad_enabled() and os.environ.get("FMI_PSP_CHANNELS_LAST") != "0":
+        return x.contiguous(memory_format=torch.channels_last)
+    return x
+
+
+
 class _SqueezeExcite(nn.Module):
     """helpers.py:56-74."""
 
@@ -106,7 +118,7 @@ class GradualStyleEncoder(nn.Module):
             self.attention2 = ExampleGuidedAttention(256, out_channels=256)
 
     def _trunk(self, x):
-        x = self.input_layer(x)
+        x = self.input_layer(_trunk_layout(x))
         taps = {}
         for i, unit in enumerate(self.body):
             x = unit(x)

@@ -225,7 +225,8 @@ def _install_compositing_callers():
         taps = {6: None, 20: None, 23: None}
 
         def trunk(t):
-            t = self.input_layer(t)
+            from .modules.psp import _trunk_layout
+            t = self.input_layer(_trunk_layout(t))     # training: the cuDNN trunk in NHWC (no layout kernels around every conv)
             feats = dict(taps)
             for idx, layer in enumerate(self.body._modules.values()):
                 t = layer(t)
